@@ -1,0 +1,251 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product (slam-eds_b200/) never does.
+PARITY UNPINNED: see the header of eds_oracle_tracking.cpp.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libeds_oracle.so")
+_lib = None
+
+REC = 76  # floats per RawResidualJacobian record (304 B)
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (g++ only)."""
+    srcs = [os.path.join(_HERE, f) for f in ("eds_oracle_tracking.cpp", "eds_oracle_ba.cpp", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    return _LIB_PATH
+
+
+class SolverConfig(C.Structure):
+    _fields_ = [("num_blocks", C.c_int), ("loss_type", C.c_int), ("loss_param", C.c_double),
+                ("max_iterations", C.c_int), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("jacobian_mode", C.c_int), ("threads", C.c_int)]
+
+
+class SolverInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("successful_steps", C.c_int), ("unsuccessful_steps", C.c_int),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("usable", C.c_int),
+                ("termination", C.c_int), ("solve_time_us", C.c_double), ("final_radius", C.c_double)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        try:
+            _lib = C.CDLL(_LIB_PATH)
+        except OSError:
+            build(force=True)
+            _lib = C.CDLL(_LIB_PATH)
+        _lib.eds_oracle_mad_tau.restype = C.c_double
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def draw_values(px, py, val, H, W, method="bilinear", use_exp=True, sigma=0.5):
+    px, py = _f64(px), _f64(py)
+    val = np.ascontiguousarray(val, dtype=np.int8)
+    img = np.zeros((H, W), np.float64)
+    rc = lib().eds_oracle_draw_values(_p(px, C.c_double), _p(py, C.c_double), _p(val, C.c_int8), C.c_int(len(px)),
+                                      C.c_int(H), C.c_int(W), C.c_int(0 if method == "nn" else 1), C.c_int(int(use_exp)),
+                                      C.c_double(sigma), _p(img, C.c_double))
+    assert rc == 0
+    return img
+
+
+def event_frame(x, y, pol, ts_us, H, W, mapx=None, mapy=None, method="bilinear", use_exp=True, sigma=0.5):
+    """Returns dict(img, frame, norm, time, delta, status)."""
+    x = np.ascontiguousarray(x, dtype=np.uint16)
+    y = np.ascontiguousarray(y, dtype=np.uint16)
+    pol = np.ascontiguousarray(pol, dtype=np.uint8)
+    ts = np.ascontiguousarray(ts_us, dtype=np.int64) if ts_us is not None else None
+    mx = _f32(mapx) if mapx is not None else None
+    my = _f32(mapy) if mapy is not None else None
+    img = np.zeros((H, W), np.float64)
+    frame = np.zeros((H, W), np.float64)
+    norm = C.c_double(0)
+    t = C.c_int64(0)
+    d = C.c_int64(0)
+    rc = lib().eds_oracle_event_frame(_p(x, C.c_uint16), _p(y, C.c_uint16), _p(pol, C.c_uint8), _p(ts, C.c_int64),
+                                      C.c_int(len(x)), C.c_int(H), C.c_int(W), _p(mx, C.c_float), _p(my, C.c_float),
+                                      C.c_int(0 if method == "nn" else 1), C.c_int(int(use_exp)), C.c_double(sigma),
+                                      _p(img, C.c_double), _p(frame, C.c_double), C.byref(norm), C.byref(t), C.byref(d))
+    return dict(img=img, frame=frame, norm=norm.value, time=t.value, delta=d.value, status=rc)
+
+
+def bicubic(grid, rows, cols):
+    grid = _f64(grid)
+    rows, cols = _f64(rows), _f64(cols)
+    n = len(rows)
+    f, dr, dc = np.zeros(n), np.zeros(n), np.zeros(n)
+    lib().eds_oracle_bicubic(_p(grid, C.c_double), C.c_int(grid.shape[0]), C.c_int(grid.shape[1]), C.c_int(n),
+                             _p(rows, C.c_double), _p(cols, C.c_double), _p(f, C.c_double), _p(dr, C.c_double), _p(dc, C.c_double))
+    return f, dr, dc
+
+
+def _kf_args(kf, frame):
+    g, nc, idp, w = _f64(kf["grad"]), _f64(kf["norm_coord"]), _f64(kf["idp"]), _f64(kf["weights"])
+    fr = _f64(frame)
+    keep = (g, nc, idp, w, fr)
+    args = [C.c_int(len(idp)), _p(g, C.c_double), _p(nc, C.c_double), _p(idp, C.c_double), _p(w, C.c_double),
+            _p(fr, C.c_double), C.c_int(kf["H"]), C.c_int(kf["W"]), C.c_double(kf["fx"]), C.c_double(kf["fy"]),
+            C.c_double(kf["cx"]), C.c_double(kf["cy"])]
+    return args, keep
+
+
+def tracker_evaluate(kf, frame, x, num_blocks, loss_type=1, loss_param=0.05, jacobian_mode=0, want_jac=True):
+    """kf: dict(grad Nx2, norm_coord Nx2, idp N, weights N, H, W, fx, fy, cx, cy). x: 13 = p, q(xyzw), v."""
+    args, keep = _kf_args(kf, frame)
+    N = len(keep[2])
+    x = _f64(x)
+    res = np.zeros(N)
+    jac = np.zeros((N, 12)) if want_jac else None
+    cost = C.c_double(0)
+    Hm, g, bs = np.zeros((12, 12)), np.zeros(12), np.zeros(num_blocks)
+    rc = lib().eds_oracle_tracker_evaluate(*args, C.c_int(num_blocks), C.c_int(loss_type), C.c_double(loss_param),
+                                           C.c_int(jacobian_mode), _p(x, C.c_double), _p(res, C.c_double), _p(jac, C.c_double),
+                                           C.byref(cost), _p(Hm, C.c_double), _p(g, C.c_double), _p(bs, C.c_double))
+    assert rc == 0, rc
+    return dict(residuals=res, jacobian=jac, cost=cost.value, H=Hm, g=g, block_sqnorm=bs)
+
+
+def tracker_solve(kf, frame, x, num_blocks=8, loss_type=1, loss_param=0.05, max_iterations=30, function_tolerance=1e-6,
+                  gradient_tolerance=1e-8, parameter_tolerance=1e-6, jacobian_mode=0, threads=1, want_trace=False):
+    args, keep = _kf_args(kf, frame)
+    N = len(keep[2])
+    x = _f64(x).copy()
+    cfg = SolverConfig(num_blocks, loss_type, loss_param, max_iterations, function_tolerance, gradient_tolerance,
+                       parameter_tolerance, jacobian_mode, threads)
+    info = SolverInfo()
+    res = np.zeros(N)
+    tau = C.c_double(0)
+    trace = np.zeros((max_iterations + 1, 16)) if want_trace else None
+    rc = lib().eds_oracle_tracker_solve(*args, C.byref(cfg), _p(x, C.c_double), _p(res, C.c_double), C.byref(tau),
+                                        C.byref(info), _p(trace, C.c_double))
+    out = dict(status=rc, x=x, residuals=res, next_loss_param=tau.value,
+               info={k: getattr(info, k) for k, _ in SolverInfo._fields_})
+    if want_trace:
+        out["trace"] = trace
+    return out
+
+
+def mad_tau(residuals):
+    r = _f64(residuals).copy()
+    return lib().eds_oracle_mad_tau(_p(r, C.c_double), C.c_int(len(r)))
+
+
+# ----------------------------------------------------------------------------- BA
+def ba_jpjd(recs):
+    recs = _f32(recs)
+    R = recs.shape[0]
+    out = np.zeros((R, 8), np.float32)
+    lib().eds_oracle_ba_jpjd(C.c_int(R), _p(recs, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def ba_fix_linearization(F, recs, host_idx, target_idx, res_begin, deltaF, adHTdeltaF, cDeltaF):
+    recs = _f32(recs)
+    R, P = recs.shape[0], len(res_begin) - 1
+    out = np.zeros((R, 8), np.float32)
+    h, t, rb = _i32(host_idx), _i32(target_idx), _i32(res_begin)
+    d, a, c = _f32(deltaF), _f32(adHTdeltaF), _f32(cDeltaF)
+    lib().eds_oracle_ba_fix_linearization(C.c_int(F), C.c_int(P), C.c_int(R), _p(recs, C.c_float), _p(h, C.c_int32),
+                                          _p(t, C.c_int32), _p(rb, C.c_int32), _p(d, C.c_float), _p(a, C.c_float),
+                                          _p(c, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def ba_top_accumulate(mode, F, recs, host_idx, target_idx, res_begin, flags, res_toZero=None, deltaF=None,
+                      adHTdeltaF=None, cDeltaF=None, threads=1):
+    recs = _f32(recs)
+    R, P = recs.shape[0], len(res_begin) - 1
+    h, t, rb = _i32(host_idx), _i32(target_idx), _i32(res_begin)
+    fl = np.ascontiguousarray(flags, dtype=np.uint8)
+    rtz = _f32(res_toZero) if res_toZero is not None else np.zeros((R, 8), np.float32)
+    d = _f32(deltaF) if deltaF is not None else np.zeros(P, np.float32)
+    a = _f32(adHTdeltaF) if adHTdeltaF is not None else np.zeros((F * F, 8), np.float32)
+    c = _f32(cDeltaF) if cDeltaF is not None else np.zeros(4, np.float32)
+    acc = np.zeros((F * F, 13, 13))
+    num = np.zeros(F * F, np.int64)
+    Hdd, bd, Hcd = np.zeros(P, np.float32), np.zeros(P, np.float32), np.zeros((P, 4), np.float32)
+    nres = C.c_int64(0)
+    rc = lib().eds_oracle_ba_top_accumulate(C.c_int(mode), C.c_int(F), C.c_int(P), C.c_int(R), _p(recs, C.c_float),
+                                            _p(h, C.c_int32), _p(t, C.c_int32), _p(rb, C.c_int32), _p(fl, C.c_uint8),
+                                            _p(rtz, C.c_float), _p(d, C.c_float), _p(a, C.c_float), _p(c, C.c_float),
+                                            C.c_int(threads), _p(acc, C.c_double), _p(num, C.c_int64), _p(Hdd, C.c_float),
+                                            _p(bd, C.c_float), _p(Hcd, C.c_float), C.byref(nres))
+    assert rc == 0
+    return dict(acc=acc, num=num, Hdd=Hdd, bd=bd, Hcd=Hcd, nres=nres.value)
+
+
+def ba_top_stitch(F, acc, adHost, adTarget, use_prior=False, cPrior=None, cDeltaF=None, frame_prior=None,
+                  frame_delta_prior=None):
+    n = 4 + 8 * F
+    acc, ah, at = _f64(acc), _f64(adHost), _f64(adTarget)
+    cp = _f64(cPrior) if cPrior is not None else np.zeros(4)
+    cd = _f32(cDeltaF) if cDeltaF is not None else np.zeros(4, np.float32)
+    fp = _f64(frame_prior) if frame_prior is not None else np.zeros((F, 8))
+    fd = _f64(frame_delta_prior) if frame_delta_prior is not None else np.zeros((F, 8))
+    H = np.zeros((n, n), order="F")
+    b = np.zeros(n)
+    lib().eds_oracle_ba_top_stitch(C.c_int(F), _p(acc, C.c_double), _p(ah, C.c_double), _p(at, C.c_double),
+                                   C.c_int(int(use_prior)), _p(cp, C.c_double), _p(cd, C.c_float), _p(fp, C.c_double),
+                                   _p(fd, C.c_double), _p(H, C.c_double), _p(b, C.c_double))
+    return H, b
+
+
+def ba_sc_accumulate(F, host_idx, target_idx, res_begin, flags, JpJdF, Hdd_A, Hdd_L, bd_A, bd_L, Hcd_A, Hcd_L, priorF,
+                     deltaF, shift_prior_to_zero=True, threads=1):
+    P = len(res_begin) - 1
+    h, t, rb = _i32(host_idx), _i32(target_idx), _i32(res_begin)
+    R = len(h)
+    fl = np.ascontiguousarray(flags, dtype=np.uint8)
+    arrs = [_f32(a) for a in (JpJdF, Hdd_A, Hdd_L, bd_A, bd_L, Hcd_A, Hcd_L, priorF, deltaF)]
+    accD, accE, accEB = np.zeros((F ** 3, 8, 8)), np.zeros((F * F, 8, 4)), np.zeros((F * F, 8))
+    accHcc, accbc = np.zeros((4, 4)), np.zeros(4)
+    HdiF, bdSum = np.zeros(P, np.float32), np.zeros(P, np.float32)
+    rc = lib().eds_oracle_ba_sc_accumulate(C.c_int(F), C.c_int(P), C.c_int(R), _p(h, C.c_int32), _p(t, C.c_int32),
+                                           _p(rb, C.c_int32), _p(fl, C.c_uint8), *[_p(a, C.c_float) for a in arrs],
+                                           C.c_int(int(shift_prior_to_zero)), C.c_int(threads), _p(accD, C.c_double),
+                                           _p(accE, C.c_double), _p(accEB, C.c_double), _p(accHcc, C.c_double),
+                                           _p(accbc, C.c_double), _p(HdiF, C.c_float), _p(bdSum, C.c_float))
+    assert rc == 0
+    return dict(accD=accD, accE=accE, accEB=accEB, accHcc=accHcc, accbc=accbc, HdiF=HdiF, bdSum=bdSum)
+
+
+def ba_sc_stitch(F, sc, adHost, adTarget):
+    n = 4 + 8 * F
+    ah, at = _f64(adHost), _f64(adTarget)
+    H = np.zeros((n, n), order="F")
+    b = np.zeros(n)
+    lib().eds_oracle_ba_sc_stitch(C.c_int(F), _p(_f64(sc["accD"]), C.c_double), _p(_f64(sc["accE"]), C.c_double),
+                                  _p(_f64(sc["accEB"]), C.c_double), _p(_f64(sc["accHcc"]), C.c_double),
+                                  _p(_f64(sc["accbc"]), C.c_double), _p(ah, C.c_double), _p(at, C.c_double),
+                                  _p(H, C.c_double), _p(b, C.c_double))
+    return H, b
