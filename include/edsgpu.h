@@ -1,0 +1,178 @@
+/*
+ * edsgpu.h -- C ABI of the B200-native EDS hot path (libedsgpu.so).
+ *
+ * Drop-in boundary for the two data-parallel paths of uzh-rpg/slam-eds:
+ *   A. event-to-model alignment  (src/tracking: EventFrame::create, Tracker::optimize)
+ *   B. windowed-BA Hessian accumulation (src/bundles: Accumulated{Top,SC}HessianSSE)
+ * The reference has no plugin/FFI layer; its seam is the C++ class surface that the
+ * external Rock task calls.  Each entry point below names the reference
+ * method (file:line, relative to the reference root) whose body it replaces; the
+ * header-only adapters in slam-eds_b200/host/ keep those method names and forward here.
+ *
+ * Conventions
+ *   - plain C types only; every function returns edsgpu_status; no exception crosses.
+ *   - pointers without a _dev suffix are HOST pointers; *_dev entry points take DEVICE
+ *     pointers on the context's device (for callers whose data already lives in HBM).
+ *   - one edsgpu_ctx = one device + one stream; a context is single-threaded.
+ *   - quaternions are (x,y,z,w) like Eigen::Quaterniond::coeffs() (Tracker.hpp:48).
+ *   - there is NO CPU fallback: without a CUDA device edsgpu_create fails.
+ */
+#ifndef EDSGPU_H_
+#define EDSGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    EDSGPU_OK = 0,
+    EDSGPU_INVALID_ARGUMENT = 1,
+    EDSGPU_CUDA_ERROR = 2,
+    EDSGPU_NOT_USABLE = 3,          /* !summary.IsSolutionUsable(), Tracker.cpp:217,237-240 */
+    EDSGPU_NON_MONOTONIC_TIME = 4,  /* EventFrame.cpp:325-329 throws std::runtime_error   */
+    EDSGPU_OUT_OF_MEMORY = 5
+} edsgpu_status;
+
+typedef struct edsgpu_ctx edsgpu_ctx;
+typedef struct edsgpu_lut edsgpu_lut;           /* device copy of EventFrame::fwd_mapx/fwd_mapy */
+typedef struct edsgpu_frames edsgpu_frames;     /* a bank of device event frames (EventFrame::event_frame[0]) */
+typedef struct edsgpu_keyframe edsgpu_keyframe; /* device copy of the KeyFrame arrays the tracker gathers */
+typedef struct edsgpu_tracker edsgpu_tracker;   /* Tracker state: px, qx, vx, loss_params (Tracker.hpp:47-49) */
+
+/* ---- context ------------------------------------------------------------------------- */
+const char* edsgpu_version(void);
+/* stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one. */
+edsgpu_status edsgpu_create(int device, void* stream, edsgpu_ctx** out);
+void edsgpu_destroy(edsgpu_ctx* ctx);
+const char* edsgpu_last_error_string(const edsgpu_ctx* ctx);
+edsgpu_status edsgpu_synchronize(edsgpu_ctx* ctx);
+/* number of kernels this context has launched so far (for gpu_launches accounting) */
+int64_t edsgpu_launch_count(const edsgpu_ctx* ctx);
+
+/* ---- A1. event frame ----------------------------------------------------------------- */
+enum { EDSGPU_DRAW_NN = 0, EDSGPU_DRAW_BILINEAR = 1 };  /* Utils.cpp:73,83 method strings */
+
+/* EventFrame::EventFrame(cam, newcam, ...) builds fwd_mapx/fwd_mapy once (EventFrame.cpp:53-81).
+ * mapx/mapy: H*W float each (CV_32F), row-major.  NULL,NULL = identity map. */
+edsgpu_status edsgpu_lut_create(edsgpu_ctx* ctx, int height, int width, const float* fwd_mapx, const float* fwd_mapy,
+                                edsgpu_lut** out);
+void edsgpu_lut_destroy(edsgpu_lut* lut);
+
+/* capacity event frames of height x width, resident on the device for the tracker. */
+edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int capacity, edsgpu_frames** out);
+void edsgpu_frames_destroy(edsgpu_frames* frames);
+
+/* EventFrame::create (EventFrame.cpp:302-389), pyramid level 0, out_scale 1:
+ *   undistort via LUT (:313-323), drawValuesPoints (Utils.cpp:50-122) with `mode`,
+ *   exp time weights if use_exp_weights (Utils.hpp:542-546), 3x3 Gaussian of `sigma`
+ *   if sigma > 0 (Utils.cpp:113-119), L2 norm (:360-364), normalise (:367-383).
+ * The reference call is (BILINEAR, use_exp_weights=1, sigma=0.5) (EventFrame.cpp:339).
+ * The frame stays on the device in `slot`; norm_out / time / delta / host_frame_out
+ * (H*W doubles, normalised) are optional.  ts_us may be NULL (no time outputs, no check). */
+edsgpu_status edsgpu_event_frame_create(edsgpu_ctx* ctx, edsgpu_frames* frames, int slot, const edsgpu_lut* lut,
+                                        const uint16_t* x, const uint16_t* y, const uint8_t* polarity, const int64_t* ts_us,
+                                        int num_events, int mode, int use_exp_weights, float sigma, double* norm_out,
+                                        int64_t* time_us_out, int64_t* delta_time_us_out, double* host_frame_out);
+
+/* `count` windows of num_events events each, into slots first_slot.. (x,y,polarity are
+ * count*num_events long).  norms_out: count doubles or NULL.  Asynchronous if norms_out is NULL. */
+edsgpu_status edsgpu_event_frame_create_batch(edsgpu_ctx* ctx, edsgpu_frames* frames, int first_slot, int count,
+                                              const edsgpu_lut* lut, const uint16_t* x, const uint16_t* y,
+                                              const uint8_t* polarity, int num_events, int mode, int use_exp_weights,
+                                              float sigma, double* norms_out);
+/* same, events already in device memory; always asynchronous on the context stream. */
+edsgpu_status edsgpu_event_frame_create_batch_dev(edsgpu_ctx* ctx, edsgpu_frames* frames, int first_slot, int count,
+                                                  const edsgpu_lut* lut, const uint16_t* x_dev, const uint16_t* y_dev,
+                                                  const uint8_t* polarity_dev, int num_events, int mode,
+                                                  int use_exp_weights, float sigma);
+/* debug/parity: the un-normalised (blurred) image of a slot as doubles, and the raw
+ * fixed-point accumulator (value * 2^40) before the blur. */
+edsgpu_status edsgpu_frames_read(edsgpu_ctx* ctx, const edsgpu_frames* frames, int slot, double* image_out /*H*W*/,
+                                 double* norm_out);
+edsgpu_status edsgpu_frames_read_accumulator(edsgpu_ctx* ctx, const edsgpu_frames* frames, int slot, int64_t* acc_out /*H*W*/);
+#define EDSGPU_ACC_FRACTION_BITS 40
+
+/* ---- A2. tracker ----------------------------------------------------------------------- */
+enum { EDSGPU_LOSS_NONE = 0, EDSGPU_LOSS_HUBER = 1, EDSGPU_LOSS_CAUCHY = 2 };     /* Tracker.cpp:146-161 */
+enum { EDSGPU_LOSS_PARAM_CONSTANT = 0, EDSGPU_LOSS_PARAM_MAD = 1, EDSGPU_LOSS_PARAM_STD = 2 }; /* Tracker.hpp:34 */
+enum { EDSGPU_TERM_CONVERGENCE = 0, EDSGPU_TERM_NO_CONVERGENCE = 1, EDSGPU_TERM_FAILURE = 2 };
+
+typedef struct {
+    int num_blocks;              /* config.options.num_threads: residual blocks (Tracker.cpp:138,178-195).
+                                    NUMERICAL parameter: model norm and loss are per block.            */
+    int loss_type;               /* config.loss_type                                                   */
+    int max_iterations;          /* config.options.max_num_iterations[id] (Tracker.cpp:139)            */
+    int loss_param_method;       /* LOSS_PARAM_METHOD argument of optimize (Tracker.hpp:80-81)         */
+    double function_tolerance;   /* config.options.function_tolerance (Tracker.cpp:140)                */
+    double gradient_tolerance;   /* 1e-8  (Tracker.cpp:142)                                            */
+    double parameter_tolerance;  /* 1e-6  (Tracker.cpp:143)                                            */
+} edsgpu_tracker_config;
+
+typedef struct {                 /* eds::tracking::TrackerInfo (tracking/Config.hpp:60-68) + solver summary */
+    int iterations;              /* successful + unsuccessful steps (Tracker.cpp:211) */
+    int successful_steps;
+    int unsuccessful_steps;
+    int termination;             /* EDSGPU_TERM_* */
+    int usable;                  /* summary.IsSolutionUsable() (Tracker.cpp:213) */
+    int num_points;
+    double initial_cost;
+    double final_cost;
+    double final_radius;
+} edsgpu_tracker_info;
+
+/* KeyFrame arrays gathered by PhotometricError (PhotometricError.hpp:58-112, KeyFrame.hpp:59-96):
+ * grad_xy, norm_xy: N x 2 interleaved (std::vector<cv::Point2d>), idp (DepthPoints::getIDepth,
+ * Tracker.cpp:167), weights: N.  Intrinsics from kf->K_ref (Tracker.cpp:164-166), size from kf->img.
+ * num_blocks fixes the residual-block partition (Tracker.cpp:178-190). */
+edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const double* grad_xy, const double* norm_xy,
+                                     const double* idp, const double* weights, int height, int width, double fx, double fy,
+                                     double cx, double cy, int num_blocks, edsgpu_keyframe** out);
+void edsgpu_keyframe_destroy(edsgpu_keyframe* kf);
+
+/* Tracker::Tracker(config) (Tracker.cpp:41-48): px=0, qx=identity, vx=normalize(1e-3*ones),
+ * loss parameter = loss_param (config.loss_params[0]). */
+edsgpu_status edsgpu_tracker_create(edsgpu_ctx* ctx, const edsgpu_tracker_config* config, double loss_param,
+                                    edsgpu_tracker** out);
+void edsgpu_tracker_destroy(edsgpu_tracker* tracker);
+/* Tracker::reset(kf, px, qx, velo) / set(T) (Tracker.cpp:50-82): any of px,qx,vx may be NULL (kept). */
+edsgpu_status edsgpu_tracker_set_state(edsgpu_tracker* tracker, const double px[3], const double qx_xyzw[4],
+                                       const double vx[6], const double* loss_param);
+/* Tracker::getTransform / getVelocity / getLossParams: synchronises the stream. */
+edsgpu_status edsgpu_tracker_get_state(edsgpu_tracker* tracker, double px[3], double qx_xyzw[4], double vx[6],
+                                       double* loss_param, edsgpu_tracker_info* info);
+
+/* bool Tracker::optimize(id, event_frame, T_kf_ef, loss_param_method) (Tracker.cpp:104-241):
+ * LM on 0.5*sum_b rho(||r_b||^2) from the tracker's current state, write-back of px,qx,vx
+ * when usable, residuals (no loss) and the next loss parameter (MAD, Tracker.cpp:223-233).
+ * residuals_out: N doubles or NULL.  Returns EDSGPU_NOT_USABLE when optimize() would return false. */
+edsgpu_status edsgpu_tracker_optimize(edsgpu_tracker* tracker, const edsgpu_keyframe* kf, const edsgpu_frames* frames,
+                                      int slot, double px[3], double qx_xyzw[4], double vx[6], double* residuals_out,
+                                      double* next_loss_param_out, edsgpu_tracker_info* info);
+
+/* `count` independent trackers (sequences), tracker i against keyframe i and frame slot
+ * first_slot+i, in one launch.  Asynchronous; read results with edsgpu_tracker_get_state
+ * or edsgpu_trackers_gather. */
+edsgpu_status edsgpu_trackers_optimize_batch(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers,
+                                             const edsgpu_keyframe* const* keyframes, int count, const edsgpu_frames* frames,
+                                             int first_slot);
+/* states_out: count x 14 doubles [px(3) qx(4) vx(6) loss_param]; infos_out optional. Synchronises. */
+edsgpu_status edsgpu_trackers_gather(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, int count, double* states_out,
+                                     edsgpu_tracker_info* infos_out);
+/* device address of tracker i's 14-double state record (for NCCL gathers by the caller) */
+void* edsgpu_tracker_state_dev(edsgpu_tracker* tracker);
+
+/* ceres::CostFunction::Evaluate as used at Tracker.cpp:228-229, plus the tangent-space
+ * Jacobian: residuals (no loss) N, jacobian N x 12 row-major [t(3) theta(3) v(6)] (may be NULL),
+ * robustified cost 0.5*sum_b rho(||r_b||^2), and the reduced normal equations (may be NULL):
+ * H 12x12 row-major = sum_b rho'_b J_b^T J_b, g 12 = sum_b rho'_b J_b^T r_b. */
+edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot,
+                                      int loss_type, double loss_param, const double px[3], const double qx_xyzw[4],
+                                      const double vx[6], double* residuals_out, double* jacobian_out, double* cost_out,
+                                      double* H_out, double* g_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDSGPU_H_ */

@@ -1,0 +1,439 @@
+// Event window -> brightness-increment event frame on the device.
+//
+// Replaces EventFrame::create (reference src/tracking/EventFrame.cpp:302-389) and
+// utils::drawValuesPoints (src/utils/Utils.cpp:50-122) for pyramid level 0:
+//   k1  scatter_events_kernel   LUT gather + bilinear/nn vote x exp time weight, accumulated
+//                               with warp-aggregated 64-bit fixed-point atomics (value * 2^40):
+//                               deterministic, exact for the integer (nn, unweighted) mode,
+//                               2^-41 absolute quantisation otherwise.
+//   k2  blur_norm_kernel        3x3 separable Gaussian (BORDER_REFLECT_101) in fp64 through a
+//                               shared-memory tile, fp32 frame out, fused sum of squares;
+//                               the last CTA of each frame reduces the per-tile partials in a
+//                               fixed order and publishes norm and 1/norm.
+// The frame is stored un-normalised in fp32; consumers multiply by 1/norm when sampling.
+#include "common.cuh"
+#include "frames.cuh"
+
+namespace {
+
+constexpr double kQ = 1099511627776.0;  // 2^40
+constexpr int TILE_W = 64, TILE_H = 16, BLUR_THREADS = 256;
+
+// Utils.hpp:542-546 with idx = i / E, window_size = 1 (Utils.cpp:72).
+__device__ __forceinline__ double exp_weight(int i, int E) {
+    double value = ((double)i / (double)(unsigned)E - 0.5) / (1.0 / 6.0);
+    return exp(-0.5 * value * value);
+}
+
+// One 64-bit atomic per distinct key in the warp: lanes with equal `key` are merged.
+// `val` is the fixed-point vote; `scaled` optional extra per-corner weights are applied by
+// the caller (all lanes of a group share them, see scatter_events_kernel).
+__device__ __forceinline__ long long warp_aggregate(unsigned active, unsigned key, long long val, bool* is_leader) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned peers = __match_any_sync(active, key);
+    int leader = __ffs(peers) - 1;
+    *is_leader = ((int)lane == leader);
+    bool multi = __any_sync(active, __popc(peers) > 1);
+    if (!multi) return val;
+    long long sum = 0;
+    for (int src = 0; src < 32; ++src) {
+        long long o = __shfl_sync(active, val, src);
+        if ((peers >> src) & 1u) sum += o;
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(256) scatter_events_kernel(const uint16_t* __restrict__ ex, const uint16_t* __restrict__ ey,
+                                                             const uint8_t* __restrict__ epol, int E, int H, int W,
+                                                             const float* __restrict__ mapx, const float* __restrict__ mapy,
+                                                             int mode, int use_exp, long long* __restrict__ acc) {
+    const int win = blockIdx.y;
+    const size_t ebase = (size_t)win * E;
+    long long* img = acc + (size_t)win * H * W;
+    const int stride = gridDim.x * blockDim.x;
+    // warp-uniform trip count so that every lane reaches the warp collectives
+    const int first = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iters = (E + stride - 1) / stride;
+    for (int it = 0; it < iters; ++it) {
+        const int i = first + it * stride;
+        const bool live = i < E;
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (!live) continue;
+        const int x = ex[ebase + i], y = ey[ebase + i];
+        const bool inside = (x < W) && (y < H);
+        const double pol = epol[ebase + i] ? 1.0 : -1.0;  // EventFrame.cpp:318
+        const double wt = use_exp ? exp_weight(i, E) : 1.0;
+        double ux = x, uy = y;
+        if (mapx != nullptr && inside) {  // EventFrame.cpp:316-317
+            ux = (double)mapx[(size_t)y * W + x];
+            uy = (double)mapy[(size_t)y * W + x];
+        }
+        // events from the same raw pixel share coordinates, hence all weights: merge them
+        const unsigned key = inside ? (unsigned)(y * W + x) : 0xffffffffu;
+        bool leader;
+        if (mode == EDSGPU_DRAW_NN) {
+            // cv::Point2i(Point2d) rounds half to even (cvRound), then clip: Utils.cpp:75-78
+            int xi = __double2int_rn(ux), yi = __double2int_rn(uy);
+            xi = max(0, min(xi, W - 1));
+            yi = max(0, min(yi, H - 1));
+            long long v = inside ? __double2ll_rn(wt * pol * kQ) : 0;
+            v = warp_aggregate(active, key, v, &leader);
+            if (leader && inside && v != 0) atomicAdd((unsigned long long*)&img[(size_t)yi * W + xi], (unsigned long long)v);
+        } else {
+            // Utils.cpp:85-106
+            const double fx0 = floor(ux), fy0 = floor(uy);
+            int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+            const double ax = ux - fx0, ay = uy - fy0;  // == ux - x0, exact
+            const double bx = (double)x1 - ux, by = (double)y1 - uy;
+            const bool x0in = x0 >= 0 && x0 < W, x1in = x1 >= 0 && x1 < W;
+            const bool y0in = y0 >= 0 && y0 < H, y1in = y1 >= 0 && y1 < H;
+            const double wa = (x0in && y0in) ? bx * by : 0.0;
+            const double wb = (x0in && y1in) ? bx * ay : 0.0;
+            const double wc = (x1in && y0in) ? ax * by : 0.0;
+            const double wd = (x1in && y1in) ? ax * ay : 0.0;
+            x0 = max(0, min(x0, W - 1)); x1 = max(0, min(x1, W - 1));
+            y0 = max(0, min(y0, H - 1)); y1 = max(0, min(y1, H - 1));
+            // merge the time-weight * polarity of same-pixel events, then apply the 4 corner weights
+            const double s = inside ? wt * pol : 0.0;
+            unsigned peers = __match_any_sync(active, key);
+            leader = ((int)(threadIdx.x & 31) == __ffs(peers) - 1);
+            double sum = s;
+            if (__any_sync(active, __popc(peers) > 1)) {
+                sum = 0.0;
+                for (int src = 0; src < 32; ++src) {
+                    double o = __shfl_sync(active, s, src);
+                    if ((peers >> src) & 1u) sum += o;
+                }
+            }
+            if (leader && inside) {
+                long long va = __double2ll_rn(sum * wa * kQ), vb = __double2ll_rn(sum * wb * kQ);
+                long long vc = __double2ll_rn(sum * wc * kQ), vd = __double2ll_rn(sum * wd * kQ);
+                if (va) atomicAdd((unsigned long long*)&img[(size_t)y0 * W + x0], (unsigned long long)va);
+                if (vb) atomicAdd((unsigned long long*)&img[(size_t)y1 * W + x0], (unsigned long long)vb);
+                if (vc) atomicAdd((unsigned long long*)&img[(size_t)y0 * W + x1], (unsigned long long)vc);
+                if (vd) atomicAdd((unsigned long long*)&img[(size_t)y1 * W + x1], (unsigned long long)vd);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    if (i < 0) return -i;
+    if (i >= n) return 2 * n - 2 - i;
+    return i;
+}
+
+// OUT64 == false: write the fp32 frame + per-tile sum of squares, last CTA publishes norm.
+// OUT64 == true : write out64 = blurred * scale (debug / host read-back path).
+template <bool OUT64>
+__global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long* __restrict__ acc, int H, int W, double k0, double k1,
+                                                                 float* __restrict__ frame, double* __restrict__ partials,
+                                                                 unsigned* __restrict__ tickets, double* __restrict__ norms,
+                                                                 int first_slot, double* __restrict__ out64,
+                                                                 const double* __restrict__ scale_ptr) {
+    __shared__ double src[TILE_H + 2][TILE_W + 2];
+    __shared__ double tmp[TILE_H + 2][TILE_W];
+    __shared__ double wsum[BLUR_THREADS / 32];
+    __shared__ bool is_last;
+    const int win = blockIdx.z;
+    const int slot = first_slot + win;
+    const long long* img = acc + (size_t)slot * H * W;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (TILE_H + 2) * (TILE_W + 2); i += BLUR_THREADS) {
+        int ly = i / (TILE_W + 2), lx = i % (TILE_W + 2);
+        int gy = reflect101(min(y0 + ly - 1, H), H), gx = reflect101(min(x0 + lx - 1, W), W);
+        // min(.., H): tiles hanging over the border may index one past the reflection range
+        gy = max(0, min(gy, H - 1));
+        gx = max(0, min(gx, W - 1));
+        src[ly][lx] = (double)img[(size_t)gy * W + gx] * (1.0 / kQ);
+    }
+    __syncthreads();
+    // row pass, generic cv::RowFilter order: left, centre, right (Utils.cpp:118)
+    for (int i = tid; i < (TILE_H + 2) * TILE_W; i += BLUR_THREADS) {
+        int ly = i / TILE_W, lx = i % TILE_W;
+        double v = __dadd_rn(__dadd_rn(__dmul_rn(src[ly][lx], k0), __dmul_rn(src[ly][lx + 1], k1)), __dmul_rn(src[ly][lx + 2], k0));
+        tmp[ly][lx] = v;
+    }
+    __syncthreads();
+    double sq = 0.0;
+    const double scale = OUT64 ? (scale_ptr ? scale_ptr[2 * slot + 1] : 1.0) : 1.0;
+    for (int i = tid; i < TILE_H * TILE_W; i += BLUR_THREADS) {
+        int ly = i / TILE_W, lx = i % TILE_W;
+        int gy = y0 + ly, gx = x0 + lx;
+        if (gy < H && gx < W) {
+            // cv::SymmColumnFilter order: centre, then k*(up+down)
+            double v = __dadd_rn(__dmul_rn(k1, tmp[ly + 1][lx]), __dmul_rn(k0, __dadd_rn(tmp[ly][lx], tmp[ly + 2][lx])));
+            if (OUT64) {
+                out64[(size_t)win * H * W + (size_t)gy * W + gx] = v * scale;
+            } else {
+                frame[(size_t)slot * H * W + (size_t)gy * W + gx] = (float)v;
+                sq += v * v;
+            }
+        }
+    }
+    if constexpr (OUT64) return;
+    // fused sum of squares (cv::norm L2, EventFrame.cpp:360-364): warp -> CTA -> ordered final pass
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((tid & 31) == 0) wsum[tid >> 5] = sq;
+    __syncthreads();
+    const int ntiles = gridDim.x * gridDim.y;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < BLUR_THREADS / 32; ++w) s += wsum[w];
+        partials[(size_t)win * ntiles + tile] = s;
+        __threadfence();
+        unsigned t = atomicAdd(&tickets[win], 1u);
+        is_last = (t == (unsigned)ntiles - 1);
+    }
+    __syncthreads();
+    if (is_last && tid < 32) {
+        __threadfence();
+        const volatile double* p = partials + (size_t)win * ntiles;
+        double s = 0.0;
+        for (int i = tid; i < ntiles; i += 32) s += p[i];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) {
+            double nrm = sqrt(s);
+            norms[2 * slot] = nrm;
+            norms[2 * slot + 1] = 1.0 / nrm;
+            tickets[win] = 0;
+        }
+    }
+}
+
+edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, int count, const edsgpu_lut* lut,
+                            const uint16_t* x_dev, const uint16_t* y_dev, const uint8_t* pol_dev, int E, int mode, int use_exp, float sigma) {
+    const int H = fr->H, W = fr->W;
+    const size_t npix = (size_t)H * W;
+    EDS_CUDA(ctx, cudaMemsetAsync(fr->acc + (size_t)first_slot * npix, 0, sizeof(long long) * npix * count, ctx->stream));
+    {
+        int threads = 256;
+        int bx = (E + threads - 1) / threads;
+        bx = max(1, min(bx, 4 * ctx->num_sms));
+        dim3 grid(bx, count);
+        scatter_events_kernel<<<grid, threads, 0, ctx->stream>>>(x_dev, y_dev, pol_dev, E, H, W, lut ? lut->mapx : nullptr,
+                                                                  lut ? lut->mapy : nullptr, mode, use_exp,
+                                                                  fr->acc + (size_t)first_slot * npix);
+        ctx->launches++;
+        EDS_CUDA(ctx, cudaGetLastError());
+    }
+    {
+        double k0 = 0.0, k1 = 1.0;
+        if (sigma > 0.f) {  // cv::getGaussianKernel(3, sigma), Utils.cpp:113-119
+            double s = (double)sigma;
+            k0 = exp(-1.0 / (2.0 * s * s));
+            double sum = k0 + 1.0 + k0;
+            k0 /= sum;
+            k1 = 1.0 / sum;
+        }
+        dim3 grid((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, count);
+        blur_norm_kernel<false><<<grid, BLUR_THREADS, 0, ctx->stream>>>(fr->acc, H, W, k0, k1, fr->frame, fr->partials, fr->tickets,
+                                                                         fr->norms, first_slot, nullptr, nullptr);
+        ctx->launches++;
+        EDS_CUDA(ctx, cudaGetLastError());
+        fr->k0 = k0;
+        fr->k1 = k1;
+    }
+    return EDSGPU_OK;
+}
+
+// blurred image of one slot as doubles (scaled by 1/norm if normalised) into ctx scratch, then to host
+edsgpu_status read_image64(edsgpu_ctx* ctx, const edsgpu_frames* fr, int slot, bool normalised, double* host_out) {
+    const int H = fr->H, W = fr->W;
+    const size_t npix = (size_t)H * W;
+    edsgpu_status st = edsgpu_ensure_scratch(ctx, npix * sizeof(double));
+    if (st != EDSGPU_OK) return st;
+    dim3 grid((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, 1);
+    blur_norm_kernel<true><<<grid, BLUR_THREADS, 0, ctx->stream>>>(fr->acc, H, W, fr->k0, fr->k1, nullptr, nullptr, nullptr, nullptr, slot,
+                                                                    (double*)ctx->scratch, normalised ? fr->norms : nullptr);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    EDS_CUDA(ctx, cudaMemcpyAsync(host_out, ctx->scratch, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+edsgpu_status edsgpu_lut_create(edsgpu_ctx* ctx, int height, int width, const float* fwd_mapx, const float* fwd_mapy, edsgpu_lut** out) {
+    if (!ctx || !out) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, height > 0 && width > 0, "lut_create: bad size");
+    EDS_REQUIRE(ctx, (fwd_mapx == nullptr) == (fwd_mapy == nullptr), "lut_create: give both maps or neither");
+    DeviceGuard g(ctx->device);
+    edsgpu_lut* lut = new edsgpu_lut();
+    lut->ctx = ctx; lut->H = height; lut->W = width;
+    if (fwd_mapx) {
+        size_t bytes = sizeof(float) * (size_t)height * width;
+        cudaError_t e = cudaMalloc(&lut->mapx, bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&lut->mapy, bytes);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(lut->mapx, fwd_mapx, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(lut->mapy, fwd_mapy, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { edsgpu_lut_destroy(lut); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
+    }
+    *out = lut;
+    return EDSGPU_OK;
+}
+
+void edsgpu_lut_destroy(edsgpu_lut* lut) {
+    if (!lut) return;
+    DeviceGuard g(lut->ctx->device);
+    if (lut->mapx) cudaFree(lut->mapx);
+    if (lut->mapy) cudaFree(lut->mapy);
+    delete lut;
+}
+
+edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int capacity, edsgpu_frames** out) {
+    if (!ctx || !out) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, height > 0 && width > 0 && capacity > 0, "frames_create: bad size");
+    EDS_REQUIRE(ctx, (size_t)height * width < (1ull << 31), "frames_create: image too large");
+    DeviceGuard g(ctx->device);
+    edsgpu_frames* fr = new edsgpu_frames();
+    fr->ctx = ctx; fr->H = height; fr->W = width; fr->capacity = capacity;
+    const size_t npix = (size_t)height * width;
+    const int ntiles = ((width + TILE_W - 1) / TILE_W) * ((height + TILE_H - 1) / TILE_H);
+    cudaError_t e = cudaMalloc(&fr->acc, sizeof(long long) * npix * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&fr->frame, sizeof(float) * npix * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&fr->partials, sizeof(double) * (size_t)ntiles * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&fr->tickets, sizeof(unsigned) * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&fr->norms, sizeof(double) * 2 * capacity);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fr->tickets, 0, sizeof(unsigned) * capacity, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fr->norms, 0, sizeof(double) * 2 * capacity, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fr->acc, 0, sizeof(long long) * npix * capacity, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fr->frame, 0, sizeof(float) * npix * capacity, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        edsgpu_frames_destroy(fr);
+        return edsgpu_fail(ctx, e == cudaErrorMemoryAllocation ? EDSGPU_OUT_OF_MEMORY : EDSGPU_CUDA_ERROR, cudaGetErrorString(e));
+    }
+    *out = fr;
+    return EDSGPU_OK;
+}
+
+void edsgpu_frames_destroy(edsgpu_frames* fr) {
+    if (!fr) return;
+    DeviceGuard g(fr->ctx->device);
+    cudaStreamSynchronize(fr->ctx->stream);
+    if (fr->acc) cudaFree(fr->acc);
+    if (fr->frame) cudaFree(fr->frame);
+    if (fr->partials) cudaFree(fr->partials);
+    if (fr->tickets) cudaFree(fr->tickets);
+    if (fr->norms) cudaFree(fr->norms);
+    if (fr->events_dev) cudaFree(fr->events_dev);
+    delete fr;
+}
+
+static edsgpu_status check_batch_args(edsgpu_ctx* ctx, edsgpu_frames* frames, int first_slot, int count, const edsgpu_lut* lut,
+                                      int num_events, int mode) {
+    EDS_REQUIRE(ctx, frames != nullptr && frames->ctx == ctx, "event_frame: frames belong to another context");
+    EDS_REQUIRE(ctx, count > 0 && first_slot >= 0 && first_slot + count <= frames->capacity, "event_frame: slot range out of bounds");
+    EDS_REQUIRE(ctx, num_events > 0, "event_frame: num_events must be positive");
+    EDS_REQUIRE(ctx, mode == EDSGPU_DRAW_NN || mode == EDSGPU_DRAW_BILINEAR, "event_frame: unknown mode");
+    EDS_REQUIRE(ctx, !lut || (lut->H == frames->H && lut->W == frames->W), "event_frame: LUT size mismatch");
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_event_frame_create_batch_dev(edsgpu_ctx* ctx, edsgpu_frames* frames, int first_slot, int count, const edsgpu_lut* lut,
+                                                  const uint16_t* x_dev, const uint16_t* y_dev, const uint8_t* polarity_dev, int num_events,
+                                                  int mode, int use_exp_weights, float sigma) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_status st = check_batch_args(ctx, frames, first_slot, count, lut, num_events, mode);
+    if (st != EDSGPU_OK) return st;
+    EDS_REQUIRE(ctx, x_dev && y_dev && polarity_dev, "event_frame: null event arrays");
+    DeviceGuard g(ctx->device);
+    return launch_frames(ctx, frames, first_slot, count, lut, x_dev, y_dev, polarity_dev, num_events, mode, use_exp_weights, sigma);
+}
+
+edsgpu_status edsgpu_event_frame_create_batch(edsgpu_ctx* ctx, edsgpu_frames* frames, int first_slot, int count, const edsgpu_lut* lut,
+                                              const uint16_t* x, const uint16_t* y, const uint8_t* polarity, int num_events, int mode,
+                                              int use_exp_weights, float sigma, double* norms_out) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_status st = check_batch_args(ctx, frames, first_slot, count, lut, num_events, mode);
+    if (st != EDSGPU_OK) return st;
+    EDS_REQUIRE(ctx, x && y && polarity, "event_frame: null event arrays");
+    DeviceGuard g(ctx->device);
+    // device staging for the events: [x u16 | y u16 | pol u8] per batch
+    const size_t n = (size_t)count * num_events;
+    const size_t off_y = align_up(n * 2, 256), off_p = off_y + align_up(n * 2, 256), total = off_p + align_up(n, 256);
+    if (frames->events_bytes < total) {
+        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (frames->events_dev) cudaFree(frames->events_dev);
+        frames->events_dev = nullptr;
+        frames->events_bytes = 0;
+        EDS_CUDA(ctx, cudaMalloc(&frames->events_dev, total));
+        frames->events_bytes = total;
+    }
+    char* d = (char*)frames->events_dev;
+    // the caller's buffers are used directly as the copy source (pinned or pageable)
+    EDS_CUDA(ctx, cudaMemcpyAsync(d, x, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    EDS_CUDA(ctx, cudaMemcpyAsync(d + off_y, y, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    EDS_CUDA(ctx, cudaMemcpyAsync(d + off_p, polarity, n, cudaMemcpyHostToDevice, ctx->stream));
+    st = launch_frames(ctx, frames, first_slot, count, lut, (const uint16_t*)d, (const uint16_t*)(d + off_y), (const uint8_t*)(d + off_p),
+                       num_events, mode, use_exp_weights, sigma);
+    if (st != EDSGPU_OK) return st;
+    if (norms_out) {
+        st = edsgpu_ensure_pinned(ctx, sizeof(double) * 2 * count);
+        if (st != EDSGPU_OK) return st;
+        EDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, frames->norms + 2 * first_slot, sizeof(double) * 2 * count, cudaMemcpyDeviceToHost, ctx->stream));
+        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < count; ++i) norms_out[i] = ((double*)ctx->pinned)[2 * i];
+    }
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_event_frame_create(edsgpu_ctx* ctx, edsgpu_frames* frames, int slot, const edsgpu_lut* lut, const uint16_t* x,
+                                        const uint16_t* y, const uint8_t* polarity, const int64_t* ts_us, int num_events, int mode,
+                                        int use_exp_weights, float sigma, double* norm_out, int64_t* time_us_out, int64_t* delta_time_us_out,
+                                        double* host_frame_out) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, num_events > 0, "event_frame: num_events must be positive");
+    if (ts_us) {
+        // EventFrame.cpp:319-336: first/last/middle timestamps, throw if first > last
+        int64_t first = ts_us[0], last = ts_us[num_events - 1];
+        if (first > last) return edsgpu_fail(ctx, EDSGPU_NON_MONOTONIC_TIME, "[EVENT_FRAME] event time[0] > event time[N-1]");
+        if (time_us_out) *time_us_out = ts_us[num_events / 2];
+        if (delta_time_us_out) *delta_time_us_out = last - first;
+    }
+    double nrm = 0.0;
+    edsgpu_status st = edsgpu_event_frame_create_batch(ctx, frames, slot, 1, lut, x, y, polarity, num_events, mode, use_exp_weights, sigma,
+                                                       (norm_out || host_frame_out) ? &nrm : nullptr);
+    if (st != EDSGPU_OK) return st;
+    if (norm_out) *norm_out = nrm;
+    if (host_frame_out) {
+        DeviceGuard g(ctx->device);
+        return read_image64(ctx, frames, slot, true, host_frame_out);
+    }
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_frames_read(edsgpu_ctx* ctx, const edsgpu_frames* frames, int slot, double* image_out, double* norm_out) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, frames && slot >= 0 && slot < frames->capacity, "frames_read: bad slot");
+    DeviceGuard g(ctx->device);
+    if (image_out) {
+        edsgpu_status st = read_image64(ctx, frames, slot, false, image_out);
+        if (st != EDSGPU_OK) return st;
+    }
+    if (norm_out) {
+        EDS_CUDA(ctx, cudaMemcpyAsync(norm_out, frames->norms + 2 * slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_frames_read_accumulator(edsgpu_ctx* ctx, const edsgpu_frames* frames, int slot, int64_t* acc_out) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, frames && acc_out && slot >= 0 && slot < frames->capacity, "frames_read_accumulator: bad arguments");
+    DeviceGuard g(ctx->device);
+    const size_t npix = (size_t)frames->H * frames->W;
+    EDS_CUDA(ctx, cudaMemcpyAsync(acc_out, frames->acc + (size_t)slot * npix, sizeof(int64_t) * npix, cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,23 @@
+// Device-resident objects shared between event_frame.cu and tracker.cu.
+#pragma once
+#include "common.cuh"
+
+struct edsgpu_lut {
+    edsgpu_ctx* ctx = nullptr;
+    int H = 0, W = 0;
+    float* mapx = nullptr;  // nullptr = identity
+    float* mapy = nullptr;
+};
+
+struct edsgpu_frames {
+    edsgpu_ctx* ctx = nullptr;
+    int H = 0, W = 0, capacity = 0;
+    long long* acc = nullptr;     // [capacity][H*W] fixed-point (2^-40) brightness increments
+    float* frame = nullptr;       // [capacity][H*W] blurred, un-normalised
+    double* partials = nullptr;   // [capacity][ntiles] per-tile sum of squares
+    unsigned* tickets = nullptr;  // [capacity] last-CTA election
+    double* norms = nullptr;      // [capacity][2] = {norm, 1/norm}
+    double k0 = 0.0, k1 = 1.0;    // Gaussian taps of the last create (for read-back)
+    void* events_dev = nullptr;   // staging for host-facing create
+    size_t events_bytes = 0;
+};

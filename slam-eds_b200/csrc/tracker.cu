@@ -1,0 +1,1088 @@
+// Event-to-model alignment on the device.
+//
+// Replaces Tracker::optimize (reference src/tracking/Tracker.cpp:104-241), the Ceres cost
+// functor PhotometricError (src/tracking/PhotometricError.hpp:56-214) and ceres::Solve
+// (un-vendored; trust-region LM restated from ceres-solver 1.14..2.1 semantics).
+//
+//   track_lm_kernel   one thread-block CLUSTER per tracking problem.  Residual blocks
+//                     (Tracker.cpp:178-195) are dealt round-robin to the CTAs of the cluster;
+//                     each CTA sweeps its points (fp64 warp/projection, fp32 bicubic + analytic
+//                     Jacobian, 90 fp32 outer-product accumulators per thread), reduces them with
+//                     a halving warp butterfly + fp64 cross-warp sum, applies the per-block loss
+//                     (rho') and stores its 91 doubles into the leader CTA's shared memory over
+//                     DSMEM.  The leader runs the whole Levenberg-Marquardt state machine
+//                     (Jacobi scaling, damping, 12x12 Cholesky, retractions, accept/reject,
+//                     tolerances) and publishes the next evaluation point to the cluster.  The LM
+//                     loop never returns to the host: one launch per batch of windows.
+//   mad_kernel        next loss parameter (MAD / STD) from the written-back residuals
+//                     (Tracker.cpp:281-317) by radix select.
+//   kf_prepare_kernel keyframe upload: fp32 SoA gather streams, fp64 3-D points
+//                     (PhotometricError.hpp:94-105) and the per-block 6x6 model Gram matrix
+//                     A_b = sum g_i g_i^T (m_i = g_i . v is linear in v, so
+//                     ||m||^2 = v^T A_b v and sum m_i g_i = A_b v need no sweep).
+#include <cooperative_groups.h>
+#include <float.h>
+
+#include "common.cuh"
+#include "frames.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int TRK_THREADS = 256;
+constexpr int TRK_WARPS = TRK_THREADS / 32;
+constexpr int NACC = 96;        // 78 (upper triangle of J^T J) + 12 (J^T r) + 6 padding
+constexpr int NSLOT = 92;       // 78 + 12 + cost + block squared norm
+constexpr int MAX_BLOCKS = 32;  // residual blocks per problem (config.options.num_threads)
+constexpr int MAX_CLUSTER = 8;
+constexpr double kEps = 1e-05;  // PhotometricError.hpp:200
+
+enum { CMD_EVAL = 1, CMD_FINAL = 2, CMD_DONE = 3 };
+enum { PHASE_INIT = 0, PHASE_CAND = 1 };
+
+struct KfDev {
+    const float4* gxy;   // {Gx, Gy, X, Y}
+    const float2* dw;    // {idp, weight}
+    const double* kpx;   // 3-D point (X,Y,1)/(idp+eps)
+    const double* kpy;
+    const double* kpz;
+    const double* A;     // [B][21] upper triangle of sum g g^T per residual block
+    int N, B, H, W;
+    double fx, fy, cx, cy;
+};
+
+struct ProblemDesc {
+    KfDev kf;
+    const float* frame;        // H*W un-normalised event frame
+    const double* norms;       // {norm, 1/norm}
+    double* state;             // 14 doubles: px(3) qx(4) vx(6) loss_param; in-out
+    float* residuals;          // N, written by the final sweep
+    edsgpu_tracker_info* info; // device
+    int loss_type, max_iter, loss_param_method, eval_only;
+    double ftol, gtol, ptol;
+    float* jac_out;            // eval_only: N x 12 local Jacobian (no loss) or null
+    double* eval_out;          // eval_only: cost, H(144), g(12)
+};
+
+// ------------------------------------------------------------------------------------------
+// small fp64 helpers (device)
+// ------------------------------------------------------------------------------------------
+// Eigen::Quaternion::toRotationMatrix (no normalisation), PhotometricError.hpp:163
+__device__ __forceinline__ void quat_to_rot(const double* q, double* R) {
+    const double tx = 2.0 * q[0], ty = 2.0 * q[1], tz = 2.0 * q[2];
+    const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+    const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+    const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+    R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz;         R[2] = txz + twy;
+    R[3] = txy + twz;         R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;         R[7] = tyz + twx;         R[8] = 1.0 - (txx + tyy);
+}
+
+// Program-level Plus over [p(3) q(4) v(6)] <- delta(12):
+// ceres::EigenQuaternionParameterization::Plus and UnitNormVectorAddition
+// (PhotometricError.hpp:32-54), Tracker.cpp:111-114,197-198.
+__device__ void state_plus(const double* x, const double* d, double* out) {
+    for (int i = 0; i < 3; ++i) out[i] = x[i] + d[i];
+    const double nd = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+    if (nd > 0.0) {
+        const double s = sin(nd) / nd;
+        const double ax = s * d[3], ay = s * d[4], az = s * d[5], aw = cos(nd);
+        const double bx = x[3], by = x[4], bz = x[5], bw = x[6];
+        out[6] = aw * bw - ax * bx - ay * by - az * bz;
+        out[3] = aw * bx + ax * bw + ay * bz - az * by;
+        out[4] = aw * by + ay * bw + az * bx - ax * bz;
+        out[5] = aw * bz + az * bw + ax * by - ay * bx;
+    } else {
+        for (int i = 3; i < 7; ++i) out[i] = x[i];
+    }
+    double sum = 0.0;
+    for (int i = 0; i < 6; ++i) { double s = x[7 + i] + d[6 + i]; sum += s * s; out[7 + i] = s; }
+    sum = 1.0 / sqrt(sum);
+    for (int i = 0; i < 6; ++i) out[7 + i] *= sum;
+}
+
+// ceres::HuberLoss / ceres::CauchyLoss (Tracker.cpp:146-161): rho(s), rho'(s)
+__device__ __forceinline__ void loss_eval(int type, double a, double s, double* rho0, double* rho1) {
+    if (type == EDSGPU_LOSS_HUBER) {
+        const double b = a * a;
+        if (s > b) {
+            const double r = sqrt(s);
+            *rho0 = 2.0 * a * r - b;
+            *rho1 = fmax(DBL_MIN, a / r);
+        } else { *rho0 = s; *rho1 = 1.0; }
+    } else if (type == EDSGPU_LOSS_CAUCHY) {
+        const double b = a * a, c = 1.0 / b;
+        const double sum = 1.0 + s * c;
+        *rho0 = b * log(sum);
+        *rho1 = fmax(DBL_MIN, 1.0 / sum);
+    } else { *rho0 = s; *rho1 = 1.0; }
+}
+
+__host__ __device__ __forceinline__ int tri_index(int a, int b) {  // a <= b < 12, row-major upper triangle
+    return a * 12 - (a * (a - 1)) / 2 + (b - a);
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory layout of one CTA
+// ------------------------------------------------------------------------------------------
+struct LmState {
+    double x[13], cand[13];
+    double H[78], g[12];      // at x, un-scaled
+    double Hs[78], gs[12];    // Jacobi-scaled
+    double scale[12], diag[12];
+    double x_cost, cand_cost, mcc, radius, dec, gmax, x_norm, initial_cost;
+    int reuse_diag, iter, n_succ, n_unsucc, consec_invalid, termination, phase;
+};
+
+struct CtaShared {
+    // published by the leader into every CTA before sync (A)
+    double x_eval[13];
+    int cmd;
+    // per-evaluation constants derived from x_eval
+    double R[9], t[3];
+    float vf[6], inv_vs, inv_vn;
+    // per residual block
+    float invM, cM3[6];
+    // reduction scratch
+    double warp_part[TRK_WARPS][NACC];
+    double warp_s[TRK_WARPS];
+    // leader only: one slot per residual block, filled over DSMEM
+    double slots[MAX_BLOCKS][NSLOT];
+    double sum[NSLOT];
+    LmState lm;
+};
+
+// ------------------------------------------------------------------------------------------
+// per-point residual + analytic tangent-space Jacobian
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_hermite(float p0, float p1, float p2, float p3, float x, float& f, float& dfdx) {
+    // ceres CubicHermiteSpline (Catmull-Rom), call site PhotometricError.hpp:172
+    const float a = 0.5f * (-p0 + 3.0f * p1 - 3.0f * p2 + p3);
+    const float b = 0.5f * (2.0f * p0 - 5.0f * p1 + 4.0f * p2 - p3);
+    const float c = 0.5f * (-p0 + p2);
+    f = p1 + x * (c + x * (b + x * a));
+    dfdx = c + x * (2.0f * b + 3.0f * a * x);
+}
+__device__ __forceinline__ float cubic_hermite_f(float p0, float p1, float p2, float p3, float x) {
+    const float a = 0.5f * (-p0 + 3.0f * p1 - 3.0f * p2 + p3);
+    const float b = 0.5f * (2.0f * p0 - 5.0f * p1 + 4.0f * p2 - p3);
+    const float c = 0.5f * (-p0 + p2);
+    return p1 + x * (c + x * (b + x * a));
+}
+
+template <bool WANT_J>
+__device__ __forceinline__ void eval_point(const KfDev& kf, const CtaShared& sh, const float* __restrict__ frame, float inv_norm,
+                                           int idx, float* __restrict__ J, float& r) {
+    const float4 g4 = __ldg(&kf.gxy[idx]);
+    const float2 dw = __ldg(&kf.dw[idx]);
+    const double kx = __ldg(&kf.kpx[idx]), ky = __ldg(&kf.kpy[idx]), kz = __ldg(&kf.kpz[idx]);
+    const float Gx = g4.x, Gy = g4.y, X = g4.z, Y = g4.w, d = dw.x, w = dw.y;
+    // model term: m = g . v with g = -(Gx dflow_x/dv + Gy dflow_y/dv), PhotometricError.hpp:114-122,145
+    float g[6];
+    g[0] = Gx * d;
+    g[1] = Gy * d;
+    g[2] = -(Gx * X + Gy * Y) * d;
+    g[3] = -(Gx * X * Y + Gy * (1.0f + Y * Y));
+    g[4] = Gx * (1.0f + X * X) + Gy * X * Y;
+    g[5] = Gy * X - Gx * Y;
+    float m = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m += g[k] * sh.vf[k];
+    // warp + projection in fp64 (PhotometricError.hpp:157-168): the pixel coordinate must not
+    // carry fp32 rounding (1.5e-5 px at |u| ~ 256), SURVEY.md section 7.
+    const double ax = sh.R[0] * kx + sh.R[1] * ky + sh.R[2] * kz;
+    const double ay = sh.R[3] * kx + sh.R[4] * ky + sh.R[5] * kz;
+    const double az = sh.R[6] * kx + sh.R[7] * ky + sh.R[8] * kz;
+    const double px = ax + sh.t[0], py = ay + sh.t[1], pz = az + sh.t[2];
+    const double iz = 1.0 / pz;
+    double u = kf.fx * (px * iz) + kf.cx;
+    double v = kf.fy * (py * iz) + kf.cy;
+    // clamped Grid2D makes the interpolant constant outside [-1, n+1]; NaN-safe clamp
+    u = fmin(fmax(u, -4.0), (double)kf.W + 4.0);
+    v = fmin(fmax(v, -4.0), (double)kf.H + 4.0);
+    const double fu = floor(u), fv = floor(v);
+    const int col = (int)fu, row = (int)fv;
+    const float tc = (float)(u - fu), tr = (float)(v - fv);
+    const int W = kf.W, H = kf.H;
+    const int c0 = max(0, min(col - 1, W - 1)), c1 = max(0, min(col, W - 1));
+    const int c2 = max(0, min(col + 1, W - 1)), c3 = max(0, min(col + 2, W - 1));
+    float fr[4], dfc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int rr = max(0, min(row - 1 + k, H - 1));
+        const float* rp = frame + (size_t)rr * W;
+        cubic_hermite(__ldg(rp + c0), __ldg(rp + c1), __ldg(rp + c2), __ldg(rp + c3), tc, fr[k], dfc[k]);
+    }
+    float f, dfdr;
+    cubic_hermite(fr[0], fr[1], fr[2], fr[3], tr, f, dfdr);
+    const float dfdc = cubic_hermite_f(dfc[0], dfc[1], dfc[2], dfc[3], tr);
+    const float e = inv_norm * f, er = inv_norm * dfdr, ec = inv_norm * dfdc;
+    r = w * (m * sh.invM - e);  // PhotometricError.hpp:173
+    if (!WANT_J) return;
+    // d r / d P  (P = R kp + t)
+    const float izf = (float)iz, fxf = (float)kf.fx, fyf = (float)kf.fy;
+    const float pxf = (float)px, pyf = (float)py;
+    const float dPx = -w * ec * fxf * izf;
+    const float dPy = -w * er * fyf * izf;
+    const float dPz = w * (ec * fxf * pxf + er * fyf * pyf) * izf * izf;
+    J[0] = dPx; J[1] = dPy; J[2] = dPz;
+    // quaternion tangent: q <- [sin|d| d/|d|, cos|d|] * q rotates by 2|d|: dP/dtheta = -2 [R kp]x
+    const float axf = (float)ax, ayf = (float)ay, azf = (float)az;
+    J[3] = 2.0f * (ayf * dPz - azf * dPy);
+    J[4] = 2.0f * (azf * dPx - axf * dPz);
+    J[5] = 2.0f * (axf * dPy - ayf * dPx);
+    // velocity: d r/d v = w (g/M - m c/M^3), then the unit-norm Plus Jacobian (I - v v^T/s)/|v|
+    float jv[6], dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { jv[k] = w * (g[k] * sh.invM - m * sh.cM3[k]); dot += jv[k] * sh.vf[k]; }
+    const float dn = dot * sh.inv_vs;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) J[6 + k] = (jv[k] - dn * sh.vf[k]) * sh.inv_vn;
+}
+
+// halving butterfly: 96 per-lane values -> 3 warp-reduced values per lane.
+// lane l ends with entries base(l)+{0,1,2}, base = 48 b4 + 24 b3 + 12 b2 + 6 b1 + 3 b0.
+template <int HALF, int OFFSET>
+__device__ __forceinline__ void butterfly_step(float* a, unsigned lane) {
+    const bool upper = (lane & OFFSET) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        const float send = upper ? a[i] : a[i + HALF];
+        const float keep = upper ? a[i + HALF] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFFSET);
+    }
+}
+__device__ __forceinline__ int butterfly_base(unsigned lane) {
+    return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
+}
+
+// One CTA evaluates the residual blocks dealt to it at sh.x_eval and stores, per block,
+// [rho' * JtJ (78) | rho' * Jtr (12) | 0.5 rho(s) | s] into slot_dst[b] (leader smem via DSMEM).
+template <bool RES_ONLY>
+__device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_base /* [MAX_BLOCKS][NSLOT] on the leader */,
+                             int rank, int csize, bool write_residuals) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const KfDev& kf = P.kf;
+    if (tid == 0) {
+        quat_to_rot(&sh.x_eval[3], sh.R);
+        sh.t[0] = sh.x_eval[0]; sh.t[1] = sh.x_eval[1]; sh.t[2] = sh.x_eval[2];
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) { s += sh.x_eval[7 + k] * sh.x_eval[7 + k]; sh.vf[k] = (float)sh.x_eval[7 + k]; }
+        sh.inv_vs = (float)(1.0 / s);
+        sh.inv_vn = (float)(1.0 / sqrt(s));
+    }
+    const float inv_norm = (float)P.norms[1];
+    const double loss_a = P.state[13];
+    const int ne = kf.N / kf.B;
+    for (int b = rank; b < kf.B; b += csize) {
+        __syncthreads();  // x_eval-derived constants ready; previous block's scratch consumed
+        if (tid == 0) {
+            // S = 1e-3 + v^T A v (PhotometricError.hpp:132,148), c = A v
+            const double* A = kf.A + 21 * b;
+            const double* v = &sh.x_eval[7];
+            double c[6] = {0, 0, 0, 0, 0, 0};
+            int k = 0;
+            for (int i = 0; i < 6; ++i)
+                for (int j = i; j < 6; ++j, ++k) {
+                    c[i] += A[k] * v[j];
+                    if (j != i) c[j] += A[k] * v[i];
+                }
+            double S = 1e-03;
+            for (int i = 0; i < 6; ++i) S += v[i] * c[i];
+            const double M = sqrt(S);
+            sh.invM = (float)(1.0 / M);
+            const double iM3 = 1.0 / (M * S);
+            for (int i = 0; i < 6; ++i) sh.cM3[i] = (float)(c[i] * iM3);
+        }
+        __syncthreads();
+        const int start = b * ne;
+        const int n = ne + ((b + 1 == kf.B) ? (kf.N - (b + 1) * ne) : 0);  // Tracker.cpp:178-190
+        if constexpr (RES_ONLY) {
+            // residual write-back only (Tracker.cpp:223-230): no Jacobian, no reduction, no DSMEM traffic
+            for (int i = tid; i < n; i += TRK_THREADS) {
+                float r;
+                eval_point<false>(kf, sh, P.frame, inv_norm, start + i, nullptr, r);
+                P.residuals[start + i] = r;
+            }
+            continue;
+        }
+        float acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+        double s_acc = 0.0;
+        for (int i = tid; i < n; i += TRK_THREADS) {
+            float J[12], r;
+            eval_point<true>(kf, sh, P.frame, inv_norm, start + i, J, r);
+            if (write_residuals) {
+                P.residuals[start + i] = r;
+                if (P.jac_out) {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * (start + i) + k] = J[k];
+                }
+            }
+            int e = 0;
+#pragma unroll
+            for (int a = 0; a < 12; ++a)
+#pragma unroll
+                for (int c2 = a; c2 < 12; ++c2) acc[e++] += J[a] * J[c2];
+#pragma unroll
+            for (int a = 0; a < 12; ++a) acc[78 + a] += J[a] * r;
+            s_acc += (double)r * (double)r;
+        }
+        butterfly_step<48, 16>(acc, lane);
+        butterfly_step<24, 8>(acc, lane);
+        butterfly_step<12, 4>(acc, lane);
+        butterfly_step<6, 2>(acc, lane);
+        butterfly_step<3, 1>(acc, lane);
+        const int base = butterfly_base(lane);
+        sh.warp_part[warp][base] = (double)acc[0];
+        sh.warp_part[warp][base + 1] = (double)acc[1];
+        sh.warp_part[warp][base + 2] = (double)acc[2];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
+        if (lane == 0) sh.warp_s[warp] = s_acc;
+        __syncthreads();
+        if (tid < NSLOT) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < TRK_WARPS; ++w) s += sh.warp_s[w];
+            double rho0, rho1;
+            loss_eval(P.loss_type, loss_a, s, &rho0, &rho1);
+            double val;
+            if (tid < 90) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < TRK_WARPS; ++w) t += sh.warp_part[w][tid];
+                val = rho1 * t;
+            } else if (tid == 90) {
+                val = 0.5 * rho0;
+            } else {
+                val = s;
+            }
+            slot_base[b * NSLOT + tid] = val;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// leader: Levenberg-Marquardt state machine (ceres TrustRegionMinimizer +
+// LevenbergMarquardtStrategy semantics; options of Tracker.cpp:117-143)
+// ------------------------------------------------------------------------------------------
+__device__ bool chol_solve12(const double* Hs /*78*/, const double* add_diag, const double* rhs, double* y) {
+    double L[78];  // lower triangle, row-major packed: L[i*(i+1)/2 + j]
+    for (int j = 0; j < 12; ++j) {
+        double dsum = Hs[tri_index(j, j)] + add_diag[j];
+        for (int k = 0; k < j; ++k) dsum -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+        if (!(dsum > 0.0) || !isfinite(dsum)) return false;
+        const double ljj = sqrt(dsum);
+        L[j * (j + 1) / 2 + j] = ljj;
+        const double inv = 1.0 / ljj;
+        for (int i = j + 1; i < 12; ++i) {
+            double s = Hs[tri_index(j, i)];
+            for (int k = 0; k < j; ++k) s -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+            L[i * (i + 1) / 2 + j] = s * inv;
+        }
+    }
+    double z[12];
+    for (int i = 0; i < 12; ++i) {
+        double s = rhs[i];
+        for (int k = 0; k < i; ++k) s -= L[i * (i + 1) / 2 + k] * z[k];
+        z[i] = s / L[i * (i + 1) / 2 + i];
+    }
+    for (int i = 11; i >= 0; --i) {
+        double s = z[i];
+        for (int k = i + 1; k < 12; ++k) s -= L[k * (k + 1) / 2 + i] * y[k];
+        y[i] = s / L[i * (i + 1) / 2 + i];
+    }
+    for (int i = 0; i < 12; ++i) if (!isfinite(y[i])) return false;
+    return true;
+}
+
+__device__ void lm_take_evaluation(LmState& lm, const double* Hsum, const double* gsum, double cost, bool first) {
+    lm.x_cost = cost;
+    for (int i = 0; i < 78; ++i) lm.H[i] = Hsum[i];
+    for (int i = 0; i < 12; ++i) lm.g[i] = gsum[i];
+    if (first)  // jacobi_scaling: computed at iteration 0 only
+        for (int i = 0; i < 12; ++i) lm.scale[i] = 1.0 / (1.0 + sqrt(lm.H[tri_index(i, i)]));
+    for (int a = 0; a < 12; ++a) {
+        lm.gs[a] = lm.g[a] * lm.scale[a];
+        for (int b = a; b < 12; ++b) lm.Hs[tri_index(a, b)] = lm.H[tri_index(a, b)] * lm.scale[a] * lm.scale[b];
+    }
+    // gradient_max_norm = || x - Plus(x, -g) ||_inf
+    double ng[12], xp[13];
+    for (int i = 0; i < 12; ++i) ng[i] = -lm.g[i];
+    state_plus(lm.x, ng, xp);
+    double m = 0.0;
+    for (int i = 0; i < 13; ++i) m = fmax(m, fabs(lm.x[i] - xp[i]));
+    lm.gmax = m;
+    double s = 0.0;
+    for (int i = 0; i < 13; ++i) s += lm.x[i] * lm.x[i];
+    lm.x_norm = sqrt(s);
+}
+
+// returns the next command; when CMD_EVAL, lm.cand holds the point to evaluate
+__device__ int lm_advance(const ProblemDesc& P, LmState& lm, const double* Hsum, const double* gsum, double cost) {
+    bool finite_eval = isfinite(cost);
+    for (int i = 0; i < 78 && finite_eval; ++i) finite_eval = isfinite(Hsum[i]);
+    for (int i = 0; i < 12 && finite_eval; ++i) finite_eval = isfinite(gsum[i]);
+    if (lm.phase == PHASE_INIT) {
+        lm.initial_cost = cost;
+        if (!finite_eval) { lm.termination = EDSGPU_TERM_FAILURE; lm.x_cost = cost; return CMD_DONE; }
+        lm_take_evaluation(lm, Hsum, gsum, cost, true);
+    } else {
+        const double cand_cost = isfinite(cost) ? cost : DBL_MAX;
+        // ParameterToleranceReached
+        double sn = 0.0;
+        for (int i = 0; i < 13; ++i) sn += (lm.x[i] - lm.cand[i]) * (lm.x[i] - lm.cand[i]);
+        sn = sqrt(sn);
+        if (sn <= P.ptol * (lm.x_norm + P.ptol)) { lm.termination = EDSGPU_TERM_CONVERGENCE; return CMD_FINAL; }
+        // FunctionToleranceReached
+        const double cost_change = lm.x_cost - cand_cost;
+        if (fabs(cost_change) <= P.ftol * lm.x_cost) { lm.termination = EDSGPU_TERM_CONVERGENCE; return CMD_FINAL; }
+        const double rel = cost_change / lm.mcc;
+        if (rel > 1e-3) {  // min_relative_decrease
+            if (!finite_eval) { lm.termination = EDSGPU_TERM_FAILURE; return CMD_DONE; }
+            for (int i = 0; i < 13; ++i) lm.x[i] = lm.cand[i];
+            lm_take_evaluation(lm, Hsum, gsum, cost, false);
+            lm.radius = lm.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+            lm.radius = fmin(1e16, lm.radius);
+            lm.dec = 2.0;
+            lm.reuse_diag = 0;
+            lm.n_succ++;
+        } else {
+            lm.radius = lm.radius / lm.dec;
+            lm.dec *= 2.0;
+            lm.reuse_diag = 1;
+            lm.n_unsucc++;
+        }
+    }
+    for (;;) {
+        if (lm.iter >= P.max_iter) { lm.termination = EDSGPU_TERM_NO_CONVERGENCE; return CMD_FINAL; }
+        if (lm.gmax <= P.gtol) { lm.termination = EDSGPU_TERM_CONVERGENCE; return CMD_FINAL; }
+        if (lm.radius < 1e-32) { lm.termination = EDSGPU_TERM_CONVERGENCE; return CMD_FINAL; }
+        lm.iter++;
+        if (!lm.reuse_diag)
+            for (int i = 0; i < 12; ++i) lm.diag[i] = fmin(fmax(lm.Hs[tri_index(i, i)], 1e-6), 1e32);
+        double add[12], y[12], step[12];
+        for (int i = 0; i < 12; ++i) add[i] = lm.diag[i] / lm.radius;
+        bool ok = chol_solve12(lm.Hs, add, lm.gs, y);
+        lm.reuse_diag = 1;
+        double mcc = 0.0;
+        if (ok) {
+            double sg = 0.0, sHs = 0.0;
+            for (int i = 0; i < 12; ++i) step[i] = -y[i];
+            for (int i = 0; i < 12; ++i) {
+                sg += step[i] * lm.gs[i];
+                double hv = 0.0;
+                for (int j = 0; j < 12; ++j) hv += lm.Hs[i <= j ? tri_index(i, j) : tri_index(j, i)] * step[j];
+                sHs += step[i] * hv;
+            }
+            mcc = -sg - 0.5 * sHs;
+            ok = mcc > 0.0;
+        }
+        if (!ok) {  // HandleInvalidStep
+            if (++lm.consec_invalid >= 5) { lm.termination = EDSGPU_TERM_FAILURE; return CMD_DONE; }
+            lm.radius = lm.radius / lm.dec;
+            lm.dec *= 2.0;
+            lm.n_unsucc++;
+            continue;
+        }
+        lm.consec_invalid = 0;
+        lm.mcc = mcc;
+        double delta[12];
+        for (int i = 0; i < 12; ++i) delta[i] = step[i] * lm.scale[i];
+        state_plus(lm.x, delta, lm.cand);
+        lm.phase = PHASE_CAND;
+        return CMD_EVAL;
+    }
+}
+
+__global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemDesc* __restrict__ problems) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    __shared__ CtaShared sh;
+    __shared__ ProblemDesc P;
+    const int tid = threadIdx.x;
+    {
+        const int* src = reinterpret_cast<const int*>(&problems[blockIdx.x / csize]);
+        int* dst = reinterpret_cast<int*>(&P);
+        for (int i = tid; i < (int)(sizeof(ProblemDesc) / sizeof(int)); i += TRK_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    CtaShared* leader = cluster.map_shared_rank(&sh, 0);
+    double* slot_base = &leader->slots[0][0];
+
+    if (rank == 0 && tid == 0) {
+        LmState& lm = sh.lm;
+        for (int i = 0; i < 13; ++i) lm.x[i] = P.state[i];
+        lm.radius = 1e4; lm.dec = 2.0; lm.reuse_diag = 0;
+        lm.iter = 0; lm.n_succ = 0; lm.n_unsucc = 0; lm.consec_invalid = 0;
+        lm.termination = EDSGPU_TERM_NO_CONVERGENCE; lm.phase = PHASE_INIT;
+        lm.x_cost = 0.0; lm.initial_cost = 0.0;
+        for (int c = 0; c < csize; ++c) {
+            CtaShared* dst = cluster.map_shared_rank(&sh, c);
+            for (int i = 0; i < 13; ++i) dst->x_eval[i] = lm.x[i];
+            dst->cmd = CMD_EVAL;
+        }
+    }
+    for (;;) {
+        cluster.sync();  // (A) command + evaluation point published to every CTA
+        const int cmd = sh.cmd;
+        if (cmd == CMD_DONE) break;
+        if (cmd == CMD_FINAL) {  // residual write-back at the accepted state; touches no remote memory
+            cta_evaluate<true>(P, sh, slot_base, rank, csize, true);
+            break;
+        }
+        cta_evaluate<false>(P, sh, slot_base, rank, csize, false);
+        cluster.sync();  // (B) every residual-block slot has landed in the leader's shared memory
+        if (rank == 0 && tid < 32) {
+            // ordered sum over residual blocks: the result does not depend on the cluster size
+            for (int e = tid; e < 91; e += 32) {
+                double s = 0.0;
+                for (int b = 0; b < P.kf.B; ++b) s += sh.slots[b][e];
+                sh.sum[e] = s;
+            }
+            __syncwarp();
+            if (tid == 0) {
+                LmState& lm = sh.lm;
+                const int next = lm_advance(P, lm, sh.sum, sh.sum + 78, sh.sum[90]);
+                const double* xe = (next == CMD_EVAL) ? lm.cand : lm.x;
+                for (int c = 0; c < csize; ++c) {
+                    CtaShared* dst = cluster.map_shared_rank(&sh, c);
+                    for (int i = 0; i < 13; ++i) dst->x_eval[i] = xe[i];
+                    dst->cmd = next;
+                }
+                if (next != CMD_EVAL) {
+                    const bool usable = lm.termination != EDSGPU_TERM_FAILURE;
+                    if (usable) for (int i = 0; i < 13; ++i) P.state[i] = lm.x[i];  // Tracker.cpp:217-220
+                    edsgpu_tracker_info inf;
+                    inf.iterations = lm.n_succ + lm.n_unsucc;
+                    inf.successful_steps = lm.n_succ;
+                    inf.unsuccessful_steps = lm.n_unsucc;
+                    inf.termination = lm.termination;
+                    inf.usable = usable ? 1 : 0;
+                    inf.num_points = P.kf.N;
+                    inf.initial_cost = lm.initial_cost;
+                    inf.final_cost = lm.x_cost;
+                    inf.final_radius = lm.radius;
+                    *P.info = inf;
+                }
+            }
+        }
+    }
+}
+
+// parity/debug entry (edsgpu_tracker_evaluate): one full evaluation at P.state, residuals and
+// Jacobian rows written out, reduced normal equations returned.
+__global__ void __launch_bounds__(TRK_THREADS, 1) track_eval_kernel(const ProblemDesc* __restrict__ problems) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const ProblemDesc& P = problems[blockIdx.x / csize];
+    __shared__ CtaShared sh;
+    CtaShared* leader = cluster.map_shared_rank(&sh, 0);
+    if (threadIdx.x < 13) sh.x_eval[threadIdx.x] = P.state[threadIdx.x];
+    __syncthreads();
+    cluster.sync();
+    cta_evaluate<false>(P, sh, &leader->slots[0][0], rank, csize, true);
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0 && P.eval_out) {
+        double cost = 0.0;
+        for (int b = 0; b < P.kf.B; ++b) cost += sh.slots[b][90];
+        P.eval_out[0] = cost;
+        for (int a = 0; a < 12; ++a) {
+            double gs = 0.0;
+            for (int b = 0; b < P.kf.B; ++b) gs += sh.slots[b][78 + a];
+            P.eval_out[1 + 144 + a] = gs;
+            for (int c2 = a; c2 < 12; ++c2) {
+                double h = 0.0;
+                for (int b = 0; b < P.kf.B; ++b) h += sh.slots[b][tri_index(a, c2)];
+                P.eval_out[1 + 12 * a + c2] = h;
+                P.eval_out[1 + 12 * c2 + a] = h;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// next loss parameter (Tracker.cpp:281-317): MAD via exact radix select on fp32 keys
+// ------------------------------------------------------------------------------------------
+constexpr int MAD_THREADS = 1024;
+
+__device__ __forceinline__ unsigned f2key(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// k-th smallest (0-based) of f(i), i < n.  All threads of the CTA must call.
+template <typename F>
+__device__ float select_kth(F f, int n, int k, unsigned* hist /*256*/, unsigned* bcast /*2*/) {
+    unsigned prefix = 0, mask = 0;
+    int kk = k;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned key = f2key(f(i));
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // warp scan over 256 bins, 8 per lane
+            unsigned local[8], sum = 0;
+            for (int j = 0; j < 8; ++j) { local[j] = hist[threadIdx.x * 8 + j]; sum += local[j]; }
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+            unsigned excl = incl - sum;
+            if ((unsigned)kk >= excl && (unsigned)kk < incl) {
+                unsigned run = excl;
+                for (int j = 0; j < 8; ++j) {
+                    if ((unsigned)kk < run + local[j]) { bcast[0] = threadIdx.x * 8 + j; bcast[1] = run; break; }
+                    run += local[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= bcast[0] << shift;
+        mask |= 255u << shift;
+        kk -= (int)bcast[1];
+        __syncthreads();
+    }
+    return key2f(prefix);
+}
+
+__global__ void __launch_bounds__(MAD_THREADS) mad_kernel(const ProblemDesc* __restrict__ problems) {
+    const ProblemDesc& P = problems[blockIdx.x];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned bcast[2];
+    __shared__ double red[MAD_THREADS / 32];
+    if (P.loss_param_method == EDSGPU_LOSS_PARAM_CONSTANT) return;
+    if (!P.info->usable) return;  // Tracker.cpp:217: only after a usable solve
+    const int n = P.kf.N;
+    const float* r = P.residuals;
+    if (P.loss_param_method == EDSGPU_LOSS_PARAM_MAD) {
+        // n_quantile_vector(v, size/2) == element size/2 of the sorted vector (Utils.hpp:315-320)
+        const float med = select_kth([r](int i) { return r[i]; }, n, n / 2, hist, bcast);
+        const float mad = select_kth([r, med](int i) { return fabsf(r[i] - med); }, n, n / 2, hist, bcast);
+        if (threadIdx.x == 0) P.state[13] = 1.345 * (1.4826 * (double)mad);
+    } else {
+        // mean_std_vector (Utils.hpp:272-290): note the reference returns the VARIANCE as "std_dev"
+        auto block_sum = [&](double v) {
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+            __syncthreads();
+            double s = 0.0;
+            for (int w = 0; w < MAD_THREADS / 32; ++w) s += red[w];
+            return s;
+        };
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)r[i];
+        const double mu = block_sum(s) / (double)n;
+        double q = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { double d = (double)r[i] - mu; q += d * d / (double)(n - 1); }
+        const double var = (n == 1) ? 0.0 : block_sum(q);
+        if (threadIdx.x == 0) P.state[13] = 1.345 * var;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// keyframe upload
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kf_prepare_kernel(const double* __restrict__ grad_xy, const double* __restrict__ norm_xy,
+                                                         const double* __restrict__ idp, const double* __restrict__ weights, int N, int B,
+                                                         float4* __restrict__ gxy, float2* __restrict__ dw, double* __restrict__ kpx,
+                                                         double* __restrict__ kpy, double* __restrict__ kpz, double* __restrict__ A) {
+    const int b = blockIdx.x;
+    const int ne = N / B;
+    const int start = b * ne;
+    const int n = ne + ((b + 1 == B) ? (N - (b + 1) * ne) : 0);
+    double a[21];
+    for (int k = 0; k < 21; ++k) a[k] = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int idx = start + i;
+        const double Gx = grad_xy[2 * idx], Gy = grad_xy[2 * idx + 1];
+        const double X = norm_xy[2 * idx], Y = norm_xy[2 * idx + 1];
+        const double d = idp[idx], w = weights[idx];
+        gxy[idx] = make_float4((float)Gx, (float)Gy, (float)X, (float)Y);
+        dw[idx] = make_float2((float)d, (float)w);
+        const double z = 1.0 / (d + kEps);  // PhotometricError.hpp:97-99
+        kpz[idx] = z;
+        kpx[idx] = X * z;
+        kpy[idx] = Y * z;
+        double g[6];
+        g[0] = Gx * d;
+        g[1] = Gy * d;
+        g[2] = -(Gx * X + Gy * Y) * d;
+        g[3] = -(Gx * X * Y + Gy * (1.0 + Y * Y));
+        g[4] = Gx * (1.0 + X * X) + Gy * X * Y;
+        g[5] = Gy * X - Gx * Y;
+        int k = 0;
+        for (int p = 0; p < 6; ++p)
+            for (int q = p; q < 6; ++q, ++k) a[k] += g[p] * g[q];
+    }
+    __shared__ double red[8][21];
+    for (int k = 0; k < 21; ++k) {
+        double v = a[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 21) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        A[21 * b + threadIdx.x] = s;
+    }
+}
+
+__global__ void float_to_double_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
+}  // namespace
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+struct edsgpu_keyframe {
+    edsgpu_ctx* ctx = nullptr;
+    KfDev dev{};
+    void* block = nullptr;  // one allocation behind all device arrays
+    float* residuals = nullptr;
+};
+
+struct edsgpu_tracker {
+    edsgpu_ctx* ctx = nullptr;
+    edsgpu_tracker_config cfg{};
+    double* state = nullptr;            // device: 14 doubles
+    edsgpu_tracker_info* info = nullptr; // device
+    ProblemDesc* desc = nullptr;        // device: one descriptor for single-problem calls
+};
+
+namespace {
+
+int pick_cluster(const edsgpu_ctx* ctx, int count, int B) {
+    int c = 1;
+    while (c * 2 <= MAX_CLUSTER && c * 2 <= B && (size_t)count * c * 2 <= (size_t)ctx->num_sms) c *= 2;
+    return c;
+}
+
+template <typename K>
+edsgpu_status launch_cluster(edsgpu_ctx* ctx, K kernel, const ProblemDesc* desc_dev, int count, int csize) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(count * csize);
+    cfg.blockDim = dim3(TRK_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EDS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, desc_dev));
+    ctx->launches++;
+    return EDSGPU_OK;
+}
+
+ProblemDesc make_desc(const edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot) {
+    ProblemDesc d{};
+    d.kf = kf->dev;
+    d.frame = frames->frame + (size_t)slot * frames->H * frames->W;
+    d.norms = frames->norms + 2 * slot;
+    d.state = tr->state;
+    d.residuals = kf->residuals;
+    d.info = tr->info;
+    d.loss_type = tr->cfg.loss_type;
+    d.max_iter = tr->cfg.max_iterations;
+    d.loss_param_method = tr->cfg.loss_param_method;
+    d.eval_only = 0;
+    d.ftol = tr->cfg.function_tolerance;
+    d.gtol = tr->cfg.gradient_tolerance;
+    d.ptol = tr->cfg.parameter_tolerance;
+    d.jac_out = nullptr;
+    d.eval_out = nullptr;
+    return d;
+}
+
+edsgpu_status check_pair(edsgpu_ctx* ctx, const edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot) {
+    EDS_REQUIRE(ctx, tr && kf && frames, "tracker: null handle");
+    EDS_REQUIRE(ctx, tr->ctx == ctx && kf->ctx == ctx && frames->ctx == ctx, "tracker: handles belong to different contexts");
+    EDS_REQUIRE(ctx, slot >= 0 && slot < frames->capacity, "tracker: frame slot out of range");
+    EDS_REQUIRE(ctx, frames->H == kf->dev.H && frames->W == kf->dev.W, "tracker: keyframe and event frame sizes differ");
+    EDS_REQUIRE(ctx, tr->cfg.num_blocks == kf->dev.B, "tracker: config.num_blocks differs from the keyframe's block partition");
+    return EDSGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const double* grad_xy, const double* norm_xy, const double* idp,
+                                     const double* weights, int height, int width, double fx, double fy, double cx, double cy, int num_blocks,
+                                     edsgpu_keyframe** out) {
+    if (!ctx || !out) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, grad_xy && norm_xy && idp && weights, "keyframe_create: null array");
+    EDS_REQUIRE(ctx, height > 0 && width > 0, "keyframe_create: bad image size");
+    EDS_REQUIRE(ctx, num_blocks >= 1 && num_blocks <= MAX_BLOCKS, "keyframe_create: num_blocks must be in [1,32]");
+    EDS_REQUIRE(ctx, num_points >= num_blocks, "keyframe_create: fewer points than residual blocks");
+    DeviceGuard g(ctx->device);
+    const size_t N = (size_t)num_points;
+    edsgpu_keyframe* kf = new edsgpu_keyframe();
+    kf->ctx = ctx;
+    // layout: gxy | dw | kpx | kpy | kpz | A | residuals
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_gxy = take(N * sizeof(float4)), o_dw = take(N * sizeof(float2)), o_kx = take(N * 8), o_ky = take(N * 8), o_kz = take(N * 8);
+    const size_t o_A = take((size_t)num_blocks * 21 * 8), o_res = take(N * sizeof(float));
+    cudaError_t e = cudaMalloc(&kf->block, off);
+    if (e != cudaSuccess) { delete kf; return edsgpu_fail(ctx, EDSGPU_OUT_OF_MEMORY, cudaGetErrorString(e)); }
+    char* base = (char*)kf->block;
+    KfDev& d = kf->dev;
+    d.gxy = (float4*)(base + o_gxy); d.dw = (float2*)(base + o_dw);
+    d.kpx = (double*)(base + o_kx); d.kpy = (double*)(base + o_ky); d.kpz = (double*)(base + o_kz);
+    d.A = (double*)(base + o_A);
+    kf->residuals = (float*)(base + o_res);
+    d.N = num_points; d.B = num_blocks; d.H = height; d.W = width;
+    d.fx = fx; d.fy = fy; d.cx = cx; d.cy = cy;
+    // stage the double arrays: pinned -> device scratch -> prepare kernel
+    const size_t stage = N * 6 * sizeof(double);
+    edsgpu_status st = edsgpu_ensure_pinned(ctx, stage);
+    if (st == EDSGPU_OK) st = edsgpu_ensure_scratch(ctx, stage);
+    if (st != EDSGPU_OK) { edsgpu_keyframe_destroy(kf); return st; }
+    double* hp = (double*)ctx->pinned;
+    memcpy(hp, grad_xy, N * 16);
+    memcpy(hp + 2 * N, norm_xy, N * 16);
+    memcpy(hp + 4 * N, idp, N * 8);
+    memcpy(hp + 5 * N, weights, N * 8);
+    double* ds = (double*)ctx->scratch;
+    e = cudaMemcpyAsync(ds, hp, stage, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        kf_prepare_kernel<<<num_blocks, 256, 0, ctx->stream>>>(ds, ds + 2 * N, ds + 4 * N, ds + 5 * N, num_points, num_blocks,
+                                                                (float4*)d.gxy, (float2*)d.dw, (double*)d.kpx, (double*)d.kpy, (double*)d.kpz,
+                                                                (double*)d.A);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // pinned/scratch are reused by later calls
+    if (e != cudaSuccess) { edsgpu_keyframe_destroy(kf); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
+    *out = kf;
+    return EDSGPU_OK;
+}
+
+void edsgpu_keyframe_destroy(edsgpu_keyframe* kf) {
+    if (!kf) return;
+    DeviceGuard g(kf->ctx->device);
+    cudaStreamSynchronize(kf->ctx->stream);
+    if (kf->block) cudaFree(kf->block);
+    delete kf;
+}
+
+edsgpu_status edsgpu_tracker_create(edsgpu_ctx* ctx, const edsgpu_tracker_config* config, double loss_param, edsgpu_tracker** out) {
+    if (!ctx || !out || !config) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, config->num_blocks >= 1 && config->num_blocks <= MAX_BLOCKS, "tracker_create: num_blocks must be in [1,32]");
+    EDS_REQUIRE(ctx, config->loss_type >= 0 && config->loss_type <= 2, "tracker_create: unknown loss type");
+    EDS_REQUIRE(ctx, config->loss_param_method >= 0 && config->loss_param_method <= 2, "tracker_create: unknown loss-parameter method");
+    EDS_REQUIRE(ctx, config->max_iterations >= 0, "tracker_create: negative max_iterations");
+    DeviceGuard g(ctx->device);
+    edsgpu_tracker* tr = new edsgpu_tracker();
+    tr->ctx = ctx;
+    tr->cfg = *config;
+    cudaError_t e = cudaMalloc(&tr->state, 14 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&tr->info, sizeof(edsgpu_tracker_info));
+    if (e == cudaSuccess) e = cudaMalloc(&tr->desc, sizeof(ProblemDesc));
+    if (e == cudaSuccess) e = cudaMemsetAsync(tr->info, 0, sizeof(edsgpu_tracker_info), ctx->stream);
+    if (e != cudaSuccess) { edsgpu_tracker_destroy(tr); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
+    // Tracker::Tracker(config), Tracker.cpp:41-48
+    const double v = 0.001 / sqrt(6.0 * 0.001 * 0.001);
+    double init[14] = {0, 0, 0, 0, 0, 0, 1, v, v, v, v, v, v, loss_param};
+    e = cudaMemcpyAsync(tr->state, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { edsgpu_tracker_destroy(tr); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
+    *out = tr;
+    return EDSGPU_OK;
+}
+
+void edsgpu_tracker_destroy(edsgpu_tracker* tr) {
+    if (!tr) return;
+    DeviceGuard g(tr->ctx->device);
+    cudaStreamSynchronize(tr->ctx->stream);
+    if (tr->state) cudaFree(tr->state);
+    if (tr->info) cudaFree(tr->info);
+    if (tr->desc) cudaFree(tr->desc);
+    delete tr;
+}
+
+edsgpu_status edsgpu_tracker_set_state(edsgpu_tracker* tr, const double px[3], const double qx[4], const double vx[6], const double* loss_param) {
+    if (!tr) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = tr->ctx;
+    DeviceGuard g(ctx->device);
+    // small synchronous copies: the source arrays are the caller's stack/heap
+    if (px) EDS_CUDA(ctx, cudaMemcpyAsync(tr->state, px, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (qx) EDS_CUDA(ctx, cudaMemcpyAsync(tr->state + 3, qx, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (vx) EDS_CUDA(ctx, cudaMemcpyAsync(tr->state + 7, vx, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (loss_param) EDS_CUDA(ctx, cudaMemcpyAsync(tr->state + 13, loss_param, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_tracker_get_state(edsgpu_tracker* tr, double px[3], double qx[4], double vx[6], double* loss_param, edsgpu_tracker_info* info) {
+    if (!tr) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = tr->ctx;
+    DeviceGuard g(ctx->device);
+    double s[14];
+    EDS_CUDA(ctx, cudaMemcpyAsync(s, tr->state, sizeof(s), cudaMemcpyDeviceToHost, ctx->stream));
+    if (info) EDS_CUDA(ctx, cudaMemcpyAsync(info, tr->info, sizeof(*info), cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (px) memcpy(px, s, 3 * sizeof(double));
+    if (qx) memcpy(qx, s + 3, 4 * sizeof(double));
+    if (vx) memcpy(vx, s + 7, 6 * sizeof(double));
+    if (loss_param) *loss_param = s[13];
+    return EDSGPU_OK;
+}
+
+void* edsgpu_tracker_state_dev(edsgpu_tracker* tr) { return tr ? (void*)tr->state : nullptr; }
+
+edsgpu_status edsgpu_trackers_optimize_batch(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes, int count,
+                                             const edsgpu_frames* frames, int first_slot) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, trackers && keyframes && count > 0, "optimize_batch: bad arguments");
+    DeviceGuard g(ctx->device);
+    int B = 0;
+    for (int i = 0; i < count; ++i) {
+        edsgpu_status st = check_pair(ctx, trackers[i], keyframes[i], frames, first_slot + i);
+        if (st != EDSGPU_OK) return st;
+        if (i == 0) B = keyframes[i]->dev.B;
+        EDS_REQUIRE(ctx, keyframes[i]->dev.B == B, "optimize_batch: all problems of a batch must share num_blocks");
+    }
+    // descriptors: pinned -> device scratch (both owned by the context, reused call to call)
+    const size_t bytes = sizeof(ProblemDesc) * (size_t)count;
+    edsgpu_status st = edsgpu_ensure_pinned(ctx, bytes);
+    if (st == EDSGPU_OK) st = edsgpu_ensure_scratch(ctx, bytes);
+    if (st != EDSGPU_OK) return st;
+    // the previous batch may still be reading the scratch descriptors / pinned source
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ProblemDesc* hd = (ProblemDesc*)ctx->pinned;
+    for (int i = 0; i < count; ++i) hd[i] = make_desc(trackers[i], keyframes[i], frames, first_slot + i);
+    EDS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, hd, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int csize = pick_cluster(ctx, count, B);
+    st = launch_cluster(ctx, track_lm_kernel, (const ProblemDesc*)ctx->scratch, count, csize);
+    if (st != EDSGPU_OK) return st;
+    mad_kernel<<<count, MAD_THREADS, 0, ctx->stream>>>((const ProblemDesc*)ctx->scratch);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_trackers_gather(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, int count, double* states_out, edsgpu_tracker_info* infos_out) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, trackers && count > 0 && states_out, "trackers_gather: bad arguments");
+    DeviceGuard g(ctx->device);
+    for (int i = 0; i < count; ++i) {
+        EDS_CUDA(ctx, cudaMemcpyAsync(states_out + 14 * i, trackers[i]->state, 14 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (infos_out) EDS_CUDA(ctx, cudaMemcpyAsync(infos_out + i, trackers[i]->info, sizeof(edsgpu_tracker_info), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_tracker_optimize(edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot, double px[3],
+                                      double qx[4], double vx[6], double* residuals_out, double* next_loss_param_out, edsgpu_tracker_info* info) {
+    if (!tr) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = tr->ctx;
+    const edsgpu_keyframe* kfs[1] = {kf};
+    edsgpu_tracker* trs[1] = {tr};
+    edsgpu_status st = edsgpu_trackers_optimize_batch(ctx, trs, kfs, 1, frames, slot);
+    if (st != EDSGPU_OK) return st;
+    DeviceGuard g(ctx->device);
+    edsgpu_tracker_info inf;
+    double tau = 0.0;
+    st = edsgpu_tracker_get_state(tr, px, qx, vx, &tau, &inf);
+    if (st != EDSGPU_OK) return st;
+    if (info) *info = inf;
+    if (!inf.usable) return edsgpu_fail(ctx, EDSGPU_NOT_USABLE, "tracker: solution not usable");
+    if (next_loss_param_out) *next_loss_param_out = tau;
+    if (residuals_out) {
+        // kf->residuals (Tracker.cpp:223-230): fp32 on the device, widened by a kernel
+        const size_t N = (size_t)kf->dev.N;
+        st = edsgpu_ensure_scratch(ctx, N * sizeof(double));
+        if (st != EDSGPU_OK) return st;
+        float_to_double_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(kf->residuals, (double*)ctx->scratch, N);
+        ctx->launches++;
+        EDS_CUDA(ctx, cudaGetLastError());
+        EDS_CUDA(ctx, cudaMemcpyAsync(residuals_out, ctx->scratch, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot, int loss_type,
+                                      double loss_param, const double px[3], const double qx[4], const double vx[6], double* residuals_out,
+                                      double* jacobian_out, double* cost_out, double* H_out, double* g_out) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, kf && frames && px && qx && vx, "tracker_evaluate: null argument");
+    EDS_REQUIRE(ctx, kf->ctx == ctx && frames->ctx == ctx, "tracker_evaluate: handles belong to different contexts");
+    EDS_REQUIRE(ctx, slot >= 0 && slot < frames->capacity, "tracker_evaluate: frame slot out of range");
+    EDS_REQUIRE(ctx, frames->H == kf->dev.H && frames->W == kf->dev.W, "tracker_evaluate: keyframe and event frame sizes differ");
+    DeviceGuard g(ctx->device);
+    const size_t N = (size_t)kf->dev.N;
+    // scratch: desc | state(14) | eval_out(157) | jac (N*12 float) | widened doubles (N*12)
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_desc = take(sizeof(ProblemDesc)), o_state = take(14 * 8), o_eval = take(157 * 8), o_info = take(sizeof(edsgpu_tracker_info));
+    const size_t o_jac = take(N * 12 * sizeof(float)), o_wide = take(N * 12 * sizeof(double));
+    edsgpu_status st = edsgpu_ensure_scratch(ctx, off);
+    if (st == EDSGPU_OK) st = edsgpu_ensure_pinned(ctx, sizeof(ProblemDesc) + 14 * 8 + 157 * 8);
+    if (st != EDSGPU_OK) return st;
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    char* ds = (char*)ctx->scratch;
+    char* hp = (char*)ctx->pinned;
+    ProblemDesc* hd = (ProblemDesc*)hp;
+    double* hstate = (double*)(hp + sizeof(ProblemDesc));
+    memset(hd, 0, sizeof(ProblemDesc));
+    hd->kf = kf->dev;
+    hd->frame = frames->frame + (size_t)slot * frames->H * frames->W;
+    hd->norms = frames->norms + 2 * slot;
+    hd->state = (double*)(ds + o_state);
+    hd->residuals = kf->residuals;
+    hd->info = (edsgpu_tracker_info*)(ds + o_info);
+    hd->loss_type = loss_type;
+    hd->eval_only = 1;
+    hd->jac_out = jacobian_out ? (float*)(ds + o_jac) : nullptr;
+    hd->eval_out = (double*)(ds + o_eval);
+    memcpy(hstate, px, 24); memcpy(hstate + 3, qx, 32); memcpy(hstate + 7, vx, 48);
+    hstate[13] = loss_param;
+    EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_desc, hd, sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
+    EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_state, hstate, 14 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int csize = pick_cluster(ctx, 1, kf->dev.B);
+    st = launch_cluster(ctx, track_eval_kernel, (const ProblemDesc*)(ds + o_desc), 1, csize);
+    if (st != EDSGPU_OK) return st;
+    double* hev = (double*)(hp + sizeof(ProblemDesc) + 14 * 8);
+    EDS_CUDA(ctx, cudaMemcpyAsync(hev, ds + o_eval, 157 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (residuals_out) {
+        float_to_double_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(kf->residuals, (double*)(ds + o_wide), N);
+        ctx->launches++;
+        EDS_CUDA(ctx, cudaMemcpyAsync(residuals_out, ds + o_wide, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (jacobian_out) {
+        float_to_double_kernel<<<(unsigned)((N * 12 + 255) / 256), 256, 0, ctx->stream>>>((const float*)(ds + o_jac), (double*)(ds + o_wide), N * 12);
+        ctx->launches++;
+        EDS_CUDA(ctx, cudaMemcpyAsync(jacobian_out, ds + o_wide, N * 12 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (cost_out) *cost_out = hev[0];
+    if (H_out) memcpy(H_out, hev + 1, 144 * 8);
+    if (g_out) memcpy(g_out, hev + 145, 12 * 8);
+    return EDSGPU_OK;
+}
+
+}  // extern "C"

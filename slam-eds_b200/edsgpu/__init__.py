@@ -1,0 +1,312 @@
+"""ctypes binding of libedsgpu.so plus thin Python mirrors of the reference classes.
+
+`EventFrame.create`, `Tracker.optimize` keep the reference method names and argument
+meaning (src/tracking/EventFrame.hpp:83-85, src/tracking/Tracker.hpp:73-81); everything
+below them is the C ABI of include/edsgpu.h.  There is no CPU fallback: if the shared
+library or a CUDA device is missing, `load()` / `Context()` raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG), "libedsgpu.so")
+_lib = None
+
+OK, INVALID_ARGUMENT, CUDA_ERROR, NOT_USABLE, NON_MONOTONIC_TIME, OUT_OF_MEMORY = range(6)
+DRAW_NN, DRAW_BILINEAR = 0, 1
+LOSS_NONE, LOSS_HUBER, LOSS_CAUCHY = 0, 1, 2
+LOSS_PARAM_CONSTANT, LOSS_PARAM_MAD, LOSS_PARAM_STD = 0, 1, 2
+TERM_CONVERGENCE, TERM_NO_CONVERGENCE, TERM_FAILURE = 0, 1, 2
+ACC_FRACTION_BITS = 40
+
+# every symbol include/edsgpu.h declares (tests check that the library exports them all)
+SYMBOLS = [
+    "edsgpu_version", "edsgpu_create", "edsgpu_destroy", "edsgpu_last_error_string", "edsgpu_synchronize",
+    "edsgpu_launch_count", "edsgpu_lut_create", "edsgpu_lut_destroy", "edsgpu_frames_create", "edsgpu_frames_destroy",
+    "edsgpu_event_frame_create", "edsgpu_event_frame_create_batch", "edsgpu_event_frame_create_batch_dev",
+    "edsgpu_frames_read", "edsgpu_frames_read_accumulator", "edsgpu_keyframe_create", "edsgpu_keyframe_destroy",
+    "edsgpu_tracker_create", "edsgpu_tracker_destroy", "edsgpu_tracker_set_state", "edsgpu_tracker_get_state",
+    "edsgpu_tracker_optimize", "edsgpu_trackers_optimize_batch", "edsgpu_trackers_gather", "edsgpu_tracker_state_dev",
+    "edsgpu_tracker_evaluate",
+]
+
+
+class EdsGpuError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("edsgpu status %d: %s" % (status, msg))
+        self.status = status
+
+
+class TrackerConfig(C.Structure):
+    _fields_ = [("num_blocks", C.c_int), ("loss_type", C.c_int), ("max_iterations", C.c_int),
+                ("loss_param_method", C.c_int), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double)]
+
+
+class TrackerInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("successful_steps", C.c_int), ("unsuccessful_steps", C.c_int),
+                ("termination", C.c_int), ("usable", C.c_int), ("num_points", C.c_int),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("final_radius", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def load():
+    """Load libedsgpu.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libedsgpu.so not built: run `make -C slam-eds_b200` (or __graft_entry__.build())")
+        lib = C.CDLL(LIB_PATH)
+        lib.edsgpu_version.restype = C.c_char_p
+        lib.edsgpu_last_error_string.restype = C.c_char_p
+        lib.edsgpu_last_error_string.argtypes = [C.c_void_p]
+        lib.edsgpu_launch_count.restype = C.c_int64
+        lib.edsgpu_launch_count.argtypes = [C.c_void_p]
+        lib.edsgpu_tracker_state_dev.restype = C.c_void_p
+        lib.edsgpu_tracker_state_dev.argtypes = [C.c_void_p]
+        for name in ("edsgpu_destroy", "edsgpu_lut_destroy", "edsgpu_frames_destroy", "edsgpu_keyframe_destroy",
+                     "edsgpu_tracker_destroy"):
+            getattr(lib, name).restype = None
+            getattr(lib, name).argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+class Context:
+    """edsgpu_ctx: one device + one stream."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.edsgpu_create(C.c_int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if st != OK:
+            raise EdsGpuError(st, "edsgpu_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def check(self, st):
+        if st != OK:
+            raise EdsGpuError(st, self.lib.edsgpu_last_error_string(self.h).decode())
+
+    def synchronize(self):
+        self.check(self.lib.edsgpu_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.edsgpu_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.edsgpu_destroy(self.h)
+            self.h = None
+
+
+class Lut:
+    def __init__(self, ctx, H, W, mapx=None, mapy=None):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        mx = np.ascontiguousarray(mapx, np.float32) if mapx is not None else None
+        my = np.ascontiguousarray(mapy, np.float32) if mapy is not None else None
+        ctx.check(ctx.lib.edsgpu_lut_create(ctx.h, C.c_int(H), C.c_int(W), _ptr(mx, C.c_float), _ptr(my, C.c_float),
+                                            C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.edsgpu_lut_destroy(self.h)
+            self.h = None
+
+
+class Frames:
+    """A bank of device event frames (EventFrame::event_frame[0] of several windows)."""
+
+    def __init__(self, ctx, H, W, capacity=1):
+        self.ctx, self.H, self.W, self.capacity = ctx, H, W, capacity
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.edsgpu_frames_create(ctx.h, C.c_int(H), C.c_int(W), C.c_int(capacity), C.byref(self.h)))
+
+    def read(self, slot=0):
+        img = np.zeros((self.H, self.W), np.float64)
+        norm = C.c_double(0)
+        self.ctx.check(self.ctx.lib.edsgpu_frames_read(self.ctx.h, self.h, C.c_int(slot), _ptr(img, C.c_double),
+                                                       C.byref(norm)))
+        return img, norm.value
+
+    def read_accumulator(self, slot=0):
+        acc = np.zeros((self.H, self.W), np.int64)
+        self.ctx.check(self.ctx.lib.edsgpu_frames_read_accumulator(self.ctx.h, self.h, C.c_int(slot), _ptr(acc, C.c_int64)))
+        return acc
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.edsgpu_frames_destroy(self.h)
+            self.h = None
+
+
+class EventFrame:
+    """Mirror of eds::tracking::EventFrame (EventFrame.hpp:31-107) for pyramid level 0.
+
+    create() fills `norm`, `time`, `delta_time` and (on request) `event_frame`, like the public
+    members of the reference class (EventFrame.hpp:41,57-61); the frame itself stays in `frames[slot]`.
+    """
+
+    def __init__(self, ctx, H, W, mapx=None, mapy=None, frames=None, slot=0):
+        self.ctx, self.H, self.W = ctx, H, W
+        self.lut = Lut(ctx, H, W, mapx, mapy) if mapx is not None else None
+        self.frames = frames or Frames(ctx, H, W, 1)
+        self.slot = slot
+        self.norm = self.time = self.delta_time = None
+        self.event_frame = None
+
+    def create(self, x, y, polarity, ts_us=None, mode=DRAW_BILINEAR, use_exp_weights=True, sigma=0.5, want_host_frame=False):
+        x = np.ascontiguousarray(x, np.uint16)
+        y = np.ascontiguousarray(y, np.uint16)
+        p = np.ascontiguousarray(polarity, np.uint8)
+        ts = np.ascontiguousarray(ts_us, np.int64) if ts_us is not None else None
+        norm, t, d = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        host = np.zeros((self.H, self.W), np.float64) if want_host_frame else None
+        self.ctx.check(self.ctx.lib.edsgpu_event_frame_create(
+            self.ctx.h, self.frames.h, C.c_int(self.slot), self.lut.h if self.lut else None, _ptr(x, C.c_uint16),
+            _ptr(y, C.c_uint16), _ptr(p, C.c_uint8), _ptr(ts, C.c_int64), C.c_int(len(x)), C.c_int(mode),
+            C.c_int(int(use_exp_weights)), C.c_float(sigma), C.byref(norm), C.byref(t), C.byref(d), _ptr(host, C.c_double)))
+        self.norm, self.time, self.delta_time, self.event_frame = norm.value, t.value, d.value, host
+        return self
+
+
+class KeyFrame:
+    """Device copy of the KeyFrame arrays the tracker gathers (KeyFrame.hpp:59-96)."""
+
+    def __init__(self, ctx, kf, num_blocks):
+        self.ctx = ctx
+        self.N = len(kf["idp"])
+        self.num_blocks = num_blocks
+        g = np.ascontiguousarray(kf["grad"], np.float64)
+        nc = np.ascontiguousarray(kf["norm_coord"], np.float64)
+        idp = np.ascontiguousarray(kf["idp"], np.float64)
+        w = np.ascontiguousarray(kf["weights"], np.float64)
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.edsgpu_keyframe_create(ctx.h, C.c_int(self.N), _ptr(g, C.c_double), _ptr(nc, C.c_double),
+                                                 _ptr(idp, C.c_double), _ptr(w, C.c_double), C.c_int(kf["H"]), C.c_int(kf["W"]),
+                                                 C.c_double(kf["fx"]), C.c_double(kf["fy"]), C.c_double(kf["cx"]),
+                                                 C.c_double(kf["cy"]), C.c_int(num_blocks), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.edsgpu_keyframe_destroy(self.h)
+            self.h = None
+
+
+class Tracker:
+    """Mirror of eds::tracking::Tracker (Tracker.hpp:36-114): optimize() + state accessors."""
+
+    def __init__(self, ctx, num_blocks=8, loss_type=LOSS_HUBER, loss_param=0.05, max_iterations=30,
+                 function_tolerance=1e-6, gradient_tolerance=1e-8, parameter_tolerance=1e-6,
+                 loss_param_method=LOSS_PARAM_MAD):
+        self.ctx = ctx
+        self.cfg = TrackerConfig(num_blocks, loss_type, max_iterations, loss_param_method, function_tolerance,
+                                 gradient_tolerance, parameter_tolerance)
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.edsgpu_tracker_create(ctx.h, C.byref(self.cfg), C.c_double(loss_param), C.byref(self.h)))
+        self.info = None
+
+    def set_state(self, px=None, qx=None, vx=None, loss_param=None):
+        arrs = [np.ascontiguousarray(a, np.float64) if a is not None else None for a in (px, qx, vx)]
+        lp = C.c_double(loss_param) if loss_param is not None else None
+        self.ctx.check(self.ctx.lib.edsgpu_tracker_set_state(self.h, *[_ptr(a, C.c_double) for a in arrs],
+                                                             C.byref(lp) if lp is not None else None))
+
+    def get_state(self):
+        px, qx, vx = np.zeros(3), np.zeros(4), np.zeros(6)
+        lp = C.c_double(0)
+        info = TrackerInfo()
+        self.ctx.check(self.ctx.lib.edsgpu_tracker_get_state(self.h, _ptr(px, C.c_double), _ptr(qx, C.c_double),
+                                                             _ptr(vx, C.c_double), C.byref(lp), C.byref(info)))
+        return px, qx, vx, lp.value, info.as_dict()
+
+    def optimize(self, kf, frames, slot=0, want_residuals=False):
+        """bool Tracker::optimize(id, event_frame, T_kf_ef, MAD) (Tracker.cpp:104-241).
+        Returns dict(usable, px, qx, vx, residuals, next_loss_param, info)."""
+        px, qx, vx = np.zeros(3), np.zeros(4), np.zeros(6)
+        res = np.zeros(kf.N) if want_residuals else None
+        tau = C.c_double(0)
+        info = TrackerInfo()
+        st = self.ctx.lib.edsgpu_tracker_optimize(self.h, kf.h, frames.h, C.c_int(slot), _ptr(px, C.c_double),
+                                                  _ptr(qx, C.c_double), _ptr(vx, C.c_double), _ptr(res, C.c_double),
+                                                  C.byref(tau), C.byref(info))
+        if st not in (OK, NOT_USABLE):
+            self.ctx.check(st)
+        self.info = info.as_dict()
+        return dict(usable=(st == OK), px=px, qx=qx, vx=vx, x=np.concatenate([px, qx, vx]), residuals=res,
+                    next_loss_param=tau.value, info=self.info)
+
+    def state_dev_ptr(self):
+        return int(self.ctx.lib.edsgpu_tracker_state_dev(self.h))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.edsgpu_tracker_destroy(self.h)
+            self.h = None
+
+
+def event_frames_batch(ctx, frames, first_slot, count, x, y, pol, num_events, lut=None, mode=DRAW_BILINEAR,
+                       use_exp_weights=True, sigma=0.5, want_norms=False):
+    """Host arrays (count*num_events) -> `count` device frames (edsgpu_event_frame_create_batch)."""
+    norms = np.zeros(count) if want_norms else None
+    ctx.check(ctx.lib.edsgpu_event_frame_create_batch(
+        ctx.h, frames.h, C.c_int(first_slot), C.c_int(count), lut.h if lut else None, _ptr(x, C.c_uint16),
+        _ptr(y, C.c_uint16), _ptr(pol, C.c_uint8), C.c_int(num_events), C.c_int(mode), C.c_int(int(use_exp_weights)),
+        C.c_float(sigma), _ptr(norms, C.c_double)))
+    return norms
+
+
+def event_frames_batch_dev(ctx, frames, first_slot, count, x_ptr, y_ptr, pol_ptr, num_events, lut=None,
+                           mode=DRAW_BILINEAR, use_exp_weights=True, sigma=0.5):
+    """Device pointers (ints) -> `count` device frames, asynchronous."""
+    ctx.check(ctx.lib.edsgpu_event_frame_create_batch_dev(
+        ctx.h, frames.h, C.c_int(first_slot), C.c_int(count), lut.h if lut else None, C.c_void_p(x_ptr),
+        C.c_void_p(y_ptr), C.c_void_p(pol_ptr), C.c_int(num_events), C.c_int(mode), C.c_int(int(use_exp_weights)),
+        C.c_float(sigma)))
+
+
+class TrackerBatch:
+    """`count` independent trackers advanced by one launch (edsgpu_trackers_optimize_batch)."""
+
+    def __init__(self, ctx, trackers, keyframes):
+        self.ctx, self.trackers, self.keyframes = ctx, trackers, keyframes
+        n = len(trackers)
+        self._tr = (C.c_void_p * n)(*[t.h for t in trackers])
+        self._kf = (C.c_void_p * n)(*[k.h for k in keyframes])
+        self.count = n
+
+    def optimize(self, frames, first_slot=0):
+        self.ctx.check(self.ctx.lib.edsgpu_trackers_optimize_batch(self.ctx.h, self._tr, self._kf, C.c_int(self.count),
+                                                                   frames.h, C.c_int(first_slot)))
+
+    def gather(self, want_infos=True):
+        states = np.zeros((self.count, 14))
+        infos = (TrackerInfo * self.count)() if want_infos else None
+        self.ctx.check(self.ctx.lib.edsgpu_trackers_gather(self.ctx.h, self._tr, C.c_int(self.count),
+                                                           _ptr(states, C.c_double), infos))
+        return states, ([i.as_dict() for i in infos] if want_infos else None)
+
+
+def tracker_evaluate(ctx, kf, frames, slot, x, loss_type=LOSS_HUBER, loss_param=0.05, want_jacobian=True):
+    """ceres::CostFunction::Evaluate-style probe (edsgpu_tracker_evaluate)."""
+    x = np.ascontiguousarray(x, np.float64)
+    px, qx, vx = x[:3].copy(), x[3:7].copy(), x[7:].copy()
+    res = np.zeros(kf.N)
+    jac = np.zeros((kf.N, 12)) if want_jacobian else None
+    cost = C.c_double(0)
+    H, g = np.zeros((12, 12)), np.zeros(12)
+    ctx.check(ctx.lib.edsgpu_tracker_evaluate(ctx.h, kf.h, frames.h, C.c_int(slot), C.c_int(loss_type), C.c_double(loss_param),
+                                              _ptr(px, C.c_double), _ptr(qx, C.c_double), _ptr(vx, C.c_double),
+                                              _ptr(res, C.c_double), _ptr(jac, C.c_double), C.byref(cost),
+                                              _ptr(H, C.c_double), _ptr(g, C.c_double)))
+    return dict(residuals=res, jacobian=jac, cost=cost.value, H=H, g=g)
