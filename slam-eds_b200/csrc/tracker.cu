@@ -39,6 +39,11 @@ constexpr int MAX_CLUSTER = 8;
 constexpr double kEps = 1e-05;  // PhotometricError.hpp:200
 
 enum { CMD_EVAL = 1, CMD_FINAL = 2, CMD_DONE = 3 };
+
+#ifdef EDS_TIMING
+__device__ unsigned long long g_timing[16];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
 enum { PHASE_INIT = 0, PHASE_CAND = 1 };
 
 struct KfDev {
@@ -127,31 +132,39 @@ __host__ __device__ __forceinline__ int tri_index(int a, int b) {  // a <= b < 1
 // shared-memory layout of one CTA
 // ------------------------------------------------------------------------------------------
 struct LmState {
-    double x[13], cand[13];
-    double H[78], g[12];      // at x, un-scaled
-    double Hs[78], gs[12];    // Jacobi-scaled
+    double x[13], cand[13], delta[12];
+    double Hs[78], gs[12];    // Jacobi-scaled normal equations at x
     double scale[12], diag[12];
-    double x_cost, cand_cost, mcc, radius, dec, gmax, x_norm, initial_cost;
+    double x_cost, mcc, radius, dec, gmax, x_norm, initial_cost;
     int reuse_diag, iter, n_succ, n_unsucc, consec_invalid, termination, phase;
 };
 
-struct CtaShared {
-    // published by the leader into every CTA before sync (A)
-    double x_eval[13];
+// Everything a CTA needs for one evaluation; written by the leader into every CTA of the
+// cluster (DSMEM) before sync (A).
+struct EvalConst {
+    double R[9], t[3];               // Eigen toRotationMatrix(q), translation
+    float vf[6], inv_vs, inv_vn;     // velocity, 1/|v|^2, 1/|v|
+    float blk[MAX_BLOCKS][8];        // per residual block: 1/M, c/M^3 (6), pad
     int cmd;
-    // per-evaluation constants derived from x_eval
-    double R[9], t[3];
-    float vf[6], inv_vs, inv_vn;
-    // per residual block
-    float invM, cM3[6];
-    // reduction scratch
-    double warp_part[TRK_WARPS][NACC];
-    double warp_s[TRK_WARPS];
-    // leader only: one slot per residual block, filled over DSMEM
-    double slots[MAX_BLOCKS][NSLOT];
+};
+
+struct CtaShared {
+    EvalConst ec;
+    // reduction scratch, double-buffered over residual blocks
+    double warp_part[2][TRK_WARPS][NACC];
+    double warp_s[2][TRK_WARPS];
+    double loss_a;
+    // leader only
+    double slots[MAX_BLOCKS][NSLOT];  // one slot per residual block, filled over DSMEM
     double sum[NSLOT];
+    double A[MAX_BLOCKS][21];         // per-block model Gram matrices
+    double x_eval[13];
     LmState lm;
 };
+
+// (a,b) of packed upper-triangle entry e (row-major, a <= b < 12)
+__constant__ unsigned char c_tri_a[78] = {0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,1,1,1,2,2,2,2,2,2,2,2,2,2,3,3,3,3,3,3,3,3,3,4,4,4,4,4,4,4,4,5,5,5,5,5,5,5,6,6,6,6,6,6,7,7,7,7,7,8,8,8,8,9,9,9,10,10,11};
+__constant__ unsigned char c_tri_b[78] = {0,1,2,3,4,5,6,7,8,9,10,11,1,2,3,4,5,6,7,8,9,10,11,2,3,4,5,6,7,8,9,10,11,3,4,5,6,7,8,9,10,11,4,5,6,7,8,9,10,11,5,6,7,8,9,10,11,6,7,8,9,10,11,7,8,9,10,11,8,9,10,11,9,10,11,10,11,11};
 
 // ------------------------------------------------------------------------------------------
 // per-point residual + analytic tangent-space Jacobian
@@ -172,8 +185,8 @@ __device__ __forceinline__ float cubic_hermite_f(float p0, float p1, float p2, f
 }
 
 template <bool WANT_J>
-__device__ __forceinline__ void eval_point(const KfDev& kf, const CtaShared& sh, const float* __restrict__ frame, float inv_norm,
-                                           int idx, float* __restrict__ J, float& r) {
+__device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, const float* __restrict__ bc /* 1/M, c/M^3 */,
+                                           const float* __restrict__ frame, float inv_norm, int idx, float* __restrict__ J, float& r) {
     const float4 g4 = __ldg(&kf.gxy[idx]);
     const float2 dw = __ldg(&kf.dw[idx]);
     const double kx = __ldg(&kf.kpx[idx]), ky = __ldg(&kf.kpy[idx]), kz = __ldg(&kf.kpz[idx]);
@@ -188,13 +201,13 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const CtaShared& sh,
     g[5] = Gy * X - Gx * Y;
     float m = 0.f;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) m += g[k] * sh.vf[k];
+    for (int k = 0; k < 6; ++k) m += g[k] * K.vf[k];
     // warp + projection in fp64 (PhotometricError.hpp:157-168): the pixel coordinate must not
     // carry fp32 rounding (1.5e-5 px at |u| ~ 256), SURVEY.md section 7.
-    const double ax = sh.R[0] * kx + sh.R[1] * ky + sh.R[2] * kz;
-    const double ay = sh.R[3] * kx + sh.R[4] * ky + sh.R[5] * kz;
-    const double az = sh.R[6] * kx + sh.R[7] * ky + sh.R[8] * kz;
-    const double px = ax + sh.t[0], py = ay + sh.t[1], pz = az + sh.t[2];
+    const double ax = K.R[0] * kx + K.R[1] * ky + K.R[2] * kz;
+    const double ay = K.R[3] * kx + K.R[4] * ky + K.R[5] * kz;
+    const double az = K.R[6] * kx + K.R[7] * ky + K.R[8] * kz;
+    const double px = ax + K.t[0], py = ay + K.t[1], pz = az + K.t[2];
     const double iz = 1.0 / pz;
     double u = kf.fx * (px * iz) + kf.cx;
     double v = kf.fy * (py * iz) + kf.cy;
@@ -218,7 +231,7 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const CtaShared& sh,
     cubic_hermite(fr[0], fr[1], fr[2], fr[3], tr, f, dfdr);
     const float dfdc = cubic_hermite_f(dfc[0], dfc[1], dfc[2], dfc[3], tr);
     const float e = inv_norm * f, er = inv_norm * dfdr, ec = inv_norm * dfdc;
-    r = w * (m * sh.invM - e);  // PhotometricError.hpp:173
+    r = w * (m * bc[0] - e);  // PhotometricError.hpp:173
     if (!WANT_J) return;
     // d r / d P  (P = R kp + t)
     const float izf = (float)iz, fxf = (float)kf.fx, fyf = (float)kf.fy;
@@ -235,10 +248,10 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const CtaShared& sh,
     // velocity: d r/d v = w (g/M - m c/M^3), then the unit-norm Plus Jacobian (I - v v^T/s)/|v|
     float jv[6], dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { jv[k] = w * (g[k] * sh.invM - m * sh.cM3[k]); dot += jv[k] * sh.vf[k]; }
-    const float dn = dot * sh.inv_vs;
+    for (int k = 0; k < 6; ++k) { jv[k] = w * (g[k] * bc[0] - m * bc[1 + k]); dot += jv[k] * K.vf[k]; }
+    const float dn = dot * K.inv_vs;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) J[6 + k] = (jv[k] - dn * sh.vf[k]) * sh.inv_vn;
+    for (int k = 0; k < 6; ++k) J[6 + k] = (jv[k] - dn * K.vf[k]) * K.inv_vn;
 }
 
 // halving butterfly: 96 per-lane values -> 3 warp-reduced values per lane.
@@ -257,52 +270,27 @@ __device__ __forceinline__ int butterfly_base(unsigned lane) {
     return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
 }
 
-// One CTA evaluates the residual blocks dealt to it at sh.x_eval and stores, per block,
-// [rho' * JtJ (78) | rho' * Jtr (12) | 0.5 rho(s) | s] into slot_dst[b] (leader smem via DSMEM).
+// One CTA evaluates the residual blocks dealt to it with the constants in sh.ec and stores, per
+// block, [rho' * JtJ (78) | rho' * Jtr (12) | 0.5 rho(s) | s] into slot_base[b] (leader smem, DSMEM).
 template <bool RES_ONLY>
 __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_base /* [MAX_BLOCKS][NSLOT] on the leader */,
                              int rank, int csize, bool write_residuals) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const KfDev& kf = P.kf;
-    if (tid == 0) {
-        quat_to_rot(&sh.x_eval[3], sh.R);
-        sh.t[0] = sh.x_eval[0]; sh.t[1] = sh.x_eval[1]; sh.t[2] = sh.x_eval[2];
-        double s = 0.0;
-        for (int k = 0; k < 6; ++k) { s += sh.x_eval[7 + k] * sh.x_eval[7 + k]; sh.vf[k] = (float)sh.x_eval[7 + k]; }
-        sh.inv_vs = (float)(1.0 / s);
-        sh.inv_vn = (float)(1.0 / sqrt(s));
-    }
+    const EvalConst& ec = sh.ec;
     const float inv_norm = (float)P.norms[1];
-    const double loss_a = P.state[13];
+    const double loss_a = sh.loss_a;
     const int ne = kf.N / kf.B;
-    for (int b = rank; b < kf.B; b += csize) {
-        __syncthreads();  // x_eval-derived constants ready; previous block's scratch consumed
-        if (tid == 0) {
-            // S = 1e-3 + v^T A v (PhotometricError.hpp:132,148), c = A v
-            const double* A = kf.A + 21 * b;
-            const double* v = &sh.x_eval[7];
-            double c[6] = {0, 0, 0, 0, 0, 0};
-            int k = 0;
-            for (int i = 0; i < 6; ++i)
-                for (int j = i; j < 6; ++j, ++k) {
-                    c[i] += A[k] * v[j];
-                    if (j != i) c[j] += A[k] * v[i];
-                }
-            double S = 1e-03;
-            for (int i = 0; i < 6; ++i) S += v[i] * c[i];
-            const double M = sqrt(S);
-            sh.invM = (float)(1.0 / M);
-            const double iM3 = 1.0 / (M * S);
-            for (int i = 0; i < 6; ++i) sh.cM3[i] = (float)(c[i] * iM3);
-        }
-        __syncthreads();
+    int buf = 0;
+    for (int b = rank; b < kf.B; b += csize, buf ^= 1) {
+        const float* bc = ec.blk[b];
         const int start = b * ne;
         const int n = ne + ((b + 1 == kf.B) ? (kf.N - (b + 1) * ne) : 0);  // Tracker.cpp:178-190
         if constexpr (RES_ONLY) {
             // residual write-back only (Tracker.cpp:223-230): no Jacobian, no reduction, no DSMEM traffic
             for (int i = tid; i < n; i += TRK_THREADS) {
                 float r;
-                eval_point<false>(kf, sh, P.frame, inv_norm, start + i, nullptr, r);
+                eval_point<false>(kf, ec, bc, P.frame, inv_norm, start + i, nullptr, r);
                 P.residuals[start + i] = r;
             }
             continue;
@@ -313,7 +301,7 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
         double s_acc = 0.0;
         for (int i = tid; i < n; i += TRK_THREADS) {
             float J[12], r;
-            eval_point<true>(kf, sh, P.frame, inv_norm, start + i, J, r);
+            eval_point<true>(kf, ec, bc, P.frame, inv_norm, start + i, J, r);
             if (write_residuals) {
                 P.residuals[start + i] = r;
                 if (P.jac_out) {
@@ -336,26 +324,28 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
         butterfly_step<6, 2>(acc, lane);
         butterfly_step<3, 1>(acc, lane);
         const int base = butterfly_base(lane);
-        sh.warp_part[warp][base] = (double)acc[0];
-        sh.warp_part[warp][base + 1] = (double)acc[1];
-        sh.warp_part[warp][base + 2] = (double)acc[2];
+        sh.warp_part[buf][warp][base] = (double)acc[0];
+        sh.warp_part[buf][warp][base + 1] = (double)acc[1];
+        sh.warp_part[buf][warp][base + 2] = (double)acc[2];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
-        if (lane == 0) sh.warp_s[warp] = s_acc;
-        __syncthreads();
+        if (lane == 0) sh.warp_s[buf][warp] = s_acc;
+        __syncthreads();  // one barrier per block: scratch is double-buffered
         if (tid < NSLOT) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < TRK_WARPS; ++w) s += sh.warp_s[w];
-            double rho0, rho1;
-            loss_eval(P.loss_type, loss_a, s, &rho0, &rho1);
+            for (int w = 0; w < TRK_WARPS; ++w) s += sh.warp_s[buf][w];
             double val;
             if (tid < 90) {
                 double t = 0.0;
 #pragma unroll
-                for (int w = 0; w < TRK_WARPS; ++w) t += sh.warp_part[w][tid];
+                for (int w = 0; w < TRK_WARPS; ++w) t += sh.warp_part[buf][w][tid];
+                double rho0, rho1;
+                loss_eval(P.loss_type, loss_a, s, &rho0, &rho1);
                 val = rho1 * t;
             } else if (tid == 90) {
+                double rho0, rho1;
+                loss_eval(P.loss_type, loss_a, s, &rho0, &rho1);
                 val = 0.5 * rho0;
             } else {
                 val = s;
@@ -369,133 +359,253 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
 // leader: Levenberg-Marquardt state machine (ceres TrustRegionMinimizer +
 // LevenbergMarquardtStrategy semantics; options of Tracker.cpp:117-143)
 // ------------------------------------------------------------------------------------------
-__device__ bool chol_solve12(const double* Hs /*78*/, const double* add_diag, const double* rhs, double* y) {
-    double L[78];  // lower triangle, row-major packed: L[i*(i+1)/2 + j]
-    for (int j = 0; j < 12; ++j) {
-        double dsum = Hs[tri_index(j, j)] + add_diag[j];
-        for (int k = 0; k < j; ++k) dsum -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-        if (!(dsum > 0.0) || !isfinite(dsum)) return false;
-        const double ljj = sqrt(dsum);
-        L[j * (j + 1) / 2 + j] = ljj;
-        const double inv = 1.0 / ljj;
-        for (int i = j + 1; i < 12; ++i) {
-            double s = Hs[tri_index(j, i)];
-            for (int k = 0; k < j; ++k) s -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-            L[i * (i + 1) / 2 + j] = s * inv;
-        }
-    }
-    double z[12];
-    for (int i = 0; i < 12; ++i) {
-        double s = rhs[i];
-        for (int k = 0; k < i; ++k) s -= L[i * (i + 1) / 2 + k] * z[k];
-        z[i] = s / L[i * (i + 1) / 2 + i];
-    }
-    for (int i = 11; i >= 0; --i) {
-        double s = z[i];
-        for (int k = i + 1; k < 12; ++k) s -= L[k * (k + 1) / 2 + i] * y[k];
-        y[i] = s / L[i * (i + 1) / 2 + i];
-    }
-    for (int i = 0; i < 12; ++i) if (!isfinite(y[i])) return false;
-    return true;
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
 }
 
-__device__ void lm_take_evaluation(LmState& lm, const double* Hsum, const double* gsum, double cost, bool first) {
-    lm.x_cost = cost;
-    for (int i = 0; i < 78; ++i) lm.H[i] = Hsum[i];
-    for (int i = 0; i < 12; ++i) lm.g[i] = gsum[i];
-    if (first)  // jacobi_scaling: computed at iteration 0 only
-        for (int i = 0; i < 12; ++i) lm.scale[i] = 1.0 / (1.0 + sqrt(lm.H[tri_index(i, i)]));
-    for (int a = 0; a < 12; ++a) {
-        lm.gs[a] = lm.g[a] * lm.scale[a];
-        for (int b = a; b < 12; ++b) lm.Hs[tri_index(a, b)] = lm.H[tri_index(a, b)] * lm.scale[a] * lm.scale[b];
+// Leader warp: publish the evaluation constants of point xe (13 doubles in leader smem) and the
+// command to every CTA of the cluster.  Lane b derives the per-block model normalisation
+// S_b = 1e-3 + v^T A_b v (PhotometricError.hpp:132,148) and c_b = A_b v.
+__device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, const double* xe, int cmd, int B, int csize) {
+    const int lane = threadIdx.x;
+    EvalConst& ec = sh.ec;  // build locally, then replicate
+    if (lane == 0) {
+        quat_to_rot(&xe[3], ec.R);
+        ec.t[0] = xe[0]; ec.t[1] = xe[1]; ec.t[2] = xe[2];
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) { s += xe[7 + k] * xe[7 + k]; ec.vf[k] = (float)xe[7 + k]; }
+        ec.inv_vs = (float)(1.0 / s);
+        ec.inv_vn = (float)rsqrt(s);
+        ec.cmd = cmd;
     }
-    // gradient_max_norm = || x - Plus(x, -g) ||_inf
-    double ng[12], xp[13];
-    for (int i = 0; i < 12; ++i) ng[i] = -lm.g[i];
-    state_plus(lm.x, ng, xp);
-    double m = 0.0;
-    for (int i = 0; i < 13; ++i) m = fmax(m, fabs(lm.x[i] - xp[i]));
-    lm.gmax = m;
-    double s = 0.0;
-    for (int i = 0; i < 13; ++i) s += lm.x[i] * lm.x[i];
-    lm.x_norm = sqrt(s);
+    if (lane < B && cmd != CMD_DONE) {
+        const double* A = sh.A[lane];
+        const double* v = &xe[7];
+        double c[6] = {0, 0, 0, 0, 0, 0};
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j, ++k) {
+                c[i] += A[k] * v[j];
+                if (j != i) c[j] += A[k] * v[i];
+            }
+        double S = 1e-03;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) S += v[i] * c[i];
+        const double iM = rsqrt(S);
+        const double iM3 = iM / S;
+        ec.blk[lane][0] = (float)iM;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ec.blk[lane][1 + i] = (float)(c[i] * iM3);
+        ec.blk[lane][7] = 0.f;
+    }
+    __syncwarp();
+    // replicate the used prefix of EvalConst (R,t,v + B block records) and cmd
+    const int nwords = (int)(offsetof(EvalConst, blk) / 4) + 8 * B;
+    const int* src = reinterpret_cast<const int*>(&ec);
+    for (int c = 1; c < csize; ++c) {
+        EvalConst* dst = &cluster.map_shared_rank(&sh, c)->ec;
+        int* d = reinterpret_cast<int*>(dst);
+        for (int i = lane; i < nwords; i += 32) d[i] = src[i];
+        if (lane == 0) dst->cmd = cmd;
+    }
 }
 
-// returns the next command; when CMD_EVAL, lm.cand holds the point to evaluate
-__device__ int lm_advance(const ProblemDesc& P, LmState& lm, const double* Hsum, const double* gsum, double cost) {
-    bool finite_eval = isfinite(cost);
-    for (int i = 0; i < 78 && finite_eval; ++i) finite_eval = isfinite(Hsum[i]);
-    for (int i = 0; i < 12 && finite_eval; ++i) finite_eval = isfinite(gsum[i]);
+// Leader warp (32 lanes, convergent): consume one evaluation and decide what to do next.
+// ceres TrustRegionMinimizer + LevenbergMarquardtStrategy semantics (options of
+// Tracker.cpp:117-143); returns the next command, lm.cand / lm.x hold the point to evaluate.
+__device__ int lm_advance_warp(const ProblemDesc& P, CtaShared& sh) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    LmState& lm = sh.lm;
+    const int B = P.kf.B;
+#ifdef EDS_TIMING
+    unsigned long long tt0 = gtime();
+#endif
+    // ordered sum over residual blocks: the result does not depend on the cluster size
+    bool fin = true;
+    for (int e = lane; e < 91; e += 32) {
+        double s = 0.0;
+        for (int b = 0; b < B; ++b) s += sh.slots[b][e];
+        sh.sum[e] = s;
+        fin = fin && isfinite(s);
+    }
+    fin = __all_sync(FULL, fin);
+    __syncwarp();
+#ifdef EDS_TIMING
+    unsigned long long tt1 = gtime();
+#endif
+    const double cost = sh.sum[90];
+    double radius = lm.radius, dec = lm.dec;
+    int reuse = lm.reuse_diag, n_succ = lm.n_succ, n_unsucc = lm.n_unsucc;
+    bool take = false, first = false;
+    int ret = 0;
     if (lm.phase == PHASE_INIT) {
-        lm.initial_cost = cost;
-        if (!finite_eval) { lm.termination = EDSGPU_TERM_FAILURE; lm.x_cost = cost; return CMD_DONE; }
-        lm_take_evaluation(lm, Hsum, gsum, cost, true);
+        if (lane == 0) lm.initial_cost = cost;
+        if (!fin) { if (lane == 0) { lm.termination = EDSGPU_TERM_FAILURE; lm.x_cost = cost; } ret = CMD_DONE; }
+        else { take = true; first = true; }
     } else {
         const double cand_cost = isfinite(cost) ? cost : DBL_MAX;
-        // ParameterToleranceReached
-        double sn = 0.0;
-        for (int i = 0; i < 13; ++i) sn += (lm.x[i] - lm.cand[i]) * (lm.x[i] - lm.cand[i]);
-        sn = sqrt(sn);
-        if (sn <= P.ptol * (lm.x_norm + P.ptol)) { lm.termination = EDSGPU_TERM_CONVERGENCE; return CMD_FINAL; }
-        // FunctionToleranceReached
+        // ParameterToleranceReached: ||x - cand|| <= ptol (||x|| + ptol)
+        double d = (lane < 13) ? lm.x[lane] - lm.cand[lane] : 0.0;
+        const double sn = sqrt(warp_sum(d * d));
         const double cost_change = lm.x_cost - cand_cost;
-        if (fabs(cost_change) <= P.ftol * lm.x_cost) { lm.termination = EDSGPU_TERM_CONVERGENCE; return CMD_FINAL; }
-        const double rel = cost_change / lm.mcc;
-        if (rel > 1e-3) {  // min_relative_decrease
-            if (!finite_eval) { lm.termination = EDSGPU_TERM_FAILURE; return CMD_DONE; }
-            for (int i = 0; i < 13; ++i) lm.x[i] = lm.cand[i];
-            lm_take_evaluation(lm, Hsum, gsum, cost, false);
-            lm.radius = lm.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
-            lm.radius = fmin(1e16, lm.radius);
-            lm.dec = 2.0;
-            lm.reuse_diag = 0;
-            lm.n_succ++;
-        } else {
-            lm.radius = lm.radius / lm.dec;
-            lm.dec *= 2.0;
-            lm.reuse_diag = 1;
-            lm.n_unsucc++;
+        if (sn <= P.ptol * (lm.x_norm + P.ptol)) { if (lane == 0) lm.termination = EDSGPU_TERM_CONVERGENCE; ret = CMD_FINAL; }
+        else if (fabs(cost_change) <= P.ftol * lm.x_cost) { if (lane == 0) lm.termination = EDSGPU_TERM_CONVERGENCE; ret = CMD_FINAL; }  // FunctionToleranceReached
+        else {
+            const double rel = cost_change / lm.mcc;
+            if (rel > 1e-3) {  // min_relative_decrease: HandleSuccessfulStep
+                if (!fin) { if (lane == 0) lm.termination = EDSGPU_TERM_FAILURE; ret = CMD_DONE; }
+                else {
+                    const double t = 2.0 * rel - 1.0;
+                    radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+                    dec = 2.0; reuse = 0; n_succ++;
+                    const double c = (lane < 13) ? lm.cand[lane] : 0.0;
+                    __syncwarp();
+                    if (lane < 13) lm.x[lane] = c;
+                    take = true;
+                }
+            } else { radius = radius / dec; dec *= 2.0; reuse = 1; n_unsucc++; }
         }
     }
-    for (;;) {
-        if (lm.iter >= P.max_iter) { lm.termination = EDSGPU_TERM_NO_CONVERGENCE; return CMD_FINAL; }
-        if (lm.gmax <= P.gtol) { lm.termination = EDSGPU_TERM_CONVERGENCE; return CMD_FINAL; }
-        if (lm.radius < 1e-32) { lm.termination = EDSGPU_TERM_CONVERGENCE; return CMD_FINAL; }
-        lm.iter++;
-        if (!lm.reuse_diag)
-            for (int i = 0; i < 12; ++i) lm.diag[i] = fmin(fmax(lm.Hs[tri_index(i, i)], 1e-6), 1e32);
-        double add[12], y[12], step[12];
-        for (int i = 0; i < 12; ++i) add[i] = lm.diag[i] / lm.radius;
-        bool ok = chol_solve12(lm.Hs, add, lm.gs, y);
-        lm.reuse_diag = 1;
-        double mcc = 0.0;
-        if (ok) {
-            double sg = 0.0, sHs = 0.0;
-            for (int i = 0; i < 12; ++i) step[i] = -y[i];
-            for (int i = 0; i < 12; ++i) {
-                sg += step[i] * lm.gs[i];
-                double hv = 0.0;
-                for (int j = 0; j < 12; ++j) hv += lm.Hs[i <= j ? tri_index(i, j) : tri_index(j, i)] * step[j];
-                sHs += step[i] * hv;
+    __syncwarp();
+    if (take) {
+        // EvaluateGradientAndJacobian: Jacobi scaling (iteration 0 only), scaled system,
+        // gradient max norm || x - Plus(x, -g) ||_inf, ||x||
+        if (first && lane < 12) lm.scale[lane] = 1.0 / (1.0 + sqrt(sh.sum[tri_index(lane, lane)]));
+        __syncwarp();
+        for (int e = lane; e < 78; e += 32) lm.Hs[e] = sh.sum[e] * lm.scale[c_tri_a[e]] * lm.scale[c_tri_b[e]];
+        if (lane < 12) lm.gs[lane] = sh.sum[78 + lane] * lm.scale[lane];
+        double gt = (lane < 3) ? fabs(sh.sum[78 + lane]) : 0.0;
+        double gmax = warp_max(gt);  // translation part of x - Plus(x,-g) is exactly g
+        if (!(gmax > P.gtol)) {
+            // only now can the full projected-gradient norm decide the gradient tolerance test
+            double ng[12], xp[13];
+            for (int i = 0; i < 12; ++i) ng[i] = -sh.sum[78 + i];
+            state_plus(lm.x, ng, xp);
+            for (int i = 0; i < 13; ++i) gmax = fmax(gmax, fabs(lm.x[i] - xp[i]));
+        }
+        const double xv = (lane < 13) ? lm.x[lane] : 0.0;
+        const double xn = sqrt(warp_sum(xv * xv));
+        if (lane == 0) { lm.x_cost = cost; lm.gmax = gmax; lm.x_norm = xn; }
+    }
+    __syncwarp();
+#ifdef EDS_TIMING
+    unsigned long long tt2 = gtime();
+#endif
+    const double gmax_now = lm.gmax;
+    int iter = lm.iter, consec = lm.consec_invalid;
+    double mcc = 0.0;
+    while (ret == 0) {
+        if (iter >= P.max_iter) { if (lane == 0) lm.termination = EDSGPU_TERM_NO_CONVERGENCE; ret = CMD_FINAL; break; }
+        if (gmax_now <= P.gtol) { if (lane == 0) lm.termination = EDSGPU_TERM_CONVERGENCE; ret = CMD_FINAL; break; }
+        if (radius < 1e-32) { if (lane == 0) lm.termination = EDSGPU_TERM_CONVERGENCE; ret = CMD_FINAL; break; }
+        iter++;
+        // LevenbergMarquardtStrategy::ComputeStep: D^2 = clamp(diag(JtJ)) / radius, (JtJ + D^2) y = Jt r
+        if (!reuse && lane < 12) lm.diag[lane] = fmin(fmax(lm.Hs[tri_index(lane, lane)], 1e-6), 1e32);
+        __syncwarp();
+        reuse = 1;
+        // lane i < 12 owns row i of the damped matrix (a) and of the un-damped one (h)
+        double a[12], h[12];
+        const int li = lane < 12 ? lane : 0;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const double v = lm.Hs[li <= j ? tri_index(li, j) : tri_index(j, li)];
+            h[j] = (lane < 12) ? v : 0.0;
+            a[j] = h[j];
+            if (j == lane) a[j] += lm.diag[li] / radius;
+        }
+        // right-looking Cholesky in registers: after step k lane i >= k holds L[i][k] in a[k],
+        // lane k holds L[j][k] (= L^T[k][j]) in a[j], j > k
+        bool ok = true;
+        double myinv = 0.0;
+        // branch-free (selects only): divergent branches around the shuffles would serialise the warp
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const double dk = __shfl_sync(FULL, a[k], k);
+            ok = ok && (dk > 0.0) && (dk < DBL_MAX);
+            const double inv = rsqrt(dk);
+            const double lik = a[k] * inv;
+            myinv = (lane == k) ? inv : myinv;
+            a[k] = (lane >= k) ? lik : a[k];
+#pragma unroll
+            for (int j = k + 1; j < 12; ++j) {
+                const double ljk = __shfl_sync(FULL, lik, j);
+                const double upd = a[j] - lik * ljk;
+                const double scl = a[j] * inv;
+                a[j] = (lane > k) ? upd : ((lane == k) ? scl : a[j]);
             }
-            mcc = -sg - 0.5 * sHs;
+        }
+        // forward L z = gs, backward L^T y = z
+        double z = (lane < 12) ? lm.gs[li] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const double zk = __shfl_sync(FULL, z * myinv, k);
+            const double upd = z - a[k] * zk;
+            z = (lane == k) ? zk : ((lane > k) ? upd : z);
+        }
+#pragma unroll
+        for (int k = 11; k >= 0; --k) {
+            const double yk = __shfl_sync(FULL, z * myinv, k);
+            const double upd = z - a[k] * yk;
+            z = (lane == k) ? yk : ((lane < k) ? upd : z);
+        }
+        const double step = (lane < 12) ? -z : 0.0;
+        ok = ok && __all_sync(FULL, isfinite(step));
+        if (ok) {
+            // model_cost_change = -step^T (gs + 0.5 Hs step)
+            double hv = 0.0;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) hv += h[j] * __shfl_sync(FULL, step, j);
+            const double gsl = (lane < 12) ? lm.gs[li] : 0.0;
+            mcc = -warp_sum(step * (gsl + 0.5 * hv));
             ok = mcc > 0.0;
         }
         if (!ok) {  // HandleInvalidStep
-            if (++lm.consec_invalid >= 5) { lm.termination = EDSGPU_TERM_FAILURE; return CMD_DONE; }
-            lm.radius = lm.radius / lm.dec;
-            lm.dec *= 2.0;
-            lm.n_unsucc++;
+            if (++consec >= 5) { if (lane == 0) lm.termination = EDSGPU_TERM_FAILURE; ret = CMD_DONE; break; }
+            radius = radius / dec; dec *= 2.0; n_unsucc++;
             continue;
         }
-        lm.consec_invalid = 0;
-        lm.mcc = mcc;
-        double delta[12];
-        for (int i = 0; i < 12; ++i) delta[i] = step[i] * lm.scale[i];
-        state_plus(lm.x, delta, lm.cand);
-        lm.phase = PHASE_CAND;
-        return CMD_EVAL;
+        consec = 0;
+        if (lane < 12) lm.delta[lane] = step * lm.scale[lane];
+        __syncwarp();
+#ifdef EDS_TIMING
+        unsigned long long tt3 = gtime();
+#endif
+        if (lane == 0) state_plus(lm.x, lm.delta, lm.cand);
+        ret = CMD_EVAL;
+#ifdef EDS_TIMING
+        if (lane == 0) { g_timing[6] += tt1 - tt0; g_timing[7] += tt2 - tt1; g_timing[8] += tt3 - tt2; g_timing[9] += gtime() - tt3; g_timing[10] += 1; }
+#endif
     }
+    if (lane == 0) {
+        lm.radius = radius; lm.dec = dec; lm.reuse_diag = reuse; lm.n_succ = n_succ; lm.n_unsucc = n_unsucc;
+        lm.iter = iter; lm.consec_invalid = consec; lm.mcc = mcc; lm.phase = PHASE_CAND;
+    }
+    __syncwarp();
+    return ret;
+}
+
+__device__ __forceinline__ void load_problem(ProblemDesc& P, CtaShared& sh, const ProblemDesc* problems, int pid, int rank) {
+    const int tid = threadIdx.x;
+    const int* src = reinterpret_cast<const int*>(&problems[pid]);
+    int* dst = reinterpret_cast<int*>(&P);
+    for (int i = tid; i < (int)(sizeof(ProblemDesc) / sizeof(int)); i += TRK_THREADS) dst[i] = src[i];
+    __syncthreads();
+    if (tid == 0) sh.loss_a = P.state[13];
+    if (rank == 0) {
+        for (int i = tid; i < 21 * P.kf.B; i += TRK_THREADS) (&sh.A[0][0])[i] = P.kf.A[i];
+        if (tid < 13) sh.x_eval[tid] = P.state[tid];
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemDesc* __restrict__ problems) {
@@ -505,70 +615,69 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
     __shared__ CtaShared sh;
     __shared__ ProblemDesc P;
     const int tid = threadIdx.x;
-    {
-        const int* src = reinterpret_cast<const int*>(&problems[blockIdx.x / csize]);
-        int* dst = reinterpret_cast<int*>(&P);
-        for (int i = tid; i < (int)(sizeof(ProblemDesc) / sizeof(int)); i += TRK_THREADS) dst[i] = src[i];
-    }
-    __syncthreads();
+    load_problem(P, sh, problems, blockIdx.x / csize, rank);
     CtaShared* leader = cluster.map_shared_rank(&sh, 0);
     double* slot_base = &leader->slots[0][0];
 
-    if (rank == 0 && tid == 0) {
+    if (rank == 0 && tid < 32) {
         LmState& lm = sh.lm;
-        for (int i = 0; i < 13; ++i) lm.x[i] = P.state[i];
-        lm.radius = 1e4; lm.dec = 2.0; lm.reuse_diag = 0;
-        lm.iter = 0; lm.n_succ = 0; lm.n_unsucc = 0; lm.consec_invalid = 0;
-        lm.termination = EDSGPU_TERM_NO_CONVERGENCE; lm.phase = PHASE_INIT;
-        lm.x_cost = 0.0; lm.initial_cost = 0.0;
-        for (int c = 0; c < csize; ++c) {
-            CtaShared* dst = cluster.map_shared_rank(&sh, c);
-            for (int i = 0; i < 13; ++i) dst->x_eval[i] = lm.x[i];
-            dst->cmd = CMD_EVAL;
+        if (tid < 13) lm.x[tid] = sh.x_eval[tid];
+        if (tid == 0) {
+            lm.radius = 1e4; lm.dec = 2.0; lm.reuse_diag = 0;
+            lm.iter = 0; lm.n_succ = 0; lm.n_unsucc = 0; lm.consec_invalid = 0;
+            lm.termination = EDSGPU_TERM_NO_CONVERGENCE; lm.phase = PHASE_INIT;
+            lm.x_cost = 0.0; lm.initial_cost = 0.0; lm.mcc = 0.0; lm.gmax = 0.0; lm.x_norm = 0.0;
         }
+        __syncwarp();
+        leader_publish(cluster, sh, lm.x, CMD_EVAL, P.kf.B, csize);
     }
     for (;;) {
-        cluster.sync();  // (A) command + evaluation point published to every CTA
-        const int cmd = sh.cmd;
+#ifdef EDS_TIMING
+        unsigned long long tA0 = gtime();
+#endif
+        cluster.sync();  // (A) command + evaluation constants published to every CTA
+#ifdef EDS_TIMING
+        unsigned long long tA = gtime();
+#endif
+        const int cmd = sh.ec.cmd;
         if (cmd == CMD_DONE) break;
         if (cmd == CMD_FINAL) {  // residual write-back at the accepted state; touches no remote memory
             cta_evaluate<true>(P, sh, slot_base, rank, csize, true);
             break;
         }
         cta_evaluate<false>(P, sh, slot_base, rank, csize, false);
+#ifdef EDS_TIMING
+        unsigned long long tE = gtime();
+#endif
         cluster.sync();  // (B) every residual-block slot has landed in the leader's shared memory
+#ifdef EDS_TIMING
+        unsigned long long tB = gtime();
+        if (rank == 0 && tid == 0) { g_timing[0] += tA - tA0; g_timing[1] += tE - tA; g_timing[2] += tB - tE; g_timing[4] += 1; }
+#endif
         if (rank == 0 && tid < 32) {
-            // ordered sum over residual blocks: the result does not depend on the cluster size
-            for (int e = tid; e < 91; e += 32) {
-                double s = 0.0;
-                for (int b = 0; b < P.kf.B; ++b) s += sh.slots[b][e];
-                sh.sum[e] = s;
-            }
-            __syncwarp();
-            if (tid == 0) {
-                LmState& lm = sh.lm;
-                const int next = lm_advance(P, lm, sh.sum, sh.sum + 78, sh.sum[90]);
-                const double* xe = (next == CMD_EVAL) ? lm.cand : lm.x;
-                for (int c = 0; c < csize; ++c) {
-                    CtaShared* dst = cluster.map_shared_rank(&sh, c);
-                    for (int i = 0; i < 13; ++i) dst->x_eval[i] = xe[i];
-                    dst->cmd = next;
-                }
-                if (next != CMD_EVAL) {
-                    const bool usable = lm.termination != EDSGPU_TERM_FAILURE;
-                    if (usable) for (int i = 0; i < 13; ++i) P.state[i] = lm.x[i];  // Tracker.cpp:217-220
-                    edsgpu_tracker_info inf;
-                    inf.iterations = lm.n_succ + lm.n_unsucc;
-                    inf.successful_steps = lm.n_succ;
-                    inf.unsuccessful_steps = lm.n_unsucc;
-                    inf.termination = lm.termination;
-                    inf.usable = usable ? 1 : 0;
-                    inf.num_points = P.kf.N;
-                    inf.initial_cost = lm.initial_cost;
-                    inf.final_cost = lm.x_cost;
-                    inf.final_radius = lm.radius;
-                    *P.info = inf;
-                }
+            LmState& lm = sh.lm;
+            const int next = lm_advance_warp(P, sh);
+#ifdef EDS_TIMING
+            if (tid == 0) g_timing[3] += gtime() - tB;
+#endif
+            leader_publish(cluster, sh, (next == CMD_EVAL) ? lm.cand : lm.x, next, P.kf.B, csize);
+#ifdef EDS_TIMING
+            if (tid == 0) g_timing[5] += gtime() - tB;
+#endif
+            if (next != CMD_EVAL && tid == 0) {
+                const bool usable = lm.termination != EDSGPU_TERM_FAILURE;
+                if (usable) for (int i = 0; i < 13; ++i) P.state[i] = lm.x[i];  // Tracker.cpp:217-220
+                edsgpu_tracker_info inf;
+                inf.iterations = lm.n_succ + lm.n_unsucc;
+                inf.successful_steps = lm.n_succ;
+                inf.unsuccessful_steps = lm.n_unsucc;
+                inf.termination = lm.termination;
+                inf.usable = usable ? 1 : 0;
+                inf.num_points = P.kf.N;
+                inf.initial_cost = lm.initial_cost;
+                inf.final_cost = lm.x_cost;
+                inf.final_radius = lm.radius;
+                *P.info = inf;
             }
         }
     }
@@ -580,11 +689,11 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_eval_kernel(const Proble
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
-    const ProblemDesc& P = problems[blockIdx.x / csize];
     __shared__ CtaShared sh;
+    __shared__ ProblemDesc P;
+    load_problem(P, sh, problems, blockIdx.x / csize, rank);
     CtaShared* leader = cluster.map_shared_rank(&sh, 0);
-    if (threadIdx.x < 13) sh.x_eval[threadIdx.x] = P.state[threadIdx.x];
-    __syncthreads();
+    if (rank == 0 && threadIdx.x < 32) leader_publish(cluster, sh, sh.x_eval, CMD_EVAL, P.kf.B, csize);
     cluster.sync();
     cta_evaluate<false>(P, sh, &leader->slots[0][0], rank, csize, true);
     cluster.sync();
@@ -950,6 +1059,14 @@ edsgpu_status edsgpu_tracker_get_state(edsgpu_tracker* tr, double px[3], double 
 }
 
 void* edsgpu_tracker_state_dev(edsgpu_tracker* tr) { return tr ? (void*)tr->state : nullptr; }
+
+#ifdef EDS_TIMING
+void edsgpu_debug_timing(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_timing, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_timing, z, sizeof(z)); }
+}
+#endif
 
 edsgpu_status edsgpu_trackers_optimize_batch(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes, int count,
                                              const edsgpu_frames* frames, int first_slot) {
