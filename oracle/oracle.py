@@ -74,7 +74,7 @@ def draw_values(px, py, val, H, W, method="bilinear", use_exp=True, sigma=0.5):
     img = np.zeros((H, W), np.float64)
     rc = lib().eds_oracle_draw_values(_p(px, C.c_double), _p(py, C.c_double), _p(val, C.c_int8), C.c_int(len(px)),
                                       C.c_int(H), C.c_int(W), C.c_int(0 if method == "nn" else 1), C.c_int(int(use_exp)),
-                                      C.c_double(sigma), _p(img, C.c_double))
+                                      C.c_double(float(np.float32(sigma))), _p(img, C.c_double))  # `const float s`, Utils.cpp:50
     assert rc == 0
     return img
 
@@ -94,7 +94,7 @@ def event_frame(x, y, pol, ts_us, H, W, mapx=None, mapy=None, method="bilinear",
     d = C.c_int64(0)
     rc = lib().eds_oracle_event_frame(_p(x, C.c_uint16), _p(y, C.c_uint16), _p(pol, C.c_uint8), _p(ts, C.c_int64),
                                       C.c_int(len(x)), C.c_int(H), C.c_int(W), _p(mx, C.c_float), _p(my, C.c_float),
-                                      C.c_int(0 if method == "nn" else 1), C.c_int(int(use_exp)), C.c_double(sigma),
+                                      C.c_int(0 if method == "nn" else 1), C.c_int(int(use_exp)), C.c_double(float(np.float32(sigma))),
                                       _p(img, C.c_double), _p(frame, C.c_double), C.byref(norm), C.byref(t), C.byref(d))
     return dict(img=img, frame=frame, norm=norm.value, time=t.value, delta=d.value, status=rc)
 

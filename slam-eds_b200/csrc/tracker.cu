@@ -864,7 +864,6 @@ struct edsgpu_keyframe {
     edsgpu_ctx* ctx = nullptr;
     KfDev dev{};
     void* block = nullptr;  // one allocation behind all device arrays
-    float* residuals = nullptr;
 };
 
 struct edsgpu_tracker {
@@ -872,7 +871,8 @@ struct edsgpu_tracker {
     edsgpu_tracker_config cfg{};
     double* state = nullptr;            // device: 14 doubles
     edsgpu_tracker_info* info = nullptr; // device
-    ProblemDesc* desc = nullptr;        // device: one descriptor for single-problem calls
+    float* residuals = nullptr;         // device: kf->residuals of the last optimize (Tracker.cpp:223-230)
+    int res_capacity = 0;
 };
 
 namespace {
@@ -908,7 +908,7 @@ ProblemDesc make_desc(const edsgpu_tracker* tr, const edsgpu_keyframe* kf, const
     d.frame = frames->frame + (size_t)slot * frames->H * frames->W;
     d.norms = frames->norms + 2 * slot;
     d.state = tr->state;
-    d.residuals = kf->residuals;
+    d.residuals = tr->residuals;
     d.info = tr->info;
     d.loss_type = tr->cfg.loss_type;
     d.max_iter = tr->cfg.max_iterations;
@@ -947,11 +947,11 @@ edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const doub
     const size_t N = (size_t)num_points;
     edsgpu_keyframe* kf = new edsgpu_keyframe();
     kf->ctx = ctx;
-    // layout: gxy | dw | kpx | kpy | kpz | A | residuals
+    // layout: gxy | dw | kpx | kpy | kpz | A
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     const size_t o_gxy = take(N * sizeof(float4)), o_dw = take(N * sizeof(float2)), o_kx = take(N * 8), o_ky = take(N * 8), o_kz = take(N * 8);
-    const size_t o_A = take((size_t)num_blocks * 21 * 8), o_res = take(N * sizeof(float));
+    const size_t o_A = take((size_t)num_blocks * 21 * 8);
     cudaError_t e = cudaMalloc(&kf->block, off);
     if (e != cudaSuccess) { delete kf; return edsgpu_fail(ctx, EDSGPU_OUT_OF_MEMORY, cudaGetErrorString(e)); }
     char* base = (char*)kf->block;
@@ -959,7 +959,6 @@ edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const doub
     d.gxy = (float4*)(base + o_gxy); d.dw = (float2*)(base + o_dw);
     d.kpx = (double*)(base + o_kx); d.kpy = (double*)(base + o_ky); d.kpz = (double*)(base + o_kz);
     d.A = (double*)(base + o_A);
-    kf->residuals = (float*)(base + o_res);
     d.N = num_points; d.B = num_blocks; d.H = height; d.W = width;
     d.fx = fx; d.fy = fy; d.cx = cx; d.cy = cy;
     // stage the double arrays: pinned -> device scratch -> prepare kernel
@@ -1007,7 +1006,6 @@ edsgpu_status edsgpu_tracker_create(edsgpu_ctx* ctx, const edsgpu_tracker_config
     tr->cfg = *config;
     cudaError_t e = cudaMalloc(&tr->state, 14 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&tr->info, sizeof(edsgpu_tracker_info));
-    if (e == cudaSuccess) e = cudaMalloc(&tr->desc, sizeof(ProblemDesc));
     if (e == cudaSuccess) e = cudaMemsetAsync(tr->info, 0, sizeof(edsgpu_tracker_info), ctx->stream);
     if (e != cudaSuccess) { edsgpu_tracker_destroy(tr); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
     // Tracker::Tracker(config), Tracker.cpp:41-48
@@ -1026,7 +1024,7 @@ void edsgpu_tracker_destroy(edsgpu_tracker* tr) {
     cudaStreamSynchronize(tr->ctx->stream);
     if (tr->state) cudaFree(tr->state);
     if (tr->info) cudaFree(tr->info);
-    if (tr->desc) cudaFree(tr->desc);
+    if (tr->residuals) cudaFree(tr->residuals);
     delete tr;
 }
 
@@ -1079,6 +1077,16 @@ edsgpu_status edsgpu_trackers_optimize_batch(edsgpu_ctx* ctx, edsgpu_tracker* co
         if (st != EDSGPU_OK) return st;
         if (i == 0) B = keyframes[i]->dev.B;
         EDS_REQUIRE(ctx, keyframes[i]->dev.B == B, "optimize_batch: all problems of a batch must share num_blocks");
+        for (int j = 0; j < i; ++j) EDS_REQUIRE(ctx, trackers[j] != trackers[i], "optimize_batch: a tracker appears twice");
+        edsgpu_tracker* tr = trackers[i];
+        if (tr->res_capacity < keyframes[i]->dev.N) {  // residuals live with the tracker: keyframes may be shared
+            EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (tr->residuals) cudaFree(tr->residuals);
+            tr->residuals = nullptr;
+            tr->res_capacity = 0;
+            EDS_CUDA(ctx, cudaMalloc(&tr->residuals, sizeof(float) * (size_t)keyframes[i]->dev.N));
+            tr->res_capacity = keyframes[i]->dev.N;
+        }
     }
     // descriptors: pinned -> device scratch (both owned by the context, reused call to call)
     const size_t bytes = sizeof(ProblemDesc) * (size_t)count;
@@ -1132,7 +1140,7 @@ edsgpu_status edsgpu_tracker_optimize(edsgpu_tracker* tr, const edsgpu_keyframe*
         const size_t N = (size_t)kf->dev.N;
         st = edsgpu_ensure_scratch(ctx, N * sizeof(double));
         if (st != EDSGPU_OK) return st;
-        float_to_double_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(kf->residuals, (double*)ctx->scratch, N);
+        float_to_double_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(tr->residuals, (double*)ctx->scratch, N);
         ctx->launches++;
         EDS_CUDA(ctx, cudaGetLastError());
         EDS_CUDA(ctx, cudaMemcpyAsync(residuals_out, ctx->scratch, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1155,7 +1163,7 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     const size_t o_desc = take(sizeof(ProblemDesc)), o_state = take(14 * 8), o_eval = take(157 * 8), o_info = take(sizeof(edsgpu_tracker_info));
-    const size_t o_jac = take(N * 12 * sizeof(float)), o_wide = take(N * 12 * sizeof(double));
+    const size_t o_jac = take(N * 12 * sizeof(float)), o_wide = take(N * 12 * sizeof(double)), o_res = take(N * sizeof(float));
     edsgpu_status st = edsgpu_ensure_scratch(ctx, off);
     if (st == EDSGPU_OK) st = edsgpu_ensure_pinned(ctx, sizeof(ProblemDesc) + 14 * 8 + 157 * 8);
     if (st != EDSGPU_OK) return st;
@@ -1169,7 +1177,7 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     hd->frame = frames->frame + (size_t)slot * frames->H * frames->W;
     hd->norms = frames->norms + 2 * slot;
     hd->state = (double*)(ds + o_state);
-    hd->residuals = kf->residuals;
+    hd->residuals = (float*)(ds + o_res);
     hd->info = (edsgpu_tracker_info*)(ds + o_info);
     hd->loss_type = loss_type;
     hd->eval_only = 1;
@@ -1185,7 +1193,7 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     double* hev = (double*)(hp + sizeof(ProblemDesc) + 14 * 8);
     EDS_CUDA(ctx, cudaMemcpyAsync(hev, ds + o_eval, 157 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (residuals_out) {
-        float_to_double_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(kf->residuals, (double*)(ds + o_wide), N);
+        float_to_double_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((const float*)(ds + o_res), (double*)(ds + o_wide), N);
         ctx->launches++;
         EDS_CUDA(ctx, cudaMemcpyAsync(residuals_out, ds + o_wide, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
         EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,340 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI
+of include/edsgpu.h, against the CPU oracle on the same seeded inputs and against the committed
+golden fixtures.  Tolerances are the ones BASELINE.json:north_star states:
+  * integer (nn, unweighted) event accumulation: bit-exact;
+  * residuals and Jacobians: 1e-5 relative (fp32 kernels vs the fp64 oracle);
+  * converged poses at the stated iteration cap: 1e-4 rad and 1e-4 x scene depth.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import edsgpu
+from edsgpu import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL_TOL = 1e-5          # residual / Jacobian gate
+ANGLE_TOL = 1e-4        # rad
+DEPTH_TOL = 1e-4 * synth.Z0  # 1e-4 x scene depth
+
+
+def _kf_from_gold(g):
+    H, W = (int(v) for v in g["kf_size"])
+    fx, fy, cx, cy = g["kf_intr"]
+    return dict(grad=g["kf_grad"], norm_coord=g["kf_norm_coord"], idp=g["kf_idp"], weights=g["kf_weights"], H=H, W=W,
+                fx=fx, fy=fy, cx=cx, cy=cy)
+
+
+@pytest.fixture(scope="module")
+def problems():
+    out = {}
+    for cfg in ("tiny", "davis240c"):
+        scene, kf, wins = synth.make_problem(cfg, 0, 2)
+        out[cfg] = (kf, wins)
+    return out
+
+
+# ------------------------------------------------------------------ event frame
+@pytest.mark.parametrize("cfg", ["tiny", "davis240c"])
+def test_integer_event_accumulation_is_bit_exact(gpu_ctx, problems, cfg):
+    kf, wins = problems[cfg]
+    w = wins[0]
+    ef = edsgpu.EventFrame(gpu_ctx, kf["H"], kf["W"])
+    ef.create(w["x"], w["y"], w["pol"], w["ts"], mode=edsgpu.DRAW_NN, use_exp_weights=False, sigma=0.0)
+    acc = ef.frames.read_accumulator(0)
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"], method="nn", use_exp=False, sigma=0.0)
+    counts = np.rint(o["img"]).astype(np.int64)
+    assert np.array_equal(acc, counts << edsgpu.ACC_FRACTION_BITS)
+    img, norm = ef.frames.read(0)
+    assert np.array_equal(img, o["img"])  # sigma = 0: the image is the integer counts, exactly
+    assert abs(norm - o["norm"]) <= 1e-14 * o["norm"]
+    # hot pixel: every event on one pixel exercises the warp-aggregated atomics
+    E = 5000
+    x = np.full(E, 7, np.uint16); y = np.full(E, 5, np.uint16)
+    pol = (np.arange(E) % 3 != 0).astype(np.uint8)
+    ef.create(x, y, pol, None, mode=edsgpu.DRAW_NN, use_exp_weights=False, sigma=0.0)
+    acc = ef.frames.read_accumulator(0)
+    assert acc[5, 7] == (int(pol.sum()) - int((1 - pol).sum())) << edsgpu.ACC_FRACTION_BITS
+    assert np.count_nonzero(acc) == 1
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "davis240c"])
+@pytest.mark.parametrize("use_lut", [False, True])
+def test_event_frame_matches_oracle(gpu_ctx, problems, cfg, use_lut):
+    kf, wins = problems[cfg]
+    w = wins[1]
+    H, W = kf["H"], kf["W"]
+    mx = my = None
+    if use_lut:
+        mx, my = synth.radtan_lut(H, W, kf["fx"], kf["fy"], kf["cx"], kf["cy"], k1=-0.3)  # pushes corners out of the image
+    ef = edsgpu.EventFrame(gpu_ctx, H, W, mx, my)
+    ef.create(w["x"], w["y"], w["pol"], w["ts"], want_host_frame=True)
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], H, W, mx, my)
+    img, norm = ef.frames.read(0)
+    # 2^-41 quantisation per vote, then a 3x3 blur with taps < 1
+    assert np.abs(img - o["img"]).max() < 1e-10
+    assert abs(norm - o["norm"]) < 1e-11 * o["norm"] and abs(ef.norm - o["norm"]) < 1e-11 * o["norm"]
+    assert np.abs(ef.event_frame - o["frame"]).max() < 1e-11
+    assert ef.time == o["time"] and ef.delta_time == o["delta"]
+    # nn + exp weights + blur (the other branch of Utils.cpp:73)
+    ef.create(w["x"], w["y"], w["pol"], w["ts"], mode=edsgpu.DRAW_NN, use_exp_weights=True, sigma=0.7)
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], H, W, mx, my, method="nn", use_exp=True, sigma=0.7)
+    img, norm = ef.frames.read(0)
+    assert np.abs(img - o["img"]).max() < 1e-10 and abs(norm - o["norm"]) < 1e-11 * o["norm"]
+
+
+def test_event_frame_is_deterministic_and_blur_is_bit_exact(gpu_ctx, problems):
+    kf, wins = problems["davis240c"]
+    w = wins[0]
+    ef = edsgpu.EventFrame(gpu_ctx, kf["H"], kf["W"])
+    ef.create(w["x"], w["y"], w["pol"], w["ts"])
+    a1, (i1, n1) = ef.frames.read_accumulator(0), ef.frames.read(0)
+    ef.create(w["x"], w["y"], w["pol"], w["ts"])
+    a2, (i2, n2) = ef.frames.read_accumulator(0), ef.frames.read(0)
+    assert np.array_equal(a1, a2) and np.array_equal(i1, i2) and n1 == n2
+    # the fp64 blur restates the OpenCV operation order: bit-exact on an exactly representable input
+    ef.create(w["x"], w["y"], w["pol"], w["ts"], mode=edsgpu.DRAW_NN, use_exp_weights=False, sigma=0.5)
+    img, _ = ef.frames.read(0)
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"], method="nn", use_exp=False, sigma=0.5)
+    assert np.array_equal(img, o["img"])
+
+
+def test_event_frame_edge_cases(gpu_ctx):
+    H, W = 20, 33  # not a multiple of the blur tile
+    ef = edsgpu.EventFrame(gpu_ctx, H, W)
+    # one event; events on all four borders
+    x = np.array([0, W - 1, 0, W - 1, 5], np.uint16); y = np.array([0, 0, H - 1, H - 1, 7], np.uint16)
+    pol = np.array([1, 0, 1, 0, 1], np.uint8); ts = np.arange(5, dtype=np.int64)
+    for n in (1, 5):
+        ef.create(x[:n], y[:n], pol[:n], ts[:n])
+        o = O.event_frame(x[:n], y[:n], pol[:n], ts[:n], H, W)
+        img, norm = ef.frames.read(0)
+        # absolute floor: one vote carries a 2^-41 = 4.5e-13 quantisation
+        assert np.abs(img - o["img"]).max() < 1e-11 and abs(norm - o["norm"]) < 1e-11 * o["norm"] + 1e-12
+    # non-monotonic timestamps: the reference throws (EventFrame.cpp:325-329)
+    with pytest.raises(edsgpu.EdsGpuError) as e:
+        ef.create(x, y, pol, ts[::-1].copy())
+    assert e.value.status == edsgpu.NON_MONOTONIC_TIME
+    # argument validation
+    with pytest.raises(edsgpu.EdsGpuError) as e:
+        ef.create(x[:0], y[:0], pol[:0], None)
+    assert e.value.status == edsgpu.INVALID_ARGUMENT
+
+
+def test_event_frame_batch_equals_singles(gpu_ctx, problems):
+    kf, wins = problems["tiny"]
+    H, W = kf["H"], kf["W"]
+    E = len(wins[0]["x"])
+    fr = edsgpu.Frames(gpu_ctx, H, W, 4)
+    x = np.concatenate([w["x"] for w in wins]); y = np.concatenate([w["y"] for w in wins]); p = np.concatenate([w["pol"] for w in wins])
+    norms = edsgpu.event_frames_batch(gpu_ctx, fr, 1, 2, x, y, p, E, want_norms=True)
+    for i, w in enumerate(wins):
+        o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], H, W)
+        img, norm = fr.read(1 + i)
+        assert np.abs(img - o["img"]).max() < 1e-10 and abs(norms[i] - o["norm"]) < 1e-11 * o["norm"] and norm == norms[i]
+
+
+# ------------------------------------------------------------------ residual / Jacobian
+@pytest.mark.parametrize("cfg,B", [("tiny", 4), ("tiny", 3), ("davis240c", 8), ("davis240c", 1), ("davis240c", 13)])
+def test_residuals_and_jacobians_within_1e5(gpu_ctx, problems, cfg, B):
+    kf, wins = problems[cfg]
+    w = wins[0]
+    ef = edsgpu.EventFrame(gpu_ctx, kf["H"], kf["W"]).create(w["x"], w["y"], w["pol"], w["ts"])
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, B)
+    for x in (w["x_init"], w["x_true"]):
+        for loss in (edsgpu.LOSS_HUBER, edsgpu.LOSS_CAUCHY, edsgpu.LOSS_NONE):
+            g = edsgpu.tracker_evaluate(gpu_ctx, kfd, ef.frames, 0, x, loss_type=loss, loss_param=0.05)
+            e = O.tracker_evaluate(kf, o["frame"], x, B, loss_type=loss, loss_param=0.05)
+            assert np.abs(g["residuals"] - e["residuals"]).max() <= REL_TOL * np.abs(e["residuals"]).max()
+            colmax = np.abs(e["jacobian"]).max(0)
+            assert np.all(np.abs(g["jacobian"] - e["jacobian"]).max(0) <= REL_TOL * colmax)
+            assert abs(g["cost"] - e["cost"]) <= 1e-6 * e["cost"]
+            assert np.abs(g["H"] - e["H"]).max() <= 1e-6 * np.abs(e["H"]).max()
+            assert np.abs(g["g"] - e["g"]).max() <= 1e-6 * np.abs(e["g"]).max() + 1e-9
+    kfd.close()
+
+
+def test_sampling_outside_the_image_is_clamped_like_grid2d(gpu_ctx, problems):
+    kf, wins = problems["tiny"]
+    w = wins[0]
+    ef = edsgpu.EventFrame(gpu_ctx, kf["H"], kf["W"]).create(w["x"], w["y"], w["pol"], w["ts"])
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, 4)
+    x = w["x_init"].copy()
+    x[:3] = [1.5, -1.0, 0.1]  # pushes most points out of the sensor
+    g = edsgpu.tracker_evaluate(gpu_ctx, kfd, ef.frames, 0, x)
+    e = O.tracker_evaluate(kf, o["frame"], x, 4)
+    assert np.abs(g["residuals"] - e["residuals"]).max() <= REL_TOL * np.abs(e["residuals"]).max()
+    assert np.all(np.abs(g["jacobian"] - e["jacobian"]).max(0) <= REL_TOL * np.abs(e["jacobian"]).max(0) + 1e-12)
+
+
+# ------------------------------------------------------------------ LM solve
+@pytest.mark.parametrize("cfg,B,iters", [("tiny", 4, 20), ("davis240c", 8, 30), ("davis240c", 8, 10), ("davis240c", 5, 30)])
+def test_converged_pose_matches_oracle(gpu_ctx, problems, cfg, B, iters):
+    kf, wins = problems[cfg]
+    w = wins[0]
+    ef = edsgpu.EventFrame(gpu_ctx, kf["H"], kf["W"]).create(w["x"], w["y"], w["pol"], w["ts"])
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, B)
+    tr = edsgpu.Tracker(gpu_ctx, num_blocks=B, max_iterations=iters)
+    x0 = w["x_init"]
+    tr.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
+    r = tr.optimize(kfd, ef.frames, 0, want_residuals=True)
+    s = O.tracker_solve(kf, o["frame"], x0, num_blocks=B, max_iterations=iters)
+    assert r["usable"] and s["status"] == 0
+    assert r["info"]["iterations"] == s["info"]["iterations"]
+    assert r["info"]["successful_steps"] == s["info"]["successful_steps"]
+    assert r["info"]["termination"] == s["info"]["termination"]
+    assert synth.quat_angle(r["qx"], s["x"][3:7]) < ANGLE_TOL
+    assert np.linalg.norm(r["px"] - s["x"][:3]) < DEPTH_TOL
+    # the unit velocity is the weakly constrained direction of this objective (flat valley,
+    # SURVEY.md section 7); north_star gates the pose only, the velocity gets a looser sanity bound
+    assert np.linalg.norm(r["vx"] - s["x"][7:]) < 5e-3
+    assert abs(r["info"]["final_cost"] - s["info"]["final_cost"]) < 1e-5 * s["info"]["final_cost"]
+    assert r["info"]["final_cost"] < r["info"]["initial_cost"]
+    # derived from the converged state, so they inherit its (velocity) tolerance
+    assert np.abs(r["residuals"] - s["residuals"]).max() < 2e-3 * np.abs(s["residuals"]).max()
+    assert abs(r["next_loss_param"] - s["next_loss_param"]) < 2e-3 * s["next_loss_param"]
+    # the tracker keeps its state (Tracker.hpp:47-49): px,qx,vx and the MAD loss parameter
+    px, qx, vx, lp, info = tr.get_state()
+    assert np.array_equal(px, r["px"]) and np.array_equal(qx, r["qx"]) and lp == r["next_loss_param"]
+    assert abs(np.linalg.norm(qx) - 1) < 1e-12 and abs(np.linalg.norm(vx) - 1) < 1e-12
+    tr.close(); kfd.close()
+
+
+def test_mad_and_other_loss_parameter_methods(gpu_ctx, problems):
+    kf, wins = problems["davis240c"]
+    w = wins[0]
+    ef = edsgpu.EventFrame(gpu_ctx, kf["H"], kf["W"]).create(w["x"], w["y"], w["pol"], w["ts"])
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, 8)
+    x0 = w["x_init"]
+    res = {}
+    for method in (edsgpu.LOSS_PARAM_MAD, edsgpu.LOSS_PARAM_CONSTANT, edsgpu.LOSS_PARAM_STD):
+        tr = edsgpu.Tracker(gpu_ctx, num_blocks=8, max_iterations=5, loss_param_method=method)
+        tr.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
+        res[method] = tr.optimize(kfd, ef.frames, 0, want_residuals=True)
+        tr.close()
+    r = res[edsgpu.LOSS_PARAM_MAD]
+    # exact selection on the fp32 residuals the device holds
+    r32 = r["residuals"].astype(np.float32)
+    med = np.sort(r32)[len(r32) // 2]
+    mad = np.sort(np.abs(r32 - med))[len(r32) // 2]
+    assert abs(r["next_loss_param"] - 1.345 * 1.4826 * float(mad)) < 1e-12
+    assert abs(r["next_loss_param"] - O.mad_tau(r["residuals"])) < 1e-6
+    assert res[edsgpu.LOSS_PARAM_CONSTANT]["next_loss_param"] == 0.05  # Tracker.cpp:287-290
+    rs = res[edsgpu.LOSS_PARAM_STD]["residuals"]
+    var = np.sum((rs - rs.mean()) ** 2 / (len(rs) - 1))  # mean_std_vector returns the variance (Utils.hpp:285-289)
+    assert abs(res[edsgpu.LOSS_PARAM_STD]["next_loss_param"] - 1.345 * var) < 1e-6 * var
+    kfd.close()
+
+
+def test_batch_matches_single_and_is_independent_of_cluster_size(gpu_ctx, problems):
+    """One launch over many trackers (other cluster size) gives bit-identical states."""
+    kf, wins = problems["davis240c"]
+    H, W = kf["H"], kf["W"]
+    n = 40  # > 148/8: forces a smaller cluster than the single-problem launch
+    fr = edsgpu.Frames(gpu_ctx, H, W, n)
+    E = len(wins[0]["x"])
+    x = np.concatenate([wins[i % 2]["x"] for i in range(n)]); y = np.concatenate([wins[i % 2]["y"] for i in range(n)])
+    p = np.concatenate([wins[i % 2]["pol"] for i in range(n)])
+    edsgpu.event_frames_batch(gpu_ctx, fr, 0, n, x, y, p, E)
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, 8)
+    trs = [edsgpu.Tracker(gpu_ctx, num_blocks=8, max_iterations=12) for _ in range(n)]
+    for i, t in enumerate(trs):
+        x0 = wins[i % 2]["x_init"]
+        t.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
+    batch = edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * n)
+    batch.optimize(fr, 0)
+    states, infos = batch.gather()
+    for k in (0, 1):
+        single = edsgpu.Tracker(gpu_ctx, num_blocks=8, max_iterations=12)
+        x0 = wins[k]["x_init"]
+        single.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
+        r = single.optimize(kfd, fr, k)
+        for i in range(k, n, 2):
+            assert np.array_equal(states[i, :13], r["x"]) and states[i, 13] == r["next_loss_param"]
+            assert infos[i]["iterations"] == r["info"]["iterations"] and infos[i]["usable"] == 1
+        single.close()
+    for t in trs:
+        t.close()
+    kfd.close()
+
+
+def test_sequence_of_windows_carries_state(gpu_ctx, problems):
+    """Window k+1 warm-starts from window k's (px,qx,vx) and tau (Tracker.cpp:233)."""
+    kf, wins = problems["davis240c"]
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, 8)
+    tr = edsgpu.Tracker(gpu_ctx, num_blocks=8, max_iterations=15)
+    x = wins[0]["x_init"].copy()
+    tau = 0.05
+    tr.set_state(x[:3], x[3:7], x[7:], tau)
+    ef = edsgpu.EventFrame(gpu_ctx, kf["H"], kf["W"])
+    for w in wins:
+        ef.create(w["x"], w["y"], w["pol"], w["ts"])
+        o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])
+        r = tr.optimize(kfd, ef.frames, 0)
+        s = O.tracker_solve(kf, o["frame"], x, num_blocks=8, loss_param=tau, max_iterations=15)
+        assert synth.quat_angle(r["qx"], s["x"][3:7]) < ANGLE_TOL and np.linalg.norm(r["px"] - s["x"][:3]) < DEPTH_TOL
+        x, tau = s["x"], s["next_loss_param"]
+    tr.close(); kfd.close()
+
+
+def test_argument_validation(gpu_ctx, problems):
+    kf, wins = problems["tiny"]
+    with pytest.raises(edsgpu.EdsGpuError):
+        edsgpu.KeyFrame(gpu_ctx, kf, 0)
+    with pytest.raises(edsgpu.EdsGpuError):
+        edsgpu.KeyFrame(gpu_ctx, kf, 33)
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, 4)
+    tr = edsgpu.Tracker(gpu_ctx, num_blocks=8)
+    fr = edsgpu.Frames(gpu_ctx, kf["H"], kf["W"], 1)
+    with pytest.raises(edsgpu.EdsGpuError) as e:  # num_blocks mismatch is a numerical parameter, not a tuning knob
+        tr.optimize(kfd, fr, 0)
+    assert e.value.status == edsgpu.INVALID_ARGUMENT
+    fr2 = edsgpu.Frames(gpu_ctx, kf["H"] + 1, kf["W"], 1)
+    tr4 = edsgpu.Tracker(gpu_ctx, num_blocks=4)
+    with pytest.raises(edsgpu.EdsGpuError):
+        tr4.optimize(kfd, fr2, 0)
+    # an all-zero frame has norm 0: the reference divides by it (EventFrame.cpp:377), the frame
+    # becomes NaN and Ceres reports an unusable solution -> optimize() returns false
+    ef0 = edsgpu.EventFrame(gpu_ctx, kf["H"], kf["W"], frames=fr)
+    ef0.create(np.array([3, 3], np.uint16), np.array([4, 4], np.uint16), np.array([1, 0], np.uint8), None,
+               use_exp_weights=False)
+    assert ef0.norm == 0.0
+    r = tr4.optimize(kfd, fr, 0)
+    assert not r["usable"] and r["info"]["termination"] == edsgpu.TERM_FAILURE
+
+
+# ------------------------------------------------------------------ committed golden fixtures
+@pytest.mark.parametrize("name", ["tracking_tiny.npz", "tracking_davis240c.npz"])
+def test_gpu_against_golden(gpu_ctx, name):
+    g = np.load(os.path.join(GOLD, name))
+    kf = _kf_from_gold(g)
+    H, W = kf["H"], kf["W"]
+    B = int(g["num_blocks"])
+    ef = edsgpu.EventFrame(gpu_ctx, H, W)
+    ef.create(g["ev_x"], g["ev_y"], g["ev_pol"], g["ev_ts"], mode=edsgpu.DRAW_NN, use_exp_weights=False, sigma=0.0)
+    assert np.array_equal(ef.frames.read_accumulator(0), g["nn_counts"].astype(np.int64) << edsgpu.ACC_FRACTION_BITS)
+    ef.create(g["ev_x"], g["ev_y"], g["ev_pol"], g["ev_ts"])
+    img, norm = ef.frames.read(0)
+    assert np.abs(img - g["bl_img"]).max() < 1e-10 and abs(norm - float(g["bl_norm"])) < 1e-11 * norm
+    assert ef.time == int(g["bl_time"]) and ef.delta_time == int(g["bl_delta"])
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, B)
+    ev = edsgpu.tracker_evaluate(gpu_ctx, kfd, ef.frames, 0, g["x0"])
+    assert np.abs(ev["residuals"] - g["ev_residuals"]).max() <= REL_TOL * np.abs(g["ev_residuals"]).max()
+    assert np.all(np.abs(ev["jacobian"] - g["ev_jacobian"]).max(0) <= REL_TOL * np.abs(g["ev_jacobian"]).max(0))
+    tr = edsgpu.Tracker(gpu_ctx, num_blocks=B, max_iterations=int(g["max_iterations"]))
+    tr.set_state(g["x0"][:3], g["x0"][3:7], g["x0"][7:], 0.05)
+    r = tr.optimize(kfd, ef.frames, 0)
+    assert r["info"]["iterations"] == int(g["so_info"][0])
+    assert synth.quat_angle(r["qx"], g["so_x"][3:7]) < ANGLE_TOL and np.linalg.norm(r["px"] - g["so_x"][:3]) < DEPTH_TOL
+    assert abs(r["next_loss_param"] - float(g["so_tau"])) < 1e-3 * float(g["so_tau"])
+    tr.close(); kfd.close()
+    if g["lut_x"].size:
+        ef2 = edsgpu.EventFrame(gpu_ctx, H, W, g["lut_x"], g["lut_y"]).create(g["ev_x"], g["ev_y"], g["ev_pol"], g["ev_ts"])
+        img, norm = ef2.frames.read(0)
+        assert np.abs(img - g["lut_img"]).max() < 1e-10 and abs(norm - float(g["lut_norm"])) < 1e-11 * norm
