@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- tracking windows/s at 640x480 (BASELINE.json metric) on N B200s of one node.
+
+Workload (config.workload): BASELINE.json configs[1] -- Prophesee Gen3 640x480, 10 240 keyframe
+points, 50 000 events/window, B = 8 residual blocks, Huber (tau0 = 0.05, MAD-updated),
+max_num_iterations = 30, function_tolerance = 1e-6 -- as a batch of
+`--sequences` (default 64, configs[4]) independent sequences PER GPU.  One step = one event
+window of every sequence: event-frame construction + device-side LM solve + MAD, warm-started
+from the previous step (px,qx,vx,tau stay in HBM).  Sequences are independent, so ranks share
+nothing on the data path (scaling: weak); the states are gathered once at the end with NCCL.
+
+  value  device-resident inputs (events already in HBM), CUDA-event timed, max over ranks
+  e2e    the same step through the host-facing C ABI: events from pinned host memory every
+         step (H2D inside the timed region) and the 64x14 state records read back (D2H)
+  --impl reference   the CPU restatement of the reference path (oracle, dual-number Jacobians =
+         the cost structure of the Ceres autodiff functor) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "slam-eds_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CONFIG = "gen3_vga"
+NUM_BLOCKS = 8
+MAX_ITER = 30
+TAU0 = 0.05
+DISTINCT_SCENES = 8      # synthetic scenes generated per rank (sequences cycle through them)
+WINDOWS_PER_SCENE = 4    # distinct event windows per scene
+
+
+def algorithmic_bytes_lm(N, H, W, B, evaluations):
+    """per LM Jacobian evaluation 24 N + min(64 N, 4 H W) + 364 B, + 4 N write-back."""
+    return evaluations * (24 * N + min(64 * N, 4 * H * W) + 364 * B)
+
+
+def make_data(rank, n_scenes=DISTINCT_SCENES, n_windows=WINDOWS_PER_SCENE):
+    from edsgpu import synth
+    data = []
+    for s in range(n_scenes):
+        scene, kf, wins = synth.make_problem(CONFIG, 100 * rank + s, n_windows)
+        data.append((kf, wins))
+    return data
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_windows_per_s(data, n_windows, concurrent, threads_per_window, jacobian_mode=1):
+    """Times the oracle on `n_windows` windows of the workload: event frame + Ceres-style solve +
+    MAD, `concurrent` independent sequences at a time, `threads_per_window` workers each (the
+    reference parallelises over its B residual blocks, Tracker.cpp:138,178-195)."""
+    from oracle import oracle as O
+    O.lib()
+    jobs = []
+    for i in range(n_windows):
+        kf, wins = data[i % len(data)]
+        jobs.append((kf, wins[(i // len(data)) % len(wins)]))
+
+    def run(job):
+        kf, w = job
+        ef = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])
+        O.tracker_solve(kf, ef["frame"], w["x_init"], num_blocks=NUM_BLOCKS, loss_type=1, loss_param=TAU0, max_iterations=MAX_ITER,
+                        function_tolerance=1e-6, jacobian_mode=jacobian_mode, threads=threads_per_window)
+
+    run(jobs[0])  # warm (page in, build)
+    t0 = time.perf_counter()
+    if concurrent <= 1:
+        for j in jobs:
+            run(j)
+    else:
+        nxt = [0]
+        lock = threading.Lock()
+
+        def worker():
+            while True:
+                with lock:
+                    k = nxt[0]
+                    nxt[0] += 1
+                if k >= len(jobs):
+                    return
+                run(jobs[k])  # ctypes releases the GIL inside the oracle
+
+        ths = [threading.Thread(target=worker) for _ in range(concurrent)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    dt = time.perf_counter() - t0
+    return n_windows / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference itself cannot be
+    built here) on all host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    concurrent = max(1, cores // NUM_BLOCKS)
+    data = make_data(0, n_scenes=2, n_windows=2)
+    per_step = max(concurrent, 2)
+    from edsgpu import synth
+    c = synth.CONFIGS[CONFIG]
+    for _ in range(args.warmup):
+        cpu_windows_per_s(data, per_step, concurrent, NUM_BLOCKS)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        wps, dt = cpu_windows_per_s(data, per_step, concurrent, NUM_BLOCKS)
+        t_total += dt
+        n_total += per_step
+    value = n_total / t_total
+    sample = "%d windows/step x %d steps of config2 (event frame + dual-number LM solve + MAD), %d concurrent sequences x %d threads" % (
+        per_step, args.steps, concurrent, NUM_BLOCKS)
+    print(json.dumps({
+        "impl": "reference", "metric": "tracking_windows_per_s_640x480", "value": value, "unit": "windows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "mevents_per_s": value * c["E"] / 1e6,
+        "config": {"workload": "config2: Gen3 640x480, 10240 points, 50000 events/window, B=8, Huber+MAD, max_iter 30",
+                   "note": "oracle restatement of the reference CPU/Ceres path (not Ceres itself), dual-number Jacobians"},
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": min(cores, concurrent * NUM_BLOCKS), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import edsgpu
+    from edsgpu import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    c = synth.CONFIGS[CONFIG]
+    H, W, N, E = c["H"], c["W"], c["N"], c["E"]
+    S = args.sequences
+
+    # one explicit stream shared by torch (events, copies, NCCL ordering) and the library
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx = edsgpu.Context(local_rank, stream.cuda_stream)
+    data = make_data(rank)
+    n_sc, n_win = len(data), len(data[0][1])
+    # sequence s follows scene s % n_sc, starting at window (s // n_sc) % n_win
+    kfs_dev = [edsgpu.KeyFrame(ctx, kf, NUM_BLOCKS) for kf, _ in data]
+    frames = edsgpu.Frames(ctx, H, W, S)
+    trackers = []
+    for s in range(S):
+        t = edsgpu.Tracker(ctx, num_blocks=NUM_BLOCKS, loss_type=edsgpu.LOSS_HUBER, loss_param=TAU0, max_iterations=MAX_ITER,
+                           function_tolerance=1e-6, loss_param_method=edsgpu.LOSS_PARAM_MAD)
+        trackers.append(t)
+    batch = edsgpu.TrackerBatch(ctx, trackers, [kfs_dev[s % n_sc] for s in range(S)], frames, 0)
+
+    def reset_states():
+        for s, t in enumerate(trackers):
+            x0 = data[s % n_sc][1][(s // n_sc) % n_win]["x_init"]
+            t.set_state(x0[:3], x0[3:7], x0[7:], TAU0)
+
+    # event windows of step k: pinned host copies and device-resident copies, n_win phases
+    host_ev, dev_ev = [], []
+    for ph in range(n_win):
+        xs = np.concatenate([data[s % n_sc][1][(s // n_sc + ph) % n_win]["x"] for s in range(S)])
+        ys = np.concatenate([data[s % n_sc][1][(s // n_sc + ph) % n_win]["y"] for s in range(S)])
+        ps = np.concatenate([data[s % n_sc][1][(s // n_sc + ph) % n_win]["pol"] for s in range(S)])
+        hx = torch.from_numpy(xs.view(np.int16).copy()).pin_memory()
+        hy = torch.from_numpy(ys.view(np.int16).copy()).pin_memory()
+        hp = torch.from_numpy(ps.copy()).pin_memory()
+        host_ev.append((hx, hy, hp))
+        dev_ev.append((hx.to(dev), hy.to(dev), hp.to(dev)))
+    states_dev = torch.zeros(S, 14, dtype=torch.float64, device=dev)
+    states_host = torch.zeros(S, 14, dtype=torch.float64).pin_memory()
+
+    def step_device(k):
+        dx, dy, dp = dev_ev[k % n_win]
+        edsgpu.event_frames_batch_dev(ctx, frames, 0, S, dx.data_ptr(), dy.data_ptr(), dp.data_ptr(), E)
+        batch.optimize()
+
+    def step_e2e(k):
+        hx, hy, hp = host_ev[k % n_win]
+        ctx.check(ctx.lib.edsgpu_event_frame_create_batch(
+            ctx.h, frames.h, 0, S, None, edsgpu.C.c_void_p(hx.data_ptr()), edsgpu.C.c_void_p(hy.data_ptr()),
+            edsgpu.C.c_void_p(hp.data_ptr()), E, edsgpu.DRAW_BILINEAR, 1, edsgpu.C.c_float(0.5), None))
+        batch.optimize()
+        batch.pack_states_dev(states_dev.data_ptr())
+        states_host.copy_(states_dev, non_blocking=True)
+        stream.synchronize()  # the step's result is on the host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) ------------------------------------------------
+    reset_states()
+    for k in range(args.warmup):
+        step_device(k)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lm_events = []
+    ev0.record(stream)
+    for k in range(args.steps):
+        dx, dy, dp = dev_ev[(args.warmup + k) % n_win]
+        edsgpu.event_frames_batch_dev(ctx, frames, 0, S, dx.data_ptr(), dy.data_ptr(), dp.data_ptr(), E)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        ctx.check(ctx.lib.edsgpu_batch_optimize(batch.h))  # track_lm_kernel + mad_kernel
+        b.record(stream)
+        lm_events.append((a, b))
+    ev1.record(stream)
+    barrier()
+    launches = ctx.launches - launches0
+    clk = clocks.stop() if rank == 0 else None
+    t_ms = ev0.elapsed_time(ev1)
+    t_all = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    t_ms_max = float(t_all.item())
+    lm_ms = float(np.mean([a.elapsed_time(b) for a, b in lm_events]))
+    states, infos = batch.gather()
+    evals = float(np.mean([sum(i["evaluations"] for i in infos)]))  # last step's launch
+    usable = sum(i["usable"] for i in infos)
+    iters = float(np.mean([i["iterations"] for i in infos]))
+
+    # ---- end-to-end timing (e2e): host buffers in, host states out, every step ---------
+    reset_states()
+    for k in range(max(1, args.warmup)):
+        step_e2e(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e(args.warmup + k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e_all = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_all, op=dist.ReduceOp.MAX)
+    e2e_s = float(e_all.item())
+
+    # ---- the one collective of the path: gather the final states over NCCL -------------
+    batch.pack_states_dev(states_dev.data_ptr())
+    if world > 1:
+        gathered = [torch.zeros_like(states_dev) for _ in range(world)]
+        dist.all_gather(gathered, states_dev)
+        torch.cuda.synchronize()
+        final_states = torch.stack(gathered).cpu().numpy()
+    else:
+        final_states = states_dev.cpu().numpy()[None]
+
+    if rank == 0:
+        windows = world * S * args.steps
+        value = windows / (t_ms_max * 1e-3)
+        e2e_value = windows / e2e_s
+        alg = algorithmic_bytes_lm(N, H, W, NUM_BLOCKS, evals) + 4 * N * S
+        achieved = alg / (lm_ms * 1e-3) / 1e9
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("track_lm_kernel_dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        out = {
+            "metric": "tracking_windows_per_s_640x480", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (fp64 warp/projection, reductions and LM solve)", "data": "synthetic",
+            "mevents_per_s": value * E / 1e6,
+            "config": {"workload": "config2 x %d sequences/GPU: Gen3 640x480, %d points, %d events/window, B=%d, Huber+MAD, max_iter %d"
+                                   % (S, N, E, NUM_BLOCKS, MAX_ITER),
+                       "sequences_per_gpu": S, "l2": "per-step working set ~%d MB (event accumulators + frames + keyframes) > 126 MB L2, no explicit flush"
+                                                   % int((S * H * W * 12 + S * E * 5 + n_sc * N * 48) / 1e6),
+                       "mean_lm_iterations": iters, "usable": "%d/%d" % (usable, S), "parallelism": "sequences sharded, %d rank(s)" % world},
+            "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(S * E * 5), "d2h_bytes_per_step": int(S * 14 * 8),
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"kernel": "track_lm_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "algorithmic_bytes_per_launch": alg, "launch_ms": lm_ms, "evaluations_per_launch": evals},
+            "final_state_checksum": float(np.abs(final_states).sum()),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_cpu = 6
+            wps, dt = cpu_windows_per_s(data[:2], n_cpu, 1, min(NUM_BLOCKS, cores))
+            out["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": min(NUM_BLOCKS, cores), "kind": "port",
+                                   "sample": "%d windows of the same workload, one sequence, %d threads (one per residual block), dual-number Jacobians, %.1f s"
+                                             % (n_cpu, min(NUM_BLOCKS, cores), dt)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--sequences", type=int, default=64, help="independent sequences per GPU (configs[4])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -117,6 +117,8 @@ typedef struct {                 /* eds::tracking::TrackerInfo (tracking/Config.
     int termination;             /* EDSGPU_TERM_* */
     int usable;                  /* summary.IsSolutionUsable() (Tracker.cpp:213) */
     int num_points;
+    int evaluations;             /* sweeps over the points (residual + Jacobian + reduction) */
+    int reserved;
     double initial_cost;
     double final_cost;
     double final_radius;
@@ -157,6 +159,16 @@ edsgpu_status edsgpu_tracker_optimize(edsgpu_tracker* tracker, const edsgpu_keyf
 edsgpu_status edsgpu_trackers_optimize_batch(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers,
                                              const edsgpu_keyframe* const* keyframes, int count, const edsgpu_frames* frames,
                                              int first_slot);
+/* A fixed set of (tracker, keyframe, frame slot) problems whose device descriptors are built
+ * once: edsgpu_batch_optimize is then two kernel launches and nothing else (asynchronous). */
+typedef struct edsgpu_batch edsgpu_batch;
+edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes,
+                                  int count, const edsgpu_frames* frames, int first_slot, edsgpu_batch** out);
+void edsgpu_batch_destroy(edsgpu_batch* batch);
+edsgpu_status edsgpu_batch_optimize(edsgpu_batch* batch);
+/* copies the count x 14 state records into one contiguous DEVICE buffer (e.g. the send buffer
+ * of the caller's final NCCL all-gather); asynchronous on the context stream. */
+edsgpu_status edsgpu_batch_pack_states_dev(edsgpu_batch* batch, double* states_dev);
 /* states_out: count x 14 doubles [px(3) qx(4) vx(6) loss_param]; infos_out optional. Synchronises. */
 edsgpu_status edsgpu_trackers_gather(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, int count, double* states_out,
                                      edsgpu_tracker_info* infos_out);

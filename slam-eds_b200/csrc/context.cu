@@ -1,5 +1,8 @@
 // Context lifetime for libedsgpu.so.  No CPU fallback: creation fails without a CUDA device.
+#include <atomic>
+
 #include "common.cuh"
+#include "frames.cuh"
 
 extern "C" {
 
@@ -49,6 +52,11 @@ edsgpu_status edsgpu_synchronize(edsgpu_ctx* ctx) {
 int64_t edsgpu_launch_count(const edsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 }  // extern "C"
+
+uint64_t edsgpu_next_uid() {
+    static std::atomic<uint64_t> counter{1};
+    return counter.fetch_add(1);
+}
 
 edsgpu_status edsgpu_ensure_pinned(edsgpu_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->pinned_bytes) return EDSGPU_OK;

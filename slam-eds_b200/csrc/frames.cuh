@@ -9,8 +9,11 @@ struct edsgpu_lut {
     float* mapy = nullptr;
 };
 
+uint64_t edsgpu_next_uid();  // process-wide, never reused: lets caches detect recycled addresses
+
 struct edsgpu_frames {
     edsgpu_ctx* ctx = nullptr;
+    uint64_t uid = edsgpu_next_uid();
     int H = 0, W = 0, capacity = 0;
     long long* acc = nullptr;     // [capacity][H*W] fixed-point (2^-40) brightness increments
     float* frame = nullptr;       // [capacity][H*W] blurred, un-normalised

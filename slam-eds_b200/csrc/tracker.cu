@@ -136,7 +136,7 @@ struct LmState {
     double Hs[78], gs[12];    // Jacobi-scaled normal equations at x
     double scale[12], diag[12];
     double x_cost, mcc, radius, dec, gmax, x_norm, initial_cost;
-    int reuse_diag, iter, n_succ, n_unsucc, consec_invalid, termination, phase;
+    int reuse_diag, iter, n_succ, n_unsucc, consec_invalid, termination, phase, n_eval;
 };
 
 // Everything a CTA needs for one evaluation; written by the leader into every CTA of the
@@ -444,6 +444,7 @@ __device__ int lm_advance_warp(const ProblemDesc& P, CtaShared& sh) {
     unsigned long long tt1 = gtime();
 #endif
     const double cost = sh.sum[90];
+    if (lane == 0) lm.n_eval++;
     double radius = lm.radius, dec = lm.dec;
     int reuse = lm.reuse_diag, n_succ = lm.n_succ, n_unsucc = lm.n_unsucc;
     bool take = false, first = false;
@@ -624,7 +625,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
         if (tid < 13) lm.x[tid] = sh.x_eval[tid];
         if (tid == 0) {
             lm.radius = 1e4; lm.dec = 2.0; lm.reuse_diag = 0;
-            lm.iter = 0; lm.n_succ = 0; lm.n_unsucc = 0; lm.consec_invalid = 0;
+            lm.iter = 0; lm.n_succ = 0; lm.n_unsucc = 0; lm.consec_invalid = 0; lm.n_eval = 0;
             lm.termination = EDSGPU_TERM_NO_CONVERGENCE; lm.phase = PHASE_INIT;
             lm.x_cost = 0.0; lm.initial_cost = 0.0; lm.mcc = 0.0; lm.gmax = 0.0; lm.x_norm = 0.0;
         }
@@ -674,6 +675,8 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
                 inf.termination = lm.termination;
                 inf.usable = usable ? 1 : 0;
                 inf.num_points = P.kf.N;
+                inf.evaluations = lm.n_eval;
+                inf.reserved = 0;
                 inf.initial_cost = lm.initial_cost;
                 inf.final_cost = lm.x_cost;
                 inf.final_radius = lm.radius;
@@ -862,6 +865,7 @@ __global__ void float_to_double_kernel(const float* __restrict__ in, double* __r
 // ==========================================================================================
 struct edsgpu_keyframe {
     edsgpu_ctx* ctx = nullptr;
+    uint64_t uid = edsgpu_next_uid();
     KfDev dev{};
     void* block = nullptr;  // one allocation behind all device arrays
 };
@@ -873,6 +877,17 @@ struct edsgpu_tracker {
     edsgpu_tracker_info* info = nullptr; // device
     float* residuals = nullptr;         // device: kf->residuals of the last optimize (Tracker.cpp:223-230)
     int res_capacity = 0;
+    // one-problem batch cached for repeated optimize() calls against the same keyframe / frame slot
+    struct edsgpu_batch* cached = nullptr;
+    uint64_t cached_kf = 0, cached_frames = 0;
+    int cached_slot = -1;
+};
+
+struct edsgpu_batch {
+    edsgpu_ctx* ctx = nullptr;
+    int count = 0, csize = 1;
+    ProblemDesc* desc = nullptr;  // device
+    std::vector<edsgpu_tracker*> trackers;
 };
 
 namespace {
@@ -1024,6 +1039,7 @@ void edsgpu_tracker_destroy(edsgpu_tracker* tr) {
     cudaStreamSynchronize(tr->ctx->stream);
     if (tr->state) cudaFree(tr->state);
     if (tr->info) cudaFree(tr->info);
+    if (tr->cached) edsgpu_batch_destroy(tr->cached);
     if (tr->residuals) cudaFree(tr->residuals);
     delete tr;
 }
@@ -1066,18 +1082,18 @@ void edsgpu_debug_timing(unsigned long long* out, int reset) {
 }
 #endif
 
-edsgpu_status edsgpu_trackers_optimize_batch(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes, int count,
-                                             const edsgpu_frames* frames, int first_slot) {
-    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
-    EDS_REQUIRE(ctx, trackers && keyframes && count > 0, "optimize_batch: bad arguments");
+edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes, int count,
+                                  const edsgpu_frames* frames, int first_slot, edsgpu_batch** out) {
+    if (!ctx || !out) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, trackers && keyframes && count > 0, "batch_create: bad arguments");
     DeviceGuard g(ctx->device);
     int B = 0;
     for (int i = 0; i < count; ++i) {
         edsgpu_status st = check_pair(ctx, trackers[i], keyframes[i], frames, first_slot + i);
         if (st != EDSGPU_OK) return st;
         if (i == 0) B = keyframes[i]->dev.B;
-        EDS_REQUIRE(ctx, keyframes[i]->dev.B == B, "optimize_batch: all problems of a batch must share num_blocks");
-        for (int j = 0; j < i; ++j) EDS_REQUIRE(ctx, trackers[j] != trackers[i], "optimize_batch: a tracker appears twice");
+        EDS_REQUIRE(ctx, keyframes[i]->dev.B == B, "batch_create: all problems of a batch must share num_blocks");
+        for (int j = 0; j < i; ++j) EDS_REQUIRE(ctx, trackers[j] != trackers[i], "batch_create: a tracker appears twice");
         edsgpu_tracker* tr = trackers[i];
         if (tr->res_capacity < keyframes[i]->dev.N) {  // residuals live with the tracker: keyframes may be shared
             EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1088,23 +1104,59 @@ edsgpu_status edsgpu_trackers_optimize_batch(edsgpu_ctx* ctx, edsgpu_tracker* co
             tr->res_capacity = keyframes[i]->dev.N;
         }
     }
-    // descriptors: pinned -> device scratch (both owned by the context, reused call to call)
-    const size_t bytes = sizeof(ProblemDesc) * (size_t)count;
-    edsgpu_status st = edsgpu_ensure_pinned(ctx, bytes);
-    if (st == EDSGPU_OK) st = edsgpu_ensure_scratch(ctx, bytes);
-    if (st != EDSGPU_OK) return st;
-    // the previous batch may still be reading the scratch descriptors / pinned source
-    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ProblemDesc* hd = (ProblemDesc*)ctx->pinned;
+    edsgpu_batch* b = new edsgpu_batch();
+    b->ctx = ctx;
+    b->count = count;
+    b->csize = pick_cluster(ctx, count, B);
+    b->trackers.assign(trackers, trackers + count);
+    std::vector<ProblemDesc> hd(count);
     for (int i = 0; i < count; ++i) hd[i] = make_desc(trackers[i], keyframes[i], frames, first_slot + i);
-    EDS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, hd, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    const int csize = pick_cluster(ctx, count, B);
-    st = launch_cluster(ctx, track_lm_kernel, (const ProblemDesc*)ctx->scratch, count, csize);
+    cudaError_t e = cudaMalloc(&b->desc, sizeof(ProblemDesc) * (size_t)count);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->desc, hd.data(), sizeof(ProblemDesc) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // hd is a stack-owned source
+    if (e != cudaSuccess) { edsgpu_batch_destroy(b); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
+    *out = b;
+    return EDSGPU_OK;
+}
+
+void edsgpu_batch_destroy(edsgpu_batch* b) {
+    if (!b) return;
+    DeviceGuard g(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->desc) cudaFree(b->desc);
+    delete b;
+}
+
+edsgpu_status edsgpu_batch_optimize(edsgpu_batch* b) {
+    if (!b) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    edsgpu_status st = launch_cluster(ctx, track_lm_kernel, (const ProblemDesc*)b->desc, b->count, b->csize);
     if (st != EDSGPU_OK) return st;
-    mad_kernel<<<count, MAD_THREADS, 0, ctx->stream>>>((const ProblemDesc*)ctx->scratch);
+    mad_kernel<<<b->count, MAD_THREADS, 0, ctx->stream>>>((const ProblemDesc*)b->desc);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
     return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_batch_pack_states_dev(edsgpu_batch* b, double* states_dev) {
+    if (!b || !states_dev) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = b->ctx;
+    DeviceGuard g(ctx->device);
+    for (int i = 0; i < b->count; ++i)
+        EDS_CUDA(ctx, cudaMemcpyAsync(states_dev + 14 * i, b->trackers[i]->state, 14 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_trackers_optimize_batch(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes, int count,
+                                             const edsgpu_frames* frames, int first_slot) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_batch* b = nullptr;
+    edsgpu_status st = edsgpu_batch_create(ctx, trackers, keyframes, count, frames, first_slot, &b);
+    if (st != EDSGPU_OK) return st;
+    st = edsgpu_batch_optimize(b);
+    edsgpu_batch_destroy(b);  // synchronises: the descriptors must outlive the launch
+    return st;
 }
 
 edsgpu_status edsgpu_trackers_gather(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, int count, double* states_out, edsgpu_tracker_info* infos_out) {
@@ -1123,9 +1175,17 @@ edsgpu_status edsgpu_tracker_optimize(edsgpu_tracker* tr, const edsgpu_keyframe*
                                       double qx[4], double vx[6], double* residuals_out, double* next_loss_param_out, edsgpu_tracker_info* info) {
     if (!tr) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = tr->ctx;
-    const edsgpu_keyframe* kfs[1] = {kf};
-    edsgpu_tracker* trs[1] = {tr};
-    edsgpu_status st = edsgpu_trackers_optimize_batch(ctx, trs, kfs, 1, frames, slot);
+    EDS_REQUIRE(ctx, kf && frames, "tracker_optimize: null handle");
+    if (!tr->cached || tr->cached_kf != kf->uid || tr->cached_frames != frames->uid || tr->cached_slot != slot) {
+        if (tr->cached) edsgpu_batch_destroy(tr->cached);
+        tr->cached = nullptr;
+        const edsgpu_keyframe* kfs[1] = {kf};
+        edsgpu_tracker* trs[1] = {tr};
+        edsgpu_status stc = edsgpu_batch_create(ctx, trs, kfs, 1, frames, slot, &tr->cached);
+        if (stc != EDSGPU_OK) return stc;
+        tr->cached_kf = kf->uid; tr->cached_frames = frames->uid; tr->cached_slot = slot;
+    }
+    edsgpu_status st = edsgpu_batch_optimize(tr->cached);
     if (st != EDSGPU_OK) return st;
     DeviceGuard g(ctx->device);
     edsgpu_tracker_info inf;

@@ -29,6 +29,7 @@ SYMBOLS = [
     "edsgpu_frames_read", "edsgpu_frames_read_accumulator", "edsgpu_keyframe_create", "edsgpu_keyframe_destroy",
     "edsgpu_tracker_create", "edsgpu_tracker_destroy", "edsgpu_tracker_set_state", "edsgpu_tracker_get_state",
     "edsgpu_tracker_optimize", "edsgpu_trackers_optimize_batch", "edsgpu_trackers_gather", "edsgpu_tracker_state_dev",
+    "edsgpu_batch_create", "edsgpu_batch_destroy", "edsgpu_batch_optimize", "edsgpu_batch_pack_states_dev",
     "edsgpu_tracker_evaluate",
 ]
 
@@ -48,7 +49,7 @@ class TrackerConfig(C.Structure):
 class TrackerInfo(C.Structure):
     _fields_ = [("iterations", C.c_int), ("successful_steps", C.c_int), ("unsuccessful_steps", C.c_int),
                 ("termination", C.c_int), ("usable", C.c_int), ("num_points", C.c_int),
-                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("final_radius", C.c_double)]
+                ("evaluations", C.c_int), ("reserved", C.c_int), ("initial_cost", C.c_double), ("final_cost", C.c_double), ("final_radius", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -69,7 +70,7 @@ def load():
         lib.edsgpu_tracker_state_dev.restype = C.c_void_p
         lib.edsgpu_tracker_state_dev.argtypes = [C.c_void_p]
         for name in ("edsgpu_destroy", "edsgpu_lut_destroy", "edsgpu_frames_destroy", "edsgpu_keyframe_destroy",
-                     "edsgpu_tracker_destroy"):
+                     "edsgpu_tracker_destroy", "edsgpu_batch_destroy"):
             getattr(lib, name).restype = None
             getattr(lib, name).argtypes = [C.c_void_p]
         _lib = lib
@@ -276,18 +277,24 @@ def event_frames_batch_dev(ctx, frames, first_slot, count, x_ptr, y_ptr, pol_ptr
 
 
 class TrackerBatch:
-    """`count` independent trackers advanced by one launch (edsgpu_trackers_optimize_batch)."""
+    """`count` independent trackers advanced by one launch (edsgpu_batch_*): tracker i runs against
+    keyframe i and frame slot first_slot+i; descriptors are built once."""
 
-    def __init__(self, ctx, trackers, keyframes):
-        self.ctx, self.trackers, self.keyframes = ctx, trackers, keyframes
+    def __init__(self, ctx, trackers, keyframes, frames, first_slot=0):
+        self.ctx, self.trackers, self.keyframes, self.frames = ctx, trackers, keyframes, frames
         n = len(trackers)
         self._tr = (C.c_void_p * n)(*[t.h for t in trackers])
         self._kf = (C.c_void_p * n)(*[k.h for k in keyframes])
         self.count = n
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.edsgpu_batch_create(ctx.h, self._tr, self._kf, C.c_int(n), frames.h, C.c_int(first_slot),
+                                              C.byref(self.h)))
 
-    def optimize(self, frames, first_slot=0):
-        self.ctx.check(self.ctx.lib.edsgpu_trackers_optimize_batch(self.ctx.h, self._tr, self._kf, C.c_int(self.count),
-                                                                   frames.h, C.c_int(first_slot)))
+    def optimize(self):
+        self.ctx.check(self.ctx.lib.edsgpu_batch_optimize(self.h))
+
+    def pack_states_dev(self, dev_ptr):
+        self.ctx.check(self.ctx.lib.edsgpu_batch_pack_states_dev(self.h, C.c_void_p(dev_ptr)))
 
     def gather(self, want_infos=True):
         states = np.zeros((self.count, 14))
@@ -295,6 +302,11 @@ class TrackerBatch:
         self.ctx.check(self.ctx.lib.edsgpu_trackers_gather(self.ctx.h, self._tr, C.c_int(self.count),
                                                            _ptr(states, C.c_double), infos))
         return states, ([i.as_dict() for i in infos] if want_infos else None)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.edsgpu_batch_destroy(self.h)
+            self.h = None
 
 
 def tracker_evaluate(ctx, kf, frames, slot, x, loss_type=LOSS_HUBER, loss_param=0.05, want_jacobian=True):

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_version_and_struct_sizes(lib):
     assert b"sm_100a" in lib.edsgpu_version()
     assert ctypes.sizeof(edsgpu.TrackerConfig) == 40
-    assert ctypes.sizeof(edsgpu.TrackerInfo) == 48
+    assert ctypes.sizeof(edsgpu.TrackerInfo) == 56
 
 
 def test_library_is_built_for_sm_100a():

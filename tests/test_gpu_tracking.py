@@ -247,9 +247,10 @@ def test_batch_matches_single_and_is_independent_of_cluster_size(gpu_ctx, proble
     for i, t in enumerate(trs):
         x0 = wins[i % 2]["x_init"]
         t.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
-    batch = edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * n)
-    batch.optimize(fr, 0)
+    batch = edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * n, fr, 0)
+    batch.optimize()
     states, infos = batch.gather()
+    batch.close()
     for k in (0, 1):
         single = edsgpu.Tracker(gpu_ctx, num_blocks=8, max_iterations=12)
         x0 = wins[k]["x_init"]
@@ -258,6 +259,7 @@ def test_batch_matches_single_and_is_independent_of_cluster_size(gpu_ctx, proble
         for i in range(k, n, 2):
             assert np.array_equal(states[i, :13], r["x"]) and states[i, 13] == r["next_loss_param"]
             assert infos[i]["iterations"] == r["info"]["iterations"] and infos[i]["usable"] == 1
+            assert infos[i]["evaluations"] == r["info"]["evaluations"] >= 1
         single.close()
     for t in trs:
         t.close()
