@@ -481,7 +481,35 @@ __device__ int lm_advance_warp(const ProblemDesc& P, CtaShared& sh) {
     if (take) {
         // EvaluateGradientAndJacobian: Jacobi scaling (iteration 0 only), scaled system,
         // gradient max norm || x - Plus(x, -g) ||_inf, ||x||
-        if (first && lane < 12) lm.scale[lane] = 1.0 / (1.0 + sqrt(sh.sum[tri_index(lane, lane)]));
+        // The unit-norm retraction makes n = [0(6), v/|v|] an exact null direction of J.
+        // The fp32 sweep leaves ~1e-7 of noise along it, which a large trust-region radius
+        // (D^2 -> 1e-12) would amplify into the step.  Project the reduced system in fp64:
+        // H <- Pi H Pi, g <- Pi g, Pi = I - n n^T, so the device behaves like exact arithmetic.
+        {
+            const double vq = (lane >= 6 && lane < 12) ? lm.x[1 + lane] : 0.0;
+            const double inv_n = rsqrt(warp_sum(vq * vq));
+            const double na = vq * inv_n;
+            const int la = lane < 12 ? lane : 0;
+            double wa = 0.0;
+#pragma unroll
+            for (int b = 6; b < 12; ++b) {
+                const double nb = __shfl_sync(FULL, na, b);
+                wa += sh.sum[la <= b ? tri_index(la, b) : tri_index(b, la)] * nb;
+            }
+            if (lane >= 12) wa = 0.0;
+            const double sw = warp_sum(na * wa);
+            const double ga = (lane < 12) ? sh.sum[78 + la] : 0.0;
+            const double gn = warp_sum(na * ga);
+            __syncwarp();
+            if (lane < 12) { lm.delta[lane] = na; lm.diag[lane] = wa; sh.sum[78 + lane] = ga - na * gn; }
+            __syncwarp();
+            for (int e = lane; e < 78; e += 32) {
+                const int a = c_tri_a[e], b = c_tri_b[e];
+                sh.sum[e] = sh.sum[e] - lm.delta[a] * lm.diag[b] - lm.diag[a] * lm.delta[b] + lm.delta[a] * lm.delta[b] * sw;
+            }
+            __syncwarp();
+        }
+        if (first && lane < 12) lm.scale[lane] = 1.0 / (1.0 + sqrt(fmax(sh.sum[tri_index(lane, lane)], 0.0)));
         __syncwarp();
         for (int e = lane; e < 78; e += 32) lm.Hs[e] = sh.sum[e] * lm.scale[c_tri_a[e]] * lm.scale[c_tri_b[e]];
         if (lane < 12) lm.gs[lane] = sh.sum[78 + lane] * lm.scale[lane];
