@@ -184,6 +184,50 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
                                       const double vx[6], double* residuals_out, double* jacobian_out, double* cost_out,
                                       double* H_out, double* g_out);
 
+/* ---- B. windowed-BA Hessian accumulation -------------------------------------------------- */
+/* One BA window = the residual graph the EnergyFunctional owns (EnergyFunctional.h:63-69,137-148):
+ * F frames (<= 8; setting_maxFrames = 7), P points, R residuals stored POINT-MAJOR like
+ * EFPoint::residualsAll: residuals of point p are [res_begin[p], res_begin[p+1]); host_idx/target_idx
+ * are EFResidual::hostIDX/targetIDX.  The (host,target) tile plan is built once per graph. */
+typedef struct edsgpu_ba edsgpu_ba;
+#define EDSGPU_RAWJAC_FLOATS 76  /* dso::RawResidualJacobian (RawResidualJacobian.h:32-61) as Eigen lays it out
+                                    with 16-byte alignment (304 B): resF[8] @0, Jpdxi[2][6] @8, Jpdc[2][4] @20, Jpdd[2] @28,
+                                    pad[2], JIdx[2][8] @32, JabF[2][8] @48, JIdx2 @64, JabJIdx @68, Jab2 @72 (Mat22f column-major) */
+enum { EDSGPU_RES_ACTIVE = 1, EDSGPU_RES_LINEARIZED = 2 };  /* EFResidual::isActive(), isLinearized */
+edsgpu_status edsgpu_ba_create(edsgpu_ctx* ctx, int num_frames, int num_points, int num_residuals, const int32_t* host_idx,
+                               const int32_t* target_idx, const int32_t* res_begin, edsgpu_ba** out);
+void edsgpu_ba_destroy(edsgpu_ba* ba);
+/* per linearisation: records (R x 76 floats), flags (R), EFResidual::res_toZeroF (R x 8, NULL if unused).
+ * Also evaluates EFResidual::takeDataF's JpJdF (EnergyFunctionalStructs.cpp:38-48) on the device. */
+edsgpu_status edsgpu_ba_set_residuals(edsgpu_ba* ba, const float* records, const uint8_t* flags, const float* res_toZero);
+/* EFPoint::deltaF, priorF (EnergyFunctionalStructs.cpp:77-83); NULL = zeros. */
+edsgpu_status edsgpu_ba_set_points(edsgpu_ba* ba, const float* deltaF, const float* priorF);
+/* EnergyFunctional::adHTdeltaF (F*F x 8), cDeltaF (4) (EnergyFunctional.cpp:171-184), adHost/adTarget
+ * (F*F Mat88, column-major = reinterpret_cast<const double*>(EF->adHost), EnergyFunctional.cpp:46-106); any may be NULL (kept). */
+edsgpu_status edsgpu_ba_set_frames(edsgpu_ba* ba, const float* adHTdeltaF, const float* cDeltaF, const double* adHost,
+                                   const double* adTarget);
+/* AccumulatedTopHessianSSE::addPoint<mode> over all points (EnergyFunctional.cpp:197-238; mode 0 active,
+ * 1 linearized, 2 marginalize; AccumulatedTopHessian.cpp:39-159).  acc_out: F*F x 13x13 doubles
+ * (AccumulatorApprox::finish()'s H, index order [C(4) xi(6) a b r], accumulator h + t*F);
+ * Hdd/bd (P) and Hcd (P x 4) are EFPoint::{Hdd,bd,Hcd}_acc{A,L}F.  All outputs optional; with none the
+ * call is asynchronous and the results stay on the device for the stitch / SC calls. */
+edsgpu_status edsgpu_ba_top_accumulate(edsgpu_ba* ba, int mode, double* acc_out, float* Hdd_out, float* bd_out, float* Hcd_out,
+                                       int64_t* nres_out);
+/* AccumulatedTopHessianSSE::stitchDoubleMT (AccumulatedTopHessian.h:91-139): which = 0 the mode-0
+ * accumulators, 1 the mode-1/2 ones.  H: (4+8F)^2 column-major (Eigen MatXX), b: 4+8F.
+ * use_prior adds cPrior / EFFrame::prior / delta_prior (.cpp:292-302). */
+edsgpu_status edsgpu_ba_top_stitch(edsgpu_ba* ba, int which, int use_prior, const double* cPrior, const double* frame_prior,
+                                   const double* frame_delta_prior, double* H, double* b);
+/* AccumulatedSCHessianSSE::addPoint over all points (EnergyFunctional.cpp:244-261, AccumulatedSCHessian.cpp:34-77)
+ * from the device-resident results of the two top accumulations.  accD: F^3 x 8x8 (index h + t1*F + t2*F*F),
+ * accE: F*F x 8x4, accEB: F*F x 8, accHcc 4x4, accbc 4 (row-major doubles); HdiF/bdSum: EFPoint::HdiF, bdSumF. */
+edsgpu_status edsgpu_ba_sc_accumulate(edsgpu_ba* ba, int shift_prior_to_zero, double* accD, double* accE, double* accEB,
+                                      double* accHcc, double* accbc, float* HdiF_out, float* bdSum_out);
+/* AccumulatedSCHessianSSE::stitchDoubleMT (AccumulatedSCHessian.h:93-133). */
+edsgpu_status edsgpu_ba_sc_stitch(edsgpu_ba* ba, double* H, double* b);
+/* EFResidual::JpJdF of every residual (R x 8). */
+edsgpu_status edsgpu_ba_get_jpjd(edsgpu_ba* ba, float* JpJdF_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,827 @@
+// DSO-derived windowed-BA Hessian accumulation on the device.
+//
+// Replaces AccumulatedTopHessianSSE::addPoint<mode> + stitchDoubleMT (reference
+// src/bundles/AccumulatedTopHessian.{h,cpp}), AccumulatedSCHessianSSE::addPoint + stitchDoubleMT
+// (src/bundles/AccumulatedSCHessian.{h,cpp}), the AccumulatorApprox / AccumulatorXX float
+// accumulators (src/bundles/MatrixAccumulators.h) and EFResidual::takeDataF
+// (src/bundles/EnergyFunctionalStructs.cpp:38-48).
+//
+//   plan (host, once per graph)   residuals bucketed by (host,target) with a stable counting sort
+//                                 and cut into single-key tiles: every CTA reduces into ONE 13x13
+//                                 accumulator, no atomics, fixed summation order (the reference's
+//                                 6-thread work stealing makes its float sums differ run to run).
+//   ba_top_kernel<mode>           one thread per residual record (19 x 128-bit loads of the 304-byte
+//                                 RawResidualJacobian), 91 fp32 accumulators per thread, halving warp
+//                                 butterfly, fp64 across warps -> one partial per tile; per-residual
+//                                 Hdd/bd/Hcd terms written for the point pass.
+//   ba_top_finalize_kernel        ordered fp64 sum of the tile partials -> F*F x 13x13 doubles.
+//   ba_point_sum_kernel           per point: Hdd_acc, bd_acc, Hcd_acc over its residuals (in order).
+//   ba_sc_kernel                  per host frame the Schur terms are one weighted Gram matrix
+//                                 sum_p HdiF_p [z_p; Hcd_p] [z_p; Hcd_p; bdSum_p]^T with z_p the
+//                                 stacked JpJdF of the point's active residuals: register-tiled 4x4
+//                                 through shared memory, chunked over points, ordered fp64 finalize.
+//   ba_*_stitch_kernel            one CTA per 8x8 output block of H (adjoint sandwiches in fp64).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int REC = 76;  // floats per record: dso::RawResidualJacobian as laid out by Eigen (304 B)
+constexpr int O_RES = 0, O_JPDXI0 = 8, O_JPDXI1 = 14, O_JPDC0 = 20, O_JPDC1 = 24, O_JPDD = 28, O_JIDX0 = 32, O_JIDX1 = 40,
+              O_JAB0 = 48, O_JAB1 = 56, O_JIDX2 = 64, O_JABJIDX = 68, O_JAB2 = 72;
+constexpr int CPARS = 4;
+constexpr int TOP_THREADS = 256, TOP_TILE = 512, NACC = 96;
+constexpr int MAXF = 8;
+constexpr int SC_THREADS = 256, SC_CHUNK = 128, SC_BATCH = 16, SC_LD = 72;  // 8*MAXF + 5 padded to 72
+
+struct BaDev {
+    int F, P, R, num_tiles;
+    const int32_t *host_idx, *target_idx, *point_of_res, *res_begin, *perm, *tile_key, *tile_start, *tile_count, *key_tile_begin;
+    const float *recs, *res_toZero, *deltaF, *priorF, *adHTdeltaF, *cDeltaF;
+    const uint8_t* flags;
+    float* res_pt;        // R x 6: bd, Hdd, Hcd[4] of each residual (zero when filtered out)
+    double* tile_partial; // num_tiles x 96
+    int* tile_nres;       // num_tiles
+};
+
+template <int HALF, int OFFSET>
+__device__ __forceinline__ void butterfly_step(float* a, unsigned lane) {
+    const bool upper = (lane & OFFSET) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        const float send = upper ? a[i] : a[i + HALF];
+        const float keep = upper ? a[i + HALF] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFFSET);
+    }
+}
+__device__ __forceinline__ int butterfly_base(unsigned lane) {
+    return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
+}
+
+// EFResidual::takeDataF (EnergyFunctionalStructs.cpp:38-48)
+__global__ void ba_jpjd_kernel(const float* __restrict__ recs, int R, float* __restrict__ JpJdF) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* J = recs + (size_t)REC * r;
+    const float d0 = J[O_JPDD], d1 = J[O_JPDD + 1];
+    const float* M = J + O_JIDX2;  // Mat22f column-major
+    const float v0 = M[0] * d0 + M[2] * d1;
+    const float v1 = M[1] * d0 + M[3] * d1;
+    float out[8];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) out[i] = J[O_JPDXI0 + i] * v0 + J[O_JPDXI1 + i] * v1;
+    const float* N = J + O_JABJIDX;
+    out[6] = N[0] * d0 + N[2] * d1;
+    out[7] = N[1] * d0 + N[3] * d1;
+    float4* o = reinterpret_cast<float4*>(JpJdF + (size_t)8 * r);
+    o[0] = make_float4(out[0], out[1], out[2], out[3]);
+    o[1] = make_float4(out[4], out[5], out[6], out[7]);
+}
+
+// AccumulatedTopHessianSSE::addPoint<MODE> (AccumulatedTopHessian.cpp:39-159) over one single-key tile.
+// Accumulator order (AccumulatorApprox, MatrixAccumulators.h:595-651): 55 upper-triangle entries of the
+// 10x10 [C(4) xi(6)] block, 30 of the 10x3 top-right block [a b r], 6 of the 3x3 bottom-right block.
+template <int MODE>
+__global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(BaDev W) {
+    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int key = W.tile_key[tile], start = W.tile_start[tile], count = W.tile_count[tile];
+    __shared__ double warp_part[TOP_THREADS / 32][NACC];
+    __shared__ int warp_n[TOP_THREADS / 32];
+    float dp[8], dc[4];
+    if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dp[k] = W.adHTdeltaF[8 * key + k];  // ef->adHTdeltaF[htIDX], :72
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dc[k] = W.cDeltaF[k];
+    }
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    int nres = 0;
+    for (int i = tid; i < count; i += TOP_THREADS) {
+        const int r = W.perm[start + i];
+        const unsigned fl = W.flags[r];
+        const bool active = fl & 1u, lin = fl & 2u;
+        bool use;
+        if (MODE == 0) use = active && !lin;        // :55-58
+        else if (MODE == 1) use = active && lin;    // :59-62
+        else use = active;                          // :63-67
+        float pt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (use) {
+            const float4* rec4 = reinterpret_cast<const float4*>(W.recs + (size_t)REC * r);
+            float J[REC];
+#pragma unroll
+            for (int k = 0; k < REC / 4; ++k) {
+                const float4 v = __ldg(rec4 + k);
+                J[4 * k] = v.x; J[4 * k + 1] = v.y; J[4 * k + 2] = v.z; J[4 * k + 3] = v.w;
+            }
+            float res[8];
+            if (MODE == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) res[k] = J[O_RES + k];
+            } else {
+                const float4* rz = reinterpret_cast<const float4*>(W.res_toZero + (size_t)8 * r);
+                const float4 a = __ldg(rz), b = __ldg(rz + 1);
+                res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w; res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
+                if (MODE == 1) {  // :81-99: rtz + [JI*Jp Ja]*delta
+                    const float dd = W.deltaF[W.point_of_res[r]];
+                    float jx = 0.f, jy = 0.f, cxs = 0.f, cys = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { jx += J[O_JPDXI0 + k] * dp[k]; jy += J[O_JPDXI1 + k] * dp[k]; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { cxs += J[O_JPDC0 + k] * dc[k]; cys += J[O_JPDC1 + k] * dc[k]; }
+                    jx = jx + cxs + J[O_JPDD] * dd;
+                    jy = jy + cys + J[O_JPDD + 1] * dd;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        res[k] = res[k] + J[O_JIDX0 + k] * jx + J[O_JIDX1 + k] * jy + J[O_JAB0 + k] * dp[6] + J[O_JAB1 + k] * dp[7];
+                }
+            }
+            // :102-112
+            float JIr0 = 0.f, JIr1 = 0.f, Jabr0 = 0.f, Jabr1 = 0.f, rr = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                JIr0 += res[k] * J[O_JIDX0 + k];
+                JIr1 += res[k] * J[O_JIDX1 + k];
+                Jabr0 += res[k] * J[O_JAB0 + k];
+                Jabr1 += res[k] * J[O_JAB1 + k];
+                rr += res[k] * res[k];
+            }
+            // x = [Jpdc[0] Jpdxi[0]], y = [Jpdc[1] Jpdxi[1]]  (:115-129)
+            float x[10], y[10];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { x[k] = J[O_JPDC0 + k]; y[k] = J[O_JPDC1 + k]; }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { x[4 + k] = J[O_JPDXI0 + k]; y[4 + k] = J[O_JPDXI1 + k]; }
+            const float a = J[O_JIDX2], b = J[O_JIDX2 + 2], c = J[O_JIDX2 + 3];  // (0,0) (0,1) (1,1), column-major
+            // AccumulatorApprox::update: a x x^T + c y y^T + b (x y^T + y x^T) = x (a x + b y)^T + y (b x + c y)^T
+            float px[10], py[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) { px[k] = a * x[k] + b * y[k]; py[k] = b * x[k] + c * y[k]; }
+            int e = 0;
+#pragma unroll
+            for (int p = 0; p < 10; ++p)
+#pragma unroll
+                for (int q = p; q < 10; ++q) acc[e++] += x[p] * px[q] + y[p] * py[q];
+            // updateTopRight: TR00,TR10 = JabJIdx(0,0),(0,1); TR01,TR11 = JabJIdx(1,0),(1,1); TR02,TR12 = JI_r
+            const float t00 = J[O_JABJIDX], t10 = J[O_JABJIDX + 2], t01 = J[O_JABJIDX + 1], t11 = J[O_JABJIDX + 3];
+#pragma unroll
+            for (int p = 0; p < 10; ++p) {
+                acc[55 + 3 * p] += x[p] * t00 + y[p] * t10;
+                acc[55 + 3 * p + 1] += x[p] * t01 + y[p] * t11;
+                acc[55 + 3 * p + 2] += x[p] * JIr0 + y[p] * JIr1;
+            }
+            // updateBotRight
+            acc[85] += J[O_JAB2]; acc[86] += J[O_JAB2 + 2]; acc[87] += Jabr0;
+            acc[88] += J[O_JAB2 + 3]; acc[89] += Jabr1; acc[90] += rr;
+            // :132-135
+            const float d0 = J[O_JPDD], d1 = J[O_JPDD + 1];
+            const float q0 = a * d0 + b * d1, q1 = b * d0 + c * d1;
+            pt[0] = JIr0 * d0 + JIr1 * d1;
+            pt[1] = q0 * d0 + q1 * d1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pt[2 + k] = J[O_JPDC0 + k] * q0 + J[O_JPDC1 + k] * q1;
+            nres++;
+        }
+        float2* o = reinterpret_cast<float2*>(W.res_pt + (size_t)6 * r);
+        o[0] = make_float2(pt[0], pt[1]); o[1] = make_float2(pt[2], pt[3]); o[2] = make_float2(pt[4], pt[5]);
+    }
+    butterfly_step<48, 16>(acc, lane);
+    butterfly_step<24, 8>(acc, lane);
+    butterfly_step<12, 4>(acc, lane);
+    butterfly_step<6, 2>(acc, lane);
+    butterfly_step<3, 1>(acc, lane);
+    const int base = butterfly_base(lane);
+    warp_part[warp][base] = (double)acc[0];
+    warp_part[warp][base + 1] = (double)acc[1];
+    warp_part[warp][base + 2] = (double)acc[2];
+    for (int o = 16; o > 0; o >>= 1) nres += __shfl_xor_sync(0xffffffffu, nres, o);
+    if (lane == 0) warp_n[warp] = nres;
+    __syncthreads();
+    if (tid < NACC) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < TOP_THREADS / 32; ++w) s += warp_part[w][tid];
+        W.tile_partial[(size_t)NACC * tile + tid] = s;
+    }
+    if (tid == 0) {
+        int n = 0;
+        for (int w = 0; w < TOP_THREADS / 32; ++w) n += warp_n[w];
+        W.tile_nres[tile] = n;
+    }
+}
+
+// ordered fp64 sum of the tile partials of each key -> 13x13 (AccumulatorApprox::finish layout)
+__global__ void ba_top_finalize_kernel(BaDev W, double* __restrict__ acc /*F*F x 169*/, long long* __restrict__ num /*F*F*/) {
+    const int key = blockIdx.x, e = threadIdx.x;
+    const int t0 = W.key_tile_begin[key], t1 = W.key_tile_begin[key + 1];
+    if (e < 91) {
+        double s = 0.0;
+        for (int t = t0; t < t1; ++t) s += W.tile_partial[(size_t)NACC * t + e];
+        int r, c;
+        if (e < 55) {
+            int p = 0, rem = e;
+            while (rem >= 10 - p) { rem -= 10 - p; ++p; }
+            r = p; c = p + rem;
+        } else if (e < 85) { r = (e - 55) / 3; c = 10 + (e - 55) % 3; }
+        else { const int br[6][2] = {{10, 10}, {10, 11}, {10, 12}, {11, 11}, {11, 12}, {12, 12}}; r = br[e - 85][0]; c = br[e - 85][1]; }
+        double* H = acc + (size_t)169 * key;
+        H[13 * r + c] = s;
+        H[13 * c + r] = s;
+    }
+    if (e == 95) {
+        long long n = 0;
+        for (int t = t0; t < t1; ++t) n += W.tile_nres[t];
+        num[key] = n;
+    }
+}
+
+// per point: Hdd_acc, bd_acc, Hcd_acc (AccumulatedTopHessian.cpp:132-157), residuals in their stored order
+__global__ void ba_point_sum_kernel(const float* __restrict__ res_pt, const int32_t* __restrict__ res_begin, int P,
+                                    float* __restrict__ Hdd, float* __restrict__ bd, float* __restrict__ Hcd) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = res_begin[p]; r < res_begin[p + 1]; ++r) {
+        const float2* v = reinterpret_cast<const float2*>(res_pt + (size_t)6 * r);
+        const float2 a = __ldg(v), b = __ldg(v + 1), c = __ldg(v + 2);
+        s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y;
+    }
+    bd[p] = s[0];
+    Hdd[p] = s[1];
+    reinterpret_cast<float4*>(Hcd)[p] = make_float4(s[2], s[3], s[4], s[5]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Schur complement (AccumulatedSCHessianSSE::addPoint, AccumulatedSCHessian.cpp:34-77)
+// ------------------------------------------------------------------------------------------
+struct ScDev {
+    int F, P, shift_prior;
+    const int32_t *res_begin, *target_idx, *pt_perm, *chunk_host, *chunk_start, *chunk_count;
+    const uint8_t* flags;
+    const float *JpJdF, *HddA, *HddL, *bdA, *bdL, *HcdA, *HcdL, *priorF, *deltaF;
+    float *HdiF, *bdSum;
+    float* partial;  // num_chunks x M x N
+};
+
+__global__ void __launch_bounds__(SC_THREADS) ba_sc_kernel(ScDev S) {
+    const int chunk = blockIdx.x, tid = threadIdx.x;
+    const int F = S.F, M = 8 * F + 4, N = 8 * F + 5;
+    const int tiles_n = (N + 3) / 4, tiles = ((M + 3) / 4) * tiles_n;
+    const int start = S.chunk_start[chunk], count = S.chunk_count[chunk];
+    __shared__ __align__(16) float z[SC_BATCH][SC_LD];   // column side: [z (8F) | Hcd (4) | bdSum]
+    __shared__ __align__(16) float zs[SC_BATCH][SC_LD];  // row side, pre-scaled by HdiF
+    float acc[2][16];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[t][i] = 0.f;
+    for (int b0 = 0; b0 < count; b0 += SC_BATCH) {
+        const int nb = min(SC_BATCH, count - b0);
+        __syncthreads();
+        for (int i = tid; i < SC_BATCH * SC_LD; i += SC_THREADS) { (&z[0][0])[i] = 0.f; (&zs[0][0])[i] = 0.f; }
+        __syncthreads();
+        if (tid < nb) {
+            const int p = S.pt_perm[start + b0 + tid];
+            int ngood = 0;
+            for (int r = S.res_begin[p]; r < S.res_begin[p + 1]; ++r) ngood += (S.flags[r] & 1u);
+            float HdiF = 0.f, bdSum = 0.f;
+            if (ngood > 0) {  // :38-56
+                float Hh = S.HddA[p] + S.HddL[p] + S.priorF[p];
+                if (Hh < 1e-10f) Hh = 1e-10f;
+                HdiF = (float)(1.0 / (double)Hh);
+                bdSum = S.bdA[p] + S.bdL[p];
+                if (S.shift_prior) bdSum += S.priorF[p] * S.deltaF[p];
+                for (int r = S.res_begin[p]; r < S.res_begin[p + 1]; ++r) {
+                    if (!(S.flags[r] & 1u)) continue;
+                    const int t = S.target_idx[r];
+                    const float4* j = reinterpret_cast<const float4*>(S.JpJdF + (size_t)8 * r);
+                    const float4 a = __ldg(j), b = __ldg(j + 1);
+                    float* zz = &z[tid][8 * t];
+                    zz[0] = a.x; zz[1] = a.y; zz[2] = a.z; zz[3] = a.w; zz[4] = b.x; zz[5] = b.y; zz[6] = b.z; zz[7] = b.w;
+                }
+                const float4 ha = reinterpret_cast<const float4*>(S.HcdA)[p], hl = reinterpret_cast<const float4*>(S.HcdL)[p];
+                z[tid][8 * F] = ha.x + hl.x; z[tid][8 * F + 1] = ha.y + hl.y; z[tid][8 * F + 2] = ha.z + hl.z; z[tid][8 * F + 3] = ha.w + hl.w;
+                z[tid][8 * F + 4] = bdSum;
+                for (int k = 0; k < M; ++k) zs[tid][k] = HdiF * z[tid][k];
+            }
+            S.HdiF[p] = HdiF;
+            S.bdSum[p] = bdSum;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int tl = tid + t * SC_THREADS;
+            if (tl < tiles) {
+                const int i0 = 4 * (tl / tiles_n), j0 = 4 * (tl % tiles_n);
+                for (int q = 0; q < nb; ++q) {
+                    const float4 rv = *reinterpret_cast<const float4*>(&zs[q][i0]);
+                    const float4 cv = *reinterpret_cast<const float4*>(&z[q][j0]);
+                    const float rr[4] = {rv.x, rv.y, rv.z, rv.w}, cc[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[t][4 * i + j] += rr[i] * cc[j];
+                }
+            }
+        }
+    }
+    float* out = S.partial + (size_t)chunk * M * N;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int tl = tid + t * SC_THREADS;
+        if (tl < tiles) {
+            const int i0 = 4 * (tl / tiles_n), j0 = 4 * (tl % tiles_n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i0 + i < M && j0 + j < N) out[(size_t)(i0 + i) * N + j0 + j] = acc[t][4 * i + j];
+        }
+    }
+}
+
+// ordered fp64 sum over the chunks of each host -> accD / accE / accEB, per-host Hcc|bc
+__global__ void ba_sc_finalize_kernel(int F, const float* __restrict__ partial, const int32_t* __restrict__ host_chunk_begin,
+                                      double* __restrict__ accD, double* __restrict__ accE, double* __restrict__ accEB,
+                                      double* __restrict__ hcc_host /*F x 20*/) {
+    const int h = blockIdx.x, M = 8 * F + 4, N = 8 * F + 5, F2 = F * F;
+    const int c0 = host_chunk_begin[h], c1 = host_chunk_begin[h + 1];
+    for (int e = threadIdx.x; e < M * N; e += blockDim.x) {
+        double s = 0.0;
+        for (int c = c0; c < c1; ++c) s += (double)partial[(size_t)c * M * N + e];
+        const int i = e / N, j = e % N;
+        if (i < 8 * F) {
+            const int t1 = i / 8, a = i % 8;
+            if (j < 8 * F) {           // accD[h + t1*F + t2*F2] (8x8)
+                const int t2 = j / 8, b = j % 8;
+                accD[(size_t)64 * (h + t1 * F + t2 * F2) + 8 * a + b] = s;
+            } else if (j < 8 * F + 4) {  // accE[h + t1*F] (8x4)
+                accE[(size_t)32 * (h + t1 * F) + 4 * a + (j - 8 * F)] = s;
+            } else {                    // accEB[h + t1*F] (8)
+                accEB[(size_t)8 * (h + t1 * F) + a] = s;
+            }
+        } else if (j >= 8 * F) {      // Hcd rows: [Hcc (4x4) | bc (4)]; the Hcd x z^T part is E^T, not needed
+            hcc_host[20 * h + 5 * (i - 8 * F) + (j - 8 * F)] = s;
+        }
+    }
+}
+__global__ void ba_sc_hcc_kernel(int F, const double* __restrict__ hcc_host, double* __restrict__ accHcc, double* __restrict__ accbc) {
+    const int e = threadIdx.x;
+    if (e >= 20) return;
+    double s = 0.0;
+    for (int h = 0; h < F; ++h) s += hcc_host[20 * h + e];
+    const int i = e / 5, j = e % 5;
+    if (j < 4) accHcc[4 * i + j] = s; else accbc[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// stitches: one CTA (64 threads) per 8x8 output block (a,b) of H, fp64
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double adj(const double* A, int r, int c) { return A[c * 8 + r]; }  // Mat88 column-major
+
+// out(i,j) += sum_m sum_n L(i,m) C(m,n) Rt(j,n), C given by functor c(m,n); thread (i,j)
+template <typename CF>
+__device__ __forceinline__ double sandwich(const double* L, CF c, const double* Rm, int i, int j) {
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        double t = 0.0;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) t += c(m, n) * adj(Rm, j, n);
+        s += adj(L, i, m) * t;
+    }
+    return s;
+}
+
+// AccumulatedTopHessianSSE::stitchDoubleInternal (AccumulatedTopHessian.cpp:241-303), by output block.
+__global__ void ba_top_stitch_kernel(int F, const double* __restrict__ acc, const double* __restrict__ adHost,
+                                     const double* __restrict__ adTarget, int use_prior, const double* __restrict__ cPrior,
+                                     const float* __restrict__ cDeltaF, const double* __restrict__ frame_prior,
+                                     const double* __restrict__ frame_delta_prior, double* __restrict__ H, double* __restrict__ bvec) {
+    const int a = blockIdx.x % F, b = blockIdx.x / F, n = CPARS + 8 * F;
+    const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+    auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
+    double s = 0.0;
+    if (a == b) {
+        for (int t = 0; t < F; ++t) {  // k = (h=a, t): adHost A88 adHost^T
+            const int k = a + F * t;
+            const double* A = acc + (size_t)169 * k;
+            s += sandwich(adHost + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adHost + 64 * k, i, j);
+        }
+        for (int h = 0; h < F; ++h) {  // k = (h, t=a): adTarget A88 adTarget^T
+            const int k = h + F * a;
+            const double* A = acc + (size_t)169 * k;
+            s += sandwich(adTarget + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adTarget + 64 * k, i, j);
+        }
+    }
+    {  // H(hIdx,tIdx) += adHost A88 adTarget^T for k = (h=a, t=b)
+        const int k = a + F * b;
+        const double* A = acc + (size_t)169 * k;
+        s += sandwich(adHost + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adTarget + 64 * k, i, j);
+    }
+    Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
+    if (a == b) {
+        // calibration columns, b segment, priors for frame a; done by the diagonal CTA
+        if (j < CPARS + 1) {
+            double v = 0.0;
+            const int col = (j < CPARS) ? j : CPARS + 8;
+            for (int t = 0; t < F; ++t) {
+                const int k = a + F * t;
+                const double* A = acc + (size_t)169 * k;
+                for (int m = 0; m < 8; ++m) v += adj(adHost + 64 * k, i, m) * A[13 * (CPARS + m) + col];
+            }
+            for (int h = 0; h < F; ++h) {
+                const int k = h + F * a;
+                const double* A = acc + (size_t)169 * k;
+                for (int m = 0; m < 8; ++m) v += adj(adTarget + 64 * k, i, m) * A[13 * (CPARS + m) + col];
+            }
+            if (j < CPARS) { Hat(CPARS + 8 * a + i, j) = v; Hat(j, CPARS + 8 * a + i) = v; }
+            else bvec[CPARS + 8 * a + i] = v + (use_prior ? frame_prior[8 * a + i] * frame_delta_prior[8 * a + i] : 0.0);
+        }
+        if (a == 0 && i < CPARS && j < CPARS + 1) {  // Hcc, bc
+            double v = 0.0;
+            const int col = (j < CPARS) ? j : CPARS + 8;
+            for (int k = 0; k < F * F; ++k) v += acc[(size_t)169 * k + 13 * i + col];
+            if (j < CPARS) Hat(i, j) = v + ((use_prior && i == j) ? cPrior[i] : 0.0);
+            else bvec[i] = v + (use_prior ? cPrior[i] * (double)cDeltaF[i] : 0.0);
+        }
+    }
+}
+// "make diagonal by copying over parts" (AccumulatedTopHessian.h:125-137) + frame priors on the diagonal
+__global__ void ba_top_symmetrise_kernel(int F, int use_prior, const double* __restrict__ frame_prior, double* __restrict__ H) {
+    const int h = blockIdx.x % F, t = blockIdx.x / F, n = CPARS + 8 * F;
+    const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+    auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
+    if (t > h) {
+        const double v = Hat(CPARS + 8 * h + i, CPARS + 8 * t + j) + Hat(CPARS + 8 * t + j, CPARS + 8 * h + i);
+        Hat(CPARS + 8 * h + i, CPARS + 8 * t + j) = v;
+        Hat(CPARS + 8 * t + j, CPARS + 8 * h + i) = v;
+    } else if (t == h && use_prior && i == j) {
+        Hat(CPARS + 8 * h + i, CPARS + 8 * h + i) += frame_prior[8 * h + i];
+    }
+}
+
+// AccumulatedSCHessianSSE::stitchDoubleInternal (AccumulatedSCHessian.cpp:78-157), by output block (a,b).
+__global__ void ba_sc_stitch_kernel(int F, const double* __restrict__ accD, const double* __restrict__ accE, const double* __restrict__ accEB,
+                                    const double* __restrict__ accHcc, const double* __restrict__ accbc, const double* __restrict__ adHost,
+                                    const double* __restrict__ adTarget, double* __restrict__ H, double* __restrict__ bvec) {
+    const int a = blockIdx.x % F, b = blockIdx.x / F, n = CPARS + 8 * F, F2 = F * F;
+    const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+    auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
+    double s = 0.0;
+    auto D = [&](int ii, int jj, int kk) { return accD + (size_t)64 * (ii + F * jj + F2 * kk); };
+    if (a == b) {  // H(iIdx,iIdx) += adHost[ij] D[ijk] adHost[ik]^T over all j,k, i = a
+        for (int jj = 0; jj < F; ++jj)
+            for (int kk = 0; kk < F; ++kk) {
+                const double* d = D(a, jj, kk);
+                s += sandwich(adHost + 64 * (a + F * jj), [&](int m, int nn) { return d[8 * m + nn]; }, adHost + 64 * (a + F * kk), i, j);
+            }
+    }
+    for (int ii = 0; ii < F; ++ii) {  // H(jIdx,kIdx) += adTarget[ij] D[ijk] adTarget[ik]^T, j = a, k = b
+        const double* d = D(ii, a, b);
+        s += sandwich(adTarget + 64 * (ii + F * a), [&](int m, int nn) { return d[8 * m + nn]; }, adTarget + 64 * (ii + F * b), i, j);
+    }
+    for (int kk = 0; kk < F; ++kk) {  // H(jIdx,iIdx) += adTarget[ij] D[ijk] adHost[ik]^T, j = a, i = b
+        const double* d = D(b, a, kk);
+        s += sandwich(adTarget + 64 * (b + F * a), [&](int m, int nn) { return d[8 * m + nn]; }, adHost + 64 * (b + F * kk), i, j);
+    }
+    for (int jj = 0; jj < F; ++jj) {  // H(iIdx,kIdx) += adHost[ij] D[ijk] adTarget[ik]^T, i = a, k = b
+        const double* d = D(a, jj, b);
+        s += sandwich(adHost + 64 * (a + F * jj), [&](int m, int nn) { return d[8 * m + nn]; }, adTarget + 64 * (a + F * b), i, j);
+    }
+    Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
+    if (a == b) {
+        if (j < CPARS + 1) {
+            double v = 0.0;
+            for (int jj = 0; jj < F; ++jj) {  // rows of frame a as host i: adHost[ij] * E[ij]
+                const int ij = a + F * jj;
+                for (int m = 0; m < 8; ++m)
+                    v += adj(adHost + 64 * ij, i, m) * (j < CPARS ? accE[(size_t)32 * ij + 4 * m + j] : accEB[(size_t)8 * ij + m]);
+            }
+            for (int ii = 0; ii < F; ++ii) {  // rows of frame a as target j: adTarget[ij] * E[ij]
+                const int ij = ii + F * a;
+                for (int m = 0; m < 8; ++m)
+                    v += adj(adTarget + 64 * ij, i, m) * (j < CPARS ? accE[(size_t)32 * ij + 4 * m + j] : accEB[(size_t)8 * ij + m]);
+            }
+            if (j < CPARS) { Hat(CPARS + 8 * a + i, j) = v; Hat(j, CPARS + 8 * a + i) = v; }
+            else bvec[CPARS + 8 * a + i] = v;
+        }
+        if (a == 0 && i < CPARS && j < CPARS + 1) {
+            if (j < CPARS) Hat(i, j) = accHcc[4 * i + j];
+            else bvec[i] = accbc[i];
+        }
+    }
+}
+
+}  // namespace
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+struct edsgpu_ba {
+    edsgpu_ctx* ctx = nullptr;
+    int F = 0, P = 0, R = 0, num_tiles = 0, num_chunks = 0;
+    void* block = nullptr;  // one device allocation
+    // plan
+    int32_t *host_idx, *target_idx, *point_of_res, *res_begin, *perm, *tile_key, *tile_start, *tile_count, *key_tile_begin;
+    int32_t *pt_perm, *chunk_host, *chunk_start, *chunk_count, *host_chunk_begin;
+    // per-linearisation data
+    float *recs, *res_toZero, *JpJdF, *deltaF, *priorF, *adHTdeltaF, *cDeltaF;
+    uint8_t* flags;
+    double *adHost, *adTarget;
+    // results
+    float *res_pt, *Hdd[2], *bd[2], *Hcd[2], *HdiF, *bdSum, *sc_partial;
+    double *tile_partial, *acc[2], *accD, *accE, *accEB, *accHcc, *accbc, *hcc_host, *Hmat, *bvec, *prior_buf;
+    long long* num[2];
+    int* tile_nres;
+};
+
+namespace {
+
+BaDev ba_dev(const edsgpu_ba* w) {
+    BaDev d{};
+    d.F = w->F; d.P = w->P; d.R = w->R; d.num_tiles = w->num_tiles;
+    d.host_idx = w->host_idx; d.target_idx = w->target_idx; d.point_of_res = w->point_of_res; d.res_begin = w->res_begin;
+    d.perm = w->perm; d.tile_key = w->tile_key; d.tile_start = w->tile_start; d.tile_count = w->tile_count; d.key_tile_begin = w->key_tile_begin;
+    d.recs = w->recs; d.res_toZero = w->res_toZero; d.deltaF = w->deltaF; d.priorF = w->priorF; d.adHTdeltaF = w->adHTdeltaF; d.cDeltaF = w->cDeltaF;
+    d.flags = w->flags; d.res_pt = w->res_pt; d.tile_partial = w->tile_partial; d.tile_nres = w->tile_nres;
+    return d;
+}
+
+edsgpu_status d2h(edsgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!dst) return EDSGPU_OK;
+    EDS_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return EDSGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+edsgpu_status edsgpu_ba_create(edsgpu_ctx* ctx, int F, int P, int R, const int32_t* host_idx, const int32_t* target_idx,
+                               const int32_t* res_begin, edsgpu_ba** out) {
+    if (!ctx || !out) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, F >= 1 && F <= MAXF, "ba_create: F must be in [1,8]");
+    EDS_REQUIRE(ctx, P >= 1 && R >= 1 && host_idx && target_idx && res_begin, "ba_create: bad arguments");
+    EDS_REQUIRE(ctx, res_begin[0] == 0 && res_begin[P] == R, "ba_create: res_begin must span [0,R]");
+    // ---- plan on the host: stable counting sort by (host,target), single-key tiles, points by host
+    const int F2 = F * F;
+    std::vector<int32_t> point_of_res(R), point_host(P, -1);
+    for (int p = 0; p < P; ++p) {
+        EDS_REQUIRE(ctx, res_begin[p] <= res_begin[p + 1], "ba_create: res_begin must be non-decreasing");
+        for (int r = res_begin[p]; r < res_begin[p + 1]; ++r) {
+            EDS_REQUIRE(ctx, host_idx[r] >= 0 && host_idx[r] < F && target_idx[r] >= 0 && target_idx[r] < F, "ba_create: frame index out of range");
+            EDS_REQUIRE(ctx, point_host[p] < 0 || point_host[p] == host_idx[r], "ba_create: residuals of a point must share the host frame");
+            point_host[p] = host_idx[r];
+            point_of_res[r] = p;
+        }
+    }
+    std::vector<int32_t> cnt(F2 + 1, 0), perm(R);
+    for (int r = 0; r < R; ++r) cnt[host_idx[r] + F * target_idx[r] + 1]++;
+    for (int k = 0; k < F2; ++k) cnt[k + 1] += cnt[k];
+    {
+        std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1);
+        for (int r = 0; r < R; ++r) perm[cur[host_idx[r] + F * target_idx[r]]++] = r;
+    }
+    std::vector<int32_t> tile_key, tile_start, tile_count, key_tile_begin(F2 + 1, 0);
+    for (int k = 0; k < F2; ++k) {
+        key_tile_begin[k] = (int32_t)tile_key.size();
+        for (int s = cnt[k]; s < cnt[k + 1]; s += TOP_TILE) {
+            tile_key.push_back(k); tile_start.push_back(s); tile_count.push_back(std::min(TOP_TILE, cnt[k + 1] - s));
+        }
+    }
+    key_tile_begin[F2] = (int32_t)tile_key.size();
+    const int T = (int)tile_key.size();
+    std::vector<int32_t> pt_perm, chunk_host, chunk_start, chunk_count, host_chunk_begin(F + 1, 0);
+    for (int h = 0; h < F; ++h) {
+        host_chunk_begin[h] = (int32_t)chunk_host.size();
+        const int s0 = (int)pt_perm.size();
+        for (int p = 0; p < P; ++p) if (point_host[p] == h) pt_perm.push_back(p);
+        const int s1 = (int)pt_perm.size();
+        for (int s = s0; s < s1; s += SC_CHUNK) { chunk_host.push_back(h); chunk_start.push_back(s); chunk_count.push_back(std::min(SC_CHUNK, s1 - s)); }
+    }
+    host_chunk_begin[F] = (int32_t)chunk_host.size();
+    const int C = (int)chunk_host.size();
+    const int Msc = 8 * F + 4, Nsc = 8 * F + 5, n = CPARS + 8 * F;
+
+    DeviceGuard g(ctx->device);
+    edsgpu_ba* w = new edsgpu_ba();
+    w->ctx = ctx; w->F = F; w->P = P; w->R = R; w->num_tiles = T; w->num_chunks = C;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(std::max<size_t>(bytes, 16), 256); return o; };
+    const size_t o_host = take(4 * (size_t)R), o_tgt = take(4 * (size_t)R), o_por = take(4 * (size_t)R), o_rb = take(4 * (size_t)(P + 1)), o_perm = take(4 * (size_t)R);
+    const size_t o_tk = take(4 * (size_t)T), o_ts = take(4 * (size_t)T), o_tc = take(4 * (size_t)T), o_ktb = take(4 * (size_t)(F2 + 1));
+    const size_t o_pp = take(4 * (size_t)pt_perm.size()), o_ch = take(4 * (size_t)C), o_cs = take(4 * (size_t)C), o_cc = take(4 * (size_t)C), o_hcb = take(4 * (size_t)(F + 1));
+    const size_t o_recs = take(4 * (size_t)REC * R), o_rtz = take(32 * (size_t)R), o_jp = take(32 * (size_t)R), o_dF = take(4 * (size_t)P), o_pF = take(4 * (size_t)P);
+    const size_t o_ad = take(32 * (size_t)F2), o_cd = take(16), o_fl = take((size_t)R), o_aH = take(512 * (size_t)F2), o_aT = take(512 * (size_t)F2);
+    const size_t o_rpt = take(24 * (size_t)R);
+    size_t o_Hdd[2], o_bd[2], o_Hcd[2], o_acc[2], o_num[2];
+    for (int s = 0; s < 2; ++s) { o_Hdd[s] = take(4 * (size_t)P); o_bd[s] = take(4 * (size_t)P); o_Hcd[s] = take(16 * (size_t)P); o_acc[s] = take(8 * 169 * (size_t)F2); o_num[s] = take(8 * (size_t)F2); }
+    const size_t o_hdi = take(4 * (size_t)P), o_bds = take(4 * (size_t)P), o_scp = take(4 * (size_t)C * Msc * Nsc), o_tp = take(8 * (size_t)NACC * T), o_tn = take(4 * (size_t)T);
+    const size_t o_D = take(8 * 64 * (size_t)F2 * F), o_E = take(8 * 32 * (size_t)F2), o_EB = take(8 * 8 * (size_t)F2), o_Hcc = take(128), o_bc = take(32), o_hh = take(8 * 20 * (size_t)F);
+    const size_t o_Hm = take(8 * (size_t)n * n), o_bv = take(8 * (size_t)n), o_pr = take(8 * (size_t)(4 + 16 * F));
+    cudaError_t e = cudaMalloc(&w->block, off);
+    if (e != cudaSuccess) { delete w; return edsgpu_fail(ctx, EDSGPU_OUT_OF_MEMORY, cudaGetErrorString(e)); }
+    char* base = (char*)w->block;
+    w->host_idx = (int32_t*)(base + o_host); w->target_idx = (int32_t*)(base + o_tgt); w->point_of_res = (int32_t*)(base + o_por);
+    w->res_begin = (int32_t*)(base + o_rb); w->perm = (int32_t*)(base + o_perm); w->tile_key = (int32_t*)(base + o_tk);
+    w->tile_start = (int32_t*)(base + o_ts); w->tile_count = (int32_t*)(base + o_tc); w->key_tile_begin = (int32_t*)(base + o_ktb);
+    w->pt_perm = (int32_t*)(base + o_pp); w->chunk_host = (int32_t*)(base + o_ch); w->chunk_start = (int32_t*)(base + o_cs);
+    w->chunk_count = (int32_t*)(base + o_cc); w->host_chunk_begin = (int32_t*)(base + o_hcb);
+    w->recs = (float*)(base + o_recs); w->res_toZero = (float*)(base + o_rtz); w->JpJdF = (float*)(base + o_jp);
+    w->deltaF = (float*)(base + o_dF); w->priorF = (float*)(base + o_pF); w->adHTdeltaF = (float*)(base + o_ad); w->cDeltaF = (float*)(base + o_cd);
+    w->flags = (uint8_t*)(base + o_fl); w->adHost = (double*)(base + o_aH); w->adTarget = (double*)(base + o_aT);
+    w->res_pt = (float*)(base + o_rpt);
+    for (int s = 0; s < 2; ++s) {
+        w->Hdd[s] = (float*)(base + o_Hdd[s]); w->bd[s] = (float*)(base + o_bd[s]); w->Hcd[s] = (float*)(base + o_Hcd[s]);
+        w->acc[s] = (double*)(base + o_acc[s]); w->num[s] = (long long*)(base + o_num[s]);
+    }
+    w->HdiF = (float*)(base + o_hdi); w->bdSum = (float*)(base + o_bds); w->sc_partial = (float*)(base + o_scp);
+    w->tile_partial = (double*)(base + o_tp); w->tile_nres = (int*)(base + o_tn);
+    w->accD = (double*)(base + o_D); w->accE = (double*)(base + o_E); w->accEB = (double*)(base + o_EB); w->accHcc = (double*)(base + o_Hcc);
+    w->accbc = (double*)(base + o_bc); w->hcc_host = (double*)(base + o_hh); w->Hmat = (double*)(base + o_Hm); w->bvec = (double*)(base + o_bv);
+    w->prior_buf = (double*)(base + o_pr);
+    e = cudaMemsetAsync(w->block, 0, off, ctx->stream);
+    auto up = [&](void* dst, const void* src, size_t bytes) { if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream); };
+    up(w->host_idx, host_idx, 4 * (size_t)R); up(w->target_idx, target_idx, 4 * (size_t)R); up(w->point_of_res, point_of_res.data(), 4 * (size_t)R);
+    up(w->res_begin, res_begin, 4 * (size_t)(P + 1)); up(w->perm, perm.data(), 4 * (size_t)R);
+    up(w->tile_key, tile_key.data(), 4 * (size_t)T); up(w->tile_start, tile_start.data(), 4 * (size_t)T); up(w->tile_count, tile_count.data(), 4 * (size_t)T);
+    up(w->key_tile_begin, key_tile_begin.data(), 4 * (size_t)(F2 + 1)); up(w->pt_perm, pt_perm.data(), 4 * pt_perm.size());
+    up(w->chunk_host, chunk_host.data(), 4 * (size_t)C); up(w->chunk_start, chunk_start.data(), 4 * (size_t)C); up(w->chunk_count, chunk_count.data(), 4 * (size_t)C);
+    up(w->host_chunk_begin, host_chunk_begin.data(), 4 * (size_t)(F + 1));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the plan vectors are stack-owned
+    if (e != cudaSuccess) { edsgpu_ba_destroy(w); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
+    *out = w;
+    return EDSGPU_OK;
+}
+
+void edsgpu_ba_destroy(edsgpu_ba* w) {
+    if (!w) return;
+    DeviceGuard g(w->ctx->device);
+    cudaStreamSynchronize(w->ctx->stream);
+    if (w->block) cudaFree(w->block);
+    delete w;
+}
+
+edsgpu_status edsgpu_ba_set_residuals(edsgpu_ba* w, const float* recs, const uint8_t* flags, const float* res_toZero) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, recs && flags, "ba_set_residuals: null array");
+    DeviceGuard g(ctx->device);
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->recs, recs, 4 * (size_t)REC * w->R, cudaMemcpyHostToDevice, ctx->stream));
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->flags, flags, (size_t)w->R, cudaMemcpyHostToDevice, ctx->stream));
+    if (res_toZero) EDS_CUDA(ctx, cudaMemcpyAsync(w->res_toZero, res_toZero, 32 * (size_t)w->R, cudaMemcpyHostToDevice, ctx->stream));
+    ba_jpjd_kernel<<<(w->R + 255) / 256, 256, 0, ctx->stream>>>(w->recs, w->R, w->JpJdF);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller buffers may be pageable and reused
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_set_points(edsgpu_ba* w, const float* deltaF, const float* priorF) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    DeviceGuard g(ctx->device);
+    if (deltaF) EDS_CUDA(ctx, cudaMemcpyAsync(w->deltaF, deltaF, 4 * (size_t)w->P, cudaMemcpyHostToDevice, ctx->stream));
+    else EDS_CUDA(ctx, cudaMemsetAsync(w->deltaF, 0, 4 * (size_t)w->P, ctx->stream));
+    if (priorF) EDS_CUDA(ctx, cudaMemcpyAsync(w->priorF, priorF, 4 * (size_t)w->P, cudaMemcpyHostToDevice, ctx->stream));
+    else EDS_CUDA(ctx, cudaMemsetAsync(w->priorF, 0, 4 * (size_t)w->P, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_set_frames(edsgpu_ba* w, const float* adHTdeltaF, const float* cDeltaF, const double* adHost, const double* adTarget) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    DeviceGuard g(ctx->device);
+    const size_t F2 = (size_t)w->F * w->F;
+    if (adHTdeltaF) EDS_CUDA(ctx, cudaMemcpyAsync(w->adHTdeltaF, adHTdeltaF, 32 * F2, cudaMemcpyHostToDevice, ctx->stream));
+    if (cDeltaF) EDS_CUDA(ctx, cudaMemcpyAsync(w->cDeltaF, cDeltaF, 16, cudaMemcpyHostToDevice, ctx->stream));
+    if (adHost) EDS_CUDA(ctx, cudaMemcpyAsync(w->adHost, adHost, 512 * F2, cudaMemcpyHostToDevice, ctx->stream));
+    if (adTarget) EDS_CUDA(ctx, cudaMemcpyAsync(w->adTarget, adTarget, 512 * F2, cudaMemcpyHostToDevice, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_top_accumulate(edsgpu_ba* w, int mode, double* acc_out, float* Hdd_out, float* bd_out, float* Hcd_out, int64_t* nres_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, mode >= 0 && mode <= 2, "ba_top_accumulate: mode must be 0 (active), 1 (linearized) or 2 (marginalize)");
+    DeviceGuard g(ctx->device);
+    const int slot = mode == 0 ? 0 : 1;
+    const BaDev d = ba_dev(w);
+    if (mode == 0) ba_top_kernel<0><<<w->num_tiles, TOP_THREADS, 0, ctx->stream>>>(d);
+    else if (mode == 1) ba_top_kernel<1><<<w->num_tiles, TOP_THREADS, 0, ctx->stream>>>(d);
+    else ba_top_kernel<2><<<w->num_tiles, TOP_THREADS, 0, ctx->stream>>>(d);
+    EDS_CUDA(ctx, cudaGetLastError());
+    ba_top_finalize_kernel<<<w->F * w->F, 96, 0, ctx->stream>>>(d, w->acc[slot], w->num[slot]);
+    ba_point_sum_kernel<<<(w->P + 255) / 256, 256, 0, ctx->stream>>>(w->res_pt, w->res_begin, w->P, w->Hdd[slot], w->bd[slot], w->Hcd[slot]);
+    ctx->launches += 3;
+    EDS_CUDA(ctx, cudaGetLastError());
+    if (mode == 2) {  // AccumulatedTopHessian.cpp:152-157: marginalisation zeroes the active-side point terms
+        EDS_CUDA(ctx, cudaMemsetAsync(w->Hdd[0], 0, 4 * (size_t)w->P, ctx->stream));
+        EDS_CUDA(ctx, cudaMemsetAsync(w->bd[0], 0, 4 * (size_t)w->P, ctx->stream));
+        EDS_CUDA(ctx, cudaMemsetAsync(w->Hcd[0], 0, 16 * (size_t)w->P, ctx->stream));
+    }
+    if (acc_out || Hdd_out || bd_out || Hcd_out || nres_out) {
+        const size_t F2 = (size_t)w->F * w->F;
+        edsgpu_status st = edsgpu_ensure_pinned(ctx, 8 * F2);
+        if (st != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, acc_out, w->acc[slot], 8 * 169 * F2)) != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, Hdd_out, w->Hdd[slot], 4 * (size_t)w->P)) != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, bd_out, w->bd[slot], 4 * (size_t)w->P)) != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, Hcd_out, w->Hcd[slot], 16 * (size_t)w->P)) != EDSGPU_OK) return st;
+        if (nres_out) EDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, w->num[slot], 8 * F2, cudaMemcpyDeviceToHost, ctx->stream));
+        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (nres_out) { int64_t n = 0; for (size_t k = 0; k < F2; ++k) n += ((long long*)ctx->pinned)[k]; *nres_out = n; }
+    }
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_top_stitch(edsgpu_ba* w, int which, int use_prior, const double* cPrior, const double* frame_prior,
+                                   const double* frame_delta_prior, double* H, double* b) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, which == 0 || which == 1, "ba_top_stitch: which must be 0 (active) or 1 (linearized)");
+    EDS_REQUIRE(ctx, !use_prior || (cPrior && frame_prior && frame_delta_prior), "ba_top_stitch: priors requested but not given");
+    DeviceGuard g(ctx->device);
+    const int F = w->F, n = CPARS + 8 * F;
+    double* pr = w->prior_buf;  // cPrior(4) | frame_prior(8F) | frame_delta_prior(8F)
+    if (use_prior) {
+        EDS_CUDA(ctx, cudaMemcpyAsync(pr, cPrior, 32, cudaMemcpyHostToDevice, ctx->stream));
+        EDS_CUDA(ctx, cudaMemcpyAsync(pr + 4, frame_prior, 64 * (size_t)F, cudaMemcpyHostToDevice, ctx->stream));
+        EDS_CUDA(ctx, cudaMemcpyAsync(pr + 4 + 8 * F, frame_delta_prior, 64 * (size_t)F, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ba_top_stitch_kernel<<<F * F, 64, 0, ctx->stream>>>(F, w->acc[which], w->adHost, w->adTarget, use_prior, pr, w->cDeltaF, pr + 4, pr + 4 + 8 * F,
+                                                        w->Hmat, w->bvec);
+    ba_top_symmetrise_kernel<<<F * F, 64, 0, ctx->stream>>>(F, use_prior, pr + 4, w->Hmat);
+    ctx->launches += 2;
+    EDS_CUDA(ctx, cudaGetLastError());
+    edsgpu_status st;
+    if ((st = d2h(ctx, H, w->Hmat, 8 * (size_t)n * n)) != EDSGPU_OK) return st;
+    if ((st = d2h(ctx, b, w->bvec, 8 * (size_t)n)) != EDSGPU_OK) return st;
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_sc_accumulate(edsgpu_ba* w, int shift_prior_to_zero, double* accD, double* accE, double* accEB, double* accHcc,
+                                      double* accbc, float* HdiF_out, float* bdSum_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    DeviceGuard g(ctx->device);
+    ScDev s{};
+    s.F = w->F; s.P = w->P; s.shift_prior = shift_prior_to_zero;
+    s.res_begin = w->res_begin; s.target_idx = w->target_idx; s.pt_perm = w->pt_perm; s.chunk_host = w->chunk_host;
+    s.chunk_start = w->chunk_start; s.chunk_count = w->chunk_count; s.flags = w->flags; s.JpJdF = w->JpJdF;
+    s.HddA = w->Hdd[0]; s.HddL = w->Hdd[1]; s.bdA = w->bd[0]; s.bdL = w->bd[1]; s.HcdA = w->Hcd[0]; s.HcdL = w->Hcd[1];
+    s.priorF = w->priorF; s.deltaF = w->deltaF; s.HdiF = w->HdiF; s.bdSum = w->bdSum; s.partial = w->sc_partial;
+    ba_sc_kernel<<<w->num_chunks, SC_THREADS, 0, ctx->stream>>>(s);
+    EDS_CUDA(ctx, cudaGetLastError());
+    const size_t F2 = (size_t)w->F * w->F;
+    EDS_CUDA(ctx, cudaMemsetAsync(w->accD, 0, 8 * 64 * F2 * w->F, ctx->stream));
+    ba_sc_finalize_kernel<<<w->F, 256, 0, ctx->stream>>>(w->F, w->sc_partial, w->host_chunk_begin, w->accD, w->accE, w->accEB, w->hcc_host);
+    ba_sc_hcc_kernel<<<1, 32, 0, ctx->stream>>>(w->F, w->hcc_host, w->accHcc, w->accbc);
+    ctx->launches += 3;
+    EDS_CUDA(ctx, cudaGetLastError());
+    if (accD || accE || accEB || accHcc || accbc || HdiF_out || bdSum_out) {
+        edsgpu_status st;
+        if ((st = d2h(ctx, accD, w->accD, 8 * 64 * F2 * w->F)) != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, accE, w->accE, 8 * 32 * F2)) != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, accEB, w->accEB, 8 * 8 * F2)) != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, accHcc, w->accHcc, 128)) != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, accbc, w->accbc, 32)) != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, HdiF_out, w->HdiF, 4 * (size_t)w->P)) != EDSGPU_OK) return st;
+        if ((st = d2h(ctx, bdSum_out, w->bdSum, 4 * (size_t)w->P)) != EDSGPU_OK) return st;
+        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_sc_stitch(edsgpu_ba* w, double* H, double* b) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    DeviceGuard g(ctx->device);
+    const int F = w->F, n = CPARS + 8 * F;
+    ba_sc_stitch_kernel<<<F * F, 64, 0, ctx->stream>>>(F, w->accD, w->accE, w->accEB, w->accHcc, w->accbc, w->adHost, w->adTarget, w->Hmat, w->bvec);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    edsgpu_status st;
+    if ((st = d2h(ctx, H, w->Hmat, 8 * (size_t)n * n)) != EDSGPU_OK) return st;
+    if ((st = d2h(ctx, b, w->bvec, 8 * (size_t)n)) != EDSGPU_OK) return st;
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_get_jpjd(edsgpu_ba* w, float* JpJdF_out) {
+    if (!w || !JpJdF_out) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    DeviceGuard g(ctx->device);
+    EDS_CUDA(ctx, cudaMemcpyAsync(JpJdF_out, w->JpJdF, 32 * (size_t)w->R, cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+}  // extern "C"

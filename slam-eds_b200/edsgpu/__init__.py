@@ -31,6 +31,8 @@ SYMBOLS = [
     "edsgpu_tracker_optimize", "edsgpu_trackers_optimize_batch", "edsgpu_trackers_gather", "edsgpu_tracker_state_dev",
     "edsgpu_batch_create", "edsgpu_batch_destroy", "edsgpu_batch_optimize", "edsgpu_batch_pack_states_dev",
     "edsgpu_tracker_evaluate",
+    "edsgpu_ba_create", "edsgpu_ba_destroy", "edsgpu_ba_set_residuals", "edsgpu_ba_set_points", "edsgpu_ba_set_frames",
+    "edsgpu_ba_top_accumulate", "edsgpu_ba_top_stitch", "edsgpu_ba_sc_accumulate", "edsgpu_ba_sc_stitch", "edsgpu_ba_get_jpjd",
 ]
 
 
@@ -70,7 +72,7 @@ def load():
         lib.edsgpu_tracker_state_dev.restype = C.c_void_p
         lib.edsgpu_tracker_state_dev.argtypes = [C.c_void_p]
         for name in ("edsgpu_destroy", "edsgpu_lut_destroy", "edsgpu_frames_destroy", "edsgpu_keyframe_destroy",
-                     "edsgpu_tracker_destroy", "edsgpu_batch_destroy"):
+                     "edsgpu_tracker_destroy", "edsgpu_batch_destroy", "edsgpu_ba_destroy"):
             getattr(lib, name).restype = None
             getattr(lib, name).argtypes = [C.c_void_p]
         _lib = lib
@@ -322,3 +324,90 @@ def tracker_evaluate(ctx, kf, frames, slot, x, loss_type=LOSS_HUBER, loss_param=
                                               _ptr(res, C.c_double), _ptr(jac, C.c_double), C.byref(cost),
                                               _ptr(H, C.c_double), _ptr(g, C.c_double)))
     return dict(residuals=res, jacobian=jac, cost=cost.value, H=H, g=g)
+
+
+class BaWindow:
+    """Mirror of the accumulator side of dso::EnergyFunctional (accumulateAF_MT / LF_MT / SCF_MT,
+    EnergyFunctional.cpp:197-261) on top of edsgpu_ba_*: the residual graph is given once, the
+    per-linearisation records per call."""
+
+    def __init__(self, ctx, F, host_idx, target_idx, res_begin):
+        self.ctx, self.F = ctx, F
+        h = np.ascontiguousarray(host_idx, np.int32)
+        t = np.ascontiguousarray(target_idx, np.int32)
+        rb = np.ascontiguousarray(res_begin, np.int32)
+        self.R, self.P = len(h), len(rb) - 1
+        self.n = 4 + 8 * F
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.edsgpu_ba_create(ctx.h, C.c_int(F), C.c_int(self.P), C.c_int(self.R), _ptr(h, C.c_int32),
+                                           _ptr(t, C.c_int32), _ptr(rb, C.c_int32), C.byref(self.h)))
+
+    def set_residuals(self, recs, flags, res_toZero=None):
+        recs = np.ascontiguousarray(recs, np.float32)
+        fl = np.ascontiguousarray(flags, np.uint8)
+        rtz = np.ascontiguousarray(res_toZero, np.float32) if res_toZero is not None else None
+        assert recs.shape == (self.R, 76) and fl.shape == (self.R,)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_set_residuals(self.h, _ptr(recs, C.c_float), _ptr(fl, C.c_uint8), _ptr(rtz, C.c_float)))
+
+    def set_points(self, deltaF=None, priorF=None):
+        d = np.ascontiguousarray(deltaF, np.float32) if deltaF is not None else None
+        p = np.ascontiguousarray(priorF, np.float32) if priorF is not None else None
+        self.ctx.check(self.ctx.lib.edsgpu_ba_set_points(self.h, _ptr(d, C.c_float), _ptr(p, C.c_float)))
+
+    def set_frames(self, adHTdeltaF=None, cDeltaF=None, adHost=None, adTarget=None):
+        a = np.ascontiguousarray(adHTdeltaF, np.float32) if adHTdeltaF is not None else None
+        c = np.ascontiguousarray(cDeltaF, np.float32) if cDeltaF is not None else None
+        ah = np.ascontiguousarray(adHost, np.float64) if adHost is not None else None
+        at = np.ascontiguousarray(adTarget, np.float64) if adTarget is not None else None
+        self.ctx.check(self.ctx.lib.edsgpu_ba_set_frames(self.h, _ptr(a, C.c_float), _ptr(c, C.c_float), _ptr(ah, C.c_double),
+                                                         _ptr(at, C.c_double)))
+
+    def top_accumulate(self, mode, want_outputs=True):
+        if not want_outputs:
+            self.ctx.check(self.ctx.lib.edsgpu_ba_top_accumulate(self.h, C.c_int(mode), None, None, None, None, None))
+            return None
+        acc = np.zeros((self.F * self.F, 13, 13))
+        Hdd, bd, Hcd = np.zeros(self.P, np.float32), np.zeros(self.P, np.float32), np.zeros((self.P, 4), np.float32)
+        nres = C.c_int64(0)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_top_accumulate(self.h, C.c_int(mode), _ptr(acc, C.c_double), _ptr(Hdd, C.c_float),
+                                                             _ptr(bd, C.c_float), _ptr(Hcd, C.c_float), C.byref(nres)))
+        return dict(acc=acc, Hdd=Hdd, bd=bd, Hcd=Hcd, nres=nres.value)
+
+    def top_stitch(self, which, use_prior=False, cPrior=None, frame_prior=None, frame_delta_prior=None):
+        H = np.zeros((self.n, self.n), order="F")
+        b = np.zeros(self.n)
+        cp = np.ascontiguousarray(cPrior, np.float64) if cPrior is not None else None
+        fp = np.ascontiguousarray(frame_prior, np.float64) if frame_prior is not None else None
+        fd = np.ascontiguousarray(frame_delta_prior, np.float64) if frame_delta_prior is not None else None
+        self.ctx.check(self.ctx.lib.edsgpu_ba_top_stitch(self.h, C.c_int(which), C.c_int(int(use_prior)), _ptr(cp, C.c_double),
+                                                         _ptr(fp, C.c_double), _ptr(fd, C.c_double), _ptr(H, C.c_double), _ptr(b, C.c_double)))
+        return H, b
+
+    def sc_accumulate(self, shift_prior_to_zero=True, want_outputs=True):
+        if not want_outputs:
+            self.ctx.check(self.ctx.lib.edsgpu_ba_sc_accumulate(self.h, C.c_int(int(shift_prior_to_zero)), None, None, None, None, None, None, None))
+            return None
+        F = self.F
+        accD, accE, accEB = np.zeros((F ** 3, 8, 8)), np.zeros((F * F, 8, 4)), np.zeros((F * F, 8))
+        accHcc, accbc = np.zeros((4, 4)), np.zeros(4)
+        HdiF, bdSum = np.zeros(self.P, np.float32), np.zeros(self.P, np.float32)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_sc_accumulate(self.h, C.c_int(int(shift_prior_to_zero)), _ptr(accD, C.c_double),
+                                                            _ptr(accE, C.c_double), _ptr(accEB, C.c_double), _ptr(accHcc, C.c_double),
+                                                            _ptr(accbc, C.c_double), _ptr(HdiF, C.c_float), _ptr(bdSum, C.c_float)))
+        return dict(accD=accD, accE=accE, accEB=accEB, accHcc=accHcc, accbc=accbc, HdiF=HdiF, bdSum=bdSum)
+
+    def sc_stitch(self):
+        H = np.zeros((self.n, self.n), order="F")
+        b = np.zeros(self.n)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_sc_stitch(self.h, _ptr(H, C.c_double), _ptr(b, C.c_double)))
+        return H, b
+
+    def jpjd(self):
+        out = np.zeros((self.R, 8), np.float32)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_get_jpjd(self.h, _ptr(out, C.c_float)))
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.edsgpu_ba_destroy(self.h)
+            self.h = None

@@ -1,0 +1,125 @@
+"""GPU parity tests for the windowed-BA Hessian accumulators (run with -m gpu): the CUDA path
+through the C ABI against the double-precision CPU oracle.  The reference accumulates in float
+with a run-to-run varying order, so the gate is norm-wise 1e-5 relative on every accumulator and
+on the stitched H, b, not bit-exactness."""
+import numpy as np
+import pytest
+
+import edsgpu
+from edsgpu import synth_ba as SB
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(np.asarray(b, np.float64)).max(), 1e-300)
+
+
+@pytest.fixture(scope="module", params=["small", "config4", "ragged"])
+def problem(request):
+    if request.param == "small":
+        return SB.make_ba_problem(F=4, points_per_frame=250, H=120, W=160)
+    if request.param == "config4":
+        return SB.make_ba_problem()  # F=7, 2048 points per keyframe, R = 86 016
+    # ragged: drop residuals so that points have 0..F-1 of them, some points none, some keys empty
+    pb = SB.make_ba_problem(F=5, points_per_frame=300, H=120, W=160, seed=99)
+    rng = np.random.default_rng(5)
+    keep = rng.random(pb["R"]) < 0.6
+    keep[pb["target_idx"] == 3] &= pb["host_idx"][pb["target_idx"] == 3] != 1  # empty (host 1, target 3) accumulator
+    pts = pb["point_of_res"][keep]
+    out = dict(pb)
+    out["recs"], out["host_idx"], out["target_idx"], out["flags"] = pb["recs"][keep], pb["host_idx"][keep], pb["target_idx"][keep], pb["flags"][keep]
+    out["res_begin"] = np.concatenate([[0], np.cumsum(np.bincount(pts, minlength=pb["P"]))]).astype(np.int32)
+    out["R"] = int(keep.sum())
+    return out
+
+
+@pytest.fixture(scope="module")
+def solved(gpu_ctx, problem):
+    pb = problem
+    F = pb["F"]
+    rtz = O.ba_fix_linearization(F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["deltaF"], pb["adHTdeltaF"], pb["cDeltaF"])
+    w = edsgpu.BaWindow(gpu_ctx, F, pb["host_idx"], pb["target_idx"], pb["res_begin"])
+    w.set_residuals(pb["recs"], pb["flags"], rtz)
+    w.set_points(pb["deltaF"], pb["priorF"])
+    w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    yield pb, rtz, w
+    w.close()
+
+
+def _oracle_top(pb, rtz, mode):
+    return O.ba_top_accumulate(mode, pb["F"], pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"],
+                               pb["adHTdeltaF"], pb["cDeltaF"], threads=4)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_top_accumulators(solved, mode):
+    pb, rtz, w = solved
+    g = w.top_accumulate(mode)
+    o = _oracle_top(pb, rtz, mode)
+    assert g["nres"] == o["nres"]
+    for k in range(pb["F"] ** 2):
+        if o["num"][k] == 0:
+            assert not g["acc"][k].any()
+        else:
+            assert rel(g["acc"][k], o["acc"][k]) < TOL, k
+            assert np.array_equal(g["acc"][k], g["acc"][k].T)
+    assert rel(g["Hdd"], o["Hdd"]) < TOL and rel(g["bd"], o["bd"]) < TOL and rel(g["Hcd"], o["Hcd"]) < TOL
+    # deterministic: fixed tile plan and summation order
+    g2 = w.top_accumulate(mode)
+    assert np.array_equal(g["acc"], g2["acc"]) and np.array_equal(g["Hdd"], g2["Hdd"])
+
+
+def test_jpjd(solved):
+    pb, rtz, w = solved
+    assert rel(w.jpjd(), O.ba_jpjd(pb["recs"])) < 1e-6
+
+
+@pytest.mark.parametrize("use_prior", [False, True])
+def test_top_stitch(solved, use_prior):
+    pb, rtz, w = solved
+    F = pb["F"]
+    for which, mode in ((0, 0), (1, 1)):
+        w.top_accumulate(mode, want_outputs=False)
+        o = _oracle_top(pb, rtz, mode)
+        args = (True, pb["cPrior"], pb["cDeltaF"], pb["frame_prior"], pb["frame_delta_prior"]) if use_prior else ()
+        Ho, bo = O.ba_top_stitch(F, o["acc"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]), *args)
+        Hg, bg = w.top_stitch(which, use_prior, pb["cPrior"], pb["frame_prior"], pb["frame_delta_prior"])
+        assert rel(Hg, Ho) < TOL and rel(bg, bo) < TOL
+        assert rel(Hg, Hg.T) < 1e-12
+
+
+@pytest.mark.parametrize("shift", [True, False])
+def test_schur_complement(solved, shift):
+    pb, rtz, w = solved
+    F = pb["F"]
+    w.top_accumulate(0, want_outputs=False)
+    w.top_accumulate(1, want_outputs=False)
+    A, L = _oracle_top(pb, rtz, 0), _oracle_top(pb, rtz, 1)
+    g = w.sc_accumulate(shift)
+    o = O.ba_sc_accumulate(F, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], O.ba_jpjd(pb["recs"]), A["Hdd"], L["Hdd"],
+                           A["bd"], L["bd"], A["Hcd"], L["Hcd"], pb["priorF"], pb["deltaF"], shift, threads=4)
+    assert rel(g["HdiF"], o["HdiF"]) < TOL and rel(g["bdSum"], o["bdSum"]) < TOL
+    for name in ("accD", "accE", "accEB", "accHcc", "accbc"):
+        assert rel(g[name], o[name]) < TOL, name
+    Hg, bg = w.sc_stitch()
+    Ho, bo = O.ba_sc_stitch(F, o, SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    assert rel(Hg, Ho) < TOL and rel(bg, bo) < TOL
+    # a point without active residuals contributes nothing and gets HdiF = 0 (AccumulatedSCHessian.cpp:38-45)
+    none = [p for p in range(pb["P"]) if not (pb["flags"][pb["res_begin"][p]:pb["res_begin"][p + 1]] & 1).any()]
+    assert all(g["HdiF"][p] == 0 and g["bdSum"][p] == 0 for p in none[:50])
+
+
+def test_argument_validation(gpu_ctx):
+    with pytest.raises(edsgpu.EdsGpuError):
+        edsgpu.BaWindow(gpu_ctx, 9, [0], [1], [0, 1])  # F > 8
+    with pytest.raises(edsgpu.EdsGpuError):
+        edsgpu.BaWindow(gpu_ctx, 3, [0, 1], [1, 2], [0, 2])  # residuals of one point with two hosts
+    with pytest.raises(edsgpu.EdsGpuError):
+        edsgpu.BaWindow(gpu_ctx, 3, [0, 5], [1, 2], [0, 1, 2])  # frame index out of range
+    w = edsgpu.BaWindow(gpu_ctx, 3, [0, 0], [1, 2], [0, 2])
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.top_accumulate(3)
+    w.close()

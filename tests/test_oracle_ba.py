@@ -1,0 +1,198 @@
+"""CPU tests pinning the BA oracle: the accumulators against the dense J^T J of the stacked 8x13
+rows, the two in-repo statements of each stitch, and the re-linearisation identity
+(AccumulatedTopHessian.cpp:84-98 adds J*delta, EnergyFunctionalStructs.cpp:101-110 subtracts it)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from edsgpu import synth_ba as SB
+
+
+@pytest.fixture(scope="module")
+def small():
+    return SB.make_ba_problem(F=4, points_per_frame=250, H=120, W=160)
+
+
+def _dense_top(pb, mode, res_override=None):
+    F = pb["F"]
+    recs = pb["recs"].astype(np.float64)
+    acc = np.zeros((F * F, 13, 13))
+    for r in range(pb["R"]):
+        fl = pb["flags"][r]
+        act, lin = fl & 1, fl & 2
+        if (mode == 0 and (lin or not act)) or (mode == 1 and (not lin or not act)) or (mode == 2 and not act):
+            continue
+        J = recs[r]
+        x = np.concatenate([J[20:24], J[8:14]])
+        y = np.concatenate([J[24:28], J[14:20]])
+        res = J[0:8] if res_override is None else res_override[r].astype(np.float64)
+        rows = np.zeros((8, 13))
+        rows[:, :10] = np.outer(J[32:40], x) + np.outer(J[40:48], y)
+        rows[:, 10], rows[:, 11], rows[:, 12] = J[48:56], J[56:64], res
+        acc[pb["host_idx"][r] + F * pb["target_idx"][r]] += rows.T @ rows
+    return acc
+
+
+def test_generator_produces_a_sane_graph(small):
+    pb = small
+    assert pb["recs"].shape == (pb["R"], 76) and pb["R"] == pb["P"] * (pb["F"] - 1)
+    assert (pb["state"] == 0).mean() > 0.8
+    assert np.all(np.isfinite(pb["recs"]))
+    act = (pb["flags"] & 1).astype(bool)
+    # shorthand 2x2 products are consistent with the stored columns (Residuals.cpp:216-247)
+    J = pb["recs"][act].astype(np.float64)
+    np.testing.assert_allclose(J[:, 64], np.sum(J[:, 32:40] ** 2, 1), rtol=1e-5)
+    np.testing.assert_allclose(J[:, 66], np.sum(J[:, 32:40] * J[:, 40:48], 1), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(J[:, 75], np.sum(J[:, 56:64] ** 2, 1), rtol=1e-5)
+
+
+def test_top_accumulator_equals_dense_normal_equations(small):
+    pb = small
+    top = O.ba_top_accumulate(0, pb["F"], pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"])
+    dense = _dense_top(pb, 0)
+    # records store the 2x2 shorthands in float32: agreement to float32 rounding of those sums
+    assert np.abs(top["acc"] - dense).max() < 1e-6 * np.abs(dense).max()
+    assert top["nres"] == int(np.sum(((pb["flags"] & 1) == 1) & ((pb["flags"] & 2) == 0)))
+    np.testing.assert_array_equal(top["num"].sum(), top["nres"])
+    for k in range(pb["F"] ** 2):
+        np.testing.assert_allclose(top["acc"][k], top["acc"][k].T)
+
+
+def test_threads_do_not_change_the_double_result(small):
+    pb = small
+    a = O.ba_top_accumulate(0, pb["F"], pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], threads=1)
+    b = O.ba_top_accumulate(0, pb["F"], pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], threads=6)
+    np.testing.assert_allclose(a["acc"], b["acc"], rtol=1e-12, atol=1e-6)
+    np.testing.assert_array_equal(a["Hdd"], b["Hdd"])
+
+
+def test_relinearisation_identity(small):
+    """mode 1 re-adds J*delta to res_toZero = resF - J*delta, so it must reproduce resF."""
+    pb = small
+    F = pb["F"]
+    rtz = O.ba_fix_linearization(F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["deltaF"], pb["adHTdeltaF"], pb["cDeltaF"])
+    lin = O.ba_top_accumulate(1, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"],
+                              pb["adHTdeltaF"], pb["cDeltaF"])
+    dense = _dense_top(pb, 1)  # with resF
+    assert np.abs(lin["acc"] - dense).max() < 2e-5 * np.abs(dense).max()
+    marg = O.ba_top_accumulate(2, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz)
+    dense2 = _dense_top(pb, 2, rtz)
+    assert np.abs(marg["acc"] - dense2).max() < 1e-6 * np.abs(dense2).max()
+
+
+def test_per_point_terms(small):
+    pb = small
+    top = O.ba_top_accumulate(0, pb["F"], pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"])
+    J = pb["recs"].astype(np.float64)
+    p = 17
+    Hdd = bd = 0.0
+    Hcd = np.zeros(4)
+    for r in range(pb["res_begin"][p], pb["res_begin"][p + 1]):
+        if (pb["flags"][r] & 1) and not (pb["flags"][r] & 2):
+            M = np.array([[J[r, 64], J[r, 66]], [J[r, 65], J[r, 67]]])
+            d = J[r, 28:30]
+            JI_r = np.array([J[r, 0:8] @ J[r, 32:40], J[r, 0:8] @ J[r, 40:48]])
+            Hdd += d @ M @ d
+            bd += JI_r @ d
+            Hcd += J[r, 20:24] * (M @ d)[0] + J[r, 24:28] * (M @ d)[1]
+    assert abs(top["Hdd"][p] - Hdd) <= 1e-5 * abs(Hdd) + 1e-6 and abs(top["bd"][p] - bd) <= 1e-5 * abs(bd) + 1e-3
+    np.testing.assert_allclose(top["Hcd"][p], Hcd, rtol=1e-5, atol=1e-3)
+
+
+def _stitch_top_reference_single(F, acc, adHost, adTarget):
+    """AccumulatedTopHessianSSE::stitchDouble (single-thread statement, AccumulatedTopHessian.cpp:171-238)."""
+    n = 4 + 8 * F
+    H, b = np.zeros((n, n)), np.zeros(n)
+    for h in range(F):
+        for t in range(F):
+            k = h + F * t
+            A = acc[k]
+            AH, AT = adHost[k], adTarget[k]
+            hI, tI = 4 + 8 * h, 4 + 8 * t
+            H[hI:hI + 8, hI:hI + 8] += AH @ A[4:12, 4:12] @ AH.T
+            H[tI:tI + 8, tI:tI + 8] += AT @ A[4:12, 4:12] @ AT.T
+            H[hI:hI + 8, tI:tI + 8] += AH @ A[4:12, 4:12] @ AT.T
+            H[hI:hI + 8, 0:4] += AH @ A[4:12, 0:4]
+            H[tI:tI + 8, 0:4] += AT @ A[4:12, 0:4]
+            H[0:4, 0:4] += A[0:4, 0:4]
+            b[hI:hI + 8] += AH @ A[4:12, 12]
+            b[tI:tI + 8] += AT @ A[4:12, 12]
+            b[0:4] += A[0:4, 12]
+    for h in range(F):
+        hI = 4 + 8 * h
+        H[0:4, hI:hI + 8] = H[hI:hI + 8, 0:4].T
+        for t in range(h + 1, F):
+            tI = 4 + 8 * t
+            H[hI:hI + 8, tI:tI + 8] += H[tI:tI + 8, hI:hI + 8].T
+            H[tI:tI + 8, hI:hI + 8] = H[hI:hI + 8, tI:tI + 8].T
+    return H, b
+
+
+def test_top_stitch_matches_single_thread_statement(small):
+    pb = small
+    F = pb["F"]
+    top = O.ba_top_accumulate(0, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"])
+    H, b = O.ba_top_stitch(F, top["acc"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    Hr, br = _stitch_top_reference_single(F, top["acc"], pb["adHost"], pb["adTarget"])
+    np.testing.assert_allclose(H, Hr, rtol=1e-12, atol=1e-9 * np.abs(Hr).max())
+    np.testing.assert_allclose(b, br, rtol=1e-12, atol=1e-9 * np.abs(br).max())
+    np.testing.assert_allclose(H, H.T, atol=1e-9 * np.abs(H).max())
+    Hp, bp = O.ba_top_stitch(F, top["acc"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]), True, pb["cPrior"], pb["cDeltaF"],
+                             pb["frame_prior"], pb["frame_delta_prior"])
+    np.testing.assert_allclose(np.diag(Hp)[:4] - np.diag(H)[:4], pb["cPrior"], rtol=1e-6)
+    np.testing.assert_allclose(np.diag(Hp)[4:] - np.diag(H)[4:], pb["frame_prior"].ravel(), rtol=1e-6, atol=1e-3)
+    np.testing.assert_allclose(bp[4:] - b[4:], (pb["frame_prior"] * pb["frame_delta_prior"]).ravel(), atol=1e-9 * np.abs(b).max() + 1e-9)
+
+
+def test_sc_accumulator_and_stitch(small):
+    pb = small
+    F, P = pb["F"], pb["P"]
+    A = O.ba_top_accumulate(0, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"])
+    rtz = O.ba_fix_linearization(F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["deltaF"], pb["adHTdeltaF"], pb["cDeltaF"])
+    L = O.ba_top_accumulate(1, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"], pb["adHTdeltaF"], pb["cDeltaF"])
+    jp = O.ba_jpjd(pb["recs"])
+    sc = O.ba_sc_accumulate(F, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], jp, A["Hdd"], L["Hdd"], A["bd"], L["bd"],
+                            A["Hcd"], L["Hcd"], pb["priorF"], pb["deltaF"])
+    # direct restatement of AccumulatedSCHessian.cpp:34-77 for a handful of accumulators
+    accD = np.zeros_like(sc["accD"]); accE = np.zeros_like(sc["accE"]); Hcc = np.zeros((4, 4))
+    for p in range(P):
+        rs = [r for r in range(pb["res_begin"][p], pb["res_begin"][p + 1]) if pb["flags"][r] & 1]
+        if not rs:
+            assert sc["HdiF"][p] == 0
+            continue
+        Hh = max(np.float32(A["Hdd"][p] + L["Hdd"][p] + pb["priorF"][p]), np.float32(1e-10))
+        w = float(np.float32(1.0 / float(Hh)))
+        Hcd = (A["Hcd"][p] + L["Hcd"][p]).astype(np.float64)
+        Hcc += w * np.outer(Hcd, Hcd)
+        for r1 in rs:
+            k1 = pb["host_idx"][r1] + F * pb["target_idx"][r1]
+            accE[k1] += w * np.outer(jp[r1].astype(np.float64), Hcd)
+            for r2 in rs:
+                accD[k1 + F * F * pb["target_idx"][r2]] += w * np.outer(jp[r1].astype(np.float64), jp[r2].astype(np.float64))
+    np.testing.assert_allclose(sc["accD"], accD, rtol=1e-10, atol=1e-12 * np.abs(accD).max())
+    np.testing.assert_allclose(sc["accE"], accE, rtol=1e-10, atol=1e-12 * np.abs(accE).max())
+    np.testing.assert_allclose(sc["accHcc"], Hcc, rtol=1e-10)
+    # stitchDouble (single) vs stitchDoubleInternal (MT) statements agree: AccumulatedSCHessian.cpp:159-219 vs :78-157
+    H, b = O.ba_sc_stitch(F, sc, SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    n = 4 + 8 * F
+    Hr, br = np.zeros((n, n)), np.zeros(n)
+    for i in range(F):
+        for j in range(F):
+            ij = i + F * j
+            iI, jI = 4 + 8 * i, 4 + 8 * j
+            Hr[iI:iI + 8, 0:4] += pb["adHost"][ij] @ sc["accE"][ij]
+            Hr[jI:jI + 8, 0:4] += pb["adTarget"][ij] @ sc["accE"][ij]
+            br[iI:iI + 8] += pb["adHost"][ij] @ sc["accEB"][ij]
+            br[jI:jI + 8] += pb["adTarget"][ij] @ sc["accEB"][ij]
+            for k in range(F):
+                kI, ik = 4 + 8 * k, i + F * k
+                Dm = sc["accD"][ij + k * F * F]
+                Hr[iI:iI + 8, iI:iI + 8] += pb["adHost"][ij] @ Dm @ pb["adHost"][ik].T
+                Hr[jI:jI + 8, kI:kI + 8] += pb["adTarget"][ij] @ Dm @ pb["adTarget"][ik].T
+                Hr[jI:jI + 8, iI:iI + 8] += pb["adTarget"][ij] @ Dm @ pb["adHost"][ik].T
+                Hr[iI:iI + 8, kI:kI + 8] += pb["adHost"][ij] @ Dm @ pb["adTarget"][ik].T
+    Hr[0:4, 0:4] = sc["accHcc"]; br[0:4] = sc["accbc"]
+    for h in range(F):
+        Hr[0:4, 4 + 8 * h:12 + 8 * h] = Hr[4 + 8 * h:12 + 8 * h, 0:4].T
+    np.testing.assert_allclose(H, Hr, rtol=1e-11, atol=1e-10 * np.abs(Hr).max())
+    np.testing.assert_allclose(b, br, rtol=1e-11, atol=1e-10 * np.abs(br).max())
