@@ -172,12 +172,56 @@ def run_reference(args):
     }))
 
 
+# --------------------------------------------------------------------------------------- BA side line
+def bench_ba(ctx, stream, reps=50):
+    """BASELINE.json configs[3]: F=7, 2048 points/keyframe, R=86016: top accumulate (modes 0 and 1),
+    SC accumulate and both stitches with the records resident in HBM; CUDA-event timed."""
+    import torch
+    import edsgpu
+    from edsgpu import synth_ba
+    from oracle import oracle as O
+    pb = synth_ba.make_ba_problem()
+    F, P, R = pb["F"], pb["P"], pb["R"]
+    rtz = np.zeros((R, 8), np.float32)
+    w = edsgpu.BaWindow(ctx, F, pb["host_idx"], pb["target_idx"], pb["res_begin"])
+    w.set_residuals(pb["recs"], pb["flags"], rtz)
+    w.set_points(pb["deltaF"], pb["priorF"])
+    w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], synth_ba.col_major(pb["adHost"]), synth_ba.col_major(pb["adTarget"]))
+
+    def once():
+        w.top_accumulate(0, want_outputs=False)
+        w.top_accumulate(1, want_outputs=False)
+        w.sc_accumulate(True, want_outputs=False)
+
+    for _ in range(5):
+        once()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(reps):
+        once()
+    b.record(stream)
+    stream.synchronize()
+    ms = a.elapsed_time(b) / reps
+    t0 = time.perf_counter()
+    n_cpu = 20
+    for _ in range(n_cpu):
+        A = O.ba_top_accumulate(0, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], threads=6)
+        L = O.ba_top_accumulate(1, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"],
+                                pb["adHTdeltaF"], pb["cDeltaF"], threads=6)
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / n_cpu
+    alg = 2 * (296 * R + 12 * R + 364 * F * F + 24 * P) + (44 * R + 48 * P + 4 * (64 * F ** 3 + 40 * F * F + 20))  # SURVEY.md 8d
+    w.close()
+    return {"workload": "config4: F=7, P=%d, R=%d; top<0> + top<1> + SC accumulate, device-resident" % (P, R),
+            "accumulations_per_s": 1e3 / ms, "ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
+            "cpu_port_top_ms_6_threads": cpu_ms}
+
+
 # --------------------------------------------------------------------------------------- GPU arm
 def run_native(args):
     import torch
     import torch.distributed as dist
     import edsgpu
-    from edsgpu import synth
+    from edsgpu import shard, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,11 +316,7 @@ def run_native(args):
     barrier()
     launches = ctx.launches - launches0
     clk = clocks.stop() if rank == 0 else None
-    t_ms = ev0.elapsed_time(ev1)
-    t_all = torch.tensor([t_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    t_ms_max = float(t_all.item())
+    t_ms_max = shard.max_over_ranks(ev0.elapsed_time(ev1), dev)
     lm_ms = float(np.mean([a.elapsed_time(b) for a, b in lm_events]))
     states, infos = batch.gather()
     evals = float(np.mean([sum(i["evaluations"] for i in infos)]))  # last step's launch
@@ -292,21 +332,13 @@ def run_native(args):
     for k in range(args.steps):
         step_e2e(args.warmup + k)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    e_all = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_all, op=dist.ReduceOp.MAX)
-    e2e_s = float(e_all.item())
+    e2e_s = shard.max_over_ranks(time.perf_counter() - t0, dev)
 
     # ---- the one collective of the path: gather the final states over NCCL -------------
     batch.pack_states_dev(states_dev.data_ptr())
-    if world > 1:
-        gathered = [torch.zeros_like(states_dev) for _ in range(world)]
-        dist.all_gather(gathered, states_dev)
-        torch.cuda.synchronize()
-        final_states = torch.stack(gathered).cpu().numpy()
-    else:
-        final_states = states_dev.cpu().numpy()[None]
+    stream.synchronize()
+    final_states = shard.gather_states(states_dev).cpu().numpy()  # global sequence order, [world*S, 14]
+    ba_line = bench_ba(ctx, stream) if (rank == 0 and not args.no_ba) else None
 
     if rank == 0:
         windows = world * S * args.steps
@@ -344,9 +376,11 @@ def run_native(args):
                          "algorithmic_bytes_per_launch": alg, "launch_ms": lm_ms, "evaluations_per_launch": evals},
             "final_state_checksum": float(np.abs(final_states).sum()),
         }
+        if ba_line:
+            out["ba"] = ba_line
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_cpu = 6
+            n_cpu = 400  # ~10 s of CPU work
             wps, dt = cpu_windows_per_s(data[:2], n_cpu, 1, min(NUM_BLOCKS, cores))
             out["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": min(NUM_BLOCKS, cores), "kind": "port",
                                    "sample": "%d windows of the same workload, one sequence, %d threads (one per residual block), dual-number Jacobians, %.1f s"
@@ -364,6 +398,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--sequences", type=int, default=64, help="independent sequences per GPU (configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ba", action="store_true", help="skip the config-4 BA accumulation side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,6 @@
+import sys, time, numpy as np
+sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/slam-eds_b200')
+import torch, edsgpu, bench
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+ctx = edsgpu.Context(0, stream.cuda_stream)
+print(bench.bench_ba(ctx, stream, reps=int(sys.argv[1]) if len(sys.argv) > 1 else 50))

@@ -34,7 +34,7 @@ constexpr int O_RES = 0, O_JPDXI0 = 8, O_JPDXI1 = 14, O_JPDC0 = 20, O_JPDC1 = 24
 constexpr int CPARS = 4;
 constexpr int TOP_THREADS = 256, TOP_TILE = 512, NACC = 96;
 constexpr int MAXF = 8;
-constexpr int SC_THREADS = 256, SC_CHUNK = 128, SC_BATCH = 16, SC_LD = 72;  // 8*MAXF + 5 padded to 72
+constexpr int SC_THREADS = 256, SC_CHUNK = 64, SC_BATCH = 32, SC_LD = 72;  // 8*MAXF + 5 padded to 72
 
 struct BaDev {
     int F, P, R, num_tiles;
@@ -283,32 +283,46 @@ __global__ void __launch_bounds__(SC_THREADS) ba_sc_kernel(ScDev S) {
         __syncthreads();
         for (int i = tid; i < SC_BATCH * SC_LD; i += SC_THREADS) { (&z[0][0])[i] = 0.f; (&zs[0][0])[i] = 0.f; }
         __syncthreads();
-        if (tid < nb) {
-            const int p = S.pt_perm[start + b0 + tid];
+        // eight lanes per point (AccumulatedSCHessian.cpp:36-76): flags and JpJdF of its residuals are
+        // fetched with independent loads, the active count is a ballot over the lane group
+        {
+            const int q = tid >> 3, part = tid & 7, lane = tid & 31;
+            const unsigned gmask = 0xffu << (lane & 24);
+            const bool live = q < nb;
+            const int p = live ? S.pt_perm[start + b0 + q] : 0;
+            const int rb = live ? S.res_begin[p] : 0, re = live ? S.res_begin[p + 1] : 0;
             int ngood = 0;
-            for (int r = S.res_begin[p]; r < S.res_begin[p + 1]; ++r) ngood += (S.flags[r] & 1u);
+            for (int r0 = rb; r0 < re; r0 += 8) {
+                const int r = r0 + part;
+                const bool act = (r < re) && (S.flags[r] & 1u);
+                ngood += __popc(__ballot_sync(gmask, act));  // group-scoped: trip counts differ between groups
+            }
             float HdiF = 0.f, bdSum = 0.f;
-            if (ngood > 0) {  // :38-56
+            if (live && ngood > 0) {
                 float Hh = S.HddA[p] + S.HddL[p] + S.priorF[p];
                 if (Hh < 1e-10f) Hh = 1e-10f;
                 HdiF = (float)(1.0 / (double)Hh);
                 bdSum = S.bdA[p] + S.bdL[p];
                 if (S.shift_prior) bdSum += S.priorF[p] * S.deltaF[p];
-                for (int r = S.res_begin[p]; r < S.res_begin[p + 1]; ++r) {
+                if (part < 4) {
+                    const float hc = S.HcdA[4 * p + part] + S.HcdL[4 * p + part];
+                    z[q][8 * F + part] = hc;
+                    zs[q][8 * F + part] = HdiF * hc;
+                } else if (part == 4) {
+                    z[q][8 * F + 4] = bdSum;
+                }
+                for (int r = rb + part; r < re; r += 8) {
                     if (!(S.flags[r] & 1u)) continue;
                     const int t = S.target_idx[r];
                     const float4* j = reinterpret_cast<const float4*>(S.JpJdF + (size_t)8 * r);
                     const float4 a = __ldg(j), b = __ldg(j + 1);
-                    float* zz = &z[tid][8 * t];
-                    zz[0] = a.x; zz[1] = a.y; zz[2] = a.z; zz[3] = a.w; zz[4] = b.x; zz[5] = b.y; zz[6] = b.z; zz[7] = b.w;
+                    *reinterpret_cast<float4*>(&z[q][8 * t]) = a;
+                    *reinterpret_cast<float4*>(&z[q][8 * t + 4]) = b;
+                    *reinterpret_cast<float4*>(&zs[q][8 * t]) = make_float4(HdiF * a.x, HdiF * a.y, HdiF * a.z, HdiF * a.w);
+                    *reinterpret_cast<float4*>(&zs[q][8 * t + 4]) = make_float4(HdiF * b.x, HdiF * b.y, HdiF * b.z, HdiF * b.w);
                 }
-                const float4 ha = reinterpret_cast<const float4*>(S.HcdA)[p], hl = reinterpret_cast<const float4*>(S.HcdL)[p];
-                z[tid][8 * F] = ha.x + hl.x; z[tid][8 * F + 1] = ha.y + hl.y; z[tid][8 * F + 2] = ha.z + hl.z; z[tid][8 * F + 3] = ha.w + hl.w;
-                z[tid][8 * F + 4] = bdSum;
-                for (int k = 0; k < M; ++k) zs[tid][k] = HdiF * z[tid][k];
             }
-            S.HdiF[p] = HdiF;
-            S.bdSum[p] = bdSum;
+            if (live && part == 0) { S.HdiF[p] = HdiF; S.bdSum[p] = bdSum; }
         }
         __syncthreads();
 #pragma unroll
@@ -349,23 +363,23 @@ __global__ void ba_sc_finalize_kernel(int F, const float* __restrict__ partial, 
                                       double* __restrict__ hcc_host /*F x 20*/) {
     const int h = blockIdx.x, M = 8 * F + 4, N = 8 * F + 5, F2 = F * F;
     const int c0 = host_chunk_begin[h], c1 = host_chunk_begin[h + 1];
-    for (int e = threadIdx.x; e < M * N; e += blockDim.x) {
-        double s = 0.0;
-        for (int c = c0; c < c1; ++c) s += (double)partial[(size_t)c * M * N + e];
-        const int i = e / N, j = e % N;
-        if (i < 8 * F) {
-            const int t1 = i / 8, a = i % 8;
-            if (j < 8 * F) {           // accD[h + t1*F + t2*F2] (8x8)
-                const int t2 = j / 8, b = j % 8;
-                accD[(size_t)64 * (h + t1 * F + t2 * F2) + 8 * a + b] = s;
-            } else if (j < 8 * F + 4) {  // accE[h + t1*F] (8x4)
-                accE[(size_t)32 * (h + t1 * F) + 4 * a + (j - 8 * F)] = s;
-            } else {                    // accEB[h + t1*F] (8)
-                accEB[(size_t)8 * (h + t1 * F) + a] = s;
-            }
-        } else if (j >= 8 * F) {      // Hcd rows: [Hcc (4x4) | bc (4)]; the Hcd x z^T part is E^T, not needed
-            hcc_host[20 * h + 5 * (i - 8 * F) + (j - 8 * F)] = s;
+    const int e = blockIdx.y * blockDim.x + threadIdx.x;
+    if (e >= M * N) return;
+    double s = 0.0;
+    for (int c = c0; c < c1; ++c) s += (double)partial[(size_t)c * M * N + e];
+    const int i = e / N, j = e % N;
+    if (i < 8 * F) {
+        const int t1 = i / 8, a = i % 8;
+        if (j < 8 * F) {           // accD[h + t1*F + t2*F2] (8x8)
+            const int t2 = j / 8, b = j % 8;
+            accD[(size_t)64 * (h + t1 * F + t2 * F2) + 8 * a + b] = s;
+        } else if (j < 8 * F + 4) {  // accE[h + t1*F] (8x4)
+            accE[(size_t)32 * (h + t1 * F) + 4 * a + (j - 8 * F)] = s;
+        } else {                    // accEB[h + t1*F] (8)
+            accEB[(size_t)8 * (h + t1 * F) + a] = s;
         }
+    } else if (j >= 8 * F) {      // Hcd rows: [Hcc (4x4) | bc (4)]; the Hcd x z^T part is E^T, not needed
+        hcc_host[20 * h + 5 * (i - 8 * F) + (j - 8 * F)] = s;
     }
 }
 __global__ void ba_sc_hcc_kernel(int F, const double* __restrict__ hcc_host, double* __restrict__ accHcc, double* __restrict__ accbc) {
@@ -586,11 +600,18 @@ edsgpu_status edsgpu_ba_create(edsgpu_ctx* ctx, int F, int P, int R, const int32
         std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1);
         for (int r = 0; r < R; ++r) perm[cur[host_idx[r] + F * target_idx[r]]++] = r;
     }
+    // tile size: the smallest multiple of 64 (>= 256) whose tile count fits one wave of one CTA per SM
+    int tile_sz = TOP_THREADS;
+    for (;; tile_sz += 64) {
+        long tiles = 0;
+        for (int k = 0; k < F2; ++k) tiles += (cnt[k + 1] - cnt[k] + tile_sz - 1) / tile_sz;
+        if (tiles <= ctx->num_sms || tile_sz >= 16384) break;
+    }
     std::vector<int32_t> tile_key, tile_start, tile_count, key_tile_begin(F2 + 1, 0);
     for (int k = 0; k < F2; ++k) {
         key_tile_begin[k] = (int32_t)tile_key.size();
-        for (int s = cnt[k]; s < cnt[k + 1]; s += TOP_TILE) {
-            tile_key.push_back(k); tile_start.push_back(s); tile_count.push_back(std::min(TOP_TILE, cnt[k + 1] - s));
+        for (int s = cnt[k]; s < cnt[k + 1]; s += tile_sz) {
+            tile_key.push_back(k); tile_start.push_back(s); tile_count.push_back(std::min(tile_sz, cnt[k + 1] - s));
         }
     }
     key_tile_begin[F2] = (int32_t)tile_key.size();
@@ -781,8 +802,10 @@ edsgpu_status edsgpu_ba_sc_accumulate(edsgpu_ba* w, int shift_prior_to_zero, dou
     ba_sc_kernel<<<w->num_chunks, SC_THREADS, 0, ctx->stream>>>(s);
     EDS_CUDA(ctx, cudaGetLastError());
     const size_t F2 = (size_t)w->F * w->F;
-    EDS_CUDA(ctx, cudaMemsetAsync(w->accD, 0, 8 * 64 * F2 * w->F, ctx->stream));
-    ba_sc_finalize_kernel<<<w->F, 256, 0, ctx->stream>>>(w->F, w->sc_partial, w->host_chunk_begin, w->accD, w->accE, w->accEB, w->hcc_host);
+    {
+        const int MN = (8 * w->F + 4) * (8 * w->F + 5);
+        ba_sc_finalize_kernel<<<dim3(w->F, (MN + 127) / 128), 128, 0, ctx->stream>>>(w->F, w->sc_partial, w->host_chunk_begin, w->accD, w->accE, w->accEB, w->hcc_host);
+    }
     ba_sc_hcc_kernel<<<1, 32, 0, ctx->stream>>>(w->F, w->hcc_host, w->accHcc, w->accbc);
     ctx->launches += 3;
     EDS_CUDA(ctx, cudaGetLastError());
