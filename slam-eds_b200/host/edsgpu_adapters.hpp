@@ -1,0 +1,269 @@
+// Header-only C++ host layer over the C ABI (include/edsgpu.h).
+//
+// Mirrors the class surface the reference exposes for the hot path -- same class names, method
+// names, argument meaning and error behaviour -- without the reference's third-party types (Eigen,
+// OpenCV, Rock base-types are not available in this image): plain arrays stand in for
+// Eigen::Vector3d / Quaterniond / base::Transform3d.  INTEGRATION.md shows the same bodies written
+// against the reference's own types.
+//
+//   eds::tracking::EventFrame   src/tracking/EventFrame.hpp:31-107
+//   eds::tracking::Tracker      src/tracking/Tracker.hpp:36-114
+//   dso::AccumulatedTopHessianSSE / AccumulatedSCHessianSSE   src/bundles/Accumulated{Top,SC}Hessian.h
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/edsgpu.h"
+
+namespace edsgpu_host {
+
+// RAII context; throws when there is no CUDA device (there is no CPU fallback).
+class Context {
+  public:
+    explicit Context(int device = 0, void* stream = nullptr) {
+        if (edsgpu_create(device, stream, &ctx_) != EDSGPU_OK) throw std::runtime_error("edsgpu_create failed: no CUDA device");
+    }
+    ~Context() { edsgpu_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    edsgpu_ctx* get() const { return ctx_; }
+    void check(edsgpu_status st) const {
+        if (st != EDSGPU_OK) throw std::runtime_error(std::string("edsgpu: ") + edsgpu_last_error_string(ctx_));
+    }
+
+  private:
+    edsgpu_ctx* ctx_ = nullptr;
+};
+
+}  // namespace edsgpu_host
+
+namespace eds { namespace tracking {
+
+struct Event {  // stand-in for base::samples::Event (src/utils/Utils.hpp:40)
+    uint16_t x, y;
+    int64_t ts_us;
+    uint8_t polarity;
+};
+
+enum LOSS_FUNCTION { NONE = 0, HUBER = 1, CAUCHY = 2 };
+enum LOSS_PARAM_METHOD { CONSTANT = 0, MAD = 1, STD = 2 };  // Tracker.hpp:34
+
+struct SolverOptions {  // tracking/Config.hpp:40-47
+    int num_threads = 8;
+    std::vector<int> max_num_iterations{30};
+    double function_tolerance = 1e-6;
+};
+struct Config {  // tracking/Config.hpp:49-57
+    LOSS_FUNCTION loss_type = HUBER;
+    std::vector<double> loss_params{0.05};
+    SolverOptions options;
+};
+struct TrackerInfo {  // tracking/Config.hpp:60-68
+    double meas_time_us = 0;
+    uint32_t num_points = 0;
+    int num_iterations = 0;
+    double time_seconds = 0;
+    uint8_t success = 0;
+};
+
+// EventFrame (EventFrame.hpp:31-107), pyramid level 0.
+class EventFrame {
+  public:
+    // EventFrame(cam, newcam, ...): the forward undistortion LUT is built once (EventFrame.cpp:53-81).
+    EventFrame(const edsgpu_host::Context& ctx, uint16_t height, uint16_t width, const float* fwd_mapx = nullptr, const float* fwd_mapy = nullptr)
+        : ctx_(ctx), height(height), width(width) {
+        if (fwd_mapx) ctx_.check(edsgpu_lut_create(ctx_.get(), height, width, fwd_mapx, fwd_mapy, &lut_));
+        ctx_.check(edsgpu_frames_create(ctx_.get(), height, width, 1, &frames_));
+    }
+    ~EventFrame() { edsgpu_frames_destroy(frames_); edsgpu_lut_destroy(lut_); }
+    EventFrame(const EventFrame&) = delete;
+    EventFrame& operator=(const EventFrame&) = delete;
+
+    // void create(idx, events, height, width, num_levels, T, out_size)  (EventFrame.cpp:302-389).
+    // Throws std::runtime_error on first_ts > last_ts like the reference (:325-329).
+    void create(const uint64_t& idx_, const std::vector<Event>& events, bool keep_host_frame = false) {
+        idx = idx_;
+        const size_t n = events.size();
+        x_.resize(n); y_.resize(n); p_.resize(n); t_.resize(n);
+        for (size_t i = 0; i < n; ++i) { x_[i] = events[i].x; y_[i] = events[i].y; p_[i] = events[i].polarity; t_[i] = events[i].ts_us; }
+        event_frame.assign(keep_host_frame ? (size_t)height * width : 0, 0.0);
+        double nrm = 0.0;
+        edsgpu_status st = edsgpu_event_frame_create(ctx_.get(), frames_, 0, lut_, x_.data(), y_.data(), p_.data(), t_.data(), (int)n,
+                                                     EDSGPU_DRAW_BILINEAR, 1, 0.5f, &nrm, &time_us, &delta_time_us,
+                                                     keep_host_frame ? event_frame.data() : nullptr);
+        if (st == EDSGPU_NON_MONOTONIC_TIME) throw std::runtime_error("[EVENT_FRAME] FATAL ERROR Event time[0] > event time [N-1] ");
+        ctx_.check(st);
+        norm = nrm;
+    }
+    const edsgpu_frames* frames() const { return frames_; }
+
+    uint64_t idx = 0;
+    uint16_t height, width;
+    double norm = 0;                   // EventFrame::norm[0]
+    int64_t time_us = 0, delta_time_us = 0;
+    std::vector<double> event_frame;   // EventFrame::event_frame[0], filled on request
+
+  private:
+    const edsgpu_host::Context& ctx_;
+    edsgpu_lut* lut_ = nullptr;
+    edsgpu_frames* frames_ = nullptr;
+    std::vector<uint16_t> x_, y_;
+    std::vector<uint8_t> p_;
+    std::vector<int64_t> t_;
+};
+
+// The KeyFrame arrays the tracker gathers (KeyFrame.hpp:59-96).
+class KeyFrame {
+  public:
+    KeyFrame(const edsgpu_host::Context& ctx, const std::vector<double>& grad_xy, const std::vector<double>& norm_coord_xy,
+             const std::vector<double>& idp, const std::vector<double>& weights, int height, int width, double fx, double fy, double cx,
+             double cy, int num_blocks)
+        : ctx_(ctx) {
+        ctx_.check(edsgpu_keyframe_create(ctx_.get(), (int)idp.size(), grad_xy.data(), norm_coord_xy.data(), idp.data(), weights.data(), height,
+                                          width, fx, fy, cx, cy, num_blocks, &kf_));
+        residuals.resize(idp.size());
+    }
+    ~KeyFrame() { edsgpu_keyframe_destroy(kf_); }
+    KeyFrame(const KeyFrame&) = delete;
+    KeyFrame& operator=(const KeyFrame&) = delete;
+    const edsgpu_keyframe* get() const { return kf_; }
+    std::vector<double> residuals;  // KeyFrame::residuals, written by Tracker::optimize (Tracker.cpp:223-230)
+
+  private:
+    const edsgpu_host::Context& ctx_;
+    edsgpu_keyframe* kf_ = nullptr;
+};
+
+// Tracker (Tracker.hpp:36-114): state px, qx, vx + config.loss_params carried across windows.
+class Tracker {
+  public:
+    Config config;
+
+    Tracker(const edsgpu_host::Context& ctx, std::shared_ptr<KeyFrame> kf, const Config& config_, int level = 0) : config(config_), ctx_(ctx), kf_(kf) {
+        edsgpu_tracker_config c{};
+        c.num_blocks = config.options.num_threads;
+        c.loss_type = (int)config.loss_type;
+        c.max_iterations = config.options.max_num_iterations.at(level);
+        c.loss_param_method = MAD;
+        c.function_tolerance = config.options.function_tolerance;
+        c.gradient_tolerance = 1e-08;   // Tracker.cpp:142
+        c.parameter_tolerance = 1e-06;  // Tracker.cpp:143
+        ctx_.check(edsgpu_tracker_create(ctx_.get(), &c, config.loss_params.at(0), &tr_));
+    }
+    ~Tracker() { edsgpu_tracker_destroy(tr_); }
+    Tracker(const Tracker&) = delete;
+    Tracker& operator=(const Tracker&) = delete;
+
+    // reset(kf, px, qx, velo) (Tracker.cpp:50-73)
+    void reset(std::shared_ptr<KeyFrame> kf, const std::array<double, 3>& px, const std::array<double, 4>& qx_xyzw, const std::array<double, 6>* velo = nullptr) {
+        kf_ = kf;
+        ctx_.check(edsgpu_tracker_set_state(tr_, px.data(), qx_xyzw.data(), velo ? velo->data() : nullptr, nullptr));
+    }
+    // set(T_kf_ef) (Tracker.cpp:75-82): the tracker works with the inverse transform
+    void set(const std::array<double, 3>& t_kf_ef, const std::array<double, 4>& q_kf_ef_xyzw) {
+        std::array<double, 3> p;
+        std::array<double, 4> q;
+        inverse(t_kf_ef, q_kf_ef_xyzw, p, q);
+        ctx_.check(edsgpu_tracker_set_state(tr_, p.data(), q.data(), nullptr, nullptr));
+    }
+    // bool optimize(id, event_frame, T_kf_ef, loss_param_method) (Tracker.cpp:104-241)
+    bool optimize(const int& id, const EventFrame& ef, std::array<double, 3>& t_kf_ef, std::array<double, 4>& q_kf_ef_xyzw,
+                  const LOSS_PARAM_METHOD loss_param_method = MAD) {
+        (void)id;
+        (void)loss_param_method;  // fixed at construction in this adapter
+        edsgpu_tracker_info inf{};
+        double tau = 0.0;
+        edsgpu_status st = edsgpu_tracker_optimize(tr_, kf_->get(), ef.frames(), 0, px.data(), qx.data(), vx.data(), kf_->residuals.data(), &tau, &inf);
+        info.num_points = (uint32_t)inf.num_points;
+        info.num_iterations = inf.iterations;
+        info.success = (uint8_t)inf.usable;
+        if (st == EDSGPU_NOT_USABLE) return false;  // !summary.IsSolutionUsable(), Tracker.cpp:237-240
+        ctx_.check(st);
+        inverse(px, qx, t_kf_ef, q_kf_ef_xyzw);     // T_kf_ef = getTransform().inverse(), Tracker.cpp:220
+        config.loss_params = {tau};                 // Tracker.cpp:233
+        return true;
+    }
+    std::array<double, 6>& getVelocity() { return vx; }
+    std::vector<double> getLossParams() const { return config.loss_params; }
+    TrackerInfo getInfo() const { return info; }
+
+    std::array<double, 3> px{};
+    std::array<double, 4> qx{{0, 0, 0, 1}};
+    std::array<double, 6> vx{};
+
+  private:
+    // inverse of a rigid transform given as (t, unit quaternion xyzw)
+    static void inverse(const std::array<double, 3>& t, const std::array<double, 4>& q, std::array<double, 3>& ti, std::array<double, 4>& qi) {
+        qi = {-q[0], -q[1], -q[2], q[3]};
+        const double x = qi[0], y = qi[1], z = qi[2], w = qi[3];
+        const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), 1 - 2 * (x * x + z * z),
+                             2 * (y * z - w * x),     2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+        for (int r = 0; r < 3; ++r) ti[r] = -(R[3 * r] * t[0] + R[3 * r + 1] * t[1] + R[3 * r + 2] * t[2]);
+    }
+    const edsgpu_host::Context& ctx_;
+    std::shared_ptr<KeyFrame> kf_;
+    edsgpu_tracker* tr_ = nullptr;
+    TrackerInfo info;
+};
+
+} }  // namespace eds::tracking
+
+namespace dso {
+
+// The accumulator side of dso::EnergyFunctional (EnergyFunctional.cpp:197-261) for one residual graph:
+// accumulateAF_MT / accumulateLF_MT / accumulateSCF_MT with their stitches.
+class HessianAccumulators {
+  public:
+    HessianAccumulators(const edsgpu_host::Context& ctx, int nFrames, const std::vector<int32_t>& hostIDX, const std::vector<int32_t>& targetIDX,
+                        const std::vector<int32_t>& res_begin)
+        : ctx_(ctx), nFrames(nFrames), n(4 + 8 * nFrames) {
+        ctx_.check(edsgpu_ba_create(ctx_.get(), nFrames, (int)res_begin.size() - 1, (int)hostIDX.size(), hostIDX.data(), targetIDX.data(),
+                                    res_begin.data(), &ba_));
+    }
+    ~HessianAccumulators() { edsgpu_ba_destroy(ba_); }
+    HessianAccumulators(const HessianAccumulators&) = delete;
+    HessianAccumulators& operator=(const HessianAccumulators&) = delete;
+
+    // records: R x 76 floats (RawResidualJacobian), flags: EDSGPU_RES_ACTIVE | EDSGPU_RES_LINEARIZED
+    void setResiduals(const float* records, const uint8_t* flags, const float* res_toZeroF) { ctx_.check(edsgpu_ba_set_residuals(ba_, records, flags, res_toZeroF)); }
+    void setPoints(const float* deltaF, const float* priorF) { ctx_.check(edsgpu_ba_set_points(ba_, deltaF, priorF)); }
+    // setAdjointsF / setDeltaF results (EnergyFunctional.cpp:46-106,171-194)
+    void setFrames(const float* adHTdeltaF, const float* cDeltaF, const double* adHost, const double* adTarget) {
+        ctx_.check(edsgpu_ba_set_frames(ba_, adHTdeltaF, cDeltaF, adHost, adTarget));
+    }
+    // accumulateAF_MT(H, b): addPoint<0> over all points + stitchDoubleMT(usePrior = false)
+    void accumulateAF_MT(std::vector<double>& H, std::vector<double>& b) {
+        ctx_.check(edsgpu_ba_top_accumulate(ba_, 0, nullptr, nullptr, nullptr, nullptr, nullptr));
+        H.assign((size_t)n * n, 0.0); b.assign(n, 0.0);
+        ctx_.check(edsgpu_ba_top_stitch(ba_, 0, 0, nullptr, nullptr, nullptr, H.data(), b.data()));
+    }
+    // accumulateLF_MT(H, b): addPoint<1> + stitchDoubleMT(usePrior = true)
+    void accumulateLF_MT(std::vector<double>& H, std::vector<double>& b, const double cPrior[4], const double* framePrior, const double* frameDeltaPrior) {
+        ctx_.check(edsgpu_ba_top_accumulate(ba_, 1, nullptr, nullptr, nullptr, nullptr, nullptr));
+        H.assign((size_t)n * n, 0.0); b.assign(n, 0.0);
+        ctx_.check(edsgpu_ba_top_stitch(ba_, 1, 1, cPrior, framePrior, frameDeltaPrior, H.data(), b.data()));
+    }
+    // accumulateSCF_MT(H, b): addPoint(p, shiftPriorToZero = true) + stitchDoubleMT; also EFPoint::HdiF, bdSumF
+    void accumulateSCF_MT(std::vector<double>& H, std::vector<double>& b, std::vector<float>* HdiF = nullptr, std::vector<float>* bdSumF = nullptr, int P = 0) {
+        if (HdiF) HdiF->assign(P, 0.f);
+        if (bdSumF) bdSumF->assign(P, 0.f);
+        ctx_.check(edsgpu_ba_sc_accumulate(ba_, 1, nullptr, nullptr, nullptr, nullptr, nullptr, HdiF ? HdiF->data() : nullptr,
+                                           bdSumF ? bdSumF->data() : nullptr));
+        H.assign((size_t)n * n, 0.0); b.assign(n, 0.0);
+        ctx_.check(edsgpu_ba_sc_stitch(ba_, H.data(), b.data()));
+    }
+
+  private:
+    const edsgpu_host::Context& ctx_;
+    edsgpu_ba* ba_ = nullptr;
+
+  public:
+    const int nFrames, n;
+};
+
+}  // namespace dso
