@@ -22,6 +22,7 @@
 //                     ||m||^2 = v^T A_b v and sum m_i g_i = A_b v need no sweep).
 #include <cooperative_groups.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "frames.cuh"
@@ -33,8 +34,12 @@ namespace {
 constexpr int TRK_THREADS = 256;
 constexpr int TRK_WARPS = TRK_THREADS / 32;
 constexpr int NACC = 96;        // 78 (upper triangle of J^T J) + 12 (J^T r) + 6 padding
+constexpr int JLD = 20;         // floats per point row in shared memory (80 B: conflict-free 128-bit access)
+constexpr int N_PROD = 6;       // producer warps: per-point residual + Jacobian rows
+constexpr int N_CONS = TRK_WARPS - N_PROD;  // consumer warps: own the outer-product accumulators
+constexpr int N_SLOTS = 2 * N_PROD;         // ring of 32-point batches, two per producer warp
 constexpr int NSLOT = 92;       // 78 + 12 + cost + block squared norm
-constexpr int MAX_BLOCKS = 32;  // residual blocks per problem (config.options.num_threads)
+constexpr int MAX_BLOCKS = 16;  // residual blocks per problem (config.options.num_threads)
 constexpr int MAX_CLUSTER = 8;
 constexpr double kEps = 1e-05;  // PhotometricError.hpp:200
 
@@ -144,15 +149,18 @@ struct LmState {
 struct EvalConst {
     double R[9], t[3];               // Eigen toRotationMatrix(q), translation
     float vf[6], inv_vs, inv_vn;     // velocity, 1/|v|^2, 1/|v|
-    float blk[MAX_BLOCKS][8];        // per residual block: 1/M, c/M^3 (6), pad
+    float blk[MAX_BLOCKS][8];        // per residual block: 1/M, alpha, beta[6] (see eval_point)
     int cmd;
 };
 
 struct CtaShared {
     EvalConst ec;
-    // reduction scratch, double-buffered over residual blocks
-    double warp_part[2][TRK_WARPS][NACC];
-    double warp_s[2][TRK_WARPS];
+    // ring of 32-point batches of rows [J(12) r pad], guarded by full/empty mbarriers
+    alignas(16) float ring[N_SLOTS][32][JLD];
+    alignas(8) unsigned long long full_bar[N_SLOTS];
+    alignas(8) unsigned long long empty_bar[N_SLOTS];
+    double blk_sum[2][NACC];          // reduced entries of the current residual block (double-buffered)
+    double warp_s[2][TRK_WARPS];      // producers' sum of r^2
     double loss_a;
     // leader only
     double slots[MAX_BLOCKS][NSLOT];  // one slot per residual block, filled over DSMEM
@@ -169,23 +177,25 @@ __constant__ unsigned char c_tri_b[78] = {0,1,2,3,4,5,6,7,8,9,10,11,1,2,3,4,5,6,
 // ------------------------------------------------------------------------------------------
 // per-point residual + analytic tangent-space Jacobian
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cubic_hermite(float p0, float p1, float p2, float p3, float x, float& f, float& dfdx) {
-    // ceres CubicHermiteSpline (Catmull-Rom), call site PhotometricError.hpp:172
-    const float a = 0.5f * (-p0 + 3.0f * p1 - 3.0f * p2 + p3);
-    const float b = 0.5f * (2.0f * p0 - 5.0f * p1 + 4.0f * p2 - p3);
-    const float c = 0.5f * (-p0 + p2);
-    f = p1 + x * (c + x * (b + x * a));
-    dfdx = c + x * (2.0f * b + 3.0f * a * x);
-}
-__device__ __forceinline__ float cubic_hermite_f(float p0, float p1, float p2, float p3, float x) {
-    const float a = 0.5f * (-p0 + 3.0f * p1 - 3.0f * p2 + p3);
-    const float b = 0.5f * (2.0f * p0 - 5.0f * p1 + 4.0f * p2 - p3);
-    const float c = 0.5f * (-p0 + p2);
-    return p1 + x * (c + x * (b + x * a));
+// Catmull-Rom weights of ceres' CubicHermiteSpline (call site PhotometricError.hpp:172) in basis
+// form: f = sum_k w_k(x) p_k, f' = sum_k dw_k(x) p_k  (same cubic as the Horner form a,b,c,d)
+__device__ __forceinline__ void cr_weights(float x, float* w, float* dw) {
+    const float x2 = x * x;
+    w[0] = 0.5f * x * ((2.0f - x) * x - 1.0f);
+    w[1] = 0.5f * (x2 * (3.0f * x - 5.0f) + 2.0f);
+    w[2] = 0.5f * x * ((4.0f - 3.0f * x) * x + 1.0f);
+    w[3] = 0.5f * x2 * (x - 1.0f);
+    dw[0] = 0.5f * ((4.0f - 3.0f * x) * x - 1.0f);
+    dw[1] = 0.5f * x * (9.0f * x - 10.0f);
+    dw[2] = 0.5f * ((8.0f - 9.0f * x) * x + 1.0f);
+    dw[3] = 0.5f * x * (3.0f * x - 2.0f);
 }
 
+// per-block constants published by the leader: bc = {1/M, alpha, beta[6]} with
+// alpha = 1/(M |v|), beta_k = (c_k/M^3 + kappa v_k)/|v|, kappa = (1/M - c.v/M^3)/|v|^2, so that the
+// tangent-space velocity Jacobian  (w (g/M - m c/M^3)) (I - v v^T/|v|^2)/|v|  =  w (alpha g - m beta)
 template <bool WANT_J>
-__device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, const float* __restrict__ bc /* 1/M, c/M^3 */,
+__device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, const float* __restrict__ bc,
                                            const float* __restrict__ frame, float inv_norm, int idx, float* __restrict__ J, float& r) {
     const float4 g4 = __ldg(&kf.gxy[idx]);
     const float2 dw = __ldg(&kf.dw[idx]);
@@ -209,53 +219,75 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, 
     const double az = K.R[6] * kx + K.R[7] * ky + K.R[8] * kz;
     const double px = ax + K.t[0], py = ay + K.t[1], pz = az + K.t[2];
     const double iz = 1.0 / pz;
-    double u = kf.fx * (px * iz) + kf.cx;
-    double v = kf.fy * (py * iz) + kf.cy;
-    // clamped Grid2D makes the interpolant constant outside [-1, n+1]; NaN-safe clamp
-    u = fmin(fmax(u, -4.0), (double)kf.W + 4.0);
-    v = fmin(fmax(v, -4.0), (double)kf.H + 4.0);
+    const double u = kf.fx * (px * iz) + kf.cx;
+    const double v = kf.fy * (py * iz) + kf.cy;
     const double fu = floor(u), fv = floor(v);
-    const int col = (int)fu, row = (int)fv;
-    const float tc = (float)(u - fu), tr = (float)(v - fv);
+    // The clamped Grid2D makes the interpolant constant more than 2 px outside the image: clamp the
+    // integer cell (saturating conversion) and drop the fraction there; identical inside.
     const int W = kf.W, H = kf.H;
+    const int col_raw = __double2int_rd(u), row_raw = __double2int_rd(v);
+    const int col = max(-4, min(col_raw, W + 3)), row = max(-4, min(row_raw, H + 3));
+    const float tc = (col == col_raw) ? (float)(u - fu) : 0.f;
+    const float tr = (row == row_raw) ? (float)(v - fv) : 0.f;
     const int c0 = max(0, min(col - 1, W - 1)), c1 = max(0, min(col, W - 1));
     const int c2 = max(0, min(col + 1, W - 1)), c3 = max(0, min(col + 2, W - 1));
-    float fr[4], dfc[4];
+    float wc[4], dwc[4], wr[4], dwr[4];
+    cr_weights(tc, wc, dwc);
+    cr_weights(tr, wr, dwr);
+    float f = 0.f, dfdr = 0.f, dfdc = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int rr = max(0, min(row - 1 + k, H - 1));
         const float* rp = frame + (size_t)rr * W;
-        cubic_hermite(__ldg(rp + c0), __ldg(rp + c1), __ldg(rp + c2), __ldg(rp + c3), tc, fr[k], dfc[k]);
+        const float p0 = __ldg(rp + c0), p1 = __ldg(rp + c1), p2 = __ldg(rp + c2), p3 = __ldg(rp + c3);
+        const float fr = wc[0] * p0 + wc[1] * p1 + wc[2] * p2 + wc[3] * p3;
+        f += wr[k] * fr;
+        dfdr += dwr[k] * fr;
+        if (WANT_J) dfdc += wr[k] * (dwc[0] * p0 + dwc[1] * p1 + dwc[2] * p2 + dwc[3] * p3);
     }
-    float f, dfdr;
-    cubic_hermite(fr[0], fr[1], fr[2], fr[3], tr, f, dfdr);
-    const float dfdc = cubic_hermite_f(dfc[0], dfc[1], dfc[2], dfc[3], tr);
-    const float e = inv_norm * f, er = inv_norm * dfdr, ec = inv_norm * dfdc;
+    const float e = inv_norm * f;
     r = w * (m * bc[0] - e);  // PhotometricError.hpp:173
     if (!WANT_J) return;
+    const float er = inv_norm * dfdr, ec = inv_norm * dfdc;
     // d r / d P  (P = R kp + t)
     const float izf = (float)iz, fxf = (float)kf.fx, fyf = (float)kf.fy;
     const float pxf = (float)px, pyf = (float)py;
-    const float dPx = -w * ec * fxf * izf;
-    const float dPy = -w * er * fyf * izf;
-    const float dPz = w * (ec * fxf * pxf + er * fyf * pyf) * izf * izf;
+    const float wiz = w * izf;
+    const float dPx = -wiz * ec * fxf;
+    const float dPy = -wiz * er * fyf;
+    const float dPz = -(dPx * pxf + dPy * pyf) * izf;
     J[0] = dPx; J[1] = dPy; J[2] = dPz;
     // quaternion tangent: q <- [sin|d| d/|d|, cos|d|] * q rotates by 2|d|: dP/dtheta = -2 [R kp]x
-    const float axf = (float)ax, ayf = (float)ay, azf = (float)az;
-    J[3] = 2.0f * (ayf * dPz - azf * dPy);
-    J[4] = 2.0f * (azf * dPx - axf * dPz);
-    J[5] = 2.0f * (axf * dPy - ayf * dPx);
-    // velocity: d r/d v = w (g/M - m c/M^3), then the unit-norm Plus Jacobian (I - v v^T/s)/|v|
-    float jv[6], dot = 0.f;
+    const float axf = 2.0f * (float)ax, ayf = 2.0f * (float)ay, azf = 2.0f * (float)az;
+    J[3] = ayf * dPz - azf * dPy;
+    J[4] = azf * dPx - axf * dPz;
+    J[5] = axf * dPy - ayf * dPx;
+    // velocity block in the tangent space of the unit-norm retraction
+    const float wa = w * bc[1], wm = w * m;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { jv[k] = w * (g[k] * bc[0] - m * bc[1 + k]); dot += jv[k] * K.vf[k]; }
-    const float dn = dot * K.inv_vs;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) J[6 + k] = (jv[k] - dn * K.vf[k]) * K.inv_vn;
+    for (int k = 0; k < 6; ++k) J[6 + k] = wa * g[k] - wm * bc[2 + k];
 }
 
-// halving butterfly: 96 per-lane values -> 3 warp-reduced values per lane.
-// lane l ends with entries base(l)+{0,1,2}, base = 48 b4 + 24 b3 + 12 b2 + 6 b1 + 3 b0.
+// ---- mbarrier helpers (shared::cta) ---------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// halving butterfly: 2*HALF per-lane values -> HALF, lanes with bit OFFSET keep the upper half
 template <int HALF, int OFFSET>
 __device__ __forceinline__ void butterfly_step(float* a, unsigned lane) {
     const bool upper = (lane & OFFSET) != 0;
@@ -266,23 +298,70 @@ __device__ __forceinline__ void butterfly_step(float* a, unsigned lane) {
         a[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFFSET);
     }
 }
-__device__ __forceinline__ int butterfly_base(unsigned lane) {
-    return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
+
+// consumer: rows [R0,R1) of the upper triangle of [J r]^T [J r] (index 12 = r; the r*r entry is kept
+// in fp64 by the producers).  Entry order: row-major over (a, c >= a).
+template <int R0, int R1>
+struct RowBlock {
+    static constexpr int count() { int n = 0; for (int a = R0; a < R1; ++a) n += 13 - a; return n; }
+    // slot of local entry i: 78 upper-triangle entries of J^T J, then 12 of J^T r
+    static __device__ __forceinline__ int slot(int i) {
+        int a = R0;
+        while (i >= 13 - a) { i -= 13 - a; ++a; }
+        const int c = a + i;
+        return (c < 12) ? tri_index(a, c) : 78 + a;
+    }
+    static __device__ __forceinline__ void accumulate(const float (*rows)[JLD], int lane, float* acc) {
+        const float4* row = reinterpret_cast<const float4*>(&rows[lane][0]);
+        float v[16];
+#pragma unroll
+        for (int q = R0 / 4; q < 4; ++q) {
+            const float4 t = row[q];
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+        int e = 0;
+#pragma unroll
+        for (int a = R0; a < R1; ++a)
+#pragma unroll
+            for (int c = a; c < 13; ++c) acc[e++] += v[a] * v[c];
+    }
+};
+typedef RowBlock<0, 4> ConsRows0;   // 13+12+11+10 = 46 entries
+typedef RowBlock<4, 12> ConsRows1;  // 9+8+...+2   = 44 entries
+
+// 48 per-lane partial sums -> warp totals; lane l (even) ends with entries base(l)+{0,1,2}
+__device__ __forceinline__ void reduce48(float* acc, unsigned lane) {
+    butterfly_step<24, 16>(acc, lane);
+    butterfly_step<12, 8>(acc, lane);
+    butterfly_step<6, 4>(acc, lane);
+    butterfly_step<3, 2>(acc, lane);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+}
+__device__ __forceinline__ int reduce48_base(unsigned lane) {
+    return 24 * ((lane >> 4) & 1) + 12 * ((lane >> 3) & 1) + 6 * ((lane >> 2) & 1) + 3 * ((lane >> 1) & 1);
 }
 
 // One CTA evaluates the residual blocks dealt to it with the constants in sh.ec and stores, per
 // block, [rho' * JtJ (78) | rho' * Jtr (12) | 0.5 rho(s) | s] into slot_base[b] (leader smem, DSMEM).
+//
+// Warp-specialised: producer warps sweep the points 32 at a time (residual + analytic Jacobian row
+// -> shared-memory ring slot, mbarrier "full"), consumer warps own the outer-product accumulators
+// (46 / 44 fp32 registers per lane) and drain the ring (mbarrier "empty").  No CTA-wide barrier inside
+// the sweep and <= 128 registers per thread, so two CTAs share an SM and hide each other's stalls
+// (and the leader's serial LM step).  `batch_counter` numbers the batches of the whole kernel so that
+// both sides derive slot and phase parity without talking to each other.
 template <bool RES_ONLY>
 __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_base /* [MAX_BLOCKS][NSLOT] on the leader */,
-                             int rank, int csize, bool write_residuals) {
+                             int rank, int csize, bool write_residuals, unsigned& batch_counter) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const KfDev& kf = P.kf;
     const EvalConst& ec = sh.ec;
     const float inv_norm = (float)P.norms[1];
     const double loss_a = sh.loss_a;
     const int ne = kf.N / kf.B;
-    int buf = 0;
-    for (int b = rank; b < kf.B; b += csize, buf ^= 1) {
+    int bsel = 0;
+    for (int b = rank; b < kf.B; b += csize, bsel ^= 1) {
         const float* bc = ec.blk[b];
         const int start = b * ne;
         const int n = ne + ((b + 1 == kf.B) ? (kf.N - (b + 1) * ne) : 0);  // Tracker.cpp:178-190
@@ -295,61 +374,77 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
             }
             continue;
         }
-        float acc[NACC];
+        const int nb = (n + 31) >> 5;  // batches of this block
+        if (warp < N_PROD) {
+            // ---------------- producer ----------------
+            double s_acc = 0.0;
+            for (int j = warp; j < nb; j += N_PROD) {
+                const unsigned g = batch_counter + (unsigned)j;
+                const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
+                mbar_wait(&sh.empty_bar[slot], (fill & 1u) ^ 1u);
+                const int i = (j << 5) + lane;
+                float J[12], r = 0.f;
+                if (i < n) {
+                    eval_point<true>(kf, ec, bc, P.frame, inv_norm, start + i, J, r);
+                    if (write_residuals) {
+                        P.residuals[start + i] = r;
+                        if (P.jac_out) {
 #pragma unroll
-        for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-        double s_acc = 0.0;
-        for (int i = tid; i < n; i += TRK_THREADS) {
-            float J[12], r;
-            eval_point<true>(kf, ec, bc, P.frame, inv_norm, start + i, J, r);
-            if (write_residuals) {
-                P.residuals[start + i] = r;
-                if (P.jac_out) {
+                            for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * (start + i) + k] = J[k];
+                        }
+                    }
+                    s_acc += (double)r * (double)r;
+                } else {
 #pragma unroll
-                    for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * (start + i) + k] = J[k];
+                    for (int k = 0; k < 12; ++k) J[k] = 0.f;
+                }
+                float4* dst = reinterpret_cast<float4*>(&sh.ring[slot][lane][0]);
+                dst[0] = make_float4(J[0], J[1], J[2], J[3]);
+                dst[1] = make_float4(J[4], J[5], J[6], J[7]);
+                dst[2] = make_float4(J[8], J[9], J[10], J[11]);
+                dst[3] = make_float4(r, 0.f, 0.f, 0.f);
+                mbar_arrive(&sh.full_bar[slot]);  // 32 arrivals complete the phase
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
+            if (lane == 0) sh.warp_s[bsel][warp] = s_acc;
+        } else {
+            // ---------------- consumer ----------------
+            float acc[48];
+#pragma unroll
+            for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+            const bool first = (warp == N_PROD);
+            for (int j = 0; j < nb; ++j) {
+                const unsigned g = batch_counter + (unsigned)j;
+                const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
+                mbar_wait(&sh.full_bar[slot], fill & 1u);
+                if (first) ConsRows0::accumulate(sh.ring[slot], lane, acc);
+                else ConsRows1::accumulate(sh.ring[slot], lane, acc);
+                mbar_arrive(&sh.empty_bar[slot]);  // 64 arrivals (both consumer warps) free the slot
+            }
+            reduce48(acc, lane);
+            if (!(lane & 1)) {
+                const int base = reduce48_base(lane);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int e = base + i;
+                    if (first) { if (e < ConsRows0::count()) sh.blk_sum[bsel][ConsRows0::slot(e)] = (double)acc[i]; }
+                    else { if (e < ConsRows1::count()) sh.blk_sum[bsel][ConsRows1::slot(e)] = (double)acc[i]; }
                 }
             }
-            int e = 0;
-#pragma unroll
-            for (int a = 0; a < 12; ++a)
-#pragma unroll
-                for (int c2 = a; c2 < 12; ++c2) acc[e++] += J[a] * J[c2];
-#pragma unroll
-            for (int a = 0; a < 12; ++a) acc[78 + a] += J[a] * r;
-            s_acc += (double)r * (double)r;
         }
-        butterfly_step<48, 16>(acc, lane);
-        butterfly_step<24, 8>(acc, lane);
-        butterfly_step<12, 4>(acc, lane);
-        butterfly_step<6, 2>(acc, lane);
-        butterfly_step<3, 1>(acc, lane);
-        const int base = butterfly_base(lane);
-        sh.warp_part[buf][warp][base] = (double)acc[0];
-        sh.warp_part[buf][warp][base + 1] = (double)acc[1];
-        sh.warp_part[buf][warp][base + 2] = (double)acc[2];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
-        if (lane == 0) sh.warp_s[buf][warp] = s_acc;
-        __syncthreads();  // one barrier per block: scratch is double-buffered
+        batch_counter += (unsigned)nb;
+        __syncthreads();  // once per residual block; blk_sum / warp_s are double-buffered over blocks
         if (tid < NSLOT) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < TRK_WARPS; ++w) s += sh.warp_s[buf][w];
+            for (int w = 0; w < N_PROD; ++w) s += sh.warp_s[bsel][w];
+            double rho0, rho1;
+            loss_eval(P.loss_type, loss_a, s, &rho0, &rho1);
             double val;
-            if (tid < 90) {
-                double t = 0.0;
-#pragma unroll
-                for (int w = 0; w < TRK_WARPS; ++w) t += sh.warp_part[buf][w][tid];
-                double rho0, rho1;
-                loss_eval(P.loss_type, loss_a, s, &rho0, &rho1);
-                val = rho1 * t;
-            } else if (tid == 90) {
-                double rho0, rho1;
-                loss_eval(P.loss_type, loss_a, s, &rho0, &rho1);
-                val = 0.5 * rho0;
-            } else {
-                val = s;
-            }
+            if (tid < 90) val = rho1 * sh.blk_sum[bsel][tid];
+            else if (tid == 90) val = 0.5 * rho0;
+            else val = s;
             slot_base[b * NSLOT + tid] = val;
         }
     }
@@ -402,10 +497,15 @@ __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, const 
         for (int i = 0; i < 6; ++i) S += v[i] * c[i];
         const double iM = rsqrt(S);
         const double iM3 = iM / S;
-        ec.blk[lane][0] = (float)iM;
+        double vs = 0.0, cv = 0.0;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) ec.blk[lane][1 + i] = (float)(c[i] * iM3);
-        ec.blk[lane][7] = 0.f;
+        for (int i = 0; i < 6; ++i) { vs += v[i] * v[i]; cv += c[i] * v[i]; }
+        const double ivn = rsqrt(vs);
+        const double kappa = (iM - cv * iM3) / vs;
+        ec.blk[lane][0] = (float)iM;
+        ec.blk[lane][1] = (float)(iM * ivn);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ec.blk[lane][2 + i] = (float)((c[i] * iM3 + kappa * v[i]) * ivn);
     }
     __syncwarp();
     // replicate the used prefix of EvalConst (R,t,v + B block records) and cmd
@@ -630,6 +730,11 @@ __device__ __forceinline__ void load_problem(ProblemDesc& P, CtaShared& sh, cons
     for (int i = tid; i < (int)(sizeof(ProblemDesc) / sizeof(int)); i += TRK_THREADS) dst[i] = src[i];
     __syncthreads();
     if (tid == 0) sh.loss_a = P.state[13];
+    if (tid < N_SLOTS) {
+        mbar_init(&sh.full_bar[tid], 32);            // one producer warp fills a slot
+        mbar_init(&sh.empty_bar[tid], 32 * N_CONS);  // every consumer lane releases it
+    }
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (rank == 0) {
         for (int i = tid; i < 21 * P.kf.B; i += TRK_THREADS) (&sh.A[0][0])[i] = P.kf.A[i];
         if (tid < 13) sh.x_eval[tid] = P.state[tid];
@@ -637,16 +742,24 @@ __device__ __forceinline__ void load_problem(ProblemDesc& P, CtaShared& sh, cons
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemDesc* __restrict__ problems) {
+struct KernelSmem {
+    CtaShared sh;
+    ProblemDesc P;
+};
+
+__global__ void __launch_bounds__(TRK_THREADS, 2) track_lm_kernel(const ProblemDesc* __restrict__ problems) {
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
-    __shared__ CtaShared sh;
-    __shared__ ProblemDesc P;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KernelSmem& ks = *reinterpret_cast<KernelSmem*>(smem_raw);
+    CtaShared& sh = ks.sh;
+    ProblemDesc& P = ks.P;
     const int tid = threadIdx.x;
     load_problem(P, sh, problems, blockIdx.x / csize, rank);
     CtaShared* leader = cluster.map_shared_rank(&sh, 0);
     double* slot_base = &leader->slots[0][0];
+    unsigned batch_counter = 0;  // same in every thread of the CTA
 
     if (rank == 0 && tid < 32) {
         LmState& lm = sh.lm;
@@ -671,10 +784,10 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
         const int cmd = sh.ec.cmd;
         if (cmd == CMD_DONE) break;
         if (cmd == CMD_FINAL) {  // residual write-back at the accepted state; touches no remote memory
-            cta_evaluate<true>(P, sh, slot_base, rank, csize, true);
+            cta_evaluate<true>(P, sh, slot_base, rank, csize, true, batch_counter);
             break;
         }
-        cta_evaluate<false>(P, sh, slot_base, rank, csize, false);
+        cta_evaluate<false>(P, sh, slot_base, rank, csize, false, batch_counter);
 #ifdef EDS_TIMING
         unsigned long long tE = gtime();
 #endif
@@ -716,17 +829,20 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
 
 // parity/debug entry (edsgpu_tracker_evaluate): one full evaluation at P.state, residuals and
 // Jacobian rows written out, reduced normal equations returned.
-__global__ void __launch_bounds__(TRK_THREADS, 1) track_eval_kernel(const ProblemDesc* __restrict__ problems) {
+__global__ void __launch_bounds__(TRK_THREADS, 2) track_eval_kernel(const ProblemDesc* __restrict__ problems) {
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
-    __shared__ CtaShared sh;
-    __shared__ ProblemDesc P;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KernelSmem& ks = *reinterpret_cast<KernelSmem*>(smem_raw);
+    CtaShared& sh = ks.sh;
+    ProblemDesc& P = ks.P;
     load_problem(P, sh, problems, blockIdx.x / csize, rank);
     CtaShared* leader = cluster.map_shared_rank(&sh, 0);
     if (rank == 0 && threadIdx.x < 32) leader_publish(cluster, sh, sh.x_eval, CMD_EVAL, P.kf.B, csize);
     cluster.sync();
-    cta_evaluate<false>(P, sh, &leader->slots[0][0], rank, csize, true);
+    unsigned batch_counter = 0;
+    cta_evaluate<false>(P, sh, &leader->slots[0][0], rank, csize, true, batch_counter);
     cluster.sync();
     if (rank == 0 && threadIdx.x == 0 && P.eval_out) {
         double cost = 0.0;
@@ -921,8 +1037,13 @@ struct edsgpu_batch {
 namespace {
 
 int pick_cluster(const edsgpu_ctx* ctx, int count, int B) {
+    if (const char* e = getenv("EDSGPU_CLUSTER")) {  // tuning/debug override
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+    }
     int c = 1;
-    while (c * 2 <= MAX_CLUSTER && c * 2 <= B && (size_t)count * c * 2 <= (size_t)ctx->num_sms) c *= 2;
+    // two CTAs are resident per SM (<= 128 registers/thread, ~75 KB shared memory each)
+    while (c * 2 <= MAX_CLUSTER && c * 2 <= B && (size_t)count * c * 2 <= (size_t)2 * ctx->num_sms) c *= 2;
     return c;
 }
 
@@ -931,8 +1052,10 @@ edsgpu_status launch_cluster(edsgpu_ctx* ctx, K kernel, const ProblemDesc* desc_
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(count * csize);
     cfg.blockDim = dim3(TRK_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = sizeof(KernelSmem);
     cfg.stream = ctx->stream;
+    // per device, cheap: opt in to > 48 KB of dynamic shared memory
+    EDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KernelSmem)));
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = csize;
@@ -984,7 +1107,7 @@ edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const doub
     if (!ctx || !out) return EDSGPU_INVALID_ARGUMENT;
     EDS_REQUIRE(ctx, grad_xy && norm_xy && idp && weights, "keyframe_create: null array");
     EDS_REQUIRE(ctx, height > 0 && width > 0, "keyframe_create: bad image size");
-    EDS_REQUIRE(ctx, num_blocks >= 1 && num_blocks <= MAX_BLOCKS, "keyframe_create: num_blocks must be in [1,32]");
+    EDS_REQUIRE(ctx, num_blocks >= 1 && num_blocks <= MAX_BLOCKS, "keyframe_create: num_blocks must be in [1,16]");
     EDS_REQUIRE(ctx, num_points >= num_blocks, "keyframe_create: fewer points than residual blocks");
     DeviceGuard g(ctx->device);
     const size_t N = (size_t)num_points;
@@ -1039,7 +1162,7 @@ void edsgpu_keyframe_destroy(edsgpu_keyframe* kf) {
 
 edsgpu_status edsgpu_tracker_create(edsgpu_ctx* ctx, const edsgpu_tracker_config* config, double loss_param, edsgpu_tracker** out) {
     if (!ctx || !out || !config) return EDSGPU_INVALID_ARGUMENT;
-    EDS_REQUIRE(ctx, config->num_blocks >= 1 && config->num_blocks <= MAX_BLOCKS, "tracker_create: num_blocks must be in [1,32]");
+    EDS_REQUIRE(ctx, config->num_blocks >= 1 && config->num_blocks <= MAX_BLOCKS, "tracker_create: num_blocks must be in [1,16]");
     EDS_REQUIRE(ctx, config->loss_type >= 0 && config->loss_type <= 2, "tracker_create: unknown loss type");
     EDS_REQUIRE(ctx, config->loss_param_method >= 0 && config->loss_param_method <= 2, "tracker_create: unknown loss-parameter method");
     EDS_REQUIRE(ctx, config->max_iterations >= 0, "tracker_create: negative max_iterations");

@@ -290,7 +290,7 @@ def test_argument_validation(gpu_ctx, problems):
     with pytest.raises(edsgpu.EdsGpuError):
         edsgpu.KeyFrame(gpu_ctx, kf, 0)
     with pytest.raises(edsgpu.EdsGpuError):
-        edsgpu.KeyFrame(gpu_ctx, kf, 33)
+        edsgpu.KeyFrame(gpu_ctx, kf, 17)
     kfd = edsgpu.KeyFrame(gpu_ctx, kf, 4)
     tr = edsgpu.Tracker(gpu_ctx, num_blocks=8)
     fr = edsgpu.Frames(gpu_ctx, kf["H"], kf["W"], 1)
