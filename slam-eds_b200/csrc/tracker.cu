@@ -94,10 +94,20 @@ __device__ __forceinline__ void quat_to_rot(const double* q, double* R) {
 // (PhotometricError.hpp:32-54), Tracker.cpp:111-114,197-198.
 __device__ void state_plus(const double* x, const double* d, double* out) {
     for (int i = 0; i < 3; ++i) out[i] = x[i] + d[i];
-    const double nd = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
-    if (nd > 0.0) {
-        const double s = sin(nd) / nd;
-        const double ax = s * d[3], ay = s * d[4], az = s * d[5], aw = cos(nd);
+    const double n2 = d[3] * d[3] + d[4] * d[4] + d[5] * d[5];
+    if (n2 > 0.0) {
+        double s, c;  // s = sin(|d|)/|d|, c = cos(|d|)
+        if (n2 < 0.0625) {
+            // |d| < 0.25: Taylor series in n2, truncation error < 1e-18 (faster than sin/cos + sqrt + div
+            // on the serial LM path; agrees with libm to the last ulp or two)
+            s = 1.0 + n2 * (-1.0 / 6 + n2 * (1.0 / 120 + n2 * (-1.0 / 5040 + n2 * (1.0 / 362880 + n2 * (-1.0 / 39916800 + n2 * (1.0 / 6227020800.0))))));
+            c = 1.0 + n2 * (-0.5 + n2 * (1.0 / 24 + n2 * (-1.0 / 720 + n2 * (1.0 / 40320 + n2 * (-1.0 / 3628800 + n2 * (1.0 / 479001600.0 + n2 * (-1.0 / 87178291200.0)))))));
+        } else {
+            const double nd = sqrt(n2);
+            s = sin(nd) / nd;
+            c = cos(nd);
+        }
+        const double ax = s * d[3], ay = s * d[4], az = s * d[5], aw = c;
         const double bx = x[3], by = x[4], bz = x[5], bw = x[6];
         out[6] = aw * bw - ax * bx - ay * by - az * bz;
         out[3] = aw * bx + ax * bw + ay * bz - az * by;
@@ -108,7 +118,7 @@ __device__ void state_plus(const double* x, const double* d, double* out) {
     }
     double sum = 0.0;
     for (int i = 0; i < 6; ++i) { double s = x[7 + i] + d[6 + i]; sum += s * s; out[7 + i] = s; }
-    sum = 1.0 / sqrt(sum);
+    sum = rsqrt(sum);
     for (int i = 0; i < 6; ++i) out[7 + i] *= sum;
 }
 
@@ -471,18 +481,26 @@ __device__ __forceinline__ double warp_max(double v) {
 __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, const double* xe, int cmd, int B, int csize) {
     const int lane = threadIdx.x;
     EvalConst& ec = sh.ec;  // build locally, then replicate
+    // every lane computes the shared constants (no divergent serial section), lane 0 stores them
+    double R[9];
+    quat_to_rot(&xe[3], R);
+    double v[6], vs = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { v[k] = xe[7 + k]; vs += v[k] * v[k]; }
+    const double ivn = rsqrt(vs), ivs = ivn * ivn;
     if (lane == 0) {
-        quat_to_rot(&xe[3], ec.R);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ec.R[k] = R[k];
         ec.t[0] = xe[0]; ec.t[1] = xe[1]; ec.t[2] = xe[2];
-        double s = 0.0;
-        for (int k = 0; k < 6; ++k) { s += xe[7 + k] * xe[7 + k]; ec.vf[k] = (float)xe[7 + k]; }
-        ec.inv_vs = (float)(1.0 / s);
-        ec.inv_vn = (float)rsqrt(s);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ec.vf[k] = (float)v[k];
+        ec.inv_vs = (float)ivs;
+        ec.inv_vn = (float)ivn;
         ec.cmd = cmd;
     }
     if (lane < B && cmd != CMD_DONE) {
+        // S_b = 1e-3 + v^T A_b v (PhotometricError.hpp:132,148), c_b = A_b v
         const double* A = sh.A[lane];
-        const double* v = &xe[7];
         double c[6] = {0, 0, 0, 0, 0, 0};
         int k = 0;
 #pragma unroll
@@ -492,16 +510,12 @@ __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, const 
                 c[i] += A[k] * v[j];
                 if (j != i) c[j] += A[k] * v[i];
             }
-        double S = 1e-03;
+        double cv = 0.0;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) S += v[i] * c[i];
-        const double iM = rsqrt(S);
-        const double iM3 = iM / S;
-        double vs = 0.0, cv = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { vs += v[i] * v[i]; cv += c[i] * v[i]; }
-        const double ivn = rsqrt(vs);
-        const double kappa = (iM - cv * iM3) / vs;
+        for (int i = 0; i < 6; ++i) cv += v[i] * c[i];
+        const double iM = rsqrt(1e-03 + cv);
+        const double iM3 = iM * iM * iM;
+        const double kappa = (iM - cv * iM3) * ivs;
         ec.blk[lane][0] = (float)iM;
         ec.blk[lane][1] = (float)(iM * ivn);
 #pragma unroll
@@ -530,13 +544,22 @@ __device__ int lm_advance_warp(const ProblemDesc& P, CtaShared& sh) {
 #ifdef EDS_TIMING
     unsigned long long tt0 = gtime();
 #endif
-    // ordered sum over residual blocks: the result does not depend on the cluster size
+    // fixed pairwise tree over the residual blocks: deterministic and independent of the cluster size
     bool fin = true;
-    for (int e = lane; e < 91; e += 32) {
-        double s = 0.0;
-        for (int b = 0; b < B; ++b) s += sh.slots[b][e];
-        sh.sum[e] = s;
-        fin = fin && isfinite(s);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int e = lane + 32 * k;
+        if (e < 91) {
+            double v[MAX_BLOCKS];
+#pragma unroll
+            for (int b = 0; b < MAX_BLOCKS; ++b) v[b] = (b < B) ? sh.slots[b][e] : 0.0;
+#pragma unroll
+            for (int w = MAX_BLOCKS / 2; w > 0; w >>= 1)
+#pragma unroll
+                for (int b = 0; b < w; ++b) v[b] += v[b + w];
+            sh.sum[e] = v[0];
+            fin = fin && isfinite(v[0]);
+        }
     }
     fin = __all_sync(FULL, fin);
     __syncwarp();
