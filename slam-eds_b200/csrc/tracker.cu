@@ -35,7 +35,7 @@ constexpr int TRK_THREADS = 256;
 constexpr int TRK_WARPS = TRK_THREADS / 32;
 constexpr int NACC = 96;        // 78 (upper triangle of J^T J) + 12 (J^T r) + 6 padding
 constexpr int JLD = 20;         // floats per point row in shared memory (80 B: conflict-free 128-bit access)
-constexpr int N_PROD = 6;       // producer warps: per-point residual + Jacobian rows
+constexpr int N_PROD = 7;       // producer warps: per-point residual + Jacobian rows
 constexpr int N_CONS = TRK_WARPS - N_PROD;  // consumer warps: own the outer-product accumulators
 constexpr int N_SLOTS = 2 * N_PROD;         // ring of 32-point batches, two per producer warp
 constexpr int NSLOT = 92;       // 78 + 12 + cost + block squared norm
@@ -224,18 +224,23 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, 
     for (int k = 0; k < 6; ++k) m += g[k] * K.vf[k];
     // warp + projection in fp64 (PhotometricError.hpp:157-168): the pixel coordinate must not
     // carry fp32 rounding (1.5e-5 px at |u| ~ 256), SURVEY.md section 7.
-    const double ax = K.R[0] * kx + K.R[1] * ky + K.R[2] * kz;
-    const double ay = K.R[3] * kx + K.R[4] * ky + K.R[5] * kz;
-    const double az = K.R[6] * kx + K.R[7] * ky + K.R[8] * kz;
-    const double px = ax + K.t[0], py = ay + K.t[1], pz = az + K.t[2];
-    const double iz = 1.0 / pz;
-    const double u = kf.fx * (px * iz) + kf.cx;
-    const double v = kf.fy * (py * iz) + kf.cy;
-    const double fu = floor(u), fv = floor(v);
+#ifdef EDS_EXPERIMENT_FP32_GEOM
+    typedef float greal;
+#else
+    typedef double greal;
+#endif
+    const greal ax = (greal)K.R[0] * (greal)kx + (greal)K.R[1] * (greal)ky + (greal)K.R[2] * (greal)kz;
+    const greal ay = (greal)K.R[3] * (greal)kx + (greal)K.R[4] * (greal)ky + (greal)K.R[5] * (greal)kz;
+    const greal az = (greal)K.R[6] * (greal)kx + (greal)K.R[7] * (greal)ky + (greal)K.R[8] * (greal)kz;
+    const greal px = ax + (greal)K.t[0], py = ay + (greal)K.t[1], pz = az + (greal)K.t[2];
+    const greal iz = (greal)1.0 / pz;
+    const greal u = (greal)kf.fx * (px * iz) + (greal)kf.cx;
+    const greal v = (greal)kf.fy * (py * iz) + (greal)kf.cy;
+    const greal fu = floor(u), fv = floor(v);
     // The clamped Grid2D makes the interpolant constant more than 2 px outside the image: clamp the
     // integer cell (saturating conversion) and drop the fraction there; identical inside.
     const int W = kf.W, H = kf.H;
-    const int col_raw = __double2int_rd(u), row_raw = __double2int_rd(v);
+    const int col_raw = __double2int_rd((double)u), row_raw = __double2int_rd((double)v);
     const int col = max(-4, min(col_raw, W + 3)), row = max(-4, min(row_raw, H + 3));
     const float tc = (col == col_raw) ? (float)(u - fu) : 0.f;
     const float tr = (row == row_raw) ? (float)(v - fv) : 0.f;
@@ -249,7 +254,11 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, 
     for (int k = 0; k < 4; ++k) {
         const int rr = max(0, min(row - 1 + k, H - 1));
         const float* rp = frame + (size_t)rr * W;
+#ifdef EDS_EXP_NOTAPS
+        const float p0 = tc + (float)rr, p1 = tr, p2 = 1.f - tc, p3 = (float)c3 * 1e-3f + (float)(rp == nullptr);
+#else
         const float p0 = __ldg(rp + c0), p1 = __ldg(rp + c1), p2 = __ldg(rp + c2), p3 = __ldg(rp + c3);
+#endif
         const float fr = wc[0] * p0 + wc[1] * p1 + wc[2] * p2 + wc[3] * p3;
         f += wr[k] * fr;
         dfdr += dwr[k] * fr;
@@ -336,20 +345,18 @@ struct RowBlock {
             for (int c = a; c < 13; ++c) acc[e++] += v[a] * v[c];
     }
 };
-typedef RowBlock<0, 4> ConsRows0;   // 13+12+11+10 = 46 entries
-typedef RowBlock<4, 12> ConsRows1;  // 9+8+...+2   = 44 entries
+typedef RowBlock<0, 12> ConsRows;  // all 90 entries: one consumer warp per CTA keeps up with 7 producers
 
-// 48 per-lane partial sums -> warp totals; lane l (even) ends with entries base(l)+{0,1,2}
-__device__ __forceinline__ void reduce48(float* acc, unsigned lane) {
-    butterfly_step<24, 16>(acc, lane);
-    butterfly_step<12, 8>(acc, lane);
-    butterfly_step<6, 4>(acc, lane);
-    butterfly_step<3, 2>(acc, lane);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+// 96 per-lane partial sums -> warp totals; lane l ends with entries base(l)+{0,1,2}
+__device__ __forceinline__ void reduce96(float* acc, unsigned lane) {
+    butterfly_step<48, 16>(acc, lane);
+    butterfly_step<24, 8>(acc, lane);
+    butterfly_step<12, 4>(acc, lane);
+    butterfly_step<6, 2>(acc, lane);
+    butterfly_step<3, 1>(acc, lane);
 }
-__device__ __forceinline__ int reduce48_base(unsigned lane) {
-    return 24 * ((lane >> 4) & 1) + 12 * ((lane >> 3) & 1) + 6 * ((lane >> 2) & 1) + 3 * ((lane >> 1) & 1);
+__device__ __forceinline__ int reduce96_base(unsigned lane) {
+    return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
 }
 
 // One CTA evaluates the residual blocks dealt to it with the constants in sh.ec and stores, per
@@ -357,7 +364,7 @@ __device__ __forceinline__ int reduce48_base(unsigned lane) {
 //
 // Warp-specialised: producer warps sweep the points 32 at a time (residual + analytic Jacobian row
 // -> shared-memory ring slot, mbarrier "full"), consumer warps own the outer-product accumulators
-// (46 / 44 fp32 registers per lane) and drain the ring (mbarrier "empty").  No CTA-wide barrier inside
+// (90 fp32 registers per lane) and drain the ring (mbarrier "empty").  No CTA-wide barrier inside
 // the sweep and <= 128 registers per thread, so two CTAs share an SM and hide each other's stalls
 // (and the leader's serial LM step).  `batch_counter` numbers the batches of the whole kernel so that
 // both sides derive slot and phase parity without talking to each other.
@@ -420,27 +427,24 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
             if (lane == 0) sh.warp_s[bsel][warp] = s_acc;
         } else {
             // ---------------- consumer ----------------
-            float acc[48];
+            float acc[96];
 #pragma unroll
-            for (int i = 0; i < 48; ++i) acc[i] = 0.f;
-            const bool first = (warp == N_PROD);
+            for (int i = 0; i < 96; ++i) acc[i] = 0.f;
             for (int j = 0; j < nb; ++j) {
                 const unsigned g = batch_counter + (unsigned)j;
                 const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
                 mbar_wait(&sh.full_bar[slot], fill & 1u);
-                if (first) ConsRows0::accumulate(sh.ring[slot], lane, acc);
-                else ConsRows1::accumulate(sh.ring[slot], lane, acc);
-                mbar_arrive(&sh.empty_bar[slot]);  // 64 arrivals (both consumer warps) free the slot
+#ifndef EDS_EXP_NOACC
+                ConsRows::accumulate(sh.ring[slot], lane, acc);
+#endif
+                mbar_arrive(&sh.empty_bar[slot]);  // 32 arrivals free the slot
             }
-            reduce48(acc, lane);
-            if (!(lane & 1)) {
-                const int base = reduce48_base(lane);
+            reduce96(acc, lane);
+            const int base = reduce96_base(lane);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int e = base + i;
-                    if (first) { if (e < ConsRows0::count()) sh.blk_sum[bsel][ConsRows0::slot(e)] = (double)acc[i]; }
-                    else { if (e < ConsRows1::count()) sh.blk_sum[bsel][ConsRows1::slot(e)] = (double)acc[i]; }
-                }
+            for (int i = 0; i < 3; ++i) {
+                const int e = base + i;
+                if (e < 90) sh.blk_sum[bsel][ConsRows::slot(e)] = (double)acc[i];
             }
         }
         batch_counter += (unsigned)nb;
