@@ -163,21 +163,29 @@ struct EvalConst {
     int cmd;
 };
 
-struct CtaShared {
+// Per-problem state.  A cluster works on TWO problems in ping-pong (see track_lm_kernel): every CTA
+// holds the published constants of both, the leader CTA additionally the reduction slots and LM state.
+struct ProblemShared {
     EvalConst ec;
+    double loss_a;
+    // leader CTA only
+    double slots[MAX_BLOCKS][NSLOT];  // one slot per residual block, filled over DSMEM
+    double sum[NSLOT];
+    double A[MAX_BLOCKS][21];         // per-block model Gram matrices
+    double x_eval[13];
+    LmState lm;
+    ProblemDesc P;
+    int valid;
+};
+
+struct CtaShared {
+    ProblemShared prob[2];
     // ring of 32-point batches of rows [J(12) r pad], guarded by full/empty mbarriers
     alignas(16) float ring[N_SLOTS][32][JLD];
     alignas(8) unsigned long long full_bar[N_SLOTS];
     alignas(8) unsigned long long empty_bar[N_SLOTS];
     double blk_sum[2][NACC];          // reduced entries of the current residual block (double-buffered)
     double warp_s[2][TRK_WARPS];      // producers' sum of r^2
-    double loss_a;
-    // leader only
-    double slots[MAX_BLOCKS][NSLOT];  // one slot per residual block, filled over DSMEM
-    double sum[NSLOT];
-    double A[MAX_BLOCKS][21];         // per-block model Gram matrices
-    double x_eval[13];
-    LmState lm;
 };
 
 // (a,b) of packed upper-triangle entry e (row-major, a <= b < 12)
@@ -368,14 +376,36 @@ __device__ __forceinline__ int reduce96_base(unsigned lane) {
 // the sweep and <= 128 registers per thread, so two CTAs share an SM and hide each other's stalls
 // (and the leader's serial LM step).  `batch_counter` numbers the batches of the whole kernel so that
 // both sides derive slot and phase parity without talking to each other.
+// Evaluator roles of one CTA.  In the leader CTA (rank 0) warp 7 is the dedicated LM leader warp and
+// does not evaluate, so that CTA has six producers; every other CTA has seven.
+struct Roles {
+    int n_prod;      // producer warps of this CTA
+    int pidx;        // producer index of this warp, -1 if not a producer
+    bool consumer;   // warp 6
+    int n_eval_threads;  // threads taking part in the evaluation (named barrier 1)
+    int etid;        // evaluator thread index
+};
+__device__ __forceinline__ Roles make_roles(int rank) {
+    const int warp = threadIdx.x >> 5;
+    Roles r;
+    r.n_prod = (rank == 0) ? 6 : 7;
+    r.consumer = (warp == 6);
+    r.pidx = (warp < 6) ? warp : ((warp == 7 && rank != 0) ? 6 : -1);
+    r.n_eval_threads = (rank == 0) ? TRK_THREADS - 32 : TRK_THREADS;
+    r.etid = threadIdx.x;  // warps 0..6 (and 7 when it evaluates) keep their index
+    return r;
+}
+__device__ __forceinline__ void eval_barrier(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
 template <bool RES_ONLY>
-__device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_base /* [MAX_BLOCKS][NSLOT] on the leader */,
-                             int rank, int csize, bool write_residuals, unsigned& batch_counter) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base /* [MAX_BLOCKS][NSLOT] on the leader */,
+                             int rank, int csize, const Roles& role, bool write_residuals, unsigned& batch_counter) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const ProblemDesc& P = ps.P;
     const KfDev& kf = P.kf;
-    const EvalConst& ec = sh.ec;
+    const EvalConst& ec = ps.ec;
     const float inv_norm = (float)P.norms[1];
-    const double loss_a = sh.loss_a;
+    const double loss_a = ps.loss_a;
     const int ne = kf.N / kf.B;
     int bsel = 0;
     for (int b = rank; b < kf.B; b += csize, bsel ^= 1) {
@@ -384,7 +414,7 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
         const int n = ne + ((b + 1 == kf.B) ? (kf.N - (b + 1) * ne) : 0);  // Tracker.cpp:178-190
         if constexpr (RES_ONLY) {
             // residual write-back only (Tracker.cpp:223-230): no Jacobian, no reduction, no DSMEM traffic
-            for (int i = tid; i < n; i += TRK_THREADS) {
+            for (int i = role.etid; i < n; i += role.n_eval_threads) {
                 float r;
                 eval_point<false>(kf, ec, bc, P.frame, inv_norm, start + i, nullptr, r);
                 P.residuals[start + i] = r;
@@ -392,10 +422,10 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
             continue;
         }
         const int nb = (n + 31) >> 5;  // batches of this block
-        if (warp < N_PROD) {
+        if (role.pidx >= 0) {
             // ---------------- producer ----------------
             double s_acc = 0.0;
-            for (int j = warp; j < nb; j += N_PROD) {
+            for (int j = role.pidx; j < nb; j += role.n_prod) {
                 const unsigned g = batch_counter + (unsigned)j;
                 const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
                 mbar_wait(&sh.empty_bar[slot], (fill & 1u) ^ 1u);
@@ -424,8 +454,8 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
-            if (lane == 0) sh.warp_s[bsel][warp] = s_acc;
-        } else {
+            if (lane == 0) sh.warp_s[bsel][role.pidx] = s_acc;
+        } else if (role.consumer) {
             // ---------------- consumer ----------------
             float acc[96];
 #pragma unroll
@@ -434,9 +464,7 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
                 const unsigned g = batch_counter + (unsigned)j;
                 const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
                 mbar_wait(&sh.full_bar[slot], fill & 1u);
-#ifndef EDS_EXP_NOACC
                 ConsRows::accumulate(sh.ring[slot], lane, acc);
-#endif
                 mbar_arrive(&sh.empty_bar[slot]);  // 32 arrivals free the slot
             }
             reduce96(acc, lane);
@@ -448,11 +476,10 @@ __device__ void cta_evaluate(const ProblemDesc& P, CtaShared& sh, double* slot_b
             }
         }
         batch_counter += (unsigned)nb;
-        __syncthreads();  // once per residual block; blk_sum / warp_s are double-buffered over blocks
+        eval_barrier(role.n_eval_threads);  // once per residual block; blk_sum / warp_s are double-buffered over blocks
         if (tid < NSLOT) {
             double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < N_PROD; ++w) s += sh.warp_s[bsel][w];
+            for (int w = 0; w < role.n_prod; ++w) s += sh.warp_s[bsel][w];
             double rho0, rho1;
             loss_eval(P.loss_type, loss_a, s, &rho0, &rho1);
             double val;
@@ -482,9 +509,10 @@ __device__ __forceinline__ double warp_max(double v) {
 // Leader warp: publish the evaluation constants of point xe (13 doubles in leader smem) and the
 // command to every CTA of the cluster.  Lane b derives the per-block model normalisation
 // S_b = 1e-3 + v^T A_b v (PhotometricError.hpp:132,148) and c_b = A_b v.
-__device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, const double* xe, int cmd, int B, int csize) {
-    const int lane = threadIdx.x;
-    EvalConst& ec = sh.ec;  // build locally, then replicate
+__device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, int which, const double* xe, int cmd, int B, int csize) {
+    const int lane = threadIdx.x & 31;
+    ProblemShared& ps = sh.prob[which];
+    EvalConst& ec = ps.ec;  // build locally, then replicate
     // every lane computes the shared constants (no divergent serial section), lane 0 stores them
     double R[9];
     quat_to_rot(&xe[3], R);
@@ -504,7 +532,7 @@ __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, const 
     }
     if (lane < B && cmd != CMD_DONE) {
         // S_b = 1e-3 + v^T A_b v (PhotometricError.hpp:132,148), c_b = A_b v
-        const double* A = sh.A[lane];
+        const double* A = ps.A[lane];
         double c[6] = {0, 0, 0, 0, 0, 0};
         int k = 0;
 #pragma unroll
@@ -530,7 +558,7 @@ __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, const 
     const int nwords = (int)(offsetof(EvalConst, blk) / 4) + 8 * B;
     const int* src = reinterpret_cast<const int*>(&ec);
     for (int c = 1; c < csize; ++c) {
-        EvalConst* dst = &cluster.map_shared_rank(&sh, c)->ec;
+        EvalConst* dst = &cluster.map_shared_rank(&sh, c)->prob[which].ec;
         int* d = reinterpret_cast<int*>(dst);
         for (int i = lane; i < nwords; i += 32) d[i] = src[i];
         if (lane == 0) dst->cmd = cmd;
@@ -540,9 +568,10 @@ __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, const 
 // Leader warp (32 lanes, convergent): consume one evaluation and decide what to do next.
 // ceres TrustRegionMinimizer + LevenbergMarquardtStrategy semantics (options of
 // Tracker.cpp:117-143); returns the next command, lm.cand / lm.x hold the point to evaluate.
-__device__ int lm_advance_warp(const ProblemDesc& P, CtaShared& sh) {
+__device__ int lm_advance_warp(ProblemShared& sh) {
+    const ProblemDesc& P = sh.P;
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     LmState& lm = sh.lm;
     const int B = P.kf.B;
 #ifdef EDS_TIMING
@@ -750,138 +779,172 @@ __device__ int lm_advance_warp(const ProblemDesc& P, CtaShared& sh) {
     return ret;
 }
 
-__device__ __forceinline__ void load_problem(ProblemDesc& P, CtaShared& sh, const ProblemDesc* problems, int pid, int rank) {
+// all threads of the CTA: descriptor, loss parameter and (leader CTA) the Gram matrices + state of one problem
+__device__ __forceinline__ void load_problem(ProblemShared& ps, const ProblemDesc* problems, int pid, int count, int rank) {
     const int tid = threadIdx.x;
-    const int* src = reinterpret_cast<const int*>(&problems[pid]);
-    int* dst = reinterpret_cast<int*>(&P);
-    for (int i = tid; i < (int)(sizeof(ProblemDesc) / sizeof(int)); i += TRK_THREADS) dst[i] = src[i];
-    __syncthreads();
-    if (tid == 0) sh.loss_a = P.state[13];
-    if (tid < N_SLOTS) {
-        mbar_init(&sh.full_bar[tid], 32);            // one producer warp fills a slot
-        mbar_init(&sh.empty_bar[tid], 32 * N_CONS);  // every consumer lane releases it
+    const bool valid = pid < count;
+    if (tid == 0) ps.valid = valid;
+    if (valid) {
+        const int* src = reinterpret_cast<const int*>(&problems[pid]);
+        int* dst = reinterpret_cast<int*>(&ps.P);
+        for (int i = tid; i < (int)(sizeof(ProblemDesc) / sizeof(int)); i += TRK_THREADS) dst[i] = src[i];
     }
-    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (rank == 0) {
-        for (int i = tid; i < 21 * P.kf.B; i += TRK_THREADS) (&sh.A[0][0])[i] = P.kf.A[i];
-        if (tid < 13) sh.x_eval[tid] = P.state[tid];
+    __syncthreads();
+    if (valid) {
+        if (tid == 0) ps.loss_a = ps.P.state[13];
+        if (rank == 0) {
+            for (int i = tid; i < 21 * ps.P.kf.B; i += TRK_THREADS) (&ps.A[0][0])[i] = ps.P.kf.A[i];
+            if (tid < 13) ps.x_eval[tid] = ps.P.state[tid];
+        }
+    }
+    if (tid == 0) ps.ec.cmd = valid ? 0 : CMD_DONE;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void init_barriers(CtaShared& sh) {
+    if (threadIdx.x < N_SLOTS) {
+        mbar_init(&sh.full_bar[threadIdx.x], 32);   // one producer warp fills a slot
+        mbar_init(&sh.empty_bar[threadIdx.x], 32);  // the consumer warp releases it
     }
     __syncthreads();
 }
 
-struct KernelSmem {
-    CtaShared sh;
-    ProblemDesc P;
-};
+// leader warp: reset the LM state of a problem and publish its first evaluation point
+__device__ void leader_start(cg::cluster_group& cluster, CtaShared& sh, int which, int csize) {
+    ProblemShared& ps = sh.prob[which];
+    const int lane = threadIdx.x & 31;
+    LmState& lm = ps.lm;
+    if (lane < 13) lm.x[lane] = ps.x_eval[lane];
+    if (lane == 0) {
+        lm.radius = 1e4; lm.dec = 2.0; lm.reuse_diag = 0;
+        lm.iter = 0; lm.n_succ = 0; lm.n_unsucc = 0; lm.consec_invalid = 0; lm.n_eval = 0;
+        lm.termination = EDSGPU_TERM_NO_CONVERGENCE; lm.phase = PHASE_INIT;
+        lm.x_cost = 0.0; lm.initial_cost = 0.0; lm.mcc = 0.0; lm.gmax = 0.0; lm.x_norm = 0.0;
+    }
+    __syncwarp();
+    leader_publish(cluster, sh, which, lm.x, CMD_EVAL, ps.P.kf.B, csize);
+}
 
-__global__ void __launch_bounds__(TRK_THREADS, 2) track_lm_kernel(const ProblemDesc* __restrict__ problems) {
+// leader warp: consume the evaluation of a problem, advance its LM state, publish the next command
+__device__ void leader_step(cg::cluster_group& cluster, CtaShared& sh, int which, int csize) {
+    ProblemShared& ps = sh.prob[which];
+    const int lane = threadIdx.x & 31;
+    LmState& lm = ps.lm;
+    const ProblemDesc& P = ps.P;
+    const int next = lm_advance_warp(ps);
+    leader_publish(cluster, sh, which, (next == CMD_EVAL) ? lm.cand : lm.x, next, P.kf.B, csize);
+    if (next != CMD_EVAL && lane == 0) {
+        const bool usable = lm.termination != EDSGPU_TERM_FAILURE;
+        if (usable) for (int i = 0; i < 13; ++i) P.state[i] = lm.x[i];  // Tracker.cpp:217-220
+        edsgpu_tracker_info inf;
+        inf.iterations = lm.n_succ + lm.n_unsucc;
+        inf.successful_steps = lm.n_succ;
+        inf.unsuccessful_steps = lm.n_unsucc;
+        inf.termination = lm.termination;
+        inf.usable = usable ? 1 : 0;
+        inf.num_points = P.kf.N;
+        inf.evaluations = lm.n_eval;
+        inf.reserved = 0;
+        inf.initial_cost = lm.initial_cost;
+        inf.final_cost = lm.x_cost;
+        inf.final_radius = lm.radius;
+        *P.info = inf;
+    }
+}
+
+// One cluster = TWO tracking problems in ping-pong.  In every phase the evaluator warps of all CTAs
+// sweep the points of problem `cur` while the dedicated leader warp (rank 0, warp 7) consumes the
+// previous evaluation of the other problem, runs its LM step and publishes its next evaluation
+// point; one cluster.sync() per phase, then the roles of the two problems swap.  The serial LM step
+// is thereby hidden behind the other problem's sweep.  With a single problem the phases simply
+// alternate between sweep and LM step.
+__global__ void __launch_bounds__(TRK_THREADS, 2) track_lm_kernel(const ProblemDesc* __restrict__ problems, int count) {
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    KernelSmem& ks = *reinterpret_cast<KernelSmem*>(smem_raw);
-    CtaShared& sh = ks.sh;
-    ProblemDesc& P = ks.P;
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
     const int tid = threadIdx.x;
-    load_problem(P, sh, problems, blockIdx.x / csize, rank);
+    const int pair = blockIdx.x / csize;
+    load_problem(sh.prob[0], problems, 2 * pair, count, rank);
+    load_problem(sh.prob[1], problems, 2 * pair + 1, count, rank);
+    init_barriers(sh);
     CtaShared* leader = cluster.map_shared_rank(&sh, 0);
-    double* slot_base = &leader->slots[0][0];
-    unsigned batch_counter = 0;  // same in every thread of the CTA
+    const Roles role = make_roles(rank);
+    const bool is_leader_warp = (rank == 0) && ((tid >> 5) == 7);
+    unsigned batch_counter = 0;  // same in every evaluator thread of the CTA
 
-    if (rank == 0 && tid < 32) {
-        LmState& lm = sh.lm;
-        if (tid < 13) lm.x[tid] = sh.x_eval[tid];
-        if (tid == 0) {
-            lm.radius = 1e4; lm.dec = 2.0; lm.reuse_diag = 0;
-            lm.iter = 0; lm.n_succ = 0; lm.n_unsucc = 0; lm.consec_invalid = 0; lm.n_eval = 0;
-            lm.termination = EDSGPU_TERM_NO_CONVERGENCE; lm.phase = PHASE_INIT;
-            lm.x_cost = 0.0; lm.initial_cost = 0.0; lm.mcc = 0.0; lm.gmax = 0.0; lm.x_norm = 0.0;
-        }
-        __syncwarp();
-        leader_publish(cluster, sh, lm.x, CMD_EVAL, P.kf.B, csize);
-    }
+    // prologue: first evaluation point of problem 0
+    if (is_leader_warp) leader_start(cluster, sh, 0, csize);
+    cluster.sync();
+    // stage of each problem as seen by the leader warp: 0 = not started, 1 = evaluation in flight / to consume
+    int started1 = 0;
+    bool done0 = false, done1 = !sh.prob[1].valid;
+    int cur = 0;
     for (;;) {
-#ifdef EDS_TIMING
-        unsigned long long tA0 = gtime();
-#endif
-        cluster.sync();  // (A) command + evaluation constants published to every CTA
-#ifdef EDS_TIMING
-        unsigned long long tA = gtime();
-#endif
-        const int cmd = sh.ec.cmd;
-        if (cmd == CMD_DONE) break;
-        if (cmd == CMD_FINAL) {  // residual write-back at the accepted state; touches no remote memory
-            cta_evaluate<true>(P, sh, slot_base, rank, csize, true, batch_counter);
-            break;
-        }
-        cta_evaluate<false>(P, sh, slot_base, rank, csize, false, batch_counter);
-#ifdef EDS_TIMING
-        unsigned long long tE = gtime();
-#endif
-        cluster.sync();  // (B) every residual-block slot has landed in the leader's shared memory
-#ifdef EDS_TIMING
-        unsigned long long tB = gtime();
-        if (rank == 0 && tid == 0) { g_timing[0] += tA - tA0; g_timing[1] += tE - tA; g_timing[2] += tB - tE; g_timing[4] += 1; }
-#endif
-        if (rank == 0 && tid < 32) {
-            LmState& lm = sh.lm;
-            const int next = lm_advance_warp(P, sh);
-#ifdef EDS_TIMING
-            if (tid == 0) g_timing[3] += gtime() - tB;
-#endif
-            leader_publish(cluster, sh, (next == CMD_EVAL) ? lm.cand : lm.x, next, P.kf.B, csize);
-#ifdef EDS_TIMING
-            if (tid == 0) g_timing[5] += gtime() - tB;
-#endif
-            if (next != CMD_EVAL && tid == 0) {
-                const bool usable = lm.termination != EDSGPU_TERM_FAILURE;
-                if (usable) for (int i = 0; i < 13; ++i) P.state[i] = lm.x[i];  // Tracker.cpp:217-220
-                edsgpu_tracker_info inf;
-                inf.iterations = lm.n_succ + lm.n_unsucc;
-                inf.successful_steps = lm.n_succ;
-                inf.unsuccessful_steps = lm.n_unsucc;
-                inf.termination = lm.termination;
-                inf.usable = usable ? 1 : 0;
-                inf.num_points = P.kf.N;
-                inf.evaluations = lm.n_eval;
-                inf.reserved = 0;
-                inf.initial_cost = lm.initial_cost;
-                inf.final_cost = lm.x_cost;
-                inf.final_radius = lm.radius;
-                *P.info = inf;
+        const int other = cur ^ 1;
+        if (is_leader_warp) {
+            // the other problem: start it, or consume the evaluation swept in the previous phase
+            if (other == 1) {
+                if (!done1) {
+                    if (!started1) { leader_start(cluster, sh, 1, csize); started1 = 1; }
+                    else leader_step(cluster, sh, 1, csize);
+                }
+            } else if (!done0) {
+                leader_step(cluster, sh, 0, csize);
+            }
+        } else {
+            ProblemShared& ps = sh.prob[cur];
+            const bool cur_done = cur ? done1 : done0;
+            if (!cur_done) {
+                const int cmd = ps.ec.cmd;
+                if (cmd == CMD_EVAL) cta_evaluate<false>(ps, sh, &leader->prob[cur].slots[0][0], rank, csize, role, false, batch_counter);
+                else if (cmd == CMD_FINAL) cta_evaluate<true>(ps, sh, nullptr, rank, csize, role, true, batch_counter);
             }
         }
+        cluster.sync();  // slots of `cur` have landed in the leader CTA, constants/command of `other` in every CTA
+        // a problem is finished once its FINAL / DONE command has been acted upon (phase with cur == it)
+        {
+            const int cmd = sh.prob[cur].ec.cmd;
+            const bool fin = (cmd == CMD_FINAL || cmd == CMD_DONE);
+            if (cur == 0) done0 = done0 || fin; else done1 = done1 || fin;
+        }
+        if (done0 && done1) break;
+        cur = other;
     }
 }
 
 // parity/debug entry (edsgpu_tracker_evaluate): one full evaluation at P.state, residuals and
 // Jacobian rows written out, reduced normal equations returned.
-__global__ void __launch_bounds__(TRK_THREADS, 2) track_eval_kernel(const ProblemDesc* __restrict__ problems) {
+__global__ void __launch_bounds__(TRK_THREADS, 2) track_eval_kernel(const ProblemDesc* __restrict__ problems, int count) {
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    KernelSmem& ks = *reinterpret_cast<KernelSmem*>(smem_raw);
-    CtaShared& sh = ks.sh;
-    ProblemDesc& P = ks.P;
-    load_problem(P, sh, problems, blockIdx.x / csize, rank);
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
+    ProblemShared& ps = sh.prob[0];
+    load_problem(ps, problems, blockIdx.x / csize, count, rank);
+    init_barriers(sh);
     CtaShared* leader = cluster.map_shared_rank(&sh, 0);
-    if (rank == 0 && threadIdx.x < 32) leader_publish(cluster, sh, sh.x_eval, CMD_EVAL, P.kf.B, csize);
+    const Roles role = make_roles(rank);
+    const bool is_leader_warp = (rank == 0) && ((threadIdx.x >> 5) == 7);
+    if (is_leader_warp) leader_publish(cluster, sh, 0, ps.x_eval, CMD_EVAL, ps.P.kf.B, csize);
     cluster.sync();
     unsigned batch_counter = 0;
-    cta_evaluate<false>(P, sh, &leader->slots[0][0], rank, csize, true, batch_counter);
+    if (!is_leader_warp) cta_evaluate<false>(ps, sh, &leader->prob[0].slots[0][0], rank, csize, role, true, batch_counter);
     cluster.sync();
+    const ProblemDesc& P = ps.P;
     if (rank == 0 && threadIdx.x == 0 && P.eval_out) {
         double cost = 0.0;
-        for (int b = 0; b < P.kf.B; ++b) cost += sh.slots[b][90];
+        for (int b = 0; b < P.kf.B; ++b) cost += ps.slots[b][90];
         P.eval_out[0] = cost;
         for (int a = 0; a < 12; ++a) {
             double gs = 0.0;
-            for (int b = 0; b < P.kf.B; ++b) gs += sh.slots[b][78 + a];
+            for (int b = 0; b < P.kf.B; ++b) gs += ps.slots[b][78 + a];
             P.eval_out[1 + 144 + a] = gs;
             for (int c2 = a; c2 < 12; ++c2) {
                 double h = 0.0;
-                for (int b = 0; b < P.kf.B; ++b) h += sh.slots[b][tri_index(a, c2)];
+                for (int b = 0; b < P.kf.B; ++b) h += ps.slots[b][tri_index(a, c2)];
                 P.eval_out[1 + 12 * a + c2] = h;
                 P.eval_out[1 + 12 * c2 + a] = h;
             }
@@ -1075,14 +1138,14 @@ int pick_cluster(const edsgpu_ctx* ctx, int count, int B) {
 }
 
 template <typename K>
-edsgpu_status launch_cluster(edsgpu_ctx* ctx, K kernel, const ProblemDesc* desc_dev, int count, int csize) {
+edsgpu_status launch_cluster(edsgpu_ctx* ctx, K kernel, const ProblemDesc* desc_dev, int count, int nclusters, int csize) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(count * csize);
+    cfg.gridDim = dim3(nclusters * csize);
     cfg.blockDim = dim3(TRK_THREADS);
-    cfg.dynamicSmemBytes = sizeof(KernelSmem);
+    cfg.dynamicSmemBytes = sizeof(CtaShared);
     cfg.stream = ctx->stream;
     // per device, cheap: opt in to > 48 KB of dynamic shared memory
-    EDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KernelSmem)));
+    EDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = csize;
@@ -1090,7 +1153,7 @@ edsgpu_status launch_cluster(edsgpu_ctx* ctx, K kernel, const ProblemDesc* desc_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    EDS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, desc_dev));
+    EDS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, desc_dev, count));
     ctx->launches++;
     return EDSGPU_OK;
 }
@@ -1285,7 +1348,7 @@ edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* tracke
     edsgpu_batch* b = new edsgpu_batch();
     b->ctx = ctx;
     b->count = count;
-    b->csize = pick_cluster(ctx, count, B);
+    b->csize = pick_cluster(ctx, (count + 1) / 2, B);  // one cluster per PAIR of problems
     b->trackers.assign(trackers, trackers + count);
     std::vector<ProblemDesc> hd(count);
     for (int i = 0; i < count; ++i) hd[i] = make_desc(trackers[i], keyframes[i], frames, first_slot + i);
@@ -1309,7 +1372,7 @@ edsgpu_status edsgpu_batch_optimize(edsgpu_batch* b) {
     if (!b) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = b->ctx;
     DeviceGuard g(ctx->device);
-    edsgpu_status st = launch_cluster(ctx, track_lm_kernel, (const ProblemDesc*)b->desc, b->count, b->csize);
+    edsgpu_status st = launch_cluster(ctx, track_lm_kernel, (const ProblemDesc*)b->desc, b->count, (b->count + 1) / 2, b->csize);
     if (st != EDSGPU_OK) return st;
     mad_kernel<<<b->count, MAD_THREADS, 0, ctx->stream>>>((const ProblemDesc*)b->desc);
     ctx->launches++;
@@ -1426,7 +1489,7 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_desc, hd, sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
     EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_state, hstate, 14 * 8, cudaMemcpyHostToDevice, ctx->stream));
     const int csize = pick_cluster(ctx, 1, kf->dev.B);
-    st = launch_cluster(ctx, track_eval_kernel, (const ProblemDesc*)(ds + o_desc), 1, csize);
+    st = launch_cluster(ctx, track_eval_kernel, (const ProblemDesc*)(ds + o_desc), 1, 1, csize);
     if (st != EDSGPU_OK) return st;
     double* hev = (double*)(hp + sizeof(ProblemDesc) + 14 * 8);
     EDS_CUDA(ctx, cudaMemcpyAsync(hev, ds + o_eval, 157 * 8, cudaMemcpyDeviceToHost, ctx->stream));
