@@ -33,6 +33,7 @@ constexpr int O_RES = 0, O_JPDXI0 = 8, O_JPDXI1 = 14, O_JPDC0 = 20, O_JPDC1 = 24
               O_JAB0 = 48, O_JAB1 = 56, O_JIDX2 = 64, O_JABJIDX = 68, O_JAB2 = 72;
 constexpr int CPARS = 4;
 constexpr int TOP_THREADS = 256, TOP_TILE = 512, NACC = 96;
+constexpr int TOP_STAGE = 512;  // records staged in shared memory per round (512 x 304 B = 152 KB)
 constexpr int MAXF = 8;
 constexpr int SC_THREADS = 256, SC_CHUNK = 64, SC_BATCH = 32, SC_LD = 72;  // 8*MAXF + 5 padded to 72
 
@@ -80,15 +81,52 @@ __global__ void ba_jpjd_kernel(const float* __restrict__ recs, int R, float* __r
     o[1] = make_float4(out[4], out[5], out[6], out[7]);
 }
 
+// ---- TMA bulk-copy + mbarrier helpers -------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// one 304-byte record: global -> shared through the TMA unit (cp.async.bulk, 16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void tma_load_record(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // AccumulatedTopHessianSSE::addPoint<MODE> (AccumulatedTopHessian.cpp:39-159) over one single-key tile.
 // Accumulator order (AccumulatorApprox, MatrixAccumulators.h:595-651): 55 upper-triangle entries of the
 // 10x10 [C(4) xi(6)] block, 30 of the 10x3 top-right block [a b r], 6 of the 3x3 bottom-right block.
+//
+// The records a tile needs are gathered (perm) 304-byte PODs.  Index and flag loads are hoisted, then
+// every thread issues one TMA bulk copy per record it will use into a shared-memory stage (up to
+// TOP_STAGE records, ~152 KB in flight per SM) and all threads wait on one mbarrier: the gather runs
+// at memory speed instead of one dependent round trip per record.  Shared reads are 128-bit with a
+// 304-byte lane stride (conflict-free).
+constexpr int TOP_KMAX = TOP_STAGE / TOP_THREADS;  // records per thread per stage
+
 template <int MODE>
 __global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(BaDev W) {
-    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int key = W.tile_key[tile], start = W.tile_start[tile], count = W.tile_count[tile];
+    extern __shared__ __align__(16) unsigned char top_smem[];
+    float* stage = reinterpret_cast<float*>(top_smem);  // [TOP_STAGE][REC]
+    __shared__ __align__(8) unsigned long long bar;
     __shared__ double warp_part[TOP_THREADS / 32][NACC];
     __shared__ int warp_n[TOP_THREADS / 32];
+    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int key = W.tile_key[tile], start = W.tile_start[tile], count = W.tile_count[tile];
+    if (tid == 0) mbar_init(&bar, TOP_THREADS);
     float dp[8], dc[4];
     if (MODE == 1) {
 #pragma unroll
@@ -100,93 +138,117 @@ __global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(BaDev W) {
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
     int nres = 0;
-    for (int i = tid; i < count; i += TOP_THREADS) {
-        const int r = W.perm[start + i];
-        const unsigned fl = W.flags[r];
-        const bool active = fl & 1u, lin = fl & 2u;
-        bool use;
-        if (MODE == 0) use = active && !lin;        // :55-58
-        else if (MODE == 1) use = active && lin;    // :59-62
-        else use = active;                          // :63-67
-        float pt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (use) {
-            const float4* rec4 = reinterpret_cast<const float4*>(W.recs + (size_t)REC * r);
-            float J[REC];
+    __syncthreads();  // barrier initialised
+    unsigned parity = 0;
+    for (int s0 = 0; s0 < count; s0 += TOP_STAGE, parity ^= 1u) {
+        // hoisted, independent index / flag loads of this thread's records in the stage
+        int rr[TOP_KMAX];
+        bool use[TOP_KMAX];
 #pragma unroll
-            for (int k = 0; k < REC / 4; ++k) {
-                const float4 v = __ldg(rec4 + k);
-                J[4 * k] = v.x; J[4 * k + 1] = v.y; J[4 * k + 2] = v.z; J[4 * k + 3] = v.w;
-            }
-            float res[8];
-            if (MODE == 0) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) res[k] = J[O_RES + k];
-            } else {
-                const float4* rz = reinterpret_cast<const float4*>(W.res_toZero + (size_t)8 * r);
-                const float4 a = __ldg(rz), b = __ldg(rz + 1);
-                res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w; res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
-                if (MODE == 1) {  // :81-99: rtz + [JI*Jp Ja]*delta
-                    const float dd = W.deltaF[W.point_of_res[r]];
-                    float jx = 0.f, jy = 0.f, cxs = 0.f, cys = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) { jx += J[O_JPDXI0 + k] * dp[k]; jy += J[O_JPDXI1 + k] * dp[k]; }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { cxs += J[O_JPDC0 + k] * dc[k]; cys += J[O_JPDC1 + k] * dc[k]; }
-                    jx = jx + cxs + J[O_JPDD] * dd;
-                    jy = jy + cys + J[O_JPDD + 1] * dd;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        res[k] = res[k] + J[O_JIDX0 + k] * jx + J[O_JIDX1 + k] * jy + J[O_JAB0 + k] * dp[6] + J[O_JAB1 + k] * dp[7];
-                }
-            }
-            // :102-112
-            float JIr0 = 0.f, JIr1 = 0.f, Jabr0 = 0.f, Jabr1 = 0.f, rr = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                JIr0 += res[k] * J[O_JIDX0 + k];
-                JIr1 += res[k] * J[O_JIDX1 + k];
-                Jabr0 += res[k] * J[O_JAB0 + k];
-                Jabr1 += res[k] * J[O_JAB1 + k];
-                rr += res[k] * res[k];
-            }
-            // x = [Jpdc[0] Jpdxi[0]], y = [Jpdc[1] Jpdxi[1]]  (:115-129)
-            float x[10], y[10];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { x[k] = J[O_JPDC0 + k]; y[k] = J[O_JPDC1 + k]; }
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { x[4 + k] = J[O_JPDXI0 + k]; y[4 + k] = J[O_JPDXI1 + k]; }
-            const float a = J[O_JIDX2], b = J[O_JIDX2 + 2], c = J[O_JIDX2 + 3];  // (0,0) (0,1) (1,1), column-major
-            // AccumulatorApprox::update: a x x^T + c y y^T + b (x y^T + y x^T) = x (a x + b y)^T + y (b x + c y)^T
-            float px[10], py[10];
-#pragma unroll
-            for (int k = 0; k < 10; ++k) { px[k] = a * x[k] + b * y[k]; py[k] = b * x[k] + c * y[k]; }
-            int e = 0;
-#pragma unroll
-            for (int p = 0; p < 10; ++p)
-#pragma unroll
-                for (int q = p; q < 10; ++q) acc[e++] += x[p] * px[q] + y[p] * py[q];
-            // updateTopRight: TR00,TR10 = JabJIdx(0,0),(0,1); TR01,TR11 = JabJIdx(1,0),(1,1); TR02,TR12 = JI_r
-            const float t00 = J[O_JABJIDX], t10 = J[O_JABJIDX + 2], t01 = J[O_JABJIDX + 1], t11 = J[O_JABJIDX + 3];
-#pragma unroll
-            for (int p = 0; p < 10; ++p) {
-                acc[55 + 3 * p] += x[p] * t00 + y[p] * t10;
-                acc[55 + 3 * p + 1] += x[p] * t01 + y[p] * t11;
-                acc[55 + 3 * p + 2] += x[p] * JIr0 + y[p] * JIr1;
-            }
-            // updateBotRight
-            acc[85] += J[O_JAB2]; acc[86] += J[O_JAB2 + 2]; acc[87] += Jabr0;
-            acc[88] += J[O_JAB2 + 3]; acc[89] += Jabr1; acc[90] += rr;
-            // :132-135
-            const float d0 = J[O_JPDD], d1 = J[O_JPDD + 1];
-            const float q0 = a * d0 + b * d1, q1 = b * d0 + c * d1;
-            pt[0] = JIr0 * d0 + JIr1 * d1;
-            pt[1] = q0 * d0 + q1 * d1;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) pt[2 + k] = J[O_JPDC0 + k] * q0 + J[O_JPDC1 + k] * q1;
-            nres++;
+        for (int k = 0; k < TOP_KMAX; ++k) {
+            const int i = s0 + tid + k * TOP_THREADS;
+            rr[k] = (i < count) ? W.perm[start + i] : -1;
         }
-        float2* o = reinterpret_cast<float2*>(W.res_pt + (size_t)6 * r);
-        o[0] = make_float2(pt[0], pt[1]); o[1] = make_float2(pt[2], pt[3]); o[2] = make_float2(pt[4], pt[5]);
+        unsigned bytes = 0;
+#pragma unroll
+        for (int k = 0; k < TOP_KMAX; ++k) {
+            const unsigned fl = (rr[k] >= 0) ? W.flags[rr[k]] : 0u;
+            const bool active = fl & 1u, lin = fl & 2u;
+            if (MODE == 0) use[k] = active && !lin;        // :55-58
+            else if (MODE == 1) use[k] = active && lin;    // :59-62
+            else use[k] = active;                          // :63-67
+            if (use[k]) bytes += 4u * REC;
+        }
+        mbar_arrive_expect_tx(&bar, bytes);
+#pragma unroll
+        for (int k = 0; k < TOP_KMAX; ++k)
+            if (use[k]) tma_load_record(stage + (size_t)REC * (tid + k * TOP_THREADS), W.recs + (size_t)REC * rr[k], 4u * REC, &bar);
+        mbar_wait(&bar, parity);
+#pragma unroll 1
+        for (int k = 0; k < TOP_KMAX; ++k) {
+            const int r = rr[k];
+            if (r < 0) continue;
+            float pt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (use[k]) {
+                const float4* rec4 = reinterpret_cast<const float4*>(stage + (size_t)REC * (tid + k * TOP_THREADS));
+                float J[REC];
+#pragma unroll
+                for (int q = 0; q < REC / 4; ++q) {
+                    const float4 v = rec4[q];
+                    J[4 * q] = v.x; J[4 * q + 1] = v.y; J[4 * q + 2] = v.z; J[4 * q + 3] = v.w;
+                }
+                float res[8];
+                if (MODE == 0) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) res[q] = J[O_RES + q];
+                } else {
+                    const float4* rz = reinterpret_cast<const float4*>(W.res_toZero + (size_t)8 * r);
+                    const float4 a = __ldg(rz), b = __ldg(rz + 1);
+                    res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w; res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
+                    if (MODE == 1) {  // :81-99: rtz + [JI*Jp Ja]*delta
+                        const float dd = W.deltaF[W.point_of_res[r]];
+                        float jx = 0.f, jy = 0.f, cxs = 0.f, cys = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) { jx += J[O_JPDXI0 + q] * dp[q]; jy += J[O_JPDXI1 + q] * dp[q]; }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { cxs += J[O_JPDC0 + q] * dc[q]; cys += J[O_JPDC1 + q] * dc[q]; }
+                        jx = jx + cxs + J[O_JPDD] * dd;
+                        jy = jy + cys + J[O_JPDD + 1] * dd;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            res[q] = res[q] + J[O_JIDX0 + q] * jx + J[O_JIDX1 + q] * jy + J[O_JAB0 + q] * dp[6] + J[O_JAB1 + q] * dp[7];
+                    }
+                }
+                // :102-112
+                float JIr0 = 0.f, JIr1 = 0.f, Jabr0 = 0.f, Jabr1 = 0.f, rsq = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    JIr0 += res[q] * J[O_JIDX0 + q];
+                    JIr1 += res[q] * J[O_JIDX1 + q];
+                    Jabr0 += res[q] * J[O_JAB0 + q];
+                    Jabr1 += res[q] * J[O_JAB1 + q];
+                    rsq += res[q] * res[q];
+                }
+                // x = [Jpdc[0] Jpdxi[0]], y = [Jpdc[1] Jpdxi[1]]  (:115-129)
+                float x[10], y[10];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { x[q] = J[O_JPDC0 + q]; y[q] = J[O_JPDC1 + q]; }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { x[4 + q] = J[O_JPDXI0 + q]; y[4 + q] = J[O_JPDXI1 + q]; }
+                const float a = J[O_JIDX2], b = J[O_JIDX2 + 2], c = J[O_JIDX2 + 3];  // (0,0) (0,1) (1,1), column-major
+                // AccumulatorApprox::update: a x x^T + c y y^T + b (x y^T + y x^T) = x (a x + b y)^T + y (b x + c y)^T
+                float px[10], py[10];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) { px[q] = a * x[q] + b * y[q]; py[q] = b * x[q] + c * y[q]; }
+                int e = 0;
+#pragma unroll
+                for (int p = 0; p < 10; ++p)
+#pragma unroll
+                    for (int q = p; q < 10; ++q) acc[e++] += x[p] * px[q] + y[p] * py[q];
+                // updateTopRight: TR00,TR10 = JabJIdx(0,0),(0,1); TR01,TR11 = JabJIdx(1,0),(1,1); TR02,TR12 = JI_r
+                const float t00 = J[O_JABJIDX], t10 = J[O_JABJIDX + 2], t01 = J[O_JABJIDX + 1], t11 = J[O_JABJIDX + 3];
+#pragma unroll
+                for (int p = 0; p < 10; ++p) {
+                    acc[55 + 3 * p] += x[p] * t00 + y[p] * t10;
+                    acc[55 + 3 * p + 1] += x[p] * t01 + y[p] * t11;
+                    acc[55 + 3 * p + 2] += x[p] * JIr0 + y[p] * JIr1;
+                }
+                // updateBotRight
+                acc[85] += J[O_JAB2]; acc[86] += J[O_JAB2 + 2]; acc[87] += Jabr0;
+                acc[88] += J[O_JAB2 + 3]; acc[89] += Jabr1; acc[90] += rsq;
+                // :132-135
+                const float d0 = J[O_JPDD], d1 = J[O_JPDD + 1];
+                const float q0 = a * d0 + b * d1, q1 = b * d0 + c * d1;
+                pt[0] = JIr0 * d0 + JIr1 * d1;
+                pt[1] = q0 * d0 + q1 * d1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pt[2 + q] = J[O_JPDC0 + q] * q0 + J[O_JPDC1 + q] * q1;
+                nres++;
+            }
+            float2* o = reinterpret_cast<float2*>(W.res_pt + (size_t)6 * r);
+            o[0] = make_float2(pt[0], pt[1]); o[1] = make_float2(pt[2], pt[3]); o[2] = make_float2(pt[4], pt[5]);
+        }
+        if (s0 + TOP_STAGE < count) __syncthreads();  // the stage is overwritten by the next round
     }
     butterfly_step<48, 16>(acc, lane);
     butterfly_step<24, 8>(acc, lane);
@@ -734,9 +796,17 @@ edsgpu_status edsgpu_ba_top_accumulate(edsgpu_ba* w, int mode, double* acc_out, 
     DeviceGuard g(ctx->device);
     const int slot = mode == 0 ? 0 : 1;
     const BaDev d = ba_dev(w);
-    if (mode == 0) ba_top_kernel<0><<<w->num_tiles, TOP_THREADS, 0, ctx->stream>>>(d);
-    else if (mode == 1) ba_top_kernel<1><<<w->num_tiles, TOP_THREADS, 0, ctx->stream>>>(d);
-    else ba_top_kernel<2><<<w->num_tiles, TOP_THREADS, 0, ctx->stream>>>(d);
+    const size_t stage_bytes = (size_t)TOP_STAGE * REC * sizeof(float);
+    if (mode == 0) {
+        EDS_CUDA(ctx, cudaFuncSetAttribute(ba_top_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+        ba_top_kernel<0><<<w->num_tiles, TOP_THREADS, stage_bytes, ctx->stream>>>(d);
+    } else if (mode == 1) {
+        EDS_CUDA(ctx, cudaFuncSetAttribute(ba_top_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+        ba_top_kernel<1><<<w->num_tiles, TOP_THREADS, stage_bytes, ctx->stream>>>(d);
+    } else {
+        EDS_CUDA(ctx, cudaFuncSetAttribute(ba_top_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+        ba_top_kernel<2><<<w->num_tiles, TOP_THREADS, stage_bytes, ctx->stream>>>(d);
+    }
     EDS_CUDA(ctx, cudaGetLastError());
     ba_top_finalize_kernel<<<w->F * w->F, 96, 0, ctx->stream>>>(d, w->acc[slot], w->num[slot]);
     ba_point_sum_kernel<<<(w->P + 255) / 256, 256, 0, ctx->stream>>>(w->res_pt, w->res_begin, w->P, w->Hdd[slot], w->bd[slot], w->Hcd[slot]);
