@@ -184,8 +184,6 @@ struct CtaShared {
     alignas(16) float ring[N_SLOTS][32][JLD];
     alignas(8) unsigned long long full_bar[N_SLOTS];
     alignas(8) unsigned long long empty_bar[N_SLOTS];
-    double blk_sum[2][NACC];          // reduced entries of the current residual block (double-buffered)
-    double warp_s[2][TRK_WARPS];      // producers' sum of r^2
 };
 
 // (a,b) of packed upper-triangle entry e (row-major, a <= b < 12)
@@ -338,7 +336,7 @@ struct RowBlock {
         const int c = a + i;
         return (c < 12) ? tri_index(a, c) : 78 + a;
     }
-    static __device__ __forceinline__ void accumulate(const float (*rows)[JLD], int lane, float* acc) {
+    static __device__ __forceinline__ float accumulate(const float (*rows)[JLD], int lane, float* acc) {
         const float4* row = reinterpret_cast<const float4*>(&rows[lane][0]);
         float v[16];
 #pragma unroll
@@ -351,6 +349,7 @@ struct RowBlock {
         for (int a = R0; a < R1; ++a)
 #pragma unroll
             for (int c = a; c < 13; ++c) acc[e++] += v[a] * v[c];
+        return v[12];
     }
 };
 typedef RowBlock<0, 12> ConsRows;  // all 90 entries: one consumer warp per CTA keeps up with 7 producers
@@ -382,7 +381,7 @@ struct Roles {
     int n_prod;      // producer warps of this CTA
     int pidx;        // producer index of this warp, -1 if not a producer
     bool consumer;   // warp 6
-    int n_eval_threads;  // threads taking part in the evaluation (named barrier 1)
+    int n_eval_threads;  // threads taking part in the evaluation
     int etid;        // evaluator thread index
 };
 __device__ __forceinline__ Roles make_roles(int rank) {
@@ -407,8 +406,7 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
     const float inv_norm = (float)P.norms[1];
     const double loss_a = ps.loss_a;
     const int ne = kf.N / kf.B;
-    int bsel = 0;
-    for (int b = rank; b < kf.B; b += csize, bsel ^= 1) {
+    for (int b = rank; b < kf.B; b += csize) {
         const float* bc = ec.blk[b];
         const int start = b * ne;
         const int n = ne + ((b + 1 == kf.B) ? (kf.N - (b + 1) * ne) : 0);  // Tracker.cpp:178-190
@@ -424,7 +422,6 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
         const int nb = (n + 31) >> 5;  // batches of this block
         if (role.pidx >= 0) {
             // ---------------- producer ----------------
-            double s_acc = 0.0;
             for (int j = role.pidx; j < nb; j += role.n_prod) {
                 const unsigned g = batch_counter + (unsigned)j;
                 const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
@@ -440,7 +437,6 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                             for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * (start + i) + k] = J[k];
                         }
                     }
-                    s_acc += (double)r * (double)r;
                 } else {
 #pragma unroll
                     for (int k = 0; k < 12; ++k) J[k] = 0.f;
@@ -452,42 +448,35 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                 dst[3] = make_float4(r, 0.f, 0.f, 0.f);
                 mbar_arrive(&sh.full_bar[slot]);  // 32 arrivals complete the phase
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
-            if (lane == 0) sh.warp_s[bsel][role.pidx] = s_acc;
         } else if (role.consumer) {
-            // ---------------- consumer ----------------
+            // ---------------- consumer: owns the block's sums, applies the loss, publishes the slot ----------
             float acc[96];
 #pragma unroll
             for (int i = 0; i < 96; ++i) acc[i] = 0.f;
+            double s_acc = 0.0;  // sum of r^2 in fp64 (the cost decides accept / reject and the tolerances)
             for (int j = 0; j < nb; ++j) {
                 const unsigned g = batch_counter + (unsigned)j;
                 const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
                 mbar_wait(&sh.full_bar[slot], fill & 1u);
-                ConsRows::accumulate(sh.ring[slot], lane, acc);
+                const float rr = ConsRows::accumulate(sh.ring[slot], lane, acc);
                 mbar_arrive(&sh.empty_bar[slot]);  // 32 arrivals free the slot
+                s_acc += (double)rr * (double)rr;
             }
             reduce96(acc, lane);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
+            double rho0, rho1;
+            loss_eval(P.loss_type, loss_a, s_acc, &rho0, &rho1);
             const int base = reduce96_base(lane);
+            double* dst = slot_base + b * NSLOT;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const int e = base + i;
-                if (e < 90) sh.blk_sum[bsel][ConsRows::slot(e)] = (double)acc[i];
+                if (e < 90) dst[ConsRows::slot(e)] = rho1 * (double)acc[i];
             }
+            if (lane == 0) { dst[90] = 0.5 * rho0; dst[91] = s_acc; }
         }
         batch_counter += (unsigned)nb;
-        eval_barrier(role.n_eval_threads);  // once per residual block; blk_sum / warp_s are double-buffered over blocks
-        if (tid < NSLOT) {
-            double s = 0.0;
-            for (int w = 0; w < role.n_prod; ++w) s += sh.warp_s[bsel][w];
-            double rho0, rho1;
-            loss_eval(P.loss_type, loss_a, s, &rho0, &rho1);
-            double val;
-            if (tid < 90) val = rho1 * sh.blk_sum[bsel][tid];
-            else if (tid == 90) val = 0.5 * rho0;
-            else val = s;
-            slot_base[b * NSLOT + tid] = val;
-        }
     }
 }
 
