@@ -306,6 +306,9 @@ edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int c
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->norms, 0, sizeof(double) * 2 * capacity, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->acc, 0, sizeof(long long) * npix * capacity, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->frame, 0, sizeof(float) * npix * capacity, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&fr->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fr->copied, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&fr->stage_free[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         edsgpu_frames_destroy(fr);
@@ -324,7 +327,12 @@ void edsgpu_frames_destroy(edsgpu_frames* fr) {
     if (fr->partials) cudaFree(fr->partials);
     if (fr->tickets) cudaFree(fr->tickets);
     if (fr->norms) cudaFree(fr->norms);
-    if (fr->events_dev) cudaFree(fr->events_dev);
+    if (fr->copy_stream) { cudaStreamSynchronize(fr->copy_stream); cudaStreamDestroy(fr->copy_stream); }
+    if (fr->copied) cudaEventDestroy(fr->copied);
+    for (int i = 0; i < 2; ++i) {
+        if (fr->stage_free[i]) cudaEventDestroy(fr->stage_free[i]);
+        if (fr->events_dev[i]) cudaFree(fr->events_dev[i]);
+    }
     delete fr;
 }
 
@@ -357,25 +365,36 @@ edsgpu_status edsgpu_event_frame_create_batch(edsgpu_ctx* ctx, edsgpu_frames* fr
     if (st != EDSGPU_OK) return st;
     EDS_REQUIRE(ctx, x && y && polarity, "event_frame: null event arrays");
     DeviceGuard g(ctx->device);
-    // device staging for the events: [x u16 | y u16 | pol u8] per batch
+    // device staging for the events: [x u16 | y u16 | pol u8] per batch, double-buffered.  The copies run
+    // on the frames' copy stream and only wait for the kernels that last READ the same staging buffer,
+    // so the H2D transfer of this batch overlaps whatever the compute stream is still doing (e.g. the LM
+    // solve of the previous batch); the compute stream then waits for the copy.
     const size_t n = (size_t)count * num_events;
     const size_t off_y = align_up(n * 2, 256), off_p = off_y + align_up(n * 2, 256), total = off_p + align_up(n, 256);
-    if (frames->events_bytes < total) {
+    const int buf = (frames->stage_idx ^= 1);
+    if (frames->events_bytes[buf] < total) {
         EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (frames->events_dev) cudaFree(frames->events_dev);
-        frames->events_dev = nullptr;
-        frames->events_bytes = 0;
-        EDS_CUDA(ctx, cudaMalloc(&frames->events_dev, total));
-        frames->events_bytes = total;
+        EDS_CUDA(ctx, cudaStreamSynchronize(frames->copy_stream));
+        if (frames->events_dev[buf]) cudaFree(frames->events_dev[buf]);
+        frames->events_dev[buf] = nullptr;
+        frames->events_bytes[buf] = 0;
+        EDS_CUDA(ctx, cudaMalloc(&frames->events_dev[buf], total));
+        frames->events_bytes[buf] = total;
     }
-    char* d = (char*)frames->events_dev;
-    // the caller's buffers are used directly as the copy source (pinned or pageable)
-    EDS_CUDA(ctx, cudaMemcpyAsync(d, x, n * 2, cudaMemcpyHostToDevice, ctx->stream));
-    EDS_CUDA(ctx, cudaMemcpyAsync(d + off_y, y, n * 2, cudaMemcpyHostToDevice, ctx->stream));
-    EDS_CUDA(ctx, cudaMemcpyAsync(d + off_p, polarity, n, cudaMemcpyHostToDevice, ctx->stream));
+    char* d = (char*)frames->events_dev[buf];
+    cudaStream_t cs = frames->copy_stream;
+    EDS_CUDA(ctx, cudaStreamWaitEvent(cs, frames->stage_free[buf], 0));
+    // the caller's buffers are the copy source (pinned for a truly asynchronous copy) and must stay
+    // unchanged until the next synchronising call
+    EDS_CUDA(ctx, cudaMemcpyAsync(d, x, n * 2, cudaMemcpyHostToDevice, cs));
+    EDS_CUDA(ctx, cudaMemcpyAsync(d + off_y, y, n * 2, cudaMemcpyHostToDevice, cs));
+    EDS_CUDA(ctx, cudaMemcpyAsync(d + off_p, polarity, n, cudaMemcpyHostToDevice, cs));
+    EDS_CUDA(ctx, cudaEventRecord(frames->copied, cs));
+    EDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, frames->copied, 0));
     st = launch_frames(ctx, frames, first_slot, count, lut, (const uint16_t*)d, (const uint16_t*)(d + off_y), (const uint8_t*)(d + off_p),
                        num_events, mode, use_exp_weights, sigma);
     if (st != EDSGPU_OK) return st;
+    EDS_CUDA(ctx, cudaEventRecord(frames->stage_free[buf], ctx->stream));
     if (norms_out) {
         st = edsgpu_ensure_pinned(ctx, sizeof(double) * 2 * count);
         if (st != EDSGPU_OK) return st;

@@ -21,6 +21,12 @@ struct edsgpu_frames {
     unsigned* tickets = nullptr;  // [capacity] last-CTA election
     double* norms = nullptr;      // [capacity][2] = {norm, 1/norm}
     double k0 = 0.0, k1 = 1.0;    // Gaussian taps of the last create (for read-back)
-    void* events_dev = nullptr;   // staging for host-facing create
-    size_t events_bytes = 0;
+    // host-facing create: two device staging buffers filled by a copy stream, so that the H2D copy of
+    // the next batch of events overlaps the kernels still working on the current one
+    void* events_dev[2] = {nullptr, nullptr};
+    size_t events_bytes[2] = {0, 0};
+    int stage_idx = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied = nullptr;
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};
 };
