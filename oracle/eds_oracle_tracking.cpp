@@ -22,6 +22,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <atomic>
+#include <functional>
 #include <limits>
 #include <thread>
 #include <vector>
@@ -469,17 +471,56 @@ void block_eval(const Problem& P, int b, const double* x, int mode, int loss_typ
 
 struct Eval { double cost; double H[144]; double g[12]; };
 
-void evaluate_all(const Problem& P, const double* x, int mode, int loss_type, double loss_a, bool want_jac, int threads, Eval* out) {
+// Persistent workers for one solve: ceres keeps a thread pool alive for the whole ceres::Solve
+// (options.num_threads, Tracker.cpp:138), so the timed CPU baseline must not pay a thread creation
+// per evaluation either.  Workers spin on a generation counter between evaluations.
+class WorkerPool {
+  public:
+    explicit WorkerPool(int n) : n_(std::max(1, n)) {
+        for (int t = 1; t < n_; ++t) threads_.emplace_back([this, t]() { loop(t); });
+    }
+    ~WorkerPool() {
+        stop_.store(true);
+        gen_.fetch_add(1);
+        for (auto& t : threads_) t.join();
+    }
+    int size() const { return n_; }
+    template <typename F>
+    void run(const F& f) {  // f(worker_index), worker 0 is the caller
+        fn_ = [&f](int t) { f(t); };
+        pending_.store(n_ - 1);
+        gen_.fetch_add(1);
+        f(0);
+        while (pending_.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    }
+
+  private:
+    void loop(int t) {
+        unsigned seen = 0;
+        for (;;) {
+            while (gen_.load(std::memory_order_acquire) == seen) std::this_thread::yield();
+            seen = gen_.load(std::memory_order_acquire);
+            if (stop_.load()) return;
+            fn_(t);
+            pending_.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    int n_;
+    std::vector<std::thread> threads_;
+    std::function<void(int)> fn_;
+    std::atomic<unsigned> gen_{0};
+    std::atomic<int> pending_{0};
+    std::atomic<bool> stop_{false};
+};
+
+void evaluate_all(const Problem& P, const double* x, int mode, int loss_type, double loss_a, bool want_jac, WorkerPool* pool, Eval* out) {
     std::vector<BlockEval> be(P.B);
     auto work = [&](int b) { block_eval(P, b, x, mode, loss_type, loss_a, want_jac, &be[b], nullptr, nullptr); };
-    if (threads > 1) {
-        // one worker per residual block, the way ceres parallelises with
-        // options.num_threads == number of blocks (Tracker.cpp:138,178-195)
-        std::vector<std::thread> th;
-        int nt = std::min(threads, P.B);
-        for (int t = 0; t < nt; ++t)
-            th.emplace_back([&, t]() { for (int b = t; b < P.B; b += nt) work(b); });
-        for (auto& t : th) t.join();
+    if (pool && pool->size() > 1) {
+        // one worker per residual block, the way ceres parallelises with options.num_threads == number of
+        // blocks (Tracker.cpp:138,178-195)
+        const int nt = pool->size();
+        pool->run([&](int t) { for (int b = t; b < P.B; b += nt) work(b); });
     } else {
         for (int b = 0; b < P.B; ++b) work(b);
     }
@@ -659,12 +700,13 @@ int eds_oracle_tracker_solve(int N, const double* grad_xy, const double* norm_xy
     Problem P = make_problem(N, grad_xy, norm_xy, idp, weights, frame, H, W, fx, fy, cx, cy, cfg->num_blocks);
     const int mode = cfg->jacobian_mode, lt = cfg->loss_type, th = cfg->threads;
     const double la = cfg->loss_param;
+    WorkerPool pool(std::min(std::max(1, th), P.B));
     auto t0 = std::chrono::high_resolution_clock::now();
 
     double xc[13];
     std::memcpy(xc, x, sizeof(xc));
     Eval ev;
-    evaluate_all(P, xc, mode, lt, la, true, th, &ev);
+    evaluate_all(P, xc, mode, lt, la, true, &pool, &ev);
     double x_cost = ev.cost;
     double scale[12];
     for (int i = 0; i < 12; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(ev.H[12 * i + i]));  // jacobi_scaling, iteration 0 only
@@ -730,7 +772,7 @@ int eds_oracle_tracker_solve(int N, const double* grad_xy, const double* norm_xy
         for (int i = 0; i < 12; ++i) delta[i] = step[i] * scale[i];
         state_plus(xc, delta, cand);
         Eval evc;
-        evaluate_all(P, cand, mode, lt, la, false, th, &evc);
+        evaluate_all(P, cand, mode, lt, la, false, &pool, &evc);
         double cand_cost = std::isfinite(evc.cost) ? evc.cost : std::numeric_limits<double>::max();
         // ParameterToleranceReached
         double sn = 0;
@@ -745,7 +787,7 @@ int eds_oracle_tracker_solve(int N, const double* grad_xy, const double* norm_xy
             // HandleSuccessfulStep
             std::memcpy(xc, cand, sizeof(xc));
             x_norm = norm13(xc);
-            evaluate_all(P, xc, mode, lt, la, true, th, &ev);
+            evaluate_all(P, xc, mode, lt, la, true, &pool, &ev);
             x_cost = ev.cost;
             apply_scale();
             gmax = grad_max_norm(xc, ev.g);
