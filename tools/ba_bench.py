@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/slam-eds_b200')
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'slam-eds_b200'))
 import torch, edsgpu, bench
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 ctx = edsgpu.Context(0, stream.cuda_stream)

@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/slam-eds_b200')
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'slam-eds_b200'))
 import edsgpu
 from edsgpu import synth
 from oracle import oracle as O

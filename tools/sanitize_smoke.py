@@ -1,0 +1,35 @@
+import sys, numpy as np
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'slam-eds_b200'))
+import edsgpu
+from edsgpu import synth, synth_ba
+ctx = edsgpu.Context(0)
+scene, kf, wins = synth.make_problem("tiny", 0, 2)
+H, W = kf["H"], kf["W"]
+mx, my = synth.radtan_lut(H, W, kf["fx"], kf["fy"], kf["cx"], kf["cy"], k1=-0.3)
+ef = edsgpu.EventFrame(ctx, H, W, mx, my)
+for w in wins:
+    ef.create(w["x"], w["y"], w["pol"], w["ts"], want_host_frame=True)
+    ef.create(w["x"], w["y"], w["pol"], w["ts"], mode=edsgpu.DRAW_NN, use_exp_weights=False, sigma=0.0)
+ef = edsgpu.EventFrame(ctx, H, W)
+ef.create(wins[0]["x"], wins[0]["y"], wins[0]["pol"], wins[0]["ts"])
+for B in (4, 3):
+    kfd = edsgpu.KeyFrame(ctx, kf, B)
+    g = edsgpu.tracker_evaluate(ctx, kfd, ef.frames, 0, wins[0]["x_init"])
+    tr = edsgpu.Tracker(ctx, num_blocks=B, max_iterations=8)
+    x0 = wins[0]["x_init"]; tr.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
+    r = tr.optimize(kfd, ef.frames, 0, want_residuals=True)
+    print("B", B, r["info"]["iterations"], r["usable"])
+n = 5
+fr = edsgpu.Frames(ctx, H, W, n)
+E = len(wins[0]["x"])
+edsgpu.event_frames_batch(ctx, fr, 0, n, np.tile(wins[0]["x"], n), np.tile(wins[0]["y"], n), np.tile(wins[0]["pol"], n), E)
+kfd = edsgpu.KeyFrame(ctx, kf, 4)
+trs = [edsgpu.Tracker(ctx, num_blocks=4, max_iterations=6) for _ in range(n)]
+for t in trs: t.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
+b = edsgpu.TrackerBatch(ctx, trs, [kfd] * n, fr, 0); b.optimize(); st, inf = b.gather(); print("batch ok", [i["iterations"] for i in inf])
+pb = synth_ba.make_ba_problem(F=4, points_per_frame=120, H=120, W=160)
+w = edsgpu.BaWindow(ctx, pb["F"], pb["host_idx"], pb["target_idx"], pb["res_begin"])
+w.set_residuals(pb["recs"], pb["flags"], np.zeros((pb["R"], 8), np.float32)); w.set_points(pb["deltaF"], pb["priorF"])
+w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], synth_ba.col_major(pb["adHost"]), synth_ba.col_major(pb["adTarget"]))
+for m in (0, 1, 2): w.top_accumulate(m)
+w.top_stitch(0); w.sc_accumulate(True); w.sc_stitch(); print("ba ok")
