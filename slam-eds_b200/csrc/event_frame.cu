@@ -128,7 +128,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // OUT64 == true : write out64 = blurred * scale (debug / host read-back path).
 template <bool OUT64>
 __global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long* __restrict__ acc, int H, int W, double k0, double k1,
-                                                                 float* __restrict__ frame, double* __restrict__ partials,
+                                                                 const cudaSurfaceObject_t* __restrict__ surfs, double* __restrict__ partials,
                                                                  unsigned* __restrict__ tickets, double* __restrict__ norms,
                                                                  int first_slot, double* __restrict__ out64,
                                                                  const double* __restrict__ scale_ptr) {
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long
             if (OUT64) {
                 out64[(size_t)win * H * W + (size_t)gy * W + gx] = v * scale;
             } else {
-                frame[(size_t)slot * H * W + (size_t)gy * W + gx] = (float)v;
+                surf2Dwrite((float)v, surfs[slot], gx * (int)sizeof(float), gy);
                 sq += v * v;
             }
         }
@@ -230,7 +230,7 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
             k1 = 1.0 / sum;
         }
         dim3 grid((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, count);
-        blur_norm_kernel<false><<<grid, BLUR_THREADS, 0, ctx->stream>>>(fr->acc, H, W, k0, k1, fr->frame, fr->partials, fr->tickets,
+        blur_norm_kernel<false><<<grid, BLUR_THREADS, 0, ctx->stream>>>(fr->acc, H, W, k0, k1, fr->surf_dev, fr->partials, fr->tickets,
                                                                          fr->norms, first_slot, nullptr, nullptr);
         ctx->launches++;
         EDS_CUDA(ctx, cudaGetLastError());
@@ -298,18 +298,43 @@ edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int c
     const size_t npix = (size_t)height * width;
     const int ntiles = ((width + TILE_W - 1) / TILE_W) * ((height + TILE_H - 1) / TILE_H);
     cudaError_t e = cudaMalloc(&fr->acc, sizeof(long long) * npix * capacity);
-    if (e == cudaSuccess) e = cudaMalloc(&fr->frame, sizeof(float) * npix * capacity);
+    fr->arrays = new cudaArray_t[capacity]();
+    fr->tex = new cudaTextureObject_t[capacity]();
+    fr->surf = new cudaSurfaceObject_t[capacity]();
+    float* zeros = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&zeros, sizeof(float) * npix);
+    if (e == cudaSuccess) e = cudaMemsetAsync(zeros, 0, sizeof(float) * npix, ctx->stream);
+    for (int i = 0; i < capacity && e == cudaSuccess; ++i) {
+        const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float>();
+        e = cudaMallocArray(&fr->arrays[i], &fmt, width, height, cudaArraySurfaceLoadStore | cudaArrayTextureGather);
+        cudaResourceDesc res{};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = fr->arrays[i];
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        if (e == cudaSuccess) e = cudaCreateTextureObject(&fr->tex[i], &res, &td, nullptr);
+        if (e == cudaSuccess) e = cudaCreateSurfaceObject(&fr->surf[i], &res);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DToArrayAsync(fr->arrays[i], 0, 0, zeros, sizeof(float) * width, sizeof(float) * width, height,
+                                         cudaMemcpyDeviceToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&fr->surf_dev, sizeof(cudaSurfaceObject_t) * capacity);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(fr->surf_dev, fr->surf, sizeof(cudaSurfaceObject_t) * capacity, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc(&fr->partials, sizeof(double) * (size_t)ntiles * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&fr->tickets, sizeof(unsigned) * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&fr->norms, sizeof(double) * 2 * capacity);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->tickets, 0, sizeof(unsigned) * capacity, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->norms, 0, sizeof(double) * 2 * capacity, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->acc, 0, sizeof(long long) * npix * capacity, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(fr->frame, 0, sizeof(float) * npix * capacity, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&fr->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fr->copied, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&fr->stage_free[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (zeros) cudaFree(zeros);
     if (e != cudaSuccess) {
         edsgpu_frames_destroy(fr);
         return edsgpu_fail(ctx, e == cudaErrorMemoryAllocation ? EDSGPU_OUT_OF_MEMORY : EDSGPU_CUDA_ERROR, cudaGetErrorString(e));
@@ -323,7 +348,15 @@ void edsgpu_frames_destroy(edsgpu_frames* fr) {
     DeviceGuard g(fr->ctx->device);
     cudaStreamSynchronize(fr->ctx->stream);
     if (fr->acc) cudaFree(fr->acc);
-    if (fr->frame) cudaFree(fr->frame);
+    for (int i = 0; i < fr->capacity && fr->arrays; ++i) {
+        if (fr->tex[i]) cudaDestroyTextureObject(fr->tex[i]);
+        if (fr->surf[i]) cudaDestroySurfaceObject(fr->surf[i]);
+        if (fr->arrays[i]) cudaFreeArray(fr->arrays[i]);
+    }
+    delete[] fr->arrays;
+    delete[] fr->tex;
+    delete[] fr->surf;
+    if (fr->surf_dev) cudaFree(fr->surf_dev);
     if (fr->partials) cudaFree(fr->partials);
     if (fr->tickets) cudaFree(fr->tickets);
     if (fr->norms) cudaFree(fr->norms);

@@ -16,7 +16,13 @@ struct edsgpu_frames {
     uint64_t uid = edsgpu_next_uid();
     int H = 0, W = 0, capacity = 0;
     long long* acc = nullptr;     // [capacity][H*W] fixed-point (2^-40) brightness increments
-    float* frame = nullptr;       // [capacity][H*W] blurred, un-normalised
+    // blurred, un-normalised fp32 frames: one block-linear CUDA array per slot, written through a
+    // surface by the blur kernel and sampled by the tracker with 2x2 texture gathers (clamp-to-edge
+    // addressing = the clamped ceres::Grid2D)
+    cudaArray_t* arrays = nullptr;            // [capacity] host
+    cudaTextureObject_t* tex = nullptr;       // [capacity] host
+    cudaSurfaceObject_t* surf = nullptr;      // [capacity] host
+    cudaSurfaceObject_t* surf_dev = nullptr;  // [capacity] device copy for the blur kernel
     double* partials = nullptr;   // [capacity][ntiles] per-tile sum of squares
     unsigned* tickets = nullptr;  // [capacity] last-CTA election
     double* norms = nullptr;      // [capacity][2] = {norm, 1/norm}

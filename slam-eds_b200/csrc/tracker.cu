@@ -31,16 +31,18 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int TRK_THREADS = 256;
+constexpr int TRK_THREADS = 512;  // one CTA per SM: 13-14 producer warps, 2 consumer warps, (1 leader warp)
 constexpr int TRK_WARPS = TRK_THREADS / 32;
 constexpr int NACC = 96;        // 78 (upper triangle of J^T J) + 12 (J^T r) + 6 padding
 constexpr int JLD = 20;         // floats per point row in shared memory (80 B: conflict-free 128-bit access)
-constexpr int N_PROD = 7;       // producer warps: per-point residual + Jacobian rows
-constexpr int N_CONS = TRK_WARPS - N_PROD;  // consumer warps: own the outer-product accumulators
-constexpr int N_SLOTS = 2 * N_PROD;         // ring of 32-point batches, two per producer warp
+constexpr int N_CONS = 2;                    // consumer warps: own the outer-product accumulators (even / odd batches)
+constexpr int N_PROD = TRK_WARPS - N_CONS;   // producer warps (one fewer in a CTA that hosts a leader warp)
+constexpr int LEADER_WARP = TRK_WARPS - 1;
+constexpr int N_SLOTS = 2 * N_PROD;          // ring of 32-point batches, two per producer warp
 constexpr int NSLOT = 92;       // 78 + 12 + cost + block squared norm
 constexpr int MAX_BLOCKS = 16;  // residual blocks per problem (config.options.num_threads)
 constexpr int MAX_CLUSTER = 8;
+constexpr int MAX_K = 4;  // problems one cluster keeps in flight
 constexpr double kEps = 1e-05;  // PhotometricError.hpp:200
 
 enum { CMD_EVAL = 1, CMD_FINAL = 2, CMD_DONE = 3 };
@@ -64,7 +66,7 @@ struct KfDev {
 
 struct ProblemDesc {
     KfDev kf;
-    const float* frame;        // H*W un-normalised event frame
+    cudaTextureObject_t frame; // H x W un-normalised event frame (point-sampled, clamp-to-edge)
     const double* norms;       // {norm, 1/norm}
     double* state;             // 14 doubles: px(3) qx(4) vx(6) loss_param; in-out
     float* residuals;          // N, written by the final sweep
@@ -179,11 +181,17 @@ struct ProblemShared {
 };
 
 struct CtaShared {
-    ProblemShared prob[2];
+    ProblemShared prob[MAX_K];
     // ring of 32-point batches of rows [J(12) r pad], guarded by full/empty mbarriers
     alignas(16) float ring[N_SLOTS][32][JLD];
     alignas(8) unsigned long long full_bar[N_SLOTS];
     alignas(8) unsigned long long empty_bar[N_SLOTS];
+    // block totals of consumer warp 1, handed to consumer warp 0 (double-buffered by block)
+    float cons_part[2][96];
+    double cons_s[2];
+    // dataflow between the evaluator warps of all CTAs and the leader warp of each problem
+    alignas(8) unsigned long long ready_bar[MAX_K];   // every CTA: "evaluation constants of problem k have landed" (32 leader lanes)
+    alignas(8) unsigned long long result_bar[MAX_K];  // leader CTA of k: "every evaluator warp of the cluster is done with problem k"
 };
 
 // (a,b) of packed upper-triangle entry e (row-major, a <= b < 12)
@@ -212,7 +220,7 @@ __device__ __forceinline__ void cr_weights(float x, float* w, float* dw) {
 // tangent-space velocity Jacobian  (w (g/M - m c/M^3)) (I - v v^T/|v|^2)/|v|  =  w (alpha g - m beta)
 template <bool WANT_J>
 __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, const float* __restrict__ bc,
-                                           const float* __restrict__ frame, float inv_norm, int idx, float* __restrict__ J, float& r) {
+                                           cudaTextureObject_t frame, float inv_norm, int idx, float* __restrict__ J, float& r) {
     const float4 g4 = __ldg(&kf.gxy[idx]);
     const float2 dw = __ldg(&kf.dw[idx]);
     const double kx = __ldg(&kf.kpx[idx]), ky = __ldg(&kf.kpy[idx]), kz = __ldg(&kf.kpz[idx]);
@@ -250,21 +258,23 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, 
     const int col = max(-4, min(col_raw, W + 3)), row = max(-4, min(row_raw, H + 3));
     const float tc = (col == col_raw) ? (float)(u - fu) : 0.f;
     const float tr = (row == row_raw) ? (float)(v - fv) : 0.f;
-    const int c0 = max(0, min(col - 1, W - 1)), c1 = max(0, min(col, W - 1));
-    const int c2 = max(0, min(col + 1, W - 1)), c3 = max(0, min(col + 2, W - 1));
     float wc[4], dwc[4], wr[4], dwr[4];
     cr_weights(tc, wc, dwc);
     cr_weights(tr, wr, dwr);
+    // 4x4 taps as four 2x2 texture gathers. A gather at the corner shared by texels (i,j),(i+1,j),
+    // (i,j+1),(i+1,j+1) returns them as {w,z,x,y}; clamp-to-edge addressing clamps every texel
+    // index on its own, which is exactly the clamped ceres::Grid2D.
+    const float xc = (float)col, yr = (float)row;
+    const float4 q00 = tex2Dgather<float4>(frame, xc, yr, 0);
+    const float4 q10 = tex2Dgather<float4>(frame, xc + 2.f, yr, 0);
+    const float4 q01 = tex2Dgather<float4>(frame, xc, yr + 2.f, 0);
+    const float4 q11 = tex2Dgather<float4>(frame, xc + 2.f, yr + 2.f, 0);
+    const float taps[4][4] = {{q00.w, q00.z, q10.w, q10.z}, {q00.x, q00.y, q10.x, q10.y},
+                              {q01.w, q01.z, q11.w, q11.z}, {q01.x, q01.y, q11.x, q11.y}};
     float f = 0.f, dfdr = 0.f, dfdc = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int rr = max(0, min(row - 1 + k, H - 1));
-        const float* rp = frame + (size_t)rr * W;
-#ifdef EDS_EXP_NOTAPS
-        const float p0 = tc + (float)rr, p1 = tr, p2 = 1.f - tc, p3 = (float)c3 * 1e-3f + (float)(rp == nullptr);
-#else
-        const float p0 = __ldg(rp + c0), p1 = __ldg(rp + c1), p2 = __ldg(rp + c2), p3 = __ldg(rp + c3);
-#endif
+        const float p0 = taps[k][0], p1 = taps[k][1], p2 = taps[k][2], p3 = taps[k][3];
         const float fr = wc[0] * p0 + wc[1] * p1 + wc[2] * p2 + wc[3] * p3;
         f += wr[k] * fr;
         dfdr += dwr[k] * fr;
@@ -305,12 +315,33 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     unsigned ok;
     do {
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)  // suspend-time hint (ns): sleep instead of spinning
             : "memory");
     } while (!ok);
 }
+
+// ---- cluster-scope variants: barrier in another CTA of the cluster, data written over DSMEM ----
+__device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned cta_rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned long long* local_bar, unsigned cta_rank) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(local_bar), cta_rank)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 
 // halving butterfly: 2*HALF per-lane values -> HALF, lanes with bit OFFSET keep the upper half
 template <int HALF, int OFFSET>
@@ -375,30 +406,30 @@ __device__ __forceinline__ int reduce96_base(unsigned lane) {
 // the sweep and <= 128 registers per thread, so two CTAs share an SM and hide each other's stalls
 // (and the leader's serial LM step).  `batch_counter` numbers the batches of the whole kernel so that
 // both sides derive slot and phase parity without talking to each other.
-// Evaluator roles of one CTA.  In the leader CTA (rank 0) warp 7 is the dedicated LM leader warp and
-// does not evaluate, so that CTA has six producers; every other CTA has seven.
+// Evaluator roles of one CTA: warps 0..N_PROD-2 produce, the next N_CONS warps consume, the last warp
+// is the dedicated LM leader warp in a CTA that hosts a problem's leader and one more producer elsewhere.
 struct Roles {
     int n_prod;      // producer warps of this CTA
     int pidx;        // producer index of this warp, -1 if not a producer
-    bool consumer;   // warp 6
+    int cidx;        // consumer index of this warp, -1 if not a consumer
     int n_eval_threads;  // threads taking part in the evaluation
     int etid;        // evaluator thread index
 };
-__device__ __forceinline__ Roles make_roles(int rank) {
+__device__ __forceinline__ Roles make_roles(bool hosts_leader) {
     const int warp = threadIdx.x >> 5;
     Roles r;
-    r.n_prod = (rank == 0) ? 6 : 7;
-    r.consumer = (warp == 6);
-    r.pidx = (warp < 6) ? warp : ((warp == 7 && rank != 0) ? 6 : -1);
-    r.n_eval_threads = (rank == 0) ? TRK_THREADS - 32 : TRK_THREADS;
-    r.etid = threadIdx.x;  // warps 0..6 (and 7 when it evaluates) keep their index
+    r.n_prod = hosts_leader ? N_PROD - 1 : N_PROD;
+    r.cidx = (warp >= N_PROD - 1 && warp < LEADER_WARP) ? warp - (N_PROD - 1) : -1;
+    r.pidx = (warp < N_PROD - 1) ? warp : ((warp == LEADER_WARP && !hosts_leader) ? N_PROD - 1 : -1);
+    r.n_eval_threads = hosts_leader ? TRK_THREADS - 32 : TRK_THREADS;
+    r.etid = threadIdx.x;  // the leader warp is the last one: evaluator threads keep their index
     return r;
 }
 __device__ __forceinline__ void eval_barrier(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 template <bool RES_ONLY>
 __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base /* [MAX_BLOCKS][NSLOT] on the leader */,
-                             int rank, int csize, const Roles& role, bool write_residuals, unsigned& batch_counter) {
+                             int rank, int csize, const Roles& role, bool write_residuals, unsigned& batch_counter, unsigned& block_counter) {
     const int tid = threadIdx.x, lane = tid & 31;
     const ProblemDesc& P = ps.P;
     const KfDev& kf = P.kf;
@@ -422,7 +453,9 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
         const int nb = (n + 31) >> 5;  // batches of this block
         if (role.pidx >= 0) {
             // ---------------- producer ----------------
-            for (int j = role.pidx; j < nb; j += role.n_prod) {
+            // batches are dealt by their running number, so uneven shares even out over consecutive blocks
+            const int j0 = (role.pidx + role.n_prod - (int)(batch_counter % (unsigned)role.n_prod)) % role.n_prod;
+            for (int j = j0; j < nb; j += role.n_prod) {
                 const unsigned g = batch_counter + (unsigned)j;
                 const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
                 mbar_wait(&sh.empty_bar[slot], (fill & 1u) ^ 1u);
@@ -448,13 +481,14 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                 dst[3] = make_float4(r, 0.f, 0.f, 0.f);
                 mbar_arrive(&sh.full_bar[slot]);  // 32 arrivals complete the phase
             }
-        } else if (role.consumer) {
-            // ---------------- consumer: owns the block's sums, applies the loss, publishes the slot ----------
+        } else if (role.cidx >= 0) {
+            // ---------------- consumers: own the block's sums (warp c the batches j = c mod N_CONS, which
+            // fixes the summation order), warp 0 applies the loss and publishes the slot ----------
             float acc[96];
 #pragma unroll
             for (int i = 0; i < 96; ++i) acc[i] = 0.f;
             double s_acc = 0.0;  // sum of r^2 in fp64 (the cost decides accept / reject and the tolerances)
-            for (int j = 0; j < nb; ++j) {
+            for (int j = role.cidx; j < nb; j += N_CONS) {
                 const unsigned g = batch_counter + (unsigned)j;
                 const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
                 mbar_wait(&sh.full_bar[slot], fill & 1u);
@@ -465,18 +499,31 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
             reduce96(acc, lane);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
-            double rho0, rho1;
-            loss_eval(P.loss_type, loss_a, s_acc, &rho0, &rho1);
-            const int base = reduce96_base(lane);
-            double* dst = slot_base + b * NSLOT;
+            const unsigned buf = block_counter & 1u;
+            if (role.cidx != 0) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const int e = base + i;
-                if (e < 90) dst[ConsRows::slot(e)] = rho1 * (double)acc[i];
+                for (int i = 0; i < 3; ++i) sh.cons_part[buf][3 * lane + i] = acc[i];
+                if (lane == 0) sh.cons_s[buf] = s_acc;
+                asm volatile("bar.sync 2, %0;" ::"n"(32 * N_CONS) : "memory");
+            } else {
+                asm volatile("bar.sync 2, %0;" ::"n"(32 * N_CONS) : "memory");
+#pragma unroll
+                for (int i = 0; i < 3; ++i) acc[i] += sh.cons_part[buf][3 * lane + i];
+                s_acc += sh.cons_s[buf];
+                double rho0, rho1;
+                loss_eval(P.loss_type, loss_a, s_acc, &rho0, &rho1);
+                const int base = reduce96_base(lane);
+                double* dst = slot_base + b * NSLOT;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int e = base + i;
+                    if (e < 90) dst[ConsRows::slot(e)] = rho1 * (double)acc[i];
+                }
+                if (lane == 0) { dst[90] = 0.5 * rho0; dst[91] = s_acc; }
             }
-            if (lane == 0) { dst[90] = 0.5 * rho0; dst[91] = s_acc; }
         }
         batch_counter += (unsigned)nb;
+        block_counter++;
     }
 }
 
@@ -498,7 +545,8 @@ __device__ __forceinline__ double warp_max(double v) {
 // Leader warp: publish the evaluation constants of point xe (13 doubles in leader smem) and the
 // command to every CTA of the cluster.  Lane b derives the per-block model normalisation
 // S_b = 1e-3 + v^T A_b v (PhotometricError.hpp:132,148) and c_b = A_b v.
-__device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, int which, const double* xe, int cmd, int B, int csize) {
+__device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, int which, const double* xe, int cmd, int B, int csize,
+                               bool signal = true) {
     const int lane = threadIdx.x & 31;
     ProblemShared& ps = sh.prob[which];
     EvalConst& ec = ps.ec;  // build locally, then replicate
@@ -546,11 +594,16 @@ __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, int wh
     // replicate the used prefix of EvalConst (R,t,v + B block records) and cmd
     const int nwords = (int)(offsetof(EvalConst, blk) / 4) + 8 * B;
     const int* src = reinterpret_cast<const int*>(&ec);
-    for (int c = 1; c < csize; ++c) {
-        EvalConst* dst = &cluster.map_shared_rank(&sh, c)->prob[which].ec;
-        int* d = reinterpret_cast<int*>(dst);
-        for (int i = lane; i < nwords; i += 32) d[i] = src[i];
-        if (lane == 0) dst->cmd = cmd;
+    const int self = (int)cluster.block_rank();
+    for (int c = 0; c < csize; ++c) {
+        if (c != self) {
+            EvalConst* dst = &cluster.map_shared_rank(&sh, c)->prob[which].ec;
+            int* d = reinterpret_cast<int*>(dst);
+            for (int i = lane; i < nwords; i += 32) d[i] = src[i];
+            if (lane == 0) dst->cmd = cmd;
+        }
+        // every lane signals after its own stores: the 32nd arrival completes the phase
+        if (signal) mbar_arrive_cluster(&sh.ready_bar[which], (unsigned)c);
     }
 }
 
@@ -769,7 +822,7 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
 }
 
 // all threads of the CTA: descriptor, loss parameter and (leader CTA) the Gram matrices + state of one problem
-__device__ __forceinline__ void load_problem(ProblemShared& ps, const ProblemDesc* problems, int pid, int count, int rank) {
+__device__ __forceinline__ void load_problem(ProblemShared& ps, const ProblemDesc* problems, int pid, int count, bool leads) {
     const int tid = threadIdx.x;
     const bool valid = pid < count;
     if (tid == 0) ps.valid = valid;
@@ -781,7 +834,7 @@ __device__ __forceinline__ void load_problem(ProblemShared& ps, const ProblemDes
     __syncthreads();
     if (valid) {
         if (tid == 0) ps.loss_a = ps.P.state[13];
-        if (rank == 0) {
+        if (leads) {
             for (int i = tid; i < 21 * ps.P.kf.B; i += TRK_THREADS) (&ps.A[0][0])[i] = ps.P.kf.A[i];
             if (tid < 13) ps.x_eval[tid] = ps.P.state[tid];
         }
@@ -790,11 +843,16 @@ __device__ __forceinline__ void load_problem(ProblemShared& ps, const ProblemDes
     __syncthreads();
 }
 
-__device__ __forceinline__ void init_barriers(CtaShared& sh) {
+__device__ __forceinline__ void init_barriers(CtaShared& sh, int evaluator_warps) {
     if (threadIdx.x < N_SLOTS) {
         mbar_init(&sh.full_bar[threadIdx.x], 32);   // one producer warp fills a slot
         mbar_init(&sh.empty_bar[threadIdx.x], 32);  // the consumer warp releases it
     }
+    if (threadIdx.x < MAX_K) {
+        mbar_init(&sh.ready_bar[threadIdx.x], 32);                          // the 32 lanes of the problem's leader warp
+        mbar_init(&sh.result_bar[threadIdx.x], (unsigned)evaluator_warps);  // one arrival per evaluator warp of the cluster
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // ready/result are signalled from other CTAs
     __syncthreads();
 }
 
@@ -821,7 +879,13 @@ __device__ void leader_step(cg::cluster_group& cluster, CtaShared& sh, int which
     LmState& lm = ps.lm;
     const ProblemDesc& P = ps.P;
     const int next = lm_advance_warp(ps);
+#ifdef EDS_TIMING
+    const unsigned long long tp0 = gtime();
+#endif
     leader_publish(cluster, sh, which, (next == CMD_EVAL) ? lm.cand : lm.x, next, P.kf.B, csize);
+#ifdef EDS_TIMING
+    if (lane == 0) g_timing[15] += gtime() - tp0;
+#endif
     if (next != CMD_EVAL && lane == 0) {
         const bool usable = lm.termination != EDSGPU_TERM_FAILURE;
         if (usable) for (int i = 0; i < 13; ++i) P.state[i] = lm.x[i];  // Tracker.cpp:217-220
@@ -841,86 +905,122 @@ __device__ void leader_step(cg::cluster_group& cluster, CtaShared& sh, int which
     }
 }
 
-// One cluster = TWO tracking problems in ping-pong.  In every phase the evaluator warps of all CTAs
-// sweep the points of problem `cur` while the dedicated leader warp (rank 0, warp 7) consumes the
-// previous evaluation of the other problem, runs its LM step and publishes its next evaluation
-// point; one cluster.sync() per phase, then the roles of the two problems swap.  The serial LM step
-// is thereby hidden behind the other problem's sweep.  With a single problem the phases simply
-// alternate between sweep and LM step.
-__global__ void __launch_bounds__(TRK_THREADS, 2) track_lm_kernel(const ProblemDesc* __restrict__ problems, int count) {
+// One cluster keeps K <= MAX_K independent tracking problems in flight (problems K*c .. K*c+K-1 for
+// cluster c).  Problem k is led by warp 7 of CTA rank k: a sequential Levenberg-Marquardt loop that
+// waits for the reduced sums of an evaluation, takes its decision and publishes the next evaluation
+// point to every CTA.  All other warps are evaluators: they visit the live problems round-robin,
+// wait until the problem's constants have landed, sweep this CTA's residual blocks and report.
+// There is no cluster-wide barrier in the loop, only two mbarrier hand-overs per evaluation
+//     ready_bar[k]  (every CTA)    leader k   -> evaluators   constants + command are in your smem
+//     result_bar[k] (leader's CTA) evaluators -> leader k     all block sums are in your smem
+// so the serial LM step of one problem (~12 us of dependent fp64 latency) runs while the evaluators
+// sweep the other K-1 problems.  With K = 1 sweep and LM step simply alternate.
+__global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemDesc* __restrict__ problems, int count, int K) {
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int pair = blockIdx.x / csize;
-    load_problem(sh.prob[0], problems, 2 * pair, count, rank);
-    load_problem(sh.prob[1], problems, 2 * pair + 1, count, rank);
-    init_barriers(sh);
-    CtaShared* leader = cluster.map_shared_rank(&sh, 0);
-    const Roles role = make_roles(rank);
-    const bool is_leader_warp = (rank == 0) && ((tid >> 5) == 7);
-    unsigned batch_counter = 0;  // same in every evaluator thread of the CTA
-
-    // prologue: first evaluation point of problem 0
-    if (is_leader_warp) leader_start(cluster, sh, 0, csize);
-    cluster.sync();
-    // stage of each problem as seen by the leader warp: 0 = not started, 1 = evaluation in flight / to consume
-    int started1 = 0;
-    bool done0 = false, done1 = !sh.prob[1].valid;
-    int cur = 0;
-    for (;;) {
-        const int other = cur ^ 1;
-        if (is_leader_warp) {
-            // the other problem: start it, or consume the evaluation swept in the previous phase
-            if (other == 1) {
-                if (!done1) {
-                    if (!started1) { leader_start(cluster, sh, 1, csize); started1 = 1; }
-                    else leader_step(cluster, sh, 1, csize);
-                }
-            } else if (!done0) {
-                leader_step(cluster, sh, 0, csize);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int first = (blockIdx.x / csize) * K;
+    for (int k = 0; k < K; ++k) load_problem(sh.prob[k], problems, first + k, count, rank == k);
+    const bool hosts_leader = rank < K;
+    init_barriers(sh, TRK_WARPS * csize - K);
+    const Roles role = make_roles(hosts_leader);
+    const bool is_leader_warp = hosts_leader && ((tid >> 5) == LEADER_WARP);
+    cluster.sync();  // barriers initialised and problems loaded everywhere before the first remote signal
+#ifdef EDS_TIMING
+    const unsigned long long t_kernel = gtime();
+    unsigned long long t_wait = 0, t_work = 0, n_work = 0;
+#endif
+    if (is_leader_warp) {
+        // ---------------- leader of problem `rank` ----------------
+        if (sh.prob[rank].valid) {
+            leader_start(cluster, sh, rank, csize);
+            unsigned parity = 0;
+            for (;;) {
+#ifdef EDS_TIMING
+                const unsigned long long t0 = gtime();
+#endif
+                mbar_wait_cluster(&sh.result_bar[rank], parity);
+                parity ^= 1u;
+#ifdef EDS_TIMING
+                const unsigned long long t1 = gtime();
+#endif
+                leader_step(cluster, sh, rank, csize);
+#ifdef EDS_TIMING
+                t_wait += t1 - t0; t_work += gtime() - t1; n_work++;
+#endif
+                if (sh.prob[rank].ec.cmd != CMD_EVAL) break;
             }
-        } else {
-            ProblemShared& ps = sh.prob[cur];
-            const bool cur_done = cur ? done1 : done0;
-            if (!cur_done) {
+        }
+#ifdef EDS_TIMING
+        if (lane == 0) { atomicAdd(&g_timing[0], t_work); atomicAdd(&g_timing[1], t_wait); atomicAdd(&g_timing[2], n_work); }
+#endif
+    } else {
+        // ---------------- evaluators ----------------
+        unsigned batch_counter = 0, block_counter = 0;  // same in every evaluator thread of the CTA
+        unsigned live = 0, parity = 0;
+        for (int k = 0; k < K; ++k) live |= sh.prob[k].valid ? (1u << k) : 0u;
+        while (live) {
+            for (int k = 0; k < K; ++k) {
+                if (!((live >> k) & 1u)) continue;
+                ProblemShared& ps = sh.prob[k];
+#ifdef EDS_TIMING
+                const unsigned long long t0 = gtime();
+#endif
+                mbar_wait_cluster(&sh.ready_bar[k], (parity >> k) & 1u);
+                parity ^= 1u << k;
+#ifdef EDS_TIMING
+                const unsigned long long t1 = gtime();
+#endif
                 const int cmd = ps.ec.cmd;
-                if (cmd == CMD_EVAL) cta_evaluate<false>(ps, sh, &leader->prob[cur].slots[0][0], rank, csize, role, false, batch_counter);
-                else if (cmd == CMD_FINAL) cta_evaluate<true>(ps, sh, nullptr, rank, csize, role, true, batch_counter);
+                if (cmd == CMD_EVAL) {
+                    cta_evaluate<false>(ps, sh, &cluster.map_shared_rank(&sh, k)->prob[k].slots[0][0], rank, csize, role, false, batch_counter, block_counter);
+                    // the consumer's block sums went over DSMEM: order them before the signal
+                    fence_cluster();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&sh.result_bar[k], (unsigned)k);
+                } else {
+                    if (cmd == CMD_FINAL) cta_evaluate<true>(ps, sh, nullptr, rank, csize, role, true, batch_counter, block_counter);
+                    live &= ~(1u << k);
+                }
+#ifdef EDS_TIMING
+                t_wait += t1 - t0; t_work += gtime() - t1; n_work++;
+#endif
             }
         }
-        cluster.sync();  // slots of `cur` have landed in the leader CTA, constants/command of `other` in every CTA
-        // a problem is finished once its FINAL / DONE command has been acted upon (phase with cur == it)
-        {
-            const int cmd = sh.prob[cur].ec.cmd;
-            const bool fin = (cmd == CMD_FINAL || cmd == CMD_DONE);
-            if (cur == 0) done0 = done0 || fin; else done1 = done1 || fin;
+#ifdef EDS_TIMING
+        if (lane == 0 && rank == csize - 1) {
+            if (role.cidx == 0) { atomicAdd(&g_timing[3], t_work); atomicAdd(&g_timing[4], t_wait); atomicAdd(&g_timing[5], n_work); }
+            else if (tid == 0) { atomicAdd(&g_timing[13], t_work); atomicAdd(&g_timing[14], t_wait); }
         }
-        if (done0 && done1) break;
-        cur = other;
+#endif
     }
+    cluster.sync();  // nobody leaves while its shared memory may still be written or signalled
+#ifdef EDS_TIMING
+    if (rank == 0 && tid == 0) { atomicAdd(&g_timing[11], gtime() - t_kernel); atomicAdd(&g_timing[12], 1ull); }
+#endif
 }
 
 // parity/debug entry (edsgpu_tracker_evaluate): one full evaluation at P.state, residuals and
 // Jacobian rows written out, reduced normal equations returned.
-__global__ void __launch_bounds__(TRK_THREADS, 2) track_eval_kernel(const ProblemDesc* __restrict__ problems, int count) {
+__global__ void __launch_bounds__(TRK_THREADS, 1) track_eval_kernel(const ProblemDesc* __restrict__ problems, int count) {
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
     ProblemShared& ps = sh.prob[0];
-    load_problem(ps, problems, blockIdx.x / csize, count, rank);
-    init_barriers(sh);
+    load_problem(ps, problems, blockIdx.x / csize, count, rank == 0);
+    init_barriers(sh, 1);
     CtaShared* leader = cluster.map_shared_rank(&sh, 0);
-    const Roles role = make_roles(rank);
-    const bool is_leader_warp = (rank == 0) && ((threadIdx.x >> 5) == 7);
-    if (is_leader_warp) leader_publish(cluster, sh, 0, ps.x_eval, CMD_EVAL, ps.P.kf.B, csize);
+    const Roles role = make_roles(rank == 0);
+    const bool is_leader_warp = (rank == 0) && ((threadIdx.x >> 5) == LEADER_WARP);
+    if (is_leader_warp) leader_publish(cluster, sh, 0, ps.x_eval, CMD_EVAL, ps.P.kf.B, csize, false);
     cluster.sync();
-    unsigned batch_counter = 0;
-    if (!is_leader_warp) cta_evaluate<false>(ps, sh, &leader->prob[0].slots[0][0], rank, csize, role, true, batch_counter);
+    unsigned batch_counter = 0, block_counter = 0;
+    if (!is_leader_warp) cta_evaluate<false>(ps, sh, &leader->prob[0].slots[0][0], rank, csize, role, true, batch_counter, block_counter);
     cluster.sync();
     const ProblemDesc& P = ps.P;
     if (rank == 0 && threadIdx.x == 0 && P.eval_out) {
@@ -1106,43 +1206,90 @@ struct edsgpu_tracker {
     int cached_slot = -1;
 };
 
+struct LaunchShape { int csize, K, nclusters; };
+
 struct edsgpu_batch {
     edsgpu_ctx* ctx = nullptr;
-    int count = 0, csize = 1;
+    int count = 0;
+    LaunchShape shape{1, 1, 0};
     ProblemDesc* desc = nullptr;  // device
     std::vector<edsgpu_tracker*> trackers;
 };
 
 namespace {
 
-int pick_cluster(const edsgpu_ctx* ctx, int count, int B) {
-    if (const char* e = getenv("EDSGPU_CLUSTER")) {  // tuning/debug override
-        const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8) return v;
-    }
-    int c = 1;
-    // two CTAs are resident per SM (<= 128 registers/thread, ~75 KB shared memory each)
-    while (c * 2 <= MAX_CLUSTER && c * 2 <= B && (size_t)count * c * 2 <= (size_t)2 * ctx->num_sms) c *= 2;
-    return c;
-}
-
-template <typename K>
-edsgpu_status launch_cluster(edsgpu_ctx* ctx, K kernel, const ProblemDesc* desc_dev, int count, int nclusters, int csize) {
-    cudaLaunchConfig_t cfg{};
+void cluster_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, cudaStream_t stream, int nclusters, int csize) {
+    cfg = cudaLaunchConfig_t{};
     cfg.gridDim = dim3(nclusters * csize);
     cfg.blockDim = dim3(TRK_THREADS);
     cfg.dynamicSmemBytes = sizeof(CtaShared);
-    cfg.stream = ctx->stream;
-    // per device, cheap: opt in to > 48 KB of dynamic shared memory
-    EDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
-    cudaLaunchAttribute attr[1];
+    cfg.stream = stream;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = csize;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    EDS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, desc_dev, count));
+}
+
+// clusters of c = 1 << k CTAs the device holds at once (cached per context)
+int resident_clusters(edsgpu_ctx* ctx, int k) {
+    if (ctx->lm_clusters[k] == 0) {
+        const int c = 1 << k;
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attr[1];
+        cluster_config(cfg, attr, ctx->stream, 1, c);
+        int n = 0;
+        cudaFuncSetAttribute(track_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared));
+        if (cudaOccupancyMaxActiveClusters(&n, track_lm_kernel, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = ctx->num_sms / c;  // one 512-thread CTA per SM
+        }
+        ctx->lm_clusters[k] = n;
+        if (getenv("EDSGPU_VERBOSE")) fprintf(stderr, "[edsgpu] device holds %d clusters of %d tracker CTAs\n", n, c);
+    }
+    return ctx->lm_clusters[k];
+}
+
+// Shape of a batched launch: CTAs per cluster (<= residual blocks) and problems K kept in flight per
+// cluster.  Wide clusters first; K grows only as far as needed to get down to about one CTA per SM
+// (more problems per cluster hide the serial LM steps, more clusters use more SMs); everything must
+// be resident at once, a second wave costs more than narrower clusters do.
+LaunchShape pick_shape(edsgpu_ctx* ctx, int count, int B) {
+    int force_c = 0, force_k = 0;
+    if (const char* e = getenv("EDSGPU_CLUSTER")) {  // tuning/debug overrides
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) force_c = v;
+    }
+    if (const char* e = getenv("EDSGPU_INFLIGHT")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= MAX_K) force_k = v;
+    }
+    for (int k = 3; k >= 0; --k) {
+        const int c = 1 << k;
+        if (force_c ? (c != force_c) : (c > MAX_CLUSTER || c > B)) continue;
+        int K = (int)(((size_t)count * c + ctx->num_sms - 1) / ctx->num_sms);
+        K = std::max(1, std::min(K, std::min(MAX_K, c)));
+        if (force_k) K = std::min(force_k, c);
+        const int n = (count + K - 1) / K;
+        if (force_c || k == 0 || n <= resident_clusters(ctx, k)) return LaunchShape{c, K, n};
+    }
+    return LaunchShape{1, 1, count};
+}
+
+template <typename K, typename... Args>
+edsgpu_status launch_cluster(edsgpu_ctx* ctx, K kernel, int nclusters, int csize, Args... args) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    cluster_config(cfg, attr, ctx->stream, nclusters, csize);
+    // per device, cheap: opt in to > 48 KB of dynamic shared memory
+    EDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
+    if (getenv("EDSGPU_VERBOSE")) {  // debug aid: how many clusters of this shape the device holds at once
+        int max_clusters = 0;
+        cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
+        fprintf(stderr, "[edsgpu] launch: %d clusters of %d CTAs; device holds %d such clusters\n", nclusters, csize, max_clusters);
+    }
+    EDS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, args...));
     ctx->launches++;
     return EDSGPU_OK;
 }
@@ -1150,7 +1297,7 @@ edsgpu_status launch_cluster(edsgpu_ctx* ctx, K kernel, const ProblemDesc* desc_
 ProblemDesc make_desc(const edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot) {
     ProblemDesc d{};
     d.kf = kf->dev;
-    d.frame = frames->frame + (size_t)slot * frames->H * frames->W;
+    d.frame = frames->tex[slot];
     d.norms = frames->norms + 2 * slot;
     d.state = tr->state;
     d.residuals = tr->residuals;
@@ -1337,7 +1484,7 @@ edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* tracke
     edsgpu_batch* b = new edsgpu_batch();
     b->ctx = ctx;
     b->count = count;
-    b->csize = pick_cluster(ctx, (count + 1) / 2, B);  // one cluster per PAIR of problems
+    b->shape = pick_shape(ctx, count, B);
     b->trackers.assign(trackers, trackers + count);
     std::vector<ProblemDesc> hd(count);
     for (int i = 0; i < count; ++i) hd[i] = make_desc(trackers[i], keyframes[i], frames, first_slot + i);
@@ -1361,7 +1508,7 @@ edsgpu_status edsgpu_batch_optimize(edsgpu_batch* b) {
     if (!b) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = b->ctx;
     DeviceGuard g(ctx->device);
-    edsgpu_status st = launch_cluster(ctx, track_lm_kernel, (const ProblemDesc*)b->desc, b->count, (b->count + 1) / 2, b->csize);
+    edsgpu_status st = launch_cluster(ctx, track_lm_kernel, b->shape.nclusters, b->shape.csize, (const ProblemDesc*)b->desc, b->count, b->shape.K);
     if (st != EDSGPU_OK) return st;
     mad_kernel<<<b->count, MAD_THREADS, 0, ctx->stream>>>((const ProblemDesc*)b->desc);
     ctx->launches++;
@@ -1464,7 +1611,7 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     double* hstate = (double*)(hp + sizeof(ProblemDesc));
     memset(hd, 0, sizeof(ProblemDesc));
     hd->kf = kf->dev;
-    hd->frame = frames->frame + (size_t)slot * frames->H * frames->W;
+    hd->frame = frames->tex[slot];
     hd->norms = frames->norms + 2 * slot;
     hd->state = (double*)(ds + o_state);
     hd->residuals = (float*)(ds + o_res);
@@ -1477,8 +1624,8 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     hstate[13] = loss_param;
     EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_desc, hd, sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
     EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_state, hstate, 14 * 8, cudaMemcpyHostToDevice, ctx->stream));
-    const int csize = pick_cluster(ctx, 1, kf->dev.B);
-    st = launch_cluster(ctx, track_eval_kernel, (const ProblemDesc*)(ds + o_desc), 1, 1, csize);
+    const int csize = pick_shape(ctx, 1, kf->dev.B).csize;
+    st = launch_cluster(ctx, track_eval_kernel, 1, csize, (const ProblemDesc*)(ds + o_desc), 1);
     if (st != EDSGPU_OK) return st;
     double* hev = (double*)(hp + sizeof(ProblemDesc) + 14 * 8);
     EDS_CUDA(ctx, cudaMemcpyAsync(hev, ds + o_eval, 157 * 8, cudaMemcpyDeviceToHost, ctx->stream));

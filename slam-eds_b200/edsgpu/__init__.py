@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_PKG), "libedsgpu.so")
+# EDSGPU_LIBRARY: developer override to A/B an experimental build of the same ABI
+LIB_PATH = os.environ.get("EDSGPU_LIBRARY") or os.path.join(os.path.dirname(_PKG), "libedsgpu.so")
 _lib = None
 
 OK, INVALID_ARGUMENT, CUDA_ERROR, NOT_USABLE, NON_MONOTONIC_TIME, OUT_OF_MEMORY = range(6)
