@@ -35,10 +35,13 @@ constexpr int TRK_THREADS = 512;  // one CTA per SM: 13-14 producer warps, 2 con
 constexpr int TRK_WARPS = TRK_THREADS / 32;
 constexpr int NACC = 96;        // 78 (upper triangle of J^T J) + 12 (J^T r) + 6 padding
 constexpr int JLD = 20;         // floats per point row in shared memory (80 B: conflict-free 128-bit access)
-constexpr int N_CONS = 2;                    // consumer warps: own the outer-product accumulators (even / odd batches)
+#ifndef EDS_N_CONS
+#define EDS_N_CONS 3
+#endif
+constexpr int N_CONS = EDS_N_CONS;           // consumer warps: own the outer-product accumulators (batches j = c mod N_CONS)
 constexpr int N_PROD = TRK_WARPS - N_CONS;   // producer warps (one fewer in a CTA that hosts a leader warp)
 constexpr int LEADER_WARP = TRK_WARPS - 1;
-constexpr int N_SLOTS = 2 * N_PROD;          // ring of 32-point batches, two per producer warp
+constexpr int N_SLOTS = 3 * N_PROD;          // ring of 32-point batches, three per producer warp (absorbs stragglers)
 constexpr int NSLOT = 92;       // 78 + 12 + cost + block squared norm
 constexpr int MAX_BLOCKS = 16;  // residual blocks per problem (config.options.num_threads)
 constexpr int MAX_CLUSTER = 8;
@@ -186,9 +189,9 @@ struct CtaShared {
     alignas(16) float ring[N_SLOTS][32][JLD];
     alignas(8) unsigned long long full_bar[N_SLOTS];
     alignas(8) unsigned long long empty_bar[N_SLOTS];
-    // block totals of consumer warp 1, handed to consumer warp 0 (double-buffered by block)
-    float cons_part[2][96];
-    double cons_s[2];
+    // block totals of consumer warps 1.., handed to consumer warp 0 (double-buffered by block)
+    float cons_part[2][N_CONS - 1][96];
+    double cons_s[2][N_CONS - 1];
     // dataflow between the evaluator warps of all CTAs and the leader warp of each problem
     alignas(8) unsigned long long ready_bar[MAX_K];   // every CTA: "evaluation constants of problem k have landed" (32 leader lanes)
     alignas(8) unsigned long long result_bar[MAX_K];  // leader CTA of k: "every evaluator warp of the cluster is done with problem k"
@@ -215,15 +218,66 @@ __device__ __forceinline__ void cr_weights(float x, float* w, float* dw) {
     dw[3] = 0.5f * x * (3.0f * x - 2.0f);
 }
 
+// Stage 1 of a point: warp into the event camera and project (PhotometricError.hpp:157-168) ->
+// interpolation cell, in-cell fractions and the camera-frame quantities the Jacobian needs.
+struct PointGeo {
+    int col, row;      // cell, clamped to [-4, W+3] x [-4, H+3]
+    float tc, tr;      // fractions in the cell (0 where clamped)
+    float iz, px, py;  // P = R kp + t: 1/Pz, Px, Py
+    float ax, ay, az;  // R kp
+};
+
+// (u - cell, cell) for u = f p / pz + c without an fp64 division on the critical path: the cell comes
+// from an fp32 estimate, the fraction from the exact fp64 numerator (f p + (c - cell) pz) times the
+// fp32 reciprocal, i.e. absolute error ~1e-7 px where plain fp32 projection would carry ~2e-5 px
+// (SURVEY.md section 7).  A cell guessed one off is repaired; at a cell boundary both choices give
+// the same interpolant.  Outside [-4, limit + 3] the clamped Grid2D is constant: fraction dropped.
+__device__ __forceinline__ void project_axis(double f, double c, double p, double pz, float pf, float izf, int limit, int& cell, float& frac) {
+    const float est = fmaf((float)f * pf, izf, (float)c);
+    int q = max(-6, min(__float2int_rd(est), limit + 5));  // saturating conversion, NaN -> 0
+    float t = (float)fma(f, p, (c - (double)q) * pz) * izf;
+    if (t < 0.f) { q -= 1; t += 1.f; }
+    else if (t >= 1.f) { q += 1; t -= 1.f; }
+    cell = max(-4, min(q, limit + 3));
+    frac = (cell == q) ? t : 0.f;
+}
+
+__device__ __forceinline__ void point_geometry(const KfDev& kf, const EvalConst& K, int idx, PointGeo& G) {
+    const double kx = __ldg(&kf.kpx[idx]), ky = __ldg(&kf.kpy[idx]), kz = __ldg(&kf.kpz[idx]);
+    const double ax = K.R[0] * kx + K.R[1] * ky + K.R[2] * kz;
+    const double ay = K.R[3] * kx + K.R[4] * ky + K.R[5] * kz;
+    const double az = K.R[6] * kx + K.R[7] * ky + K.R[8] * kz;
+    const double px = ax + K.t[0], py = ay + K.t[1], pz = az + K.t[2];
+    G.ax = (float)ax; G.ay = (float)ay; G.az = (float)az;
+    G.px = (float)px; G.py = (float)py;
+    G.iz = __frcp_rn((float)pz);
+    project_axis(kf.fx, kf.cx, px, pz, G.px, G.iz, kf.W, G.col, G.tc);
+    project_axis(kf.fy, kf.cy, py, pz, G.py, G.iz, kf.H, G.row, G.tr);
+}
+
+// 4x4 taps as four 2x2 texture gathers. A gather at the corner shared by texels (i,j),(i+1,j),
+// (i,j+1),(i+1,j+1) returns them as {w,z,x,y}; clamp-to-edge addressing clamps every texel index on
+// its own, which is exactly the clamped ceres::Grid2D.
+struct Taps { float4 q00, q10, q01, q11; };
+__device__ __forceinline__ Taps fetch_taps(cudaTextureObject_t frame, int col, int row) {
+    const float xc = (float)col, yr = (float)row;
+    Taps t;
+    t.q00 = tex2Dgather<float4>(frame, xc, yr, 0);
+    t.q10 = tex2Dgather<float4>(frame, xc + 2.f, yr, 0);
+    t.q01 = tex2Dgather<float4>(frame, xc, yr + 2.f, 0);
+    t.q11 = tex2Dgather<float4>(frame, xc + 2.f, yr + 2.f, 0);
+    return t;
+}
+
 // per-block constants published by the leader: bc = {1/M, alpha, beta[6]} with
 // alpha = 1/(M |v|), beta_k = (c_k/M^3 + kappa v_k)/|v|, kappa = (1/M - c.v/M^3)/|v|^2, so that the
 // tangent-space velocity Jacobian  (w (g/M - m c/M^3)) (I - v v^T/|v|^2)/|v|  =  w (alpha g - m beta)
+//
+// Stage 2 of a point: bicubic sample + residual + Jacobian row from the geometry, the fetched taps and
+// the point's gradient record g4 = {Gx, Gy, X, Y}, dw = {inverse depth, weight}.
 template <bool WANT_J>
-__device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, const float* __restrict__ bc,
-                                           cudaTextureObject_t frame, float inv_norm, int idx, float* __restrict__ J, float& r) {
-    const float4 g4 = __ldg(&kf.gxy[idx]);
-    const float2 dw = __ldg(&kf.dw[idx]);
-    const double kx = __ldg(&kf.kpx[idx]), ky = __ldg(&kf.kpy[idx]), kz = __ldg(&kf.kpz[idx]);
+__device__ __forceinline__ void point_finish(const KfDev& kf, const EvalConst& K, const float* __restrict__ bc, float inv_norm,
+                                             const PointGeo& G, const Taps& T, float4 g4, float2 dw, float* __restrict__ J, float& r) {
     const float Gx = g4.x, Gy = g4.y, X = g4.z, Y = g4.w, d = dw.x, w = dw.y;
     // model term: m = g . v with g = -(Gx dflow_x/dv + Gy dflow_y/dv), PhotometricError.hpp:114-122,145
     float g[6];
@@ -236,41 +290,11 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, 
     float m = 0.f;
 #pragma unroll
     for (int k = 0; k < 6; ++k) m += g[k] * K.vf[k];
-    // warp + projection in fp64 (PhotometricError.hpp:157-168): the pixel coordinate must not
-    // carry fp32 rounding (1.5e-5 px at |u| ~ 256), SURVEY.md section 7.
-#ifdef EDS_EXPERIMENT_FP32_GEOM
-    typedef float greal;
-#else
-    typedef double greal;
-#endif
-    const greal ax = (greal)K.R[0] * (greal)kx + (greal)K.R[1] * (greal)ky + (greal)K.R[2] * (greal)kz;
-    const greal ay = (greal)K.R[3] * (greal)kx + (greal)K.R[4] * (greal)ky + (greal)K.R[5] * (greal)kz;
-    const greal az = (greal)K.R[6] * (greal)kx + (greal)K.R[7] * (greal)ky + (greal)K.R[8] * (greal)kz;
-    const greal px = ax + (greal)K.t[0], py = ay + (greal)K.t[1], pz = az + (greal)K.t[2];
-    const greal iz = (greal)1.0 / pz;
-    const greal u = (greal)kf.fx * (px * iz) + (greal)kf.cx;
-    const greal v = (greal)kf.fy * (py * iz) + (greal)kf.cy;
-    const greal fu = floor(u), fv = floor(v);
-    // The clamped Grid2D makes the interpolant constant more than 2 px outside the image: clamp the
-    // integer cell (saturating conversion) and drop the fraction there; identical inside.
-    const int W = kf.W, H = kf.H;
-    const int col_raw = __double2int_rd((double)u), row_raw = __double2int_rd((double)v);
-    const int col = max(-4, min(col_raw, W + 3)), row = max(-4, min(row_raw, H + 3));
-    const float tc = (col == col_raw) ? (float)(u - fu) : 0.f;
-    const float tr = (row == row_raw) ? (float)(v - fv) : 0.f;
     float wc[4], dwc[4], wr[4], dwr[4];
-    cr_weights(tc, wc, dwc);
-    cr_weights(tr, wr, dwr);
-    // 4x4 taps as four 2x2 texture gathers. A gather at the corner shared by texels (i,j),(i+1,j),
-    // (i,j+1),(i+1,j+1) returns them as {w,z,x,y}; clamp-to-edge addressing clamps every texel
-    // index on its own, which is exactly the clamped ceres::Grid2D.
-    const float xc = (float)col, yr = (float)row;
-    const float4 q00 = tex2Dgather<float4>(frame, xc, yr, 0);
-    const float4 q10 = tex2Dgather<float4>(frame, xc + 2.f, yr, 0);
-    const float4 q01 = tex2Dgather<float4>(frame, xc, yr + 2.f, 0);
-    const float4 q11 = tex2Dgather<float4>(frame, xc + 2.f, yr + 2.f, 0);
-    const float taps[4][4] = {{q00.w, q00.z, q10.w, q10.z}, {q00.x, q00.y, q10.x, q10.y},
-                              {q01.w, q01.z, q11.w, q11.z}, {q01.x, q01.y, q11.x, q11.y}};
+    cr_weights(G.tc, wc, dwc);
+    cr_weights(G.tr, wr, dwr);
+    const float taps[4][4] = {{T.q00.w, T.q00.z, T.q10.w, T.q10.z}, {T.q00.x, T.q00.y, T.q10.x, T.q10.y},
+                              {T.q01.w, T.q01.z, T.q11.w, T.q11.z}, {T.q01.x, T.q01.y, T.q11.x, T.q11.y}};
     float f = 0.f, dfdr = 0.f, dfdc = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -285,15 +309,14 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, 
     if (!WANT_J) return;
     const float er = inv_norm * dfdr, ec = inv_norm * dfdc;
     // d r / d P  (P = R kp + t)
-    const float izf = (float)iz, fxf = (float)kf.fx, fyf = (float)kf.fy;
-    const float pxf = (float)px, pyf = (float)py;
-    const float wiz = w * izf;
+    const float fxf = (float)kf.fx, fyf = (float)kf.fy;
+    const float wiz = w * G.iz;
     const float dPx = -wiz * ec * fxf;
     const float dPy = -wiz * er * fyf;
-    const float dPz = -(dPx * pxf + dPy * pyf) * izf;
+    const float dPz = -(dPx * G.px + dPy * G.py) * G.iz;
     J[0] = dPx; J[1] = dPy; J[2] = dPz;
     // quaternion tangent: q <- [sin|d| d/|d|, cos|d|] * q rotates by 2|d|: dP/dtheta = -2 [R kp]x
-    const float axf = 2.0f * (float)ax, ayf = 2.0f * (float)ay, azf = 2.0f * (float)az;
+    const float axf = 2.0f * G.ax, ayf = 2.0f * G.ay, azf = 2.0f * G.az;
     J[3] = ayf * dPz - azf * dPy;
     J[4] = azf * dPx - axf * dPz;
     J[5] = axf * dPy - ayf * dPx;
@@ -301,6 +324,16 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, 
     const float wa = w * bc[1], wm = w * m;
 #pragma unroll
     for (int k = 0; k < 6; ++k) J[6 + k] = wa * g[k] - wm * bc[2 + k];
+}
+
+// both stages back to back (residual-only sweeps, small paths)
+template <bool WANT_J>
+__device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, const float* __restrict__ bc,
+                                           cudaTextureObject_t frame, float inv_norm, int idx, float* __restrict__ J, float& r) {
+    PointGeo G;
+    point_geometry(kf, K, idx, G);
+    const Taps T = fetch_taps(frame, G.col, G.row);
+    point_finish<WANT_J>(kf, K, bc, inv_norm, G, T, __ldg(&kf.gxy[idx]), __ldg(&kf.dw[idx]), J, r);
 }
 
 // ---- mbarrier helpers (shared::cta) ---------------------------------------------------------
@@ -331,6 +364,10 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned cta_r
 __device__ __forceinline__ void mbar_arrive_cluster(unsigned long long* local_bar, unsigned cta_rank) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(local_bar), cta_rank)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(unsigned long long* local_bar, unsigned cta_rank) {  // after fence_cluster()
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(local_bar), cta_rank)) : "memory");
+}
+__device__ __forceinline__ void fence_cluster();
 __device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, unsigned parity) {
     unsigned ok;
     do {
@@ -420,6 +457,7 @@ __device__ __forceinline__ Roles make_roles(bool hosts_leader) {
     Roles r;
     r.n_prod = hosts_leader ? N_PROD - 1 : N_PROD;
     r.cidx = (warp >= N_PROD - 1 && warp < LEADER_WARP) ? warp - (N_PROD - 1) : -1;
+    static_assert(N_CONS >= 2 && N_CONS <= 4, "consumer warps");
     r.pidx = (warp < N_PROD - 1) ? warp : ((warp == LEADER_WARP && !hosts_leader) ? N_PROD - 1 : -1);
     r.n_eval_threads = hosts_leader ? TRK_THREADS - 32 : TRK_THREADS;
     r.etid = threadIdx.x;  // the leader warp is the last one: evaluator threads keep their index
@@ -437,6 +475,94 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
     const float inv_norm = (float)P.norms[1];
     const double loss_a = ps.loss_a;
     const int ne = kf.N / kf.B;
+    // The texture handle is read from shared memory, which the compiler cannot prove warp-uniform: it
+    // would wrap every fetch in a loop over the distinct handles of the warp.  A warp-wide OR leaves
+    // the value unchanged and lands in a uniform register.
+    const cudaTextureObject_t frame = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(P.frame >> 32)) << 32) |
+                                      (unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)P.frame);
+    if constexpr (!RES_ONLY) {
+        if (role.pidx >= 0) {
+            // ---------------- producer ----------------
+            // This warp's batches of the visit, across the CTA's blocks: batches are dealt by their running
+            // number (uneven shares even out over consecutive blocks and visits).  Two-stage software
+            // pipeline: the fp64 geometry of the NEXT batch is computed while the texture gathers of the
+            // current one are in flight; the per-batch dependent latency is what bounds the sweep.
+            const int B = kf.B, n_prod = role.n_prod;
+            // every block has `ne` points except the last one, which also takes the remainder (Tracker.cpp:178-190)
+            const int n_last = kf.N - (B - 1) * ne;
+            const int nb_reg = (ne + 31) >> 5, nb_last = (n_last + 31) >> 5;
+            auto points_of = [&](int b) { return (b + 1 == B) ? n_last : ne; };
+            auto settle = [&](int& b, int& j, unsigned& gbase) {  // move (b, j) to the block that holds batch j
+                while (b < B) {
+                    const int nbb = (b + 1 == B) ? nb_last : nb_reg;
+                    if (j < nbb) break;
+                    j -= nbb; gbase += (unsigned)nbb; b += csize;
+                }
+            };
+            int b = rank, j = (role.pidx + n_prod - (int)(batch_counter % (unsigned)n_prod)) % n_prod;
+            unsigned gbase = batch_counter;
+            settle(b, j, gbase);
+            PointGeo G = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            bool valid = false;
+            int idx = 0;
+            if (b < B) {
+                const int i = (j << 5) + lane;
+                valid = i < points_of(b);
+                idx = b * ne + i;
+                if (valid) point_geometry(kf, ec, idx, G);
+            }
+            while (b < B) {
+                // current batch: taps and gradient record in flight
+                const Taps T = fetch_taps(frame, G.col, G.row);
+                float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float2 dw = make_float2(0.f, 0.f);
+                if (valid) { g4 = __ldg(&kf.gxy[idx]); dw = __ldg(&kf.dw[idx]); }
+                // next batch: geometry
+                int b2 = b, j2 = j + n_prod;
+                unsigned gbase2 = gbase;
+                settle(b2, j2, gbase2);
+                PointGeo G2 = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                bool valid2 = false;
+                int idx2 = 0;
+                if (b2 < B) {
+                    const int i2 = (j2 << 5) + lane;
+                    valid2 = i2 < points_of(b2);
+                    idx2 = b2 * ne + i2;
+                    if (valid2) point_geometry(kf, ec, idx2, G2);
+                }
+                // current batch: finish and hand over
+                const unsigned g = gbase + (unsigned)j;
+                const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
+                float J[12], r = 0.f;
+                if (valid) {
+                    point_finish<true>(kf, ec, ec.blk[b], inv_norm, G, T, g4, dw, J, r);
+                    if (write_residuals) {
+                        P.residuals[idx] = r;
+                        if (P.jac_out) {
+#pragma unroll
+                            for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * idx + k] = J[k];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) J[k] = 0.f;
+                }
+                mbar_wait(&sh.empty_bar[slot], (fill & 1u) ^ 1u);
+                float4* dst = reinterpret_cast<float4*>(&sh.ring[slot][lane][0]);
+                dst[0] = make_float4(J[0], J[1], J[2], J[3]);
+                dst[1] = make_float4(J[4], J[5], J[6], J[7]);
+                dst[2] = make_float4(J[8], J[9], J[10], J[11]);
+                dst[3] = make_float4(r, 0.f, 0.f, 0.f);
+                mbar_arrive(&sh.full_bar[slot]);  // 32 arrivals complete the phase
+                b = b2; j = j2; gbase = gbase2; G = G2; valid = valid2; idx = idx2;
+            }
+            for (int bb = rank; bb < B; bb += csize) {  // the counters advance as they do for the consumers
+                batch_counter += (unsigned)((bb + 1 == B) ? nb_last : nb_reg);
+                block_counter++;
+            }
+            return;
+        }
+    }
     for (int b = rank; b < kf.B; b += csize) {
         const float* bc = ec.blk[b];
         const int start = b * ne;
@@ -445,43 +571,13 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
             // residual write-back only (Tracker.cpp:223-230): no Jacobian, no reduction, no DSMEM traffic
             for (int i = role.etid; i < n; i += role.n_eval_threads) {
                 float r;
-                eval_point<false>(kf, ec, bc, P.frame, inv_norm, start + i, nullptr, r);
+                eval_point<false>(kf, ec, bc, frame, inv_norm, start + i, nullptr, r);
                 P.residuals[start + i] = r;
             }
             continue;
         }
         const int nb = (n + 31) >> 5;  // batches of this block
-        if (role.pidx >= 0) {
-            // ---------------- producer ----------------
-            // batches are dealt by their running number, so uneven shares even out over consecutive blocks
-            const int j0 = (role.pidx + role.n_prod - (int)(batch_counter % (unsigned)role.n_prod)) % role.n_prod;
-            for (int j = j0; j < nb; j += role.n_prod) {
-                const unsigned g = batch_counter + (unsigned)j;
-                const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
-                mbar_wait(&sh.empty_bar[slot], (fill & 1u) ^ 1u);
-                const int i = (j << 5) + lane;
-                float J[12], r = 0.f;
-                if (i < n) {
-                    eval_point<true>(kf, ec, bc, P.frame, inv_norm, start + i, J, r);
-                    if (write_residuals) {
-                        P.residuals[start + i] = r;
-                        if (P.jac_out) {
-#pragma unroll
-                            for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * (start + i) + k] = J[k];
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 12; ++k) J[k] = 0.f;
-                }
-                float4* dst = reinterpret_cast<float4*>(&sh.ring[slot][lane][0]);
-                dst[0] = make_float4(J[0], J[1], J[2], J[3]);
-                dst[1] = make_float4(J[4], J[5], J[6], J[7]);
-                dst[2] = make_float4(J[8], J[9], J[10], J[11]);
-                dst[3] = make_float4(r, 0.f, 0.f, 0.f);
-                mbar_arrive(&sh.full_bar[slot]);  // 32 arrivals complete the phase
-            }
-        } else if (role.cidx >= 0) {
+        if (role.cidx >= 0) {
             // ---------------- consumers: own the block's sums (warp c the batches j = c mod N_CONS, which
             // fixes the summation order), warp 0 applies the loss and publishes the slot ----------
             float acc[96];
@@ -502,14 +598,17 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
             const unsigned buf = block_counter & 1u;
             if (role.cidx != 0) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) sh.cons_part[buf][3 * lane + i] = acc[i];
-                if (lane == 0) sh.cons_s[buf] = s_acc;
+                for (int i = 0; i < 3; ++i) sh.cons_part[buf][role.cidx - 1][3 * lane + i] = acc[i];
+                if (lane == 0) sh.cons_s[buf][role.cidx - 1] = s_acc;
                 asm volatile("bar.sync 2, %0;" ::"n"(32 * N_CONS) : "memory");
             } else {
                 asm volatile("bar.sync 2, %0;" ::"n"(32 * N_CONS) : "memory");
 #pragma unroll
-                for (int i = 0; i < 3; ++i) acc[i] += sh.cons_part[buf][3 * lane + i];
-                s_acc += sh.cons_s[buf];
+                for (int c = 0; c < N_CONS - 1; ++c) {  // fixed order: the sums do not depend on timing
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) acc[i] += sh.cons_part[buf][c][3 * lane + i];
+                    s_acc += sh.cons_s[buf][c];
+                }
                 double rho0, rho1;
                 loss_eval(P.loss_type, loss_a, s_acc, &rho0, &rho1);
                 const int base = reduce96_base(lane);
@@ -596,14 +695,17 @@ __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, int wh
     const int* src = reinterpret_cast<const int*>(&ec);
     const int self = (int)cluster.block_rank();
     for (int c = 0; c < csize; ++c) {
-        if (c != self) {
-            EvalConst* dst = &cluster.map_shared_rank(&sh, c)->prob[which].ec;
-            int* d = reinterpret_cast<int*>(dst);
-            for (int i = lane; i < nwords; i += 32) d[i] = src[i];
-            if (lane == 0) dst->cmd = cmd;
-        }
-        // every lane signals after its own stores: the 32nd arrival completes the phase
-        if (signal) mbar_arrive_cluster(&sh.ready_bar[which], (unsigned)c);
+        if (c == self) continue;
+        EvalConst* dst = &cluster.map_shared_rank(&sh, c)->prob[which].ec;
+        int* d = reinterpret_cast<int*>(dst);
+        for (int i = lane; i < nwords; i += 32) d[i] = src[i];
+        if (lane == 0) dst->cmd = cmd;
+    }
+    if (signal) {
+        // one fence orders all of this lane's stores, then every lane signals every CTA: the 32nd
+        // arrival completes the phase there
+        fence_cluster();
+        for (int c = 0; c < csize; ++c) mbar_arrive_cluster_relaxed(&sh.ready_bar[which], (unsigned)c);
     }
 }
 
@@ -750,40 +852,35 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
             a[j] = h[j];
             if (j == lane) a[j] += lm.diag[li] / radius;
         }
-        // right-looking Cholesky in registers: after step k lane i >= k holds L[i][k] in a[k],
-        // lane k holds L[j][k] (= L^T[k][j]) in a[j], j > k
+        // Right-looking Cholesky in registers with the forward substitution L z = gs folded in.  After
+        // step k lane i >= k holds L[i][k] in a[k]; lane k keeps its row j > k UNSCALED (L[k][k] L[j][k]),
+        // the 1/L[k][k] it owes goes into the back substitution.  Straight-line code: lanes that must not
+        // take part in an update multiply by zero instead of branching around it.
         bool ok = true;
         double myinv = 0.0;
-        // branch-free (selects only): divergent branches around the shuffles would serialise the warp
-#pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            const double dk = __shfl_sync(FULL, a[k], k);
-            ok = ok && (dk > 0.0) && (dk < DBL_MAX);
-            const double inv = rsqrt(dk);
-            const double lik = a[k] * inv;
-            myinv = (lane == k) ? inv : myinv;
-            a[k] = (lane >= k) ? lik : a[k];
-#pragma unroll
-            for (int j = k + 1; j < 12; ++j) {
-                const double ljk = __shfl_sync(FULL, lik, j);
-                const double upd = a[j] - lik * ljk;
-                const double scl = a[j] * inv;
-                a[j] = (lane > k) ? upd : ((lane == k) ? scl : a[j]);
-            }
-        }
-        // forward L z = gs, backward L^T y = z
         double z = (lane < 12) ? lm.gs[li] : 0.0;
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
-            const double zk = __shfl_sync(FULL, z * myinv, k);
-            const double upd = z - a[k] * zk;
-            z = (lane == k) ? zk : ((lane > k) ? upd : z);
+            const double dk = __shfl_sync(FULL, a[k], k);
+            const double zs = __shfl_sync(FULL, z, k);
+            ok = ok && (dk > 0.0) && (dk < DBL_MAX);
+            const double inv = rsqrt(dk);
+            const double lik = a[k] * inv;
+            const double zk = zs * inv;
+            const double lm_ik = (lane > k) ? lik : 0.0;  // masked column: zero on and above the diagonal
+            myinv = (lane == k) ? inv : myinv;
+            z = (lane == k) ? zk : z - lm_ik * zk;
+            a[k] = (lane >= k) ? lik : a[k];
+#pragma unroll
+            for (int j = k + 1; j < 12; ++j) a[j] -= lm_ik * __shfl_sync(FULL, lik, j);
         }
+        // backward L^T y = z: lane i uses L[k][i] = a[k] / L[i][i] for k > i
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a[k] = (lane < k) ? a[k] * myinv : 0.0;
 #pragma unroll
         for (int k = 11; k >= 0; --k) {
             const double yk = __shfl_sync(FULL, z * myinv, k);
-            const double upd = z - a[k] * yk;
-            z = (lane == k) ? yk : ((lane < k) ? upd : z);
+            z = (lane == k) ? yk : z - a[k] * yk;
         }
         const double step = (lane < 12) ? -z : 0.0;
         ok = ok && __all_sync(FULL, isfinite(step));
@@ -978,7 +1075,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
                 if (cmd == CMD_EVAL) {
                     cta_evaluate<false>(ps, sh, &cluster.map_shared_rank(&sh, k)->prob[k].slots[0][0], rank, csize, role, false, batch_counter, block_counter);
                     // the consumer's block sums went over DSMEM: order them before the signal
-                    fence_cluster();
+                    if (role.cidx == 0) fence_cluster();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(&sh.result_bar[k], (unsigned)k);
                 } else {
