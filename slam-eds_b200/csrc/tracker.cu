@@ -33,7 +33,6 @@ namespace {
 
 constexpr int TRK_THREADS = 512;  // one CTA per SM: 13-14 producer warps, 2 consumer warps, (1 leader warp)
 constexpr int TRK_WARPS = TRK_THREADS / 32;
-constexpr int NACC = 96;        // 78 (upper triangle of J^T J) + 12 (J^T r) + 6 padding
 constexpr int JLD = 20;         // floats per point row in shared memory (80 B: conflict-free 128-bit access)
 #ifndef EDS_N_CONS
 #define EDS_N_CONS 3
@@ -51,7 +50,7 @@ constexpr double kEps = 1e-05;  // PhotometricError.hpp:200
 enum { CMD_EVAL = 1, CMD_FINAL = 2, CMD_DONE = 3 };
 
 #ifdef EDS_TIMING
-__device__ unsigned long long g_timing[16];
+__device__ unsigned long long g_timing[32];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #endif
 enum { PHASE_INIT = 0, PHASE_CAND = 1 };
@@ -404,14 +403,15 @@ struct RowBlock {
         const int c = a + i;
         return (c < 12) ? tri_index(a, c) : 78 + a;
     }
-    static __device__ __forceinline__ float accumulate(const float (*rows)[JLD], int lane, float* acc) {
+    static __device__ __forceinline__ void load(const float (*rows)[JLD], int lane, float* v) {
         const float4* row = reinterpret_cast<const float4*>(&rows[lane][0]);
-        float v[16];
 #pragma unroll
         for (int q = R0 / 4; q < 4; ++q) {
             const float4 t = row[q];
             v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
         }
+    }
+    static __device__ __forceinline__ float accumulate(const float* v, float* acc) {
         int e = 0;
 #pragma unroll
         for (int a = R0; a < R1; ++a)
@@ -463,7 +463,6 @@ __device__ __forceinline__ Roles make_roles(bool hosts_leader) {
     r.etid = threadIdx.x;  // the leader warp is the last one: evaluator threads keep their index
     return r;
 }
-__device__ __forceinline__ void eval_barrier(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 template <bool RES_ONLY>
 __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base /* [MAX_BLOCKS][NSLOT] on the leader */,
@@ -547,13 +546,20 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
 #pragma unroll
                     for (int k = 0; k < 12; ++k) J[k] = 0.f;
                 }
+#ifdef EDS_TIMING
+                const long long te0 = clock64();
+#endif
                 mbar_wait(&sh.empty_bar[slot], (fill & 1u) ^ 1u);
+#ifdef EDS_TIMING
+                if (lane == 0 && rank == csize - 1) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
+#endif
                 float4* dst = reinterpret_cast<float4*>(&sh.ring[slot][lane][0]);
                 dst[0] = make_float4(J[0], J[1], J[2], J[3]);
                 dst[1] = make_float4(J[4], J[5], J[6], J[7]);
                 dst[2] = make_float4(J[8], J[9], J[10], J[11]);
                 dst[3] = make_float4(r, 0.f, 0.f, 0.f);
-                mbar_arrive(&sh.full_bar[slot]);  // 32 arrivals complete the phase
+                __syncwarp();  // all 32 rows are written: one elected arrival publishes the slot
+                if (lane == 0) mbar_arrive(&sh.full_bar[slot]);
                 b = b2; j = j2; gbase = gbase2; G = G2; valid = valid2; idx = idx2;
             }
             for (int bb = rank; bb < B; bb += csize) {  // the counters advance as they do for the consumers
@@ -587,9 +593,18 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
             for (int j = role.cidx; j < nb; j += N_CONS) {
                 const unsigned g = batch_counter + (unsigned)j;
                 const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
+#ifdef EDS_TIMING
+                const long long tw0 = clock64();
+#endif
                 mbar_wait(&sh.full_bar[slot], fill & 1u);
-                const float rr = ConsRows::accumulate(sh.ring[slot], lane, acc);
-                mbar_arrive(&sh.empty_bar[slot]);  // 32 arrivals free the slot
+#ifdef EDS_TIMING
+                if (lane == 0 && rank == csize - 1 && role.cidx == 0) { atomicAdd(&g_timing[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_timing[17], 1ull); }
+#endif
+                float v[16];
+                ConsRows::load(sh.ring[slot], lane, v);
+                __syncwarp();  // every lane has its row in registers: one elected arrival frees the slot
+                if (lane == 0) mbar_arrive(&sh.empty_bar[slot]);
+                const float rr = ConsRows::accumulate(v, acc);
                 s_acc += (double)rr * (double)rr;
             }
             reduce96(acc, lane);
@@ -942,8 +957,8 @@ __device__ __forceinline__ void load_problem(ProblemShared& ps, const ProblemDes
 
 __device__ __forceinline__ void init_barriers(CtaShared& sh, int evaluator_warps) {
     if (threadIdx.x < N_SLOTS) {
-        mbar_init(&sh.full_bar[threadIdx.x], 32);   // one producer warp fills a slot
-        mbar_init(&sh.empty_bar[threadIdx.x], 32);  // the consumer warp releases it
+        mbar_init(&sh.full_bar[threadIdx.x], 1);   // the elected lane of the producer warp that filled the slot
+        mbar_init(&sh.empty_bar[threadIdx.x], 1);  // the elected lane of the consumer warp that drained it
     }
     if (threadIdx.x < MAX_K) {
         mbar_init(&sh.ready_bar[threadIdx.x], 32);                          // the 32 lanes of the problem's leader warp
@@ -1091,6 +1106,9 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
         if (lane == 0 && rank == csize - 1) {
             if (role.cidx == 0) { atomicAdd(&g_timing[3], t_work); atomicAdd(&g_timing[4], t_wait); atomicAdd(&g_timing[5], n_work); }
             else if (tid == 0) { atomicAdd(&g_timing[13], t_work); atomicAdd(&g_timing[14], t_wait); }
+            else if (role.pidx == role.n_prod - 1) { atomicAdd(&g_timing[20], t_work); }
+            else if (role.pidx == 6) { atomicAdd(&g_timing[21], t_work); }
+            else if (role.cidx == 1) { atomicAdd(&g_timing[22], t_work); }
         }
 #endif
     }
@@ -1551,8 +1569,8 @@ void* edsgpu_tracker_state_dev(edsgpu_tracker* tr) { return tr ? (void*)tr->stat
 #ifdef EDS_TIMING
 void edsgpu_debug_timing(unsigned long long* out, int reset) {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, g_timing, sizeof(unsigned long long) * 16);
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_timing, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(out, g_timing, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_timing, z, sizeof(z)); }
 }
 #endif
 

@@ -33,7 +33,7 @@ def main():
     ctx.check(ctx.lib.edsgpu_event_frame_create_batch(ctx.h, frames.h, 0, S, None, xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p),
                                                       ps.ctypes.data_as(C.c_void_p), c["E"], edsgpu.DRAW_BILINEAR, 1, C.c_float(0.5), None))
     ctx.synchronize()
-    out = (C.c_ulonglong * 16)()
+    out = (C.c_ulonglong * 32)()
     for rep in range(3):
         for s, t in enumerate(trackers):
             x0 = data[s % n_sc][1][(s // n_sc) % n_win]["x_init"]
@@ -49,6 +49,8 @@ def main():
     m = max(t[5], 1)
     print("last CTA of each cluster, per visit [us]: consumer work %.2f wait %.2f | producer 0 work %.2f wait %.2f  (%d visits)" % (
         t[3] / m / 1e3, t[4] / m / 1e3, t[13] / m / 1e3, t[14] / m / 1e3, m))
+    print("  producer 6 work %.2f, last producer work %.2f, consumer 1 work %.2f | consumer 0 wait-full %.0f cycles/batch, producers wait-empty %.0f cycles/batch" % (
+        t[21] / m / 1e3, t[20] / m / 1e3, t[22] / m / 1e3, t[16] / max(t[17], 1), t[18] / max(t[19], 1)))
     k = max(t[10], 1)
     print("leader step parts [us]: tree %.2f  decide %.2f  solve %.2f  plus %.2f  publish %.2f (steps %d)" % (
         t[6] / k / 1e3, t[7] / k / 1e3, t[8] / k / 1e3, t[9] / k / 1e3, t[15] / k / 1e3, k))
