@@ -245,13 +245,16 @@ def run_native(args):
     n_sc, n_win = len(data), len(data[0][1])
     # sequence s follows scene s % n_sc, starting at window (s // n_sc) % n_win
     kfs_dev = [edsgpu.KeyFrame(ctx, kf, NUM_BLOCKS) for kf, _ in data]
-    frames = edsgpu.Frames(ctx, H, W, S)
+    # two banks of S frame slots: the library builds event frames on its own stream, so the frames of window
+    # k+1 (bank (k+1)&1) are built while window k (bank k&1) is being solved
+    frames = edsgpu.Frames(ctx, H, W, 2 * S)
     trackers = []
     for s in range(S):
         t = edsgpu.Tracker(ctx, num_blocks=NUM_BLOCKS, loss_type=edsgpu.LOSS_HUBER, loss_param=TAU0, max_iterations=MAX_ITER,
                            function_tolerance=1e-6, loss_param_method=edsgpu.LOSS_PARAM_MAD)
         trackers.append(t)
-    batch = edsgpu.TrackerBatch(ctx, trackers, [kfs_dev[s % n_sc] for s in range(S)], frames, 0)
+    banks = [edsgpu.TrackerBatch(ctx, trackers, [kfs_dev[s % n_sc] for s in range(S)], frames, bank * S) for bank in (0, 1)]
+    batch = banks[0]
 
     def reset_states():
         for s, t in enumerate(trackers):
@@ -272,16 +275,31 @@ def run_native(args):
     states_dev = torch.zeros(S, 14, dtype=torch.float64, device=dev)
     states_host = torch.zeros(S, 14, dtype=torch.float64).pin_memory()
 
-    def step_device(k):
+    def create_device(k):
         dx, dy, dp = dev_ev[k % n_win]
-        edsgpu.event_frames_batch_dev(ctx, frames, 0, S, dx.data_ptr(), dy.data_ptr(), dp.data_ptr(), E)
-        batch.optimize()
+        edsgpu.event_frames_batch_dev(ctx, frames, (k & 1) * S, S, dx.data_ptr(), dy.data_ptr(), dp.data_ptr(), E)
+
+    def run_device(first, n, events=None):
+        """n steps, inputs resident in HBM; one step = event frames of window k + batched LM solve + MAD.
+        Software-pipelined like the streaming front end: window k+1's frames are queued before window k's solve."""
+        create_device(first)
+        for i in range(n):
+            k = first + i
+            if i + 1 < n:
+                create_device(k + 1)
+            if events is not None:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+            ctx.check(ctx.lib.edsgpu_batch_optimize(banks[k & 1].h))  # track_lm_kernel + mad_kernel
+            if events is not None:
+                b.record(stream)
+                events.append((a, b))
 
     def issue_create(k):
         # host-facing C ABI with HOST (pinned) buffers: asynchronous, H2D on the library's copy stream
         hx, hy, hp = host_ev[k % n_win]
         ctx.check(ctx.lib.edsgpu_event_frame_create_batch(
-            ctx.h, frames.h, 0, S, None, edsgpu.C.c_void_p(hx.data_ptr()), edsgpu.C.c_void_p(hy.data_ptr()),
+            ctx.h, frames.h, (k & 1) * S, S, None, edsgpu.C.c_void_p(hx.data_ptr()), edsgpu.C.c_void_p(hy.data_ptr()),
             edsgpu.C.c_void_p(hp.data_ptr()), E, edsgpu.DRAW_BILINEAR, 1, edsgpu.C.c_float(0.5), None))
 
     states_host2 = [states_host, torch.zeros(S, 14, dtype=torch.float64).pin_memory()]
@@ -294,12 +312,12 @@ def run_native(args):
         issue_create(first)
         for i in range(n):
             k = first + i
-            batch.optimize()
-            batch.pack_states_dev(states_dev.data_ptr())
-            states_host2[i & 1].copy_(states_dev, non_blocking=True)
-            done_evt[i & 1].record(stream)
             if i + 1 < n:
                 issue_create(k + 1)
+            banks[k & 1].optimize()
+            banks[k & 1].pack_states_dev(states_dev.data_ptr())
+            states_host2[i & 1].copy_(states_dev, non_blocking=True)
+            done_evt[i & 1].record(stream)
             done_evt[i & 1].synchronize()  # step k's result is on the host
 
     def barrier():
@@ -309,8 +327,7 @@ def run_native(args):
 
     # ---- device-resident timing (value) ------------------------------------------------
     reset_states()
-    for k in range(args.warmup):
-        step_device(k)
+    run_device(0, args.warmup)
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -319,14 +336,7 @@ def run_native(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lm_events = []
     ev0.record(stream)
-    for k in range(args.steps):
-        dx, dy, dp = dev_ev[(args.warmup + k) % n_win]
-        edsgpu.event_frames_batch_dev(ctx, frames, 0, S, dx.data_ptr(), dy.data_ptr(), dp.data_ptr(), E)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        ctx.check(ctx.lib.edsgpu_batch_optimize(batch.h))  # track_lm_kernel + mad_kernel
-        b.record(stream)
-        lm_events.append((a, b))
+    run_device(args.warmup, args.steps, lm_events)
     ev1.record(stream)
     barrier()
     launches = ctx.launches - launches0

@@ -16,6 +16,7 @@ struct edsgpu_ctx {
     bool own_stream = false;
     int num_sms = 0;
     int64_t launches = 0;
+    std::vector<struct edsgpu_frames*> frames_list;  // their build streams are part of edsgpu_synchronize()
     int lm_clusters[4] = {0, 0, 0, 0};  // co-resident clusters of 1/2/4/8 tracker CTAs (0 = not queried yet)
     std::string last_error;
     // pinned staging (grown on demand) for host-facing entry points

@@ -46,6 +46,7 @@ edsgpu_status edsgpu_synchronize(edsgpu_ctx* ctx) {
     if (!ctx) return EDSGPU_INVALID_ARGUMENT;
     DeviceGuard g(ctx->device);
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (edsgpu_frames* fr : ctx->frames_list) EDS_CUDA(ctx, cudaStreamSynchronize(fr->build_stream));  // event frames are built on their own stream
     return EDSGPU_OK;
 }
 

@@ -208,13 +208,22 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
                             const uint16_t* x_dev, const uint16_t* y_dev, const uint8_t* pol_dev, int E, int mode, int use_exp, float sigma) {
     const int H = fr->H, W = fr->W;
     const size_t npix = (size_t)H * W;
-    EDS_CUDA(ctx, cudaMemsetAsync(fr->acc + (size_t)first_slot * npix, 0, sizeof(long long) * npix * count, ctx->stream));
+    cudaStream_t bs = fr->build_stream;
+    {   // wait for the last readers of the slots about to be overwritten
+        cudaEvent_t prev = nullptr;
+        for (int s = first_slot; s < first_slot + count; ++s) {
+            cudaEvent_t e = fr->slot_read[s];
+            if (e && e != prev) EDS_CUDA(ctx, cudaStreamWaitEvent(bs, e, 0));
+            prev = e;
+        }
+    }
+    EDS_CUDA(ctx, cudaMemsetAsync(fr->acc + (size_t)first_slot * npix, 0, sizeof(long long) * npix * count, bs));
     {
         int threads = 256;
         int bx = (E + threads - 1) / threads;
         bx = max(1, min(bx, 4 * ctx->num_sms));
         dim3 grid(bx, count);
-        scatter_events_kernel<<<grid, threads, 0, ctx->stream>>>(x_dev, y_dev, pol_dev, E, H, W, lut ? lut->mapx : nullptr,
+        scatter_events_kernel<<<grid, threads, 0, bs>>>(x_dev, y_dev, pol_dev, E, H, W, lut ? lut->mapx : nullptr,
                                                                   lut ? lut->mapy : nullptr, mode, use_exp,
                                                                   fr->acc + (size_t)first_slot * npix);
         ctx->launches++;
@@ -230,12 +239,18 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
             k1 = 1.0 / sum;
         }
         dim3 grid((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, count);
-        blur_norm_kernel<false><<<grid, BLUR_THREADS, 0, ctx->stream>>>(fr->acc, H, W, k0, k1, fr->surf_dev, fr->partials, fr->tickets,
+        blur_norm_kernel<false><<<grid, BLUR_THREADS, 0, bs>>>(fr->acc, H, W, k0, k1, fr->surf_dev, fr->partials, fr->tickets,
                                                                          fr->norms, first_slot, nullptr, nullptr);
         ctx->launches++;
         EDS_CUDA(ctx, cudaGetLastError());
         fr->k0 = k0;
         fr->k1 = k1;
+    }
+    {   // readers of these slots wait for this build
+        cudaEvent_t e = fr->built_pool[fr->built_next];
+        fr->built_next = (fr->built_next + 1) % edsgpu_frames::kEventPool;
+        EDS_CUDA(ctx, cudaEventRecord(e, bs));
+        for (int s = first_slot; s < first_slot + count; ++s) fr->slot_built[s] = e;
     }
     return EDSGPU_OK;
 }
@@ -245,6 +260,7 @@ edsgpu_status read_image64(edsgpu_ctx* ctx, const edsgpu_frames* fr, int slot, b
     const int H = fr->H, W = fr->W;
     const size_t npix = (size_t)H * W;
     edsgpu_status st = edsgpu_ensure_scratch(ctx, npix * sizeof(double));
+    if (st == EDSGPU_OK) st = edsgpu_frames_wait_built(fr, slot, 1, ctx->stream);
     if (st != EDSGPU_OK) return st;
     dim3 grid((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, 1);
     blur_norm_kernel<true><<<grid, BLUR_THREADS, 0, ctx->stream>>>(fr->acc, H, W, fr->k0, fr->k1, nullptr, nullptr, nullptr, nullptr, slot,
@@ -252,11 +268,32 @@ edsgpu_status read_image64(edsgpu_ctx* ctx, const edsgpu_frames* fr, int slot, b
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
     EDS_CUDA(ctx, cudaMemcpyAsync(host_out, ctx->scratch, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    st = edsgpu_frames_mark_read(fr, slot, 1, ctx->stream);
+    if (st != EDSGPU_OK) return st;
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EDSGPU_OK;
 }
 
 }  // namespace
+
+edsgpu_status edsgpu_frames_wait_built(const edsgpu_frames* fr, int first, int count, cudaStream_t stream) {
+    cudaEvent_t prev = nullptr;
+    for (int s = first; s < first + count; ++s) {
+        cudaEvent_t e = fr->slot_built[s];
+        if (e && e != prev) EDS_CUDA(fr->ctx, cudaStreamWaitEvent(stream, e, 0));
+        prev = e;
+    }
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_frames_mark_read(const edsgpu_frames* cfr, int first, int count, cudaStream_t stream) {
+    edsgpu_frames* fr = const_cast<edsgpu_frames*>(cfr);  // bookkeeping only: the images are not touched
+    cudaEvent_t e = fr->read_pool[fr->read_next];
+    fr->read_next = (fr->read_next + 1) % edsgpu_frames::kEventPool;
+    EDS_CUDA(fr->ctx, cudaEventRecord(e, stream));
+    for (int s = first; s < first + count; ++s) fr->slot_read[s] = e;
+    return EDSGPU_OK;
+}
 
 extern "C" {
 
@@ -330,6 +367,14 @@ edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int c
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->tickets, 0, sizeof(unsigned) * capacity, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->norms, 0, sizeof(double) * 2 * capacity, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->acc, 0, sizeof(long long) * npix * capacity, ctx->stream);
+    fr->slot_built.assign(capacity, nullptr);
+    fr->slot_read.assign(capacity, nullptr);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&fr->build_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fr->order_evt, cudaEventDisableTiming);
+    for (int i = 0; i < edsgpu_frames::kEventPool && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&fr->built_pool[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fr->read_pool[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&fr->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fr->copied, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&fr->stage_free[i], cudaEventDisableTiming);
@@ -339,6 +384,7 @@ edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int c
         edsgpu_frames_destroy(fr);
         return edsgpu_fail(ctx, e == cudaErrorMemoryAllocation ? EDSGPU_OUT_OF_MEMORY : EDSGPU_CUDA_ERROR, cudaGetErrorString(e));
     }
+    ctx->frames_list.push_back(fr);
     *out = fr;
     return EDSGPU_OK;
 }
@@ -347,6 +393,17 @@ void edsgpu_frames_destroy(edsgpu_frames* fr) {
     if (!fr) return;
     DeviceGuard g(fr->ctx->device);
     cudaStreamSynchronize(fr->ctx->stream);
+    {
+        auto& list = fr->ctx->frames_list;
+        for (size_t i = 0; i < list.size(); ++i)
+            if (list[i] == fr) { list.erase(list.begin() + i); break; }
+    }
+    if (fr->build_stream) { cudaStreamSynchronize(fr->build_stream); cudaStreamDestroy(fr->build_stream); }
+    if (fr->order_evt) cudaEventDestroy(fr->order_evt);
+    for (int i = 0; i < edsgpu_frames::kEventPool; ++i) {
+        if (fr->built_pool[i]) cudaEventDestroy(fr->built_pool[i]);
+        if (fr->read_pool[i]) cudaEventDestroy(fr->read_pool[i]);
+    }
     if (fr->acc) cudaFree(fr->acc);
     for (int i = 0; i < fr->capacity && fr->arrays; ++i) {
         if (fr->tex[i]) cudaDestroyTextureObject(fr->tex[i]);
@@ -387,6 +444,9 @@ edsgpu_status edsgpu_event_frame_create_batch_dev(edsgpu_ctx* ctx, edsgpu_frames
     if (st != EDSGPU_OK) return st;
     EDS_REQUIRE(ctx, x_dev && y_dev && polarity_dev, "event_frame: null event arrays");
     DeviceGuard g(ctx->device);
+    // the device arrays were produced by work the caller queued on the context's stream
+    EDS_CUDA(ctx, cudaEventRecord(frames->order_evt, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamWaitEvent(frames->build_stream, frames->order_evt, 0));
     return launch_frames(ctx, frames, first_slot, count, lut, x_dev, y_dev, polarity_dev, num_events, mode, use_exp_weights, sigma);
 }
 
@@ -400,13 +460,13 @@ edsgpu_status edsgpu_event_frame_create_batch(edsgpu_ctx* ctx, edsgpu_frames* fr
     DeviceGuard g(ctx->device);
     // device staging for the events: [x u16 | y u16 | pol u8] per batch, double-buffered.  The copies run
     // on the frames' copy stream and only wait for the kernels that last READ the same staging buffer,
-    // so the H2D transfer of this batch overlaps whatever the compute stream is still doing (e.g. the LM
-    // solve of the previous batch); the compute stream then waits for the copy.
+    // so the H2D transfer of this batch overlaps whatever the other streams are still doing (e.g. the LM
+    // solve of the previous batch); the build stream then waits for the copy.
     const size_t n = (size_t)count * num_events;
     const size_t off_y = align_up(n * 2, 256), off_p = off_y + align_up(n * 2, 256), total = off_p + align_up(n, 256);
     const int buf = (frames->stage_idx ^= 1);
     if (frames->events_bytes[buf] < total) {
-        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        EDS_CUDA(ctx, cudaStreamSynchronize(frames->build_stream));
         EDS_CUDA(ctx, cudaStreamSynchronize(frames->copy_stream));
         if (frames->events_dev[buf]) cudaFree(frames->events_dev[buf]);
         frames->events_dev[buf] = nullptr;
@@ -423,13 +483,14 @@ edsgpu_status edsgpu_event_frame_create_batch(edsgpu_ctx* ctx, edsgpu_frames* fr
     EDS_CUDA(ctx, cudaMemcpyAsync(d + off_y, y, n * 2, cudaMemcpyHostToDevice, cs));
     EDS_CUDA(ctx, cudaMemcpyAsync(d + off_p, polarity, n, cudaMemcpyHostToDevice, cs));
     EDS_CUDA(ctx, cudaEventRecord(frames->copied, cs));
-    EDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, frames->copied, 0));
+    EDS_CUDA(ctx, cudaStreamWaitEvent(frames->build_stream, frames->copied, 0));
     st = launch_frames(ctx, frames, first_slot, count, lut, (const uint16_t*)d, (const uint16_t*)(d + off_y), (const uint8_t*)(d + off_p),
                        num_events, mode, use_exp_weights, sigma);
     if (st != EDSGPU_OK) return st;
-    EDS_CUDA(ctx, cudaEventRecord(frames->stage_free[buf], ctx->stream));
+    EDS_CUDA(ctx, cudaEventRecord(frames->stage_free[buf], frames->build_stream));
     if (norms_out) {
         st = edsgpu_ensure_pinned(ctx, sizeof(double) * 2 * count);
+        if (st == EDSGPU_OK) st = edsgpu_frames_wait_built(frames, first_slot, count, ctx->stream);
         if (st != EDSGPU_OK) return st;
         EDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, frames->norms + 2 * first_slot, sizeof(double) * 2 * count, cudaMemcpyDeviceToHost, ctx->stream));
         EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -472,6 +533,8 @@ edsgpu_status edsgpu_frames_read(edsgpu_ctx* ctx, const edsgpu_frames* frames, i
         if (st != EDSGPU_OK) return st;
     }
     if (norm_out) {
+        edsgpu_status st = edsgpu_frames_wait_built(frames, slot, 1, ctx->stream);
+        if (st != EDSGPU_OK) return st;
         EDS_CUDA(ctx, cudaMemcpyAsync(norm_out, frames->norms + 2 * slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -483,7 +546,11 @@ edsgpu_status edsgpu_frames_read_accumulator(edsgpu_ctx* ctx, const edsgpu_frame
     EDS_REQUIRE(ctx, frames && acc_out && slot >= 0 && slot < frames->capacity, "frames_read_accumulator: bad arguments");
     DeviceGuard g(ctx->device);
     const size_t npix = (size_t)frames->H * frames->W;
+    edsgpu_status st = edsgpu_frames_wait_built(frames, slot, 1, ctx->stream);
+    if (st != EDSGPU_OK) return st;
     EDS_CUDA(ctx, cudaMemcpyAsync(acc_out, frames->acc + (size_t)slot * npix, sizeof(int64_t) * npix, cudaMemcpyDeviceToHost, ctx->stream));
+    st = edsgpu_frames_mark_read(frames, slot, 1, ctx->stream);
+    if (st != EDSGPU_OK) return st;
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EDSGPU_OK;
 }

@@ -1,6 +1,7 @@
 // Device-resident objects shared between event_frame.cu and tracker.cu.
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 struct edsgpu_lut {
     edsgpu_ctx* ctx = nullptr;
@@ -35,4 +36,20 @@ struct edsgpu_frames {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied = nullptr;
     cudaEvent_t stage_free[2] = {nullptr, nullptr};
+    // Event frames are BUILT on their own stream, so that the frames of the next windows can be built
+    // while the context's stream is still solving the current ones (on the SMs the solve leaves free).
+    // Ordering is per slot: a build waits for the last reader of the slots it overwrites, a reader
+    // waits for the last build of the slots it samples.  Events come from small round-robin pools; a
+    // recycled event can only over-synchronise.
+    static constexpr int kEventPool = 8;
+    cudaStream_t build_stream = nullptr;
+    cudaEvent_t order_evt = nullptr;  // "everything the caller queued on the context's stream so far"
+    cudaEvent_t built_pool[kEventPool] = {}, read_pool[kEventPool] = {};
+    int built_next = 0, read_next = 0;
+    std::vector<cudaEvent_t> slot_built, slot_read;  // [capacity] last build / last reader, nullptr = none
 };
+
+// make `stream` wait for the last build of slots [first, first + count)
+edsgpu_status edsgpu_frames_wait_built(const edsgpu_frames* fr, int first, int count, cudaStream_t stream);
+// record, after a reader of slots [first, first + count) has been queued on `stream`, that later builds must wait for it
+edsgpu_status edsgpu_frames_mark_read(const edsgpu_frames* fr, int first, int count, cudaStream_t stream);

@@ -1291,6 +1291,12 @@ __global__ void __launch_bounds__(256) kf_prepare_kernel(const double* __restric
     }
 }
 
+// 14-double state record (px qx vx tau) of every problem of a batch, contiguous
+__global__ void pack_states_kernel(const ProblemDesc* __restrict__ problems, int count, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 14 * count) out[i] = problems[i / 14].state[i % 14];
+}
+
 __global__ void float_to_double_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (double)in[i];
@@ -1327,6 +1333,8 @@ struct edsgpu_batch {
     edsgpu_ctx* ctx = nullptr;
     int count = 0;
     LaunchShape shape{1, 1, 0};
+    const edsgpu_frames* frames = nullptr;  // slots first_slot .. first_slot + count - 1
+    int first_slot = 0;
     ProblemDesc* desc = nullptr;  // device
     std::vector<edsgpu_tracker*> trackers;
 };
@@ -1600,6 +1608,8 @@ edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* tracke
     b->ctx = ctx;
     b->count = count;
     b->shape = pick_shape(ctx, count, B);
+    b->frames = frames;
+    b->first_slot = first_slot;
     b->trackers.assign(trackers, trackers + count);
     std::vector<ProblemDesc> hd(count);
     for (int i = 0; i < count; ++i) hd[i] = make_desc(trackers[i], keyframes[i], frames, first_slot + i);
@@ -1623,7 +1633,12 @@ edsgpu_status edsgpu_batch_optimize(edsgpu_batch* b) {
     if (!b) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = b->ctx;
     DeviceGuard g(ctx->device);
-    edsgpu_status st = launch_cluster(ctx, track_lm_kernel, b->shape.nclusters, b->shape.csize, (const ProblemDesc*)b->desc, b->count, b->shape.K);
+    // the event frames are built on their own stream: wait for the builds of our slots only
+    edsgpu_status st = edsgpu_frames_wait_built(b->frames, b->first_slot, b->count, ctx->stream);
+    if (st != EDSGPU_OK) return st;
+    st = launch_cluster(ctx, track_lm_kernel, b->shape.nclusters, b->shape.csize, (const ProblemDesc*)b->desc, b->count, b->shape.K);
+    if (st != EDSGPU_OK) return st;
+    st = edsgpu_frames_mark_read(b->frames, b->first_slot, b->count, ctx->stream);
     if (st != EDSGPU_OK) return st;
     mad_kernel<<<b->count, MAD_THREADS, 0, ctx->stream>>>((const ProblemDesc*)b->desc);
     ctx->launches++;
@@ -1635,8 +1650,10 @@ edsgpu_status edsgpu_batch_pack_states_dev(edsgpu_batch* b, double* states_dev) 
     if (!b || !states_dev) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = b->ctx;
     DeviceGuard g(ctx->device);
-    for (int i = 0; i < b->count; ++i)
-        EDS_CUDA(ctx, cudaMemcpyAsync(states_dev + 14 * i, b->trackers[i]->state, 14 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    const int n = 14 * b->count;
+    pack_states_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const ProblemDesc*)b->desc, b->count, states_dev);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
     return EDSGPU_OK;
 }
 
@@ -1740,7 +1757,9 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_desc, hd, sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
     EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_state, hstate, 14 * 8, cudaMemcpyHostToDevice, ctx->stream));
     const int csize = pick_shape(ctx, 1, kf->dev.B).csize;
-    st = launch_cluster(ctx, track_eval_kernel, 1, csize, (const ProblemDesc*)(ds + o_desc), 1);
+    st = edsgpu_frames_wait_built(frames, slot, 1, ctx->stream);
+    if (st == EDSGPU_OK) st = launch_cluster(ctx, track_eval_kernel, 1, csize, (const ProblemDesc*)(ds + o_desc), 1);
+    if (st == EDSGPU_OK) st = edsgpu_frames_mark_read(frames, slot, 1, ctx->stream);
     if (st != EDSGPU_OK) return st;
     double* hev = (double*)(hp + sizeof(ProblemDesc) + 14 * 8);
     EDS_CUDA(ctx, cudaMemcpyAsync(hev, ds + o_eval, 157 * 8, cudaMemcpyDeviceToHost, ctx->stream));
