@@ -63,6 +63,7 @@ struct KfDev {
     const double* kpz;
     const double* A;     // [B][21] upper triangle of sum g g^T per residual block
     int N, B, H, W;
+    int ne;              // N / B: points per residual block (the last block also takes the remainder)
     double fx, fy, cx, cy;
 };
 
@@ -235,8 +236,9 @@ __device__ __forceinline__ void project_axis(double f, double c, double p, doubl
     const float est = fmaf((float)f * pf, izf, (float)c);
     int q = max(-6, min(__float2int_rd(est), limit + 5));  // saturating conversion, NaN -> 0
     float t = (float)fma(f, p, (c - (double)q) * pz) * izf;
-    if (t < 0.f) { q -= 1; t += 1.f; }
-    else if (t >= 1.f) { q += 1; t -= 1.f; }
+    const int below = t < 0.f ? 1 : 0, above = t >= 1.f ? 1 : 0;  // at most one of them
+    q += above - below;
+    t += (float)(below - above);
     cell = max(-4, min(q, limit + 3));
     frac = (cell == q) ? t : 0.f;
 }
@@ -473,7 +475,7 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
     const EvalConst& ec = ps.ec;
     const float inv_norm = (float)P.norms[1];
     const double loss_a = ps.loss_a;
-    const int ne = kf.N / kf.B;
+    const int ne = kf.ne;
     // The texture handle is read from shared memory, which the compiler cannot prove warp-uniform: it
     // would wrap every fetch in a loop over the distinct handles of the warp.  A warp-wide OR leaves
     // the value unchanged and lands in a uniform register.
@@ -490,51 +492,64 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
             // every block has `ne` points except the last one, which also takes the remainder (Tracker.cpp:178-190)
             const int n_last = kf.N - (B - 1) * ne;
             const int nb_reg = (ne + 31) >> 5, nb_last = (n_last + 31) >> 5;
-            auto points_of = [&](int b) { return (b + 1 == B) ? n_last : ne; };
-            auto settle = [&](int& b, int& j, unsigned& gbase) {  // move (b, j) to the block that holds batch j
-                while (b < B) {
-                    const int nbb = (b + 1 == B) ? nb_last : nb_reg;
-                    if (j < nbb) break;
-                    j -= nbb; gbase += (unsigned)nbb; b += csize;
+            // iterator over this warp's batches: block b, batch j of nbb in it (n_pts points), ring slot and phase
+            struct Cursor { int b, j, nbb, n_pts; unsigned slot, phase; };
+            auto enter = [&](Cursor& c) {  // move to the block that holds batch j (rare: once per block)
+                while (c.b < B && c.j >= c.nbb) {
+                    c.j -= c.nbb;
+                    c.b += csize;
+                    c.nbb = (c.b + 1 == B) ? nb_last : nb_reg;
+                    c.n_pts = (c.b + 1 == B) ? n_last : ne;
                 }
             };
-            int b = rank, j = (role.pidx + n_prod - (int)(batch_counter % (unsigned)n_prod)) % n_prod;
-            unsigned gbase = batch_counter;
-            settle(b, j, gbase);
+            auto advance = [&](Cursor& c) {  // consecutive batches of a warp are n_prod apart in the running numbering
+                c.j += n_prod;
+                c.slot += (unsigned)n_prod;
+                if (c.slot >= (unsigned)N_SLOTS) { c.slot -= N_SLOTS; c.phase ^= 1u; }
+                if (c.j >= c.nbb) enter(c);
+            };
+            Cursor cur;
+            cur.b = rank;
+            cur.j = (role.pidx + n_prod - (int)(batch_counter % (unsigned)n_prod)) % n_prod;
+            cur.nbb = (rank + 1 == B) ? nb_last : nb_reg;
+            cur.n_pts = (rank + 1 == B) ? n_last : ne;
+            {
+                const unsigned g0 = batch_counter + (unsigned)cur.j;
+                cur.slot = g0 % N_SLOTS;
+                cur.phase = (g0 / N_SLOTS) & 1u;
+            }
+            enter(cur);
             PointGeo G = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             bool valid = false;
             int idx = 0;
-            if (b < B) {
-                const int i = (j << 5) + lane;
-                valid = i < points_of(b);
-                idx = b * ne + i;
+            if (cur.b < B) {
+                const int i = (cur.j << 5) + lane;
+                valid = i < cur.n_pts;
+                idx = cur.b * ne + i;
                 if (valid) point_geometry(kf, ec, idx, G);
             }
-            while (b < B) {
+            while (cur.b < B) {
                 // current batch: taps and gradient record in flight
                 const Taps T = fetch_taps(frame, G.col, G.row);
                 float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 float2 dw = make_float2(0.f, 0.f);
                 if (valid) { g4 = __ldg(&kf.gxy[idx]); dw = __ldg(&kf.dw[idx]); }
                 // next batch: geometry
-                int b2 = b, j2 = j + n_prod;
-                unsigned gbase2 = gbase;
-                settle(b2, j2, gbase2);
+                Cursor nxt = cur;
+                advance(nxt);
                 PointGeo G2 = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 bool valid2 = false;
                 int idx2 = 0;
-                if (b2 < B) {
-                    const int i2 = (j2 << 5) + lane;
-                    valid2 = i2 < points_of(b2);
-                    idx2 = b2 * ne + i2;
+                if (nxt.b < B) {
+                    const int i2 = (nxt.j << 5) + lane;
+                    valid2 = i2 < nxt.n_pts;
+                    idx2 = nxt.b * ne + i2;
                     if (valid2) point_geometry(kf, ec, idx2, G2);
                 }
                 // current batch: finish and hand over
-                const unsigned g = gbase + (unsigned)j;
-                const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
                 float J[12], r = 0.f;
                 if (valid) {
-                    point_finish<true>(kf, ec, ec.blk[b], inv_norm, G, T, g4, dw, J, r);
+                    point_finish<true>(kf, ec, ec.blk[cur.b], inv_norm, G, T, g4, dw, J, r);
                     if (write_residuals) {
                         P.residuals[idx] = r;
                         if (P.jac_out) {
@@ -546,10 +561,11 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
 #pragma unroll
                     for (int k = 0; k < 12; ++k) J[k] = 0.f;
                 }
+                const unsigned slot = cur.slot;
 #ifdef EDS_TIMING
                 const long long te0 = clock64();
 #endif
-                mbar_wait(&sh.empty_bar[slot], (fill & 1u) ^ 1u);
+                mbar_wait(&sh.empty_bar[slot], cur.phase ^ 1u);
 #ifdef EDS_TIMING
                 if (lane == 0 && rank == csize - 1) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
 #endif
@@ -560,7 +576,7 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                 dst[3] = make_float4(r, 0.f, 0.f, 0.f);
                 __syncwarp();  // all 32 rows are written: one elected arrival publishes the slot
                 if (lane == 0) mbar_arrive(&sh.full_bar[slot]);
-                b = b2; j = j2; gbase = gbase2; G = G2; valid = valid2; idx = idx2;
+                cur = nxt; G = G2; valid = valid2; idx = idx2;
             }
             for (int bb = rank; bb < B; bb += csize) {  // the counters advance as they do for the consumers
                 batch_counter += (unsigned)((bb + 1 == B) ? nb_last : nb_reg);
@@ -590,13 +606,18 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
 #pragma unroll
             for (int i = 0; i < 96; ++i) acc[i] = 0.f;
             double s_acc = 0.0;  // sum of r^2 in fp64 (the cost decides accept / reject and the tolerances)
-            for (int j = role.cidx; j < nb; j += N_CONS) {
-                const unsigned g = batch_counter + (unsigned)j;
-                const unsigned slot = g % N_SLOTS, fill = g / N_SLOTS;
+            unsigned slot, phase;
+            {
+                const unsigned g0 = batch_counter + (unsigned)role.cidx;
+                slot = g0 % N_SLOTS;
+                phase = (g0 / N_SLOTS) & 1u;
+            }
+            for (int j = role.cidx; j < nb; j += N_CONS, slot += N_CONS) {
+                if (slot >= (unsigned)N_SLOTS) { slot -= N_SLOTS; phase ^= 1u; }
 #ifdef EDS_TIMING
                 const long long tw0 = clock64();
 #endif
-                mbar_wait(&sh.full_bar[slot], fill & 1u);
+                mbar_wait(&sh.full_bar[slot], phase);
 #ifdef EDS_TIMING
                 if (lane == 0 && rank == csize - 1 && role.cidx == 0) { atomicAdd(&g_timing[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_timing[17], 1ull); }
 #endif
@@ -1475,6 +1496,7 @@ edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const doub
     d.kpx = (double*)(base + o_kx); d.kpy = (double*)(base + o_ky); d.kpz = (double*)(base + o_kz);
     d.A = (double*)(base + o_A);
     d.N = num_points; d.B = num_blocks; d.H = height; d.W = width;
+    d.ne = num_points / num_blocks;
     d.fx = fx; d.fy = fy; d.cx = cx; d.cy = cy;
     // stage the double arrays: pinned -> device scratch -> prepare kernel
     const size_t stage = N * 6 * sizeof(double);
