@@ -77,12 +77,18 @@ edsgpu_status edsgpu_event_frame_create(edsgpu_ctx* ctx, edsgpu_frames* frames, 
                                         int64_t* time_us_out, int64_t* delta_time_us_out, double* host_frame_out);
 
 /* `count` windows of num_events events each, into slots first_slot.. (x,y,polarity are
- * count*num_events long).  norms_out: count doubles or NULL.  Asynchronous if norms_out is NULL. */
+ * count*num_events long).  norms_out: count doubles or NULL.  Asynchronous if norms_out is NULL.
+ * Frames are BUILT on a stream of their own, ordered per slot against the library's readers
+ * (a build waits for the last optimize/evaluate/read of the slots it overwrites, those wait for
+ * the last build of the slots they use): with two banks of slots the frames of the next windows
+ * are built while the context's stream still solves the current ones.  edsgpu_synchronize()
+ * covers the build streams too. */
 edsgpu_status edsgpu_event_frame_create_batch(edsgpu_ctx* ctx, edsgpu_frames* frames, int first_slot, int count,
                                               const edsgpu_lut* lut, const uint16_t* x, const uint16_t* y,
                                               const uint8_t* polarity, int num_events, int mode, int use_exp_weights,
                                               float sigma, double* norms_out);
-/* same, events already in device memory; always asynchronous on the context stream. */
+/* same, events already in device memory; always asynchronous.  The build is ordered after
+ * everything queued on the context stream at the time of the call (the producer of the arrays). */
 edsgpu_status edsgpu_event_frame_create_batch_dev(edsgpu_ctx* ctx, edsgpu_frames* frames, int first_slot, int count,
                                                   const edsgpu_lut* lut, const uint16_t* x_dev, const uint16_t* y_dev,
                                                   const uint8_t* polarity_dev, int num_events, int mode,

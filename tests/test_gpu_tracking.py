@@ -285,6 +285,57 @@ def test_sequence_of_windows_carries_state(gpu_ctx, problems):
     tr.close(); kfd.close()
 
 
+def test_frames_built_ahead_in_two_banks_give_the_serial_result(gpu_ctx, problems):
+    """Event frames are built on their own stream: window k+1's frames (other bank of slots) are queued
+    before window k's solve and a bank is rebuilt while it may still be read.  Without any host
+    synchronisation in between, the per-slot ordering must give exactly the serial results."""
+    kf, wins = problems["davis240c"]
+    H, W, S, steps = kf["H"], kf["W"], 6, 5
+    E = len(wins[0]["x"])
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, 8)
+
+    def window(k):  # S sequences, each offset by one window
+        return [np.concatenate([wins[(k + s) % len(wins)][key] for s in range(S)]) for key in ("x", "y", "pol")]
+
+    def run(pipelined):
+        fr = edsgpu.Frames(gpu_ctx, H, W, 2 * S)
+        trs = [edsgpu.Tracker(gpu_ctx, num_blocks=8, max_iterations=8) for _ in range(S)]
+        for s, t in enumerate(trs):
+            x0 = wins[s % len(wins)]["x_init"]
+            t.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
+        banks = [edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * S, fr, b * S) for b in (0, 1)]
+        keep = []  # the host arrays are copy sources until the next synchronising call
+        out = []
+        if pipelined:
+            keep.append(window(0))
+            edsgpu.event_frames_batch(gpu_ctx, fr, 0, S, *keep[-1], E)
+            for k in range(steps):
+                if k + 1 < steps:
+                    keep.append(window(k + 1))
+                    edsgpu.event_frames_batch(gpu_ctx, fr, ((k + 1) & 1) * S, S, *keep[-1], E)
+                banks[k & 1].optimize()
+            gpu_ctx.synchronize()
+            out = banks[0].gather()[0]
+        else:
+            for k in range(steps):
+                edsgpu.event_frames_batch(gpu_ctx, fr, (k & 1) * S, S, *window(k), E)
+                gpu_ctx.synchronize()
+                banks[k & 1].optimize()
+                gpu_ctx.synchronize()
+            out = banks[0].gather()[0]
+        for b in banks:
+            b.close()
+        for t in trs:
+            t.close()
+        fr.close()
+        return out
+
+    serial = run(False)
+    for _ in range(3):
+        assert np.array_equal(run(True), serial)
+    kfd.close()
+
+
 def test_argument_validation(gpu_ctx, problems):
     kf, wins = problems["tiny"]
     with pytest.raises(edsgpu.EdsGpuError):
