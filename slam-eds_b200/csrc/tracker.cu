@@ -243,8 +243,11 @@ __device__ __forceinline__ void project_axis(double f, double c, double p, doubl
     frac = (cell == q) ? t : 0.f;
 }
 
-__device__ __forceinline__ void point_geometry(const KfDev& kf, const EvalConst& K, int idx, PointGeo& G) {
-    const double kx = __ldg(&kf.kpx[idx]), ky = __ldg(&kf.kpy[idx]), kz = __ldg(&kf.kpz[idx]);
+struct Kp { double x, y, z; };  // 3-D key-frame point (X,Y,1)/(idp+eps)
+__device__ __forceinline__ Kp load_kp(const KfDev& kf, int idx) { return Kp{__ldg(&kf.kpx[idx]), __ldg(&kf.kpy[idx]), __ldg(&kf.kpz[idx])}; }
+
+__device__ __forceinline__ void point_geometry(const KfDev& kf, const EvalConst& K, const Kp& kp, PointGeo& G) {
+    const double kx = kp.x, ky = kp.y, kz = kp.z;
     const double ax = K.R[0] * kx + K.R[1] * ky + K.R[2] * kz;
     const double ay = K.R[3] * kx + K.R[4] * ky + K.R[5] * kz;
     const double az = K.R[6] * kx + K.R[7] * ky + K.R[8] * kz;
@@ -332,7 +335,7 @@ template <bool WANT_J>
 __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, const float* __restrict__ bc,
                                            cudaTextureObject_t frame, float inv_norm, int idx, float* __restrict__ J, float& r) {
     PointGeo G;
-    point_geometry(kf, K, idx, G);
+    point_geometry(kf, K, load_kp(kf, idx), G);
     const Taps T = fetch_taps(frame, G.col, G.row);
     point_finish<WANT_J>(kf, K, bc, inv_norm, G, T, __ldg(&kf.gxy[idx]), __ldg(&kf.dw[idx]), J, r);
 }
@@ -519,33 +522,42 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                 cur.phase = (g0 / N_SLOTS) & 1u;
             }
             enter(cur);
-            PointGeo G = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            bool valid = false;
-            int idx = 0;
-            if (cur.b < B) {
-                const int i = (cur.j << 5) + lane;
-                valid = i < cur.n_pts;
-                idx = cur.b * ne + i;
-                if (valid) point_geometry(kf, ec, idx, G);
-            }
+            // pipeline state: `cur` has its geometry, `nxt` has its 3-D points loaded (two batches of loads in
+            // flight hide the L2 latency), the batch after `nxt` is loaded inside the loop
+            const PointGeo G0 = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const Kp kp0 = {0.0, 0.0, 1.0};
+            auto locate = [&](const Cursor& c, int& idx, bool& valid) {
+                const int i = (c.j << 5) + lane;
+                valid = (c.b < B) && (i < c.n_pts);
+                idx = c.b * ne + i;
+            };
+            PointGeo G = G0;
+            bool valid, valid2;
+            int idx, idx2;
+            locate(cur, idx, valid);
+            if (valid) point_geometry(kf, ec, load_kp(kf, idx), G);
+            Cursor nxt = cur;
+            if (cur.b < B) advance(nxt);
+            locate(nxt, idx2, valid2);
+            Kp kp2 = kp0;
+            if (valid2) kp2 = load_kp(kf, idx2);
             while (cur.b < B) {
                 // current batch: taps and gradient record in flight
                 const Taps T = fetch_taps(frame, G.col, G.row);
                 float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 float2 dw = make_float2(0.f, 0.f);
                 if (valid) { g4 = __ldg(&kf.gxy[idx]); dw = __ldg(&kf.dw[idx]); }
-                // next batch: geometry
-                Cursor nxt = cur;
-                advance(nxt);
-                PointGeo G2 = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                bool valid2 = false;
-                int idx2 = 0;
-                if (nxt.b < B) {
-                    const int i2 = (nxt.j << 5) + lane;
-                    valid2 = i2 < nxt.n_pts;
-                    idx2 = nxt.b * ne + i2;
-                    if (valid2) point_geometry(kf, ec, idx2, G2);
-                }
+                // batch after next: 3-D points in flight
+                Cursor nn = nxt;
+                if (nxt.b < B) advance(nn);
+                int idx3;
+                bool valid3;
+                locate(nn, idx3, valid3);
+                Kp kp3 = kp0;
+                if (valid3) kp3 = load_kp(kf, idx3);
+                // next batch: geometry from the points loaded one iteration ago
+                PointGeo G2 = G0;
+                if (valid2) point_geometry(kf, ec, kp2, G2);
                 // current batch: finish and hand over
                 float J[12], r = 0.f;
                 if (valid) {
@@ -577,6 +589,7 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                 __syncwarp();  // all 32 rows are written: one elected arrival publishes the slot
                 if (lane == 0) mbar_arrive(&sh.full_bar[slot]);
                 cur = nxt; G = G2; valid = valid2; idx = idx2;
+                nxt = nn; kp2 = kp3; valid2 = valid3; idx2 = idx3;
             }
             for (int bb = rank; bb < B; bb += csize) {  // the counters advance as they do for the consumers
                 batch_counter += (unsigned)((bb + 1 == B) ? nb_last : nb_reg);
@@ -763,11 +776,20 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
     for (int k = 0; k < 3; ++k) {
         const int e = lane + 32 * k;
         if (e < 91) {
+            // the tree is over MAX_BLOCKS leaves, missing blocks are zeros; with B <= 8 its first level only
+            // adds zeros, so the 8-leaf tree gives the same bits with half the loads
             double v[MAX_BLOCKS];
+            if (B <= MAX_BLOCKS / 2) {
 #pragma unroll
-            for (int b = 0; b < MAX_BLOCKS; ++b) v[b] = (b < B) ? sh.slots[b][e] : 0.0;
+                for (int b = 0; b < MAX_BLOCKS / 2; ++b) v[b] = (b < B) ? sh.slots[b][e] : 0.0;
+            } else {
 #pragma unroll
-            for (int w = MAX_BLOCKS / 2; w > 0; w >>= 1)
+                for (int b = 0; b < MAX_BLOCKS; ++b) v[b] = (b < B) ? sh.slots[b][e] : 0.0;
+#pragma unroll
+                for (int b = 0; b < MAX_BLOCKS / 2; ++b) v[b] += v[b + MAX_BLOCKS / 2];
+            }
+#pragma unroll
+            for (int w = MAX_BLOCKS / 4; w > 0; w >>= 1)
 #pragma unroll
                 for (int b = 0; b < w; ++b) v[b] += v[b + w];
             sh.sum[e] = v[0];
@@ -881,12 +903,12 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
         // lane i < 12 owns row i of the damped matrix (a) and of the un-damped one (h)
         double a[12], h[12];
         const int li = lane < 12 ? lane : 0;
+        const double damping = lm.diag[li] / radius;  // D^2 of this lane's diagonal entry
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
             const double v = lm.Hs[li <= j ? tri_index(li, j) : tri_index(j, li)];
             h[j] = (lane < 12) ? v : 0.0;
-            a[j] = h[j];
-            if (j == lane) a[j] += lm.diag[li] / radius;
+            a[j] = (j == lane) ? h[j] + damping : h[j];
         }
         // Right-looking Cholesky in registers with the forward substitution L z = gs folded in.  After
         // step k lane i >= k holds L[i][k] in a[k]; lane k keeps its row j > k UNSCALED (L[k][k] L[j][k]),
