@@ -234,6 +234,36 @@ edsgpu_status edsgpu_ba_sc_stitch(edsgpu_ba* ba, double* H, double* b);
 /* EFResidual::JpJdF of every residual (R x 8). */
 edsgpu_status edsgpu_ba_get_jpjd(edsgpu_ba* ba, float* JpJdF_out);
 
+/* ---- the feeder on the device --------------------------------------
+ * PointFrameResidual::linearize (src/tracking/Residuals.cpp:69-265) for every residual of the
+ * window, computed on the device: the 304-byte records are produced in HBM where the
+ * accumulators read them and never cross PCIe (edsgpu_ba_set_residuals is then not needed).
+ * Replaces the loop FullSystem::linearizeAll_Reductor runs over activeResiduals. */
+#define EDSGPU_PRECALC_FLOATS 28
+/* FrameHessian::dI of frame `frame`: height*width Vec3f {I, dx, dy} (HessianBlocks.h:118). */
+edsgpu_status edsgpu_ba_set_image(edsgpu_ba* ba, int frame, int height, int width, const float* dI);
+/* precalc: F*F records of EDSGPU_PRECALC_FLOATS floats at index host + F*target, the members of
+ *   FrameFramePrecalc (HessianBlocks.h:77-104) the feeder reads, 3x3 blocks column-major as Eigen
+ *   stores them: PRE_RTll_0 (9), PRE_tTll_0 (3), PRE_KRKiTll (9), PRE_KtTll (3), PRE_aff_mode (2),
+ *   PRE_b0_mode (1), pad (1).
+ * calib: CalibHessian fxl, fyl, cxl, cyl.  frame_energy_th: FrameHessian::frameEnergyTH, F floats.
+ * per point (P): PointHessian u, v, idepth_zero_scaled, idepth_scaled, color[8], weights[8]. */
+edsgpu_status edsgpu_ba_set_linearize_inputs(edsgpu_ba* ba, const float* precalc, const float calib[4], const float* frame_energy_th,
+                                             const float* u, const float* v, const float* idepth_zero_scaled,
+                                             const float* idepth_scaled, const float* color, const float* weights);
+/* state_in: ResState per residual (0 IN, 1 OOB, 2 OUTLIER) or NULL = none is OOB yet (OOB ones
+ *   are skipped, :73-74).  linearized: EFResidual::isLinearized per residual or NULL = none;
+ *   res_toZero as in edsgpu_ba_set_residuals (needed for linearized residuals only).
+ * Afterwards the window holds the records, JpJdF and the flags (ACTIVE <=> new state IN).
+ * state_out / energy_out: state_NewState / state_NewEnergy (R each) or NULL; the call is
+ * asynchronous when every host pointer is NULL.  Records of residuals that leave as OOB are zero
+ * (the reference leaves J stale there and never reads it); projectedTo / centerProjectedTo
+ * (visualisation only) are not produced. */
+edsgpu_status edsgpu_ba_linearize(edsgpu_ba* ba, const uint8_t* state_in, const uint8_t* linearized, const float* res_toZero,
+                                  int32_t* state_out, float* energy_out);
+/* debug/parity: the records and flags as they sit on the device (R x 76 floats, R bytes). */
+edsgpu_status edsgpu_ba_get_residuals(edsgpu_ba* ba, float* recs_out, uint8_t* flags_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -417,4 +417,134 @@ void eds_oracle_ba_sc_stitch(int F, const double* accD, const double* accE, cons
     }
 }
 
+// PointFrameResidual::linearize, src/tracking/Residuals.cpp:69-265 (the feeder of the accumulators),
+// for every residual of the window.  float arithmetic in the reference's operation order; built with
+// -ffp-contract=off, so the GPU kernel (written with explicit round-to-nearest mul/add) can be compared bit for bit.
+//   dI          [F][H*W*3]  FrameHessian::dI, Vec3f {I, dx, dy} per pixel
+//   precalc     [F*F][28]   FrameFramePrecalc (HessianBlocks.h:77-104) of (host,target) at host + F*target:
+//                           PRE_RTll_0 (9, column-major like Eigen), PRE_tTll_0 (3), PRE_KRKiTll (9, column-major),
+//                           PRE_KtTll (3), PRE_aff_mode (2), PRE_b0_mode (1), pad (1)
+//   calib       fxl, fyl, cxl, cyl
+//   points      u, v, idepth_zero_scaled, idepth_scaled [P]; color, weights [P][8]
+//   state_in    [R] ResState (0 IN, 1 OOB, 2 OUTLIER) or null = all IN; OOB residuals are skipped (:73-74)
+//   frame_energy_th [F]     FrameHessian::frameEnergyTH
+// out: recs [R][76] (zeroed where the residual leaves as OOB: the reference leaves J stale there and never reads it),
+//      state_new [R], energy_new [R] (state_NewEnergy; 0 where OOB: the reference keeps the old state_energy)
+void eds_oracle_ba_linearize(int F, int P, int R, int H, int W, const float* dI, const float* precalc, const float* calib,
+                             const float* pu, const float* pv, const float* idepth_zero_scaled, const float* idepth_scaled,
+                             const float* color, const float* weights, const int32_t* host_idx, const int32_t* target_idx,
+                             const int32_t* res_begin, const uint8_t* state_in, const float* frame_energy_th, float* recs,
+                             int32_t* state_new, float* energy_new) {
+    static const int patternP[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};  // settings.cpp:276
+    const float setting_huberTH = 9.0f;                      // settings.cpp:127
+    const float setting_outlierTHSumComponent = 50.0f * 50.0f;  // settings.cpp:91
+    const float fxl = calib[0], fyl = calib[1], cxl = calib[2], cyl = calib[3];
+    const float fxli = 1.0f / fxl, fyli = 1.0f / fyl;
+    const float wM3G = (float)(W - 3), hM3G = (float)(H - 3);  // globalCalib.cpp:74-75
+    for (int p = 0; p < P; ++p)
+        for (int r = res_begin[p]; r < res_begin[p + 1]; ++r) {
+            float* J = recs + (size_t)REC * r;
+            for (int i = 0; i < REC; ++i) J[i] = 0.f;
+            energy_new[r] = 0.f;
+            state_new[r] = 1;  // OOB unless the residual survives
+            if (state_in && state_in[r] == 1) continue;  // :73-74
+            const int h = host_idx[r], t = target_idx[r];
+            const float* pc = precalc + (size_t)28 * (h + F * t);
+            auto Rm = [&](int i, int j) { return pc[j * 3 + i]; };         // PRE_RTll_0(i,j)
+            auto KRKi = [&](int i, int j) { return pc[12 + j * 3 + i]; };  // PRE_KRKiTll(i,j)
+            const float* tt = pc + 9;
+            const float* Kt = pc + 21;
+            const float aff0 = pc[24], aff1 = pc[25], b0 = pc[26];
+            const float* dIl = dI + (size_t)t * H * W * 3;
+            // centre point, ResidualProjections.h:60-86 with dx = dy = 0
+            const float KliP0 = (pu[p] + 0 - cxl) * fxli, KliP1 = (pv[p] + 0 - cyl) * fyli;
+            float ptp[3];
+            for (int i = 0; i < 3; ++i) ptp[i] = ((Rm(i, 0) * KliP0 + Rm(i, 1) * KliP1) + Rm(i, 2) * 1.0f) + tt[i] * idepth_zero_scaled[p];
+            const float drescale = 1.0f / ptp[2];
+            const float new_idepth = idepth_zero_scaled[p] * drescale;
+            if (!(drescale > 0)) continue;
+            const float u = ptp[0] * drescale, v = ptp[1] * drescale;
+            const float Ku0 = u * fxl + cxl, Kv0 = v * fyl + cyl;
+            if (!(Ku0 > 1.1f && Kv0 > 1.1f && Ku0 < wM3G && Kv0 < hM3G)) continue;
+            // :108-147 (SCALE_IDEPTH = SCALE_F = SCALE_C = 1, HessianBlocks.h:58-62)
+            float rec[REC];
+            for (int i = 0; i < REC; ++i) rec[i] = 0.f;
+            rec[O_JPDD] = drescale * (tt[0] - tt[2] * u) * 1.0f * fxl;
+            rec[O_JPDD + 1] = drescale * (tt[1] - tt[2] * v) * 1.0f * fyl;
+            float dCx2 = drescale * (Rm(2, 0) * u - Rm(0, 0));
+            float dCx3 = fxl * drescale * (Rm(2, 1) * u - Rm(0, 1)) * fyli;
+            float dCx0 = KliP0 * dCx2, dCx1 = KliP1 * dCx3;
+            float dCy2 = fyl * drescale * (Rm(2, 0) * v - Rm(1, 0)) * fxli;
+            float dCy3 = drescale * (Rm(2, 1) * v - Rm(1, 1));
+            float dCy0 = KliP0 * dCy2, dCy1 = KliP1 * dCy3;
+            rec[O_JPDC0 + 0] = (dCx0 + u) * 1.0f;
+            rec[O_JPDC0 + 1] = dCx1 * 1.0f;
+            rec[O_JPDC0 + 2] = (dCx2 + 1) * 1.0f;
+            rec[O_JPDC0 + 3] = dCx3 * 1.0f;
+            rec[O_JPDC1 + 0] = dCy0 * 1.0f;
+            rec[O_JPDC1 + 1] = (dCy1 + v) * 1.0f;
+            rec[O_JPDC1 + 2] = dCy2 * 1.0f;
+            rec[O_JPDC1 + 3] = (dCy3 + 1) * 1.0f;
+            rec[O_JPDXI0 + 0] = new_idepth * fxl;
+            rec[O_JPDXI0 + 1] = 0;
+            rec[O_JPDXI0 + 2] = -new_idepth * u * fxl;
+            rec[O_JPDXI0 + 3] = -u * v * fxl;
+            rec[O_JPDXI0 + 4] = (1 + u * u) * fxl;
+            rec[O_JPDXI0 + 5] = -v * fxl;
+            rec[O_JPDXI1 + 0] = 0;
+            rec[O_JPDXI1 + 1] = new_idepth * fyl;
+            rec[O_JPDXI1 + 2] = -new_idepth * v * fyl;
+            rec[O_JPDXI1 + 3] = -(1 + v * v) * fyl;
+            rec[O_JPDXI1 + 4] = u * v * fyl;
+            rec[O_JPDXI1 + 5] = u * fyl;
+            float J00 = 0, J11 = 0, J10 = 0, A00 = 0, A01 = 0, A10 = 0, A11 = 0, B00 = 0, B01 = 0, B11 = 0, wJI2 = 0, energyLeft = 0;
+            bool oob = false;
+            for (int idx = 0; idx < 8 && !oob; ++idx) {
+                // ResidualProjections.h:46-56
+                const float up = pu[p] + patternP[idx][0], vp = pv[p] + patternP[idx][1];
+                float q[3];
+                for (int i = 0; i < 3; ++i) q[i] = ((KRKi(i, 0) * up + KRKi(i, 1) * vp) + KRKi(i, 2) * 1.0f) + Kt[i] * idepth_scaled[p];
+                const float Ku = q[0] / q[2], Kv = q[1] / q[2];
+                if (!(Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G)) { oob = true; break; }
+                // getInterpolatedElement33, globalFuncs.h:78-92
+                const int ix = (int)Ku, iy = (int)Kv;
+                const float dx = Ku - ix, dy = Kv - iy, dxdy = dx * dy;
+                const float* bp = dIl + (size_t)3 * (ix + iy * W);
+                float hit[3];
+                for (int c = 0; c < 3; ++c)
+                    hit[c] = ((dxdy * bp[3 * (1 + W) + c] + (dy - dxdy) * bp[3 * W + c]) + (dx - dxdy) * bp[3 + c]) + (1 - dx - dy + dxdy) * bp[c];
+                const float residual = hit[0] - (float)(aff0 * color[8 * p + idx] + aff1);
+                const float drdA = color[8 * p + idx] - b0;
+                if (!std::isfinite(hit[0])) { oob = true; break; }
+                float w = sqrtf(setting_outlierTHSumComponent / (setting_outlierTHSumComponent + (hit[1] * hit[1] + hit[2] * hit[2])));
+                w = 0.5f * (w + weights[8 * p + idx]);
+                float hw = fabsf(residual) < setting_huberTH ? 1 : setting_huberTH / fabsf(residual);
+                energyLeft += w * w * hw * residual * residual * (2 - hw);
+                if (hw < 1) hw = sqrtf(hw);
+                hw = hw * w;
+                hit[1] *= hw;
+                hit[2] *= hw;
+                rec[O_RES + idx] = residual * hw;
+                rec[O_JIDX0 + idx] = hit[1];
+                rec[O_JIDX1 + idx] = hit[2];
+                rec[O_JAB0 + idx] = drdA * hw;
+                rec[O_JAB1 + idx] = hw;
+                J00 += hit[1] * hit[1]; J11 += hit[2] * hit[2]; J10 += hit[1] * hit[2];
+                A00 += drdA * hw * hit[1]; A01 += drdA * hw * hit[2]; A10 += hw * hit[1]; A11 += hw * hit[2];
+                B00 += drdA * drdA * hw * hw; B01 += drdA * hw * hw; B11 += hw * hw;
+                wJI2 += hw * hw * (hit[1] * hit[1] + hit[2] * hit[2]);
+            }
+            if (oob) continue;
+            // Mat22f members are column-major: (0,0) (1,0) (0,1) (1,1)
+            rec[O_JIDX2 + 0] = J00; rec[O_JIDX2 + 1] = J10; rec[O_JIDX2 + 2] = J10; rec[O_JIDX2 + 3] = J11;
+            rec[O_JABJIDX + 0] = A00; rec[O_JABJIDX + 1] = A10; rec[O_JABJIDX + 2] = A01; rec[O_JABJIDX + 3] = A11;
+            rec[O_JAB2 + 0] = B00; rec[O_JAB2 + 1] = B01; rec[O_JAB2 + 2] = B01; rec[O_JAB2 + 3] = B11;
+            for (int i = 0; i < REC; ++i) J[i] = rec[i];
+            const float th = std::max<float>(frame_energy_th[h], frame_energy_th[t]);  // :253-261
+            if (energyLeft > th || wJI2 < 2) { energyLeft = th; state_new[r] = 2; }
+            else state_new[r] = 0;
+            energy_new[r] = energyLeft;
+        }
+}
+
 }  // extern "C"

@@ -169,6 +169,26 @@ def ba_jpjd(recs):
     return out
 
 
+def ba_linearize(F, H, W, dI, precalc, calib, pu, pv, idepth_zero_scaled, idepth_scaled, color, weights, host_idx, target_idx,
+                 res_begin, frame_energy_th, state_in=None):
+    """PointFrameResidual::linearize for every residual -> (recs [R,76], state_new [R], energy_new [R])."""
+    dI, precalc, calib = _f32(dI), _f32(precalc), _f32(calib)
+    pu, pv, iz, isc = _f32(pu), _f32(pv), _f32(idepth_zero_scaled), _f32(idepth_scaled)
+    color, weights, th = _f32(color), _f32(weights), _f32(frame_energy_th)
+    h, t, rb = _i32(host_idx), _i32(target_idx), _i32(res_begin)
+    R, P = len(h), len(rb) - 1
+    st = None if state_in is None else np.ascontiguousarray(state_in, np.uint8)
+    recs = np.zeros((R, 76), np.float32)
+    state = np.zeros(R, np.int32)
+    energy = np.zeros(R, np.float32)
+    lib().eds_oracle_ba_linearize(C.c_int(F), C.c_int(P), C.c_int(R), C.c_int(H), C.c_int(W), _p(dI, C.c_float), _p(precalc, C.c_float),
+                                  _p(calib, C.c_float), _p(pu, C.c_float), _p(pv, C.c_float), _p(iz, C.c_float), _p(isc, C.c_float),
+                                  _p(color, C.c_float), _p(weights, C.c_float), _p(h, C.c_int32), _p(t, C.c_int32), _p(rb, C.c_int32),
+                                  _p(st, C.c_uint8) if st is not None else None, _p(th, C.c_float), _p(recs, C.c_float),
+                                  _p(state, C.c_int32), _p(energy, C.c_float))
+    return recs, state, energy
+
+
 def ba_fix_linearization(F, recs, host_idx, target_idx, res_begin, deltaF, adHTdeltaF, cDeltaF):
     recs = _f32(recs)
     R, P = recs.shape[0], len(res_begin) - 1

@@ -81,6 +81,172 @@ __global__ void ba_jpjd_kernel(const float* __restrict__ recs, int R, float* __r
     o[1] = make_float4(out[4], out[5], out[6], out[7]);
 }
 
+// ------------------------------------------------------------------------------------------
+// PointFrameResidual::linearize (src/tracking/Residuals.cpp:69-265), SURVEY.md 8 a12 / 8(f) rank 1:
+// the feeder of the accumulators on the device, one thread per residual.  The records never cross
+// PCIe: what is uploaded per linearisation is the point state (80 B/point) and the frame-frame
+// precalc (112 B/pair) instead of 304 B/residual.  Arithmetic is float32 in the reference's
+// operation order with explicit round-to-nearest mul/add (no FMA contraction), so the records are
+// reproducible bit for bit by a plain float32 CPU evaluation.  Images are kept as float4 {I, dx, dy, 0} per pixel: one 128-bit
+// load per bilinear tap.
+// ------------------------------------------------------------------------------------------
+constexpr int PRECALC = EDSGPU_PRECALC_FLOATS;
+__constant__ int c_pattern[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};  // settings.cpp:276
+
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fadd_rn(a, -b); }
+
+struct LinDev {
+    int F, P, R, H, W;
+    const float4* images;   // [F][H*W]
+    const float* precalc;   // [F*F][PRECALC]
+    float fxl, fyl, cxl, cyl;
+    const float* frame_energy_th;
+    const float *pu, *pv, *idepth_zero, *idepth, *color, *weights;
+    const int32_t *host_idx, *target_idx, *point_of_res;
+    const uint8_t* state_in;    // or null
+    const uint8_t* linearized;  // or null
+    float* recs;
+    uint8_t* flags;
+    int32_t* state_new;
+    float* energy_new;
+};
+
+__global__ void __launch_bounds__(128) ba_linearize_kernel(LinDev d) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.R) return;
+    float rec[REC];
+#pragma unroll
+    for (int i = 0; i < REC; ++i) rec[i] = 0.f;
+    int state = 1;  // OOB unless the residual survives
+    float energy = 0.f;
+    const int p = d.point_of_res[r];
+    const int h = d.host_idx[r], t = d.target_idx[r];
+    const bool skip = d.state_in && d.state_in[r] == 1;  // :73-74
+    if (!skip) {
+        const float* pc = d.precalc + (size_t)PRECALC * (h + d.F * t);
+        const float fxl = d.fxl, fyl = d.fyl, cxl = d.cxl, cyl = d.cyl;
+        const float fxli = __fdiv_rn(1.0f, fxl), fyli = __fdiv_rn(1.0f, fyl);
+        const float wM3G = (float)(d.W - 3), hM3G = (float)(d.H - 3);  // globalCalib.cpp:74-75
+        const float u0 = d.pu[p], v0 = d.pv[p], idz = d.idepth_zero[p], ids = d.idepth[p];
+        // centre point, ResidualProjections.h:60-86: ptp = R KliP + t idepth; 3x3 blocks are column-major
+        const float K0 = fm(fs(u0, cxl), fxli), K1 = fm(fs(v0, cyl), fyli);
+        float ptp[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ptp[i] = fa(fa(fa(fm(__ldg(pc + i), K0), fm(__ldg(pc + 3 + i), K1)), __ldg(pc + 6 + i)), fm(__ldg(pc + 9 + i), idz));
+        const float drescale = __fdiv_rn(1.0f, ptp[2]);
+        const float new_idepth = fm(idz, drescale);
+        const float u = fm(ptp[0], drescale), v = fm(ptp[1], drescale);
+        const float Ku0 = fa(fm(u, fxl), cxl), Kv0 = fa(fm(v, fyl), cyl);
+        bool ok = (drescale > 0) && Ku0 > 1.1f && Kv0 > 1.1f && Ku0 < wM3G && Kv0 < hM3G;
+        if (ok) {
+            const float R00 = __ldg(pc + 0), R10 = __ldg(pc + 1), R20 = __ldg(pc + 2), R01 = __ldg(pc + 3), R11 = __ldg(pc + 4), R21 = __ldg(pc + 5);
+            const float t0 = __ldg(pc + 9), t1 = __ldg(pc + 10), t2 = __ldg(pc + 11);
+            // :108-147 (SCALE_IDEPTH = SCALE_F = SCALE_C = 1)
+            rec[O_JPDD] = fm(fm(drescale, fs(t0, fm(t2, u))), fxl);
+            rec[O_JPDD + 1] = fm(fm(drescale, fs(t1, fm(t2, v))), fyl);
+            const float dCx2 = fm(drescale, fs(fm(R20, u), R00));
+            const float dCx3 = fm(fm(fm(fxl, drescale), fs(fm(R21, u), R01)), fyli);
+            const float dCy2 = fm(fm(fm(fyl, drescale), fs(fm(R20, v), R10)), fxli);
+            const float dCy3 = fm(drescale, fs(fm(R21, v), R11));
+            rec[O_JPDC0 + 0] = fa(fm(K0, dCx2), u);
+            rec[O_JPDC0 + 1] = fm(K1, dCx3);
+            rec[O_JPDC0 + 2] = fa(dCx2, 1.0f);
+            rec[O_JPDC0 + 3] = dCx3;
+            rec[O_JPDC1 + 0] = fm(K0, dCy2);
+            rec[O_JPDC1 + 1] = fa(fm(K1, dCy3), v);
+            rec[O_JPDC1 + 2] = dCy2;
+            rec[O_JPDC1 + 3] = fa(dCy3, 1.0f);
+            rec[O_JPDXI0 + 0] = fm(new_idepth, fxl);
+            rec[O_JPDXI0 + 2] = fm(fm(-new_idepth, u), fxl);
+            rec[O_JPDXI0 + 3] = fm(fm(-u, v), fxl);
+            rec[O_JPDXI0 + 4] = fm(fa(1.0f, fm(u, u)), fxl);
+            rec[O_JPDXI0 + 5] = fm(-v, fxl);
+            rec[O_JPDXI1 + 1] = fm(new_idepth, fyl);
+            rec[O_JPDXI1 + 2] = fm(fm(-new_idepth, v), fyl);
+            rec[O_JPDXI1 + 3] = fm(-fa(1.0f, fm(v, v)), fyl);
+            rec[O_JPDXI1 + 4] = fm(fm(u, v), fyl);
+            rec[O_JPDXI1 + 5] = fm(u, fyl);
+            const float aff0 = __ldg(pc + 24), aff1 = __ldg(pc + 25), b0 = __ldg(pc + 26);
+            const float4* img = d.images + (size_t)t * d.H * d.W;
+            float J00 = 0, J11 = 0, J10 = 0, A00 = 0, A01 = 0, A10 = 0, A11 = 0, B00 = 0, B01 = 0, B11 = 0, wJI2 = 0;
+            const float TH = 2500.0f, HUBER = 9.0f;  // settings.cpp:91,127
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) {
+                // ResidualProjections.h:46-56
+                const float up = fa(u0, (float)c_pattern[idx][0]), vp = fa(v0, (float)c_pattern[idx][1]);
+                float q[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    q[i] = fa(fa(fa(fm(__ldg(pc + 12 + i), up), fm(__ldg(pc + 15 + i), vp)), __ldg(pc + 18 + i)), fm(__ldg(pc + 21 + i), ids));
+                const float Ku = __fdiv_rn(q[0], q[2]), Kv = __fdiv_rn(q[1], q[2]);
+                const bool inb = Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G;
+                ok = ok && inb;
+                // getInterpolatedElement33, globalFuncs.h:78-92 (a safe pixel once the residual is lost)
+                const float Kus = inb ? Ku : 4.0f, Kvs = inb ? Kv : 4.0f;
+                const int ix = (int)Kus, iy = (int)Kvs;
+                const float dx = fs(Kus, (float)ix), dy = fs(Kvs, (float)iy), dxdy = fm(dx, dy);
+                const float4* bp = img + (ix + iy * d.W);
+                const float4 p00 = __ldg(bp), p10 = __ldg(bp + 1), p01 = __ldg(bp + d.W), p11 = __ldg(bp + 1 + d.W);
+                const float w11 = dxdy, w01 = fs(dy, dxdy), w10 = fs(dx, dxdy), w00 = fa(fs(fs(1.0f, dx), dy), dxdy);
+                const float hit0 = fa(fa(fa(fm(w11, p11.x), fm(w01, p01.x)), fm(w10, p10.x)), fm(w00, p00.x));
+                float hit1 = fa(fa(fa(fm(w11, p11.y), fm(w01, p01.y)), fm(w10, p10.y)), fm(w00, p00.y));
+                float hit2 = fa(fa(fa(fm(w11, p11.z), fm(w01, p01.z)), fm(w10, p10.z)), fm(w00, p00.z));
+                const float col = d.color[8 * p + idx];
+                const float residual = fs(hit0, fa(fm(aff0, col), aff1));
+                const float drdA = fs(col, b0);
+                ok = ok && isfinite(hit0);
+                float w = __fsqrt_rn(__fdiv_rn(TH, fa(TH, fa(fm(hit1, hit1), fm(hit2, hit2)))));
+                w = fm(0.5f, fa(w, d.weights[8 * p + idx]));
+                const float ar = fabsf(residual);
+                float hw = ar < HUBER ? 1.0f : __fdiv_rn(HUBER, ar);
+                energy = fa(energy, fm(fm(fm(fm(fm(w, w), hw), residual), residual), fs(2.0f, hw)));
+                if (hw < 1.0f) hw = __fsqrt_rn(hw);
+                hw = fm(hw, w);
+                hit1 = fm(hit1, hw);
+                hit2 = fm(hit2, hw);
+                rec[O_RES + idx] = fm(residual, hw);
+                rec[O_JIDX0 + idx] = hit1;
+                rec[O_JIDX1 + idx] = hit2;
+                const float dh = fm(drdA, hw);
+                rec[O_JAB0 + idx] = dh;
+                rec[O_JAB1 + idx] = hw;
+                J00 = fa(J00, fm(hit1, hit1)); J11 = fa(J11, fm(hit2, hit2)); J10 = fa(J10, fm(hit1, hit2));
+                A00 = fa(A00, fm(dh, hit1)); A01 = fa(A01, fm(dh, hit2)); A10 = fa(A10, fm(hw, hit1)); A11 = fa(A11, fm(hw, hit2));
+                B00 = fa(B00, fm(fm(fm(drdA, drdA), hw), hw)); B01 = fa(B01, fm(dh, hw)); B11 = fa(B11, fm(hw, hw));
+                wJI2 = fa(wJI2, fm(fm(hw, hw), fa(fm(hit1, hit1), fm(hit2, hit2))));
+            }
+            if (ok) {
+                // Mat22f members are column-major: (0,0) (1,0) (0,1) (1,1)
+                rec[O_JIDX2 + 0] = J00; rec[O_JIDX2 + 1] = J10; rec[O_JIDX2 + 2] = J10; rec[O_JIDX2 + 3] = J11;
+                rec[O_JABJIDX + 0] = A00; rec[O_JABJIDX + 1] = A10; rec[O_JABJIDX + 2] = A01; rec[O_JABJIDX + 3] = A11;
+                rec[O_JAB2 + 0] = B00; rec[O_JAB2 + 1] = B01; rec[O_JAB2 + 2] = B01; rec[O_JAB2 + 3] = B11;
+                const float th = fmaxf(d.frame_energy_th[h], d.frame_energy_th[t]);  // :253-261
+                if (energy > th || wJI2 < 2.0f) { energy = th; state = 2; }
+                else state = 0;
+            }
+        }
+        if (state == 1) {  // lost on the way: no Jacobian (the reference leaves J stale and never reads it)
+#pragma unroll
+            for (int i = 0; i < REC; ++i) rec[i] = 0.f;
+            energy = 0.f;
+        }
+    }
+    float4* out = reinterpret_cast<float4*>(d.recs + (size_t)REC * r);
+#pragma unroll
+    for (int i = 0; i < REC / 4; ++i) out[i] = make_float4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
+    d.state_new[r] = state;
+    d.energy_new[r] = energy;
+    d.flags[r] = (uint8_t)((state == 0 ? EDSGPU_RES_ACTIVE : 0) | ((d.linearized && d.linearized[r]) ? EDSGPU_RES_LINEARIZED : 0));
+}
+
+// Vec3f image -> float4 {I, dx, dy, 0}
+__global__ void ba_pad_image_kernel(const float* __restrict__ src, float4* __restrict__ dst, size_t npix) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npix) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+}
+
 // ---- TMA bulk-copy + mbarrier helpers -------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -613,6 +779,17 @@ struct edsgpu_ba {
     double *tile_partial, *acc[2], *accD, *accE, *accEB, *accHcc, *accbc, *hcc_host, *Hmat, *bvec, *prior_buf;
     long long* num[2];
     int* tile_nres;
+    // device-side linearisation (edsgpu_ba_linearize): images, precalc, point state, results
+    int H = 0, W = 0;
+    float4* images = nullptr;    // [F][H*W], allocated by the first set_image
+    void* lin_block = nullptr;   // precalc, thresholds, point arrays, state / energy / input flags
+    float *precalc = nullptr, *frame_energy_th = nullptr, *pu = nullptr, *pv = nullptr, *idepth_zero = nullptr, *idepth = nullptr;
+    float *color = nullptr, *weights = nullptr, *energy_new = nullptr;
+    int32_t* state_new = nullptr;
+    uint8_t *state_in = nullptr, *linearized = nullptr;
+    float calib[4] = {0, 0, 0, 0};
+    bool lin_inputs_set = false;
+    unsigned images_set = 0;  // bit per frame
 };
 
 namespace {
@@ -746,6 +923,8 @@ void edsgpu_ba_destroy(edsgpu_ba* w) {
     DeviceGuard g(w->ctx->device);
     cudaStreamSynchronize(w->ctx->stream);
     if (w->block) cudaFree(w->block);
+    if (w->images) cudaFree(w->images);
+    if (w->lin_block) cudaFree(w->lin_block);
     delete w;
 }
 
@@ -913,6 +1092,110 @@ edsgpu_status edsgpu_ba_get_jpjd(edsgpu_ba* w, float* JpJdF_out) {
     edsgpu_ctx* ctx = w->ctx;
     DeviceGuard g(ctx->device);
     EDS_CUDA(ctx, cudaMemcpyAsync(JpJdF_out, w->JpJdF, 32 * (size_t)w->R, cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+// ---- device-side linearisation -------------------------------------------------------------
+edsgpu_status edsgpu_ba_set_image(edsgpu_ba* w, int frame, int height, int width, const float* dI) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, dI && frame >= 0 && frame < w->F && height > 4 && width > 4, "ba_set_image: bad arguments");
+    EDS_REQUIRE(ctx, w->images == nullptr || (height == w->H && width == w->W), "ba_set_image: all frames of a window share one size");
+    DeviceGuard g(ctx->device);
+    const size_t npix = (size_t)height * width;
+    if (!w->images) {
+        cudaError_t e = cudaMalloc(&w->images, sizeof(float4) * npix * w->F);
+        if (e != cudaSuccess) return edsgpu_fail(ctx, e == cudaErrorMemoryAllocation ? EDSGPU_OUT_OF_MEMORY : EDSGPU_CUDA_ERROR, cudaGetErrorString(e));
+        w->H = height; w->W = width;
+    }
+    edsgpu_status st = edsgpu_ensure_scratch(ctx, npix * 3 * sizeof(float));
+    if (st != EDSGPU_OK) return st;
+    EDS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, dI, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ba_pad_image_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>((const float*)ctx->scratch, w->images + npix * frame, npix);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller's buffer may be pageable and reused; scratch is shared
+    w->images_set |= 1u << frame;
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_set_linearize_inputs(edsgpu_ba* w, const float* precalc, const float calib[4], const float* frame_energy_th,
+                                             const float* u, const float* v, const float* idepth_zero_scaled, const float* idepth_scaled,
+                                             const float* color, const float* weights) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, precalc && calib && frame_energy_th && u && v && idepth_zero_scaled && idepth_scaled && color && weights,
+                "ba_set_linearize_inputs: null array");
+    DeviceGuard g(ctx->device);
+    const size_t F = w->F, P = w->P, R = w->R;
+    if (!w->lin_block) {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+        const size_t o_pre = take(4 * PRECALC * F * F), o_th = take(4 * F), o_u = take(4 * P), o_v = take(4 * P), o_iz = take(4 * P), o_id = take(4 * P);
+        const size_t o_c = take(32 * P), o_w = take(32 * P), o_e = take(4 * R), o_s = take(4 * R), o_si = take(R), o_l = take(R);
+        cudaError_t e = cudaMalloc(&w->lin_block, off);
+        if (e != cudaSuccess) return edsgpu_fail(ctx, e == cudaErrorMemoryAllocation ? EDSGPU_OUT_OF_MEMORY : EDSGPU_CUDA_ERROR, cudaGetErrorString(e));
+        char* b = (char*)w->lin_block;
+        w->precalc = (float*)(b + o_pre); w->frame_energy_th = (float*)(b + o_th); w->pu = (float*)(b + o_u); w->pv = (float*)(b + o_v);
+        w->idepth_zero = (float*)(b + o_iz); w->idepth = (float*)(b + o_id); w->color = (float*)(b + o_c); w->weights = (float*)(b + o_w);
+        w->energy_new = (float*)(b + o_e); w->state_new = (int32_t*)(b + o_s); w->state_in = (uint8_t*)(b + o_si); w->linearized = (uint8_t*)(b + o_l);
+    }
+    cudaStream_t s = ctx->stream;
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->precalc, precalc, 4 * PRECALC * F * F, cudaMemcpyHostToDevice, s));
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->frame_energy_th, frame_energy_th, 4 * F, cudaMemcpyHostToDevice, s));
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->pu, u, 4 * P, cudaMemcpyHostToDevice, s));
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->pv, v, 4 * P, cudaMemcpyHostToDevice, s));
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->idepth_zero, idepth_zero_scaled, 4 * P, cudaMemcpyHostToDevice, s));
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->idepth, idepth_scaled, 4 * P, cudaMemcpyHostToDevice, s));
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->color, color, 32 * P, cudaMemcpyHostToDevice, s));
+    EDS_CUDA(ctx, cudaMemcpyAsync(w->weights, weights, 32 * P, cudaMemcpyHostToDevice, s));
+    EDS_CUDA(ctx, cudaStreamSynchronize(s));
+    memcpy(w->calib, calib, sizeof(w->calib));
+    w->lin_inputs_set = true;
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_linearize(edsgpu_ba* w, const uint8_t* state_in, const uint8_t* linearized, const float* res_toZero,
+                                  int32_t* state_out, float* energy_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, w->lin_inputs_set, "ba_linearize: call edsgpu_ba_set_linearize_inputs first");
+    EDS_REQUIRE(ctx, w->images && w->images_set == (1u << w->F) - 1u, "ba_linearize: call edsgpu_ba_set_image for every frame first");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    if (state_in) EDS_CUDA(ctx, cudaMemcpyAsync(w->state_in, state_in, (size_t)w->R, cudaMemcpyHostToDevice, s));
+    if (linearized) EDS_CUDA(ctx, cudaMemcpyAsync(w->linearized, linearized, (size_t)w->R, cudaMemcpyHostToDevice, s));
+    if (res_toZero) EDS_CUDA(ctx, cudaMemcpyAsync(w->res_toZero, res_toZero, 32 * (size_t)w->R, cudaMemcpyHostToDevice, s));
+    LinDev d{};
+    d.F = w->F; d.P = w->P; d.R = w->R; d.H = w->H; d.W = w->W;
+    d.images = w->images; d.precalc = w->precalc;
+    d.fxl = w->calib[0]; d.fyl = w->calib[1]; d.cxl = w->calib[2]; d.cyl = w->calib[3];
+    d.frame_energy_th = w->frame_energy_th;
+    d.pu = w->pu; d.pv = w->pv; d.idepth_zero = w->idepth_zero; d.idepth = w->idepth; d.color = w->color; d.weights = w->weights;
+    d.host_idx = w->host_idx; d.target_idx = w->target_idx; d.point_of_res = w->point_of_res;
+    d.state_in = state_in ? w->state_in : nullptr;
+    d.linearized = linearized ? w->linearized : nullptr;
+    d.recs = w->recs; d.flags = w->flags; d.state_new = w->state_new; d.energy_new = w->energy_new;
+    ba_linearize_kernel<<<(w->R + 127) / 128, 128, 0, s>>>(d);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    ba_jpjd_kernel<<<(w->R + 255) / 256, 256, 0, s>>>(w->recs, w->R, w->JpJdF);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    if (state_out) EDS_CUDA(ctx, cudaMemcpyAsync(state_out, w->state_new, 4 * (size_t)w->R, cudaMemcpyDeviceToHost, s));
+    if (energy_out) EDS_CUDA(ctx, cudaMemcpyAsync(energy_out, w->energy_new, 4 * (size_t)w->R, cudaMemcpyDeviceToHost, s));
+    if (state_in || linearized || res_toZero || state_out || energy_out) EDS_CUDA(ctx, cudaStreamSynchronize(s));
+    return EDSGPU_OK;
+}
+
+// debug/parity: the records as they sit on the device (uploaded or linearised there)
+edsgpu_status edsgpu_ba_get_residuals(edsgpu_ba* w, float* recs_out, uint8_t* flags_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    DeviceGuard g(ctx->device);
+    if (recs_out) EDS_CUDA(ctx, cudaMemcpyAsync(recs_out, w->recs, 4 * (size_t)REC * w->R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (flags_out) EDS_CUDA(ctx, cudaMemcpyAsync(flags_out, w->flags, (size_t)w->R, cudaMemcpyDeviceToHost, ctx->stream));
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EDSGPU_OK;
 }

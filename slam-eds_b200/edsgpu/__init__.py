@@ -34,6 +34,7 @@ SYMBOLS = [
     "edsgpu_tracker_evaluate",
     "edsgpu_ba_create", "edsgpu_ba_destroy", "edsgpu_ba_set_residuals", "edsgpu_ba_set_points", "edsgpu_ba_set_frames",
     "edsgpu_ba_top_accumulate", "edsgpu_ba_top_stitch", "edsgpu_ba_sc_accumulate", "edsgpu_ba_sc_stitch", "edsgpu_ba_get_jpjd",
+    "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_get_residuals",
 ]
 
 
@@ -349,6 +350,36 @@ class BaWindow:
         rtz = np.ascontiguousarray(res_toZero, np.float32) if res_toZero is not None else None
         assert recs.shape == (self.R, 76) and fl.shape == (self.R,)
         self.ctx.check(self.ctx.lib.edsgpu_ba_set_residuals(self.h, _ptr(recs, C.c_float), _ptr(fl, C.c_uint8), _ptr(rtz, C.c_float)))
+
+    # ---- the feeder on the device: PointFrameResidual::linearize (Residuals.cpp:69-265) ----
+    def set_images(self, dI):
+        """dI: (F, H, W, 3) float32, FrameHessian::dI of every frame of the window."""
+        dI = np.ascontiguousarray(dI, np.float32)
+        assert dI.ndim == 4 and dI.shape[0] == self.F and dI.shape[3] == 3
+        for f in range(self.F):
+            self.ctx.check(self.ctx.lib.edsgpu_ba_set_image(self.h, C.c_int(f), C.c_int(dI.shape[1]), C.c_int(dI.shape[2]), _ptr(dI[f], C.c_float)))
+
+    def set_linearize_inputs(self, precalc, calib, frame_energy_th, u, v, idepth_zero_scaled, idepth_scaled, color, weights):
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)  # noqa: E731
+        a = [f32(x) for x in (precalc, calib, frame_energy_th, u, v, idepth_zero_scaled, idepth_scaled, color, weights)]
+        assert a[0].shape == (self.F * self.F, 28) and a[1].shape == (4,) and a[7].shape == (self.P, 8) and a[8].shape == (self.P, 8)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_set_linearize_inputs(self.h, *[_ptr(x, C.c_float) for x in a]))
+
+    def linearize(self, state_in=None, linearized=None, res_toZero=None, want_outputs=True):
+        """-> (state_new, energy_new) or None; the records, JpJdF and flags stay on the device."""
+        u8 = lambda a: np.ascontiguousarray(a, np.uint8) if a is not None else None  # noqa: E731
+        si, li = u8(state_in), u8(linearized)
+        rtz = np.ascontiguousarray(res_toZero, np.float32) if res_toZero is not None else None
+        st = np.zeros(self.R, np.int32) if want_outputs else None
+        en = np.zeros(self.R, np.float32) if want_outputs else None
+        self.ctx.check(self.ctx.lib.edsgpu_ba_linearize(self.h, _ptr(si, C.c_uint8), _ptr(li, C.c_uint8), _ptr(rtz, C.c_float),
+                                                        _ptr(st, C.c_int32), _ptr(en, C.c_float)))
+        return (st, en) if want_outputs else None
+
+    def get_residuals(self):
+        recs, flags = np.zeros((self.R, 76), np.float32), np.zeros(self.R, np.uint8)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_get_residuals(self.h, _ptr(recs, C.c_float), _ptr(flags, C.c_uint8)))
+        return recs, flags
 
     def set_points(self, deltaF=None, priorF=None):
         d = np.ascontiguousarray(deltaF, np.float32) if deltaF is not None else None

@@ -133,6 +133,8 @@ def make_ba_problem(F=7, points_per_frame=2048, H=480, W=640, seed=4234, lineari
     Ki = np.linalg.inv(K)
     fxi, fyi = f32(1.0 / fx), f32(1.0 / fy)
     frame_energy_th = f32(12 * 12 * 8)  # setting_outlierTH * patternNum (FullSystem default)
+    # FrameFramePrecalc of (host,target) at host + F*target, layout of include/edsgpu.h (3x3 blocks column-major like Eigen)
+    precalc = np.zeros((F * F, 28), f32)
     for h in range(F):
         Rh, th = poses[h]
         for t in range(F):
@@ -148,6 +150,9 @@ def make_ba_problem(F=7, points_per_frame=2048, H=480, W=640, seed=4234, lineari
             Kt = (K @ tll).astype(f32)
             a_ll, b_ll = from_to_vec_exposure(aff[h], aff[t])
             a_ll, b_ll, b0 = f32(a_ll), f32(b_ll), f32(aff[h][1])
+            pc = precalc[h + F * t]
+            pc[0:9] = PRE_R.T.reshape(-1); pc[9:12] = PRE_t; pc[12:21] = KRKi.T.reshape(-1); pc[21:24] = Kt
+            pc[24], pc[25], pc[26] = a_ll, b_ll, b0
             p = point_of_res[m]
             u0, v0, idp = pu[p], pv[p], pid[p]
             # centre projection (ResidualProjections.h:60-86)
@@ -206,7 +211,7 @@ def make_ba_problem(F=7, points_per_frame=2048, H=480, W=640, seed=4234, lineari
                 hit = _interp33(dIs[t], Kus, Kvs)
                 residual = hit[:, 0] - (a_ll * colors[p, k] + b_ll)
                 drdA = colors[p, k] - b0
-                wgt = np.sqrt(SETTING_OUTLIER_TH_SUMC / (SETTING_OUTLIER_TH_SUMC + hit[:, 1] ** 2 + hit[:, 2] ** 2)).astype(f32)
+                wgt = np.sqrt(SETTING_OUTLIER_TH_SUMC / (SETTING_OUTLIER_TH_SUMC + (hit[:, 1] ** 2 + hit[:, 2] ** 2))).astype(f32)  # tail<2>().squaredNorm() first
                 wgt = f32(0.5) * (wgt + pweights[p, k])
                 ar = np.abs(residual)
                 hw = np.where(ar < SETTING_HUBER_TH, f32(1.0), SETTING_HUBER_TH / np.maximum(ar, f32(1e-20))).astype(f32)
@@ -268,7 +273,10 @@ def make_ba_problem(F=7, points_per_frame=2048, H=480, W=640, seed=4234, lineari
     return dict(F=F, P=P, R=R, H=H, W=W, recs=recs, host_idx=host_idx, target_idx=target_idx, point_of_res=point_of_res,
                 res_begin=res_begin, flags=flags, state=state, deltaF=deltaF, priorF=priorF, adHTdeltaF=adHTdeltaF,
                 cDeltaF=cDeltaF, adHost=adHost, adTarget=adTarget, cPrior=np.full(4, 5e9),
-                frame_prior=np.abs(rng.normal(scale=1e3, size=(F, 8))), frame_delta_prior=rng.normal(scale=perturb, size=(F, 8)))
+                frame_prior=np.abs(rng.normal(scale=1e3, size=(F, 8))), frame_delta_prior=rng.normal(scale=perturb, size=(F, 8)),
+                # inputs of the feeder itself (PointFrameResidual::linearize), for the device-side linearisation
+                dI=np.stack(dIs), precalc=precalc, calib=np.array([fx, fy, cx, cy], f32), pu=pu, pv=pv, idepth=pid,
+                color=colors, weights=pweights, frame_energy_th=np.full(F, frame_energy_th, f32))
 
 
 def col_major(mats):

@@ -112,6 +112,58 @@ def test_schur_complement(solved, shift):
     assert all(g["HdiF"][p] == 0 and g["bdSum"][p] == 0 for p in none[:50])
 
 
+@pytest.mark.parametrize("cfg", ["small", "config4"])
+def test_device_linearize_is_bit_exact_and_feeds_the_accumulators(gpu_ctx, cfg):
+    """PointFrameResidual::linearize on the device (SURVEY 8f rank 1) against the float32 oracle: same
+    bits for the records, same ResState, same energies; the accumulators fed by the device-made records
+    give the same result as when the records are uploaded."""
+    pb = SB.make_ba_problem(F=4, points_per_frame=250, H=120, W=160) if cfg == "small" else SB.make_ba_problem()
+    ref_recs, ref_state, ref_energy = O.ba_linearize(pb["F"], pb["H"], pb["W"], pb["dI"], pb["precalc"], pb["calib"], pb["pu"], pb["pv"],
+                                                     pb["idepth"], pb["idepth"], pb["color"], pb["weights"], pb["host_idx"],
+                                                     pb["target_idx"], pb["res_begin"], pb["frame_energy_th"])
+    w = edsgpu.BaWindow(gpu_ctx, pb["F"], pb["host_idx"], pb["target_idx"], pb["res_begin"])
+    w.set_images(pb["dI"])
+    w.set_linearize_inputs(pb["precalc"], pb["calib"], pb["frame_energy_th"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"],
+                           pb["color"], pb["weights"])
+    linearized = (pb["flags"] >> 1) & 1
+    rtz = O.ba_fix_linearization(pb["F"], pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["deltaF"], pb["adHTdeltaF"],
+                                 pb["cDeltaF"])
+    state, energy = w.linearize(linearized=linearized, res_toZero=rtz)
+    recs, flags = w.get_residuals()
+    assert np.array_equal(state, ref_state) and {0, 1} <= set(np.unique(state))
+    assert np.array_equal(recs, ref_recs)
+    assert np.array_equal(energy, ref_energy)
+    assert np.array_equal(flags, pb["flags"])
+    assert np.array_equal(w.jpjd(), O.ba_jpjd(ref_recs)) or rel(w.jpjd(), O.ba_jpjd(ref_recs)) < 1e-6
+    # downstream: identical to the upload path
+    w.set_points(pb["deltaF"], pb["priorF"])
+    w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    a = w.top_accumulate(0)
+    w2 = edsgpu.BaWindow(gpu_ctx, pb["F"], pb["host_idx"], pb["target_idx"], pb["res_begin"])
+    w2.set_residuals(pb["recs"], pb["flags"], rtz)
+    w2.set_points(pb["deltaF"], pb["priorF"])
+    w2.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    b = w2.top_accumulate(0)
+    assert np.array_equal(a["acc"], b["acc"]) and np.array_equal(a["Hdd"], b["Hdd"]) and a["nres"] == b["nres"]
+    # a sticky OOB input state is honoured
+    st_in = np.zeros(pb["R"], np.uint8); st_in[::7] = 1
+    state2, _ = w.linearize(state_in=st_in)
+    assert np.all(state2[::7] == 1) and np.array_equal(np.delete(state2, np.s_[::7]), np.delete(ref_state, np.s_[::7]))
+    w.close(); w2.close()
+
+
+def test_linearize_needs_its_inputs(gpu_ctx):
+    pb = SB.make_ba_problem(F=3, points_per_frame=50, H=64, W=80)
+    w = edsgpu.BaWindow(gpu_ctx, pb["F"], pb["host_idx"], pb["target_idx"], pb["res_begin"])
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.linearize()
+    w.set_linearize_inputs(pb["precalc"], pb["calib"], pb["frame_energy_th"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"],
+                           pb["color"], pb["weights"])
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.linearize()  # images missing
+    w.close()
+
+
 def test_argument_validation(gpu_ctx):
     with pytest.raises(edsgpu.EdsGpuError):
         edsgpu.BaWindow(gpu_ctx, 9, [0], [1], [0, 1])  # F > 8

@@ -196,3 +196,62 @@ def test_sc_accumulator_and_stitch(small):
         Hr[0:4, 4 + 8 * h:12 + 8 * h] = Hr[4 + 8 * h:12 + 8 * h, 0:4].T
     np.testing.assert_allclose(H, Hr, rtol=1e-11, atol=1e-10 * np.abs(Hr).max())
     np.testing.assert_allclose(b, br, rtol=1e-11, atol=1e-10 * np.abs(br).max())
+
+
+def _linearize_inputs(pb):
+    return (pb["F"], pb["H"], pb["W"], pb["dI"], pb["precalc"], pb["calib"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"],
+            pb["color"], pb["weights"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["frame_energy_th"])
+
+
+def test_linearize_two_independent_restatements_agree_bit_for_bit():
+    """PointFrameResidual::linearize (Residuals.cpp:69-265): the C++ oracle and the numpy restatement that
+    generates the synthetic records were written separately from the reference; in float32 without FMA
+    contraction they must produce the same bits (records, ResState)."""
+    pb = SB.make_ba_problem(F=4, points_per_frame=300, H=120, W=160, seed=3)
+    recs, state, energy = O.ba_linearize(*_linearize_inputs(pb))
+    assert np.array_equal(state, pb["state"])
+    assert set(np.unique(state)) >= {0, 1}  # the problem has residuals that stay in and that leave the image
+    assert np.array_equal(recs, pb["recs"])
+    th = pb["frame_energy_th"][0]
+    assert np.all(energy[state == 2] == th) and np.all(energy[state == 1] == 0) and np.all(energy[state == 0] <= th)
+
+
+def test_linearize_state_machine_and_known_answers():
+    """Hand-checkable cases: identity motion on a linear intensity ramp."""
+    F, H, W = 2, 32, 40
+    dI = np.zeros((F, H, W, 3), np.float32)
+    xs = np.arange(W, dtype=np.float32)[None, :].repeat(H, 0)
+    for f in range(F):
+        dI[f, ..., 0] = 2.0 * xs + 10.0   # I = 2x + 10
+        dI[f, ..., 1] = 2.0               # dI/dx
+    fx, fy, cx, cy = 30.0, 30.0, 20.0, 16.0
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    pre = np.zeros((F * F, 28), np.float32)
+    for k in range(F * F):
+        pre[k, 0:9] = np.eye(3).T.reshape(-1); pre[k, 12:21] = (K @ np.eye(3) @ np.linalg.inv(K)).T.reshape(-1)
+        pre[k, 24] = 1.0  # affLL = (1, 0), b0 = 0
+    pu = np.array([10.0, 3.0, 20.0], np.float32)   # second point: pattern pixel u-2 = 1 < 1.1 -> OOB
+    pv = np.array([12.0, 12.0, 12.0], np.float32)
+    idp = np.ones(3, np.float32)
+    color = np.zeros((3, 8), np.float32)
+    pat = np.array([[0, -2], [-1, -1], [1, -1], [-2, 0], [0, 0], [2, 0], [-1, 1], [0, 2]], np.float32)
+    for p in range(3):
+        color[p] = 2.0 * (pu[p] + pat[:, 0]) + 10.0
+    color[2] += 100.0  # third point: |residual| = 100 on every pixel -> Huber, energy above the threshold -> OUTLIER
+    weights = np.ones((3, 8), np.float32)
+    host = np.zeros(3, np.int32); target = np.ones(3, np.int32); rb = np.arange(4, dtype=np.int32)
+    th = np.full(F, 12 * 12 * 8, np.float32)
+    recs, state, energy = O.ba_linearize(F, H, W, dI, pre, [fx, fy, cx, cy], pu, pv, idp, idp, color, weights, host, target, rb, th)
+    assert list(state) == [0, 1, 2]
+    assert np.all(recs[1] == 0) and energy[1] == 0
+    w = 0.5 * (np.sqrt(np.float32(2500.0) / np.float32(2504.0)) + 1.0)
+    assert np.allclose(recs[0, 0:8], 0.0, atol=1e-4)                 # perfect match: zero residual
+    assert np.allclose(recs[0, 32:40], 2.0 * w, rtol=1e-6)           # JIdx[0] = dx * hw
+    assert np.allclose(recs[0, 40:48], 0.0)                          # JIdx[1] = dy * hw
+    assert np.allclose(recs[0, 56:64], w, rtol=1e-6)                 # JabF[1] = hw
+    assert np.isclose(recs[0, 8], fx) and recs[0, 9] == 0           # Jpdxi[0] = (new_idepth fx, 0, ...)
+    assert energy[2] == th[0]
+    # an input state of OOB is sticky (:73-74)
+    _, state2, _ = O.ba_linearize(F, H, W, dI, pre, [fx, fy, cx, cy], pu, pv, idp, idp, color, weights, host, target, rb, th,
+                                  state_in=np.array([1, 0, 0], np.uint8))
+    assert list(state2) == [1, 1, 2]
