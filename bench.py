@@ -210,10 +210,34 @@ def bench_ba(ctx, stream, reps=50):
                                 pb["adHTdeltaF"], pb["cDeltaF"], threads=6)
     cpu_ms = 1e3 * (time.perf_counter() - t0) / n_cpu
     alg = 2 * (296 * R + 12 * R + 364 * F * F + 24 * P) + (44 * R + 48 * P + 4 * (64 * F ** 3 + 40 * F * F + 20))
+    # the feeder on the device: PointFrameResidual::linearize + takeDataF, inputs resident
+    w.set_images(pb["dI"])
+    w.set_linearize_inputs(pb["precalc"], pb["calib"], pb["frame_energy_th"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"],
+                           pb["color"], pb["weights"])
+    for _ in range(5):
+        w.linearize(want_outputs=False)
+    a.record(stream)
+    for _ in range(reps):
+        w.linearize(want_outputs=False)
+    b.record(stream)
+    stream.synchronize()
+    lin_ms = a.elapsed_time(b) / reps
+    t0 = time.perf_counter()
+    for _ in range(5):
+        O.ba_linearize(F, pb["H"], pb["W"], pb["dI"], pb["precalc"], pb["calib"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"],
+                       pb["color"], pb["weights"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["frame_energy_th"])
+    lin_cpu_ms = 1e3 * (time.perf_counter() - t0) / 5
+    # per residual: 8 pattern pixels x 4 taps x 16 B gathered, 80 B of point state, 112 B of precalc, 304 B record + 32 B JpJdF
+    # written (and the record read once more by takeDataF), 9 B of state / energy / flag
+    lin_alg = R * (8 * 4 * 16 + 80 + 112 + 304 + 304 + 32 + 9)
     w.close()
     return {"workload": "config4: F=7, P=%d, R=%d; top<0> + top<1> + SC accumulate, device-resident" % (P, R),
             "accumulations_per_s": 1e3 / ms, "ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
-            "cpu_port_top_ms_6_threads": cpu_ms}
+            "cpu_port_top_ms_6_threads": cpu_ms,
+            "linearize": {"what": "PointFrameResidual::linearize + takeDataF for all R residuals on the device (records stay in HBM)",
+                          "ms": lin_ms, "residuals_per_s": R / (lin_ms * 1e-3), "algorithmic_bytes": lin_alg,
+                          "achieved_gbs": lin_alg / (lin_ms * 1e-3) / 1e9, "cpu_port_ms_1_thread": lin_cpu_ms,
+                          "upload_avoided_bytes": 304 * R}}
 
 
 # --------------------------------------------------------------------------------------- GPU arm

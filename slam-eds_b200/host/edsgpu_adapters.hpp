@@ -232,6 +232,18 @@ class HessianAccumulators {
     // records: R x 76 floats (RawResidualJacobian), flags: EDSGPU_RES_ACTIVE | EDSGPU_RES_LINEARIZED
     void setResiduals(const float* records, const uint8_t* flags, const float* res_toZeroF) { ctx_.check(edsgpu_ba_set_residuals(ba_, records, flags, res_toZeroF)); }
     void setPoints(const float* deltaF, const float* priorF) { ctx_.check(edsgpu_ba_set_points(ba_, deltaF, priorF)); }
+    // The feeder on the device instead of setResiduals: FrameHessian::dI per frame, then the state
+    // PointFrameResidual::linearize reads (Residuals.cpp:69-265), then linearizeAll() for every residual.
+    void setImage(int frame, int height, int width, const float* dI_vec3f) { ctx_.check(edsgpu_ba_set_image(ba_, frame, height, width, dI_vec3f)); }
+    void setLinearizeInputs(const float* precalc, const float calib[4], const float* frameEnergyTH, const float* u, const float* v,
+                            const float* idepth_zero_scaled, const float* idepth_scaled, const float* color, const float* weights) {
+        ctx_.check(edsgpu_ba_set_linearize_inputs(ba_, precalc, calib, frameEnergyTH, u, v, idepth_zero_scaled, idepth_scaled, color, weights));
+    }
+    // state_NewState / state_NewEnergy of every residual (optional); records, JpJdF and flags stay on the device
+    void linearizeAll(const uint8_t* state_state, const uint8_t* isLinearized, const float* res_toZeroF, int32_t* state_NewState,
+                      float* state_NewEnergy) {
+        ctx_.check(edsgpu_ba_linearize(ba_, state_state, isLinearized, res_toZeroF, state_NewState, state_NewEnergy));
+    }
     // setAdjointsF / setDeltaF results (EnergyFunctional.cpp:46-106,171-194)
     void setFrames(const float* adHTdeltaF, const float* cDeltaF, const double* adHost, const double* adTarget) {
         ctx_.check(edsgpu_ba_set_frames(ba_, adHTdeltaF, cDeltaF, adHost, adTarget));
