@@ -261,6 +261,20 @@ edsgpu_status edsgpu_ba_set_linearize_inputs(edsgpu_ba* ba, const float* precalc
  * (visualisation only) are not produced. */
 edsgpu_status edsgpu_ba_linearize(edsgpu_ba* ba, const uint8_t* state_in, const uint8_t* linearized, const float* res_toZero,
                                   int32_t* state_out, float* energy_out);
+/* ---- after the solve -------------------------------------------------
+ * EnergyFunctional::resubstituteF_MT (EnergyFunctional.cpp:263-317): per-point inverse-depth step
+ * from the solved update x (4 + 8F doubles).  Needs the adjoints (edsgpu_ba_set_frames) and the
+ * results of top_accumulate(0), top_accumulate(1) and sc_accumulate of this linearisation, which
+ * are still on the device.  point_step_out: PointHessian::step, P floats. */
+edsgpu_status edsgpu_ba_resubstitute(edsgpu_ba* ba, const double* x, float* point_step_out);
+/* EFResidual::fixLinearizationF (EnergyFunctionalStructs.cpp:87-113) for the residuals with
+ * select[r] != 0 (NULL = every active residual): res_toZero = resF - J delta with the current
+ * deltas, isLinearized = true.  res_toZero_out: R x 8 floats or NULL. */
+edsgpu_status edsgpu_ba_fix_linearization(edsgpu_ba* ba, const uint8_t* select, float* res_toZero_out);
+/* EnergyFunctional::calcLEnergyF_MT (EnergyFunctional.cpp:332-415): energy of the linearised part
+ * at the current deltas; cPrior (4), frame_prior / frame_delta_prior (F x 8) may be NULL. */
+edsgpu_status edsgpu_ba_calc_l_energy(edsgpu_ba* ba, const double* cPrior, const double* frame_prior, const double* frame_delta_prior,
+                                      double* energy_out);
 /* debug/parity: the records and flags as they sit on the device (R x 76 floats, R bytes). */
 edsgpu_status edsgpu_ba_get_residuals(edsgpu_ba* ba, float* recs_out, uint8_t* flags_out);
 

@@ -547,4 +547,83 @@ void eds_oracle_ba_linearize(int F, int P, int R, int H, int W, const float* dI,
         }
 }
 
+// EnergyFunctional::resubstituteF_MT + resubstituteFPt, src/bundles/EnergyFunctional.cpp:263-317 (float arithmetic):
+// per-point inverse-depth step from the solved frame / calibration update x (4 + 8F doubles).
+// adHost / adTarget: F*F column-major 8x8 (index host + F*target), cast to float like adHostF / adTargetF.
+void eds_oracle_ba_resubstitute(int F, int P, int R, const double* x, const double* adHost, const double* adTarget,
+                                const int32_t* host_idx, const int32_t* target_idx, const int32_t* res_begin, const uint8_t* flags,
+                                const float* JpJdF, const float* bdSumF, const float* Hcd_accAF, const float* Hcd_accLF, const float* HdiF,
+                                float* step_out) {
+    std::vector<float> xF(CPARS + 8 * F);
+    for (size_t i = 0; i < xF.size(); ++i) xF[i] = (float)x[i];
+    std::vector<float> xAd((size_t)F * F * 8);  // xAd[F*h + t]
+    for (int h = 0; h < F; ++h)
+        for (int t = 0; t < F; ++t) {
+            const double* AH = adHost + (size_t)64 * (h + F * t);
+            const double* AT = adTarget + (size_t)64 * (h + F * t);
+            for (int c = 0; c < 8; ++c) {
+                float a = 0.f, b = 0.f;
+                for (int k = 0; k < 8; ++k) a += xF[CPARS + 8 * h + k] * (float)AH[c * 8 + k];  // row vector times column c
+                for (int k = 0; k < 8; ++k) b += xF[CPARS + 8 * t + k] * (float)AT[c * 8 + k];
+                xAd[(size_t)8 * (F * h + t) + c] = a + b;
+            }
+        }
+    for (int p = 0; p < P; ++p) {
+        int ngoodres = 0;
+        for (int r = res_begin[p]; r < res_begin[p + 1]; ++r) if (flags[r] & 1) ngoodres++;
+        if (ngoodres == 0) { step_out[p] = 0.f; continue; }
+        float b = bdSumF[p];
+        float dot = 0.f;
+        for (int k = 0; k < CPARS; ++k) dot += xF[k] * (Hcd_accAF[4 * p + k] + Hcd_accLF[4 * p + k]);
+        b -= dot;
+        for (int r = res_begin[p]; r < res_begin[p + 1]; ++r) {
+            if (!(flags[r] & 1)) continue;
+            const float* xa = &xAd[(size_t)8 * (host_idx[r] * F + target_idx[r])];
+            float d = 0.f;
+            for (int k = 0; k < 8; ++k) d += xa[k] * JpJdF[(size_t)8 * r + k];
+            b -= d;
+        }
+        step_out[p] = -b * HdiF[p];
+    }
+}
+
+// EnergyFunctional::calcLEnergyF_MT + calcLEnergyPt, EnergyFunctional.cpp:332-415: energy of the linearised part at
+// the current delta, E = sum over linearised active residuals (2 res_toZero + J delta) . J delta + sum_p deltaF^2 priorF
+// + the frame / calibration prior terms.  The reference sums in float (Accumulator11); the oracle in double.
+double eds_oracle_ba_calc_l_energy(int F, int P, int R, const float* recs, const int32_t* host_idx, const int32_t* target_idx,
+                                   const int32_t* res_begin, const uint8_t* flags, const float* res_toZero, const float* deltaF,
+                                   const float* priorF, const float* adHTdeltaF, const float* cDeltaF, const double* cPrior,
+                                   const double* frame_prior, const double* frame_delta_prior) {
+    double E = 0.0;
+    if (frame_prior && frame_delta_prior)
+        for (int i = 0; i < 8 * F; ++i) E += frame_delta_prior[i] * frame_prior[i] * frame_delta_prior[i];
+    if (cPrior)
+        for (int k = 0; k < CPARS; ++k) E += (double)cDeltaF[k] * (double)(float)cPrior[k] * (double)cDeltaF[k];
+    for (int p = 0; p < P; ++p) {
+        const float dd = deltaF[p];
+        for (int r = res_begin[p]; r < res_begin[p + 1]; ++r) {
+            if (!(flags[r] & 2) || !(flags[r] & 1)) continue;
+            const float* J = recs + (size_t)REC * r;
+            const float* dp = adHTdeltaF + (size_t)8 * (host_idx[r] + F * target_idx[r]);
+            float jx = 0, jy = 0, cx = 0, cy = 0;
+            for (int k = 0; k < 6; ++k) { jx += J[O_JPDXI0 + k] * dp[k]; jy += J[O_JPDXI1 + k] * dp[k]; }
+            for (int k = 0; k < 4; ++k) { cx += J[O_JPDC0 + k] * cDeltaF[k]; cy += J[O_JPDC1 + k] * cDeltaF[k]; }
+            jx = jx + cx + J[O_JPDD] * dd;
+            jy = jy + cy + J[O_JPDD + 1] * dd;
+            for (int i = 0; i < PATTERN; ++i) {
+                float Jdelta = J[O_JIDX0 + i] * jx;
+                Jdelta += J[O_JIDX1 + i] * jy;
+                Jdelta += J[O_JAB0 + i] * dp[6];
+                Jdelta += J[O_JAB1 + i] * dp[7];
+                float r0 = res_toZero[(size_t)8 * r + i];
+                r0 = r0 + r0;
+                r0 = r0 + Jdelta;
+                E += (double)(Jdelta * r0);
+            }
+        }
+        E += (double)(deltaF[p] * deltaF[p] * priorF[p]);
+    }
+    return E;
+}
+
 }  // extern "C"

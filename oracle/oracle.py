@@ -201,6 +201,39 @@ def ba_fix_linearization(F, recs, host_idx, target_idx, res_begin, deltaF, adHTd
     return out
 
 
+def ba_resubstitute(F, x, adHost, adTarget, host_idx, target_idx, res_begin, flags, JpJdF, bdSumF, Hcd_A, Hcd_L, HdiF):
+    """resubstituteF_MT: per-point step (P floats). adHost/adTarget: F*F column-major 8x8 doubles."""
+    h, t, rb = _i32(host_idx), _i32(target_idx), _i32(res_begin)
+    R, P = len(h), len(rb) - 1
+    x, ah, at = _f64(x), _f64(adHost), _f64(adTarget)
+    fl = np.ascontiguousarray(flags, np.uint8)
+    j, b, ca, cl, hd = _f32(JpJdF), _f32(bdSumF), _f32(Hcd_A), _f32(Hcd_L), _f32(HdiF)
+    out = np.zeros(P, np.float32)
+    lib().eds_oracle_ba_resubstitute(C.c_int(F), C.c_int(P), C.c_int(R), _p(x, C.c_double), _p(ah, C.c_double), _p(at, C.c_double),
+                                     _p(h, C.c_int32), _p(t, C.c_int32), _p(rb, C.c_int32), _p(fl, C.c_uint8), _p(j, C.c_float),
+                                     _p(b, C.c_float), _p(ca, C.c_float), _p(cl, C.c_float), _p(hd, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def ba_calc_l_energy(F, recs, host_idx, target_idx, res_begin, flags, res_toZero, deltaF, priorF, adHTdeltaF, cDeltaF, cPrior=None,
+                     frame_prior=None, frame_delta_prior=None):
+    """calcLEnergyF_MT (double)."""
+    recs = _f32(recs)
+    h, t, rb = _i32(host_idx), _i32(target_idx), _i32(res_begin)
+    R, P = len(h), len(rb) - 1
+    fl = np.ascontiguousarray(flags, np.uint8)
+    rtz, d, pr, a, c = _f32(res_toZero), _f32(deltaF), _f32(priorF), _f32(adHTdeltaF), _f32(cDeltaF)
+    cp = _f64(cPrior) if cPrior is not None else None
+    fp = _f64(frame_prior) if frame_prior is not None else None
+    fd = _f64(frame_delta_prior) if frame_delta_prior is not None else None
+    f = lib().eds_oracle_ba_calc_l_energy
+    f.restype = C.c_double
+    return f(C.c_int(F), C.c_int(P), C.c_int(R), _p(recs, C.c_float), _p(h, C.c_int32), _p(t, C.c_int32), _p(rb, C.c_int32),
+             _p(fl, C.c_uint8), _p(rtz, C.c_float), _p(d, C.c_float), _p(pr, C.c_float), _p(a, C.c_float), _p(c, C.c_float),
+             _p(cp, C.c_double) if cp is not None else None, _p(fp, C.c_double) if fp is not None else None,
+             _p(fd, C.c_double) if fd is not None else None)
+
+
 def ba_top_accumulate(mode, F, recs, host_idx, target_idx, res_begin, flags, res_toZero=None, deltaF=None,
                       adHTdeltaF=None, cDeltaF=None, threads=1):
     recs = _f32(recs)

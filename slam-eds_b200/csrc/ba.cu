@@ -247,6 +247,128 @@ __global__ void ba_pad_image_kernel(const float* __restrict__ src, float4* __res
     if (i < npix) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
 }
 
+// ------------------------------------------------------------------------------------------
+// After the solve: back-substitution, linearised energy, fixLinearization.
+// Everything they read (records, JpJdF, Hcd, bdSum, HdiF, flags) is already resident.
+// ------------------------------------------------------------------------------------------
+// EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:291-317): one thread per point.
+__global__ void ba_resubstitute_kernel(int F, int P, const int32_t* __restrict__ res_begin, const int32_t* __restrict__ host_idx,
+                                       const int32_t* __restrict__ target_idx, const uint8_t* __restrict__ flags,
+                                       const float* __restrict__ JpJdF, const float* __restrict__ bdSum, const float* __restrict__ HcdA,
+                                       const float* __restrict__ HcdL, const float* __restrict__ HdiF, const float* __restrict__ xAd,
+                                       const float* __restrict__ cstep, float* __restrict__ step) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    int ngood = 0;
+    float b = bdSum[p];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dot += cstep[k] * (HcdA[4 * p + k] + HcdL[4 * p + k]);
+    b -= dot;
+    for (int r = res_begin[p]; r < res_begin[p + 1]; ++r) {
+        if (!(flags[r] & EDSGPU_RES_ACTIVE)) continue;
+        ngood++;
+        const float* xa = xAd + 8 * (host_idx[r] * F + target_idx[r]);
+        const float4 j0 = *reinterpret_cast<const float4*>(JpJdF + (size_t)8 * r), j1 = *reinterpret_cast<const float4*>(JpJdF + (size_t)8 * r + 4);
+        float d = xa[0] * j0.x;
+        d += xa[1] * j0.y; d += xa[2] * j0.z; d += xa[3] * j0.w;
+        d += xa[4] * j1.x; d += xa[5] * j1.y; d += xa[6] * j1.z; d += xa[7] * j1.w;
+        b -= d;
+    }
+    step[p] = ngood ? -b * HdiF[p] : 0.f;
+}
+
+// J * delta of one residual in the image plane (fixLinearizationF / calcLEnergyPt share it)
+__device__ __forceinline__ void jp_delta(const float* __restrict__ J, const float* __restrict__ dp, const float* __restrict__ dc, float dd,
+                                         float& jx, float& jy) {
+    jx = 0.f; jy = 0.f;
+    float cx = 0.f, cy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { jx += J[O_JPDXI0 + k] * dp[k]; jy += J[O_JPDXI1 + k] * dp[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { cx += J[O_JPDC0 + k] * dc[k]; cy += J[O_JPDC1 + k] * dc[k]; }
+    jx = jx + cx + J[O_JPDD] * dd;
+    jy = jy + cy + J[O_JPDD + 1] * dd;
+}
+
+// EFResidual::fixLinearizationF (EnergyFunctionalStructs.cpp:87-113): res_toZero = resF - J delta, isLinearized = true
+__global__ void ba_fix_linearization_kernel(int F, int R, const float* __restrict__ recs, const int32_t* __restrict__ host_idx,
+                                            const int32_t* __restrict__ target_idx, const int32_t* __restrict__ point_of_res,
+                                            const float* __restrict__ deltaF, const float* __restrict__ adHTdeltaF,
+                                            const float* __restrict__ cDeltaF, const uint8_t* __restrict__ select, float* __restrict__ res_toZero,
+                                            uint8_t* __restrict__ flags) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    if (select ? !select[r] : !(flags[r] & EDSGPU_RES_ACTIVE)) return;
+    const float* J = recs + (size_t)REC * r;
+    const float* dp = adHTdeltaF + 8 * (host_idx[r] + F * target_idx[r]);
+    float jx, jy;
+    jp_delta(J, dp, cDeltaF, deltaF[point_of_res[r]], jx, jy);
+    float out[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v = J[O_RES + i];
+        v -= J[O_JIDX0 + i] * jx;
+        v -= J[O_JIDX1 + i] * jy;
+        v -= J[O_JAB0 + i] * dp[6];
+        v -= J[O_JAB1 + i] * dp[7];
+        out[i] = v;
+    }
+    float4* o = reinterpret_cast<float4*>(res_toZero + (size_t)8 * r);
+    o[0] = make_float4(out[0], out[1], out[2], out[3]);
+    o[1] = make_float4(out[4], out[5], out[6], out[7]);
+    flags[r] |= EDSGPU_RES_LINEARIZED;
+}
+
+// EnergyFunctional::calcLEnergyPt (EnergyFunctional.cpp:332-392): thread i takes residual i and point i; per-block
+// partial sums in double, summed in block order by ba_sum_partials_kernel (deterministic).
+constexpr int LE_THREADS = 256;
+__global__ void __launch_bounds__(LE_THREADS) ba_lenergy_kernel(int F, int P, int R, const float* __restrict__ recs,
+                                                                const int32_t* __restrict__ host_idx, const int32_t* __restrict__ target_idx,
+                                                                const int32_t* __restrict__ point_of_res, const uint8_t* __restrict__ flags,
+                                                                const float* __restrict__ res_toZero, const float* __restrict__ deltaF,
+                                                                const float* __restrict__ priorF, const float* __restrict__ adHTdeltaF,
+                                                                const float* __restrict__ cDeltaF, double* __restrict__ partial) {
+    __shared__ double wsum[LE_THREADS / 32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (i < R && (flags[i] & EDSGPU_RES_ACTIVE) && (flags[i] & EDSGPU_RES_LINEARIZED)) {
+        const float* J = recs + (size_t)REC * i;
+        const float* dp = adHTdeltaF + 8 * (host_idx[i] + F * target_idx[i]);
+        float jx, jy;
+        jp_delta(J, dp, cDeltaF, deltaF[point_of_res[i]], jx, jy);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float Jdelta = J[O_JIDX0 + k] * jx;
+            Jdelta += J[O_JIDX1 + k] * jy;
+            Jdelta += J[O_JAB0 + k] * dp[6];
+            Jdelta += J[O_JAB1 + k] * dp[7];
+            float r0 = res_toZero[(size_t)8 * i + k];
+            r0 = r0 + r0;
+            r0 = r0 + Jdelta;
+            e += (double)(Jdelta * r0);
+        }
+    }
+    if (i < P) e += (double)(deltaF[i] * deltaF[i] * priorF[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < LE_THREADS / 32; ++w) s += wsum[w];
+        partial[blockIdx.x] = s;
+    }
+}
+__global__ void ba_sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    // one warp, fixed order: lane l sums l, l+32, ...; then a butterfly
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = s;
+}
+
 // ---- TMA bulk-copy + mbarrier helpers -------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -790,6 +912,8 @@ struct edsgpu_ba {
     float calib[4] = {0, 0, 0, 0};
     bool lin_inputs_set = false;
     unsigned images_set = 0;  // bit per frame
+    std::vector<double> adHost_h, adTarget_h;  // host copies for xAd of the back-substitution
+    void* post_block = nullptr;                // xAd (F*F*8 floats), cstep (4), step (P), energy partials
 };
 
 namespace {
@@ -925,6 +1049,7 @@ void edsgpu_ba_destroy(edsgpu_ba* w) {
     if (w->block) cudaFree(w->block);
     if (w->images) cudaFree(w->images);
     if (w->lin_block) cudaFree(w->lin_block);
+    if (w->post_block) cudaFree(w->post_block);
     delete w;
 }
 
@@ -964,6 +1089,8 @@ edsgpu_status edsgpu_ba_set_frames(edsgpu_ba* w, const float* adHTdeltaF, const 
     if (cDeltaF) EDS_CUDA(ctx, cudaMemcpyAsync(w->cDeltaF, cDeltaF, 16, cudaMemcpyHostToDevice, ctx->stream));
     if (adHost) EDS_CUDA(ctx, cudaMemcpyAsync(w->adHost, adHost, 512 * F2, cudaMemcpyHostToDevice, ctx->stream));
     if (adTarget) EDS_CUDA(ctx, cudaMemcpyAsync(w->adTarget, adTarget, 512 * F2, cudaMemcpyHostToDevice, ctx->stream));
+    if (adHost) w->adHost_h.assign(adHost, adHost + 64 * F2);
+    if (adTarget) w->adTarget_h.assign(adTarget, adTarget + 64 * F2);
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EDSGPU_OK;
 }
@@ -1197,6 +1324,116 @@ edsgpu_status edsgpu_ba_get_residuals(edsgpu_ba* w, float* recs_out, uint8_t* fl
     if (recs_out) EDS_CUDA(ctx, cudaMemcpyAsync(recs_out, w->recs, 4 * (size_t)REC * w->R, cudaMemcpyDeviceToHost, ctx->stream));
     if (flags_out) EDS_CUDA(ctx, cudaMemcpyAsync(flags_out, w->flags, (size_t)w->R, cudaMemcpyDeviceToHost, ctx->stream));
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+// ---- after the solve ------------------------------------------------------------------------
+namespace {
+edsgpu_status ensure_post_block(edsgpu_ba* w) {
+    if (w->post_block) return EDSGPU_OK;
+    const size_t n_part = (size_t)(std::max(w->R, w->P) + LE_THREADS - 1) / LE_THREADS;
+    const size_t bytes = align_up(32 * (size_t)w->F * w->F, 256) + 256 + align_up(4 * (size_t)w->P, 256) + align_up(8 * n_part, 256) + 256;
+    cudaError_t e = cudaMalloc(&w->post_block, bytes);
+    if (e != cudaSuccess) return edsgpu_fail(w->ctx, e == cudaErrorMemoryAllocation ? EDSGPU_OUT_OF_MEMORY : EDSGPU_CUDA_ERROR, cudaGetErrorString(e));
+    return EDSGPU_OK;
+}
+}  // namespace
+
+edsgpu_status edsgpu_ba_resubstitute(edsgpu_ba* w, const double* x, float* point_step_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, x != nullptr, "ba_resubstitute: null x");
+    const size_t F = w->F, F2 = F * F;
+    EDS_REQUIRE(ctx, w->adHost_h.size() == 64 * F2 && w->adTarget_h.size() == 64 * F2, "ba_resubstitute: call edsgpu_ba_set_frames with the adjoints first");
+    DeviceGuard g(ctx->device);
+    edsgpu_status st = ensure_post_block(w);
+    if (st == EDSGPU_OK) st = edsgpu_ensure_pinned(ctx, 4 * (8 * F2 + 4));
+    if (st != EDSGPU_OK) return st;
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned block is shared
+    // xAd[F*h + t] = xF_h^T adHostF[h + F*t] + xF_t^T adTargetF[h + F*t]  (EnergyFunctional.cpp:272-281), float
+    float* xAd = (float*)ctx->pinned;
+    float* cstep = xAd + 8 * F2;
+    std::vector<float> xF(4 + 8 * F);
+    for (size_t i = 0; i < xF.size(); ++i) xF[i] = (float)x[i];
+    for (size_t h = 0; h < F; ++h)
+        for (size_t t = 0; t < F; ++t) {
+            const double* AH = &w->adHost_h[64 * (h + F * t)];
+            const double* AT = &w->adTarget_h[64 * (h + F * t)];
+            for (int c = 0; c < 8; ++c) {
+                float a = 0.f, b = 0.f;
+                for (int k = 0; k < 8; ++k) a += xF[4 + 8 * h + k] * (float)AH[c * 8 + k];
+                for (int k = 0; k < 8; ++k) b += xF[4 + 8 * t + k] * (float)AT[c * 8 + k];
+                xAd[8 * (F * h + t) + c] = a + b;
+            }
+        }
+    for (int k = 0; k < 4; ++k) cstep[k] = xF[k];
+    char* pb = (char*)w->post_block;
+    float* d_xAd = (float*)pb;
+    float* d_cstep = (float*)(pb + align_up(32 * F2, 256));
+    float* d_step = (float*)(pb + align_up(32 * F2, 256) + 256);
+    EDS_CUDA(ctx, cudaMemcpyAsync(d_xAd, xAd, 32 * F2, cudaMemcpyHostToDevice, ctx->stream));
+    EDS_CUDA(ctx, cudaMemcpyAsync(d_cstep, cstep, 16, cudaMemcpyHostToDevice, ctx->stream));
+    ba_resubstitute_kernel<<<(w->P + 127) / 128, 128, 0, ctx->stream>>>(w->F, w->P, w->res_begin, w->host_idx, w->target_idx, w->flags, w->JpJdF,
+                                                                       w->bdSum, w->Hcd[0], w->Hcd[1], w->HdiF, d_xAd, d_cstep, d_step);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    if (point_step_out) EDS_CUDA(ctx, cudaMemcpyAsync(point_step_out, d_step, 4 * (size_t)w->P, cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_fix_linearization(edsgpu_ba* w, const uint8_t* select, float* res_toZero_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    DeviceGuard g(ctx->device);
+    uint8_t* d_select = nullptr;
+    if (select) {
+        edsgpu_status st = edsgpu_ensure_scratch(ctx, (size_t)w->R);
+        if (st != EDSGPU_OK) return st;
+        d_select = (uint8_t*)ctx->scratch;
+        EDS_CUDA(ctx, cudaMemcpyAsync(d_select, select, (size_t)w->R, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ba_fix_linearization_kernel<<<(w->R + 255) / 256, 256, 0, ctx->stream>>>(w->F, w->R, w->recs, w->host_idx, w->target_idx, w->point_of_res,
+                                                                            w->deltaF, w->adHTdeltaF, w->cDeltaF, d_select, w->res_toZero, w->flags);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    if (res_toZero_out) EDS_CUDA(ctx, cudaMemcpyAsync(res_toZero_out, w->res_toZero, 32 * (size_t)w->R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (select || res_toZero_out) EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_calc_l_energy(edsgpu_ba* w, const double* cPrior, const double* frame_prior, const double* frame_delta_prior,
+                                      double* energy_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, energy_out != nullptr, "ba_calc_l_energy: null output");
+    DeviceGuard g(ctx->device);
+    edsgpu_status st = ensure_post_block(w);
+    if (st == EDSGPU_OK) st = edsgpu_ensure_pinned(ctx, 64);
+    if (st != EDSGPU_OK) return st;
+    const size_t F = w->F, F2 = F * F;
+    const int n_part = (std::max(w->R, w->P) + LE_THREADS - 1) / LE_THREADS;
+    char* pb = (char*)w->post_block;
+    double* d_partial = (double*)(pb + align_up(32 * F2, 256) + 256 + align_up(4 * (size_t)w->P, 256));
+    double* d_sum = d_partial + align_up(8 * (size_t)n_part, 256) / 8;
+    ba_lenergy_kernel<<<n_part, LE_THREADS, 0, ctx->stream>>>(w->F, w->P, w->R, w->recs, w->host_idx, w->target_idx, w->point_of_res, w->flags,
+                                                            w->res_toZero, w->deltaF, w->priorF, w->adHTdeltaF, w->cDeltaF, d_partial);
+    ctx->launches++;
+    ba_sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(d_partial, n_part, d_sum);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    float cd[4];
+    EDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_sum, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 16, w->cDeltaF, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double E = *(double*)ctx->pinned;
+    memcpy(cd, (char*)ctx->pinned + 16, 16);
+    // EnergyFunctional.cpp:403-409: frame and calibration prior terms
+    if (frame_prior && frame_delta_prior)
+        for (size_t i = 0; i < 8 * F; ++i) E += frame_delta_prior[i] * frame_prior[i] * frame_delta_prior[i];
+    if (cPrior)
+        for (int k = 0; k < 4; ++k) E += (double)cd[k] * (double)(float)cPrior[k] * (double)cd[k];
+    *energy_out = E;
     return EDSGPU_OK;
 }
 

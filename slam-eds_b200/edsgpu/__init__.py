@@ -35,6 +35,7 @@ SYMBOLS = [
     "edsgpu_ba_create", "edsgpu_ba_destroy", "edsgpu_ba_set_residuals", "edsgpu_ba_set_points", "edsgpu_ba_set_frames",
     "edsgpu_ba_top_accumulate", "edsgpu_ba_top_stitch", "edsgpu_ba_sc_accumulate", "edsgpu_ba_sc_stitch", "edsgpu_ba_get_jpjd",
     "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_get_residuals",
+    "edsgpu_ba_resubstitute", "edsgpu_ba_fix_linearization", "edsgpu_ba_calc_l_energy",
 ]
 
 
@@ -375,6 +376,28 @@ class BaWindow:
         self.ctx.check(self.ctx.lib.edsgpu_ba_linearize(self.h, _ptr(si, C.c_uint8), _ptr(li, C.c_uint8), _ptr(rtz, C.c_float),
                                                         _ptr(st, C.c_int32), _ptr(en, C.c_float)))
         return (st, en) if want_outputs else None
+
+    # ---- after the solve (EnergyFunctional.cpp:263-415, EnergyFunctionalStructs.cpp:87-113) ----
+    def resubstitute(self, x):
+        """resubstituteF_MT: per-point step from the solved update x (4 + 8F)."""
+        x = np.ascontiguousarray(x, np.float64)
+        assert x.shape == (self.n,)
+        step = np.zeros(self.P, np.float32)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_resubstitute(self.h, _ptr(x, C.c_double), _ptr(step, C.c_float)))
+        return step
+
+    def fix_linearization(self, select=None, want_output=True):
+        sel = np.ascontiguousarray(select, np.uint8) if select is not None else None
+        out = np.zeros((self.R, 8), np.float32) if want_output else None
+        self.ctx.check(self.ctx.lib.edsgpu_ba_fix_linearization(self.h, _ptr(sel, C.c_uint8), _ptr(out, C.c_float)))
+        return out
+
+    def calc_l_energy(self, cPrior=None, frame_prior=None, frame_delta_prior=None):
+        f64 = lambda a: np.ascontiguousarray(a, np.float64) if a is not None else None  # noqa: E731
+        cp, fp, fd = f64(cPrior), f64(frame_prior), f64(frame_delta_prior)
+        e = C.c_double(0.0)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_calc_l_energy(self.h, _ptr(cp, C.c_double), _ptr(fp, C.c_double), _ptr(fd, C.c_double), C.byref(e)))
+        return e.value
 
     def get_residuals(self):
         recs, flags = np.zeros((self.R, 76), np.float32), np.zeros(self.R, np.uint8)

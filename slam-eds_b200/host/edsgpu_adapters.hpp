@@ -270,6 +270,17 @@ class HessianAccumulators {
         ctx_.check(edsgpu_ba_sc_stitch(ba_, H.data(), b.data()));
     }
 
+    // resubstituteF_MT(x): PointHessian::step of every point (EnergyFunctional.cpp:263-317)
+    void resubstituteF_MT(const double* x, float* pointStep) { ctx_.check(edsgpu_ba_resubstitute(ba_, x, pointStep)); }
+    // calcLEnergyF_MT() (EnergyFunctional.cpp:396-415)
+    double calcLEnergyF_MT(const double cPrior[4], const double* framePrior, const double* frameDeltaPrior) {
+        double e = 0.0;
+        ctx_.check(edsgpu_ba_calc_l_energy(ba_, cPrior, framePrior, frameDeltaPrior, &e));
+        return e;
+    }
+    // EFResidual::fixLinearizationF for the selected residuals (EnergyFunctionalStructs.cpp:87-113)
+    void fixLinearizationF(const uint8_t* select, float* res_toZeroF = nullptr) { ctx_.check(edsgpu_ba_fix_linearization(ba_, select, res_toZeroF)); }
+
   private:
     const edsgpu_host::Context& ctx_;
     edsgpu_ba* ba_ = nullptr;

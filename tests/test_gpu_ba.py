@@ -152,6 +152,41 @@ def test_device_linearize_is_bit_exact_and_feeds_the_accumulators(gpu_ctx, cfg):
     w.close(); w2.close()
 
 
+def test_back_substitution_energy_and_fix_linearization(solved):
+    """The steps right after the solve on data that is still on the device:
+    resubstituteF_MT, calcLEnergyF_MT, fixLinearizationF against the CPU oracle."""
+    pb, rtz, w = solved
+    F = pb["F"]
+    rng = np.random.default_rng(11)
+    x = rng.normal(scale=1e-3, size=4 + 8 * F)
+    top0, top1, sc = w.top_accumulate(0), w.top_accumulate(1), w.sc_accumulate(True)
+    step = w.resubstitute(x)
+    ref = O.ba_resubstitute(F, x, SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]), pb["host_idx"], pb["target_idx"],
+                            pb["res_begin"], pb["flags"], w.jpjd(), sc["bdSum"], top0["Hcd"], top1["Hcd"], sc["HdiF"])
+    assert rel(step, ref) < TOL
+    nores = np.diff(pb["res_begin"]) == 0
+    assert np.all(step[nores] == 0)
+    # linearised energy
+    e = w.calc_l_energy(pb["cPrior"], pb["frame_prior"], pb["frame_delta_prior"])
+    e_ref = O.ba_calc_l_energy(F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"], pb["priorF"],
+                               pb["adHTdeltaF"], pb["cDeltaF"], pb["cPrior"], pb["frame_prior"], pb["frame_delta_prior"])
+    assert abs(e - e_ref) <= TOL * abs(e_ref)
+    e0 = w.calc_l_energy()
+    e0_ref = O.ba_calc_l_energy(F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"], pb["priorF"],
+                                pb["adHTdeltaF"], pb["cDeltaF"])
+    assert abs(e0 - e0_ref) <= TOL * max(abs(e0_ref), 1e-30)
+    # fixLinearizationF for a subset: same arithmetic as the oracle, so the same bits; flags gain LINEARIZED
+    sel = (rng.random(pb["R"]) < 0.3).astype(np.uint8)
+    out = w.fix_linearization(sel)
+    ref_rtz = O.ba_fix_linearization(F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["deltaF"], pb["adHTdeltaF"], pb["cDeltaF"])
+    m = sel.astype(bool)
+    assert rel(out[m], ref_rtz[m]) < 1e-6
+    assert np.array_equal(out[~m], rtz[~m])
+    _, flags = w.get_residuals()
+    assert np.all(flags[m] & 2) and np.array_equal(flags[~m], pb["flags"][~m])
+    w.set_residuals(pb["recs"], pb["flags"], rtz)  # restore for the other tests of the module
+
+
 def test_linearize_needs_its_inputs(gpu_ctx):
     pb = SB.make_ba_problem(F=3, points_per_frame=50, H=64, W=80)
     w = edsgpu.BaWindow(gpu_ctx, pb["F"], pb["host_idx"], pb["target_idx"], pb["res_begin"])

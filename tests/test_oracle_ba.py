@@ -255,3 +255,33 @@ def test_linearize_state_machine_and_known_answers():
     _, state2, _ = O.ba_linearize(F, H, W, dI, pre, [fx, fy, cx, cy], pu, pv, idp, idp, color, weights, host, target, rb, th,
                                   state_in=np.array([1, 0, 0], np.uint8))
     assert list(state2) == [1, 1, 2]
+
+
+def test_resubstitute_and_l_energy_known_answers():
+    """resubstituteFPt / calcLEnergyPt (EnergyFunctional.cpp:291-392) on hand-checkable inputs."""
+    F, P = 2, 3
+    host = np.array([0, 0, 1], np.int32); target = np.array([1, 1, 0], np.int32)
+    rb = np.array([0, 2, 3, 3], np.int32)               # point 2 has no residual
+    flags = np.array([1, 0, 1], np.uint8)               # the second residual of point 0 is inactive
+    eye = np.stack([np.eye(8)] * (F * F))
+    x = np.zeros(4 + 8 * F); x[0] = 2.0; x[4 + 1] = 3.0; x[4 + 8 + 1] = 5.0   # calib[0], frame0[1], frame1[1]
+    JpJd = np.zeros((3, 8), np.float32); JpJd[:, 1] = [1.0, 100.0, 2.0]
+    bd = np.array([10.0, 20.0, 30.0], np.float32)
+    HcdA = np.zeros((P, 4), np.float32); HcdA[:, 0] = 1.0
+    HcdL = np.zeros((P, 4), np.float32); HcdL[:, 0] = 0.5
+    Hdi = np.array([0.5, 0.25, 1.0], np.float32)
+    step = O.ba_resubstitute(F, x, SB.col_major(eye), SB.col_major(eye), host, target, rb, flags, JpJd, bd, HcdA, HcdL, Hdi)
+    # xAd[h,t][1] = x_h[1] + x_t[1] = 8 for both pairs; b = bd - 2*(1.5) - 8*JpJd[.,1]
+    assert np.allclose(step, [-(10 - 3 - 8 * 1.0) * 0.5, -(20 - 3 - 8 * 2.0) * 0.25, 0.0])
+    # energy: zero deltas leave only the depth prior term; a single linearised residual adds (2 rtz + J d) . J d
+    recs = np.zeros((3, 76), np.float32)
+    recs[0, 56:64] = 1.0                                 # JabF[1] = 1: J delta = delta_b
+    rtz = np.zeros((3, 8), np.float32); rtz[0] = 0.5
+    deltaF = np.array([0.1, 0.0, 0.2], np.float32); priorF = np.array([0.0, 7.0, 2500.0], np.float32)
+    ad = np.zeros((F * F, 8), np.float32)
+    lin = np.array([3, 0, 1], np.uint8)                  # residual 0 active + linearised
+    e = O.ba_calc_l_energy(F, recs, host, target, rb, lin, rtz, deltaF, priorF, ad, np.zeros(4, np.float32))
+    assert np.isclose(e, 0.2 * 0.2 * 2500.0)
+    ad[0 + F * 1, 7] = 0.25                              # delta_b of (host 0, target 1)
+    e = O.ba_calc_l_energy(F, recs, host, target, rb, lin, rtz, deltaF, priorF, ad, np.zeros(4, np.float32))
+    assert np.isclose(e, 100.0 + 8 * (2 * 0.5 + 0.25) * 0.25)
