@@ -230,6 +230,19 @@ def bench_ba(ctx, stream, reps=50):
     # per residual: 8 pattern pixels x 4 taps x 16 B gathered, 80 B of point state, 112 B of precalc, 304 B record + 32 B JpJdF
     # written (and the record read once more by takeDataF), 9 B of state / energy / flag
     lin_alg = R * (8 * 4 * 16 + 80 + 112 + 304 + 304 + 32 + 9)
+    # after the solve: back-substitution + linearised energy, host-synchronous calls
+    once()
+    xs = np.random.default_rng(0).normal(scale=1e-3, size=4 + 8 * F)
+    for _ in range(3):
+        w.resubstitute(xs); w.calc_l_energy()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        w.resubstitute(xs)
+    resub_ms = 1e3 * (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        w.calc_l_energy()
+    energy_ms = 1e3 * (time.perf_counter() - t0) / 20
     w.close()
     return {"workload": "config4: F=7, P=%d, R=%d; top<0> + top<1> + SC accumulate, device-resident" % (P, R),
             "accumulations_per_s": 1e3 / ms, "ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
@@ -237,7 +250,9 @@ def bench_ba(ctx, stream, reps=50):
             "linearize": {"what": "PointFrameResidual::linearize + takeDataF for all R residuals on the device (records stay in HBM)",
                           "ms": lin_ms, "residuals_per_s": R / (lin_ms * 1e-3), "algorithmic_bytes": lin_alg,
                           "achieved_gbs": lin_alg / (lin_ms * 1e-3) / 1e9, "cpu_port_ms_1_thread": lin_cpu_ms,
-                          "upload_avoided_bytes": 304 * R}}
+                          "upload_avoided_bytes": 304 * R},
+            "after_solve": {"what": "resubstituteF_MT (P steps back to the host) and calcLEnergyF_MT, wall clock per host-synchronous call",
+                            "resubstitute_ms": resub_ms, "calc_l_energy_ms": energy_ms}}
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -417,7 +432,7 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(S * E * 5), "d2h_bytes_per_step": int(S * 14 * 8),
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "how": "edsgpu_event_frame_create_batch (pinned host events) + edsgpu_batch_optimize + state read-back every step; "
-                           "next window's H2D overlaps the current solve"},
+                           "next window's H2D copy and frame build (other bank of slots, build stream) overlap the current solve"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"kernel": "track_lm_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
