@@ -33,3 +33,19 @@ w.set_residuals(pb["recs"], pb["flags"], np.zeros((pb["R"], 8), np.float32)); w.
 w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], synth_ba.col_major(pb["adHost"]), synth_ba.col_major(pb["adTarget"]))
 for m in (0, 1, 2): w.top_accumulate(m)
 w.top_stitch(0); w.sc_accumulate(True); w.sc_stitch(); print("ba ok")
+# the feeder and the after-solve steps on the device
+w.set_images(pb["dI"])
+w.set_linearize_inputs(pb["precalc"], pb["calib"], pb["frame_energy_th"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"], pb["color"], pb["weights"])
+st, en = w.linearize(linearized=(pb["flags"] >> 1) & 1, res_toZero=np.zeros((pb["R"], 8), np.float32))
+for m in (0, 1): w.top_accumulate(m)
+w.sc_accumulate(True)
+w.resubstitute(np.full(4 + 8 * pb["F"], 1e-3)); w.calc_l_energy(); w.fix_linearization(None); print("ba linearize / after-solve ok", np.bincount(st))
+# frames built ahead in two banks, K problems in flight per cluster
+fr2 = edsgpu.Frames(ctx, H, W, 2 * n)
+banks = [edsgpu.TrackerBatch(ctx, trs, [kfd] * n, fr2, k * n) for k in (0, 1)]
+ev = (np.tile(wins[0]["x"], n), np.tile(wins[0]["y"], n), np.tile(wins[0]["pol"], n))
+edsgpu.event_frames_batch(ctx, fr2, 0, n, *ev, E)
+for k in range(3):
+    edsgpu.event_frames_batch(ctx, fr2, ((k + 1) & 1) * n, n, *ev, E)
+    banks[k & 1].optimize()
+ctx.synchronize(); print("pipelined ok")
