@@ -278,6 +278,29 @@ edsgpu_status edsgpu_ba_calc_l_energy(edsgpu_ba* ba, const double* cPrior, const
 /* debug/parity: the records and flags as they sit on the device (R x 76 floats, R bytes). */
 edsgpu_status edsgpu_ba_get_residuals(edsgpu_ba* ba, float* recs_out, uint8_t* flags_out);
 
+/* ---- DSO coarse tracker evaluation ----------------------------------
+ * CoarseTracker::calcRes fused with CoarseTracker::calcGSSSE (src/tracking/CoarseTracker.cpp:
+ * 287-498): direct alignment of a new frame against the reference point cloud at one pyramid
+ * level.  The Gauss-Newton loop of trackNewestCoarse (:520-701) stays on the host (8x8 solves);
+ * each of its evaluations is one call. */
+typedef struct edsgpu_coarse edsgpu_coarse;
+edsgpu_status edsgpu_coarse_create(edsgpu_ctx* ctx, int num_levels, edsgpu_coarse** out);
+void edsgpu_coarse_destroy(edsgpu_coarse* coarse);
+/* makeK (:67-100): size and intrinsics of pyramid level lvl, Ki = K[lvl].inverse() as Eigen stores
+ * it (9 floats, column-major). */
+edsgpu_status edsgpu_coarse_set_level(edsgpu_coarse* coarse, int lvl, int width, int height, float fx, float fy, float cx, float cy,
+                                      const float Ki[9]);
+/* setCoarseTrackingRef / makeCoarseDepthL0 output (:103-283): pc_u, pc_v, pc_idepth, pc_color of level lvl. */
+edsgpu_status edsgpu_coarse_set_reference(edsgpu_coarse* coarse, int lvl, int n, const float* pc_u, const float* pc_v,
+                                          const float* pc_idepth, const float* pc_color);
+/* newFrame->dIp[lvl]: height*width Vec3f {I, dx, dy}. */
+edsgpu_status edsgpu_coarse_set_new_frame(edsgpu_coarse* coarse, int lvl, const float* dI);
+/* R (row-major), t: refToNew; affLL = AffLight::fromToVecExposure(...) as floats, b0 = lastRef_aff_g2l.b.
+ * rs: the Vec6 calcRes returns {E, numTermsInE, flow_t, 0, flow_rt, saturated ratio}; H (8x8), b (8):
+ * calcGSSSE's outputs including the SCALE_* factors; H and b may be NULL (residual only). */
+edsgpu_status edsgpu_coarse_calc_res_gs(edsgpu_coarse* coarse, int lvl, const double R[9], const double t[3], const float affLL[2],
+                                        float b0, float cutoffTH, double rs[6], double H[64], double b[8]);
+
 #ifdef __cplusplus
 }
 #endif

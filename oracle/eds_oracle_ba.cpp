@@ -626,4 +626,111 @@ double eds_oracle_ba_calc_l_energy(int F, int P, int R, const float* recs, const
     return E;
 }
 
+// CoarseTracker::calcRes + calcGSSSE, src/tracking/CoarseTracker.cpp:287-498: direct image
+// alignment of a new frame against the reference point cloud at one pyramid level -- residual statistics and the
+// 8x8 Gauss-Newton system (6 pose + 2 affine brightness).  float arithmetic in the reference's operation order
+// (built with -ffp-contract=off); the sums E, H, b are taken in double where the reference uses float accumulators.
+//   dINew [hl*wl*3] Vec3f {I,dx,dy};  Ki [9] column-major float (K[lvl].inverse());  R [9] row-major, t [3]: refToNew
+//   affLL {a, b} = AffLight::fromToVecExposure(...), b0 = lastRef_aff_g2l.b
+// out: rs[6] as calcRes returns it, H [64] row-major, b [8], counts {numTermsInE, numTermsInWarped (unpadded), numSaturated}
+void eds_oracle_coarse_calc_res_gs(int lvl, int wl, int hl, const float* dINew, float fxl, float fyl, float cxl, float cyl, const float* Ki,
+                                   const double* R, const double* t, const float* affLL, float b0, float cutoffTH, int n, const float* pc_u,
+                                   const float* pc_v, const float* pc_idepth, const float* pc_color, double* rs, double* H_out, double* b_out,
+                                   int64_t* counts) {
+    const float setting_huberTH = 9.0f;  // settings.cpp:127
+    float RKi[3][3], tf[3];
+    for (int i = 0; i < 3; ++i) {
+        tf[i] = (float)t[i];
+        for (int j = 0; j < 3; ++j)
+            RKi[i][j] = ((float)R[3 * i + 0] * Ki[3 * j + 0] + (float)R[3 * i + 1] * Ki[3 * j + 1]) + (float)R[3 * i + 2] * Ki[3 * j + 2];
+    }
+    auto KiM = [&](int i, int j) { return Ki[3 * j + i]; };
+    double E = 0;
+    int64_t numTermsInE = 0, numTermsInWarped = 0, numSaturated = 0;
+    float sumSquaredShiftT = 0, sumSquaredShiftRT = 0, sumSquaredShiftNum = 0;
+    const float maxEnergy = 2 * setting_huberTH * cutoffTH - setting_huberTH * setting_huberTH;  // :372
+    double acc[9][9];
+    for (auto& row : acc) for (double& v : row) v = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const float id = pc_idepth[i], x = pc_u[i], y = pc_v[i];
+        float pt[3];
+        for (int k = 0; k < 3; ++k) pt[k] = ((RKi[k][0] * x + RKi[k][1] * y) + RKi[k][2] * 1.0f) + tf[k] * id;
+        const float u = pt[0] / pt[2], v = pt[1] / pt[2];
+        const float Ku = fxl * u + cxl, Kv = fyl * v + cyl;
+        const float new_idepth = id / pt[2];
+        if (lvl == 0 && i % 32 == 0) {  // :403-434: mean optical flow, translation only and rotation + translation
+            float p1[3], p2[3], p3[3];
+            for (int k = 0; k < 3; ++k) {
+                const float kp = (KiM(k, 0) * x + KiM(k, 1) * y) + KiM(k, 2) * 1.0f;
+                p1[k] = kp + tf[k] * id;
+                p2[k] = kp - tf[k] * id;
+                p3[k] = ((RKi[k][0] * x + RKi[k][1] * y) + RKi[k][2] * 1.0f) - tf[k] * id;
+            }
+            const float KuT = fxl * (p1[0] / p1[2]) + cxl, KvT = fyl * (p1[1] / p1[2]) + cyl;
+            const float KuT2 = fxl * (p2[0] / p2[2]) + cxl, KvT2 = fyl * (p2[1] / p2[2]) + cyl;
+            const float Ku3 = fxl * (p3[0] / p3[2]) + cxl, Kv3 = fyl * (p3[1] / p3[2]) + cyl;
+            sumSquaredShiftT += (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
+            sumSquaredShiftT += (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+            sumSquaredShiftRT += (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
+            sumSquaredShiftRT += (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+            sumSquaredShiftNum += 2;
+        }
+        if (!(Ku > 2 && Kv > 2 && Ku < wl - 3 && Kv < hl - 3 && new_idepth > 0)) continue;
+        const float refColor = pc_color[i];
+        const int ix = (int)Ku, iy = (int)Kv;  // getInterpolatedElement33, globalFuncs.h:78-92
+        const float dx = Ku - ix, dy = Kv - iy, dxdy = dx * dy;
+        const float* bp = dINew + (size_t)3 * (ix + iy * wl);
+        float hit[3];
+        for (int c = 0; c < 3; ++c)
+            hit[c] = ((dxdy * bp[3 * (1 + wl) + c] + (dy - dxdy) * bp[3 * wl + c]) + (dx - dxdy) * bp[3 + c]) + (1 - dx - dy + dxdy) * bp[c];
+        if (!std::isfinite(hit[0])) continue;
+        const float residual = hit[0] - (float)(affLL[0] * refColor + affLL[1]);
+        const float hw = fabsf(residual) < setting_huberTH ? 1 : setting_huberTH / fabsf(residual);
+        if (fabsf(residual) > cutoffTH) {
+            E += maxEnergy;
+            numTermsInE++;
+            numSaturated++;
+            continue;
+        }
+        E += hw * residual * residual * (2 - hw);
+        numTermsInE++;
+        numTermsInWarped++;
+        // calcGSSSE :303-330 on the warped sample
+        const float ddx = hit[1] * fxl, ddy = hit[2] * fyl;
+        float J[9];
+        J[0] = new_idepth * ddx;
+        J[1] = new_idepth * ddy;
+        J[2] = 0 - new_idepth * (u * ddx + v * ddy);
+        J[3] = 0 - ((u * v) * ddx + ddy * (1 + v * v));
+        J[4] = (u * v) * ddy + ddx * (1 + u * u);
+        J[5] = u * ddy - v * ddx;
+        J[6] = affLL[0] * (b0 - refColor);
+        J[7] = -1;
+        J[8] = residual;
+        for (int a = 0; a < 9; ++a) {
+            const float Jw = J[a] * hw;  // MatrixAccumulators.h:1091-1150
+            for (int c = a; c < 9; ++c) acc[a][c] += (double)(Jw * J[c]);
+        }
+    }
+    const int64_t npad = (numTermsInWarped + 3) / 4 * 4;  // :466-478: the SSE buffers are padded with zeros
+    const float inv_n = 1.0f / (float)npad;
+    for (int a = 0; a < 8; ++a) {
+        for (int c = 0; c < 8; ++c) H_out[8 * a + c] = (double)(float)acc[a < c ? a : c][a < c ? c : a] * inv_n;
+        b_out[a] = (double)(float)acc[a][8] * inv_n;
+    }
+    // SCALE_XI_ROT = SCALE_XI_TRANS = 1, SCALE_A = 10, SCALE_B = 1000 (HessianBlocks.h:59-65), :333-344
+    const double sc[8] = {1, 1, 1, 1, 1, 1, 10.0f, 1000.0f};
+    for (int a = 0; a < 8; ++a) {
+        for (int c = 0; c < 8; ++c) H_out[8 * a + c] *= (sc[a] * sc[c]);
+        b_out[a] *= sc[a];
+    }
+    rs[0] = E;
+    rs[1] = (double)numTermsInE;
+    rs[2] = sumSquaredShiftT / (sumSquaredShiftNum + 0.1);
+    rs[3] = 0;
+    rs[4] = sumSquaredShiftRT / (sumSquaredShiftNum + 0.1);
+    rs[5] = numSaturated / (float)numTermsInE;
+    counts[0] = numTermsInE; counts[1] = numTermsInWarped; counts[2] = numSaturated;
+}
+
 }  // extern "C"

@@ -302,3 +302,21 @@ def ba_sc_stitch(F, sc, adHost, adTarget):
                                   _p(_f64(sc["accbc"]), C.c_double), _p(ah, C.c_double), _p(at, C.c_double),
                                   _p(H, C.c_double), _p(b, C.c_double))
     return H, b
+
+
+# ----------------------------------------------------------------------------- coarse tracker
+def coarse_calc_res_gs(lvl, dI, fx, fy, cx, cy, Ki, R, t, affLL, b0, cutoffTH, pc_u, pc_v, pc_idepth, pc_color):
+    """CoarseTracker::calcRes + calcGSSSE at one level -> dict(rs[6], H[8,8], b[8], counts[3])."""
+    dI = _f32(dI)
+    hl, wl = dI.shape[0], dI.shape[1]
+    Ki, aff = _f32(Ki).reshape(-1), _f32(affLL)
+    R, t = _f64(R).reshape(-1), _f64(t)
+    u, v, idp, col = _f32(pc_u), _f32(pc_v), _f32(pc_idepth), _f32(pc_color)
+    rs, H, b = np.zeros(6), np.zeros((8, 8)), np.zeros(8)
+    counts = np.zeros(3, np.int64)
+    lib().eds_oracle_coarse_calc_res_gs(C.c_int(lvl), C.c_int(wl), C.c_int(hl), _p(dI, C.c_float), C.c_float(fx), C.c_float(fy), C.c_float(cx),
+                                        C.c_float(cy), _p(Ki, C.c_float), _p(R, C.c_double), _p(t, C.c_double), _p(aff, C.c_float),
+                                        C.c_float(b0), C.c_float(cutoffTH), C.c_int(len(u)), _p(u, C.c_float), _p(v, C.c_float),
+                                        _p(idp, C.c_float), _p(col, C.c_float), _p(rs, C.c_double), _p(H, C.c_double), _p(b, C.c_double),
+                                        _p(counts, C.c_int64))
+    return dict(rs=rs, H=H, b=b, counts=counts)

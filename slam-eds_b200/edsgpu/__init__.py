@@ -36,6 +36,8 @@ SYMBOLS = [
     "edsgpu_ba_top_accumulate", "edsgpu_ba_top_stitch", "edsgpu_ba_sc_accumulate", "edsgpu_ba_sc_stitch", "edsgpu_ba_get_jpjd",
     "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_get_residuals",
     "edsgpu_ba_resubstitute", "edsgpu_ba_fix_linearization", "edsgpu_ba_calc_l_energy",
+    "edsgpu_coarse_create", "edsgpu_coarse_destroy", "edsgpu_coarse_set_level", "edsgpu_coarse_set_reference",
+    "edsgpu_coarse_set_new_frame", "edsgpu_coarse_calc_res_gs",
 ]
 
 
@@ -465,4 +467,46 @@ class BaWindow:
     def close(self):
         if self.h:
             self.ctx.lib.edsgpu_ba_destroy(self.h)
+            self.h = None
+
+
+class CoarseTracker:
+    """Evaluation side of dso::CoarseTracker (src/tracking/CoarseTracker.cpp): calcRes fused with
+    calcGSSSE per pyramid level on the device; the Gauss-Newton loop of trackNewestCoarse stays with
+    the caller."""
+
+    def __init__(self, ctx, num_levels):
+        self.ctx, self.num_levels = ctx, num_levels
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.edsgpu_coarse_create(ctx.h, C.c_int(num_levels), C.byref(self.h)))
+
+    def set_level(self, lvl, width, height, fx, fy, cx, cy, Ki):
+        ki = np.ascontiguousarray(Ki, np.float32).reshape(-1)
+        assert ki.shape == (9,)
+        self.ctx.check(self.ctx.lib.edsgpu_coarse_set_level(self.h, C.c_int(lvl), C.c_int(width), C.c_int(height), C.c_float(fx), C.c_float(fy),
+                                                            C.c_float(cx), C.c_float(cy), _ptr(ki, C.c_float)))
+
+    def set_reference(self, lvl, pc_u, pc_v, pc_idepth, pc_color):
+        a = [np.ascontiguousarray(x, np.float32) for x in (pc_u, pc_v, pc_idepth, pc_color)]
+        self.ctx.check(self.ctx.lib.edsgpu_coarse_set_reference(self.h, C.c_int(lvl), C.c_int(len(a[0])), *[_ptr(x, C.c_float) for x in a]))
+
+    def set_new_frame(self, lvl, dI):
+        d = np.ascontiguousarray(dI, np.float32)
+        self.ctx.check(self.ctx.lib.edsgpu_coarse_set_new_frame(self.h, C.c_int(lvl), _ptr(d, C.c_float)))
+
+    def calc_res_gs(self, lvl, R, t, affLL, b0, cutoffTH, want_system=True):
+        R = np.ascontiguousarray(R, np.float64).reshape(-1)
+        t = np.ascontiguousarray(t, np.float64)
+        aff = np.ascontiguousarray(affLL, np.float32)
+        rs = np.zeros(6)
+        H = np.zeros((8, 8)) if want_system else None
+        b = np.zeros(8) if want_system else None
+        self.ctx.check(self.ctx.lib.edsgpu_coarse_calc_res_gs(self.h, C.c_int(lvl), _ptr(R, C.c_double), _ptr(t, C.c_double), _ptr(aff, C.c_float),
+                                                              C.c_float(b0), C.c_float(cutoffTH), _ptr(rs, C.c_double), _ptr(H, C.c_double),
+                                                              _ptr(b, C.c_double)))
+        return dict(rs=rs, H=H, b=b)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.edsgpu_coarse_destroy(self.h)
             self.h = None

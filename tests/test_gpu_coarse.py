@@ -1,0 +1,68 @@
+"""GPU parity tests for the coarse-tracker evaluation (run with -m gpu): CoarseTracker::calcRes fused with
+calcGSSSE through the C ABI against the CPU oracle.  Inclusion decisions (in bounds, cutoff) are float32
+comparisons evaluated in the same operation order on both sides, so the counts must be exact; the sums
+(E, H, b) are gated at 1e-5 relative (the reference accumulates them in float)."""
+import numpy as np
+import pytest
+
+import edsgpu
+from edsgpu import synth_coarse as SC
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(np.asarray(b, np.float64)).max(), 1e-300)
+
+
+@pytest.mark.parametrize("size", ["small", "vga"])
+def test_calc_res_and_gs_match_oracle(gpu_ctx, size):
+    pb = SC.make_coarse_problem(W=160, H=120, levels=3, points=3000) if size == "small" else SC.make_coarse_problem()
+    ct = edsgpu.CoarseTracker(gpu_ctx, len(pb["levels"]))
+    for lvl, L in enumerate(pb["levels"]):
+        ct.set_level(lvl, L["w"], L["h"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"])
+        ct.set_reference(lvl, L["pc_u"], L["pc_v"], L["pc_idepth"], L["pc_color"])
+        ct.set_new_frame(lvl, L["dI_new"])
+    for lvl, L in enumerate(pb["levels"]):
+        ref = O.coarse_calc_res_gs(lvl, L["dI_new"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"], pb["R"], pb["t"], pb["affLL"], pb["b0"],
+                                   pb["cutoffTH"], L["pc_u"], L["pc_v"], L["pc_idepth"], L["pc_color"])
+        got = ct.calc_res_gs(lvl, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"])
+        assert got["rs"][1] == ref["rs"][1] and got["rs"][5] == ref["rs"][5] and got["rs"][3] == 0   # counts are exact
+        assert abs(got["rs"][0] - ref["rs"][0]) <= TOL * ref["rs"][0]
+        for k in (2, 4):
+            assert abs(got["rs"][k] - ref["rs"][k]) <= TOL * max(ref["rs"][k], 1e-30)
+        assert rel(got["H"], ref["H"]) < TOL and rel(got["b"], ref["b"]) < TOL
+        assert np.allclose(got["H"], got["H"].T, rtol=0, atol=0)
+        # residual-only evaluation (the accept / reject test of trackNewestCoarse)
+        only = ct.calc_res_gs(lvl, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"], want_system=False)
+        assert np.array_equal(only["rs"], got["rs"])
+        # deterministic
+        again = ct.calc_res_gs(lvl, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"])
+        assert np.array_equal(again["H"], got["H"]) and np.array_equal(again["b"], got["b"]) and np.array_equal(again["rs"], got["rs"])
+    ct.close()
+
+
+def test_coarse_edge_cases(gpu_ctx):
+    pb = SC.make_coarse_problem(W=96, H=64, levels=1, points=500)
+    L = pb["levels"][0]
+    ct = edsgpu.CoarseTracker(gpu_ctx, 1)
+    with pytest.raises(edsgpu.EdsGpuError):
+        ct.set_new_frame(0, L["dI_new"])           # level not described yet
+    ct.set_level(0, L["w"], L["h"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"])
+    with pytest.raises(edsgpu.EdsGpuError):
+        ct.calc_res_gs(0, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"])   # no reference, no frame
+    ct.set_new_frame(0, L["dI_new"])
+    # every point behind the camera / out of the image: nothing survives, like the reference (0 terms)
+    ct.set_reference(0, L["pc_u"], L["pc_v"], -np.abs(L["pc_idepth"]), L["pc_color"])
+    r = ct.calc_res_gs(0, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"], want_system=False)
+    assert r["rs"][0] == 0 and r["rs"][1] == 0
+    # a ragged point count (not a multiple of the warp or of 4)
+    n = 333
+    ct.set_reference(0, L["pc_u"][:n], L["pc_v"][:n], L["pc_idepth"][:n], L["pc_color"][:n])
+    ref = O.coarse_calc_res_gs(0, L["dI_new"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"], pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"],
+                               L["pc_u"][:n], L["pc_v"][:n], L["pc_idepth"][:n], L["pc_color"][:n])
+    got = ct.calc_res_gs(0, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"])
+    assert got["rs"][1] == ref["rs"][1] and rel(got["H"], ref["H"]) < TOL and rel(got["b"], ref["b"]) < TOL
+    ct.close()

@@ -1,0 +1,45 @@
+"""CPU tests of the coarse-tracker oracle (CoarseTracker::calcRes + calcGSSSE).
+The reference has no golden vectors for this path (parity unpinned): the checks are properties the
+algorithm must have on the synthetic plane scene."""
+import numpy as np
+
+from edsgpu import synth_coarse as SC
+from oracle import oracle as O
+
+
+def _eval(pb, lvl, R, t, aff=None):
+    L = pb["levels"][lvl]
+    return O.coarse_calc_res_gs(lvl, L["dI_new"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"], R, t, pb["affLL"] if aff is None else aff,
+                                pb["b0"], pb["cutoffTH"], L["pc_u"], L["pc_v"], L["pc_idepth"], L["pc_color"])
+
+
+def test_counts_rejections_and_system_shape():
+    pb = SC.make_coarse_problem(W=160, H=120, levels=3, points=3000)
+    for lvl in range(3):
+        r = _eval(pb, lvl, pb["R"], pb["t"])
+        n = len(pb["levels"][lvl]["pc_u"])
+        nE, nW, nSat = r["counts"]
+        assert 0 < nW <= nE <= n and nE == nW + nSat and nSat > 0       # the +60 colours saturate, the negative depths are dropped
+        assert nE <= n - len(range(0, n, 97))
+        assert r["rs"][1] == nE and np.isclose(r["rs"][5], np.float32(nSat) / np.float32(nE))
+        assert np.allclose(r["H"], r["H"].T) and np.linalg.eigvalsh(r["H"]).min() > -1e-6 * np.abs(r["H"]).max()
+        assert np.all(np.isfinite(r["b"]))
+        if lvl == 0:
+            assert r["rs"][2] > 0 and r["rs"][4] > 0                    # mean flow is sampled on level 0 only (:403)
+        else:
+            assert r["rs"][2] == 0 and r["rs"][4] == 0
+
+
+def test_energy_is_lower_at_the_true_pose_and_a_newton_step_reduces_it():
+    pb = SC.make_coarse_problem(W=160, H=120, levels=1, points=4000, seed=3, pose_error=0.0)
+    L = pb["levels"][0]
+    L["pc_color"][::53] -= 60.0  # remove the planted outliers for this test
+    aff = np.array([1.0, 0.0], np.float32)
+    good = _eval(pb, 0, pb["R"], pb["t"], aff)
+    bad_t = pb["t"] + np.array([0.02, -0.015, 0.0])
+    bad = _eval(pb, 0, pb["R"], bad_t, aff)
+    assert good["rs"][0] / good["rs"][1] < 0.5 * bad["rs"][0] / bad["rs"][1]
+    # b is the gradient of the mean energy wrt the left pose increment: moving the translation along -H^-1 b lowers E
+    inc = -np.linalg.solve(bad["H"] + 1e-3 * np.eye(8), bad["b"])
+    stepped = _eval(pb, 0, pb["R"], bad_t + inc[:3], aff)   # SE3 increment: translation first (NumType: Vec6 = [trans, rot])
+    assert stepped["rs"][0] / stepped["rs"][1] < bad["rs"][0] / bad["rs"][1]
