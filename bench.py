@@ -255,6 +255,40 @@ def bench_ba(ctx, stream, reps=50):
                             "resubstitute_ms": resub_ms, "calc_l_energy_ms": energy_ms}}
 
 
+def bench_coarse(ctx, stream, reps=200):
+    """one evaluation of the DSO coarse tracker (calcRes fused with calcGSSSE) per pyramid
+    level on a 640x480 frame with 20 000 reference points at level 0; wall clock of the host-synchronous call
+    (that is how trackNewestCoarse uses it: every evaluation is followed by an 8x8 solve on the host)."""
+    import edsgpu
+    from edsgpu import synth_coarse
+    from oracle import oracle as O
+    pb = synth_coarse.make_coarse_problem()
+    ct = edsgpu.CoarseTracker(ctx, len(pb["levels"]))
+    for lvl, L in enumerate(pb["levels"]):
+        ct.set_level(lvl, L["w"], L["h"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"])
+        ct.set_reference(lvl, L["pc_u"], L["pc_v"], L["pc_idepth"], L["pc_color"])
+        ct.set_new_frame(lvl, L["dI_new"])
+    out = []
+    for lvl, L in enumerate(pb["levels"]):
+        args = (lvl, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"])
+        for _ in range(10):
+            ct.calc_res_gs(*args)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ct.calc_res_gs(*args)
+        ms = 1e3 * (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(5):
+            O.coarse_calc_res_gs(lvl, L["dI_new"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"], pb["R"], pb["t"], pb["affLL"], pb["b0"],
+                                 pb["cutoffTH"], L["pc_u"], L["pc_v"], L["pc_idepth"], L["pc_color"])
+        cpu_ms = 1e3 * (time.perf_counter() - t0) / 5
+        n = len(L["pc_u"])
+        out.append({"level": lvl, "points": n, "ms_per_evaluation": ms, "points_per_s": n / (ms * 1e-3), "cpu_port_ms_1_thread": cpu_ms,
+                    "algorithmic_bytes": n * (16 + 4 * 16)})  # point record + 4 bilinear taps of {I,dx,dy,0}
+    ct.close()
+    return {"workload": "coarse tracker: calcRes + calcGSSSE per level, 640x480, host-synchronous call", "levels": out}
+
+
 # --------------------------------------------------------------------------------------- GPU arm
 def run_native(args):
     import torch
@@ -401,6 +435,7 @@ def run_native(args):
     stream.synchronize()
     final_states = shard.gather_states(states_dev).cpu().numpy()  # global sequence order, [world*S, 14]
     ba_line = bench_ba(ctx, stream) if (rank == 0 and not args.no_ba) else None
+    coarse_line = bench_coarse(ctx, stream) if (rank == 0 and not args.no_ba) else None
 
     if rank == 0:
         windows = world * S * args.steps
@@ -442,6 +477,8 @@ def run_native(args):
         }
         if ba_line:
             out["ba"] = ba_line
+        if coarse_line:
+            out["coarse_tracker"] = coarse_line
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n_cpu = 400  # ~10 s of CPU work

@@ -289,4 +289,27 @@ class HessianAccumulators {
     const int nFrames, n;
 };
 
+// dso::CoarseTracker (src/tracking/CoarseTracker.{h,cpp}): the evaluation calcRes + calcGSSSE per pyramid level;
+// the Gauss-Newton loop of trackNewestCoarse stays with the caller.
+class CoarseTrackerEval {
+  public:
+    CoarseTrackerEval(const edsgpu_host::Context& ctx, int levels) : ctx_(ctx) { ctx_.check(edsgpu_coarse_create(ctx_.get(), levels, &ct_)); }
+    ~CoarseTrackerEval() { edsgpu_coarse_destroy(ct_); }
+    CoarseTrackerEval(const CoarseTrackerEval&) = delete;
+    CoarseTrackerEval& operator=(const CoarseTrackerEval&) = delete;
+    void makeK(int lvl, int w, int h, float fx, float fy, float cx, float cy, const float Ki[9]) { ctx_.check(edsgpu_coarse_set_level(ct_, lvl, w, h, fx, fy, cx, cy, Ki)); }
+    void setCoarseTrackingRef(int lvl, int n, const float* pc_u, const float* pc_v, const float* pc_idepth, const float* pc_color) {
+        ctx_.check(edsgpu_coarse_set_reference(ct_, lvl, n, pc_u, pc_v, pc_idepth, pc_color));
+    }
+    void setNewFrame(int lvl, const float* dIp) { ctx_.check(edsgpu_coarse_set_new_frame(ct_, lvl, dIp)); }
+    // rs = calcRes(...), H / b = calcGSSSE(...) (either both or none)
+    void calcResAndGS(int lvl, const double R[9], const double t[3], const float affLL[2], float b0, float cutoffTH, double rs[6], double* H, double* b) {
+        ctx_.check(edsgpu_coarse_calc_res_gs(ct_, lvl, R, t, affLL, b0, cutoffTH, rs, H, b));
+    }
+
+  private:
+    const edsgpu_host::Context& ctx_;
+    edsgpu_coarse* ct_ = nullptr;
+};
+
 }  // namespace dso
