@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "slam-eds_b200"))
 from oracle import oracle as O  # noqa: E402
-from edsgpu import synth  # noqa: E402
+from edsgpu import synth, synth_ba, synth_coarse  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -46,6 +46,46 @@ def tracking_fixture(config, name, num_blocks, max_iterations, with_lut=True):
     print(name, "iterations", so["info"]["iterations"], "cost", so["info"]["initial_cost"], "->", so["info"]["final_cost"])
 
 
+def ba_fixture(name):
+    """Windowed BA on a small window: the feeder (linearize), both top accumulators, the Schur complement, the
+    stitched systems, back-substitution and linearised energy; inputs are regenerated from the seed by the tests."""
+    kw = dict(F=4, points_per_frame=120, H=96, W=128, seed=21)
+    pb = synth_ba.make_ba_problem(**kw)
+    F = pb["F"]
+    recs, state, energy = O.ba_linearize(F, pb["H"], pb["W"], pb["dI"], pb["precalc"], pb["calib"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"],
+                                         pb["color"], pb["weights"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["frame_energy_th"])
+    rtz = O.ba_fix_linearization(F, recs, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["deltaF"], pb["adHTdeltaF"], pb["cDeltaF"])
+    top = [O.ba_top_accumulate(m, F, recs, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"], pb["adHTdeltaF"],
+                               pb["cDeltaF"], threads=1) for m in (0, 1)]
+    jp = O.ba_jpjd(recs)
+    sc = O.ba_sc_accumulate(F, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], jp, top[0]["Hdd"], top[1]["Hdd"], top[0]["bd"],
+                            top[1]["bd"], top[0]["Hcd"], top[1]["Hcd"], pb["priorF"], pb["deltaF"], True)
+    x = np.random.default_rng(5).normal(scale=1e-3, size=4 + 8 * F)
+    step = O.ba_resubstitute(F, x, synth_ba.col_major(pb["adHost"]), synth_ba.col_major(pb["adTarget"]), pb["host_idx"], pb["target_idx"],
+                             pb["res_begin"], pb["flags"], jp, sc["bdSum"], top[0]["Hcd"], top[1]["Hcd"], sc["HdiF"])
+    e = O.ba_calc_l_energy(F, recs, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"], pb["priorF"],
+                           pb["adHTdeltaF"], pb["cDeltaF"], pb["cPrior"], pb["frame_prior"], pb["frame_delta_prior"])
+    np.savez_compressed(os.path.join(HERE, name), kw=np.array([kw["F"], kw["points_per_frame"], kw["H"], kw["W"], kw["seed"]]), recs=recs,
+                        state=state, energy=energy, res_toZero=rtz, acc0=top[0]["acc"], acc1=top[1]["acc"], Hdd0=top[0]["Hdd"], bd0=top[0]["bd"],
+                        Hcd0=top[0]["Hcd"], JpJdF=jp, accD=sc["accD"], accE=sc["accE"], accEB=sc["accEB"], HdiF=sc["HdiF"], bdSum=sc["bdSum"],
+                        x=x, step=step, l_energy=e)
+    print(name, "R", pb["R"], "states", np.bincount(state), "l_energy", e)
+
+
+def coarse_fixture(name):
+    kw = dict(W=128, H=96, levels=3, points=2000, seed=13)
+    pb = synth_coarse.make_coarse_problem(**kw)
+    out = {"kw": np.array([kw["W"], kw["H"], kw["levels"], kw["points"], kw["seed"]])}
+    for lvl, L in enumerate(pb["levels"]):
+        r = O.coarse_calc_res_gs(lvl, L["dI_new"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"], pb["R"], pb["t"], pb["affLL"], pb["b0"],
+                                 pb["cutoffTH"], L["pc_u"], L["pc_v"], L["pc_idepth"], L["pc_color"])
+        out["rs%d" % lvl], out["H%d" % lvl], out["b%d" % lvl], out["counts%d" % lvl] = r["rs"], r["H"], r["b"], r["counts"]
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, [out["counts%d" % l].tolist() for l in range(kw["levels"])])
+
+
 if __name__ == "__main__":
+    ba_fixture("ba_small.npz")
+    coarse_fixture("coarse_small.npz")
     tracking_fixture("tiny", "tracking_tiny.npz", 4, 20)
     tracking_fixture("davis240c", "tracking_davis240c.npz", 8, 30, with_lut=False)

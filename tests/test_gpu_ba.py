@@ -187,6 +187,29 @@ def test_back_substitution_energy_and_fix_linearization(solved):
     w.set_residuals(pb["recs"], pb["flags"], rtz)  # restore for the other tests of the module
 
 
+def test_gpu_against_committed_ba_fixture(gpu_ctx):
+    """The CUDA path against tests/golden/ba_small.npz, without rebuilding or calling the oracle."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_small.npz"))
+    F, ppf, H, W, seed = [int(v) for v in g["kw"]]
+    pb = SB.make_ba_problem(F=F, points_per_frame=ppf, H=H, W=W, seed=seed)
+    w = edsgpu.BaWindow(gpu_ctx, F, pb["host_idx"], pb["target_idx"], pb["res_begin"])
+    w.set_images(pb["dI"])
+    w.set_linearize_inputs(pb["precalc"], pb["calib"], pb["frame_energy_th"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"], pb["color"], pb["weights"])
+    state, energy = w.linearize(linearized=(pb["flags"] >> 1) & 1, res_toZero=g["res_toZero"])
+    recs, _ = w.get_residuals()
+    assert np.array_equal(recs, g["recs"]) and np.array_equal(state, g["state"]) and np.array_equal(energy, g["energy"])
+    w.set_points(pb["deltaF"], pb["priorF"])
+    w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    t0, t1, sc = w.top_accumulate(0), w.top_accumulate(1), w.sc_accumulate(True)
+    assert rel(t0["acc"], g["acc0"]) < TOL and rel(t1["acc"], g["acc1"]) < TOL and rel(t0["Hdd"], g["Hdd0"]) < TOL
+    assert rel(sc["accD"], g["accD"]) < TOL and rel(sc["HdiF"], g["HdiF"]) < TOL and rel(sc["bdSum"], g["bdSum"]) < TOL
+    assert rel(w.resubstitute(g["x"]), g["step"]) < TOL
+    e = w.calc_l_energy(pb["cPrior"], pb["frame_prior"], pb["frame_delta_prior"])
+    assert abs(e - float(g["l_energy"])) <= TOL * abs(float(g["l_energy"]))
+    w.close()
+
+
 def test_linearize_needs_its_inputs(gpu_ctx):
     pb = SB.make_ba_problem(F=3, points_per_frame=50, H=64, W=80)
     w = edsgpu.BaWindow(gpu_ctx, pb["F"], pb["host_idx"], pb["target_idx"], pb["res_begin"])

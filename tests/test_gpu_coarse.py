@@ -66,3 +66,20 @@ def test_coarse_edge_cases(gpu_ctx):
     got = ct.calc_res_gs(0, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"])
     assert got["rs"][1] == ref["rs"][1] and rel(got["H"], ref["H"]) < TOL and rel(got["b"], ref["b"]) < TOL
     ct.close()
+
+
+def test_gpu_against_committed_coarse_fixture(gpu_ctx):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "coarse_small.npz"))
+    W, H, levels, points, seed = [int(v) for v in g["kw"]]
+    pb = SC.make_coarse_problem(W=W, H=H, levels=levels, points=points, seed=seed)
+    ct = edsgpu.CoarseTracker(gpu_ctx, levels)
+    for lvl, L in enumerate(pb["levels"]):
+        ct.set_level(lvl, L["w"], L["h"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"])
+        ct.set_reference(lvl, L["pc_u"], L["pc_v"], L["pc_idepth"], L["pc_color"])
+        ct.set_new_frame(lvl, L["dI_new"])
+        got = ct.calc_res_gs(lvl, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"])
+        ref = g["rs%d" % lvl]
+        assert got["rs"][1] == ref[1] and got["rs"][5] == ref[5] and abs(got["rs"][0] - ref[0]) <= TOL * ref[0]
+        assert rel(got["H"], g["H%d" % lvl]) < TOL and rel(got["b"], g["b%d" % lvl]) < TOL
+    ct.close()

@@ -285,3 +285,21 @@ def test_resubstitute_and_l_energy_known_answers():
     ad[0 + F * 1, 7] = 0.25                              # delta_b of (host 0, target 1)
     e = O.ba_calc_l_energy(F, recs, host, target, rb, lin, rtz, deltaF, priorF, ad, np.zeros(4, np.float32))
     assert np.isclose(e, 100.0 + 8 * (2 * 0.5 + 0.25) * 0.25)
+
+
+def test_oracle_against_committed_ba_fixture():
+    """tests/golden/ba_small.npz (generate_golden.py): freezes the oracle's outputs for the whole BA chain."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_small.npz"))
+    F, ppf, H, W, seed = [int(v) for v in g["kw"]]
+    pb = SB.make_ba_problem(F=F, points_per_frame=ppf, H=H, W=W, seed=seed)
+    recs, state, energy = O.ba_linearize(*_linearize_inputs(pb))
+    assert np.array_equal(recs, g["recs"]) and np.array_equal(state, g["state"]) and np.array_equal(energy, g["energy"])
+    rtz = O.ba_fix_linearization(F, recs, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["deltaF"], pb["adHTdeltaF"], pb["cDeltaF"])
+    assert np.array_equal(rtz, g["res_toZero"])
+    top0 = O.ba_top_accumulate(0, F, recs, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"], pb["adHTdeltaF"],
+                               pb["cDeltaF"], threads=1)
+    assert np.array_equal(top0["acc"], g["acc0"]) and np.array_equal(top0["Hdd"], g["Hdd0"])
+    e = O.ba_calc_l_energy(F, recs, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"], pb["priorF"],
+                           pb["adHTdeltaF"], pb["cDeltaF"], pb["cPrior"], pb["frame_prior"], pb["frame_delta_prior"])
+    assert e == float(g["l_energy"])

@@ -43,3 +43,14 @@ def test_energy_is_lower_at_the_true_pose_and_a_newton_step_reduces_it():
     inc = -np.linalg.solve(bad["H"] + 1e-3 * np.eye(8), bad["b"])
     stepped = _eval(pb, 0, pb["R"], bad_t + inc[:3], aff)   # SE3 increment: translation first (NumType: Vec6 = [trans, rot])
     assert stepped["rs"][0] / stepped["rs"][1] < bad["rs"][0] / bad["rs"][1]
+
+
+def test_oracle_against_committed_coarse_fixture():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "coarse_small.npz"))
+    W, H, levels, points, seed = [int(v) for v in g["kw"]]
+    pb = SC.make_coarse_problem(W=W, H=H, levels=levels, points=points, seed=seed)
+    for lvl in range(levels):
+        r = _eval(pb, lvl, pb["R"], pb["t"])
+        assert np.array_equal(r["counts"], g["counts%d" % lvl])
+        assert np.array_equal(r["rs"], g["rs%d" % lvl]) and np.array_equal(r["H"], g["H%d" % lvl]) and np.array_equal(r["b"], g["b%d" % lvl])
