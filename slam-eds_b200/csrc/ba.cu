@@ -32,7 +32,7 @@ constexpr int REC = 76;  // floats per record: dso::RawResidualJacobian as laid 
 constexpr int O_RES = 0, O_JPDXI0 = 8, O_JPDXI1 = 14, O_JPDC0 = 20, O_JPDC1 = 24, O_JPDD = 28, O_JIDX0 = 32, O_JIDX1 = 40,
               O_JAB0 = 48, O_JAB1 = 56, O_JIDX2 = 64, O_JABJIDX = 68, O_JAB2 = 72;
 constexpr int CPARS = 4;
-constexpr int TOP_THREADS = 256, TOP_TILE = 512, NACC = 96;
+constexpr int TOP_THREADS = 256, NACC = 96;
 constexpr int TOP_STAGE = 512;  // records staged in shared memory per round (512 x 304 B = 152 KB)
 constexpr int MAXF = 8;
 constexpr int SC_THREADS = 256, SC_CHUNK = 64, SC_BATCH = 32, SC_LD = 72;  // 8*MAXF + 5 padded to 72

@@ -173,33 +173,34 @@ __global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long
             }
         }
     }
-    if constexpr (OUT64) return;
-    // fused sum of squares (cv::norm L2, EventFrame.cpp:360-364): warp -> CTA -> ordered final pass
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((tid & 31) == 0) wsum[tid >> 5] = sq;
-    __syncthreads();
-    const int ntiles = gridDim.x * gridDim.y;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < BLUR_THREADS / 32; ++w) s += wsum[w];
-        partials[(size_t)win * ntiles + tile] = s;
-        __threadfence();
-        unsigned t = atomicAdd(&tickets[win], 1u);
-        is_last = (t == (unsigned)ntiles - 1);
-    }
-    __syncthreads();
-    if (is_last && tid < 32) {
-        __threadfence();
-        const volatile double* p = partials + (size_t)win * ntiles;
-        double s = 0.0;
-        for (int i = tid; i < ntiles; i += 32) s += p[i];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if constexpr (!OUT64) {
+        // fused sum of squares (cv::norm L2, EventFrame.cpp:360-364): warp -> CTA -> ordered final pass
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if ((tid & 31) == 0) wsum[tid >> 5] = sq;
+        __syncthreads();
+        const int ntiles = gridDim.x * gridDim.y;
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
         if (tid == 0) {
-            double nrm = sqrt(s);
-            norms[2 * slot] = nrm;
-            norms[2 * slot + 1] = 1.0 / nrm;
-            tickets[win] = 0;
+            double s = 0.0;
+            for (int w = 0; w < BLUR_THREADS / 32; ++w) s += wsum[w];
+            partials[(size_t)win * ntiles + tile] = s;
+            __threadfence();
+            unsigned t = atomicAdd(&tickets[win], 1u);
+            is_last = (t == (unsigned)ntiles - 1);
+        }
+        __syncthreads();
+        if (is_last && tid < 32) {
+            __threadfence();
+            const volatile double* p = partials + (size_t)win * ntiles;
+            double s = 0.0;
+            for (int i = tid; i < ntiles; i += 32) s += p[i];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (tid == 0) {
+                double nrm = sqrt(s);
+                norms[2 * slot] = nrm;
+                norms[2 * slot + 1] = 1.0 / nrm;
+                tickets[win] = 0;
+            }
         }
     }
 }

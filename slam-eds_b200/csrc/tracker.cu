@@ -197,10 +197,6 @@ struct CtaShared {
     alignas(8) unsigned long long result_bar[MAX_K];  // leader CTA of k: "every evaluator warp of the cluster is done with problem k"
 };
 
-// (a,b) of packed upper-triangle entry e (row-major, a <= b < 12)
-__constant__ unsigned char c_tri_a[78] = {0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,1,1,1,2,2,2,2,2,2,2,2,2,2,3,3,3,3,3,3,3,3,3,4,4,4,4,4,4,4,4,5,5,5,5,5,5,5,6,6,6,6,6,6,7,7,7,7,7,8,8,8,8,9,9,9,10,10,11};
-__constant__ unsigned char c_tri_b[78] = {0,1,2,3,4,5,6,7,8,9,10,11,1,2,3,4,5,6,7,8,9,10,11,2,3,4,5,6,7,8,9,10,11,3,4,5,6,7,8,9,10,11,4,5,6,7,8,9,10,11,5,6,7,8,9,10,11,6,7,8,9,10,11,7,8,9,10,11,8,9,10,11,9,10,11,10,11,11};
-
 // ------------------------------------------------------------------------------------------
 // per-point residual + analytic tangent-space Jacobian
 // ------------------------------------------------------------------------------------------
@@ -836,6 +832,10 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
         }
     }
     __syncwarp();
+    // row `lane` of the scaled system once a new point has been taken (kept in registers for the solve)
+    double Hr[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) Hr[q] = 0.0;
     if (take) {
         // EvaluateGradientAndJacobian: Jacobi scaling (iteration 0 only), scaled system,
         // gradient max norm || x - Plus(x, -g) ||_inf, ||x||
@@ -843,38 +843,54 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
         // The fp32 sweep leaves ~1e-7 of noise along it, which a large trust-region radius
         // (D^2 -> 1e-12) would amplify into the step.  Project the reduced system in fp64:
         // H <- Pi H Pi, g <- Pi g, Pi = I - n n^T, so the device behaves like exact arithmetic.
-        {
-            const double vq = (lane >= 6 && lane < 12) ? lm.x[1 + lane] : 0.0;
-            const double inv_n = rsqrt(warp_sum(vq * vq));
-            const double na = vq * inv_n;
-            const int la = lane < 12 ? lane : 0;
-            double wa = 0.0;
+        // Lane i < 12 holds row i of H and g_i in registers; vectors are exchanged by shuffles, so the
+        // whole block needs no shared-memory round trip.
+        const int la = lane < 12 ? lane : 0;
 #pragma unroll
-            for (int b = 6; b < 12; ++b) {
-                const double nb = __shfl_sync(FULL, na, b);
-                wa += sh.sum[la <= b ? tri_index(la, b) : tri_index(b, la)] * nb;
-            }
-            if (lane >= 12) wa = 0.0;
-            const double sw = warp_sum(na * wa);
-            const double ga = (lane < 12) ? sh.sum[78 + la] : 0.0;
-            const double gn = warp_sum(na * ga);
-            __syncwarp();
-            if (lane < 12) { lm.delta[lane] = na; lm.diag[lane] = wa; sh.sum[78 + lane] = ga - na * gn; }
-            __syncwarp();
-            for (int e = lane; e < 78; e += 32) {
-                const int a = c_tri_a[e], b = c_tri_b[e];
-                sh.sum[e] = sh.sum[e] - lm.delta[a] * lm.diag[b] - lm.diag[a] * lm.delta[b] + lm.delta[a] * lm.delta[b] * sw;
-            }
-            __syncwarp();
+        for (int q = 0; q < 12; ++q) {
+            const double v = sh.sum[la <= q ? tri_index(la, q) : tri_index(q, la)];
+            Hr[q] = (lane < 12) ? v : 0.0;
         }
-        if (first && lane < 12) lm.scale[lane] = 1.0 / (1.0 + sqrt(fmax(sh.sum[tri_index(lane, lane)], 0.0)));
-        __syncwarp();
-        for (int e = lane; e < 78; e += 32) lm.Hs[e] = sh.sum[e] * lm.scale[c_tri_a[e]] * lm.scale[c_tri_b[e]];
-        if (lane < 12) lm.gs[lane] = sh.sum[78 + lane] * lm.scale[lane];
-        double gt = (lane < 3) ? fabs(sh.sum[78 + lane]) : 0.0;
+        double g = (lane < 12) ? sh.sum[78 + la] : 0.0;
+        const double vq = (lane >= 6 && lane < 12) ? lm.x[1 + lane] : 0.0;
+        const double inv_n = rsqrt(warp_sum(vq * vq));
+        const double na = vq * inv_n;
+        double wa = 0.0;  // (H n)_i
+#pragma unroll
+        for (int b = 6; b < 12; ++b) wa += Hr[b] * __shfl_sync(FULL, na, b);
+        const double sw = warp_sum(na * wa);
+        const double gn = warp_sum(na * g);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const double nq = __shfl_sync(FULL, na, q), wq = __shfl_sync(FULL, wa, q);
+            Hr[q] = Hr[q] - na * wq - wa * nq + na * nq * sw;
+        }
+        g = g - na * gn;
+        double sc;
+        if (first) {
+            double diag = 0.0;
+#pragma unroll
+            for (int q = 0; q < 12; ++q) diag = (q == lane) ? Hr[q] : diag;
+            sc = 1.0 / (1.0 + sqrt(fmax(diag, 0.0)));
+            if (lane < 12) lm.scale[lane] = sc;
+        } else {
+            sc = lm.scale[la];
+        }
+#pragma unroll
+        for (int q = 0; q < 12; ++q) Hr[q] = Hr[q] * sc * __shfl_sync(FULL, sc, q);
+        if (lane < 12) {
+            // kept for the re-solves after a rejected step and for the gradient tolerance test
+#pragma unroll
+            for (int q = 0; q < 12; ++q)
+                if (q >= lane) lm.Hs[tri_index(lane, q)] = Hr[q];
+            lm.gs[lane] = g * sc;
+            sh.sum[78 + lane] = g;
+        }
+        double gt = (lane < 3) ? fabs(g) : 0.0;
         double gmax = warp_max(gt);  // translation part of x - Plus(x,-g) is exactly g
         if (!(gmax > P.gtol)) {
             // only now can the full projected-gradient norm decide the gradient tolerance test
+            __syncwarp();
             double ng[12], xp[13];
             for (int i = 0; i < 12; ++i) ng[i] = -sh.sum[78 + i];
             state_plus(lm.x, ng, xp);
@@ -906,8 +922,12 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
         const double damping = lm.diag[li] / radius;  // D^2 of this lane's diagonal entry
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
-            const double v = lm.Hs[li <= j ? tri_index(li, j) : tri_index(j, li)];
-            h[j] = (lane < 12) ? v : 0.0;
+            if (take) {
+                h[j] = Hr[j];  // this call has just formed the scaled system
+            } else {
+                const double v = lm.Hs[li <= j ? tri_index(li, j) : tri_index(j, li)];
+                h[j] = (lane < 12) ? v : 0.0;
+            }
             a[j] = (j == lane) ? h[j] + damping : h[j];
         }
         // Right-looking Cholesky in registers with the forward substitution L z = gs folded in.  After
