@@ -266,6 +266,46 @@ def test_batch_matches_single_and_is_independent_of_cluster_size(gpu_ctx, proble
     kfd.close()
 
 
+def test_results_do_not_depend_on_launch_shape(gpu_ctx, problems, monkeypatch):
+    """Cluster width (CTAs per cluster) and the number of problems a cluster keeps in flight are scheduling
+    choices: every combination must give bit-identical states, iteration counts and next loss parameters.
+    (EDSGPU_CLUSTER / EDSGPU_INFLIGHT are the library's tuning overrides, read when a batch is created.)"""
+    kf, wins = problems["davis240c"]
+    H, W, n = kf["H"], kf["W"], 7
+    fr = edsgpu.Frames(gpu_ctx, H, W, n)
+    E = len(wins[0]["x"])
+    ev = [np.concatenate([wins[i % 2][k] for i in range(n)]) for k in ("x", "y", "pol")]
+    edsgpu.event_frames_batch(gpu_ctx, fr, 0, n, *ev, E)
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, 8)
+
+    def run():
+        trs = [edsgpu.Tracker(gpu_ctx, num_blocks=8, max_iterations=10 + (i % 3)) for i in range(n)]  # problems finish at different times
+        for i, t in enumerate(trs):
+            x0 = wins[i % 2]["x_init"]
+            t.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
+        b = edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * n, fr, 0)
+        b.optimize()
+        states, infos = b.gather()
+        b.close()
+        for t in trs:
+            t.close()
+        return states, [(i["iterations"], i["evaluations"], i["termination"], i["usable"]) for i in infos]
+
+    monkeypatch.delenv("EDSGPU_CLUSTER", raising=False)
+    monkeypatch.delenv("EDSGPU_INFLIGHT", raising=False)
+    base_states, base_infos = run()
+    for csize in (1, 2, 4, 8):
+        for inflight in (1, 2, 3, 4):
+            if inflight > csize:
+                continue
+            monkeypatch.setenv("EDSGPU_CLUSTER", str(csize))
+            monkeypatch.setenv("EDSGPU_INFLIGHT", str(inflight))
+            states, infos = run()
+            assert np.array_equal(states, base_states), (csize, inflight)
+            assert infos == base_infos, (csize, inflight)
+    kfd.close(); fr.close()
+
+
 def test_sequence_of_windows_carries_state(gpu_ctx, problems):
     """Window k+1 warm-starts from window k's (px,qx,vx) and tau (Tracker.cpp:233)."""
     kf, wins = problems["davis240c"]
