@@ -301,6 +301,24 @@ edsgpu_status edsgpu_coarse_set_new_frame(edsgpu_coarse* coarse, int lvl, const 
 edsgpu_status edsgpu_coarse_calc_res_gs(edsgpu_coarse* coarse, int lvl, const double R[9], const double t[3], const float affLL[2],
                                         float b0, float cutoffTH, double rs[6], double H[64], double b[8]);
 
+/* ---- per-point depth filter -----------------------------------------
+ * eds::mapping::DepthPoints (src/mapping/DepthPoints.{hpp,cpp}): the filter state {mu = inverse
+ * depth, sigma2, a, b} of every key-frame point stays on the device; update() is one launch. */
+typedef struct edsgpu_depth_points edsgpu_depth_points;
+/* DepthPoints::init (:52-91): inv_depth NULL = every point at the mean depth with sigma2 = range^2,
+ * else the given inverse depths with sigma2 = range^2 / 36.  px_noise is the reference's 3 px. */
+edsgpu_status edsgpu_depth_points_create(edsgpu_ctx* ctx, int num_points, double fx, double fy, double cx, double cy, double min_depth,
+                                         double max_depth, const double* inv_depth, double init_a, double init_b,
+                                         edsgpu_depth_points** out);
+void edsgpu_depth_points_destroy(edsgpu_depth_points* dp);
+/* DepthPoints::update (:93-176): T_kf_ef row-major 4x4; kf_coord / ef_coord: N x 2 pixel coordinates
+ * (std::vector<cv::Point2d> is layout-compatible); coords_are_tracks != 0: ef_coord holds the offsets
+ * (KeyFrame::tracks) instead.  ok_out: filterVogiatzis' return value per point, N bytes or NULL. */
+edsgpu_status edsgpu_depth_points_update(edsgpu_depth_points* dp, const double T_kf_ef[16], const double* kf_coord, const double* ef_coord,
+                                         int coords_are_tracks, uint8_t* ok_out);
+/* N x 4 doubles {mu, sigma2, a, b} (getIDepth is column 0). */
+edsgpu_status edsgpu_depth_points_get(edsgpu_depth_points* dp, double* state_out);
+
 #ifdef __cplusplus
 }
 #endif

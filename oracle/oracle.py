@@ -320,3 +320,17 @@ def coarse_calc_res_gs(lvl, dI, fx, fy, cx, cy, Ki, R, t, affLL, b0, cutoffTH, p
                                         _p(idp, C.c_float), _p(col, C.c_float), _p(rs, C.c_double), _p(H, C.c_double), _p(b, C.c_double),
                                         _p(counts, C.c_int64))
     return dict(rs=rs, H=H, b=b, counts=counts)
+
+
+# ----------------------------------------------------------------------------- depth filter
+def depth_update(fx, fy, cx, cy, mu_range, px_error_angle, T_kf_ef, kf_coord, ef_coord, state, coords_are_tracks=False):
+    """DepthPoints::update on a copy of state (N x 4: mu, sigma2, a, b) -> (new state, ok flags)."""
+    T = _f64(T_kf_ef).reshape(-1)
+    kf, ef = _f64(kf_coord), _f64(ef_coord)
+    st = np.array(state, np.float64, copy=True, order="C")
+    N = len(st)
+    ok = np.zeros(N, np.uint8)
+    lib().eds_oracle_depth_update(C.c_int(N), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), C.c_double(mu_range),
+                                  C.c_double(px_error_angle), _p(T, C.c_double), _p(kf, C.c_double), _p(ef, C.c_double),
+                                  C.c_int(int(coords_are_tracks)), _p(st, C.c_double), _p(ok, C.c_uint8))
+    return st, ok

@@ -38,6 +38,7 @@ SYMBOLS = [
     "edsgpu_ba_resubstitute", "edsgpu_ba_fix_linearization", "edsgpu_ba_calc_l_energy",
     "edsgpu_coarse_create", "edsgpu_coarse_destroy", "edsgpu_coarse_set_level", "edsgpu_coarse_set_reference",
     "edsgpu_coarse_set_new_frame", "edsgpu_coarse_calc_res_gs",
+    "edsgpu_depth_points_create", "edsgpu_depth_points_destroy", "edsgpu_depth_points_update", "edsgpu_depth_points_get",
 ]
 
 
@@ -509,4 +510,37 @@ class CoarseTracker:
     def close(self):
         if self.h:
             self.ctx.lib.edsgpu_coarse_destroy(self.h)
+            self.h = None
+
+
+class DepthPoints:
+    """eds::mapping::DepthPoints (src/mapping/DepthPoints.{hpp,cpp}): per-point Vogiatzis depth filter with
+    the state {mu, sigma2, a, b} resident on the device."""
+
+    def __init__(self, ctx, num_points, fx, fy, cx, cy, min_depth, max_depth, inv_depth=None, init_a=10.0, init_b=10.0):
+        self.ctx, self.N = ctx, num_points
+        idp = np.ascontiguousarray(inv_depth, np.float64) if inv_depth is not None else None
+        assert idp is None or idp.shape == (num_points,)
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.edsgpu_depth_points_create(ctx.h, C.c_int(num_points), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy),
+                                                     C.c_double(min_depth), C.c_double(max_depth), _ptr(idp, C.c_double), C.c_double(init_a),
+                                                     C.c_double(init_b), C.byref(self.h)))
+
+    def update(self, T_kf_ef, kf_coord, ef_coord, coords_are_tracks=False):
+        T = np.ascontiguousarray(T_kf_ef, np.float64).reshape(-1)
+        kf, ef = np.ascontiguousarray(kf_coord, np.float64), np.ascontiguousarray(ef_coord, np.float64)
+        assert T.shape == (16,) and kf.shape == (self.N, 2) and ef.shape == (self.N, 2)
+        ok = np.zeros(self.N, np.uint8)
+        self.ctx.check(self.ctx.lib.edsgpu_depth_points_update(self.h, _ptr(T, C.c_double), _ptr(kf, C.c_double), _ptr(ef, C.c_double),
+                                                               C.c_int(int(coords_are_tracks)), _ptr(ok, C.c_uint8)))
+        return ok
+
+    def get(self):
+        st = np.zeros((self.N, 4))
+        self.ctx.check(self.ctx.lib.edsgpu_depth_points_get(self.h, _ptr(st, C.c_double)))
+        return st
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.edsgpu_depth_points_destroy(self.h)
             self.h = None
