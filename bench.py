@@ -289,6 +289,36 @@ def bench_coarse(ctx, stream, reps=200):
     return {"workload": "coarse tracker: calcRes + calcGSSSE per level, 640x480, host-synchronous call", "levels": out}
 
 
+def bench_depth(ctx, stream, n=10240, reps=100):
+    """SURVEY.md 8(f) rank 4: DepthPoints::update for the key frame's points (config 2: 10 240 points), host
+    coordinates in, state resident on the device; wall clock of the host-synchronous call."""
+    import edsgpu
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    fx = fy = 520.0
+    cx, cy = 320.0, 240.0
+    kf = np.stack([rng.uniform(20, 620, n), rng.uniform(20, 460, n)], 1)
+    depth = rng.uniform(1.0, 6.0, n)
+    T = np.eye(4); T[:3, 3] = [0.25, -0.08, 0.05]
+    Pk = np.stack([(kf[:, 0] - cx) / fx * depth, (kf[:, 1] - cy) / fy * depth, depth], 1) - T[:3, 3]
+    ef = np.stack([fx * Pk[:, 0] / Pk[:, 2] + cx, fy * Pk[:, 1] / Pk[:, 2] + cy], 1)
+    dp = edsgpu.DepthPoints(ctx, n, fx, fy, cx, cy, 0.5, 5.5, inv_depth=1.0 / depth)
+    for _ in range(5):
+        dp.update(T, kf, ef)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dp.update(T, kf, ef)
+    ms = 1e3 * (time.perf_counter() - t0) / reps
+    st = dp.get()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        O.depth_update(fx, fy, cx, cy, 5.0, np.arctan(3.0 / (2 * fx)) + np.arctan(3.0 / (2 * fy)), T, kf, ef, st)
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / 10
+    dp.close()
+    return {"workload": "depth filter: DepthPoints::update, %d points, coordinates from the host, state on the device" % n,
+            "ms_per_update": ms, "points_per_s": n / (ms * 1e-3), "cpu_port_ms_1_thread": cpu_ms, "h2d_bytes": 32 * n}
+
+
 # --------------------------------------------------------------------------------------- GPU arm
 def run_native(args):
     import torch
@@ -440,6 +470,7 @@ def run_native(args):
     final_states = shard.gather_states(states_dev).cpu().numpy()  # global sequence order, [world*S, 14]
     ba_line = bench_ba(ctx, stream) if (rank == 0 and not args.no_ba) else None
     coarse_line = bench_coarse(ctx, stream) if (rank == 0 and not args.no_ba) else None
+    depth_line = bench_depth(ctx, stream) if (rank == 0 and not args.no_ba) else None
 
     if rank == 0:
         windows = world * S * args.steps
@@ -483,6 +514,8 @@ def run_native(args):
             out["ba"] = ba_line
         if coarse_line:
             out["coarse_tracker"] = coarse_line
+        if depth_line:
+            out["depth_filter"] = depth_line
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n_cpu = 400  # ~10 s of CPU work

@@ -213,6 +213,36 @@ class Tracker {
 
 } }  // namespace eds::tracking
 
+namespace eds { namespace mapping {
+// eds::mapping::DepthPoints (src/mapping/DepthPoints.{hpp,cpp}): filter state on the device
+class DepthPoints {
+  public:
+    DepthPoints(const edsgpu_host::Context& ctx, double fx, double fy, double cx, double cy, const std::vector<double>& inv_depth, double min_depth,
+                double max_depth, double init_a = 10.0, double init_b = 10.0)
+        : ctx_(ctx), n_((int)inv_depth.size()) {
+        ctx_.check(edsgpu_depth_points_create(ctx_.get(), n_, fx, fy, cx, cy, min_depth, max_depth, inv_depth.data(), init_a, init_b, &dp_));
+    }
+    ~DepthPoints() { edsgpu_depth_points_destroy(dp_); }
+    DepthPoints(const DepthPoints&) = delete;
+    DepthPoints& operator=(const DepthPoints&) = delete;
+    // T_kf_ef: row-major 4x4; coordinates: N x 2 doubles (std::vector<cv::Point2d>)
+    void update(const double T_kf_ef[16], const double* kf_coord, const double* ef_coord, bool coords_are_tracks = false) {
+        ctx_.check(edsgpu_depth_points_update(dp_, T_kf_ef, kf_coord, ef_coord, coords_are_tracks ? 1 : 0, nullptr));
+    }
+    void getIDepth(std::vector<double>& x) {
+        std::vector<double> st(4 * (size_t)n_);
+        ctx_.check(edsgpu_depth_points_get(dp_, st.data()));
+        x.resize(n_);
+        for (int i = 0; i < n_; ++i) x[i] = st[4 * (size_t)i];
+    }
+
+  private:
+    const edsgpu_host::Context& ctx_;
+    int n_;
+    edsgpu_depth_points* dp_ = nullptr;
+};
+}}  // namespace eds::mapping
+
 namespace dso {
 
 // The accumulator side of dso::EnergyFunctional (EnergyFunctional.cpp:197-261) for one residual graph:
