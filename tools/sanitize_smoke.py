@@ -49,3 +49,16 @@ for k in range(3):
     edsgpu.event_frames_batch(ctx, fr2, ((k + 1) & 1) * n, n, *ev, E)
     banks[k & 1].optimize()
 ctx.synchronize(); print("pipelined ok")
+# coarse tracker evaluation and depth filter
+from edsgpu import synth_coarse
+cp = synth_coarse.make_coarse_problem(W=96, H=64, levels=2, points=700)
+ct = edsgpu.CoarseTracker(ctx, 2)
+for lvl, L in enumerate(cp["levels"]):
+    ct.set_level(lvl, L["w"], L["h"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"]); ct.set_reference(lvl, L["pc_u"], L["pc_v"], L["pc_idepth"], L["pc_color"])
+    ct.set_new_frame(lvl, L["dI_new"]); r = ct.calc_res_gs(lvl, cp["R"], cp["t"], cp["affLL"], cp["b0"], cp["cutoffTH"])
+print("coarse ok", r["rs"][1])
+rng = np.random.default_rng(0); nd = 777
+dp = edsgpu.DepthPoints(ctx, nd, 500.0, 500.0, 80.0, 60.0, 0.5, 5.5, inv_depth=np.full(nd, 0.4))
+Td = np.eye(4); Td[:3, 3] = [0.2, 0.0, 0.05]
+kfc = np.stack([rng.uniform(5, 150, nd), rng.uniform(5, 110, nd)], 1)
+dp.update(Td, kfc, kfc + rng.normal(scale=2.0, size=(nd, 2))); dp.update(Td, kfc, rng.normal(scale=2.0, size=(nd, 2)), coords_are_tracks=True); print("depth ok", dp.get()[:2, 0])
