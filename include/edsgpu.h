@@ -318,6 +318,19 @@ edsgpu_status edsgpu_depth_points_update(edsgpu_depth_points* dp, const double T
                                          int coords_are_tracks, uint8_t* ok_out);
 /* N x 4 doubles {mu, sigma2, a, b} (getIDepth is column 0). */
 edsgpu_status edsgpu_depth_points_get(edsgpu_depth_points* dp, double* state_out);
+/* Tracker::getCoord (Tracker.cpp:319-376) with the filter's current inverse depths and the tracker's
+ * pose, all on the device: coord_out N x 2 pixel coordinates in the event frame, outlier_out[i] != 0
+ * where the reference would erase the point (outside the image); either may be NULL (asynchronous). */
+edsgpu_status edsgpu_tracker_get_coord(edsgpu_tracker* tracker, const edsgpu_keyframe* kf, const edsgpu_depth_points* dp, double* coord_out,
+                                       uint8_t* outlier_out);
+/* The key frame's inverse depths <- the filter's means, on the device (what re-uploading the key frame
+ * after KeyFrame::inv_depth changed would do; Tracker.cpp:167). */
+edsgpu_status edsgpu_keyframe_refresh_idepth(edsgpu_keyframe* kf, const edsgpu_depth_points* dp);
+/* One call per tracked window: getCoord -> DepthPoints::update(T_kf_ef = getTransform().inverse(), kf_coord,
+ * coord) -> optional key-frame refresh, without leaving the device.  kf_coord: KeyFrame::coord (N x 2),
+ * needed on the first call for a key frame, NULL afterwards.  Asynchronous when kf_coord is NULL. */
+edsgpu_status edsgpu_depth_points_update_from_tracker(edsgpu_depth_points* dp, edsgpu_tracker* tracker, edsgpu_keyframe* kf,
+                                                      const double* kf_coord, int refresh_keyframe);
 
 #ifdef __cplusplus
 }

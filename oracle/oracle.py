@@ -334,3 +334,19 @@ def depth_update(fx, fy, cx, cy, mu_range, px_error_angle, T_kf_ef, kf_coord, ef
                                   C.c_double(px_error_angle), _p(T, C.c_double), _p(kf, C.c_double), _p(ef, C.c_double),
                                   C.c_int(int(coords_are_tracks)), _p(st, C.c_double), _p(ok, C.c_uint8))
     return st, ok
+
+
+def tracker_get_coord(kf, inv_depth, px, qx):
+    """Tracker::getCoord (Tracker.cpp:319-376), numpy double: key-frame points at inverse depths `inv_depth` warped with
+    (px, qx = xyzw) into the event frame -> (coord N x 2, outlier flags)."""
+    x, y, z, w = [float(v) for v in qx]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    nc = np.asarray(kf["norm_coord"], np.float64)
+    pz = 1.0 / np.asarray(inv_depth, np.float64)
+    p = np.stack([nc[:, 0] * pz, nc[:, 1] * pz, pz], 1) @ R.T + np.asarray(px, np.float64)
+    xp = kf["fx"] * (p[:, 0] / p[:, 2]) + kf["cx"]
+    yp = kf["fy"] * (p[:, 1] / p[:, 2]) + kf["cy"]
+    outlier = (xp < 0.0) | (xp > kf["W"]) | (yp < 0.0) | (yp > kf["H"])
+    return np.stack([xp, yp], 1), outlier.astype(np.uint8)

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "depth.cuh"
 
 namespace {
 
@@ -28,9 +29,45 @@ __device__ __forceinline__ void cross3(const double* a, const double* b, double*
 }
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
+// Eigen::Quaterniond::toRotationMatrix for (x,y,z,w)
+__device__ __forceinline__ void quat_rot(const double* q, double* R) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
+}
+
+__device__ __forceinline__ void depth_update_point(const DepthArgs& d, int i);
+
 __global__ void __launch_bounds__(128) depth_update_kernel(DepthArgs d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.N) return;
+    depth_update_point(d, i);
+}
+
+// the pose comes from a tracker's state on the device: (px, qx) is T_ef_kf (Tracker.cpp:338-341), the filter
+// wants T_kf_ef = T_ef_kf^-1 (Tracker.cpp:220) and inverts it again (DepthPoints.cpp:102-104)
+__global__ void __launch_bounds__(128) depth_update_tracked_kernel(DepthArgs d, const double* __restrict__ tracker_state) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.N) return;
+    double R[9];
+    quat_rot(tracker_state + 3, R);
+    const double px[3] = {tracker_state[0], tracker_state[1], tracker_state[2]};
+    const double K[9] = {d.fx, 0, d.cx, 0, d.fy, d.cy, 0, 0, 1};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d.M2[3 * r + c] = K[3 * r] * R[c] + K[3 * r + 1] * R[3 + c] + K[3 * r + 2] * R[6 + c];
+        d.epipole[r] = K[3 * r] * px[0] + K[3 * r + 1] * px[1] + K[3 * r + 2] * px[2];
+        d.t[r] = -(R[r] * px[0] + R[3 + r] * px[1] + R[6 + r] * px[2]);  // -R^T px
+    }
+    d.tnorm = sqrt(d.t[0] * d.t[0] + d.t[1] * d.t[1] + d.t[2] * d.t[2]);
+    depth_update_point(d, i);
+}
+
+__device__ __forceinline__ void depth_update_point(const DepthArgs& d, int i) {
     const double2 kf = reinterpret_cast<const double2*>(d.kf_coord)[i];
     double2 ef = reinterpret_cast<const double2*>(d.ef_coord)[i];
     if (d.tracks) { ef.x += kf.x; ef.y += kf.y; }
@@ -100,14 +137,20 @@ __global__ void __launch_bounds__(128) depth_update_kernel(DepthArgs d) {
 
 }  // namespace
 
-struct edsgpu_depth_points {
-    edsgpu_ctx* ctx = nullptr;
-    int N = 0;
-    double fx = 0, fy = 0, cx = 0, cy = 0, mu_range = 0, px_error_angle = 0;
-    double* state = nullptr;   // [N][4]
-    double* coords = nullptr;  // [2][N][2] staging: kf, ef
-    unsigned char* ok = nullptr;
-};
+
+edsgpu_status edsgpu_depth_update_tracked(edsgpu_depth_points* d, const double* tracker_state_dev, const double* kf_coord_dev,
+                                          const double* ef_coord_dev) {
+    edsgpu_ctx* ctx = d->ctx;
+    DepthArgs a{};
+    a.N = d->N; a.tracks = 0;
+    a.fx = d->fx; a.fy = d->fy; a.cx = d->cx; a.cy = d->cy; a.mu_range = d->mu_range; a.px_error_angle = d->px_error_angle;
+    a.kf_coord = kf_coord_dev; a.ef_coord = ef_coord_dev;
+    a.state = d->state; a.ok = d->ok;
+    depth_update_tracked_kernel<<<(d->N + 127) / 128, 128, 0, ctx->stream>>>(a, tracker_state_dev);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    return EDSGPU_OK;
+}
 
 extern "C" {
 

@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "depth.cuh"
 #include "frames.cuh"
 
 namespace cg = cooperative_groups;
@@ -1306,10 +1307,34 @@ __global__ void __launch_bounds__(MAD_THREADS) mad_kernel(const ProblemDesc* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// Tracker::getCoord (Tracker.cpp:319-376): the key-frame points at the filter's current inverse depths,
+// warped with the tracker's pose into the event frame.  One thread per point, fp64.
+// ------------------------------------------------------------------------------------------
+__global__ void get_coord_kernel(int N, const double* __restrict__ norm_xy, const double* __restrict__ filter_state,
+                                 const double* __restrict__ tracker_state, double fx, double fy, double cx, double cy, int W, int H,
+                                 double* __restrict__ coord, unsigned char* __restrict__ outlier) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double R[9];
+    quat_to_rot(tracker_state + 3, R);
+    double p[3];
+    p[2] = 1.0 / filter_state[4 * (size_t)i];  // eds::mapping::mu
+    p[0] = norm_xy[2 * (size_t)i] * p[2];
+    p[1] = norm_xy[2 * (size_t)i + 1] * p[2];
+    double q[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) q[r] = R[3 * r] * p[0] + R[3 * r + 1] * p[1] + R[3 * r + 2] * p[2] + tracker_state[r];
+    const double xp = fx * (q[0] / q[2]) + cx, yp = fy * (q[1] / q[2]) + cy;
+    coord[2 * (size_t)i] = xp;
+    coord[2 * (size_t)i + 1] = yp;
+    if (outlier) outlier[i] = ((xp < 0.0 || xp > (double)W) || (yp < 0.0 || yp > (double)H)) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // keyframe upload
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kf_prepare_kernel(const double* __restrict__ grad_xy, const double* __restrict__ norm_xy,
-                                                         const double* __restrict__ idp, const double* __restrict__ weights, int N, int B,
+                                                         const double* __restrict__ idp, int idp_stride, const double* __restrict__ weights, int N, int B,
                                                          float4* __restrict__ gxy, float2* __restrict__ dw, double* __restrict__ kpx,
                                                          double* __restrict__ kpy, double* __restrict__ kpz, double* __restrict__ A) {
     const int b = blockIdx.x;
@@ -1322,7 +1347,7 @@ __global__ void __launch_bounds__(256) kf_prepare_kernel(const double* __restric
         const int idx = start + i;
         const double Gx = grad_xy[2 * idx], Gy = grad_xy[2 * idx + 1];
         const double X = norm_xy[2 * idx], Y = norm_xy[2 * idx + 1];
-        const double d = idp[idx], w = weights[idx];
+        const double d = idp[(size_t)idp_stride * idx], w = weights[idx];
         gxy[idx] = make_float4((float)Gx, (float)Gy, (float)X, (float)Y);
         dw[idx] = make_float2((float)d, (float)w);
         const double z = 1.0 / (d + kEps);  // PhotometricError.hpp:97-99
@@ -1375,6 +1400,7 @@ struct edsgpu_keyframe {
     uint64_t uid = edsgpu_next_uid();
     KfDev dev{};
     void* block = nullptr;  // one allocation behind all device arrays
+    double* src = nullptr;  // device copies of the caller's double arrays: grad_xy (2N) | norm_xy (2N) | idp (N) | weights (N)
 };
 
 struct edsgpu_tracker {
@@ -1530,6 +1556,7 @@ edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const doub
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     const size_t o_gxy = take(N * sizeof(float4)), o_dw = take(N * sizeof(float2)), o_kx = take(N * 8), o_ky = take(N * 8), o_kz = take(N * 8);
     const size_t o_A = take((size_t)num_blocks * 21 * 8);
+    const size_t o_src = take(N * 6 * sizeof(double));  // kept: the inverse depths can be refreshed on the device
     cudaError_t e = cudaMalloc(&kf->block, off);
     if (e != cudaSuccess) { delete kf; return edsgpu_fail(ctx, EDSGPU_OUT_OF_MEMORY, cudaGetErrorString(e)); }
     char* base = (char*)kf->block;
@@ -1537,29 +1564,29 @@ edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const doub
     d.gxy = (float4*)(base + o_gxy); d.dw = (float2*)(base + o_dw);
     d.kpx = (double*)(base + o_kx); d.kpy = (double*)(base + o_ky); d.kpz = (double*)(base + o_kz);
     d.A = (double*)(base + o_A);
+    kf->src = (double*)(base + o_src);
     d.N = num_points; d.B = num_blocks; d.H = height; d.W = width;
     d.ne = num_points / num_blocks;
     d.fx = fx; d.fy = fy; d.cx = cx; d.cy = cy;
-    // stage the double arrays: pinned -> device scratch -> prepare kernel
+    // stage the double arrays: pinned -> device copy -> prepare kernel
     const size_t stage = N * 6 * sizeof(double);
     edsgpu_status st = edsgpu_ensure_pinned(ctx, stage);
-    if (st == EDSGPU_OK) st = edsgpu_ensure_scratch(ctx, stage);
     if (st != EDSGPU_OK) { edsgpu_keyframe_destroy(kf); return st; }
     double* hp = (double*)ctx->pinned;
     memcpy(hp, grad_xy, N * 16);
     memcpy(hp + 2 * N, norm_xy, N * 16);
     memcpy(hp + 4 * N, idp, N * 8);
     memcpy(hp + 5 * N, weights, N * 8);
-    double* ds = (double*)ctx->scratch;
+    double* ds = kf->src;
     e = cudaMemcpyAsync(ds, hp, stage, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
-        kf_prepare_kernel<<<num_blocks, 256, 0, ctx->stream>>>(ds, ds + 2 * N, ds + 4 * N, ds + 5 * N, num_points, num_blocks,
+        kf_prepare_kernel<<<num_blocks, 256, 0, ctx->stream>>>(ds, ds + 2 * N, ds + 4 * N, 1, ds + 5 * N, num_points, num_blocks,
                                                                 (float4*)d.gxy, (float2*)d.dw, (double*)d.kpx, (double*)d.kpy, (double*)d.kpz,
                                                                 (double*)d.A);
         ctx->launches++;
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // pinned/scratch are reused by later calls
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the pinned block is reused by later calls
     if (e != cudaSuccess) { edsgpu_keyframe_destroy(kf); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
     *out = kf;
     return EDSGPU_OK;
@@ -1843,6 +1870,58 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     if (H_out) memcpy(H_out, hev + 1, 144 * 8);
     if (g_out) memcpy(g_out, hev + 145, 12 * 8);
     return EDSGPU_OK;
+}
+
+// ---- tracker <-> depth filter on the device --------------------------
+edsgpu_status edsgpu_tracker_get_coord(edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_depth_points* dp, double* coord_out,
+                                       uint8_t* outlier_out) {
+    if (!tr) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = tr->ctx;
+    EDS_REQUIRE(ctx, kf && dp && kf->ctx == ctx && dp->ctx == ctx, "tracker_get_coord: handles belong to different contexts");
+    EDS_REQUIRE(ctx, dp->N == kf->dev.N, "tracker_get_coord: the filter and the key frame have different point counts");
+    DeviceGuard g(ctx->device);
+    const size_t N = (size_t)kf->dev.N;
+    double* coord_dev = dp->coords + 2 * N;  // the filter's event-frame coordinate buffer
+    get_coord_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(kf->dev.N, kf->src + 2 * N, dp->state, tr->state, kf->dev.fx, kf->dev.fy,
+                                                                           kf->dev.cx, kf->dev.cy, kf->dev.W, kf->dev.H, coord_dev, dp->ok);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    if (coord_out) EDS_CUDA(ctx, cudaMemcpyAsync(coord_out, coord_dev, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (outlier_out) EDS_CUDA(ctx, cudaMemcpyAsync(outlier_out, dp->ok, N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (coord_out || outlier_out) EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_keyframe_refresh_idepth(edsgpu_keyframe* kf, const edsgpu_depth_points* dp) {
+    if (!kf) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = kf->ctx;
+    EDS_REQUIRE(ctx, dp && dp->ctx == ctx && dp->N == kf->dev.N, "keyframe_refresh_idepth: filter of another context or size");
+    DeviceGuard g(ctx->device);
+    const size_t N = (size_t)kf->dev.N;
+    KfDev& d = kf->dev;
+    // same preparation as at upload, the inverse depths read from column 0 of the filter state (KeyFrame::inv_depth.getIDepth, Tracker.cpp:167)
+    kf_prepare_kernel<<<d.B, 256, 0, ctx->stream>>>(kf->src, kf->src + 2 * N, dp->state, 4, kf->src + 5 * N, d.N, d.B, (float4*)d.gxy, (float2*)d.dw,
+                                                   (double*)d.kpx, (double*)d.kpy, (double*)d.kpz, (double*)d.A);
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_depth_points_update_from_tracker(edsgpu_depth_points* dp, edsgpu_tracker* tr, edsgpu_keyframe* kf, const double* kf_coord,
+                                                      int refresh_keyframe) {
+    if (!dp || !tr || !kf) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = dp->ctx;
+    EDS_REQUIRE(ctx, tr->ctx == ctx && kf->ctx == ctx && dp->N == kf->dev.N, "depth_points_update_from_tracker: mismatched handles");
+    DeviceGuard g(ctx->device);
+    const size_t N = (size_t)dp->N;
+    if (kf_coord) {  // KeyFrame::coord, once per key frame
+        EDS_CUDA(ctx, cudaMemcpyAsync(dp->coords, kf_coord, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, ctx->stream));
+        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    edsgpu_status st = edsgpu_tracker_get_coord(tr, kf, dp, nullptr, nullptr);
+    if (st == EDSGPU_OK) st = edsgpu_depth_update_tracked(dp, tr->state, dp->coords, dp->coords + 2 * N);
+    if (st == EDSGPU_OK && refresh_keyframe) st = edsgpu_keyframe_refresh_idepth(kf, dp);
+    return st;
 }
 
 }  // extern "C"

@@ -39,6 +39,7 @@ SYMBOLS = [
     "edsgpu_coarse_create", "edsgpu_coarse_destroy", "edsgpu_coarse_set_level", "edsgpu_coarse_set_reference",
     "edsgpu_coarse_set_new_frame", "edsgpu_coarse_calc_res_gs",
     "edsgpu_depth_points_create", "edsgpu_depth_points_destroy", "edsgpu_depth_points_update", "edsgpu_depth_points_get",
+    "edsgpu_tracker_get_coord", "edsgpu_keyframe_refresh_idepth", "edsgpu_depth_points_update_from_tracker",
 ]
 
 
@@ -539,6 +540,19 @@ class DepthPoints:
         st = np.zeros((self.N, 4))
         self.ctx.check(self.ctx.lib.edsgpu_depth_points_get(self.h, _ptr(st, C.c_double)))
         return st
+
+    def get_coord(self, tracker, keyframe):
+        """Tracker::getCoord with this filter's inverse depths -> (coord N x 2, outlier flags)."""
+        coord, out = np.zeros((self.N, 2)), np.zeros(self.N, np.uint8)
+        self.ctx.check(self.ctx.lib.edsgpu_tracker_get_coord(tracker.h, keyframe.h, self.h, _ptr(coord, C.c_double), _ptr(out, C.c_uint8)))
+        return coord, out
+
+    def update_from_tracker(self, tracker, keyframe, kf_coord=None, refresh_keyframe=True):
+        """getCoord -> update -> key-frame refresh, on the device (one call per tracked window)."""
+        kc = np.ascontiguousarray(kf_coord, np.float64) if kf_coord is not None else None
+        assert kc is None or kc.shape == (self.N, 2)
+        self.ctx.check(self.ctx.lib.edsgpu_depth_points_update_from_tracker(self.h, tracker.h, keyframe.h, _ptr(kc, C.c_double),
+                                                                            C.c_int(int(refresh_keyframe))))
 
     def close(self):
         if self.h:
