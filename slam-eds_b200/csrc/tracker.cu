@@ -4,16 +4,21 @@
 // functor PhotometricError (src/tracking/PhotometricError.hpp:56-214) and ceres::Solve
 // (un-vendored; trust-region LM restated from ceres-solver 1.14..2.1 semantics).
 //
-//   track_lm_kernel   one thread-block CLUSTER per tracking problem.  Residual blocks
-//                     (Tracker.cpp:178-195) are dealt round-robin to the CTAs of the cluster;
-//                     each CTA sweeps its points (fp64 warp/projection, fp32 bicubic + analytic
-//                     Jacobian, 90 fp32 outer-product accumulators per thread), reduces them with
-//                     a halving warp butterfly + fp64 cross-warp sum, applies the per-block loss
-//                     (rho') and stores its 91 doubles into the leader CTA's shared memory over
-//                     DSMEM.  The leader runs the whole Levenberg-Marquardt state machine
-//                     (Jacobi scaling, damping, 12x12 Cholesky, retractions, accept/reject,
-//                     tolerances) and publishes the next evaluation point to the cluster.  The LM
-//                     loop never returns to the host: one launch per batch of windows.
+//   track_lm_kernel   thread-block CLUSTERS of 512-thread CTAs, one CTA per SM; a cluster keeps K <= 4
+//                     tracking problems in flight.  Residual blocks (Tracker.cpp:178-195) are dealt
+//                     round-robin to the CTAs of the cluster.  In every CTA producer warps evaluate
+//                     32 points at a time (division-free fp64-exact projection, bicubic window as
+//                     four texture gathers, analytic Jacobian in fp32; software-pipelined) into a
+//                     shared-memory ring guarded by mbarriers, consumer warps own the 90 fp32
+//                     outer-product accumulators, reduce a block with a halving warp butterfly,
+//                     apply the per-block loss (rho') and store 92 doubles into the shared memory
+//                     of the problem's leader CTA over DSMEM.  One leader warp per problem runs the
+//                     whole Levenberg-Marquardt state machine (Jacobi scaling, damping, register-
+//                     resident 12x12 Cholesky, retractions, accept/reject, tolerances) and publishes
+//                     the next evaluation point to the cluster.  Evaluators and leaders hand over
+//                     through ready/result mbarriers (no cluster-wide barrier in the loop), so the
+//                     serial LM step of one problem overlaps the sweeps of the others.  The LM loop
+//                     never returns to the host: one launch per batch of windows.
 //   mad_kernel        next loss parameter (MAD / STD) from the written-back residuals
 //                     (Tracker.cpp:281-317) by radix select.
 //   kf_prepare_kernel keyframe upload: fp32 SoA gather streams, fp64 3-D points
@@ -169,8 +174,8 @@ struct EvalConst {
     int cmd;
 };
 
-// Per-problem state.  A cluster works on TWO problems in ping-pong (see track_lm_kernel): every CTA
-// holds the published constants of both, the leader CTA additionally the reduction slots and LM state.
+// Per-problem state.  A cluster keeps up to MAX_K problems in flight (see track_lm_kernel): every CTA holds the
+// published constants of all of them, the CTA that hosts a problem's leader additionally its reduction slots and LM state.
 struct ProblemShared {
     EvalConst ec;
     double loss_a;
@@ -422,7 +427,7 @@ struct RowBlock {
         return v[12];
     }
 };
-typedef RowBlock<0, 12> ConsRows;  // all 90 entries: one consumer warp per CTA keeps up with 7 producers
+typedef RowBlock<0, 12> ConsRows;  // all 90 entries per consumer warp; the consumers split the batches, not the rows
 
 // 96 per-lane partial sums -> warp totals; lane l ends with entries base(l)+{0,1,2}
 __device__ __forceinline__ void reduce96(float* acc, unsigned lane) {
@@ -442,7 +447,7 @@ __device__ __forceinline__ int reduce96_base(unsigned lane) {
 // Warp-specialised: producer warps sweep the points 32 at a time (residual + analytic Jacobian row
 // -> shared-memory ring slot, mbarrier "full"), consumer warps own the outer-product accumulators
 // (90 fp32 registers per lane) and drain the ring (mbarrier "empty").  No CTA-wide barrier inside
-// the sweep and <= 128 registers per thread, so two CTAs share an SM and hide each other's stalls
+// the sweep; 512 threads at <= 128 registers per thread = one CTA per SM, whose 16 warps hide each other's stalls
 // (and the leader's serial LM step).  `batch_counter` numbers the batches of the whole kernel so that
 // both sides derive slot and phase parity without talking to each other.
 // Evaluator roles of one CTA: warps 0..N_PROD-2 produce, the next N_CONS warps consume, the last warp
@@ -1082,7 +1087,7 @@ __device__ void leader_step(cg::cluster_group& cluster, CtaShared& sh, int which
 }
 
 // One cluster keeps K <= MAX_K independent tracking problems in flight (problems K*c .. K*c+K-1 for
-// cluster c).  Problem k is led by warp 7 of CTA rank k: a sequential Levenberg-Marquardt loop that
+// cluster c).  Problem k is led by the last warp of CTA rank k: a sequential Levenberg-Marquardt loop that
 // waits for the reduced sums of an evaluation, takes its decision and publishes the next evaluation
 // point to every CTA.  All other warps are evaluators: they visit the live problems round-robin,
 // wait until the problem's constants have landed, sweep this CTA's residual blocks and report.
