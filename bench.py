@@ -507,7 +507,9 @@ def run_native(args):
             "clocks": clk,
             "roofline": {"kernel": "track_lm_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "algorithmic_bytes_per_launch": alg, "launch_ms": lm_ms, "evaluations_per_launch": evals},
+                         "algorithmic_bytes_per_launch": alg, "launch_ms": lm_ms, "evaluations_per_launch": evals,
+                         "note": "launch_ms covers track_lm_kernel + mad_kernel; the working set is L2-resident (traffic << algorithmic bytes), "
+                                 "the kernel is bound by per-SM issue/latency of the sweep (~320 cycles per 32-point batch), see DESIGN.md 4.2"},
             "final_state_checksum": float(np.abs(final_states).sum()),
         }
         if ba_line:
