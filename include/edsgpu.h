@@ -301,6 +301,18 @@ edsgpu_status edsgpu_coarse_set_new_frame(edsgpu_coarse* coarse, int lvl, const 
 edsgpu_status edsgpu_coarse_calc_res_gs(edsgpu_coarse* coarse, int lvl, const double R[9], const double t[3], const float affLL[2],
                                         float b0, float cutoffTH, double rs[6], double H[64], double b[8]);
 
+/* CoarseTracker::trackNewestCoarse (:520-701): the coarse-to-fine Gauss-Newton loop (levels coarsest_lvl..0,
+ * Levenberg damping, step extrapolation, accept / reject, cutoff repeat) run on the host around the device
+ * evaluation; Sophus' SE3::exp and Eigen's 8x8 LDLT are restated.  R (row-major), t: lastToNew_out, in-out;
+ * aff_g2l: {a, b} of the new frame, in-out; ref_aff_g2l: lastRef_aff_g2l; exposures: ab_exposure of both frames;
+ * min_res_for_abort: 5 values or NULL (never abort); last_residuals (5, NaN where a level was not reached) and
+ * last_flow (3): lastResiduals / lastFlowIndicators.  Returns EDSGPU_NOT_USABLE where the reference returns
+ * false (pose and affine parameters are then left untouched, except for the affine range check, as in the
+ * reference). */
+edsgpu_status edsgpu_coarse_track(edsgpu_coarse* coarse, int coarsest_lvl, double R[9], double t[3], double aff_g2l[2],
+                                  const double ref_aff_g2l[2], float ref_exposure, float new_exposure, const double min_res_for_abort[5],
+                                  double last_residuals[5], double last_flow[3], int* evaluations_out);
+
 /* ---- per-point depth filter -----------------------------------------
  * eds::mapping::DepthPoints (src/mapping/DepthPoints.{hpp,cpp}): the filter state {mu = inverse
  * depth, sigma2, a, b} of every key-frame point stays on the device; update() is one launch. */

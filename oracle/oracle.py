@@ -350,3 +350,30 @@ def tracker_get_coord(kf, inv_depth, px, qx):
     yp = kf["fy"] * (p[:, 1] / p[:, 2]) + kf["cy"]
     outlier = (xp < 0.0) | (xp > kf["W"]) | (yp < 0.0) | (yp > kf["H"])
     return np.stack([xp, yp], 1), outlier.astype(np.uint8)
+
+
+def coarse_track(pb, coarsest_lvl, R, t, aff=(0.0, 0.0), ref_aff=(0.0, 0.0), ref_exposure=1.0, new_exposure=1.0, min_res_for_abort=None):
+    """CoarseTracker::trackNewestCoarse on a synth_coarse problem -> dict(ok, R, t, aff, last_residuals, last_flow, evaluations)."""
+    L = pb["levels"]
+    nl = len(L)
+    keep = []
+
+    def arr_of_ptrs(key):
+        a = [_f32(l[key]) for l in L]
+        keep.append(a)
+        return (C.POINTER(C.c_float) * nl)(*[_p(x, C.c_float) for x in a])
+
+    wl = _i32([l["w"] for l in L]); hl = _i32([l["h"] for l in L]); n = _i32([len(l["pc_u"]) for l in L])
+    fx, fy = _f32([l["fx"] for l in L]), _f32([l["fy"] for l in L])
+    cx, cy = _f32([l["cx"] for l in L]), _f32([l["cy"] for l in L])
+    Rm, tv, af, raf = np.array(R, np.float64).reshape(-1).copy(), np.array(t, np.float64).copy(), np.array(aff, np.float64), _f64(ref_aff)
+    mra = _f64(min_res_for_abort if min_res_for_abort is not None else [np.inf] * 5)
+    lr, lf = np.zeros(5), np.zeros(3)
+    ev = C.c_int(0)
+    f = lib().eds_oracle_coarse_track
+    f.restype = C.c_int
+    ok = f(C.c_int(coarsest_lvl), _p(wl, C.c_int32), _p(hl, C.c_int32), arr_of_ptrs("dI_new"), _p(fx, C.c_float), _p(fy, C.c_float),
+           _p(cx, C.c_float), _p(cy, C.c_float), arr_of_ptrs("Ki"), _p(n, C.c_int32), arr_of_ptrs("pc_u"), arr_of_ptrs("pc_v"),
+           arr_of_ptrs("pc_idepth"), arr_of_ptrs("pc_color"), _p(Rm, C.c_double), _p(tv, C.c_double), _p(af, C.c_double), _p(raf, C.c_double),
+           C.c_float(ref_exposure), C.c_float(new_exposure), _p(mra, C.c_double), _p(lr, C.c_double), _p(lf, C.c_double), C.byref(ev))
+    return dict(ok=bool(ok), R=Rm.reshape(3, 3), t=tv, aff=af, last_residuals=lr, last_flow=lf, evaluations=ev.value)

@@ -10,6 +10,7 @@
 // contraction), so the in-bounds / cutoff decisions are those a plain float32 CPU evaluation takes;
 // the sums E, H, b are carried in double across threads.
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -316,6 +317,163 @@ edsgpu_status edsgpu_coarse_calc_res_gs(edsgpu_coarse* c, int lvl, const double 
             b[r] = (double)(float)full[r][8] * inv_n * sc[r];
         }
     }
+    return EDSGPU_OK;
+}
+
+// ---- trackNewestCoarse: the coarse-to-fine Gauss-Newton loop on the host around the device evaluation ----------
+namespace {
+
+// Sophus SO3::exp (quaternion form) -> rotation matrix, row-major
+void so3_exp(const double* w, double* R) {
+    const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+    double imag, real;
+    if (th < 1e-10) {
+        const double th4 = th2 * th2;
+        imag = 0.5 - th2 / 48.0 + th4 / 3840.0;
+        real = 1.0 - th2 / 8.0 + th4 / 384.0;
+    } else {
+        imag = sin(0.5 * th) / th;
+        real = cos(0.5 * th);
+    }
+    const double x = imag * w[0], y = imag * w[1], z = imag * w[2], q = real;
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * q); R[2] = 2 * (x * z + y * q);
+    R[3] = 2 * (x * y + z * q); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * q);
+    R[6] = 2 * (x * z - y * q); R[7] = 2 * (y * z + x * q); R[8] = 1 - 2 * (x * x + y * y);
+}
+
+// (R, t) <- SE3::exp(inc) * (R, t), inc = [translation part, rotation part]
+void se3_left_update(const double* inc6, double* R, double* t) {
+    const double* u = inc6;
+    const double* w = inc6 + 3;
+    double Re[9], V[9];
+    so3_exp(w, Re);
+    const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+    const double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    if (th < 1e-10) {
+        for (int i = 0; i < 9; ++i) V[i] = Re[i];
+    } else {
+        const double A = (1.0 - cos(th)) / th2, B = (th - sin(th)) / (th2 * th);
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                double w2 = 0;
+                for (int k = 0; k < 3; ++k) w2 += W[3 * r + k] * W[3 * k + c];
+                V[3 * r + c] = (r == c ? 1.0 : 0.0) + A * W[3 * r + c] + B * w2;
+            }
+    }
+    double te[3], Rn[9], tn[3];
+    for (int r = 0; r < 3; ++r) te[r] = V[3 * r] * u[0] + V[3 * r + 1] * u[1] + V[3 * r + 2] * u[2];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) Rn[3 * r + c] = Re[3 * r] * R[c] + Re[3 * r + 1] * R[3 + c] + Re[3 * r + 2] * R[6 + c];
+        tn[r] = Re[3 * r] * t[0] + Re[3 * r + 1] * t[1] + Re[3 * r + 2] * t[2] + te[r];
+    }
+    memcpy(R, Rn, sizeof(Rn));
+    memcpy(t, tn, sizeof(tn));
+}
+
+// x = A^-1 rhs, A symmetric positive definite 8x8 (LDL^T; the reference calls Eigen's ldlt().solve)
+void solve8(const double* A, const double* rhs, double* x) {
+    double L[64] = {0}, D[8], y[8];
+    for (int j = 0; j < 8; ++j) {
+        double d = A[8 * j + j];
+        for (int k = 0; k < j; ++k) d -= L[8 * j + k] * L[8 * j + k] * D[k];
+        D[j] = d;
+        L[8 * j + j] = 1.0;
+        for (int i = j + 1; i < 8; ++i) {
+            double v = A[8 * i + j];
+            for (int k = 0; k < j; ++k) v -= L[8 * i + k] * L[8 * j + k] * D[k];
+            L[8 * i + j] = v / d;
+        }
+    }
+    for (int i = 0; i < 8; ++i) { double v = rhs[i]; for (int k = 0; k < i; ++k) v -= L[8 * i + k] * y[k]; y[i] = v; }
+    for (int i = 0; i < 8; ++i) y[i] /= D[i];
+    for (int i = 7; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 8; ++k) v -= L[8 * k + i] * x[k]; x[i] = v; }
+}
+
+}  // namespace
+
+edsgpu_status edsgpu_coarse_track(edsgpu_coarse* c, int coarsest_lvl, double R[9], double t[3], double aff_g2l[2], const double ref_aff_g2l[2],
+                                  float ref_exposure, float new_exposure, const double min_res_for_abort[5], double last_residuals[5],
+                                  double last_flow[3], int* evaluations_out) {
+    if (!c) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = c->ctx;
+    EDS_REQUIRE(ctx, R && t && aff_g2l && ref_aff_g2l && last_residuals && last_flow, "coarse_track: null argument");
+    EDS_REQUIRE(ctx, coarsest_lvl >= 0 && coarsest_lvl < 5 && coarsest_lvl < (int)c->levels.size(), "coarse_track: coarsest level out of range");
+    const float setting_coarseCutoffTH = 20.0f;  // settings.cpp:138
+    const int maxIterations[5] = {10, 20, 100, 100, 100};
+    const float lambdaExtrapolationLimit = 0.001f;
+    int evaluations = 0;
+    edsgpu_status st = EDSGPU_OK;
+    auto eval = [&](int lvl, const double* Rc, const double* tc, const double* affc, float cutoff, double* rs, double* H, double* b) {
+        // AffLight::fromToVecExposure, NumType.h:175-187
+        float eF = ref_exposure, eT = new_exposure;
+        if (eF == 0 || eT == 0) eF = eT = 1;
+        const double a = exp(affc[0] - ref_aff_g2l[0]) * eT / eF;
+        const float ll[2] = {(float)a, (float)(affc[1] - a * ref_aff_g2l[1])};
+        ++evaluations;
+        return edsgpu_coarse_calc_res_gs(c, lvl, Rc, tc, ll, (float)ref_aff_g2l[1], cutoff, rs, H, b);
+    };
+    for (int i = 0; i < 5; ++i) last_residuals[i] = NAN;
+    for (int i = 0; i < 3; ++i) last_flow[i] = 1000;
+    double Rc[9], tc[3], affc[2] = {aff_g2l[0], aff_g2l[1]};
+    memcpy(Rc, R, sizeof(Rc));
+    memcpy(tc, t, sizeof(tc));
+    bool haveRepeated = false, ok = true;
+    for (int lvl = coarsest_lvl; lvl >= 0 && ok; lvl--) {
+        double H[64], b[8], resOld[6];
+        float levelCutoffRepeat = 1;
+        if ((st = eval(lvl, Rc, tc, affc, setting_coarseCutoffTH * levelCutoffRepeat, resOld, H, b)) != EDSGPU_OK) return st;
+        while (resOld[5] > 0.6 && levelCutoffRepeat < 50) {
+            levelCutoffRepeat *= 2;
+            if ((st = eval(lvl, Rc, tc, affc, setting_coarseCutoffTH * levelCutoffRepeat, resOld, H, b)) != EDSGPU_OK) return st;
+        }
+        float lambda = 0.01f;
+        for (int iteration = 0; iteration < maxIterations[lvl]; iteration++) {
+            double Hl[64], nb[8], inc[8];
+            memcpy(Hl, H, sizeof(Hl));
+            for (int i = 0; i < 8; ++i) { Hl[9 * i] *= (1 + lambda); nb[i] = -b[i]; }
+            solve8(Hl, nb, inc);  // both affine parameters are optimised (setting_affineOptModeA/B >= 0, settings.cpp:119-120)
+            float extrapFac = 1;
+            if (lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / lambda));
+            for (int i = 0; i < 8; ++i) inc[i] *= extrapFac;
+            double incScaled[8];
+            memcpy(incScaled, inc, sizeof(inc));
+            incScaled[6] *= 10.0f;    // SCALE_A (SCALE_XI_ROT = SCALE_XI_TRANS = 1)
+            incScaled[7] *= 1000.0f;  // SCALE_B
+            double sum = 0;
+            for (int i = 0; i < 8; ++i) sum += incScaled[i];
+            if (!std::isfinite(sum)) memset(incScaled, 0, sizeof(incScaled));
+            double Rn[9], tn[3], affn[2] = {affc[0] + incScaled[6], affc[1] + incScaled[7]};
+            memcpy(Rn, Rc, sizeof(Rn));
+            memcpy(tn, tc, sizeof(tn));
+            se3_left_update(incScaled, Rn, tn);
+            double resNew[6], Hn[64], bn[8];  // the fused evaluation already has the system the reference recomputes on accept
+            if ((st = eval(lvl, Rn, tn, affn, setting_coarseCutoffTH * levelCutoffRepeat, resNew, Hn, bn)) != EDSGPU_OK) return st;
+            const bool accept = (resNew[0] / resNew[1]) < (resOld[0] / resOld[1]);
+            if (accept) {
+                memcpy(H, Hn, sizeof(H)); memcpy(b, bn, sizeof(b)); memcpy(resOld, resNew, sizeof(resOld));
+                affc[0] = affn[0]; affc[1] = affn[1];
+                memcpy(Rc, Rn, sizeof(Rc)); memcpy(tc, tn, sizeof(tc));
+                lambda *= 0.5f;
+            } else {
+                lambda *= 4;
+                if (lambda < lambdaExtrapolationLimit) lambda = lambdaExtrapolationLimit;
+            }
+            double norm2 = 0;
+            for (int i = 0; i < 8; ++i) norm2 += inc[i] * inc[i];
+            if (!(sqrt(norm2) > 1e-3)) break;
+        }
+        last_residuals[lvl] = sqrtf((float)(resOld[0] / resOld[1]));
+        for (int i = 0; i < 3; ++i) last_flow[i] = resOld[2 + i];
+        if (min_res_for_abort && last_residuals[lvl] > 1.5 * min_res_for_abort[lvl]) ok = false;
+        if (ok && levelCutoffRepeat > 1 && !haveRepeated) { lvl++; haveRepeated = true; }
+    }
+    if (evaluations_out) *evaluations_out = evaluations;
+    if (!ok) return edsgpu_fail(ctx, EDSGPU_NOT_USABLE, "coarse_track: residual above the abort threshold");
+    memcpy(R, Rc, sizeof(Rc));
+    memcpy(t, tc, sizeof(tc));
+    aff_g2l[0] = affc[0]; aff_g2l[1] = affc[1];
+    if (fabsf((float)affc[0]) > 1.2f || fabsf((float)affc[1]) > 200.f)  // :683-685
+        return edsgpu_fail(ctx, EDSGPU_NOT_USABLE, "coarse_track: affine brightness parameters out of range");
     return EDSGPU_OK;
 }
 

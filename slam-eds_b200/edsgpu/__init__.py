@@ -37,7 +37,7 @@ SYMBOLS = [
     "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_get_residuals",
     "edsgpu_ba_resubstitute", "edsgpu_ba_fix_linearization", "edsgpu_ba_calc_l_energy",
     "edsgpu_coarse_create", "edsgpu_coarse_destroy", "edsgpu_coarse_set_level", "edsgpu_coarse_set_reference",
-    "edsgpu_coarse_set_new_frame", "edsgpu_coarse_calc_res_gs",
+    "edsgpu_coarse_set_new_frame", "edsgpu_coarse_calc_res_gs", "edsgpu_coarse_track",
     "edsgpu_depth_points_create", "edsgpu_depth_points_destroy", "edsgpu_depth_points_update", "edsgpu_depth_points_get",
     "edsgpu_tracker_get_coord", "edsgpu_keyframe_refresh_idepth", "edsgpu_depth_points_update_from_tracker",
 ]
@@ -507,6 +507,20 @@ class CoarseTracker:
                                                               C.c_float(b0), C.c_float(cutoffTH), _ptr(rs, C.c_double), _ptr(H, C.c_double),
                                                               _ptr(b, C.c_double)))
         return dict(rs=rs, H=H, b=b)
+
+    def track(self, coarsest_lvl, R, t, aff=(0.0, 0.0), ref_aff=(0.0, 0.0), ref_exposure=1.0, new_exposure=1.0, min_res_for_abort=None):
+        """trackNewestCoarse -> dict(ok, R, t, aff, last_residuals, last_flow, evaluations)."""
+        Rm = np.array(R, np.float64).reshape(-1).copy()
+        tv, af = np.array(t, np.float64).copy(), np.array(aff, np.float64).copy()
+        raf = np.ascontiguousarray(ref_aff, np.float64)
+        mra = np.ascontiguousarray(min_res_for_abort, np.float64) if min_res_for_abort is not None else None
+        lr, lf, ev = np.zeros(5), np.zeros(3), C.c_int(0)
+        st = self.ctx.lib.edsgpu_coarse_track(self.h, C.c_int(coarsest_lvl), _ptr(Rm, C.c_double), _ptr(tv, C.c_double), _ptr(af, C.c_double),
+                                              _ptr(raf, C.c_double), C.c_float(ref_exposure), C.c_float(new_exposure), _ptr(mra, C.c_double),
+                                              _ptr(lr, C.c_double), _ptr(lf, C.c_double), C.byref(ev))
+        if st not in (OK, NOT_USABLE):
+            self.ctx.check(st)
+        return dict(ok=(st == OK), R=Rm.reshape(3, 3), t=tv, aff=af, last_residuals=lr, last_flow=lf, evaluations=ev.value)
 
     def close(self):
         if self.h:

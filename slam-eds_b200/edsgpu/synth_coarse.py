@@ -28,7 +28,7 @@ def make_coarse_problem(W=640, H=480, levels=4, points=20000, seed=7, pose_error
     t_true = rng.normal(scale=0.03, size=3)
     fx0 = fy0 = 520.0 * W / 640.0
     cx0, cy0 = W / 2 - 0.5, H / 2 - 0.5
-    out = dict(levels=[], R=(_so3_exp(rng.normal(scale=pose_error, size=3)) @ R_true), t=t_true + rng.normal(scale=pose_error, size=3),
+    out = dict(levels=[], R_true=R_true, t_true=t_true, R=(_so3_exp(rng.normal(scale=pose_error, size=3)) @ R_true), t=t_true + rng.normal(scale=pose_error, size=3),
                affLL=np.array([1.02, -1.5], f32), b0=f32(0.7), cutoffTH=f32(20.0))
     lo, hi = -3.0, 3.0
     for lvl in range(levels):

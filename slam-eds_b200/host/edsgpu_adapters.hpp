@@ -336,6 +336,15 @@ class CoarseTrackerEval {
     void calcResAndGS(int lvl, const double R[9], const double t[3], const float affLL[2], float b0, float cutoffTH, double rs[6], double* H, double* b) {
         ctx_.check(edsgpu_coarse_calc_res_gs(ct_, lvl, R, t, affLL, b0, cutoffTH, rs, H, b));
     }
+    // trackNewestCoarse: false where the reference returns false
+    bool trackNewestCoarse(int coarsestLvl, double R[9], double t[3], double aff_g2l[2], const double ref_aff_g2l[2], float refExposure,
+                           float newExposure, const double minResForAbort[5], double lastResiduals[5], double lastFlowIndicators[3]) {
+        const edsgpu_status st = edsgpu_coarse_track(ct_, coarsestLvl, R, t, aff_g2l, ref_aff_g2l, refExposure, newExposure, minResForAbort,
+                                                     lastResiduals, lastFlowIndicators, nullptr);
+        if (st == EDSGPU_NOT_USABLE) return false;
+        ctx_.check(st);
+        return true;
+    }
 
   private:
     const edsgpu_host::Context& ctx_;

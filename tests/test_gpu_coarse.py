@@ -83,3 +83,25 @@ def test_gpu_against_committed_coarse_fixture(gpu_ctx):
         assert got["rs"][1] == ref[1] and got["rs"][5] == ref[5] and abs(got["rs"][0] - ref[0]) <= TOL * ref[0]
         assert rel(got["H"], g["H%d" % lvl]) < TOL and rel(got["b"], g["b%d" % lvl]) < TOL
     ct.close()
+
+
+def test_track_newest_coarse_matches_the_oracle_loop(gpu_ctx):
+    """edsgpu_coarse_track (host loop around the device evaluation) against the oracle's loop: same number of
+    evaluations, same accept / reject history, final pose and brightness parameters to 1e-6."""
+    pb = SC.make_coarse_problem(W=320, H=240, levels=4, points=8000, seed=5, pose_error=6e-3)
+    ct = edsgpu.CoarseTracker(gpu_ctx, 4)
+    for lvl, L in enumerate(pb["levels"]):
+        ct.set_level(lvl, L["w"], L["h"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"])
+        ct.set_reference(lvl, L["pc_u"], L["pc_v"], L["pc_idepth"], L["pc_color"])
+        ct.set_new_frame(lvl, L["dI_new"])
+    ref = O.coarse_track(pb, 3, pb["R"], pb["t"])
+    got = ct.track(3, pb["R"], pb["t"])
+    assert got["ok"] and ref["ok"] and got["evaluations"] == ref["evaluations"]
+    assert np.abs(got["R"] - ref["R"]).max() < 1e-6 and np.abs(got["t"] - ref["t"]).max() < 1e-6
+    assert np.abs(got["aff"] - ref["aff"]).max() < 1e-4
+    assert np.allclose(got["last_residuals"][:4], ref["last_residuals"][:4], rtol=1e-5) and np.isnan(got["last_residuals"][4])
+    assert np.allclose(got["last_flow"], ref["last_flow"], rtol=1e-5)
+    # failure is reported like the reference's `return false`, the caller's pose is left alone
+    bad = ct.track(3, pb["R"], pb["t"], min_res_for_abort=[1e-3] * 5)
+    assert not bad["ok"] and np.array_equal(bad["R"], np.asarray(pb["R"], np.float64)) and np.array_equal(bad["t"], pb["t"])
+    ct.close()

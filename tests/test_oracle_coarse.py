@@ -54,3 +54,25 @@ def test_oracle_against_committed_coarse_fixture():
         r = _eval(pb, lvl, pb["R"], pb["t"])
         assert np.array_equal(r["counts"], g["counts%d" % lvl])
         assert np.array_equal(r["rs"], g["rs%d" % lvl]) and np.array_equal(r["H"], g["H%d" % lvl]) and np.array_equal(r["b"], g["b%d" % lvl])
+
+
+def _angle(Ra, Rb):
+    return float(np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)))
+
+
+def test_track_newest_coarse_recovers_the_pose():
+    """trackNewestCoarse (oracle restatement incl. Sophus SE3::exp and the 8x8 LDLT) on the synthetic pyramid: from a
+    wrong start the coarse-to-fine loop must land near the true relative pose (the point depths carry 1 % noise)."""
+    pb = SC.make_coarse_problem(W=320, H=240, levels=4, points=8000, seed=5, pose_error=6e-3)
+    for L in pb["levels"]:
+        L["pc_color"][::53] -= 60.0   # no planted outliers here
+    e0 = (_angle(pb["R"], pb["R_true"]), np.linalg.norm(pb["t"] - pb["t_true"]))
+    r = O.coarse_track(pb, 3, pb["R"], pb["t"])
+    e1 = (_angle(r["R"], pb["R_true"]), np.linalg.norm(r["t"] - pb["t_true"]))
+    assert r["ok"] and 8 <= r["evaluations"] <= 200
+    assert e1[0] < 0.15 * e0[0] and e1[1] < 0.1 * e0[1]
+    assert np.all(np.isfinite(r["last_residuals"][:4])) and np.isnan(r["last_residuals"][4])
+    assert abs(r["aff"][0]) < 0.01 and abs(r["aff"][1]) < 0.5        # both frames were rendered with the same brightness
+    # the abort threshold of the caller is honoured (:668)
+    bad = O.coarse_track(pb, 3, pb["R"], pb["t"], min_res_for_abort=[1e-3] * 5)
+    assert not bad["ok"]
