@@ -285,8 +285,21 @@ def bench_coarse(ctx, stream, reps=200):
         n = len(L["pc_u"])
         out.append({"level": lvl, "points": n, "ms_per_evaluation": ms, "points_per_s": n / (ms * 1e-3), "cpu_port_ms_1_thread": cpu_ms,
                     "algorithmic_bytes": n * (16 + 4 * 16)})  # point record + 4 bilinear taps of {I,dx,dy,0}
+    # the whole of trackNewestCoarse from a wrong start (coarsest level 3)
+    for _ in range(3):
+        tr = ct.track(3, pb["R"], pb["t"])
+    t0 = time.perf_counter()
+    for _ in range(20):
+        tr = ct.track(3, pb["R"], pb["t"])
+    track_ms = 1e3 * (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(3):
+        tr_cpu = O.coarse_track(pb, 3, pb["R"], pb["t"])
+    track_cpu_ms = 1e3 * (time.perf_counter() - t0) / 3
     ct.close()
-    return {"workload": "coarse tracker: calcRes + calcGSSSE per level, 640x480, host-synchronous call", "levels": out}
+    return {"workload": "coarse tracker: calcRes + calcGSSSE per level, 640x480, host-synchronous call", "levels": out,
+            "track_newest_coarse": {"ms": track_ms, "evaluations": tr["evaluations"], "ok": tr["ok"], "cpu_port_ms_1_thread": track_cpu_ms,
+                                    "cpu_evaluations": tr_cpu["evaluations"]}}
 
 
 def bench_depth(ctx, stream, n=10240, reps=100):
