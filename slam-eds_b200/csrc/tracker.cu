@@ -1742,6 +1742,14 @@ edsgpu_status edsgpu_batch_optimize(edsgpu_batch* b) {
     return EDSGPU_OK;
 }
 
+edsgpu_status edsgpu_batch_launch_shape(const edsgpu_batch* b, int* clusters, int* ctas_per_cluster, int* problems_in_flight) {
+    if (!b) return EDSGPU_INVALID_ARGUMENT;
+    if (clusters) *clusters = b->shape.nclusters;
+    if (ctas_per_cluster) *ctas_per_cluster = b->shape.csize;
+    if (problems_in_flight) *problems_in_flight = b->shape.K;
+    return EDSGPU_OK;
+}
+
 edsgpu_status edsgpu_batch_pack_states_dev(edsgpu_batch* b, double* states_dev) {
     if (!b || !states_dev) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = b->ctx;

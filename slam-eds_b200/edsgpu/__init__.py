@@ -30,7 +30,7 @@ SYMBOLS = [
     "edsgpu_frames_read", "edsgpu_frames_read_accumulator", "edsgpu_keyframe_create", "edsgpu_keyframe_destroy",
     "edsgpu_tracker_create", "edsgpu_tracker_destroy", "edsgpu_tracker_set_state", "edsgpu_tracker_get_state",
     "edsgpu_tracker_optimize", "edsgpu_trackers_optimize_batch", "edsgpu_trackers_gather", "edsgpu_tracker_state_dev",
-    "edsgpu_batch_create", "edsgpu_batch_destroy", "edsgpu_batch_optimize", "edsgpu_batch_pack_states_dev",
+    "edsgpu_batch_create", "edsgpu_batch_destroy", "edsgpu_batch_optimize", "edsgpu_batch_pack_states_dev", "edsgpu_batch_launch_shape",
     "edsgpu_tracker_evaluate",
     "edsgpu_ba_create", "edsgpu_ba_destroy", "edsgpu_ba_set_residuals", "edsgpu_ba_set_points", "edsgpu_ba_set_frames",
     "edsgpu_ba_top_accumulate", "edsgpu_ba_top_stitch", "edsgpu_ba_sc_accumulate", "edsgpu_ba_sc_stitch", "edsgpu_ba_get_jpjd",
@@ -301,6 +301,12 @@ class TrackerBatch:
 
     def optimize(self):
         self.ctx.check(self.ctx.lib.edsgpu_batch_optimize(self.h))
+
+    def launch_shape(self):
+        """(clusters, CTAs per cluster, problems in flight per cluster) of the batched launch."""
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self.ctx.check(self.ctx.lib.edsgpu_batch_launch_shape(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def pack_states_dev(self, dev_ptr):
         self.ctx.check(self.ctx.lib.edsgpu_batch_pack_states_dev(self.h, C.c_void_p(dev_ptr)))
