@@ -46,11 +46,20 @@ constexpr int JLD = 20;         // floats per point row in shared memory (80 B: 
 constexpr int N_CONS = EDS_N_CONS;           // consumer warps: own the outer-product accumulators (batches j = c mod N_CONS)
 constexpr int N_PROD = TRK_WARPS - N_CONS;   // producer warps (one fewer in a CTA that hosts a leader warp)
 constexpr int LEADER_WARP = TRK_WARPS - 1;
-constexpr int N_SLOTS = 3 * N_PROD;          // ring of 32-point batches, three per producer warp (absorbs stragglers)
+#ifndef EDS_RING_DEPTH
+#define EDS_RING_DEPTH 3
+#endif
+constexpr int RING_DEPTH = EDS_RING_DEPTH;   // ring slots per producer warp (three absorb stragglers)
+// capacity of the ring of 32-point batches; a CTA uses the largest multiple of its producer count that fits: RING_DEPTH
+// slots per warp with N_PROD producers, one more per warp in a CTA that gives a warp to a leader
+constexpr int N_SLOTS = (RING_DEPTH * N_PROD > (RING_DEPTH + 1) * (N_PROD - 1)) ? RING_DEPTH * N_PROD : (RING_DEPTH + 1) * (N_PROD - 1);
 constexpr int NSLOT = 92;       // 78 + 12 + cost + block squared norm
 constexpr int MAX_BLOCKS = 16;  // residual blocks per problem (config.options.num_threads)
 constexpr int MAX_CLUSTER = 8;
-constexpr int MAX_K = 4;  // problems one cluster keeps in flight
+#ifndef EDS_MAX_K
+#define EDS_MAX_K 4
+#endif
+constexpr int MAX_K = EDS_MAX_K;  // problems one cluster keeps in flight
 constexpr double kEps = 1e-05;  // PhotometricError.hpp:200
 
 enum { CMD_EVAL = 1, CMD_FINAL = 2, CMD_DONE = 3 };
@@ -350,14 +359,26 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity, int tag = 0) {
     unsigned ok;
+#ifdef EDS_WATCHDOG
+    unsigned long long spins = 0;
+#endif
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)  // suspend-time hint (ns): sleep instead of spinning
             : "memory");
+#ifdef EDS_WATCHDOG
+        if (!ok && ++spins > 400000ull) {  // debug build: report the wait that does not end (~1 s), then stop the kernel
+            if ((threadIdx.x & 31) == 0)
+                printf("[watchdog] block %d warp %d stuck in wait %d, barrier offset %u, parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), tag,
+                       smem_u32(bar), parity);
+            __nanosleep(100000000);
+            __trap();
+        }
+#endif
     } while (!ok);
 }
 
@@ -374,14 +395,26 @@ __device__ __forceinline__ void mbar_arrive_cluster_relaxed(unsigned long long* 
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(local_bar), cta_rank)) : "memory");
 }
 __device__ __forceinline__ void fence_cluster();
-__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, unsigned parity, int tag = 0) {
     unsigned ok;
+#ifdef EDS_WATCHDOG
+    unsigned long long spins = 0;
+#endif
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
             : "memory");
+#ifdef EDS_WATCHDOG
+        if (!ok && ++spins > 400000ull) {
+            if ((threadIdx.x & 31) == 0)
+                printf("[watchdog] block %d warp %d stuck in cluster wait %d, barrier offset %u, parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+                       tag, smem_u32(bar), parity);
+            __nanosleep(100000000);
+            __trap();
+        }
+#endif
     } while (!ok);
 }
 __device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
@@ -471,7 +504,7 @@ __device__ __forceinline__ Roles make_roles(bool hosts_leader) {
     return r;
 }
 
-template <bool RES_ONLY>
+template <bool RES_ONLY, bool HOSTS_LEADER>
 __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base /* [MAX_BLOCKS][NSLOT] on the leader */,
                              int rank, int csize, const Roles& role, bool write_residuals, unsigned& batch_counter, unsigned& block_counter) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -481,6 +514,12 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
     const float inv_norm = (float)P.norms[1];
     const double loss_a = ps.loss_a;
     const int ne = kf.ne;
+    // The ring of this CTA has a whole number of slots per producer warp, so that batch g and batch g + n_slots -- the
+    // successive occupants of a slot -- always belong to the SAME producer.  That warp passes through every
+    // "empty" wait of its slots in order and can never be a whole lap ahead of the barrier's phase (with slots shared
+    // between producers a fast warp could test a parity that is two phases stale and overwrite an unconsumed batch).
+    constexpr int CTA_PROD = HOSTS_LEADER ? N_PROD - 1 : N_PROD;  // compile-time: strides and wrap tests fold into immediates
+    constexpr unsigned n_slots = (unsigned)(CTA_PROD * (N_SLOTS / CTA_PROD));
     // The texture handle is read from shared memory, which the compiler cannot prove warp-uniform: it
     // would wrap every fetch in a loop over the distinct handles of the warp.  A warp-wide OR leaves
     // the value unchanged and lands in a uniform register.
@@ -493,7 +532,8 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
             // number (uneven shares even out over consecutive blocks and visits).  Two-stage software
             // pipeline: the fp64 geometry of the NEXT batch is computed while the texture gathers of the
             // current one are in flight; the per-batch dependent latency is what bounds the sweep.
-            const int B = kf.B, n_prod = role.n_prod;
+            const int B = kf.B;
+            constexpr int n_prod = CTA_PROD;
             // every block has `ne` points except the last one, which also takes the remainder (Tracker.cpp:178-190)
             const int n_last = kf.N - (B - 1) * ne;
             const int nb_reg = (ne + 31) >> 5, nb_last = (n_last + 31) >> 5;
@@ -510,7 +550,7 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
             auto advance = [&](Cursor& c) {  // consecutive batches of a warp are n_prod apart in the running numbering
                 c.j += n_prod;
                 c.slot += (unsigned)n_prod;
-                if (c.slot >= (unsigned)N_SLOTS) { c.slot -= N_SLOTS; c.phase ^= 1u; }
+                if (c.slot >= n_slots) { c.slot -= n_slots; c.phase ^= 1u; }
                 if (c.j >= c.nbb) enter(c);
             };
             Cursor cur;
@@ -520,8 +560,8 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
             cur.n_pts = (rank + 1 == B) ? n_last : ne;
             {
                 const unsigned g0 = batch_counter + (unsigned)cur.j;
-                cur.slot = g0 % N_SLOTS;
-                cur.phase = (g0 / N_SLOTS) & 1u;
+                cur.slot = g0 % n_slots;
+                cur.phase = (g0 / n_slots) & 1u;
             }
             enter(cur);
             // pipeline state: `cur` has its geometry, `nxt` has its 3-D points loaded (two batches of loads in
@@ -579,7 +619,7 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
 #ifdef EDS_TIMING
                 const long long te0 = clock64();
 #endif
-                mbar_wait(&sh.empty_bar[slot], cur.phase ^ 1u);
+                mbar_wait(&sh.empty_bar[slot], cur.phase ^ 1u, 1);
 #ifdef EDS_TIMING
                 if (lane == 0 && rank == csize - 1) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
 #endif
@@ -624,15 +664,15 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
             unsigned slot, phase;
             {
                 const unsigned g0 = batch_counter + (unsigned)role.cidx;
-                slot = g0 % N_SLOTS;
-                phase = (g0 / N_SLOTS) & 1u;
+                slot = g0 % n_slots;
+                phase = (g0 / n_slots) & 1u;
             }
             for (int j = role.cidx; j < nb; j += N_CONS, slot += N_CONS) {
-                if (slot >= (unsigned)N_SLOTS) { slot -= N_SLOTS; phase ^= 1u; }
+                if (slot >= n_slots) { slot -= n_slots; phase ^= 1u; }
 #ifdef EDS_TIMING
                 const long long tw0 = clock64();
 #endif
-                mbar_wait(&sh.full_bar[slot], phase);
+                mbar_wait(&sh.full_bar[slot], phase, 2);
 #ifdef EDS_TIMING
                 if (lane == 0 && rank == csize - 1 && role.cidx == 0) { atomicAdd(&g_timing[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_timing[17], 1ull); }
 #endif
@@ -1123,7 +1163,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
 #ifdef EDS_TIMING
                 const unsigned long long t0 = gtime();
 #endif
-                mbar_wait_cluster(&sh.result_bar[rank], parity);
+                mbar_wait_cluster(&sh.result_bar[rank], parity, 4);
                 parity ^= 1u;
 #ifdef EDS_TIMING
                 const unsigned long long t1 = gtime();
@@ -1150,20 +1190,22 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
 #ifdef EDS_TIMING
                 const unsigned long long t0 = gtime();
 #endif
-                mbar_wait_cluster(&sh.ready_bar[k], (parity >> k) & 1u);
+                mbar_wait_cluster(&sh.ready_bar[k], (parity >> k) & 1u, 3);
                 parity ^= 1u << k;
 #ifdef EDS_TIMING
                 const unsigned long long t1 = gtime();
 #endif
                 const int cmd = ps.ec.cmd;
                 if (cmd == CMD_EVAL) {
-                    cta_evaluate<false>(ps, sh, &cluster.map_shared_rank(&sh, k)->prob[k].slots[0][0], rank, csize, role, false, batch_counter, block_counter);
+                    double* slots = &cluster.map_shared_rank(&sh, k)->prob[k].slots[0][0];
+                    if (hosts_leader) cta_evaluate<false, true>(ps, sh, slots, rank, csize, role, false, batch_counter, block_counter);
+                    else cta_evaluate<false, false>(ps, sh, slots, rank, csize, role, false, batch_counter, block_counter);
                     // the consumer's block sums went over DSMEM: order them before the signal
                     if (role.cidx == 0) fence_cluster();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(&sh.result_bar[k], (unsigned)k);
                 } else {
-                    if (cmd == CMD_FINAL) cta_evaluate<true>(ps, sh, nullptr, rank, csize, role, true, batch_counter, block_counter);
+                    if (cmd == CMD_FINAL) cta_evaluate<true, false>(ps, sh, nullptr, rank, csize, role, true, batch_counter, block_counter);
                     live &= ~(1u << k);
                 }
 #ifdef EDS_TIMING
@@ -1204,7 +1246,10 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_eval_kernel(const Proble
     if (is_leader_warp) leader_publish(cluster, sh, 0, ps.x_eval, CMD_EVAL, ps.P.kf.B, csize, false);
     cluster.sync();
     unsigned batch_counter = 0, block_counter = 0;
-    if (!is_leader_warp) cta_evaluate<false>(ps, sh, &leader->prob[0].slots[0][0], rank, csize, role, true, batch_counter, block_counter);
+    if (!is_leader_warp) {
+        if (rank == 0) cta_evaluate<false, true>(ps, sh, &leader->prob[0].slots[0][0], rank, csize, role, true, batch_counter, block_counter);
+        else cta_evaluate<false, false>(ps, sh, &leader->prob[0].slots[0][0], rank, csize, role, true, batch_counter, block_counter);
+    }
     cluster.sync();
     const ProblemDesc& P = ps.P;
     if (rank == 0 && threadIdx.x == 0 && P.eval_out) {
