@@ -520,6 +520,11 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
     // between producers a fast warp could test a parity that is two phases stale and overwrite an unconsumed batch).
     constexpr int CTA_PROD = HOSTS_LEADER ? N_PROD - 1 : N_PROD;  // compile-time: strides and wrap tests fold into immediates
     constexpr unsigned n_slots = (unsigned)(CTA_PROD * (N_SLOTS / CTA_PROD));
+    // The mirror image on the "full" side: within a residual block the successive occupants of a slot must be drained by
+    // the SAME consumer warp (it takes its batches in order, so it cannot test a stale parity either); batch j goes to
+    // consumer j mod N_CONS, hence the ring size must be a multiple of N_CONS.  Across blocks the consumers' end-of-block
+    // barrier keeps them within one block of each other.
+    static_assert(n_slots % N_CONS == 0, "ring slots per CTA must be a multiple of the consumer warps");
     // The texture handle is read from shared memory, which the compiler cannot prove warp-uniform: it
     // would wrap every fetch in a loop over the distinct handles of the warp.  A warp-wide OR leaves
     // the value unchanged and lands in a uniform register.
