@@ -50,9 +50,8 @@ constexpr int LEADER_WARP = TRK_WARPS - 1;
 #define EDS_RING_DEPTH 3
 #endif
 constexpr int RING_DEPTH = EDS_RING_DEPTH;   // ring slots per producer warp (three absorb stragglers)
-// capacity of the ring of 32-point batches; a CTA uses the largest multiple of its producer count that fits: RING_DEPTH
-// slots per warp with N_PROD producers, one more per warp in a CTA that gives a warp to a leader
-constexpr int N_SLOTS = (RING_DEPTH * N_PROD > (RING_DEPTH + 1) * (N_PROD - 1)) ? RING_DEPTH * N_PROD : (RING_DEPTH + 1) * (N_PROD - 1);
+// capacity of the ring of 32-point batches; a CTA uses RING_DEPTH slots per producer warp it actually has
+constexpr int N_SLOTS = RING_DEPTH * N_PROD;
 constexpr int NSLOT = 92;       // 78 + 12 + cost + block squared norm
 constexpr int MAX_BLOCKS = 16;  // residual blocks per problem (config.options.num_threads)
 constexpr int MAX_CLUSTER = 8;
