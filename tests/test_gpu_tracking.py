@@ -294,6 +294,16 @@ def test_results_do_not_depend_on_launch_shape(gpu_ctx, problems, monkeypatch):
     monkeypatch.delenv("EDSGPU_CLUSTER", raising=False)
     monkeypatch.delenv("EDSGPU_INFLIGHT", raising=False)
     base_states, base_infos = run()
+    trs = [edsgpu.Tracker(gpu_ctx, num_blocks=8) for _ in range(n)]
+    b = edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * n, fr, 0)
+    clusters, ctas, inflight = b.launch_shape()       # 7 problems on an empty device: one cluster of 8 CTAs each
+    assert (clusters, ctas, inflight) == (7, 8, 1)
+    monkeypatch.setenv("EDSGPU_CLUSTER", "2"); monkeypatch.setenv("EDSGPU_INFLIGHT", "2")
+    b2 = edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * n, fr, 0)
+    assert b2.launch_shape() == (4, 2, 2)
+    b.close(); b2.close()
+    for t in trs:
+        t.close()
     for csize in (1, 2, 4, 8):
         for inflight in (1, 2, 3, 4):
             if inflight > csize:
