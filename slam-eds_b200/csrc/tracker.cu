@@ -1325,6 +1325,48 @@ __device__ float select_kth(F f, int n, int k, unsigned* hist /*256*/, unsigned*
     return key2f(prefix);
 }
 
+// Same selection with the values held in registers (n <= PER_THREAD * blockDim.x): the residuals are read once
+// for both selections instead of once per radix pass.
+constexpr int MAD_PER_THREAD = 16;
+template <typename F>
+__device__ float select_kth_reg(const float* vals, int cnt, F f, int k, unsigned* hist, unsigned* bcast) {
+    unsigned prefix = 0, mask = 0;
+    int kk = k;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < MAD_PER_THREAD; ++q) {
+            if (q < cnt) {
+                const unsigned key = f2key(f(vals[q]));
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned local[8], sum = 0;
+            for (int j = 0; j < 8; ++j) { local[j] = hist[threadIdx.x * 8 + j]; sum += local[j]; }
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+            unsigned excl = incl - sum;
+            if ((unsigned)kk >= excl && (unsigned)kk < incl) {
+                unsigned run = excl;
+                for (int j = 0; j < 8; ++j) {
+                    if ((unsigned)kk < run + local[j]) { bcast[0] = threadIdx.x * 8 + j; bcast[1] = run; break; }
+                    run += local[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= bcast[0] << shift;
+        mask |= 255u << shift;
+        kk -= (int)bcast[1];
+        __syncthreads();
+    }
+    return key2f(prefix);
+}
+
 __global__ void __launch_bounds__(MAD_THREADS) mad_kernel(const ProblemDesc* __restrict__ problems) {
     const ProblemDesc& P = problems[blockIdx.x];
     __shared__ unsigned hist[256];
@@ -1334,8 +1376,20 @@ __global__ void __launch_bounds__(MAD_THREADS) mad_kernel(const ProblemDesc* __r
     if (!P.info->usable) return;  // Tracker.cpp:217: only after a usable solve
     const int n = P.kf.N;
     const float* r = P.residuals;
-    if (P.loss_param_method == EDSGPU_LOSS_PARAM_MAD) {
-        // n_quantile_vector(v, size/2) == element size/2 of the sorted vector (Utils.hpp:315-320)
+    if (P.loss_param_method == EDSGPU_LOSS_PARAM_MAD && n <= MAD_PER_THREAD * MAD_THREADS) {
+        // n_quantile_vector(v, size/2) == element size/2 of the sorted vector (Utils.hpp:315-320); residuals in registers
+        float vals[MAD_PER_THREAD];
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < MAD_PER_THREAD; ++q) {
+            const int i = threadIdx.x + q * MAD_THREADS;
+            vals[q] = (i < n) ? r[i] : 0.f;
+            cnt += (i < n) ? 1 : 0;
+        }
+        const float med = select_kth_reg(vals, cnt, [](float v) { return v; }, n / 2, hist, bcast);
+        const float mad = select_kth_reg(vals, cnt, [med](float v) { return fabsf(v - med); }, n / 2, hist, bcast);
+        if (threadIdx.x == 0) P.state[13] = 1.345 * (1.4826 * (double)mad);
+    } else if (P.loss_param_method == EDSGPU_LOSS_PARAM_MAD) {
         const float med = select_kth([r](int i) { return r[i]; }, n, n / 2, hist, bcast);
         const float mad = select_kth([r, med](int i) { return fabsf(r[i] - med); }, n, n / 2, hist, bcast);
         if (threadIdx.x == 0) P.state[13] = 1.345 * (1.4826 * (double)mad);
