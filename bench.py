@@ -179,7 +179,7 @@ def bench_ba(ctx, stream, reps=50):
     import torch
     import edsgpu
     from edsgpu import synth_ba
-    from oracle import oracle as O
+    from oracle import oracle as O  # CPU baseline leg of this side line only: the timed CPU port, never on the GPU path
     pb = synth_ba.make_ba_problem()
     F, P, R = pb["F"], pb["P"], pb["R"]
     rtz = np.zeros((R, 8), np.float32)
@@ -261,7 +261,7 @@ def bench_coarse(ctx, stream, reps=200):
     (that is how trackNewestCoarse uses it: every evaluation is followed by an 8x8 solve on the host)."""
     import edsgpu
     from edsgpu import synth_coarse
-    from oracle import oracle as O
+    from oracle import oracle as O  # CPU baseline leg of this side line only
     pb = synth_coarse.make_coarse_problem()
     ct = edsgpu.CoarseTracker(ctx, len(pb["levels"]))
     for lvl, L in enumerate(pb["levels"]):
@@ -306,7 +306,7 @@ def bench_depth(ctx, stream, n=10240, reps=100):
     """SURVEY.md 8(f) rank 4: DepthPoints::update for the key frame's points (config 2: 10 240 points), host
     coordinates in, state resident on the device; wall clock of the host-synchronous call."""
     import edsgpu
-    from oracle import oracle as O
+    from oracle import oracle as O  # CPU baseline leg of this side line only
     rng = np.random.default_rng(0)
     fx = fy = 520.0
     cx, cy = 320.0, 240.0
