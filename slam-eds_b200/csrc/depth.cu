@@ -201,6 +201,7 @@ edsgpu_status edsgpu_depth_points_update(edsgpu_depth_points* d, const double T_
     DeviceGuard g(ctx->device);
     const size_t n = (size_t)d->N;
     EDS_CUDA(ctx, cudaMemcpyAsync(d->coords, kf_coord, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    d->kf_coord_set = true;
     EDS_CUDA(ctx, cudaMemcpyAsync(d->coords + 2 * n, ef_coord, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     DepthArgs a{};
     a.N = d->N; a.tracks = coords_are_tracks ? 1 : 0;

@@ -9,6 +9,7 @@ struct edsgpu_depth_points {
     double* state = nullptr;   // [N][4]
     double* coords = nullptr;  // [2][N][2] staging: kf, ef
     unsigned char* ok = nullptr;
+    bool kf_coord_set = false;  // coords[0..2N) holds KeyFrame::coord
 };
 
 // DepthPoints::update with the pose taken from a tracker's 14-double state on the device and the event-frame

@@ -2033,7 +2033,9 @@ edsgpu_status edsgpu_depth_points_update_from_tracker(edsgpu_depth_points* dp, e
     if (kf_coord) {  // KeyFrame::coord, once per key frame
         EDS_CUDA(ctx, cudaMemcpyAsync(dp->coords, kf_coord, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, ctx->stream));
         EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        dp->kf_coord_set = true;
     }
+    EDS_REQUIRE(ctx, dp->kf_coord_set, "depth_points_update_from_tracker: the key-frame coordinates were never given");
     edsgpu_status st = edsgpu_tracker_get_coord(tr, kf, dp, nullptr, nullptr);
     if (st == EDSGPU_OK) st = edsgpu_depth_update_tracked(dp, tr->state, dp->coords, dp->coords + 2 * N);
     if (st == EDSGPU_OK && refresh_keyframe) st = edsgpu_keyframe_refresh_idepth(kf, dp);

@@ -61,6 +61,8 @@ def test_tracking_loop_with_the_depth_filter_stays_on_the_device(gpu_ctx):
     st = np.stack([idp0, np.full(N, 25.0 / 36.0), np.full(N, 10.0), np.full(N, 10.0)], 1)
     kf_cpu = dict(kf); kf_cpu["idp"] = idp0.copy()
     px_ang = np.arctan(3.0 / (2 * kf["fx"])) + np.arctan(3.0 / (2 * kf["fy"]))
+    with pytest.raises(edsgpu.EdsGpuError):
+        dp.update_from_tracker(tr, kfd, None)            # KeyFrame::coord was never given
     for k, w in enumerate(wins):
         ef.create(w["x"], w["y"], w["pol"], w["ts"])
         r = tr.optimize(kfd, ef.frames, 0)
