@@ -912,6 +912,7 @@ struct edsgpu_ba {
     float calib[4] = {0, 0, 0, 0};
     bool lin_inputs_set = false;
     unsigned images_set = 0;  // bit per frame
+    bool have_top[2] = {false, false}, have_sc = false;  // which accumulations of the current linearisation are on the device
     std::vector<double> adHost_h, adTarget_h;  // host copies for xAd of the back-substitution
     void* post_block = nullptr;                // xAd (F*F*8 floats), cstep (4), step (P), energy partials
 };
@@ -1058,6 +1059,7 @@ edsgpu_status edsgpu_ba_set_residuals(edsgpu_ba* w, const float* recs, const uin
     edsgpu_ctx* ctx = w->ctx;
     EDS_REQUIRE(ctx, recs && flags, "ba_set_residuals: null array");
     DeviceGuard g(ctx->device);
+    w->have_top[0] = w->have_top[1] = w->have_sc = false;
     EDS_CUDA(ctx, cudaMemcpyAsync(w->recs, recs, 4 * (size_t)REC * w->R, cudaMemcpyHostToDevice, ctx->stream));
     EDS_CUDA(ctx, cudaMemcpyAsync(w->flags, flags, (size_t)w->R, cudaMemcpyHostToDevice, ctx->stream));
     if (res_toZero) EDS_CUDA(ctx, cudaMemcpyAsync(w->res_toZero, res_toZero, 32 * (size_t)w->R, cudaMemcpyHostToDevice, ctx->stream));
@@ -1101,6 +1103,7 @@ edsgpu_status edsgpu_ba_top_accumulate(edsgpu_ba* w, int mode, double* acc_out, 
     EDS_REQUIRE(ctx, mode >= 0 && mode <= 2, "ba_top_accumulate: mode must be 0 (active), 1 (linearized) or 2 (marginalize)");
     DeviceGuard g(ctx->device);
     const int slot = mode == 0 ? 0 : 1;
+    w->have_top[slot] = true;
     const BaDev d = ba_dev(w);
     const size_t stage_bytes = (size_t)TOP_STAGE * REC * sizeof(float);
     if (mode == 0) {
@@ -1169,6 +1172,8 @@ edsgpu_status edsgpu_ba_sc_accumulate(edsgpu_ba* w, int shift_prior_to_zero, dou
     if (!w) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = w->ctx;
     DeviceGuard g(ctx->device);
+    EDS_REQUIRE(ctx, w->have_top[0] && w->have_top[1], "ba_sc_accumulate: run top_accumulate for the active and the linearized residuals first");
+    w->have_sc = true;
     ScDev s{};
     s.F = w->F; s.P = w->P; s.shift_prior = shift_prior_to_zero;
     s.res_begin = w->res_begin; s.target_idx = w->target_idx; s.pt_perm = w->pt_perm; s.chunk_host = w->chunk_host;
@@ -1294,6 +1299,7 @@ edsgpu_status edsgpu_ba_linearize(edsgpu_ba* w, const uint8_t* state_in, const u
     if (state_in) EDS_CUDA(ctx, cudaMemcpyAsync(w->state_in, state_in, (size_t)w->R, cudaMemcpyHostToDevice, s));
     if (linearized) EDS_CUDA(ctx, cudaMemcpyAsync(w->linearized, linearized, (size_t)w->R, cudaMemcpyHostToDevice, s));
     if (res_toZero) EDS_CUDA(ctx, cudaMemcpyAsync(w->res_toZero, res_toZero, 32 * (size_t)w->R, cudaMemcpyHostToDevice, s));
+    w->have_top[0] = w->have_top[1] = w->have_sc = false;
     LinDev d{};
     d.F = w->F; d.P = w->P; d.R = w->R; d.H = w->H; d.W = w->W;
     d.images = w->images; d.precalc = w->precalc;
@@ -1345,6 +1351,7 @@ edsgpu_status edsgpu_ba_resubstitute(edsgpu_ba* w, const double* x, float* point
     EDS_REQUIRE(ctx, x != nullptr, "ba_resubstitute: null x");
     const size_t F = w->F, F2 = F * F;
     EDS_REQUIRE(ctx, w->adHost_h.size() == 64 * F2 && w->adTarget_h.size() == 64 * F2, "ba_resubstitute: call edsgpu_ba_set_frames with the adjoints first");
+    EDS_REQUIRE(ctx, w->have_top[0] && w->have_top[1] && w->have_sc, "ba_resubstitute: needs top_accumulate(0), top_accumulate(1) and sc_accumulate of this linearisation");
     DeviceGuard g(ctx->device);
     edsgpu_status st = ensure_post_block(w);
     if (st == EDSGPU_OK) st = edsgpu_ensure_pinned(ctx, 4 * (8 * F2 + 4));

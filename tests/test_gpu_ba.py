@@ -215,6 +215,14 @@ def test_linearize_needs_its_inputs(gpu_ctx):
     w = edsgpu.BaWindow(gpu_ctx, pb["F"], pb["host_idx"], pb["target_idx"], pb["res_begin"])
     with pytest.raises(edsgpu.EdsGpuError):
         w.linearize()
+    # the steps after the solve need the accumulations of the current linearisation
+    w.set_residuals(pb["recs"], pb["flags"], np.zeros((pb["R"], 8), np.float32))
+    w.set_points(pb["deltaF"], pb["priorF"])
+    w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.sc_accumulate(True)
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.resubstitute(np.zeros(4 + 8 * pb["F"]))
     w.set_linearize_inputs(pb["precalc"], pb["calib"], pb["frame_energy_th"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"],
                            pb["color"], pb["weights"])
     with pytest.raises(edsgpu.EdsGpuError):
