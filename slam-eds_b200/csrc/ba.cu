@@ -1074,6 +1074,7 @@ edsgpu_status edsgpu_ba_set_points(edsgpu_ba* w, const float* deltaF, const floa
     if (!w) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = w->ctx;
     DeviceGuard g(ctx->device);
+    w->have_top[1] = w->have_sc = false;  // deltaF feeds the re-linearisation of mode 1, deltaF / priorF the Schur terms
     if (deltaF) EDS_CUDA(ctx, cudaMemcpyAsync(w->deltaF, deltaF, 4 * (size_t)w->P, cudaMemcpyHostToDevice, ctx->stream));
     else EDS_CUDA(ctx, cudaMemsetAsync(w->deltaF, 0, 4 * (size_t)w->P, ctx->stream));
     if (priorF) EDS_CUDA(ctx, cudaMemcpyAsync(w->priorF, priorF, 4 * (size_t)w->P, cudaMemcpyHostToDevice, ctx->stream));
@@ -1087,6 +1088,7 @@ edsgpu_status edsgpu_ba_set_frames(edsgpu_ba* w, const float* adHTdeltaF, const 
     edsgpu_ctx* ctx = w->ctx;
     DeviceGuard g(ctx->device);
     const size_t F2 = (size_t)w->F * w->F;
+    if (adHTdeltaF || cDeltaF) w->have_top[1] = w->have_sc = false;  // inputs of the mode-1 re-linearisation
     if (adHTdeltaF) EDS_CUDA(ctx, cudaMemcpyAsync(w->adHTdeltaF, adHTdeltaF, 32 * F2, cudaMemcpyHostToDevice, ctx->stream));
     if (cDeltaF) EDS_CUDA(ctx, cudaMemcpyAsync(w->cDeltaF, cDeltaF, 16, cudaMemcpyHostToDevice, ctx->stream));
     if (adHost) EDS_CUDA(ctx, cudaMemcpyAsync(w->adHost, adHost, 512 * F2, cudaMemcpyHostToDevice, ctx->stream));
@@ -1103,7 +1105,10 @@ edsgpu_status edsgpu_ba_top_accumulate(edsgpu_ba* w, int mode, double* acc_out, 
     EDS_REQUIRE(ctx, mode >= 0 && mode <= 2, "ba_top_accumulate: mode must be 0 (active), 1 (linearized) or 2 (marginalize)");
     DeviceGuard g(ctx->device);
     const int slot = mode == 0 ? 0 : 1;
-    w->have_top[slot] = true;
+    // a new accumulation of either side makes the Schur terms that were built from the old one stale
+    w->have_top[slot] = false;
+    w->have_sc = false;
+    if (mode == 2) w->have_top[0] = false;
     const BaDev d = ba_dev(w);
     const size_t stage_bytes = (size_t)TOP_STAGE * REC * sizeof(float);
     if (mode == 0) {
@@ -1126,6 +1131,11 @@ edsgpu_status edsgpu_ba_top_accumulate(edsgpu_ba* w, int mode, double* acc_out, 
         EDS_CUDA(ctx, cudaMemsetAsync(w->bd[0], 0, 4 * (size_t)w->P, ctx->stream));
         EDS_CUDA(ctx, cudaMemsetAsync(w->Hcd[0], 0, 16 * (size_t)w->P, ctx->stream));
     }
+    // set only once everything above was queued without error.  addPoint<2> defines BOTH point-term sides (the
+    // linearized one and, as zeros, the active one), so marginalizePointsF's sequence addPoint<2> -> SC addPoint
+    // (EnergyFunctional.cpp:538-560) needs no separate active pass.
+    w->have_top[slot] = true;
+    if (mode == 2) w->have_top[0] = true;
     if (acc_out || Hdd_out || bd_out || Hcd_out || nres_out) {
         const size_t F2 = (size_t)w->F * w->F;
         edsgpu_status st = edsgpu_ensure_pinned(ctx, 8 * F2);
@@ -1173,7 +1183,7 @@ edsgpu_status edsgpu_ba_sc_accumulate(edsgpu_ba* w, int shift_prior_to_zero, dou
     edsgpu_ctx* ctx = w->ctx;
     DeviceGuard g(ctx->device);
     EDS_REQUIRE(ctx, w->have_top[0] && w->have_top[1], "ba_sc_accumulate: run top_accumulate for the active and the linearized residuals first");
-    w->have_sc = true;
+    w->have_sc = false;
     ScDev s{};
     s.F = w->F; s.P = w->P; s.shift_prior = shift_prior_to_zero;
     s.res_begin = w->res_begin; s.target_idx = w->target_idx; s.pt_perm = w->pt_perm; s.chunk_host = w->chunk_host;
@@ -1190,6 +1200,7 @@ edsgpu_status edsgpu_ba_sc_accumulate(edsgpu_ba* w, int shift_prior_to_zero, dou
     ba_sc_hcc_kernel<<<1, 32, 0, ctx->stream>>>(w->F, w->hcc_host, w->accHcc, w->accbc);
     ctx->launches += 3;
     EDS_CUDA(ctx, cudaGetLastError());
+    w->have_sc = true;
     if (accD || accE || accEB || accHcc || accbc || HdiF_out || bdSum_out) {
         edsgpu_status st;
         if ((st = d2h(ctx, accD, w->accD, 8 * 64 * F2 * w->F)) != EDSGPU_OK) return st;
@@ -1404,6 +1415,7 @@ edsgpu_status edsgpu_ba_fix_linearization(edsgpu_ba* w, const uint8_t* select, f
                                                                             w->deltaF, w->adHTdeltaF, w->cDeltaF, d_select, w->res_toZero, w->flags);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
+    w->have_top[0] = w->have_top[1] = w->have_sc = false;  // flags (isLinearized) and res_toZero changed under every accumulation
     if (res_toZero_out) EDS_CUDA(ctx, cudaMemcpyAsync(res_toZero_out, w->res_toZero, 32 * (size_t)w->R, cudaMemcpyDeviceToHost, ctx->stream));
     if (select || res_toZero_out) EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EDSGPU_OK;

@@ -532,98 +532,73 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
     if constexpr (!RES_ONLY) {
         if (role.pidx >= 0) {
             // ---------------- producer ----------------
-            // This warp's batches of the visit, across the CTA's blocks: batches are dealt by their running
-            // number (uneven shares even out over consecutive blocks and visits).  Two-stage software
-            // pipeline: the fp64 geometry of the NEXT batch is computed while the texture gathers of the
-            // current one are in flight; the per-batch dependent latency is what bounds the sweep.
+            // The CTA's batches of this visit are numbered t = 0 .. nb_tot-1 across its blocks (every block has
+            // nb_reg batches except the problem's last one, which takes the remainder and belongs to one CTA as its
+            // last block); batch t lives in ring slot (batch_counter + t) mod n_slots.  Warp p takes the batches
+            // t = t0 + k n_prod, t0 chosen from the running number so that uneven shares even out over visits.
+            // A batch is located from t alone (one multiply-high), so the three pipeline stages need no cursor state:
+            //   A(k+2)  3-D points of the batch after next: loads in flight
+            //   B(k+1)  fp64 geometry of the next batch, then its four texture gathers + gradient record in flight
+            //   C(k)    finish the current batch (its gathers were issued a whole iteration ago) and hand it over
             const int B = kf.B;
             constexpr int n_prod = CTA_PROD;
-            // every block has `ne` points except the last one, which also takes the remainder (Tracker.cpp:178-190)
-            const int n_last = kf.N - (B - 1) * ne;
+            const int n_last = kf.N - (B - 1) * ne;  // Tracker.cpp:178-190
             const int nb_reg = (ne + 31) >> 5, nb_last = (n_last + 31) >> 5;
-            // iterator over this warp's batches: block b, batch j of nbb in it (n_pts points), ring slot and phase
-            struct Cursor { int b, j, nbb, n_pts; unsigned slot, phase; };
-            auto enter = [&](Cursor& c) {  // move to the block that holds batch j (rare: once per block)
-                while (c.b < B && c.j >= c.nbb) {
-                    c.j -= c.nbb;
-                    c.b += csize;
-                    c.nbb = (c.b + 1 == B) ? nb_last : nb_reg;
-                    c.n_pts = (c.b + 1 == B) ? n_last : ne;
-                }
+            const int n_blk = (B - rank + csize - 1) / csize;
+            const bool has_last = ((B - 1 - rank) % csize) == 0;
+            const int nb_tot = n_blk * nb_reg + (has_last ? nb_last - nb_reg : 0);
+            // floor(t / nb_reg) = umulhi(t, ceil(2^32 / nb_reg)), exact while t nb_reg < 2^32 (keyframe_create: N <= 2^20);
+            // nb_reg = 1 has no 32-bit magic number: the quotient is t itself
+            const unsigned magic = nb_reg > 1 ? 0xFFFFFFFFu / (unsigned)nb_reg + 1u : 0u;
+            auto locate = [&](int t, int& idx, int& b) -> bool {
+                const int bl = min(nb_reg > 1 ? (int)__umulhi((unsigned)t, magic) : t, n_blk - 1);
+                b = rank + bl * csize;
+                const int i = ((t - bl * nb_reg) << 5) + lane;
+                idx = b * ne + i;
+                return (t < nb_tot) && (i < ((b + 1 == B) ? n_last : ne));
             };
-            auto advance = [&](Cursor& c) {  // consecutive batches of a warp are n_prod apart in the running numbering
-                c.j += n_prod;
-                c.slot += (unsigned)n_prod;
-                if (c.slot >= n_slots) { c.slot -= n_slots; c.phase ^= 1u; }
-                if (c.j >= c.nbb) enter(c);
-            };
-            Cursor cur;
-            cur.b = rank;
-            cur.j = (role.pidx + n_prod - (int)(batch_counter % (unsigned)n_prod)) % n_prod;
-            cur.nbb = (rank + 1 == B) ? nb_last : nb_reg;
-            cur.n_pts = (rank + 1 == B) ? n_last : ne;
-            {
-                const unsigned g0 = batch_counter + (unsigned)cur.j;
-                cur.slot = g0 % n_slots;
-                cur.phase = (g0 / n_slots) & 1u;
-            }
-            enter(cur);
-            // pipeline state: `cur` has its geometry, `nxt` has its 3-D points loaded (two batches of loads in
-            // flight hide the L2 latency), the batch after `nxt` is loaded inside the loop
+            struct Stage { Taps T; float4 g4; float2 dw; PointGeo G; int idx, b; bool valid; };
             const PointGeo G0 = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const Kp kp0 = {0.0, 0.0, 1.0};
-            auto locate = [&](const Cursor& c, int& idx, bool& valid) {
-                const int i = (c.j << 5) + lane;
-                valid = (c.b < B) && (i < c.n_pts);
-                idx = c.b * ne + i;
+            // stage B: geometry + gathers in flight
+            auto stage_b = [&](Stage& s, const Kp& kp) {
+                s.G = G0;
+                s.g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                s.dw = make_float2(0.f, 0.f);
+                if (s.valid) {
+                    point_geometry(kf, ec, kp, s.G);
+                    s.g4 = __ldg(&kf.gxy[s.idx]);
+                    s.dw = __ldg(&kf.dw[s.idx]);
+                }
+                s.T = fetch_taps(frame, s.G.col, s.G.row);
             };
-            PointGeo G = G0;
-            bool valid, valid2;
-            int idx, idx2;
-            locate(cur, idx, valid);
-            if (valid) point_geometry(kf, ec, load_kp(kf, idx), G);
-            Cursor nxt = cur;
-            if (cur.b < B) advance(nxt);
-            locate(nxt, idx2, valid2);
-            Kp kp2 = kp0;
-            if (valid2) kp2 = load_kp(kf, idx2);
-            while (cur.b < B) {
-                // current batch: taps and gradient record in flight
-                const Taps T = fetch_taps(frame, G.col, G.row);
-                float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                float2 dw = make_float2(0.f, 0.f);
-                if (valid) { g4 = __ldg(&kf.gxy[idx]); dw = __ldg(&kf.dw[idx]); }
-                // batch after next: 3-D points in flight
-                Cursor nn = nxt;
-                if (nxt.b < B) advance(nn);
-                int idx3;
-                bool valid3;
-                locate(nn, idx3, valid3);
-                Kp kp3 = kp0;
-                if (valid3) kp3 = load_kp(kf, idx3);
-                // next batch: geometry from the points loaded one iteration ago
-                PointGeo G2 = G0;
-                if (valid2) point_geometry(kf, ec, kp2, G2);
-                // current batch: finish and hand over
+            int t = (role.pidx + n_prod - (int)(batch_counter % (unsigned)n_prod)) % n_prod;
+            unsigned slot, phase;
+            {
+                const unsigned g0 = batch_counter + (unsigned)t;
+                slot = g0 % n_slots;
+                phase = (g0 / n_slots) & 1u;
+            }
+            // stage C: finish + hand over
+            auto stage_c = [&](const Stage& s) {
                 float J[12], r = 0.f;
-                if (valid) {
-                    point_finish<true>(kf, ec, ec.blk[cur.b], inv_norm, G, T, g4, dw, J, r);
+                if (s.valid) {
+                    point_finish<true>(kf, ec, ec.blk[s.b], inv_norm, s.G, s.T, s.g4, s.dw, J, r);
                     if (write_residuals) {
-                        P.residuals[idx] = r;
+                        P.residuals[s.idx] = r;
                         if (P.jac_out) {
 #pragma unroll
-                            for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * idx + k] = J[k];
+                            for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * s.idx + k] = J[k];
                         }
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 12; ++k) J[k] = 0.f;
                 }
-                const unsigned slot = cur.slot;
 #ifdef EDS_TIMING
                 const long long te0 = clock64();
 #endif
-                mbar_wait(&sh.empty_bar[slot], cur.phase ^ 1u, 1);
+                mbar_wait(&sh.empty_bar[slot], phase ^ 1u, 1);
 #ifdef EDS_TIMING
                 if (lane == 0 && rank == csize - 1) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
 #endif
@@ -634,8 +609,36 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                 dst[3] = make_float4(r, 0.f, 0.f, 0.f);
                 __syncwarp();  // all 32 rows are written: one elected arrival publishes the slot
                 if (lane == 0) mbar_arrive(&sh.full_bar[slot]);
-                cur = nxt; G = G2; valid = valid2; idx = idx2;
-                nxt = nn; kp2 = kp3; valid2 = valid3; idx2 = idx3;
+                slot += (unsigned)n_prod;
+                if (slot >= n_slots) { slot -= n_slots; phase ^= 1u; }
+            };
+            // one pipeline step: `cur` holds batch t with its gathers in flight, `nxt` receives batch t + n_prod,
+            // kp holds the 3-D points of batch t + n_prod and is refilled with those of batch t + 2 n_prod
+            auto step = [&](Stage& cur, Stage& nxt, Kp& kp) {
+                const Kp kpb = kp;
+                int idx_a, b_a;
+                const bool valid_a = locate(t + 2 * n_prod, idx_a, b_a);
+                kp = kp0;
+                if (valid_a) kp = load_kp(kf, idx_a);
+                stage_b(nxt, kpb);
+                stage_c(cur);
+                // the batch after next becomes the next one
+                cur.idx = idx_a; cur.b = b_a; cur.valid = valid_a;
+                t += n_prod;
+            };
+            if (t < nb_tot) {
+                Stage s0, s1;
+                Kp kp;
+                s0.valid = locate(t, s0.idx, s0.b);
+                stage_b(s0, s0.valid ? load_kp(kf, s0.idx) : kp0);
+                s1.valid = locate(t + n_prod, s1.idx, s1.b);
+                kp = s1.valid ? load_kp(kf, s1.idx) : kp0;
+                for (;;) {
+                    step(s0, s1, kp);  // finishes s0, fills s1; s0's (idx, b, valid) now describe batch t + n_prod
+                    if (t >= nb_tot) break;
+                    step(s1, s0, kp);
+                    if (t >= nb_tot) break;
+                }
             }
             for (int bb = rank; bb < B; bb += csize) {  // the counters advance as they do for the consumers
                 batch_counter += (unsigned)((bb + 1 == B) ? nb_last : nb_reg);
@@ -1518,6 +1521,7 @@ struct edsgpu_tracker {
     edsgpu_tracker_info* info = nullptr; // device
     float* residuals = nullptr;         // device: kf->residuals of the last optimize (Tracker.cpp:223-230)
     int res_capacity = 0;
+    uint64_t res_generation = 0;        // bumped when `residuals` is reallocated: batches holding the old pointer re-patch themselves
     // one-problem batch cached for repeated optimize() calls against the same keyframe / frame slot
     struct edsgpu_batch* cached = nullptr;
     uint64_t cached_kf = 0, cached_frames = 0;
@@ -1534,6 +1538,8 @@ struct edsgpu_batch {
     int first_slot = 0;
     ProblemDesc* desc = nullptr;  // device
     std::vector<edsgpu_tracker*> trackers;
+    std::vector<const edsgpu_keyframe*> keyframes;  // must outlive the batch (the descriptors hold their device arrays)
+    std::vector<uint64_t> res_generation;           // trackers[i]->res_generation the descriptors were made with
 };
 
 namespace {
@@ -1634,6 +1640,21 @@ ProblemDesc make_desc(const edsgpu_tracker* tr, const edsgpu_keyframe* kf, const
     return d;
 }
 
+// (re)build the device descriptors of a batch from its trackers' current buffers
+edsgpu_status upload_descriptors(edsgpu_batch* b) {
+    edsgpu_ctx* ctx = b->ctx;
+    std::vector<ProblemDesc> hd(b->count);
+    b->res_generation.resize(b->count);
+    for (int i = 0; i < b->count; ++i) {
+        EDS_REQUIRE(ctx, b->trackers[i]->res_capacity >= b->keyframes[i]->dev.N, "batch: a tracker's residual buffer is smaller than its key frame");
+        hd[i] = make_desc(b->trackers[i], b->keyframes[i], b->frames, b->first_slot + i);
+        b->res_generation[i] = b->trackers[i]->res_generation;
+    }
+    EDS_CUDA(ctx, cudaMemcpyAsync(b->desc, hd.data(), sizeof(ProblemDesc) * (size_t)b->count, cudaMemcpyHostToDevice, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // hd is a stack-owned source
+    return EDSGPU_OK;
+}
+
 edsgpu_status check_pair(edsgpu_ctx* ctx, const edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot) {
     EDS_REQUIRE(ctx, tr && kf && frames, "tracker: null handle");
     EDS_REQUIRE(ctx, tr->ctx == ctx && kf->ctx == ctx && frames->ctx == ctx, "tracker: handles belong to different contexts");
@@ -1655,6 +1676,7 @@ edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const doub
     EDS_REQUIRE(ctx, height > 0 && width > 0, "keyframe_create: bad image size");
     EDS_REQUIRE(ctx, num_blocks >= 1 && num_blocks <= MAX_BLOCKS, "keyframe_create: num_blocks must be in [1,16]");
     EDS_REQUIRE(ctx, num_points >= num_blocks, "keyframe_create: fewer points than residual blocks");
+    EDS_REQUIRE(ctx, num_points <= (1 << 20), "keyframe_create: more than 2^20 points");
     DeviceGuard g(ctx->device);
     const size_t N = (size_t)num_points;
     edsgpu_keyframe* kf = new edsgpu_keyframe();
@@ -1801,6 +1823,7 @@ edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* tracke
             tr->res_capacity = 0;
             EDS_CUDA(ctx, cudaMalloc(&tr->residuals, sizeof(float) * (size_t)keyframes[i]->dev.N));
             tr->res_capacity = keyframes[i]->dev.N;
+            tr->res_generation++;  // older batches of this tracker hold the freed pointer: they re-patch before their next launch
         }
     }
     edsgpu_batch* b = new edsgpu_batch();
@@ -1810,12 +1833,11 @@ edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* tracke
     b->frames = frames;
     b->first_slot = first_slot;
     b->trackers.assign(trackers, trackers + count);
-    std::vector<ProblemDesc> hd(count);
-    for (int i = 0; i < count; ++i) hd[i] = make_desc(trackers[i], keyframes[i], frames, first_slot + i);
+    b->keyframes.assign(keyframes, keyframes + count);
     cudaError_t e = cudaMalloc(&b->desc, sizeof(ProblemDesc) * (size_t)count);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(b->desc, hd.data(), sizeof(ProblemDesc) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // hd is a stack-owned source
     if (e != cudaSuccess) { edsgpu_batch_destroy(b); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
+    edsgpu_status st = upload_descriptors(b);
+    if (st != EDSGPU_OK) { edsgpu_batch_destroy(b); return st; }
     *out = b;
     return EDSGPU_OK;
 }
@@ -1832,6 +1854,13 @@ edsgpu_status edsgpu_batch_optimize(edsgpu_batch* b) {
     if (!b) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = b->ctx;
     DeviceGuard g(ctx->device);
+    // a tracker of this batch was since paired with a larger key frame (its residual buffer moved): refresh the descriptors
+    for (int i = 0; i < b->count; ++i)
+        if (b->trackers[i]->res_generation != b->res_generation[i]) {
+            edsgpu_status stp = upload_descriptors(b);
+            if (stp != EDSGPU_OK) return stp;
+            break;
+        }
     // the event frames are built on their own stream: wait for the builds of our slots only
     edsgpu_status st = edsgpu_frames_wait_built(b->frames, b->first_slot, b->count, ctx->stream);
     if (st != EDSGPU_OK) return st;

@@ -112,6 +112,56 @@ def test_schur_complement(solved, shift):
     assert all(g["HdiF"][p] == 0 and g["bdSum"][p] == 0 for p in none[:50])
 
 
+def test_marginalisation_sequence_mode2_then_schur(solved):
+    """marginalizePointsF (EnergyFunctional.cpp:538-560): addPoint<2> followed by the Schur addPoint(p, false) with no
+    separate active pass -- mode 2 defines both point-term sides (the active one as zeros, AccumulatedTopHessian.cpp:152-157)."""
+    pb, rtz, w = solved
+    F = pb["F"]
+    w.set_residuals(pb["recs"], pb["flags"], rtz)  # resets every freshness flag
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.sc_accumulate(False)
+    w.top_accumulate(2, want_outputs=False)
+    g = w.sc_accumulate(False)
+    M = _oracle_top(pb, rtz, 2)
+    z1, z4 = np.zeros(pb["P"], np.float32), np.zeros((pb["P"], 4), np.float32)
+    o = O.ba_sc_accumulate(F, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], O.ba_jpjd(pb["recs"]), z1, M["Hdd"],
+                           z1, M["bd"], z4, M["Hcd"], pb["priorF"], pb["deltaF"], False, threads=4)
+    assert rel(g["HdiF"], o["HdiF"]) < TOL and rel(g["bdSum"], o["bdSum"]) < TOL
+    for name in ("accD", "accE", "accEB", "accHcc", "accbc"):
+        assert rel(g[name], o[name]) < TOL, name
+    Hg, bg = w.sc_stitch()
+    Ho, bo = O.ba_sc_stitch(F, o, SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    assert rel(Hg, Ho) < TOL and rel(bg, bo) < TOL
+
+
+def test_stale_accumulations_are_refused(solved):
+    """Whatever changes an input of an accumulation invalidates it: new deltas (mode 1 and the Schur terms), new frame
+    deltas, fixLinearizationF (flags and res_toZero), a newer top accumulation (the Schur terms were built from the old one)."""
+    pb, rtz, w = solved
+    x = np.zeros(4 + 8 * pb["F"])
+
+    def all_three():
+        w.top_accumulate(0, want_outputs=False); w.top_accumulate(1, want_outputs=False); w.sc_accumulate(True, want_outputs=False)
+
+    all_three(); w.resubstitute(x)
+    w.set_points(pb["deltaF"], pb["priorF"])
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.sc_accumulate(True)  # the linearized side is stale
+    all_three()
+    w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.resubstitute(x)
+    all_three()
+    w.top_accumulate(0, want_outputs=False)
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.resubstitute(x)  # Schur terms older than the active accumulation
+    all_three()
+    w.fix_linearization(np.zeros(pb["R"], np.uint8))
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.sc_accumulate(True)
+    w.set_residuals(pb["recs"], pb["flags"], rtz)
+
+
 @pytest.mark.parametrize("cfg", ["small", "config4"])
 def test_device_linearize_is_bit_exact_and_feeds_the_accumulators(gpu_ctx, cfg):
     """PointFrameResidual::linearize on the device (SURVEY 8f rank 1) against the float32 oracle: same
