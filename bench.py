@@ -511,7 +511,7 @@ def run_native(args):
                                    % (S, N, E, NUM_BLOCKS, MAX_ITER),
                        "sequences_per_gpu": S, "l2": "per-step working set ~%d MB (event accumulators + frames + keyframes) > 126 MB L2, no explicit flush"
                                                    % int((S * H * W * 12 + S * E * 5 + n_sc * N * 48) / 1e6),
-                       "mean_lm_iterations": iters, "launch_shape": "%d clusters x %d CTAs of 512 threads, %d problems in flight per cluster" % banks[0].launch_shape(), "usable": "%d/%d" % (usable, S), "parallelism": "sequences sharded, %d rank(s)" % world},
+                       "mean_lm_iterations": iters, "launch_shape": "%d evaluator CTAs + %d leader CTAs of 512 threads, %d problems in flight" % banks[0].launch_shape(), "usable": "%d/%d" % (usable, S), "parallelism": "sequences sharded, %d rank(s)" % world},
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(S * E * 5), "d2h_bytes_per_step": int(S * 14 * 8),
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "how": "edsgpu_event_frame_create_batch (pinned host events) + edsgpu_batch_optimize + state read-back every step; "

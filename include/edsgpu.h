@@ -172,9 +172,10 @@ edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* tracke
                                   int count, const edsgpu_frames* frames, int first_slot, edsgpu_batch** out);
 void edsgpu_batch_destroy(edsgpu_batch* batch);
 edsgpu_status edsgpu_batch_optimize(edsgpu_batch* batch);
-/* How edsgpu_batch_optimize will launch: thread-block clusters, CTAs per cluster, problems a cluster keeps in
- * flight (chosen from the device's cluster occupancy when the batch is created; informational). */
-edsgpu_status edsgpu_batch_launch_shape(const edsgpu_batch* batch, int* clusters, int* ctas_per_cluster, int* problems_in_flight);
+/* How edsgpu_batch_optimize will launch: evaluator CTAs (they sweep residual blocks of any problem, taken from a
+ * global task queue), leader CTAs (one warp per problem runs its Levenberg-Marquardt loop) and the number of problems
+ * kept in flight at once (chosen when the batch is created; informational -- results do not depend on it). */
+edsgpu_status edsgpu_batch_launch_shape(const edsgpu_batch* batch, int* evaluator_ctas, int* leader_ctas, int* problems_in_flight);
 /* copies the count x 14 state records into one contiguous DEVICE buffer (e.g. the send buffer
  * of the caller's final NCCL all-gather); asynchronous on the context stream. */
 edsgpu_status edsgpu_batch_pack_states_dev(edsgpu_batch* batch, double* states_dev);

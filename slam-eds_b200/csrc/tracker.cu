@@ -4,28 +4,25 @@
 // functor PhotometricError (src/tracking/PhotometricError.hpp:56-214) and ceres::Solve
 // (un-vendored; trust-region LM restated from ceres-solver 1.14..2.1 semantics).
 //
-//   track_lm_kernel   thread-block CLUSTERS of 512-thread CTAs, one CTA per SM; a cluster keeps K <= 4
-//                     tracking problems in flight.  Residual blocks (Tracker.cpp:178-195) are dealt
-//                     round-robin to the CTAs of the cluster.  In every CTA producer warps evaluate
-//                     32 points at a time (division-free fp64-exact projection, bicubic window as
-//                     four texture gathers, analytic Jacobian in fp32; software-pipelined) into a
-//                     shared-memory ring guarded by mbarriers, consumer warps own the 90 fp32
-//                     outer-product accumulators, reduce a block with a halving warp butterfly,
-//                     apply the per-block loss (rho') and store 92 doubles into the shared memory
-//                     of the problem's leader CTA over DSMEM.  One leader warp per problem runs the
-//                     whole Levenberg-Marquardt state machine (Jacobi scaling, damping, register-
-//                     resident 12x12 Cholesky, retractions, accept/reject, tolerances) and publishes
-//                     the next evaluation point to the cluster.  Evaluators and leaders hand over
-//                     through ready/result mbarriers (no cluster-wide barrier in the loop), so the
-//                     serial LM step of one problem overlaps the sweeps of the others.  The LM loop
-//                     never returns to the host: one launch per batch of windows.
+//   track_lm_kernel   persistent dataflow over global memory, 512-thread CTAs, one per SM.  A few LEADER CTAs: each of
+//                     their warps runs the whole Levenberg-Marquardt state machine of one problem (Jacobi scaling,
+//                     damping, register-resident 12x12 Cholesky, retractions, accept/reject, tolerances) and turns
+//                     every evaluation into one task per residual block (Tracker.cpp:178-195) in a global queue.
+//                     All other CTAs are EVALUATORS: a control warp pops tasks (running ahead through a mailbox),
+//                     producer warps evaluate 32 points at a time (division-free fp64-exact projection, bicubic
+//                     window as four texture gathers, analytic Jacobian in fp32; software-pipelined) into a
+//                     shared-memory ring guarded by mbarriers, consumer warps own the 90 fp32 outer-product
+//                     accumulators, reduce the block with a halving warp butterfly, apply the per-block loss (rho')
+//                     and store 92 doubles into the problem's slot, then bump the counter its leader polls.  Any
+//                     evaluator serves any problem: every SM stays busy whatever the batch size, and the serial LM
+//                     step of one problem overlaps the sweeps of all the others.  The LM loop never returns to the
+//                     host: one launch per batch of windows.
 //   mad_kernel        next loss parameter (MAD / STD) from the written-back residuals
 //                     (Tracker.cpp:281-317) by radix select.
 //   kf_prepare_kernel keyframe upload: fp32 SoA gather streams, fp64 3-D points
 //                     (PhotometricError.hpp:94-105) and the per-block 6x6 model Gram matrix
 //                     A_b = sum g_i g_i^T (m_i = g_i . v is linear in v, so
 //                     ||m||^2 = v^T A_b v and sum m_i g_i = A_b v need no sweep).
-#include <cooperative_groups.h>
 #include <float.h>
 #include <stdlib.h>
 
@@ -33,39 +30,39 @@
 #include "depth.cuh"
 #include "frames.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace {
 
-constexpr int TRK_THREADS = 512;  // one CTA per SM: 13-14 producer warps, 2 consumer warps, (1 leader warp)
+constexpr int TRK_THREADS = 512;  // one CTA per SM
 constexpr int TRK_WARPS = TRK_THREADS / 32;
 constexpr int JLD = 20;         // floats per point row in shared memory (80 B: conflict-free 128-bit access)
 #ifndef EDS_N_CONS
 #define EDS_N_CONS 3
 #endif
-constexpr int N_CONS = EDS_N_CONS;           // consumer warps: own the outer-product accumulators (batches j = c mod N_CONS)
-constexpr int N_PROD = TRK_WARPS - N_CONS;   // producer warps (one fewer in a CTA that hosts a leader warp)
-constexpr int LEADER_WARP = TRK_WARPS - 1;
+constexpr int N_CONS = EDS_N_CONS;               // consumer warps: own the outer-product accumulators (batches j = c mod N_CONS)
+constexpr int CTRL_WARP = TRK_WARPS - 1;         // evaluator CTA: the warp that fetches tasks from the global queue
+constexpr int N_PROD = TRK_WARPS - 1 - N_CONS;   // producer warps of an evaluator CTA
+constexpr int N_EVAL_WARPS = TRK_WARPS - 1;      // producers + consumers
 #ifndef EDS_RING_DEPTH
 #define EDS_RING_DEPTH 3
 #endif
 constexpr int RING_DEPTH = EDS_RING_DEPTH;   // ring slots per producer warp (three absorb stragglers)
-// capacity of the ring of 32-point batches; a CTA uses RING_DEPTH slots per producer warp it actually has
-constexpr int N_SLOTS = RING_DEPTH * N_PROD;
+constexpr int N_SLOTS = RING_DEPTH * N_PROD; // ring of 32-point batches
 constexpr int NSLOT = 92;       // 78 + 12 + cost + block squared norm
 constexpr int MAX_BLOCKS = 16;  // residual blocks per problem (config.options.num_threads)
-constexpr int MAX_CLUSTER = 8;
-#ifndef EDS_MAX_K
-#define EDS_MAX_K 4
+#ifndef EDS_MAILBOX
+#define EDS_MAILBOX 2
 #endif
-constexpr int MAX_K = EDS_MAX_K;  // problems one cluster keeps in flight
+constexpr int MAILBOX = EDS_MAILBOX;       // tasks an evaluator CTA holds: the running one and the prefetched ones
+constexpr int LEAD_WARPS = TRK_WARPS;      // leader warps of a leader CTA, one problem in flight each
+constexpr int MAX_LEAD_CTAS = 8;
 constexpr double kEps = 1e-05;  // PhotometricError.hpp:200
 
-enum { CMD_EVAL = 1, CMD_FINAL = 2, CMD_DONE = 3 };
+enum { CMD_EVAL = 1, CMD_FINAL = 2, CMD_DONE = 3, CMD_EXIT = 4 };
 
 #ifdef EDS_TIMING
 __device__ unsigned long long g_timing[32];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define g_timing_cta ((int)gridDim.x - 1)  // the evaluator CTA whose warps report their clocks
 #endif
 enum { PHASE_INIT = 0, PHASE_CAND = 1 };
 
@@ -163,7 +160,7 @@ __host__ __device__ __forceinline__ int tri_index(int a, int b) {  // a <= b < 1
 }
 
 // ------------------------------------------------------------------------------------------
-// shared-memory layout of one CTA
+// dataflow state: global memory (leader <-> evaluators) and the shared memory of the two kinds of CTA
 // ------------------------------------------------------------------------------------------
 struct LmState {
     double x[13], cand[13], delta[12];
@@ -173,8 +170,7 @@ struct LmState {
     int reuse_diag, iter, n_succ, n_unsucc, consec_invalid, termination, phase, n_eval;
 };
 
-// Everything a CTA needs for one evaluation; written by the leader into every CTA of the
-// cluster (DSMEM) before sync (A).
+// Everything an evaluator needs for one evaluation; published by the problem's leader.
 struct EvalConst {
     double R[9], t[3];               // Eigen toRotationMatrix(q), translation
     float vf[6], inv_vs, inv_vn;     // velocity, 1/|v|^2, 1/|v|
@@ -182,23 +178,33 @@ struct EvalConst {
     int cmd;
 };
 
-// Per-problem state.  A cluster keeps up to MAX_K problems in flight (see track_lm_kernel): every CTA holds the
-// published constants of all of them, the CTA that hosts a problem's leader additionally its reduction slots and LM state.
-struct ProblemShared {
-    EvalConst ec;
-    double loss_a;
-    // leader CTA only
-    double slots[MAX_BLOCKS][NSLOT];  // one slot per residual block, filled over DSMEM
-    double sum[NSLOT];
-    double A[MAX_BLOCKS][21];         // per-block model Gram matrices
-    double x_eval[13];
-    LmState lm;
-    ProblemDesc P;
-    int valid;
+// One per problem of a batch, in global memory: what the leader publishes and what the evaluators report.
+struct ProblemWork {
+    EvalConst ec;                      // evaluation point of the tasks in the queue
+    double loss_a;                     // loss parameter of this solve (state[13] when the solve started)
+    double slots[MAX_BLOCKS][NSLOT];   // block sums of the current evaluation, one writer (evaluator CTA) per block
+    unsigned done;                     // +1 per finished EVAL task, +1 per evaluator warp of a finished FINAL task; never reset
+    unsigned pad_[3];
 };
 
-struct CtaShared {
-    ProblemShared prob[MAX_K];
+// Task queue shared by all CTAs of a launch.  head / tail / finished only ever grow (also across launches of the same batch):
+// ticket k lives in entries[k & mask] and is valid once its upper half equals k + 1.
+struct QueueCtl { unsigned head, tail, finished, pad_; };
+__device__ __forceinline__ unsigned pack_task(int problem, int block, int cmd) { return (unsigned)problem | ((unsigned)block << 20) | ((unsigned)cmd << 26); }
+
+// A task as the evaluator warps see it (copied out of global memory by the CTA's control warp).
+struct TaskShared {
+    EvalConst ec;
+    double loss_a;
+    ProblemDesc P;
+    double* slots;     // ProblemWork::slots of the problem
+    unsigned* done;    // ProblemWork::done
+    int block, cmd;
+};
+
+// shared memory of an evaluator CTA
+struct EvalShared {
+    TaskShared task[MAILBOX];
     // ring of 32-point batches of rows [J(12) r pad], guarded by full/empty mbarriers
     alignas(16) float ring[N_SLOTS][32][JLD];
     alignas(8) unsigned long long full_bar[N_SLOTS];
@@ -206,10 +212,37 @@ struct CtaShared {
     // block totals of consumer warps 1.., handed to consumer warp 0 (double-buffered by block)
     float cons_part[2][N_CONS - 1][96];
     double cons_s[2][N_CONS - 1];
-    // dataflow between the evaluator warps of all CTAs and the leader warp of each problem
-    alignas(8) unsigned long long ready_bar[MAX_K];   // every CTA: "evaluation constants of problem k have landed" (32 leader lanes)
-    alignas(8) unsigned long long result_bar[MAX_K];  // leader CTA of k: "every evaluator warp of the cluster is done with problem k"
+    // mailbox hand-over between the control warp and the evaluator warps
+    alignas(8) unsigned long long task_full[MAILBOX];   // control warp -> evaluators: task[slot] is complete (1 arrival)
+    alignas(8) unsigned long long task_empty[MAILBOX];  // evaluators -> control warp: every evaluator warp is done with task[slot]
 };
+
+// shared memory of a leader CTA: one problem in flight per warp
+struct LeaderProblem {
+    EvalConst ec;
+    double loss_a;
+    double sum[NSLOT];
+    double A[MAX_BLOCKS][21];  // per-block model Gram matrices
+    double x_eval[13];
+    LmState lm;
+    ProblemDesc P;
+};
+struct LeadShared { LeaderProblem prob[LEAD_WARPS]; };
+
+// ---- global-memory hand-over primitives -----------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // per-point residual + analytic tangent-space Jacobian
@@ -381,43 +414,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     } while (!ok);
 }
 
-// ---- cluster-scope variants: barrier in another CTA of the cluster, data written over DSMEM ----
-__device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned cta_rank) {
-    unsigned r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(unsigned long long* local_bar, unsigned cta_rank) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(local_bar), cta_rank)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(unsigned long long* local_bar, unsigned cta_rank) {  // after fence_cluster()
-    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(local_bar), cta_rank)) : "memory");
-}
-__device__ __forceinline__ void fence_cluster();
-__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, unsigned parity, int tag = 0) {
-    unsigned ok;
-#ifdef EDS_WATCHDOG
-    unsigned long long spins = 0;
-#endif
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
-            : "memory");
-#ifdef EDS_WATCHDOG
-        if (!ok && ++spins > 400000ull) {
-            if ((threadIdx.x & 31) == 0)
-                printf("[watchdog] block %d warp %d stuck in cluster wait %d, barrier offset %u, parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
-                       tag, smem_u32(bar), parity);
-            __nanosleep(100000000);
-            __trap();
-        }
-#endif
-    } while (!ok);
-}
-__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
-
 // halving butterfly: 2*HALF per-lane values -> HALF, lanes with bit OFFSET keep the upper half
 template <int HALF, int OFFSET>
 __device__ __forceinline__ void butterfly_step(float* a, unsigned lane) {
@@ -473,39 +469,32 @@ __device__ __forceinline__ int reduce96_base(unsigned lane) {
     return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
 }
 
-// One CTA evaluates the residual blocks dealt to it with the constants in sh.ec and stores, per
-// block, [rho' * JtJ (78) | rho' * Jtr (12) | 0.5 rho(s) | s] into slot_base[b] (leader smem, DSMEM).
+// One evaluator CTA evaluates ONE residual block (a task) with the constants in ts.ec and stores
+// [rho' * JtJ (78) | rho' * Jtr (12) | 0.5 rho(s) | s] into the problem's slot of that block (global memory).
 //
 // Warp-specialised: producer warps sweep the points 32 at a time (residual + analytic Jacobian row
 // -> shared-memory ring slot, mbarrier "full"), consumer warps own the outer-product accumulators
 // (90 fp32 registers per lane) and drain the ring (mbarrier "empty").  No CTA-wide barrier inside
-// the sweep; 512 threads at <= 128 registers per thread = one CTA per SM, whose 16 warps hide each other's stalls
-// (and the leader's serial LM step).  `batch_counter` numbers the batches of the whole kernel so that
-// both sides derive slot and phase parity without talking to each other.
-// Evaluator roles of one CTA: warps 0..N_PROD-2 produce, the next N_CONS warps consume, the last warp
-// is the dedicated LM leader warp in a CTA that hosts a problem's leader and one more producer elsewhere.
+// the sweep; 512 threads at <= 128 registers per thread = one CTA per SM.  `batch_counter` numbers the batches the CTA
+// has processed since the kernel started, so that both sides derive slot and phase parity without talking to each other;
+// it runs on across tasks: the producers may be a task ahead of the consumers.
 struct Roles {
-    int n_prod;      // producer warps of this CTA
     int pidx;        // producer index of this warp, -1 if not a producer
     int cidx;        // consumer index of this warp, -1 if not a consumer
-    int n_eval_threads;  // threads taking part in the evaluation
-    int etid;        // evaluator thread index
 };
-__device__ __forceinline__ Roles make_roles(bool hosts_leader) {
+__device__ __forceinline__ Roles make_roles() {
     const int warp = threadIdx.x >> 5;
     Roles r;
-    r.n_prod = hosts_leader ? N_PROD - 1 : N_PROD;
-    r.cidx = (warp >= N_PROD - 1 && warp < LEADER_WARP) ? warp - (N_PROD - 1) : -1;
     static_assert(N_CONS >= 2 && N_CONS <= 4, "consumer warps");
-    r.pidx = (warp < N_PROD - 1) ? warp : ((warp == LEADER_WARP && !hosts_leader) ? N_PROD - 1 : -1);
-    r.n_eval_threads = hosts_leader ? TRK_THREADS - 32 : TRK_THREADS;
-    r.etid = threadIdx.x;  // the leader warp is the last one: evaluator threads keep their index
+    r.pidx = warp < N_PROD ? warp : -1;
+    r.cidx = (warp >= N_PROD && warp < N_PROD + N_CONS) ? warp - N_PROD : -1;
     return r;
 }
 
-template <bool RES_ONLY, bool HOSTS_LEADER>
-__device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base /* [MAX_BLOCKS][NSLOT] on the leader */,
-                             int rank, int csize, const Roles& role, bool write_residuals, unsigned& batch_counter, unsigned& block_counter) {
+// returns (to every lane of consumer warp 0) the value of the task's completion counter before this task was added; 0 elsewhere
+template <bool RES_ONLY>
+__device__ unsigned cta_evaluate(TaskShared& ps, EvalShared& sh, const Roles& role, bool write_residuals, unsigned& batch_counter,
+                                 unsigned& block_counter) {
     const int tid = threadIdx.x, lane = tid & 31;
     const ProblemDesc& P = ps.P;
     const KfDev& kf = P.kf;
@@ -513,54 +502,55 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
     const float inv_norm = (float)P.norms[1];
     const double loss_a = ps.loss_a;
     const int ne = kf.ne;
-    // The ring of this CTA has a whole number of slots per producer warp, so that batch g and batch g + n_slots -- the
+    const int b = ps.block;
+    const float* bc = ec.blk[b];
+    const int start = b * ne;
+    const int n = ne + ((b + 1 == kf.B) ? (kf.N - (b + 1) * ne) : 0);  // the last block also takes the remainder, Tracker.cpp:178-190
+    const int nb = (n + 31) >> 5;                                      // batches of this block
+    // The ring has a whole number of slots per producer warp, so that batch g and batch g + n_slots -- the
     // successive occupants of a slot -- always belong to the SAME producer.  That warp passes through every
     // "empty" wait of its slots in order and can never be a whole lap ahead of the barrier's phase (with slots shared
     // between producers a fast warp could test a parity that is two phases stale and overwrite an unconsumed batch).
-    constexpr int CTA_PROD = HOSTS_LEADER ? N_PROD - 1 : N_PROD;  // compile-time: strides and wrap tests fold into immediates
-    constexpr unsigned n_slots = (unsigned)(CTA_PROD * (N_SLOTS / CTA_PROD));
-    // The mirror image on the "full" side: within a residual block the successive occupants of a slot must be drained by
-    // the SAME consumer warp (it takes its batches in order, so it cannot test a stale parity either); batch j goes to
-    // consumer j mod N_CONS, hence the ring size must be a multiple of N_CONS.  Across blocks the consumers' end-of-block
-    // barrier keeps them within one block of each other.
+    constexpr unsigned n_slots = (unsigned)N_SLOTS;
+    // The mirror image on the "full" side: the successive occupants of a slot must be drained by the SAME consumer warp
+    // (it takes its batches in order, so it cannot test a stale parity either); batch g goes to consumer g mod N_CONS,
+    // hence the ring size must be a multiple of N_CONS.
     static_assert(n_slots % N_CONS == 0, "ring slots per CTA must be a multiple of the consumer warps");
     // The texture handle is read from shared memory, which the compiler cannot prove warp-uniform: it
     // would wrap every fetch in a loop over the distinct handles of the warp.  A warp-wide OR leaves
     // the value unchanged and lands in a uniform register.
     const cudaTextureObject_t frame = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(P.frame >> 32)) << 32) |
                                       (unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)P.frame);
-    if constexpr (!RES_ONLY) {
+    if constexpr (RES_ONLY) {
+        // residual write-back only (Tracker.cpp:223-230): no Jacobian, no reduction
+        if (role.pidx >= 0 || role.cidx >= 0) {
+            for (int i = tid; i < n; i += 32 * N_EVAL_WARPS) {
+                float r;
+                eval_point<false>(kf, ec, bc, frame, inv_norm, start + i, nullptr, r);
+                P.residuals[start + i] = r;
+            }
+            // every evaluator warp reports on its own: the leader waits for N_EVAL_WARPS arrivals per block
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(ps.done, 1u);
+        }
+        return 0;
+    } else {
         if (role.pidx >= 0) {
             // ---------------- producer ----------------
-            // The CTA's batches of this visit are numbered t = 0 .. nb_tot-1 across its blocks (every block has
-            // nb_reg batches except the problem's last one, which takes the remainder and belongs to one CTA as its
-            // last block); batch t lives in ring slot (batch_counter + t) mod n_slots.  Warp p takes the batches
-            // t = t0 + k n_prod, t0 chosen from the running number so that uneven shares even out over visits.
-            // A batch is located from t alone (one multiply-high), so the three pipeline stages need no cursor state:
+            // Warp p takes the batches t = t0 + k N_PROD of the block, t0 chosen from the running number so that uneven
+            // shares even out over consecutive tasks.  Three pipeline stages per warp:
             //   A(k+2)  3-D points of the batch after next: loads in flight
             //   B(k+1)  fp64 geometry of the next batch, then its four texture gathers + gradient record in flight
             //   C(k)    finish the current batch (its gathers were issued a whole iteration ago) and hand it over
-            const int B = kf.B;
-            constexpr int n_prod = CTA_PROD;
-            const int n_last = kf.N - (B - 1) * ne;  // Tracker.cpp:178-190
-            const int nb_reg = (ne + 31) >> 5, nb_last = (n_last + 31) >> 5;
-            const int n_blk = (B - rank + csize - 1) / csize;
-            const bool has_last = ((B - 1 - rank) % csize) == 0;
-            const int nb_tot = n_blk * nb_reg + (has_last ? nb_last - nb_reg : 0);
-            // floor(t / nb_reg) = umulhi(t, ceil(2^32 / nb_reg)), exact while t nb_reg < 2^32 (keyframe_create: N <= 2^20);
-            // nb_reg = 1 has no 32-bit magic number: the quotient is t itself
-            const unsigned magic = nb_reg > 1 ? 0xFFFFFFFFu / (unsigned)nb_reg + 1u : 0u;
-            auto locate = [&](int t, int& idx, int& b) -> bool {
-                const int bl = min(nb_reg > 1 ? (int)__umulhi((unsigned)t, magic) : t, n_blk - 1);
-                b = rank + bl * csize;
-                const int i = ((t - bl * nb_reg) << 5) + lane;
-                idx = b * ne + i;
-                return (t < nb_tot) && (i < ((b + 1 == B) ? n_last : ne));
-            };
-            struct Stage { Taps T; float4 g4; float2 dw; PointGeo G; int idx, b; bool valid; };
+            struct Stage { Taps T; float4 g4; float2 dw; PointGeo G; int idx; bool valid; };
             const PointGeo G0 = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const Kp kp0 = {0.0, 0.0, 1.0};
-            // stage B: geometry + gathers in flight
+            auto locate = [&](int t, int& idx) -> bool {
+                const int i = (t << 5) + lane;
+                idx = start + i;
+                return (t < nb) && (i < n);
+            };
             auto stage_b = [&](Stage& s, const Kp& kp) {
                 s.G = G0;
                 s.g4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -572,18 +562,17 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                 }
                 s.T = fetch_taps(frame, s.G.col, s.G.row);
             };
-            int t = (role.pidx + n_prod - (int)(batch_counter % (unsigned)n_prod)) % n_prod;
+            int t = (role.pidx + N_PROD - (int)(batch_counter % (unsigned)N_PROD)) % N_PROD;
             unsigned slot, phase;
             {
                 const unsigned g0 = batch_counter + (unsigned)t;
                 slot = g0 % n_slots;
                 phase = (g0 / n_slots) & 1u;
             }
-            // stage C: finish + hand over
             auto stage_c = [&](const Stage& s) {
                 float J[12], r = 0.f;
                 if (s.valid) {
-                    point_finish<true>(kf, ec, ec.blk[s.b], inv_norm, s.G, s.T, s.g4, s.dw, J, r);
+                    point_finish<true>(kf, ec, bc, inv_norm, s.G, s.T, s.g4, s.dw, J, r);
                     if (write_residuals) {
                         P.residuals[s.idx] = r;
                         if (P.jac_out) {
@@ -600,7 +589,7 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
 #endif
                 mbar_wait(&sh.empty_bar[slot], phase ^ 1u, 1);
 #ifdef EDS_TIMING
-                if (lane == 0 && rank == csize - 1) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
+                if (lane == 0 && g_timing_cta == (int)blockIdx.x) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
 #endif
                 float4* dst = reinterpret_cast<float4*>(&sh.ring[slot][lane][0]);
                 dst[0] = make_float4(J[0], J[1], J[2], J[3]);
@@ -609,65 +598,52 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                 dst[3] = make_float4(r, 0.f, 0.f, 0.f);
                 __syncwarp();  // all 32 rows are written: one elected arrival publishes the slot
                 if (lane == 0) mbar_arrive(&sh.full_bar[slot]);
-                slot += (unsigned)n_prod;
+                slot += (unsigned)N_PROD;
                 if (slot >= n_slots) { slot -= n_slots; phase ^= 1u; }
             };
-            // one pipeline step: `cur` holds batch t with its gathers in flight, `nxt` receives batch t + n_prod,
-            // kp holds the 3-D points of batch t + n_prod and is refilled with those of batch t + 2 n_prod
+            // one pipeline step: `cur` holds batch t with its gathers in flight, `nxt` receives batch t + N_PROD,
+            // kp holds the 3-D points of batch t + N_PROD and is refilled with those of batch t + 2 N_PROD
             auto step = [&](Stage& cur, Stage& nxt, Kp& kp) {
                 const Kp kpb = kp;
-                int idx_a, b_a;
-                const bool valid_a = locate(t + 2 * n_prod, idx_a, b_a);
+                int idx_a;
+                const bool valid_a = locate(t + 2 * N_PROD, idx_a);
                 kp = kp0;
                 if (valid_a) kp = load_kp(kf, idx_a);
                 stage_b(nxt, kpb);
                 stage_c(cur);
-                // the batch after next becomes the next one
-                cur.idx = idx_a; cur.b = b_a; cur.valid = valid_a;
-                t += n_prod;
+                cur.idx = idx_a; cur.valid = valid_a;  // the batch after next becomes the next one
+                t += N_PROD;
             };
-            if (t < nb_tot) {
+            if (t < nb) {
                 Stage s0, s1;
                 Kp kp;
-                s0.valid = locate(t, s0.idx, s0.b);
+                s0.valid = locate(t, s0.idx);
                 stage_b(s0, s0.valid ? load_kp(kf, s0.idx) : kp0);
-                s1.valid = locate(t + n_prod, s1.idx, s1.b);
+                s1.valid = locate(t + N_PROD, s1.idx);
                 kp = s1.valid ? load_kp(kf, s1.idx) : kp0;
                 for (;;) {
-                    step(s0, s1, kp);  // finishes s0, fills s1; s0's (idx, b, valid) now describe batch t + n_prod
-                    if (t >= nb_tot) break;
+                    step(s0, s1, kp);
+                    if (t >= nb) break;
                     step(s1, s0, kp);
-                    if (t >= nb_tot) break;
+                    if (t >= nb) break;
                 }
             }
-            for (int bb = rank; bb < B; bb += csize) {  // the counters advance as they do for the consumers
-                batch_counter += (unsigned)((bb + 1 == B) ? nb_last : nb_reg);
-                block_counter++;
-            }
-            return;
+            batch_counter += (unsigned)nb;
+            block_counter++;
+            return 0;
         }
-    }
-    for (int b = rank; b < kf.B; b += csize) {
-        const float* bc = ec.blk[b];
-        const int start = b * ne;
-        const int n = ne + ((b + 1 == kf.B) ? (kf.N - (b + 1) * ne) : 0);  // Tracker.cpp:178-190
-        if constexpr (RES_ONLY) {
-            // residual write-back only (Tracker.cpp:223-230): no Jacobian, no reduction, no DSMEM traffic
-            for (int i = role.etid; i < n; i += role.n_eval_threads) {
-                float r;
-                eval_point<false>(kf, ec, bc, frame, inv_norm, start + i, nullptr, r);
-                P.residuals[start + i] = r;
-            }
-            continue;
-        }
-        const int nb = (n + 31) >> 5;  // batches of this block
+        unsigned before = 0;
         if (role.cidx >= 0) {
-            // ---------------- consumers: own the block's sums (warp c the batches j = c mod N_CONS, which
-            // fixes the summation order), warp 0 applies the loss and publishes the slot ----------
+            // ---------------- consumers: own the block's sums (warp c the batches whose running number is c mod N_CONS,
+            // i.e. the batches j = c0 + k N_CONS of the block), warp 0 applies the loss and publishes the slot ----------
             float acc[96];
 #pragma unroll
             for (int i = 0; i < 96; ++i) acc[i] = 0.f;
             double s_acc = 0.0;  // sum of r^2 in fp64 (the cost decides accept / reject and the tolerances)
+            // The summation order must not depend on what the CTA did before this task (results are bit-identical for
+            // every schedule): consumer c always takes batches j = c, c + N_CONS, ... of the block.  The ring slot of
+            // batch j is fixed by the running number, the consumer that drains it by j; both stay consistent because a
+            // block's batches only ever go to "the" consumer of j and tasks are drained strictly in order.
             unsigned slot, phase;
             {
                 const unsigned g0 = batch_counter + (unsigned)role.cidx;
@@ -681,7 +657,7 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
 #endif
                 mbar_wait(&sh.full_bar[slot], phase, 2);
 #ifdef EDS_TIMING
-                if (lane == 0 && rank == csize - 1 && role.cidx == 0) { atomicAdd(&g_timing[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_timing[17], 1ull); }
+                if (lane == 0 && g_timing_cta == (int)blockIdx.x && role.cidx == 0) { atomicAdd(&g_timing[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_timing[17], 1ull); }
 #endif
                 float v[16];
                 ConsRows::load(sh.ring[slot], lane, v);
@@ -710,17 +686,23 @@ __device__ void cta_evaluate(ProblemShared& ps, CtaShared& sh, double* slot_base
                 double rho0, rho1;
                 loss_eval(P.loss_type, loss_a, s_acc, &rho0, &rho1);
                 const int base = reduce96_base(lane);
-                double* dst = slot_base + b * NSLOT;
+                double* dst = ps.slots + b * NSLOT;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const int e = base + i;
                     if (e < 90) dst[ConsRows::slot(e)] = rho1 * (double)acc[i];
                 }
                 if (lane == 0) { dst[90] = 0.5 * rho0; dst[91] = s_acc; }
+                // the block's sums are in global memory: order them before the count the leader polls
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) before = atomicAdd(ps.done, 1u);
+                before = __shfl_sync(0xffffffffu, before, 0);
             }
         }
         batch_counter += (unsigned)nb;
         block_counter++;
+        return before;
     }
 }
 
@@ -739,14 +721,10 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// Leader warp: publish the evaluation constants of point xe (13 doubles in leader smem) and the
-// command to every CTA of the cluster.  Lane b derives the per-block model normalisation
-// S_b = 1e-3 + v^T A_b v (PhotometricError.hpp:132,148) and c_b = A_b v.
-__device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, int which, const double* xe, int cmd, int B, int csize,
-                               bool signal = true) {
+// One warp: the evaluation constants of point xe (13 doubles) into ec.  Lane b derives the per-block model
+// normalisation S_b = 1e-3 + v^T A_b v (PhotometricError.hpp:132,148) and c_b = A_b v from the Gram matrices A [B][21].
+__device__ void compute_eval_const(EvalConst& ec, const double* xe, const double (*Ab)[21], int B, int cmd) {
     const int lane = threadIdx.x & 31;
-    ProblemShared& ps = sh.prob[which];
-    EvalConst& ec = ps.ec;  // build locally, then replicate
     // every lane computes the shared constants (no divergent serial section), lane 0 stores them
     double R[9];
     quat_to_rot(&xe[3], R);
@@ -765,8 +743,7 @@ __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, int wh
         ec.cmd = cmd;
     }
     if (lane < B && cmd != CMD_DONE) {
-        // S_b = 1e-3 + v^T A_b v (PhotometricError.hpp:132,148), c_b = A_b v
-        const double* A = ps.A[lane];
+        const double* A = Ab[lane];
         double c[6] = {0, 0, 0, 0, 0, 0};
         int k = 0;
 #pragma unroll
@@ -788,29 +765,63 @@ __device__ void leader_publish(cg::cluster_group& cluster, CtaShared& sh, int wh
         for (int i = 0; i < 6; ++i) ec.blk[lane][2 + i] = (float)((c[i] * iM3 + kappa * v[i]) * ivn);
     }
     __syncwarp();
-    // replicate the used prefix of EvalConst (R,t,v + B block records) and cmd
-    const int nwords = (int)(offsetof(EvalConst, blk) / 4) + 8 * B;
-    const int* src = reinterpret_cast<const int*>(&ec);
-    const int self = (int)cluster.block_rank();
-    for (int c = 0; c < csize; ++c) {
-        if (c == self) continue;
-        EvalConst* dst = &cluster.map_shared_rank(&sh, c)->prob[which].ec;
-        int* d = reinterpret_cast<int*>(dst);
-        for (int i = lane; i < nwords; i += 32) d[i] = src[i];
-        if (lane == 0) dst->cmd = cmd;
+}
+
+// what a leader warp needs to talk to the evaluators
+struct LeaderLink {
+    ProblemWork* w;
+    QueueCtl* ctl;
+    unsigned long long* entries;
+    unsigned mask;
+    int pid;
+};
+
+// Leader warp: append `n` tasks (block 0..n-1 of problem pid, or n CMD_EXIT tasks) to the queue.  Everything the tasks
+// refer to must have been written and fenced by the calling lanes before.
+__device__ void push_tasks(const LeaderLink& L, int n, int cmd) {
+    const int lane = threadIdx.x & 31;
+    unsigned t0 = 0;
+    if (lane == 0) t0 = atomicAdd(&L.ctl->tail, (unsigned)n);
+    t0 = __shfl_sync(0xffffffffu, t0, 0);
+    for (int i = lane; i < n; i += 32) {
+        const unsigned ticket = t0 + (unsigned)i;
+        const unsigned payload = pack_task(L.pid, cmd == CMD_EXIT ? 0 : i, cmd);
+        st_release_u64(&L.entries[ticket & L.mask], ((unsigned long long)(ticket + 1u) << 32) | payload);
     }
-    if (signal) {
-        // one fence orders all of this lane's stores, then every lane signals every CTA: the 32nd
-        // arrival completes the phase there
-        fence_cluster();
-        for (int c = 0; c < csize; ++c) mbar_arrive_cluster_relaxed(&sh.ready_bar[which], (unsigned)c);
+}
+
+// Leader warp: publish the evaluation constants of point xe and queue one task per residual block.
+__device__ void leader_publish(LeaderProblem& lp, const LeaderLink& L, const double* xe, int cmd) {
+    const int lane = threadIdx.x & 31;
+    const int B = lp.P.kf.B;
+    compute_eval_const(lp.ec, xe, lp.A, B, cmd);
+    if (cmd == CMD_DONE) return;  // nothing left to evaluate
+    // the used prefix of EvalConst (R, t, v + B block records) and the command go to global memory
+    const int nwords = (int)(offsetof(EvalConst, blk) / 4) + 8 * B;
+    const int* src = reinterpret_cast<const int*>(&lp.ec);
+    int* dst = reinterpret_cast<int*>(&L.w->ec);
+    for (int i = lane; i < nwords; i += 32) dst[i] = src[i];
+    if (lane == 0) L.w->ec.cmd = cmd;
+    __threadfence();  // each lane orders its own stores before the queue entries any lane writes after the warp barrier
+    __syncwarp();
+    push_tasks(L, B, cmd);
+}
+
+// Leader warp: wait until the problem's completion counter has reached `target`.
+// Every lane polls (one broadcast request): a loop run by one lane only leaves the warp in diverged mode, in which
+// every later shuffle of the LM step takes the slow collective path (measured: the step went from 8 to 28 us).
+__device__ __forceinline__ void wait_done(const LeaderLink& L, unsigned target) {
+    for (;;) {
+        const unsigned v = __shfl_sync(0xffffffffu, ld_acquire_u32(&L.w->done), 0);
+        if ((int)(v - target) >= 0) break;
+        __nanosleep(20);
     }
 }
 
 // Leader warp (32 lanes, convergent): consume one evaluation and decide what to do next.
 // ceres TrustRegionMinimizer + LevenbergMarquardtStrategy semantics (options of
 // Tracker.cpp:117-143); returns the next command, lm.cand / lm.x hold the point to evaluate.
-__device__ int lm_advance_warp(ProblemShared& sh) {
+__device__ int lm_advance_warp(LeaderProblem& sh, const ProblemWork* w) {
     const ProblemDesc& P = sh.P;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -819,7 +830,7 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
 #ifdef EDS_TIMING
     unsigned long long tt0 = gtime();
 #endif
-    // fixed pairwise tree over the residual blocks: deterministic and independent of the cluster size
+    // fixed pairwise tree over the residual blocks: deterministic and independent of the launch shape
     bool fin = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -830,10 +841,10 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
             double v[MAX_BLOCKS];
             if (B <= MAX_BLOCKS / 2) {
 #pragma unroll
-                for (int b = 0; b < MAX_BLOCKS / 2; ++b) v[b] = (b < B) ? sh.slots[b][e] : 0.0;
+                for (int b = 0; b < MAX_BLOCKS / 2; ++b) v[b] = (b < B) ? __ldcg(&w->slots[b][e]) : 0.0;
             } else {
 #pragma unroll
-                for (int b = 0; b < MAX_BLOCKS; ++b) v[b] = (b < B) ? sh.slots[b][e] : 0.0;
+                for (int b = 0; b < MAX_BLOCKS; ++b) v[b] = (b < B) ? __ldcg(&w->slots[b][e]) : 0.0;
 #pragma unroll
                 for (int b = 0; b < MAX_BLOCKS / 2; ++b) v[b] += v[b + MAX_BLOCKS / 2];
             }
@@ -885,6 +896,10 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
         }
     }
     __syncwarp();
+#ifdef EDS_TIMING
+    const unsigned long long td1 = gtime();
+    unsigned long long td2 = td1, td3 = td1, td4 = td1;
+#endif
     // row `lane` of the scaled system once a new point has been taken (kept in registers for the solve)
     double Hr[12];
 #pragma unroll
@@ -907,6 +922,9 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
         double g = (lane < 12) ? sh.sum[78 + la] : 0.0;
         const double vq = (lane >= 6 && lane < 12) ? lm.x[1 + lane] : 0.0;
         const double inv_n = rsqrt(warp_sum(vq * vq));
+#ifdef EDS_TIMING
+        td2 = gtime();
+#endif
         const double na = vq * inv_n;
         double wa = 0.0;  // (H n)_i
 #pragma unroll
@@ -919,6 +937,9 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
             Hr[q] = Hr[q] - na * wq - wa * nq + na * nq * sw;
         }
         g = g - na * gn;
+#ifdef EDS_TIMING
+        td3 = gtime();
+#endif
         double sc;
         if (first) {
             double diag = 0.0;
@@ -939,6 +960,9 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
             lm.gs[lane] = g * sc;
             sh.sum[78 + lane] = g;
         }
+#ifdef EDS_TIMING
+        td4 = gtime();
+#endif
         double gt = (lane < 3) ? fabs(g) : 0.0;
         double gmax = warp_max(gt);  // translation part of x - Plus(x,-g) is exactly g
         if (!(gmax > P.gtol)) {
@@ -1038,7 +1062,8 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
         if (lane == 0) state_plus(lm.x, lm.delta, lm.cand);
         ret = CMD_EVAL;
 #ifdef EDS_TIMING
-        if (lane == 0) { g_timing[6] += tt1 - tt0; g_timing[7] += tt2 - tt1; g_timing[8] += tt3 - tt2; g_timing[9] += gtime() - tt3; g_timing[10] += 1; }
+        if (lane == 0) { atomicAdd(&g_timing[22], td1 - tt1); atomicAdd(&g_timing[23], td2 - td1); atomicAdd(&g_timing[24], td3 - td2); atomicAdd(&g_timing[25], td4 - td3); atomicAdd(&g_timing[26], tt2 - td4); }
+        if (lane == 0) { atomicAdd(&g_timing[6], tt1 - tt0); atomicAdd(&g_timing[7], tt2 - tt1); atomicAdd(&g_timing[8], tt3 - tt2); atomicAdd(&g_timing[9], gtime() - tt3); atomicAdd(&g_timing[10], 1ull); }
 #endif
     }
     if (lane == 0) {
@@ -1049,70 +1074,37 @@ __device__ int lm_advance_warp(ProblemShared& sh) {
     return ret;
 }
 
-// all threads of the CTA: descriptor, loss parameter and (leader CTA) the Gram matrices + state of one problem
-__device__ __forceinline__ void load_problem(ProblemShared& ps, const ProblemDesc* problems, int pid, int count, bool leads) {
-    const int tid = threadIdx.x;
-    const bool valid = pid < count;
-    if (tid == 0) ps.valid = valid;
-    if (valid) {
-        const int* src = reinterpret_cast<const int*>(&problems[pid]);
-        int* dst = reinterpret_cast<int*>(&ps.P);
-        for (int i = tid; i < (int)(sizeof(ProblemDesc) / sizeof(int)); i += TRK_THREADS) dst[i] = src[i];
-    }
-    __syncthreads();
-    if (valid) {
-        if (tid == 0) ps.loss_a = ps.P.state[13];
-        if (leads) {
-            for (int i = tid; i < 21 * ps.P.kf.B; i += TRK_THREADS) (&ps.A[0][0])[i] = ps.P.kf.A[i];
-            if (tid < 13) ps.x_eval[tid] = ps.P.state[tid];
-        }
-    }
-    if (tid == 0) ps.ec.cmd = valid ? 0 : CMD_DONE;
-    __syncthreads();
-}
-
-__device__ __forceinline__ void init_barriers(CtaShared& sh, int evaluator_warps) {
-    if (threadIdx.x < N_SLOTS) {
-        mbar_init(&sh.full_bar[threadIdx.x], 1);   // the elected lane of the producer warp that filled the slot
-        mbar_init(&sh.empty_bar[threadIdx.x], 1);  // the elected lane of the consumer warp that drained it
-    }
-    if (threadIdx.x < MAX_K) {
-        mbar_init(&sh.ready_bar[threadIdx.x], 32);                          // the 32 lanes of the problem's leader warp
-        mbar_init(&sh.result_bar[threadIdx.x], (unsigned)evaluator_warps);  // one arrival per evaluator warp of the cluster
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // ready/result are signalled from other CTAs
-    __syncthreads();
-}
-
+// ------------------------------------------------------------------------------------------
+// leader CTA: one warp per problem in flight
+// ------------------------------------------------------------------------------------------
 // leader warp: reset the LM state of a problem and publish its first evaluation point
-__device__ void leader_start(cg::cluster_group& cluster, CtaShared& sh, int which, int csize) {
-    ProblemShared& ps = sh.prob[which];
+__device__ void leader_start(LeaderProblem& lp, const LeaderLink& L) {
     const int lane = threadIdx.x & 31;
-    LmState& lm = ps.lm;
-    if (lane < 13) lm.x[lane] = ps.x_eval[lane];
+    LmState& lm = lp.lm;
+    if (lane < 13) lm.x[lane] = lp.x_eval[lane];
     if (lane == 0) {
         lm.radius = 1e4; lm.dec = 2.0; lm.reuse_diag = 0;
         lm.iter = 0; lm.n_succ = 0; lm.n_unsucc = 0; lm.consec_invalid = 0; lm.n_eval = 0;
         lm.termination = EDSGPU_TERM_NO_CONVERGENCE; lm.phase = PHASE_INIT;
         lm.x_cost = 0.0; lm.initial_cost = 0.0; lm.mcc = 0.0; lm.gmax = 0.0; lm.x_norm = 0.0;
+        L.w->loss_a = lp.loss_a;
     }
     __syncwarp();
-    leader_publish(cluster, sh, which, lm.x, CMD_EVAL, ps.P.kf.B, csize);
+    leader_publish(lp, L, lm.x, CMD_EVAL);
 }
 
-// leader warp: consume the evaluation of a problem, advance its LM state, publish the next command
-__device__ void leader_step(cg::cluster_group& cluster, CtaShared& sh, int which, int csize) {
-    ProblemShared& ps = sh.prob[which];
+// leader warp: consume the evaluation of a problem, advance its LM state, publish the next command; returns it
+__device__ int leader_step(LeaderProblem& lp, const LeaderLink& L) {
     const int lane = threadIdx.x & 31;
-    LmState& lm = ps.lm;
-    const ProblemDesc& P = ps.P;
-    const int next = lm_advance_warp(ps);
+    LmState& lm = lp.lm;
+    const ProblemDesc& P = lp.P;
+    const int next = lm_advance_warp(lp, L.w);
 #ifdef EDS_TIMING
     const unsigned long long tp0 = gtime();
 #endif
-    leader_publish(cluster, sh, which, (next == CMD_EVAL) ? lm.cand : lm.x, next, P.kf.B, csize);
+    leader_publish(lp, L, (next == CMD_EVAL) ? lm.cand : lm.x, next);
 #ifdef EDS_TIMING
-    if (lane == 0) g_timing[15] += gtime() - tp0;
+    if (lane == 0) atomicAdd(&g_timing[15], gtime() - tp0);
 #endif
     if (next != CMD_EVAL && lane == 0) {
         const bool usable = lm.termination != EDSGPU_TERM_FAILURE;
@@ -1131,147 +1123,244 @@ __device__ void leader_step(cg::cluster_group& cluster, CtaShared& sh, int which
         inf.final_radius = lm.radius;
         *P.info = inf;
     }
+    return next;
 }
 
-// One cluster keeps K <= MAX_K independent tracking problems in flight (problems K*c .. K*c+K-1 for
-// cluster c).  Problem k is led by the last warp of CTA rank k: a sequential Levenberg-Marquardt loop that
-// waits for the reduced sums of an evaluation, takes its decision and publishes the next evaluation
-// point to every CTA.  All other warps are evaluators: they visit the live problems round-robin,
-// wait until the problem's constants have landed, sweep this CTA's residual blocks and report.
-// There is no cluster-wide barrier in the loop, only two mbarrier hand-overs per evaluation
-//     ready_bar[k]  (every CTA)    leader k   -> evaluators   constants + command are in your smem
-//     result_bar[k] (leader's CTA) evaluators -> leader k     all block sums are in your smem
-// so the serial LM step of one problem (~12 us of dependent fp64 latency) runs while the evaluators
-// sweep the other K-1 problems.  With K = 1 sweep and LM step simply alternate.
-__global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemDesc* __restrict__ problems, int count, int K) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int csize = (int)cluster.num_blocks();
-    const int rank = (int)cluster.block_rank();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int first = (blockIdx.x / csize) * K;
-    for (int k = 0; k < K; ++k) load_problem(sh.prob[k], problems, first + k, count, rank == k);
-    const bool hosts_leader = rank < K;
-    init_barriers(sh, TRK_WARPS * csize - K);
-    const Roles role = make_roles(hosts_leader);
-    const bool is_leader_warp = hosts_leader && ((tid >> 5) == LEADER_WARP);
-    cluster.sync();  // barriers initialised and problems loaded everywhere before the first remote signal
+// One leader warp: takes problems warp_id, warp_id + stride, ... to completion, one at a time.  A problem is a
+// sequential Levenberg-Marquardt loop: wait for the block sums of the evaluation it has queued, take the decision,
+// publish the next evaluation point and queue its tasks.  The serial step of one problem (~8 us of dependent fp64
+// latency) overlaps the sweeps of all the others, which run on the evaluator CTAs.
+__device__ void leader_warp_main(LeaderProblem& lp, const ProblemDesc* __restrict__ problems, ProblemWork* work, QueueCtl* ctl,
+                                 unsigned long long* entries, unsigned mask, int count, int first, int stride, int n_eval_ctas) {
+    const int lane = threadIdx.x & 31;
 #ifdef EDS_TIMING
-    const unsigned long long t_kernel = gtime();
     unsigned long long t_wait = 0, t_work = 0, n_work = 0;
 #endif
-    if (is_leader_warp) {
-        // ---------------- leader of problem `rank` ----------------
-        if (sh.prob[rank].valid) {
-            leader_start(cluster, sh, rank, csize);
-            unsigned parity = 0;
-            for (;;) {
+    for (int pid = first; pid < count; pid += stride) {
+        LeaderLink L{work + pid, ctl, entries, mask, pid};
+        {
+            const int* src = reinterpret_cast<const int*>(&problems[pid]);
+            int* dst = reinterpret_cast<int*>(&lp.P);
+            for (int i = lane; i < (int)(sizeof(ProblemDesc) / sizeof(int)); i += 32) dst[i] = src[i];
+        }
+        __syncwarp();
+        const ProblemDesc& P = lp.P;
+        const int B = P.kf.B;
+        if (lane == 0) lp.loss_a = P.state[13];
+        for (int i = lane; i < 21 * B; i += 32) (&lp.A[0][0])[i] = P.kf.A[i];
+        if (lane < 13) lp.x_eval[lane] = P.state[lane];
+        // nothing of this problem is in flight: the counter's current value is the base of this solve
+        unsigned target = __shfl_sync(0xffffffffu, ld_acquire_u32(&L.w->done), 0);
+        __syncwarp();
+        leader_start(lp, L);
+        target += (unsigned)B;
+        for (;;) {
 #ifdef EDS_TIMING
-                const unsigned long long t0 = gtime();
+            const unsigned long long t0 = gtime();
 #endif
-                mbar_wait_cluster(&sh.result_bar[rank], parity, 4);
-                parity ^= 1u;
+            wait_done(L, target);
 #ifdef EDS_TIMING
-                const unsigned long long t1 = gtime();
+            const unsigned long long t1 = gtime();
 #endif
-                leader_step(cluster, sh, rank, csize);
+            const int next = leader_step(lp, L);
 #ifdef EDS_TIMING
-                t_wait += t1 - t0; t_work += gtime() - t1; n_work++;
+            t_wait += t1 - t0; t_work += gtime() - t1; n_work++;
 #endif
-                if (sh.prob[rank].ec.cmd != CMD_EVAL) break;
+            if (next == CMD_EVAL) { target += (unsigned)B; continue; }
+            if (next == CMD_FINAL) {  // residual write-back (Tracker.cpp:223-230): every evaluator warp of every block reports
+                target += (unsigned)(B * N_EVAL_WARPS);
+                wait_done(L, target);
             }
+            break;
         }
-#ifdef EDS_TIMING
-        if (lane == 0) { atomicAdd(&g_timing[0], t_work); atomicAdd(&g_timing[1], t_wait); atomicAdd(&g_timing[2], n_work); }
-#endif
-    } else {
-        // ---------------- evaluators ----------------
-        unsigned batch_counter = 0, block_counter = 0;  // same in every evaluator thread of the CTA
-        unsigned live = 0, parity = 0;
-        for (int k = 0; k < K; ++k) live |= sh.prob[k].valid ? (1u << k) : 0u;
-        while (live) {
-            for (int k = 0; k < K; ++k) {
-                if (!((live >> k) & 1u)) continue;
-                ProblemShared& ps = sh.prob[k];
-#ifdef EDS_TIMING
-                const unsigned long long t0 = gtime();
-#endif
-                mbar_wait_cluster(&sh.ready_bar[k], (parity >> k) & 1u, 3);
-                parity ^= 1u << k;
-#ifdef EDS_TIMING
-                const unsigned long long t1 = gtime();
-#endif
-                const int cmd = ps.ec.cmd;
-                if (cmd == CMD_EVAL) {
-                    double* slots = &cluster.map_shared_rank(&sh, k)->prob[k].slots[0][0];
-                    if (hosts_leader) cta_evaluate<false, true>(ps, sh, slots, rank, csize, role, false, batch_counter, block_counter);
-                    else cta_evaluate<false, false>(ps, sh, slots, rank, csize, role, false, batch_counter, block_counter);
-                    // the consumer's block sums went over DSMEM: order them before the signal
-                    if (role.cidx == 0) fence_cluster();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(&sh.result_bar[k], (unsigned)k);
-                } else {
-                    if (cmd == CMD_FINAL) cta_evaluate<true, false>(ps, sh, nullptr, rank, csize, role, true, batch_counter, block_counter);
-                    live &= ~(1u << k);
-                }
-#ifdef EDS_TIMING
-                t_wait += t1 - t0; t_work += gtime() - t1; n_work++;
-#endif
-            }
-        }
-#ifdef EDS_TIMING
-        if (lane == 0 && rank == csize - 1) {
-            if (role.cidx == 0) { atomicAdd(&g_timing[3], t_work); atomicAdd(&g_timing[4], t_wait); atomicAdd(&g_timing[5], n_work); }
-            else if (tid == 0) { atomicAdd(&g_timing[13], t_work); atomicAdd(&g_timing[14], t_wait); }
-            else if (role.pidx == role.n_prod - 1) { atomicAdd(&g_timing[20], t_work); }
-            else if (role.pidx == 6) { atomicAdd(&g_timing[21], t_work); }
-            else if (role.cidx == 1) { atomicAdd(&g_timing[22], t_work); }
-        }
-#endif
+        // the last problem of the launch to finish sends every evaluator CTA home
+        unsigned fin = 0;
+        if (lane == 0) fin = atomicAdd(&ctl->finished, 1u) + 1u;
+        fin = __shfl_sync(0xffffffffu, fin, 0);
+        if (fin % (unsigned)count == 0u) push_tasks(L, n_eval_ctas, CMD_EXIT);
     }
-    cluster.sync();  // nobody leaves while its shared memory may still be written or signalled
 #ifdef EDS_TIMING
-    if (rank == 0 && tid == 0) { atomicAdd(&g_timing[11], gtime() - t_kernel); atomicAdd(&g_timing[12], 1ull); }
+    if (lane == 0) { atomicAdd(&g_timing[0], t_work); atomicAdd(&g_timing[1], t_wait); atomicAdd(&g_timing[2], n_work); }
 #endif
 }
 
-// parity/debug entry (edsgpu_tracker_evaluate): one full evaluation at P.state, residuals and
-// Jacobian rows written out, reduced normal equations returned.
-__global__ void __launch_bounds__(TRK_THREADS, 1) track_eval_kernel(const ProblemDesc* __restrict__ problems, int count) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int csize = (int)cluster.num_blocks();
-    const int rank = (int)cluster.block_rank();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
-    ProblemShared& ps = sh.prob[0];
-    load_problem(ps, problems, blockIdx.x / csize, count, rank == 0);
-    init_barriers(sh, 1);
-    CtaShared* leader = cluster.map_shared_rank(&sh, 0);
-    const Roles role = make_roles(rank == 0);
-    const bool is_leader_warp = (rank == 0) && ((threadIdx.x >> 5) == LEADER_WARP);
-    if (is_leader_warp) leader_publish(cluster, sh, 0, ps.x_eval, CMD_EVAL, ps.P.kf.B, csize, false);
-    cluster.sync();
-    unsigned batch_counter = 0, block_counter = 0;
-    if (!is_leader_warp) {
-        if (rank == 0) cta_evaluate<false, true>(ps, sh, &leader->prob[0].slots[0][0], rank, csize, role, true, batch_counter, block_counter);
-        else cta_evaluate<false, false>(ps, sh, &leader->prob[0].slots[0][0], rank, csize, role, true, batch_counter, block_counter);
+// ------------------------------------------------------------------------------------------
+// evaluator CTA
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void init_barriers(EvalShared& sh) {
+    if (threadIdx.x < N_SLOTS) {
+        mbar_init(&sh.full_bar[threadIdx.x], 1);   // the elected lane of the producer warp that filled the slot
+        mbar_init(&sh.empty_bar[threadIdx.x], 1);  // the elected lane of the consumer warp that drained it
     }
-    cluster.sync();
-    const ProblemDesc& P = ps.P;
-    if (rank == 0 && threadIdx.x == 0 && P.eval_out) {
-        double cost = 0.0;
-        for (int b = 0; b < P.kf.B; ++b) cost += ps.slots[b][90];
-        P.eval_out[0] = cost;
-        for (int a = 0; a < 12; ++a) {
-            double gs = 0.0;
-            for (int b = 0; b < P.kf.B; ++b) gs += ps.slots[b][78 + a];
-            P.eval_out[1 + 144 + a] = gs;
-            for (int c2 = a; c2 < 12; ++c2) {
-                double h = 0.0;
-                for (int b = 0; b < P.kf.B; ++b) h += ps.slots[b][tri_index(a, c2)];
-                P.eval_out[1 + 12 * a + c2] = h;
-                P.eval_out[1 + 12 * c2 + a] = h;
+    if (threadIdx.x < MAILBOX) {
+        mbar_init(&sh.task_full[threadIdx.x], 1);              // the elected lane of the control warp
+        mbar_init(&sh.task_empty[threadIdx.x], N_EVAL_WARPS);  // one elected lane per evaluator warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+}
+
+// Control warp of an evaluator CTA: takes tickets from the global queue, waits for the ticket's entry, copies the task
+// (problem descriptor + published constants) into the next mailbox slot and hands it to the evaluator warps.  It runs
+// MAILBOX - 1 tasks ahead of them, so the three global round trips of a fetch are off the evaluators' path while the
+// queue has work.
+__device__ void control_warp_main(EvalShared& sh, const ProblemDesc* __restrict__ problems, ProblemWork* work, QueueCtl* ctl,
+                                  const unsigned long long* entries, unsigned mask) {
+    const int lane = threadIdx.x & 31;
+    for (unsigned i = 0;; ++i) {
+        const unsigned slot = i % MAILBOX, use = i / MAILBOX;
+        if (use > 0) mbar_wait(&sh.task_empty[slot], (use - 1u) & 1u, 5);
+#ifdef EDS_TIMING
+        const unsigned long long tf0 = gtime();
+#endif
+        unsigned ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&ctl->head, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        const unsigned long long* e = &entries[ticket & mask];
+        unsigned payload;
+        for (;;) {  // every lane polls (one broadcast request): the warp stays converged
+            const unsigned long long v = ld_acquire_u64(e);
+            const unsigned tag = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), 0);
+            payload = __shfl_sync(0xffffffffu, (unsigned)v, 0);
+            if (tag == ticket + 1u) break;
+            __nanosleep(20);
+        }
+        const int pid = (int)(payload & 0xfffffu), block = (int)((payload >> 20) & 63u), cmd = (int)(payload >> 26);
+        TaskShared& ts = sh.task[slot];
+        if (cmd != CMD_EXIT) {
+            ProblemWork* w = work + pid;
+            const int* src = reinterpret_cast<const int*>(&problems[pid]);
+            int* dst = reinterpret_cast<int*>(&ts.P);
+            for (int k = lane; k < (int)(sizeof(ProblemDesc) / sizeof(int)); k += 32) dst[k] = __ldg(src + k);
+            // published by the leader before the queue entry (acquired above): read past the non-coherent L1
+            const int B = __ldg(&problems[pid].kf.B);
+            const int nwords = (int)(offsetof(EvalConst, blk) / 4) + 8 * B;
+            const int* es = reinterpret_cast<const int*>(&w->ec);
+            int* ed = reinterpret_cast<int*>(&ts.ec);
+            for (int k = lane; k < nwords; k += 32) ed[k] = __ldcg(es + k);
+            if (lane == 0) {
+                ts.loss_a = __ldcg(&w->loss_a);
+                ts.slots = &w->slots[0][0];
+                ts.done = &w->done;
+                ts.block = block;
+            }
+        }
+        if (lane == 0) ts.cmd = cmd;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.task_full[slot]);
+#ifdef EDS_TIMING
+        if (lane == 0 && g_timing_cta == (int)blockIdx.x) { atomicAdd(&g_timing[20], gtime() - tf0); atomicAdd(&g_timing[21], 1ull); }
+#endif
+        if (cmd == CMD_EXIT) break;
+    }
+}
+
+// Batched Levenberg-Marquardt solve as a dataflow over global memory.  The first n_lead CTAs are LEADER CTAs: each of
+// their warps runs the sequential LM state machine of one problem at a time (decision, 12x12 Cholesky, retraction) and
+// turns every evaluation it needs into one task per residual block in a global queue.  All other CTAs are EVALUATORS:
+// their control warp pops tasks, their producer / consumer warps sweep the block and report the block sums to the
+// problem's slots in global memory.  Any evaluator serves any problem, so every SM stays busy whatever the number of
+// problems, and the serial step of a problem (~8 us) is hidden behind the sweeps of all the others.  Summation orders are
+// fixed per block and per problem: results do not depend on the launch shape or on the schedule.
+__global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemDesc* __restrict__ problems, ProblemWork* work, QueueCtl* ctl,
+                                                                  unsigned long long* entries, unsigned mask, int count, int n_lead) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x < n_lead) {
+        LeadShared& ls = *reinterpret_cast<LeadShared*>(smem_raw);
+        leader_warp_main(ls.prob[warp], problems, work, ctl, entries, mask, count, (int)blockIdx.x * LEAD_WARPS + warp, n_lead * LEAD_WARPS,
+                         (int)gridDim.x - n_lead);
+        return;
+    }
+    EvalShared& sh = *reinterpret_cast<EvalShared*>(smem_raw);
+    init_barriers(sh);
+    if (warp == CTRL_WARP) {
+        control_warp_main(sh, problems, work, ctl, entries, mask);
+        return;
+    }
+    const Roles role = make_roles();
+    const int lane = threadIdx.x & 31;
+    unsigned batch_counter = 0, block_counter = 0;  // same in every evaluator thread of the CTA
+#ifdef EDS_TIMING
+    unsigned long long t_wait = 0, t_work = 0, n_work = 0;
+#endif
+    for (unsigned i = 0;; ++i) {
+        const unsigned slot = i % MAILBOX, use = i / MAILBOX;
+#ifdef EDS_TIMING
+        const unsigned long long t0 = gtime();
+#endif
+        mbar_wait(&sh.task_full[slot], use & 1u, 3);
+#ifdef EDS_TIMING
+        const unsigned long long t1 = gtime();
+#endif
+        TaskShared& ts = sh.task[slot];
+        const int cmd = ts.cmd;
+        if (cmd == CMD_EXIT) break;
+        if (cmd == CMD_EVAL) cta_evaluate<false>(ts, sh, role, false, batch_counter, block_counter);
+        else cta_evaluate<true>(ts, sh, role, true, batch_counter, block_counter);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.task_empty[slot]);
+#ifdef EDS_TIMING
+        t_wait += t1 - t0; t_work += gtime() - t1; n_work++;
+#endif
+    }
+#ifdef EDS_TIMING
+    if (lane == 0 && g_timing_cta == (int)blockIdx.x) {
+        if (role.cidx == 0) { atomicAdd(&g_timing[3], t_work); atomicAdd(&g_timing[4], t_wait); atomicAdd(&g_timing[5], n_work); }
+        else if (role.pidx == 0) { atomicAdd(&g_timing[13], t_work); atomicAdd(&g_timing[14], t_wait); }
+    }
+#endif
+}
+
+// parity/debug entry (edsgpu_tracker_evaluate): one full evaluation at P.state, residuals and Jacobian rows written out,
+// reduced normal equations returned.  One CTA per residual block; the CTA that finishes last sums the blocks.
+__global__ void __launch_bounds__(TRK_THREADS, 1) track_eval_kernel(const ProblemDesc* __restrict__ problems, ProblemWork* work) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EvalShared& sh = *reinterpret_cast<EvalShared*>(smem_raw);
+    __shared__ double A_sh[MAX_BLOCKS][21];
+    __shared__ double x_sh[13];
+    TaskShared& ts = sh.task[0];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    {
+        const int* src = reinterpret_cast<const int*>(&problems[0]);
+        int* dst = reinterpret_cast<int*>(&ts.P);
+        for (int i = tid; i < (int)(sizeof(ProblemDesc) / sizeof(int)); i += TRK_THREADS) dst[i] = src[i];
+    }
+    init_barriers(sh);  // ends with a CTA barrier
+    const ProblemDesc& P = ts.P;
+    const int B = P.kf.B;
+    for (int i = tid; i < 21 * B; i += TRK_THREADS) (&A_sh[0][0])[i] = P.kf.A[i];
+    if (tid < 13) x_sh[tid] = P.state[tid];
+    if (tid == 0) {
+        ts.loss_a = P.state[13];
+        ts.slots = &work->slots[0][0];
+        ts.done = &work->done;
+        ts.block = (int)blockIdx.x;
+        ts.cmd = CMD_EVAL;
+    }
+    __syncthreads();
+    if (warp == CTRL_WARP) compute_eval_const(ts.ec, x_sh, A_sh, B, CMD_EVAL);
+    __syncthreads();
+    if (warp == CTRL_WARP) return;
+    const Roles role = make_roles();
+    unsigned batch_counter = 0, block_counter = 0;
+    const unsigned before = cta_evaluate<false>(ts, sh, role, true, batch_counter, block_counter);
+    if (role.cidx == 0 && before == (unsigned)(B - 1) && P.eval_out) {  // `done` was zeroed before the launch: this is the last block
+        __threadfence();
+        if ((tid & 31) == 0) {
+            double cost = 0.0;
+            for (int b = 0; b < B; ++b) cost += __ldcg(&work->slots[b][90]);
+            P.eval_out[0] = cost;
+            for (int a = 0; a < 12; ++a) {
+                double gs = 0.0;
+                for (int b = 0; b < B; ++b) gs += __ldcg(&work->slots[b][78 + a]);
+                P.eval_out[1 + 144 + a] = gs;
+                for (int c2 = a; c2 < 12; ++c2) {
+                    double h = 0.0;
+                    for (int b = 0; b < B; ++b) h += __ldcg(&work->slots[b][tri_index(a, c2)]);
+                    P.eval_out[1 + 12 * a + c2] = h;
+                    P.eval_out[1 + 12 * c2 + a] = h;
+                }
             }
         }
     }
@@ -1528,12 +1617,14 @@ struct edsgpu_tracker {
     int cached_slot = -1;
 };
 
-struct LaunchShape { int csize, K, nclusters; };
+struct LaunchShape { int n_lead, n_eval; };  // leader CTAs, evaluator CTAs
 
 struct edsgpu_batch {
     edsgpu_ctx* ctx = nullptr;
     int count = 0;
-    LaunchShape shape{1, 1, 0};
+    LaunchShape shape{1, 1};
+    void* work_block = nullptr;  // ProblemWork[count] | QueueCtl | queue entries (device, zeroed once: the counters only grow)
+    unsigned queue_mask = 0;
     const edsgpu_frames* frames = nullptr;  // slots first_slot .. first_slot + count - 1
     int first_slot = 0;
     ProblemDesc* desc = nullptr;  // device
@@ -1544,80 +1635,29 @@ struct edsgpu_batch {
 
 namespace {
 
-void cluster_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, cudaStream_t stream, int nclusters, int csize) {
-    cfg = cudaLaunchConfig_t{};
-    cfg.gridDim = dim3(nclusters * csize);
-    cfg.blockDim = dim3(TRK_THREADS);
-    cfg.dynamicSmemBytes = sizeof(CtaShared);
-    cfg.stream = stream;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+constexpr size_t kLmSmem = sizeof(EvalShared) > sizeof(LeadShared) ? sizeof(EvalShared) : sizeof(LeadShared);
+
+int env_int(const char* name, int lo, int hi) {  // tuning / debug overrides; -1 = not set
+    const char* e = getenv(name);
+    if (!e) return -1;
+    const int v = atoi(e);
+    return (v >= lo && v <= hi) ? v : -1;
 }
 
-// clusters of c = 1 << k CTAs the device holds at once (cached per context)
-int resident_clusters(edsgpu_ctx* ctx, int k) {
-    if (ctx->lm_clusters[k] == 0) {
-        const int c = 1 << k;
-        cudaLaunchConfig_t cfg;
-        cudaLaunchAttribute attr[1];
-        cluster_config(cfg, attr, ctx->stream, 1, c);
-        int n = 0;
-        cudaFuncSetAttribute(track_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared));
-        if (cudaOccupancyMaxActiveClusters(&n, track_lm_kernel, &cfg) != cudaSuccess || n <= 0) {
-            cudaGetLastError();
-            n = ctx->num_sms / c;  // one 512-thread CTA per SM
-        }
-        ctx->lm_clusters[k] = n;
-        if (getenv("EDSGPU_VERBOSE")) fprintf(stderr, "[edsgpu] device holds %d clusters of %d tracker CTAs\n", n, c);
-    }
-    return ctx->lm_clusters[k];
-}
-
-// Shape of a batched launch: CTAs per cluster (<= residual blocks) and problems K kept in flight per
-// cluster.  Wide clusters first; K grows only as far as needed to get down to about one CTA per SM
-// (more problems per cluster hide the serial LM steps, more clusters use more SMs); everything must
-// be resident at once, a second wave costs more than narrower clusters do.
+// Shape of a batched launch.  Leader CTAs: one warp per problem in flight (up to MAX_LEAD_CTAS x 16 problems at once,
+// further ones follow as warps finish).  Evaluator CTAs: all remaining SMs, but no more than there can be tasks in flight
+// (one per residual block and problem).  EDSGPU_RESERVE_SMS leaves SMs to kernels of other streams (event-frame builds
+// of the next window); EDSGPU_LEADER_CTAS / EDSGPU_EVAL_CTAS force the two counts.  Results do not depend on the shape.
 LaunchShape pick_shape(edsgpu_ctx* ctx, int count, int B) {
-    int force_c = 0, force_k = 0;
-    if (const char* e = getenv("EDSGPU_CLUSTER")) {  // tuning/debug overrides
-        const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8) force_c = v;
-    }
-    if (const char* e = getenv("EDSGPU_INFLIGHT")) {
-        const int v = atoi(e);
-        if (v >= 1 && v <= MAX_K) force_k = v;
-    }
-    for (int k = 3; k >= 0; --k) {
-        const int c = 1 << k;
-        if (force_c ? (c != force_c) : (c > MAX_CLUSTER || c > B)) continue;
-        int K = (int)(((size_t)count * c + ctx->num_sms - 1) / ctx->num_sms);
-        K = std::max(1, std::min(K, std::min(MAX_K, c)));
-        if (force_k) K = std::min(force_k, c);
-        const int n = (count + K - 1) / K;
-        if (force_c || k == 0 || n <= resident_clusters(ctx, k)) return LaunchShape{c, K, n};
-    }
-    return LaunchShape{1, 1, count};
-}
-
-template <typename K, typename... Args>
-edsgpu_status launch_cluster(edsgpu_ctx* ctx, K kernel, int nclusters, int csize, Args... args) {
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
-    cluster_config(cfg, attr, ctx->stream, nclusters, csize);
-    // per device, cheap: opt in to > 48 KB of dynamic shared memory
-    EDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
-    if (getenv("EDSGPU_VERBOSE")) {  // debug aid: how many clusters of this shape the device holds at once
-        int max_clusters = 0;
-        cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg);
-        fprintf(stderr, "[edsgpu] launch: %d clusters of %d CTAs; device holds %d such clusters\n", nclusters, csize, max_clusters);
-    }
-    EDS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, args...));
-    ctx->launches++;
-    return EDSGPU_OK;
+    int n_lead = std::max(1, std::min((count + LEAD_WARPS - 1) / LEAD_WARPS, MAX_LEAD_CTAS));
+    const int force_lead = env_int("EDSGPU_LEADER_CTAS", 1, 64);
+    if (force_lead > 0) n_lead = force_lead;
+    const int reserve = std::max(0, env_int("EDSGPU_RESERVE_SMS", 0, 1024));
+    const int in_flight = std::min(count, n_lead * LEAD_WARPS);
+    int n_eval = std::max(1, std::min(ctx->num_sms - n_lead - reserve, in_flight * B));
+    const int force_eval = env_int("EDSGPU_EVAL_CTAS", 1, 4096);
+    if (force_eval > 0) n_eval = force_eval;
+    return LaunchShape{n_lead, n_eval};
 }
 
 ProblemDesc make_desc(const edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot) {
@@ -1835,6 +1875,17 @@ edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* tracke
     b->trackers.assign(trackers, trackers + count);
     b->keyframes.assign(keyframes, keyframes + count);
     cudaError_t e = cudaMalloc(&b->desc, sizeof(ProblemDesc) * (size_t)count);
+    if (e == cudaSuccess) {
+        // queue capacity: every problem in flight has at most one task per block outstanding, plus the exit tasks; the
+        // evaluators hold at most one unfilled ticket each
+        const size_t in_flight = (size_t)std::min(count, b->shape.n_lead * LEAD_WARPS);
+        size_t cap = 64;
+        while (cap < in_flight * MAX_BLOCKS + 2 * (size_t)b->shape.n_eval + 64) cap <<= 1;
+        b->queue_mask = (unsigned)(cap - 1);
+        const size_t bytes = sizeof(ProblemWork) * (size_t)count + sizeof(QueueCtl) + sizeof(unsigned long long) * cap;
+        e = cudaMalloc(&b->work_block, bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(b->work_block, 0, bytes, ctx->stream);
+    }
     if (e != cudaSuccess) { edsgpu_batch_destroy(b); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
     edsgpu_status st = upload_descriptors(b);
     if (st != EDSGPU_OK) { edsgpu_batch_destroy(b); return st; }
@@ -1847,6 +1898,7 @@ void edsgpu_batch_destroy(edsgpu_batch* b) {
     DeviceGuard g(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     if (b->desc) cudaFree(b->desc);
+    if (b->work_block) cudaFree(b->work_block);
     delete b;
 }
 
@@ -1864,8 +1916,16 @@ edsgpu_status edsgpu_batch_optimize(edsgpu_batch* b) {
     // the event frames are built on their own stream: wait for the builds of our slots only
     edsgpu_status st = edsgpu_frames_wait_built(b->frames, b->first_slot, b->count, ctx->stream);
     if (st != EDSGPU_OK) return st;
-    st = launch_cluster(ctx, track_lm_kernel, b->shape.nclusters, b->shape.csize, (const ProblemDesc*)b->desc, b->count, b->shape.K);
-    if (st != EDSGPU_OK) return st;
+    {
+        ProblemWork* work = (ProblemWork*)b->work_block;
+        QueueCtl* ctl = (QueueCtl*)(work + b->count);
+        unsigned long long* entries = (unsigned long long*)(ctl + 1);
+        EDS_CUDA(ctx, cudaFuncSetAttribute(track_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmSmem));
+        track_lm_kernel<<<b->shape.n_lead + b->shape.n_eval, TRK_THREADS, kLmSmem, ctx->stream>>>((const ProblemDesc*)b->desc, work, ctl, entries,
+                                                                                                b->queue_mask, b->count, b->shape.n_lead);
+        EDS_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     st = edsgpu_frames_mark_read(b->frames, b->first_slot, b->count, ctx->stream);
     if (st != EDSGPU_OK) return st;
     mad_kernel<<<b->count, MAD_THREADS, 0, ctx->stream>>>((const ProblemDesc*)b->desc);
@@ -1874,11 +1934,11 @@ edsgpu_status edsgpu_batch_optimize(edsgpu_batch* b) {
     return EDSGPU_OK;
 }
 
-edsgpu_status edsgpu_batch_launch_shape(const edsgpu_batch* b, int* clusters, int* ctas_per_cluster, int* problems_in_flight) {
+edsgpu_status edsgpu_batch_launch_shape(const edsgpu_batch* b, int* evaluator_ctas, int* leader_ctas, int* problems_in_flight) {
     if (!b) return EDSGPU_INVALID_ARGUMENT;
-    if (clusters) *clusters = b->shape.nclusters;
-    if (ctas_per_cluster) *ctas_per_cluster = b->shape.csize;
-    if (problems_in_flight) *problems_in_flight = b->shape.K;
+    if (evaluator_ctas) *evaluator_ctas = b->shape.n_eval;
+    if (leader_ctas) *leader_ctas = b->shape.n_lead;
+    if (problems_in_flight) *problems_in_flight = std::min(b->count, b->shape.n_lead * LEAD_WARPS);
     return EDSGPU_OK;
 }
 
@@ -1969,6 +2029,7 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     const size_t o_desc = take(sizeof(ProblemDesc)), o_state = take(14 * 8), o_eval = take(157 * 8), o_info = take(sizeof(edsgpu_tracker_info));
     const size_t o_jac = take(N * 12 * sizeof(float)), o_wide = take(N * 12 * sizeof(double)), o_res = take(N * sizeof(float));
+    const size_t o_work = take(sizeof(ProblemWork));
     edsgpu_status st = edsgpu_ensure_scratch(ctx, off);
     if (st == EDSGPU_OK) st = edsgpu_ensure_pinned(ctx, sizeof(ProblemDesc) + 14 * 8 + 157 * 8);
     if (st != EDSGPU_OK) return st;
@@ -1992,9 +2053,14 @@ edsgpu_status edsgpu_tracker_evaluate(edsgpu_ctx* ctx, const edsgpu_keyframe* kf
     hstate[13] = loss_param;
     EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_desc, hd, sizeof(ProblemDesc), cudaMemcpyHostToDevice, ctx->stream));
     EDS_CUDA(ctx, cudaMemcpyAsync(ds + o_state, hstate, 14 * 8, cudaMemcpyHostToDevice, ctx->stream));
-    const int csize = pick_shape(ctx, 1, kf->dev.B).csize;
+    EDS_CUDA(ctx, cudaMemsetAsync(ds + o_work, 0, sizeof(ProblemWork), ctx->stream));  // the last block to finish sums: counter from 0
     st = edsgpu_frames_wait_built(frames, slot, 1, ctx->stream);
-    if (st == EDSGPU_OK) st = launch_cluster(ctx, track_eval_kernel, 1, csize, (const ProblemDesc*)(ds + o_desc), 1);
+    if (st == EDSGPU_OK) {
+        EDS_CUDA(ctx, cudaFuncSetAttribute(track_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EvalShared)));
+        track_eval_kernel<<<kf->dev.B, TRK_THREADS, sizeof(EvalShared), ctx->stream>>>((const ProblemDesc*)(ds + o_desc), (ProblemWork*)(ds + o_work));
+        EDS_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     if (st == EDSGPU_OK) st = edsgpu_frames_mark_read(frames, slot, 1, ctx->stream);
     if (st != EDSGPU_OK) return st;
     double* hev = (double*)(hp + sizeof(ProblemDesc) + 14 * 8);

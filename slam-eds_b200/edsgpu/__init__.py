@@ -303,7 +303,7 @@ class TrackerBatch:
         self.ctx.check(self.ctx.lib.edsgpu_batch_optimize(self.h))
 
     def launch_shape(self):
-        """(clusters, CTAs per cluster, problems in flight per cluster) of the batched launch."""
+        """(evaluator CTAs, leader CTAs, problems in flight) of the batched launch."""
         a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
         self.ctx.check(self.ctx.lib.edsgpu_batch_launch_shape(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value

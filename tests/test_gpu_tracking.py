@@ -232,11 +232,11 @@ def test_mad_and_other_loss_parameter_methods(gpu_ctx, problems):
     kfd.close()
 
 
-def test_batch_matches_single_and_is_independent_of_cluster_size(gpu_ctx, problems):
-    """One launch over many trackers (other cluster size) gives bit-identical states."""
+def test_batch_matches_single(gpu_ctx, problems):
+    """One launch over many trackers (another launch shape) gives the states of single solves, bit for bit."""
     kf, wins = problems["davis240c"]
     H, W = kf["H"], kf["W"]
-    n = 40  # > 148/8: forces a smaller cluster than the single-problem launch
+    n = 40
     fr = edsgpu.Frames(gpu_ctx, H, W, n)
     E = len(wins[0]["x"])
     x = np.concatenate([wins[i % 2]["x"] for i in range(n)]); y = np.concatenate([wins[i % 2]["y"] for i in range(n)])
@@ -267,52 +267,51 @@ def test_batch_matches_single_and_is_independent_of_cluster_size(gpu_ctx, proble
 
 
 def test_results_do_not_depend_on_launch_shape(gpu_ctx, problems, monkeypatch):
-    """Cluster width (CTAs per cluster) and the number of problems a cluster keeps in flight are scheduling
-    choices: every combination must give bit-identical states, iteration counts and next loss parameters.
-    (EDSGPU_CLUSTER / EDSGPU_INFLIGHT are the library's tuning overrides, read when a batch is created.)"""
+    """How many evaluator CTAs sweep the residual blocks, how many leader CTAs (16 problems in flight each) run the LM loops
+    and how many SMs are left to other streams are scheduling choices: every combination must give bit-identical states,
+    iteration counts and next loss parameters -- including shapes where problems queue up behind a single leader warp and
+    where one evaluator CTA serves every problem.  (EDSGPU_EVAL_CTAS / EDSGPU_LEADER_CTAS / EDSGPU_RESERVE_SMS are the
+    library's tuning overrides, read when a batch is created.)"""
     kf, wins = problems["davis240c"]
-    H, W, n = kf["H"], kf["W"], 7
+    H, W, n = kf["H"], kf["W"], 21
     fr = edsgpu.Frames(gpu_ctx, H, W, n)
     E = len(wins[0]["x"])
     ev = [np.concatenate([wins[i % 2][k] for i in range(n)]) for k in ("x", "y", "pol")]
     edsgpu.event_frames_batch(gpu_ctx, fr, 0, n, *ev, E)
     kfd = edsgpu.KeyFrame(gpu_ctx, kf, 8)
 
-    def run():
+    def run(repeat=1):
         trs = [edsgpu.Tracker(gpu_ctx, num_blocks=8, max_iterations=10 + (i % 3)) for i in range(n)]  # problems finish at different times
-        for i, t in enumerate(trs):
-            x0 = wins[i % 2]["x_init"]
-            t.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
         b = edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * n, fr, 0)
-        b.optimize()
+        for _ in range(repeat):  # the queue counters of a batch run on across its launches
+            for i, t in enumerate(trs):
+                x0 = wins[i % 2]["x_init"]
+                t.set_state(x0[:3], x0[3:7], x0[7:], 0.05)
+            b.optimize()
         states, infos = b.gather()
+        shape = b.launch_shape()
         b.close()
         for t in trs:
             t.close()
-        return states, [(i["iterations"], i["evaluations"], i["termination"], i["usable"]) for i in infos]
+        return states, [(i["iterations"], i["evaluations"], i["termination"], i["usable"]) for i in infos], shape
 
-    monkeypatch.delenv("EDSGPU_CLUSTER", raising=False)
-    monkeypatch.delenv("EDSGPU_INFLIGHT", raising=False)
-    base_states, base_infos = run()
-    trs = [edsgpu.Tracker(gpu_ctx, num_blocks=8) for _ in range(n)]
-    b = edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * n, fr, 0)
-    clusters, ctas, inflight = b.launch_shape()       # 7 problems on an empty device: one cluster of 8 CTAs each
-    assert (clusters, ctas, inflight) == (7, 8, 1)
-    monkeypatch.setenv("EDSGPU_CLUSTER", "2"); monkeypatch.setenv("EDSGPU_INFLIGHT", "2")
-    b2 = edsgpu.TrackerBatch(gpu_ctx, trs, [kfd] * n, fr, 0)
-    assert b2.launch_shape() == (4, 2, 2)
-    b.close(); b2.close()
-    for t in trs:
-        t.close()
-    for csize in (1, 2, 4, 8):
-        for inflight in (1, 2, 3, 4):
-            if inflight > csize:
-                continue
-            monkeypatch.setenv("EDSGPU_CLUSTER", str(csize))
-            monkeypatch.setenv("EDSGPU_INFLIGHT", str(inflight))
-            states, infos = run()
-            assert np.array_equal(states, base_states), (csize, inflight)
-            assert infos == base_infos, (csize, inflight)
+    for k in ("EDSGPU_EVAL_CTAS", "EDSGPU_LEADER_CTAS", "EDSGPU_RESERVE_SMS"):
+        monkeypatch.delenv(k, raising=False)
+    base_states, base_infos, shape = run()
+    assert shape[1] == 2 and shape[2] == n and 1 <= shape[0] <= 8 * n  # 21 problems: two leader CTAs, all in flight
+    for evals, leads, reserve, repeat in ((1, 1, 0, 1), (2, 1, 0, 3), (7, 2, 0, 1), (64, 4, 0, 2), (0, 0, 40, 1), (200, 0, 0, 1)):
+        for k, v in (("EDSGPU_EVAL_CTAS", evals), ("EDSGPU_LEADER_CTAS", leads), ("EDSGPU_RESERVE_SMS", reserve)):
+            if v:
+                monkeypatch.setenv(k, str(v))
+            else:
+                monkeypatch.delenv(k, raising=False)
+        states, infos, shape = run(repeat)
+        assert np.array_equal(states, base_states), (evals, leads, reserve)
+        assert infos == base_infos, (evals, leads, reserve)
+        if evals:
+            assert shape[0] == evals
+        if leads:
+            assert shape[1] == leads and shape[2] == min(n, 16 * leads)
     kfd.close(); fr.close()
 
 

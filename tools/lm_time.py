@@ -73,13 +73,14 @@ def main():
         n = max(t[2], 1)
         print("  leader warps: %d steps, per step [us]: work %.2f  waiting for results %.2f" % (n, t[0] / n / 1e3, t[1] / n / 1e3))
         m = max(t[5], 1)
-        print("  last CTA of each cluster, per visit [us]: consumer work %.2f wait %.2f | producer 0 work %.2f wait %.2f  (%d visits)" % (
+        print("  last evaluator CTA, per task [us]: consumer 0 work %.2f wait-for-task %.2f | producer 0 work %.2f wait-for-task %.2f  (%d tasks)" % (
             t[3] / m / 1e3, t[4] / m / 1e3, t[13] / m / 1e3, t[14] / m / 1e3, m))
-        print("  producer 6 work %.2f, last producer work %.2f, consumer 1 work %.2f | consumer 0 wait-full %.0f cycles/batch, producers wait-empty %.0f cycles/batch" % (
-            t[21] / m / 1e3, t[20] / m / 1e3, t[22] / m / 1e3, t[16] / max(t[17], 1), t[18] / max(t[19], 1)))
+        print("  consumer 0 wait-full %.0f cycles/batch, producers wait-empty %.0f cycles/batch, control warp fetch %.2f us/task" % (
+            t[16] / max(t[17], 1), t[18] / max(t[19], 1), t[20] / max(t[21], 1) / 1e3))
         k = max(t[10], 1)
         print("  leader step parts [us]: tree %.2f  decide %.2f  solve %.2f  plus %.2f  publish %.2f (steps %d)" % (
             t[6] / k / 1e3, t[7] / k / 1e3, t[8] / k / 1e3, t[9] / k / 1e3, t[15] / k / 1e3, k))
+        print("  decide parts [us]: accept test %.2f  load rows %.2f  projection %.2f  scaling+stores %.2f  gradient norm %.2f" % tuple(t[22:27] / k / 1e3))
 
 
 if __name__ == "__main__":

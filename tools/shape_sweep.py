@@ -11,11 +11,11 @@ for S in (24, 48, 70, 100):
     ev = [np.tile(w[k], S) for k in ("x", "y", "pol")]
     edsgpu.event_frames_batch(ctx, fr, 0, S, *ev, E)
     res = []
-    for c, k in ((0, 0), (8, 1), (8, 2), (8, 3), (8, 4), (4, 1), (4, 2), (4, 3), (4, 4), (2, 1), (2, 2)):
+    for c, k in ((0, 0), (144, 4), (140, 8), (128, 4), (112, 4), (96, 4), (64, 4)):  # (evaluator CTAs, leader CTAs)
         if c:
-            os.environ["EDSGPU_CLUSTER"] = str(c); os.environ["EDSGPU_INFLIGHT"] = str(k)
+            os.environ["EDSGPU_EVAL_CTAS"] = str(c); os.environ["EDSGPU_LEADER_CTAS"] = str(k)
         else:
-            os.environ.pop("EDSGPU_CLUSTER", None); os.environ.pop("EDSGPU_INFLIGHT", None)
+            os.environ.pop("EDSGPU_EVAL_CTAS", None); os.environ.pop("EDSGPU_LEADER_CTAS", None)
         trs = [edsgpu.Tracker(ctx, num_blocks=8, max_iterations=30) for i in range(S)]
         b = edsgpu.TrackerBatch(ctx, trs, [kfd] * S, fr, 0)
         ts = []
