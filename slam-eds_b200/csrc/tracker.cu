@@ -32,7 +32,10 @@
 
 namespace {
 
-constexpr int TRK_THREADS = 512;  // one CTA per SM
+#ifndef EDS_TRK_THREADS
+#define EDS_TRK_THREADS 512
+#endif
+constexpr int TRK_THREADS = EDS_TRK_THREADS;  // one CTA per SM
 constexpr int TRK_WARPS = TRK_THREADS / 32;
 constexpr int JLD = 20;         // floats per point row in shared memory (80 B: conflict-free 128-bit access)
 #ifndef EDS_N_CONS
@@ -53,7 +56,7 @@ constexpr int MAX_BLOCKS = 16;  // residual blocks per problem (config.options.n
 #define EDS_MAILBOX 2
 #endif
 constexpr int MAILBOX = EDS_MAILBOX;       // tasks an evaluator CTA holds: the running one and the prefetched ones
-constexpr int LEAD_WARPS = TRK_WARPS;      // leader warps of a leader CTA, one problem in flight each
+constexpr int LEAD_WARPS = 16;             // leader warps of a leader CTA (its other warps leave at once), one problem in flight each
 constexpr int MAX_LEAD_CTAS = 8;
 constexpr double kEps = 1e-05;  // PhotometricError.hpp:200
 
@@ -182,6 +185,7 @@ struct EvalConst {
 struct ProblemWork {
     EvalConst ec;                      // evaluation point of the tasks in the queue
     double loss_a;                     // loss parameter of this solve (state[13] when the solve started)
+    double inv_norm;                   // 1 / L2 norm of the problem's event frame
     double slots[MAX_BLOCKS][NSLOT];   // block sums of the current evaluation, one writer (evaluator CTA) per block
     unsigned done;                     // +1 per finished EVAL task, +1 per evaluator warp of a finished FINAL task; never reset
     unsigned pad_[3];
@@ -199,6 +203,7 @@ struct TaskShared {
     ProblemDesc P;
     double* slots;     // ProblemWork::slots of the problem
     unsigned* done;    // ProblemWork::done
+    float inv_norm;    // 1 / L2 norm of the problem's event frame (EventFrame.cpp:360-383), applied at sample time
     int block, cmd;
 };
 
@@ -209,9 +214,9 @@ struct EvalShared {
     alignas(16) float ring[N_SLOTS][32][JLD];
     alignas(8) unsigned long long full_bar[N_SLOTS];
     alignas(8) unsigned long long empty_bar[N_SLOTS];
-    // block totals of consumer warps 1.., handed to consumer warp 0 (double-buffered by block)
-    float cons_part[2][N_CONS - 1][96];
-    double cons_s[2][N_CONS - 1];
+    // block totals of the consumer warps, added up by one of them in turn (double-buffered by block)
+    float cons_part[2][N_CONS][96];
+    double cons_s[2][N_CONS];
     // mailbox hand-over between the control warp and the evaluator warps
     alignas(8) unsigned long long task_full[MAILBOX];   // control warp -> evaluators: task[slot] is complete (1 arrival)
     alignas(8) unsigned long long task_empty[MAILBOX];  // evaluators -> control warp: every evaluator warp is done with task[slot]
@@ -239,6 +244,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -413,6 +421,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #endif
     } while (!ok);
 }
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {  // non-blocking
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
 
 // halving butterfly: 2*HALF per-lane values -> HALF, lanes with bit OFFSET keep the upper half
 template <int HALF, int OFFSET>
@@ -469,15 +485,27 @@ __device__ __forceinline__ int reduce96_base(unsigned lane) {
     return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
 }
 
-// One evaluator CTA evaluates ONE residual block (a task) with the constants in ts.ec and stores
-// [rho' * JtJ (78) | rho' * Jtr (12) | 0.5 rho(s) | s] into the problem's slot of that block (global memory).
-//
-// Warp-specialised: producer warps sweep the points 32 at a time (residual + analytic Jacobian row
-// -> shared-memory ring slot, mbarrier "full"), consumer warps own the outer-product accumulators
-// (90 fp32 registers per lane) and drain the ring (mbarrier "empty").  No CTA-wide barrier inside
-// the sweep; 512 threads at <= 128 registers per thread = one CTA per SM.  `batch_counter` numbers the batches the CTA
-// has processed since the kernel started, so that both sides derive slot and phase parity without talking to each other;
-// it runs on across tasks: the producers may be a task ahead of the consumers.
+// ------------------------------------------------------------------------------------------
+// evaluator CTA: producer warps -> ring -> consumer warps
+// ------------------------------------------------------------------------------------------
+// A task is ONE residual block of one problem at one evaluation point.  The CTA's tasks arrive through the mailbox in
+// an order every evaluator warp follows; the batches (32 points) of consecutive EVAL tasks carry one running number g,
+// from which both sides derive ring slot and phase without talking to each other:
+//   producers  sweep the points (residual + analytic Jacobian row -> ring slot g mod N_SLOTS, mbarrier "full").  Warp p
+//              takes the batches g = p (mod N_PROD) and treats the tasks as ONE stream: its three-stage software
+//              pipeline (3-D points in flight | fp64 geometry + texture gathers in flight | finish + hand over) runs
+//              across task boundaries whenever the next task is already in the mailbox, so a block of only ~3 batches
+//              per warp does not pay the pipeline fill for every task.
+//   consumers  own the outer-product accumulators (90 fp32 registers per lane): consumer c takes the batches
+//              j = c (mod N_CONS) of the block (a fixed summation order), the block ends with a halving warp butterfly,
+//              one of them (in turn) adds the three partial sums in index order, applies the per-block loss and stores
+//              [rho' * JtJ (78) | rho' * Jtr (12) | 0.5 rho(s) | s] into the problem's slot of that block, then bumps
+//              the counter the problem's leader polls.
+// The ring has a whole number of slots per producer warp, so that the successive occupants of a slot always belong to
+// the SAME producer: it passes through every "empty" wait of its slots in order and can never test a parity that is two
+// phases stale.  The mirror image on the "full" side: the successive occupants of a slot within a block are drained by
+// the same consumer (N_SLOTS is a multiple of N_CONS), and the consumers' end-of-block barrier keeps them within one
+// block of each other.
 struct Roles {
     int pidx;        // producer index of this warp, -1 if not a producer
     int cidx;        // consumer index of this warp, -1 if not a consumer
@@ -485,179 +513,221 @@ struct Roles {
 __device__ __forceinline__ Roles make_roles() {
     const int warp = threadIdx.x >> 5;
     Roles r;
+    static_assert(MAILBOX >= 2, "the evaluate entry needs two mailbox slots");
     static_assert(N_CONS >= 2 && N_CONS <= 4, "consumer warps");
+    static_assert(N_SLOTS % N_CONS == 0, "ring slots per CTA must be a multiple of the consumer warps");
     r.pidx = warp < N_PROD ? warp : -1;
     r.cidx = (warp >= N_PROD && warp < N_PROD + N_CONS) ? warp - N_PROD : -1;
     return r;
 }
 
-// returns (to every lane of consumer warp 0) the value of the task's completion counter before this task was added; 0 elsewhere
-template <bool RES_ONLY>
-__device__ unsigned cta_evaluate(TaskShared& ps, EvalShared& sh, const Roles& role, bool write_residuals, unsigned& batch_counter,
-                                 unsigned& block_counter) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const ProblemDesc& P = ps.P;
-    const KfDev& kf = P.kf;
-    const EvalConst& ec = ps.ec;
-    const float inv_norm = (float)P.norms[1];
-    const double loss_a = ps.loss_a;
-    const int ne = kf.ne;
-    const int b = ps.block;
-    const float* bc = ec.blk[b];
-    const int start = b * ne;
-    const int n = ne + ((b + 1 == kf.B) ? (kf.N - (b + 1) * ne) : 0);  // the last block also takes the remainder, Tracker.cpp:178-190
-    const int nb = (n + 31) >> 5;                                      // batches of this block
-    // The ring has a whole number of slots per producer warp, so that batch g and batch g + n_slots -- the
-    // successive occupants of a slot -- always belong to the SAME producer.  That warp passes through every
-    // "empty" wait of its slots in order and can never be a whole lap ahead of the barrier's phase (with slots shared
-    // between producers a fast warp could test a parity that is two phases stale and overwrite an unconsumed batch).
-    constexpr unsigned n_slots = (unsigned)N_SLOTS;
-    // The mirror image on the "full" side: the successive occupants of a slot must be drained by the SAME consumer warp
-    // (it takes its batches in order, so it cannot test a stale parity either); batch g goes to consumer g mod N_CONS,
-    // hence the ring size must be a multiple of N_CONS.
-    static_assert(n_slots % N_CONS == 0, "ring slots per CTA must be a multiple of the consumer warps");
-    // The texture handle is read from shared memory, which the compiler cannot prove warp-uniform: it
-    // would wrap every fetch in a loop over the distinct handles of the warp.  A warp-wide OR leaves
-    // the value unchanged and lands in a uniform register.
-    const cudaTextureObject_t frame = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(P.frame >> 32)) << 32) |
-                                      (unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)P.frame);
-    if constexpr (RES_ONLY) {
-        // residual write-back only (Tracker.cpp:223-230): no Jacobian, no reduction
-        if (role.pidx >= 0 || role.cidx >= 0) {
-            for (int i = tid; i < n; i += 32 * N_EVAL_WARPS) {
-                float r;
-                eval_point<false>(kf, ec, bc, frame, inv_norm, start + i, nullptr, r);
-                P.residuals[start + i] = r;
+// points [start, start + n) and batches of residual block b (the last block also takes the remainder, Tracker.cpp:178-190)
+__device__ __forceinline__ void block_extent(const KfDev& kf, int b, int& start, int& n, int& nb) {
+    start = b * kf.ne;
+    n = kf.ne + ((b + 1 == kf.B) ? (kf.N - (b + 1) * kf.ne) : 0);
+    nb = (n + 31) >> 5;
+}
+
+// the texture handle is read from shared memory, which the compiler cannot prove warp-uniform: it would wrap every fetch
+// in a loop over the distinct handles of the warp.  A warp-wide OR leaves the value unchanged and lands in a uniform register.
+__device__ __forceinline__ cudaTextureObject_t uniform_handle(cudaTextureObject_t h) {
+    return ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(h >> 32)) << 32) | (unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)h);
+}
+
+// residual write-back of a FINAL task (Tracker.cpp:223-230): no Jacobian, no reduction; every evaluator warp takes a
+// slice and reports on its own (the leader waits for N_EVAL_WARPS arrivals per block)
+__device__ void final_slice(const TaskShared& ts) {
+    const ProblemDesc& P = ts.P;
+    int start, n, nb;
+    block_extent(P.kf, ts.block, start, n, nb);
+    const cudaTextureObject_t frame = uniform_handle(P.frame);
+    const float* bc = ts.ec.blk[ts.block];
+    for (int i = threadIdx.x; i < n; i += 32 * N_EVAL_WARPS) {
+        float r;
+        eval_point<false>(P.kf, ts.ec, bc, frame, ts.inv_norm, start + i, nullptr, r);
+        P.residuals[start + i] = r;
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) red_release_add(ts.done, 1u);
+}
+
+__device__ void producer_warp_main(EvalShared& sh, const int pidx) {
+    const int lane = threadIdx.x & 31;
+    // ---- cursor over this warp's batches of the task stream ----
+    struct Cursor { unsigned ord, base; int nb, t, start, n; bool known; } cur = {0u, 0u, 0, 0, 0, 0, false};
+    struct Ref { unsigned ord, g; int first, count; };  // task ordinal (mailbox slot = ord mod MAILBOX), running batch number, first point, points
+    enum { GOT_BATCH, GOT_NONE, GOT_SPECIAL };
+    unsigned released = 0;  // tasks [0, released) have been given back to the control warp by this warp
+    auto release_upto = [&](unsigned ord) {
+        __syncwarp();
+        for (; released < ord; ++released)
+            if (lane == 0) mbar_arrive(&sh.task_empty[released % MAILBOX]);
+    };
+    auto advance = [&](bool blocking, Ref& r) -> int {
+        for (;;) {
+            const unsigned slot = cur.ord % MAILBOX;
+            if (!cur.known) {
+                const unsigned parity = (cur.ord / MAILBOX) & 1u;
+                if (blocking) mbar_wait(&sh.task_full[slot], parity, 3);
+                else if (!mbar_test(&sh.task_full[slot], parity)) return GOT_NONE;
+                const TaskShared& ts = sh.task[slot];
+                if (ts.cmd != CMD_EVAL) return GOT_SPECIAL;
+                block_extent(ts.P.kf, ts.block, cur.start, cur.n, cur.nb);
+                cur.t = (pidx + N_PROD - (int)(cur.base % (unsigned)N_PROD)) % N_PROD;  // this warp's batches have g = pidx (mod N_PROD)
+                cur.known = true;
             }
-            // every evaluator warp reports on its own: the leader waits for N_EVAL_WARPS arrivals per block
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) atomicAdd(ps.done, 1u);
+            if (cur.t < cur.nb) {
+                r.ord = cur.ord; r.g = cur.base + (unsigned)cur.t;
+                r.first = cur.start + (cur.t << 5); r.count = min(32, cur.n - (cur.t << 5));
+                cur.t += N_PROD;
+                return GOT_BATCH;
+            }
+            cur.base += (unsigned)cur.nb; cur.ord++; cur.known = false;  // nothing (left) for this warp in the task
+            // A blocking look-up runs with an empty pipeline: whatever the cursor passes is finished for this warp and must
+            // be given back at once -- the control warp cannot fetch the task this warp is about to wait for before
+            // every warp has released the mailbox slot it goes into.
+            if (blocking) release_upto(cur.ord);
         }
-        return 0;
-    } else {
-        if (role.pidx >= 0) {
-            // ---------------- producer ----------------
-            // Warp p takes the batches t = t0 + k N_PROD of the block, t0 chosen from the running number so that uneven
-            // shares even out over consecutive tasks.  Three pipeline stages per warp:
-            //   A(k+2)  3-D points of the batch after next: loads in flight
-            //   B(k+1)  fp64 geometry of the next batch, then its four texture gathers + gradient record in flight
-            //   C(k)    finish the current batch (its gathers were issued a whole iteration ago) and hand it over
-            struct Stage { Taps T; float4 g4; float2 dw; PointGeo G; int idx; bool valid; };
-            const PointGeo G0 = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            const Kp kp0 = {0.0, 0.0, 1.0};
-            auto locate = [&](int t, int& idx) -> bool {
-                const int i = (t << 5) + lane;
-                idx = start + i;
-                return (t < nb) && (i < n);
-            };
-            auto stage_b = [&](Stage& s, const Kp& kp) {
-                s.G = G0;
-                s.g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                s.dw = make_float2(0.f, 0.f);
-                if (s.valid) {
-                    point_geometry(kf, ec, kp, s.G);
-                    s.g4 = __ldg(&kf.gxy[s.idx]);
-                    s.dw = __ldg(&kf.dw[s.idx]);
-                }
-                s.T = fetch_taps(frame, s.G.col, s.G.row);
-            };
-            int t = (role.pidx + N_PROD - (int)(batch_counter % (unsigned)N_PROD)) % N_PROD;
-            unsigned slot, phase;
-            {
-                const unsigned g0 = batch_counter + (unsigned)t;
-                slot = g0 % n_slots;
-                phase = (g0 / n_slots) & 1u;
-            }
-            auto stage_c = [&](const Stage& s) {
-                float J[12], r = 0.f;
-                if (s.valid) {
-                    point_finish<true>(kf, ec, bc, inv_norm, s.G, s.T, s.g4, s.dw, J, r);
-                    if (write_residuals) {
-                        P.residuals[s.idx] = r;
-                        if (P.jac_out) {
-#pragma unroll
-                            for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * s.idx + k] = J[k];
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 12; ++k) J[k] = 0.f;
-                }
-#ifdef EDS_TIMING
-                const long long te0 = clock64();
-#endif
-                mbar_wait(&sh.empty_bar[slot], phase ^ 1u, 1);
-#ifdef EDS_TIMING
-                if (lane == 0 && g_timing_cta == (int)blockIdx.x) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
-#endif
-                float4* dst = reinterpret_cast<float4*>(&sh.ring[slot][lane][0]);
-                dst[0] = make_float4(J[0], J[1], J[2], J[3]);
-                dst[1] = make_float4(J[4], J[5], J[6], J[7]);
-                dst[2] = make_float4(J[8], J[9], J[10], J[11]);
-                dst[3] = make_float4(r, 0.f, 0.f, 0.f);
-                __syncwarp();  // all 32 rows are written: one elected arrival publishes the slot
-                if (lane == 0) mbar_arrive(&sh.full_bar[slot]);
-                slot += (unsigned)N_PROD;
-                if (slot >= n_slots) { slot -= n_slots; phase ^= 1u; }
-            };
-            // one pipeline step: `cur` holds batch t with its gathers in flight, `nxt` receives batch t + N_PROD,
-            // kp holds the 3-D points of batch t + N_PROD and is refilled with those of batch t + 2 N_PROD
-            auto step = [&](Stage& cur, Stage& nxt, Kp& kp) {
-                const Kp kpb = kp;
-                int idx_a;
-                const bool valid_a = locate(t + 2 * N_PROD, idx_a);
-                kp = kp0;
-                if (valid_a) kp = load_kp(kf, idx_a);
-                stage_b(nxt, kpb);
-                stage_c(cur);
-                cur.idx = idx_a; cur.valid = valid_a;  // the batch after next becomes the next one
-                t += N_PROD;
-            };
-            if (t < nb) {
-                Stage s0, s1;
-                Kp kp;
-                s0.valid = locate(t, s0.idx);
-                stage_b(s0, s0.valid ? load_kp(kf, s0.idx) : kp0);
-                s1.valid = locate(t + N_PROD, s1.idx);
-                kp = s1.valid ? load_kp(kf, s1.idx) : kp0;
-                for (;;) {
-                    step(s0, s1, kp);
-                    if (t >= nb) break;
-                    step(s1, s0, kp);
-                    if (t >= nb) break;
-                }
-            }
-            batch_counter += (unsigned)nb;
-            block_counter++;
-            return 0;
+    };
+    // ---- pipeline stages ----
+    struct Stage { Taps T; float4 g4; float2 dw; PointGeo G; Ref ref; bool present; };
+    const PointGeo G0 = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const Kp kp0 = {0.0, 0.0, 1.0};
+    auto stage_a = [&](const Ref& r) -> Kp {  // 3-D points in flight
+        return (lane < r.count) ? load_kp(sh.task[r.ord % MAILBOX].P.kf, r.first + lane) : kp0;
+    };
+    auto stage_b = [&](Stage& s, const Kp& kp) {  // geometry, then gathers + gradient record in flight
+        const TaskShared& ts = sh.task[s.ref.ord % MAILBOX];
+        const KfDev& kf = ts.P.kf;
+        s.G = G0;
+        s.g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        s.dw = make_float2(0.f, 0.f);
+        if (lane < s.ref.count) {
+            point_geometry(kf, ts.ec, kp, s.G);
+            s.g4 = __ldg(&kf.gxy[s.ref.first + lane]);
+            s.dw = __ldg(&kf.dw[s.ref.first + lane]);
         }
-        unsigned before = 0;
-        if (role.cidx >= 0) {
-            // ---------------- consumers: own the block's sums (warp c the batches whose running number is c mod N_CONS,
-            // i.e. the batches j = c0 + k N_CONS of the block), warp 0 applies the loss and publishes the slot ----------
+        s.T = fetch_taps(uniform_handle(ts.P.frame), s.G.col, s.G.row);
+    };
+    auto stage_c = [&](const Stage& s) {  // finish + hand over
+        const TaskShared& ts = sh.task[s.ref.ord % MAILBOX];
+        const ProblemDesc& P = ts.P;
+        if (s.ref.ord > released) release_upto(s.ref.ord);  // every batch of the earlier tasks has been handed over
+        float J[12], r = 0.f;
+        if (lane < s.ref.count) {
+            point_finish<true>(P.kf, ts.ec, ts.ec.blk[ts.block], ts.inv_norm, s.G, s.T, s.g4, s.dw, J, r);
+            if (P.eval_only) {  // parity/debug entry: residuals and Jacobian rows written out
+                const int idx = s.ref.first + lane;
+                P.residuals[idx] = r;
+                if (P.jac_out) {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * idx + k] = J[k];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) J[k] = 0.f;
+        }
+        const unsigned slot = s.ref.g % (unsigned)N_SLOTS, phase = (s.ref.g / (unsigned)N_SLOTS) & 1u;
+#ifdef EDS_TIMING
+        const long long te0 = clock64();
+#endif
+        mbar_wait(&sh.empty_bar[slot], phase ^ 1u, 1);
+#ifdef EDS_TIMING
+        if (lane == 0 && g_timing_cta == (int)blockIdx.x) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
+#endif
+        float4* dst = reinterpret_cast<float4*>(&sh.ring[slot][lane][0]);
+        dst[0] = make_float4(J[0], J[1], J[2], J[3]);
+        dst[1] = make_float4(J[4], J[5], J[6], J[7]);
+        dst[2] = make_float4(J[8], J[9], J[10], J[11]);
+        dst[3] = make_float4(r, 0.f, 0.f, 0.f);
+        __syncwarp();  // all 32 rows are written: one elected arrival publishes the slot
+        if (lane == 0) mbar_arrive(&sh.full_bar[slot]);
+    };
+    // one pipeline step: `cur_s` holds a batch with its gathers in flight, `nxt_s` (its reference already set) receives the
+    // geometry of the following batch whose 3-D points are in kp, and the batch after that is looked up without
+    // blocking: if its task has not arrived yet the pipeline simply runs dry
+    auto step = [&](Stage& cur_s, Stage& nxt_s, Kp& kp) {
+        const Kp kpb = kp;
+        Ref ra;
+        const bool got = advance(false, ra) == GOT_BATCH;
+        if (got) kp = stage_a(ra);
+        if (nxt_s.present) stage_b(nxt_s, kpb);
+        if (cur_s.present) stage_c(cur_s);
+        cur_s.present = got;  // the batch after next becomes the next one
+        cur_s.ref = ra;
+    };
+    for (;;) {
+        Stage s0, s1;
+        Kp kp = kp0;
+        const int got = advance(true, s0.ref);
+        if (got == GOT_SPECIAL) {  // the stream stops at a task that is not an evaluation: the pipeline is empty here
+            const TaskShared& ts = sh.task[cur.ord % MAILBOX];
+            const int cmd = ts.cmd;
+            release_upto(cur.ord);
+            if (cmd == CMD_FINAL) final_slice(ts);
+            cur.ord++;  // a special task has no batches: the running number stays
+            release_upto(cur.ord);
+            if (cmd == CMD_EXIT) return;
+            continue;
+        }
+        s0.present = true;
+        stage_b(s0, stage_a(s0.ref));
+        s1.present = advance(false, s1.ref) == GOT_BATCH;
+        if (s1.present) kp = stage_a(s1.ref);
+        // a stage may be absent (the look-ahead found nothing at that moment): the bubble travels through the pipeline,
+        // no batch the cursor has handed out is ever dropped
+        do {
+            step(s0, s1, kp);  // finishes s0, fills s1; s0 then describes the batch after s1
+            step(s1, s0, kp);
+        } while (s0.present || s1.present);
+        // ran dry (the look-ahead never skips a batch, it only stops early): everything before the cursor's task is handed over
+        release_upto(cur.ord);
+    }
+}
+
+__device__ void consumer_warp_main(EvalShared& sh, const int cidx) {
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0, block_counter = 0;  // running batch number, EVAL tasks seen
+#ifdef EDS_TIMING
+    unsigned long long t_wait = 0, t_work = 0, n_work = 0;
+#endif
+    for (unsigned ord = 0;; ++ord) {
+        const unsigned tslot = ord % MAILBOX;
+#ifdef EDS_TIMING
+        const unsigned long long t0 = gtime();
+#endif
+        mbar_wait(&sh.task_full[tslot], (ord / MAILBOX) & 1u, 3);
+#ifdef EDS_TIMING
+        const unsigned long long t1 = gtime();
+#endif
+        const TaskShared& ts = sh.task[tslot];
+        const int cmd = ts.cmd;
+        if (cmd == CMD_EXIT) break;
+        if (cmd == CMD_FINAL) {
+            final_slice(ts);
+        } else {
+            const ProblemDesc& P = ts.P;
+            int start, n, nb;
+            block_extent(P.kf, ts.block, start, n, nb);
             float acc[96];
 #pragma unroll
             for (int i = 0; i < 96; ++i) acc[i] = 0.f;
             double s_acc = 0.0;  // sum of r^2 in fp64 (the cost decides accept / reject and the tolerances)
-            // The summation order must not depend on what the CTA did before this task (results are bit-identical for
-            // every schedule): consumer c always takes batches j = c, c + N_CONS, ... of the block.  The ring slot of
-            // batch j is fixed by the running number, the consumer that drains it by j; both stay consistent because a
-            // block's batches only ever go to "the" consumer of j and tasks are drained strictly in order.
             unsigned slot, phase;
             {
-                const unsigned g0 = batch_counter + (unsigned)role.cidx;
-                slot = g0 % n_slots;
-                phase = (g0 / n_slots) & 1u;
+                const unsigned g0 = base + (unsigned)cidx;
+                slot = g0 % (unsigned)N_SLOTS;
+                phase = (g0 / (unsigned)N_SLOTS) & 1u;
             }
-            for (int j = role.cidx; j < nb; j += N_CONS, slot += N_CONS) {
-                if (slot >= n_slots) { slot -= n_slots; phase ^= 1u; }
+            for (int j = cidx; j < nb; j += N_CONS, slot += N_CONS) {
+                if (slot >= (unsigned)N_SLOTS) { slot -= (unsigned)N_SLOTS; phase ^= 1u; }
 #ifdef EDS_TIMING
                 const long long tw0 = clock64();
 #endif
                 mbar_wait(&sh.full_bar[slot], phase, 2);
 #ifdef EDS_TIMING
-                if (lane == 0 && g_timing_cta == (int)blockIdx.x && role.cidx == 0) { atomicAdd(&g_timing[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_timing[17], 1ull); }
+                if (lane == 0 && g_timing_cta == (int)blockIdx.x && cidx == 0) { atomicAdd(&g_timing[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_timing[17], 1ull); }
 #endif
                 float v[16];
                 ConsRows::load(sh.ring[slot], lane, v);
@@ -669,41 +739,76 @@ __device__ unsigned cta_evaluate(TaskShared& ps, EvalShared& sh, const Roles& ro
             reduce96(acc, lane);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
+            // every consumer leaves its block totals in shared memory; they take turns at adding them up (always in
+            // index order, so the sum does not depend on whose turn it is) and publishing the block
             const unsigned buf = block_counter & 1u;
-            if (role.cidx != 0) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) sh.cons_part[buf][role.cidx - 1][3 * lane + i] = acc[i];
-                if (lane == 0) sh.cons_s[buf][role.cidx - 1] = s_acc;
-                asm volatile("bar.sync 2, %0;" ::"n"(32 * N_CONS) : "memory");
-            } else {
-                asm volatile("bar.sync 2, %0;" ::"n"(32 * N_CONS) : "memory");
+            for (int i = 0; i < 3; ++i) sh.cons_part[buf][cidx][3 * lane + i] = acc[i];
+            if (lane == 0) sh.cons_s[buf][cidx] = s_acc;
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * N_CONS) : "memory");
+            if ((int)(block_counter % (unsigned)N_CONS) == cidx) {
+                float tot[3];
 #pragma unroll
-                for (int c = 0; c < N_CONS - 1; ++c) {  // fixed order: the sums do not depend on timing
+                for (int i = 0; i < 3; ++i) tot[i] = sh.cons_part[buf][0][3 * lane + i];
+                double s_tot = sh.cons_s[buf][0];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) acc[i] += sh.cons_part[buf][c][3 * lane + i];
-                    s_acc += sh.cons_s[buf][c];
+                for (int c = 1; c < N_CONS; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) tot[i] += sh.cons_part[buf][c][3 * lane + i];
+                    s_tot += sh.cons_s[buf][c];
                 }
                 double rho0, rho1;
-                loss_eval(P.loss_type, loss_a, s_acc, &rho0, &rho1);
-                const int base = reduce96_base(lane);
-                double* dst = ps.slots + b * NSLOT;
+                loss_eval(P.loss_type, ts.loss_a, s_tot, &rho0, &rho1);
+                const int base_e = reduce96_base(lane);
+                double* dst = ts.slots + ts.block * NSLOT;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const int e = base + i;
-                    if (e < 90) dst[ConsRows::slot(e)] = rho1 * (double)acc[i];
+                    const int e = base_e + i;
+                    if (e < 90) dst[ConsRows::slot(e)] = rho1 * (double)tot[i];
                 }
-                if (lane == 0) { dst[90] = 0.5 * rho0; dst[91] = s_acc; }
-                // the block's sums are in global memory: order them before the count the leader polls
-                __threadfence();
+                if (lane == 0) { dst[90] = 0.5 * rho0; dst[91] = s_tot; }
+                // The lanes' stores happen before the warp barrier, the barrier before the elected lane's release: the
+                // release is cumulative over what the lane has synchronised with, so the leader that acquires the count
+                // sees every lane's sums (the CUTLASS semaphore pattern: barrier, then one thread's red.release.gpu).
                 __syncwarp();
-                if (lane == 0) before = atomicAdd(ps.done, 1u);
-                before = __shfl_sync(0xffffffffu, before, 0);
+                if (!P.eval_only) {
+                    if (lane == 0) red_release_add(ts.done, 1u);
+                } else {
+                    // parity/debug entry (track_eval_kernel): the block that finishes last sums the blocks
+                    unsigned before = 0;
+                    if (lane == 0) { __threadfence(); before = atomicAdd(ts.done, 1u); }
+                    before = __shfl_sync(0xffffffffu, before, 0);
+                    if (before == (unsigned)(P.kf.B - 1) && P.eval_out) {
+                        __threadfence();
+                        const int B = P.kf.B;
+                        for (int e = lane; e < 91; e += 32) {
+                            double v = 0.0;
+                            for (int b = 0; b < B; ++b) v += __ldcg(&ts.slots[b * NSLOT + e]);
+                            if (e == 90) P.eval_out[0] = v;
+                            else if (e >= 78) P.eval_out[1 + 144 + (e - 78)] = v;
+                            else {
+                                int a = 0, rem = e;
+                                while (rem >= 12 - a) { rem -= 12 - a; ++a; }
+                                const int c2 = a + rem;
+                                P.eval_out[1 + 12 * a + c2] = v;
+                                P.eval_out[1 + 12 * c2 + a] = v;
+                            }
+                        }
+                    }
+                }
             }
+            base += (unsigned)nb;
+            block_counter++;
         }
-        batch_counter += (unsigned)nb;
-        block_counter++;
-        return before;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.task_empty[tslot]);
+#ifdef EDS_TIMING
+        t_wait += t1 - t0; t_work += gtime() - t1; n_work++;
+#endif
     }
+#ifdef EDS_TIMING
+    if (lane == 0 && g_timing_cta == (int)blockIdx.x && cidx == 0) { atomicAdd(&g_timing[3], t_work); atomicAdd(&g_timing[4], t_wait); atomicAdd(&g_timing[5], n_work); }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1088,6 +1193,7 @@ __device__ void leader_start(LeaderProblem& lp, const LeaderLink& L) {
         lm.termination = EDSGPU_TERM_NO_CONVERGENCE; lm.phase = PHASE_INIT;
         lm.x_cost = 0.0; lm.initial_cost = 0.0; lm.mcc = 0.0; lm.gmax = 0.0; lm.x_norm = 0.0;
         L.w->loss_a = lp.loss_a;
+        L.w->inv_norm = lp.P.norms[1];
     }
     __syncwarp();
     leader_publish(lp, L, lm.x, CMD_EVAL);
@@ -1228,20 +1334,31 @@ __device__ void control_warp_main(EvalShared& sh, const ProblemDesc* __restrict_
         const int pid = (int)(payload & 0xfffffu), block = (int)((payload >> 20) & 63u), cmd = (int)(payload >> 26);
         TaskShared& ts = sh.task[slot];
         if (cmd != CMD_EXIT) {
+            // one round trip: the descriptor (immutable during the launch) and the whole EvalConst the leader published
+            // before the queue entry (acquired above; read past the non-coherent L1)
             ProblemWork* w = work + pid;
             const int* src = reinterpret_cast<const int*>(&problems[pid]);
             int* dst = reinterpret_cast<int*>(&ts.P);
-            for (int k = lane; k < (int)(sizeof(ProblemDesc) / sizeof(int)); k += 32) dst[k] = __ldg(src + k);
-            // published by the leader before the queue entry (acquired above): read past the non-coherent L1
-            const int B = __ldg(&problems[pid].kf.B);
-            const int nwords = (int)(offsetof(EvalConst, blk) / 4) + 8 * B;
             const int* es = reinterpret_cast<const int*>(&w->ec);
             int* ed = reinterpret_cast<int*>(&ts.ec);
-            for (int k = lane; k < nwords; k += 32) ed[k] = __ldcg(es + k);
+            constexpr int ND = (int)(sizeof(ProblemDesc) / sizeof(int)), NE = (int)(sizeof(EvalConst) / sizeof(int));
+            int dv[(ND + 31) / 32], evv[(NE + 31) / 32];
+#pragma unroll
+            for (int k = 0; k < (ND + 31) / 32; ++k) dv[k] = (lane + 32 * k < ND) ? __ldg(src + lane + 32 * k) : 0;
+#pragma unroll
+            for (int k = 0; k < (NE + 31) / 32; ++k) evv[k] = (lane + 32 * k < NE) ? __ldcg(es + lane + 32 * k) : 0;
+            const double loss_a = __ldcg(&w->loss_a);
+            const double inv_norm = __ldcg(&w->inv_norm);
+#pragma unroll
+            for (int k = 0; k < (ND + 31) / 32; ++k) if (lane + 32 * k < ND) dst[lane + 32 * k] = dv[k];
+#pragma unroll
+            for (int k = 0; k < (NE + 31) / 32; ++k) if (lane + 32 * k < NE) ed[lane + 32 * k] = evv[k];
+            __syncwarp();
             if (lane == 0) {
-                ts.loss_a = __ldcg(&w->loss_a);
+                ts.loss_a = loss_a;
                 ts.slots = &w->slots[0][0];
                 ts.done = &w->done;
+                ts.inv_norm = (float)inv_norm;
                 ts.block = block;
             }
         }
@@ -1268,6 +1385,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
     const int warp = threadIdx.x >> 5;
     if ((int)blockIdx.x < n_lead) {
         LeadShared& ls = *reinterpret_cast<LeadShared*>(smem_raw);
+        if (warp >= LEAD_WARPS) return;
         leader_warp_main(ls.prob[warp], problems, work, ctl, entries, mask, count, (int)blockIdx.x * LEAD_WARPS + warp, n_lead * LEAD_WARPS,
                          (int)gridDim.x - n_lead);
         return;
@@ -1279,37 +1397,8 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
         return;
     }
     const Roles role = make_roles();
-    const int lane = threadIdx.x & 31;
-    unsigned batch_counter = 0, block_counter = 0;  // same in every evaluator thread of the CTA
-#ifdef EDS_TIMING
-    unsigned long long t_wait = 0, t_work = 0, n_work = 0;
-#endif
-    for (unsigned i = 0;; ++i) {
-        const unsigned slot = i % MAILBOX, use = i / MAILBOX;
-#ifdef EDS_TIMING
-        const unsigned long long t0 = gtime();
-#endif
-        mbar_wait(&sh.task_full[slot], use & 1u, 3);
-#ifdef EDS_TIMING
-        const unsigned long long t1 = gtime();
-#endif
-        TaskShared& ts = sh.task[slot];
-        const int cmd = ts.cmd;
-        if (cmd == CMD_EXIT) break;
-        if (cmd == CMD_EVAL) cta_evaluate<false>(ts, sh, role, false, batch_counter, block_counter);
-        else cta_evaluate<true>(ts, sh, role, true, batch_counter, block_counter);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.task_empty[slot]);
-#ifdef EDS_TIMING
-        t_wait += t1 - t0; t_work += gtime() - t1; n_work++;
-#endif
-    }
-#ifdef EDS_TIMING
-    if (lane == 0 && g_timing_cta == (int)blockIdx.x) {
-        if (role.cidx == 0) { atomicAdd(&g_timing[3], t_work); atomicAdd(&g_timing[4], t_wait); atomicAdd(&g_timing[5], n_work); }
-        else if (role.pidx == 0) { atomicAdd(&g_timing[13], t_work); atomicAdd(&g_timing[14], t_wait); }
-    }
-#endif
+    if (role.pidx >= 0) producer_warp_main(sh, role.pidx);
+    else consumer_warp_main(sh, role.cidx);
 }
 
 // parity/debug entry (edsgpu_tracker_evaluate): one full evaluation at P.state, residuals and Jacobian rows written out,
@@ -1334,36 +1423,21 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_eval_kernel(const Proble
     if (tid == 0) {
         ts.loss_a = P.state[13];
         ts.slots = &work->slots[0][0];
-        ts.done = &work->done;
+        ts.done = &work->done;  // zeroed before the launch: the block that counts B - 1 before itself is the last one
+        ts.inv_norm = (float)P.norms[1];
         ts.block = (int)blockIdx.x;
         ts.cmd = CMD_EVAL;
+        sh.task[1].cmd = CMD_EXIT;  // the stream of this CTA: one evaluation, then the end
     }
     __syncthreads();
-    if (warp == CTRL_WARP) compute_eval_const(ts.ec, x_sh, A_sh, B, CMD_EVAL);
-    __syncthreads();
-    if (warp == CTRL_WARP) return;
+    if (warp == CTRL_WARP) {
+        compute_eval_const(ts.ec, x_sh, A_sh, B, CMD_EVAL);
+        if ((tid & 31) == 0) { mbar_arrive(&sh.task_full[0]); mbar_arrive(&sh.task_full[1]); }
+        return;
+    }
     const Roles role = make_roles();
-    unsigned batch_counter = 0, block_counter = 0;
-    const unsigned before = cta_evaluate<false>(ts, sh, role, true, batch_counter, block_counter);
-    if (role.cidx == 0 && before == (unsigned)(B - 1) && P.eval_out) {  // `done` was zeroed before the launch: this is the last block
-        __threadfence();
-        if ((tid & 31) == 0) {
-            double cost = 0.0;
-            for (int b = 0; b < B; ++b) cost += __ldcg(&work->slots[b][90]);
-            P.eval_out[0] = cost;
-            for (int a = 0; a < 12; ++a) {
-                double gs = 0.0;
-                for (int b = 0; b < B; ++b) gs += __ldcg(&work->slots[b][78 + a]);
-                P.eval_out[1 + 144 + a] = gs;
-                for (int c2 = a; c2 < 12; ++c2) {
-                    double h = 0.0;
-                    for (int b = 0; b < B; ++b) h += __ldcg(&work->slots[b][tri_index(a, c2)]);
-                    P.eval_out[1 + 12 * a + c2] = h;
-                    P.eval_out[1 + 12 * c2 + a] = h;
-                }
-            }
-        }
-    }
+    if (role.pidx >= 0) producer_warp_main(sh, role.pidx);
+    else consumer_warp_main(sh, role.cidx);
 }
 
 // ------------------------------------------------------------------------------------------

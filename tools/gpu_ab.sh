@@ -7,6 +7,6 @@ sizes=$1; shift
 for v in "$@"; do
   lib=$B/libedsgpu_$v.so; [ "$v" = product ] && lib=$PWD/slam-eds_b200/libedsgpu.so
   for S in $sizes; do
-    EDSGPU_LIBRARY=$lib timeout 120 python tools/lm_time.py $S 10 2>&1 | grep -v "^$" | tail -6
+    EDSGPU_LIBRARY=$lib timeout 40 python tools/lm_time.py $S 10 2>&1 | grep -v "^$" | tail -7 || echo "TIMEOUT $v $S"
   done
 done
