@@ -8,6 +8,7 @@ import pytest
 
 from oracle import oracle as O
 from edsgpu import synth
+import drift
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -248,3 +249,31 @@ def test_oracle_reproduces_golden(name):
     assert synth.quat_angle(so["x"][3:7], g["so_x"][3:7]) < 1e-7
     np.testing.assert_allclose(so["x"][:3], g["so_x"][:3], atol=1e-7)
     assert abs(so["next_loss_param"] - float(g["so_tau"])) < 1e-7
+
+
+# ------------------------------------------------------------------ where the pose gate is meaningful
+@pytest.mark.parametrize("config", ["gen3_vga", "gen4_hd"])
+def test_oracle_self_drift_bounds_the_pose_gate(config):
+    """BASELINE.md section 3 gates the converged pose at 1e-4 rad / 1e-4 x depth.  This test pins, on the oracle ALONE, where
+    that gate can be met by any implementation: perturbing the inputs by one ulp of double (or rounding them to the fp32 the
+    device stores), or switching between analytic and dual-number Jacobians, moves the oracle's own pose by
+      * <= 1e-6 rad / 1e-6 m at max_num_iterations = 20 (two orders below the gate), but
+      * more than the gate at max_num_iterations = 30 (measured 1.8e-4 rad / 3..4e-4 m on configs 2 and 3),
+    because the trust-region radius has passed 1e15 by then (every step accepted with gain ratio > 1, radius x3 per
+    iteration, Tracker.cpp:138-143 leaves Ceres' defaults) and the damping of the null velocity direction is below double
+    rounding.  tests/test_gpu_fullsize.py therefore gates 1e-4 strictly at 20 iterations and bounds the difference at 30 by
+    drift.DRIFT_FACTOR x this self-drift."""
+    scene, kf, wins = synth.make_problem(config, 3, 2)
+    w = wins[0]
+    frame = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])["frame"]
+    a20, t20, _, ref20 = drift.oracle_self_drift(kf, frame, w["x_init"], 20)
+    assert a20 <= 1e-6 and t20 <= 1e-6, (a20, t20)
+    assert ref20["info"]["final_radius"] < 1e15
+    a30, t30, detail, ref30 = drift.oracle_self_drift(kf, frame, w["x_init"], 30)
+    assert ref30["info"]["final_radius"] >= 1e15 and ref30["info"]["iterations"] == 30
+    assert a30 > drift.ANGLE_GATE / 4 or t30 > drift.DEPTH_GATE / 4, detail   # the strict gate has no headroom left here ...
+    assert a30 < 5e-3 and t30 < 5e-3 * synth.Z0, detail                         # ... yet the solution stays put at the 1e-3 level
+    # the cost moves too, but only at the 1e-4 level (measured 1.1e-4): the valley is flat along the drift direction
+    c = [O.tracker_solve(k2, f2, w["x_init"], num_blocks=8, max_iterations=30, threads=8)["info"]["final_cost"]
+         for _, k2, f2 in drift.perturbed_inputs(kf, frame)[:3]]
+    assert max(abs(v - ref30["info"]["final_cost"]) for v in c) < 5e-4 * ref30["info"]["final_cost"]
