@@ -1,19 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- tracking windows/s at 640x480 (BASELINE.json metric) on N B200s of one node.
 
-Workload (config.workload): BASELINE.json configs[1] -- Prophesee Gen3 640x480, 10 240 keyframe
-points, 50 000 events/window, B = 8 residual blocks, Huber (tau0 = 0.05, MAD-updated),
-max_num_iterations = 30, function_tolerance = 1e-6 -- as a batch of
-`--sequences` (default 64, configs[4]) independent sequences PER GPU.  One step = one event
-window of every sequence: event-frame construction + device-side LM solve + MAD, warm-started
-from the previous step (px,qx,vx,tau stay in HBM).  Sequences are independent, so ranks share
-nothing on the data path (scaling: weak); the states are gathered once at the end with NCCL.
+Workload (config.workload): BASELINE.json configs[4] = 64 independent sequences of configs[1] -- Prophesee Gen3 640x480,
+10 240 keyframe points, 50 000 events/window, B = 8 residual blocks, Huber (tau0 = 0.05, MAD-updated), max_num_iterations = 30,
+function_tolerance = 1e-6.  One step = one event window of every sequence: event-frame construction +
+device-side LM solve + MAD, warm-started from the previous window (px, qx, vx, tau stay in HBM).  Every sequence has its own
+scene and key frame and runs through WINDOWS consecutive windows of its own trajectory (then round again).
 
+  --scaling strong (default)  the 64 sequences are dealt round-robin to the N ranks; `weak` (64 per rank) is
+                              reported next to it as the `weak` object when N > 1
   value  device-resident inputs (events already in HBM), CUDA-event timed, max over ranks
-  e2e    the same step through the host-facing C ABI: events from pinned host memory every
-         step (H2D inside the timed region) and the 64x14 state records read back (D2H)
-  --impl reference   the CPU restatement of the reference path (oracle, dual-number Jacobians =
-         the cost structure of the Ceres autodiff functor) on the box's host cores.
+  e2e    the same step through the host-facing C ABI: events from pinned host memory every step (H2D inside the timed
+         region) and the state records read back (D2H)
+  config1 / config3 objects   the other two sensor shapes (240x180, 1280x720), same step, own roofline (N = 1 only)
+  --impl reference   the CPU restatement of the reference path (oracle, dual-number Jacobians = the cost structure of the
+         Ceres autodiff functor) on the box's host cores, warm-started and tau-carried like the GPU arm.
 """
 import argparse
 import json
@@ -22,6 +23,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ProcessPoolExecutor
 
 import numpy as np
 
@@ -34,22 +36,39 @@ CONFIG = "gen3_vga"
 NUM_BLOCKS = 8
 MAX_ITER = 30
 TAU0 = 0.05
-DISTINCT_SCENES = 8      # synthetic scenes generated per rank (sequences cycle through them)
-WINDOWS_PER_SCENE = 4    # distinct event windows per scene
+WINDOWS = 16             # consecutive windows generated per sequence of the headline workload
+SIDE_SCENES, SIDE_WINDOWS = 8, 4   # the config1 / config3 side measurements cycle through fewer distinct inputs
+RESERVE_SMS = 16         # SMs the batched solve leaves to the event-frame builds of the next window (other stream)
+PARITY_NOTE = ("pose gate 1e-4 rad / 1e-4 x depth met at <= 20 LM iterations; at this cap (30) GPU-vs-oracle differences are bounded by "
+               "4 x the oracle's own drift under 1-ulp input perturbations (tests/test_oracle_tracking.py, tests/test_gpu_fullsize.py)")
 
 
 def algorithmic_bytes_lm(N, H, W, B, evaluations):
-    """per LM Jacobian evaluation 24 N + min(64 N, 4 H W) + 364 B, + 4 N write-back."""
+    """per LM Jacobian evaluation 24 N + min(64 N, 4 H W) + 364 B (+ 4 N write-back per window, added by the caller)."""
     return evaluations * (24 * N + min(64 * N, 4 * H * W) + 364 * B)
 
 
-def make_data(rank, n_scenes=DISTINCT_SCENES, n_windows=WINDOWS_PER_SCENE):
+def algorithmic_bytes_ef(E, H, W):
+    """per window 16 E + 12 H W."""
+    return 16 * E + 12 * H * W
+
+
+def _make_sequence(args):
     from edsgpu import synth
-    data = []
-    for s in range(n_scenes):
-        scene, kf, wins = synth.make_problem(CONFIG, 100 * rank + s, n_windows)
-        data.append((kf, wins))
-    return data
+    config, seq, n_windows = args
+    scene, kf, wins = synth.make_problem(config, seq, n_windows)
+    return kf, wins
+
+
+def make_sequences(config, seq_ids, n_windows, procs=None):
+    """[(keyframe, windows)] for the given sequence ids (seed = 1234 + 1000 config_id + id), generated in parallel."""
+    seq_ids = list(seq_ids)
+    procs = procs or max(1, min(len(seq_ids), (os.cpu_count() or 1)))
+    jobs = [(config, int(s), n_windows) for s in seq_ids]
+    if procs == 1 or len(jobs) == 1:
+        return [_make_sequence(j) for j in jobs]
+    with ProcessPoolExecutor(max_workers=min(procs, len(jobs))) as ex:
+        return list(ex.map(_make_sequence, jobs))
 
 
 class ClockSampler:
@@ -95,28 +114,34 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def cpu_windows_per_s(data, n_windows, concurrent, threads_per_window, jacobian_mode=1):
-    """Times the oracle on `n_windows` windows of the workload: event frame + Ceres-style solve +
-    MAD, `concurrent` independent sequences at a time, `threads_per_window` workers each (the
-    reference parallelises over its B residual blocks, Tracker.cpp:138,178-195)."""
+def cpu_windows_per_s(data, windows_per_sequence, concurrent, threads_per_window, jacobian_mode=1):
+    """Times the oracle on `windows_per_sequence` consecutive windows of every sequence in `data`: event frame + Ceres-style
+    solve + MAD, warm-started from the previous window's state and tau exactly like the GPU arm, `concurrent` sequences at a
+    time, `threads_per_window` workers each (the reference parallelises over its B residual blocks, Tracker.cpp:138,178-195).
+    -> (windows/s, seconds, windows, mean LM iterations)"""
     from oracle import oracle as O
     O.lib()
-    jobs = []
-    for i in range(n_windows):
-        kf, wins = data[i % len(data)]
-        jobs.append((kf, wins[(i // len(data)) % len(wins)]))
+    iters = []
 
-    def run(job):
-        kf, w = job
-        ef = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])
-        O.tracker_solve(kf, ef["frame"], w["x_init"], num_blocks=NUM_BLOCKS, loss_type=1, loss_param=TAU0, max_iterations=MAX_ITER,
-                        function_tolerance=1e-6, jacobian_mode=jacobian_mode, threads=threads_per_window)
+    def run_sequence(kf, wins):
+        x, tau = wins[0]["x_init"].copy(), TAU0
+        for k in range(windows_per_sequence):
+            w = wins[k % len(wins)]
+            ef = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])
+            s = O.tracker_solve(kf, ef["frame"], x, num_blocks=NUM_BLOCKS, loss_type=1, loss_param=tau, max_iterations=MAX_ITER,
+                                function_tolerance=1e-6, jacobian_mode=jacobian_mode, threads=threads_per_window)
+            iters.append(s["info"]["iterations"])
+            if s["info"]["usable"]:  # Tracker.cpp:217-233
+                x, tau = s["x"], s["next_loss_param"]
 
-    run(jobs[0])  # warm (page in, build)
+    kf0, w0 = data[0]
+    O.tracker_solve(kf0, O.event_frame(w0[0]["x"], w0[0]["y"], w0[0]["pol"], w0[0]["ts"], kf0["H"], kf0["W"])["frame"], w0[0]["x_init"],
+                    num_blocks=NUM_BLOCKS, max_iterations=2, jacobian_mode=jacobian_mode, threads=threads_per_window)  # warm (page in)
+    iters.clear()
     t0 = time.perf_counter()
     if concurrent <= 1:
-        for j in jobs:
-            run(j)
+        for kf, wins in data:
+            run_sequence(kf, wins)
     else:
         nxt = [0]
         lock = threading.Lock()
@@ -126,9 +151,9 @@ def cpu_windows_per_s(data, n_windows, concurrent, threads_per_window, jacobian_
                 with lock:
                     k = nxt[0]
                     nxt[0] += 1
-                if k >= len(jobs):
+                if k >= len(data):
                     return
-                run(jobs[k])  # ctypes releases the GIL inside the oracle
+                run_sequence(*data[k])  # ctypes releases the GIL inside the oracle
 
         ths = [threading.Thread(target=worker) for _ in range(concurrent)]
         for t in ths:
@@ -136,38 +161,49 @@ def cpu_windows_per_s(data, n_windows, concurrent, threads_per_window, jacobian_
         for t in ths:
             t.join()
     dt = time.perf_counter() - t0
-    return n_windows / dt, dt
+    n = len(data) * windows_per_sequence
+    return n / dt, dt, n, float(np.mean(iters))
+
+
+def workload_string(c):
+    return "config2: Gen3 640x480, %d points, %d events/window, B=%d, Huber+MAD, max_iter %d" % (c["N"], c["E"], NUM_BLOCKS, MAX_ITER)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the reference itself cannot be
-    built here) on all host cores; rank 0 only."""
+    """--impl reference: the reference's CPU path (oracle port; the reference itself cannot be built here) on all host
+    cores; rank 0 only.  A step = `concurrent` sequences advancing by 2 consecutive windows each."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    from oracle import oracle as O
+    flags = O.use_native_build()
+    from edsgpu import synth
     cores = os.cpu_count() or 1
     concurrent = max(1, cores // NUM_BLOCKS)
-    data = make_data(0, n_scenes=2, n_windows=2)
-    per_step = max(concurrent, 2)
-    from edsgpu import synth
+    per_seq = 2
+    data = make_sequences(CONFIG, range(concurrent), per_seq)
     c = synth.CONFIGS[CONFIG]
     for _ in range(args.warmup):
-        cpu_windows_per_s(data, per_step, concurrent, NUM_BLOCKS)
-    t_total, n_total = 0.0, 0
+        cpu_windows_per_s(data, per_seq, concurrent, NUM_BLOCKS)
+    t_total, n_total, it = 0.0, 0, []
     for _ in range(args.steps):
-        wps, dt = cpu_windows_per_s(data, per_step, concurrent, NUM_BLOCKS)
+        wps, dt, n, iters = cpu_windows_per_s(data, per_seq, concurrent, NUM_BLOCKS)
         t_total += dt
-        n_total += per_step
+        n_total += n
+        it.append(iters)
     value = n_total / t_total
-    sample = "%d windows/step x %d steps of config2 (event frame + dual-number LM solve + MAD), %d concurrent sequences x %d threads" % (
-        per_step, args.steps, concurrent, NUM_BLOCKS)
+    _, dt_a, n_a, _ = cpu_windows_per_s(data, per_seq, concurrent, NUM_BLOCKS, jacobian_mode=0)
+    sample = "%d windows/step x %d steps of config2 (event frame + dual-number LM solve + MAD, warm-started, tau carried), %d concurrent sequences x %d threads" % (
+        concurrent * per_seq, args.steps, concurrent, NUM_BLOCKS)
     print(json.dumps({
         "impl": "reference", "metric": "tracking_windows_per_s_640x480", "value": value, "unit": "windows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "mevents_per_s": value * c["E"] / 1e6,
-        "config": {"workload": "config2: Gen3 640x480, 10240 points, 50000 events/window, B=8, Huber+MAD, max_iter 30",
-                   "note": "oracle restatement of the reference CPU/Ceres path (not Ceres itself), dual-number Jacobians"},
-        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": min(cores, concurrent * NUM_BLOCKS), "kind": "port", "sample": sample},
+        "config": {"workload": workload_string(c),
+                   "note": "oracle restatement of the reference CPU/Ceres path (not Ceres itself), dual-number Jacobians; built " + flags,
+                   "mean_lm_iterations": float(np.mean(it))},
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": min(cores, concurrent * NUM_BLOCKS), "kind": "port", "sample": sample,
+                         "build": flags, "analytic_jacobian_value": n_a / dt_a},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -205,9 +241,9 @@ def bench_ba(ctx, stream, reps=50):
     t0 = time.perf_counter()
     n_cpu = 20
     for _ in range(n_cpu):
-        A = O.ba_top_accumulate(0, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], threads=6)
-        L = O.ba_top_accumulate(1, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"],
-                                pb["adHTdeltaF"], pb["cDeltaF"], threads=6)
+        O.ba_top_accumulate(0, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], threads=6)
+        O.ba_top_accumulate(1, F, pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"],
+                            pb["adHTdeltaF"], pb["cDeltaF"], threads=6)
     cpu_ms = 1e3 * (time.perf_counter() - t0) / n_cpu
     alg = 2 * (296 * R + 12 * R + 364 * F * F + 24 * P) + (44 * R + 48 * P + 4 * (64 * F ** 3 + 40 * F * F + 20))
     # the feeder on the device: PointFrameResidual::linearize + takeDataF, inputs resident
@@ -333,6 +369,169 @@ def bench_depth(ctx, stream, n=10240, reps=100):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+class TrackRun:
+    """`S` sequences of one sensor configuration on this rank: device objects, event buffers (pinned host + HBM-resident
+    copies) and the two timed loops.  Sequence i follows data[i % len(data)] (the headline workload has one entry per sequence)."""
+
+    def __init__(self, ctx, torch, dev, stream, config, data, S):
+        import edsgpu
+        from edsgpu import synth
+        self.edsgpu, self.torch, self.ctx, self.dev, self.stream = edsgpu, torch, ctx, dev, stream
+        self.c = c = synth.CONFIGS[config]
+        self.S, self.data, self.n_win = S, data, len(data[0][1])
+        self.kfs = [edsgpu.KeyFrame(ctx, kf, NUM_BLOCKS) for kf, _ in data]
+        # two banks of S frame slots: the library builds event frames on its own stream, so the frames of window
+        # k+1 (bank (k+1)&1) are built while window k (bank k&1) is being solved
+        self.frames = edsgpu.Frames(ctx, c["H"], c["W"], 2 * S)
+        self.build_stream = torch.cuda.ExternalStream(self.frames.build_stream(), device=dev)
+        self.trackers = [edsgpu.Tracker(ctx, num_blocks=NUM_BLOCKS, loss_type=edsgpu.LOSS_HUBER, loss_param=TAU0, max_iterations=MAX_ITER,
+                                        function_tolerance=1e-6, loss_param_method=edsgpu.LOSS_PARAM_MAD) for _ in range(S)]
+        self.banks = [edsgpu.TrackerBatch(ctx, self.trackers, [self.kfs[s % len(data)] for s in range(S)], self.frames, bank * S)
+                      for bank in (0, 1)]
+        # event windows of step k (window k % n_win of every sequence): pinned host copies and device-resident copies
+        self.host_ev, self.dev_ev = [], []
+        for k in range(self.n_win):
+            arrs = []
+            for key in ("x", "y", "pol"):
+                a = np.concatenate([data[s % len(data)][1][k][key] for s in range(S)])
+                t = torch.from_numpy(a.view(np.int16).copy() if a.dtype == np.uint16 else a.copy()).pin_memory()
+                arrs.append(t)
+            self.host_ev.append(tuple(arrs))
+            self.dev_ev.append(tuple(t.to(dev) for t in arrs))
+        self.states_dev = torch.zeros(S, 14, dtype=torch.float64, device=dev)
+        self.states_host = [torch.zeros(S, 14, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.done_evt = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def reset_states(self):
+        for s, t in enumerate(self.trackers):
+            x0 = self.data[s % len(self.data)][1][0]["x_init"]
+            t.set_state(x0[:3], x0[3:7], x0[7:], TAU0)
+
+    def _create_device(self, k, events=None):
+        dx, dy, dp = self.dev_ev[k % self.n_win]
+        if events is not None:
+            a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            a.record(self.build_stream)
+        self.edsgpu.event_frames_batch_dev(self.ctx, self.frames, (k & 1) * self.S, self.S, dx.data_ptr(), dy.data_ptr(), dp.data_ptr(), self.c["E"])
+        if events is not None:
+            b.record(self.build_stream)
+            events.append((a, b))
+
+    def run_device(self, first, n, lm_events=None, ef_events=None):
+        """n steps, inputs resident in HBM; one step = event frames of window k + batched LM solve + MAD.
+        Software-pipelined like the streaming front end: window k+1's frames are queued before window k's solve."""
+        self._create_device(first, ef_events)
+        for i in range(n):
+            k = first + i
+            if i + 1 < n:
+                self._create_device(k + 1, ef_events)
+            if lm_events is not None:
+                a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                a.record(self.stream)
+            self.ctx.check(self.ctx.lib.edsgpu_batch_optimize(self.banks[k & 1].h))  # track_lm_kernel + mad_kernel
+            if lm_events is not None:
+                b.record(self.stream)
+                lm_events.append((a, b))
+
+    def time_event_frames(self, n):
+        """Mean CUDA-event time of one frame build (S windows: accumulator clear + scatter + blur/norm) with nothing else
+        on the device: the kernel time behind the event_frame roofline."""
+        self.ctx.synchronize()
+        evs = []
+        for k in range(n + 2):
+            self._create_device(k, evs)
+        self.ctx.synchronize()
+        return float(np.mean([a.elapsed_time(b) for a, b in evs[2:]]))
+
+    def _issue_create(self, k):
+        # host-facing C ABI with HOST (pinned) buffers: asynchronous, H2D on the library's copy stream
+        C = self.edsgpu.C
+        hx, hy, hp = self.host_ev[k % self.n_win]
+        self.ctx.check(self.ctx.lib.edsgpu_event_frame_create_batch(
+            self.ctx.h, self.frames.h, (k & 1) * self.S, self.S, None, C.c_void_p(hx.data_ptr()), C.c_void_p(hy.data_ptr()),
+            C.c_void_p(hp.data_ptr()), self.c["E"], self.edsgpu.DRAW_BILINEAR, 1, C.c_float(0.5), None))
+
+    def run_e2e(self, first, n):
+        """n steps; every step copies its events H2D from pinned host memory and reads its S x 14 state records back.
+        Software-pipelined like a streaming front end: the next window's events are handed to the library while the
+        current window is being solved (their H2D copy and frame build overlap the solve), and the host picks up step k's
+        states while step k+1 is already queued (the poses of a window are consumed one window later; every step's
+        read-back completes inside the timed region)."""
+        self._issue_create(first)
+        for i in range(n):
+            k = first + i
+            if i + 1 < n:
+                self._issue_create(k + 1)
+            self.banks[k & 1].optimize()
+            self.banks[k & 1].pack_states_dev(self.states_dev.data_ptr())
+            self.states_host[i & 1].copy_(self.states_dev, non_blocking=True)
+            self.done_evt[i & 1].record(self.stream)
+            if i > 0:
+                self.done_evt[(i - 1) & 1].synchronize()  # step k-1's result is on the host
+        self.done_evt[(n - 1) & 1].synchronize()
+
+    def close(self):
+        self.ctx.synchronize()
+        for b in self.banks:
+            b.close()
+        for t in self.trackers:
+            t.close()
+        self.frames.close()
+        for k in self.kfs:
+            k.close()
+
+
+def measure(run, steps, warmup, barrier, max_over_ranks, peak, traffic):
+    """value / e2e / roofline of one TrackRun (all ranks call this together)."""
+    torch = run.torch
+    c, S = run.c, run.S
+    run.reset_states()
+    run.run_device(0, warmup)
+    barrier()
+    launches0 = run.ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lm_events = []
+    ev0.record(run.stream)
+    run.run_device(warmup, steps, lm_events)
+    ev1.record(run.stream)
+    barrier()
+    launches = run.ctx.launches - launches0
+    t_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    lm_ms = float(np.mean([a.elapsed_time(b) for a, b in lm_events]))
+    ef_ms = run.time_event_frames(min(steps, 10))
+    states, infos = run.banks[(warmup + steps - 1) & 1].gather()
+    evals = float(sum(i["evaluations"] for i in infos))  # last step's launch
+    usable = sum(i["usable"] for i in infos)
+    iters = float(np.mean([i["iterations"] for i in infos]))
+    run.reset_states()
+    run.run_e2e(0, max(1, warmup))
+    barrier()
+    t0 = time.perf_counter()
+    run.run_e2e(warmup, steps)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    alg = algorithmic_bytes_lm(c["N"], c["H"], c["W"], NUM_BLOCKS, evals) + 4 * c["N"] * S
+    achieved = alg / (lm_ms * 1e-3) / 1e9
+    ef_alg = S * algorithmic_bytes_ef(c["E"], c["H"], c["W"])
+    shape = run.banks[0].launch_shape()
+    return {
+        "t_ms": t_ms, "e2e_s": e2e_s, "launches": int(launches), "iters": iters, "usable": usable, "states": states,
+        "launch_shape": "%d evaluator CTAs + %d leader CTAs of 512 threads, %d problems in flight" % shape,
+        "roofline": {"kernel": "track_lm_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (traffic or {}).get("track_lm_kernel_dram_bytes_per_launch"),
+                     "l2_bytes": (traffic or {}).get("track_lm_kernel_lts_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": alg, "launch_ms": lm_ms, "evaluations_per_launch": evals,
+                     "note": "launch_ms covers track_lm_kernel + mad_kernel (CUDA events on the launching stream, frame builds of the next window running "
+                             "beside it); traffic / l2_bytes are from the ncu capture in profiles/ (config 2, 64 sequences): the working set is "
+                             "L2-resident, the kernel is bound by per-SM latency / issue, see DESIGN.md 4.2"},
+        "event_frame": {"kernels": "scatter_events_kernel + blur_norm_kernel (+ accumulator clear)", "bound": "hbm", "ms": ef_ms,
+                        "algorithmic_bytes": ef_alg, "achieved": ef_alg / (ef_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": ef_alg / (ef_ms * 1e-3) / 1e9 / peak,
+                        "note": "CUDA events on the library's build stream around one build of all S windows, measured alone (inside a step the build of "
+                                "window k+1 shares the device with the solve of window k)"},
+    }
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -348,183 +547,115 @@ def run_native(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    os.environ.setdefault("EDSGPU_RESERVE_SMS", str(RESERVE_SMS))
     c = synth.CONFIGS[CONFIG]
-    H, W, N, E = c["H"], c["W"], c["N"], c["E"]
-    S = args.sequences
-
     # one explicit stream shared by torch (events, copies, NCCL ordering) and the library
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx = edsgpu.Context(local_rank, stream.cuda_stream)
-    data = make_data(rank)
-    n_sc, n_win = len(data), len(data[0][1])
-    # sequence s follows scene s % n_sc, starting at window (s // n_sc) % n_win
-    kfs_dev = [edsgpu.KeyFrame(ctx, kf, NUM_BLOCKS) for kf, _ in data]
-    # two banks of S frame slots: the library builds event frames on its own stream, so the frames of window
-    # k+1 (bank (k+1)&1) are built while window k (bank k&1) is being solved
-    frames = edsgpu.Frames(ctx, H, W, 2 * S)
-    trackers = []
-    for s in range(S):
-        t = edsgpu.Tracker(ctx, num_blocks=NUM_BLOCKS, loss_type=edsgpu.LOSS_HUBER, loss_param=TAU0, max_iterations=MAX_ITER,
-                           function_tolerance=1e-6, loss_param_method=edsgpu.LOSS_PARAM_MAD)
-        trackers.append(t)
-    banks = [edsgpu.TrackerBatch(ctx, trackers, [kfs_dev[s % n_sc] for s in range(S)], frames, bank * S) for bank in (0, 1)]
-    batch = banks[0]
-
-    def reset_states():
-        for s, t in enumerate(trackers):
-            x0 = data[s % n_sc][1][(s // n_sc) % n_win]["x_init"]
-            t.set_state(x0[:3], x0[3:7], x0[7:], TAU0)
-
-    # event windows of step k: pinned host copies and device-resident copies, n_win phases
-    host_ev, dev_ev = [], []
-    for ph in range(n_win):
-        xs = np.concatenate([data[s % n_sc][1][(s // n_sc + ph) % n_win]["x"] for s in range(S)])
-        ys = np.concatenate([data[s % n_sc][1][(s // n_sc + ph) % n_win]["y"] for s in range(S)])
-        ps = np.concatenate([data[s % n_sc][1][(s // n_sc + ph) % n_win]["pol"] for s in range(S)])
-        hx = torch.from_numpy(xs.view(np.int16).copy()).pin_memory()
-        hy = torch.from_numpy(ys.view(np.int16).copy()).pin_memory()
-        hp = torch.from_numpy(ps.copy()).pin_memory()
-        host_ev.append((hx, hy, hp))
-        dev_ev.append((hx.to(dev), hy.to(dev), hp.to(dev)))
-    states_dev = torch.zeros(S, 14, dtype=torch.float64, device=dev)
-    states_host = torch.zeros(S, 14, dtype=torch.float64).pin_memory()
-
-    def create_device(k):
-        dx, dy, dp = dev_ev[k % n_win]
-        edsgpu.event_frames_batch_dev(ctx, frames, (k & 1) * S, S, dx.data_ptr(), dy.data_ptr(), dp.data_ptr(), E)
-
-    def run_device(first, n, events=None):
-        """n steps, inputs resident in HBM; one step = event frames of window k + batched LM solve + MAD.
-        Software-pipelined like the streaming front end: window k+1's frames are queued before window k's solve."""
-        create_device(first)
-        for i in range(n):
-            k = first + i
-            if i + 1 < n:
-                create_device(k + 1)
-            if events is not None:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-            ctx.check(ctx.lib.edsgpu_batch_optimize(banks[k & 1].h))  # track_lm_kernel + mad_kernel
-            if events is not None:
-                b.record(stream)
-                events.append((a, b))
-
-    def issue_create(k):
-        # host-facing C ABI with HOST (pinned) buffers: asynchronous, H2D on the library's copy stream
-        hx, hy, hp = host_ev[k % n_win]
-        ctx.check(ctx.lib.edsgpu_event_frame_create_batch(
-            ctx.h, frames.h, (k & 1) * S, S, None, edsgpu.C.c_void_p(hx.data_ptr()), edsgpu.C.c_void_p(hy.data_ptr()),
-            edsgpu.C.c_void_p(hp.data_ptr()), E, edsgpu.DRAW_BILINEAR, 1, edsgpu.C.c_float(0.5), None))
-
-    states_host2 = [states_host, torch.zeros(S, 14, dtype=torch.float64).pin_memory()]
-    done_evt = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def run_e2e(first, n):
-        """n steps; every step copies its events H2D from pinned host memory and reads its 64x14 state
-        records back.  Software-pipelined like a streaming front end: the next window's events are handed
-        to the library while the current window is being solved (their H2D copy and frame build overlap the
-        solve), and the host picks up step k's states while step k+1 is already queued (the poses of a
-        window are consumed one window later; every step's read-back completes inside the timed region)."""
-        issue_create(first)
-        for i in range(n):
-            k = first + i
-            if i + 1 < n:
-                issue_create(k + 1)
-            banks[k & 1].optimize()
-            banks[k & 1].pack_states_dev(states_dev.data_ptr())
-            states_host2[i & 1].copy_(states_dev, non_blocking=True)
-            done_evt[i & 1].record(stream)
-            if i > 0:
-                done_evt[(i - 1) & 1].synchronize()  # step k-1's result is on the host
-        done_evt[(n - 1) & 1].synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing (value) ------------------------------------------------
-    reset_states()
-    run_device(0, args.warmup)
-    barrier()
+    def max_over_ranks(v):
+        return shard.max_over_ranks(v, dev)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except (OSError, ValueError):
+        pass
+
+    total = args.sequences
+    procs = max(1, (os.cpu_count() or 1) // world)
     clocks = ClockSampler(local_rank)
+    # ---- headline: strong scaling -- the `total` sequences dealt round-robin to the ranks --------------------------
+    strong = args.scaling == "strong"
+    ids = shard.local_sequences(total, world, rank) if strong else [rank * total + s for s in range(total)]
+    data = make_sequences(CONFIG, ids, WINDOWS, procs)
+    run = TrackRun(ctx, torch, dev, stream, CONFIG, data, len(ids))
+    barrier()
     if rank == 0:
         clocks.start()
-    launches0 = ctx.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lm_events = []
-    ev0.record(stream)
-    run_device(args.warmup, args.steps, lm_events)
-    ev1.record(stream)
-    barrier()
-    launches = ctx.launches - launches0
+    m = measure(run, args.steps, args.warmup, barrier, max_over_ranks, peak, traffic)
     clk = clocks.stop() if rank == 0 else None
-    t_ms_max = shard.max_over_ranks(ev0.elapsed_time(ev1), dev)
-    lm_ms = float(np.mean([a.elapsed_time(b) for a, b in lm_events]))
-    states, infos = batch.gather()
-    evals = float(np.mean([sum(i["evaluations"] for i in infos)]))  # last step's launch
-    usable = sum(i["usable"] for i in infos)
-    iters = float(np.mean([i["iterations"] for i in infos]))
-
-    # ---- end-to-end timing (e2e): host buffers in, host states out, every step ---------
-    reset_states()
-    run_e2e(0, max(1, args.warmup))
-    barrier()
-    t0 = time.perf_counter()
-    run_e2e(args.warmup, args.steps)
-    barrier()
-    e2e_s = shard.max_over_ranks(time.perf_counter() - t0, dev)
-
-    # ---- the one collective of the path: gather the final states over NCCL -------------
-    batch.pack_states_dev(states_dev.data_ptr())
+    n_global = total if strong else total * world
+    # ---- the one collective of the path: gather the final states over NCCL ----------------------------------------
+    run.banks[(args.warmup + args.steps - 1) & 1].pack_states_dev(run.states_dev.data_ptr())
     stream.synchronize()
-    final_states = shard.gather_states(states_dev).cpu().numpy()  # global sequence order, [world*S, 14]
+    final_states = shard.gather_states(run.states_dev, n_global if strong else None).cpu().numpy()
+    run.close()
+    weak = None
+    if world > 1 and strong and not args.no_weak:
+        wdata = make_sequences(CONFIG, [rank * total + s for s in range(total)], WINDOWS, procs)
+        wrun = TrackRun(ctx, torch, dev, stream, CONFIG, wdata, total)
+        barrier()
+        wm = measure(wrun, args.steps, args.warmup, barrier, max_over_ranks, peak, traffic)
+        weak = {"scaling": "weak", "sequences_per_gpu": total, "value": world * total * args.steps / (wm["t_ms"] * 1e-3),
+                "ms_per_step": wm["t_ms"] / args.steps, "e2e_value": world * total * args.steps / wm["e2e_s"], "roofline_frac": wm["roofline"]["frac"]}
+        wrun.close()
+    side = {}
+    if world == 1 and not args.no_side:
+        # the other two sensor shapes named in BASELINE.json (configs[0] and configs[2]): same step, own roofline
+        for key, cfg, S_side, steps in (("config1", "davis240c", 64, args.steps), ("config3", "gen4_hd", 32, max(5, args.steps // 5))):
+            sdata = make_sequences(cfg, range(SIDE_SCENES), SIDE_WINDOWS, procs)
+            srun = TrackRun(ctx, torch, dev, stream, cfg, sdata, S_side)
+            sm = measure(srun, steps, args.warmup, barrier, max_over_ranks, peak, None)
+            sc = synth.CONFIGS[cfg]
+            val = S_side * steps / (sm["t_ms"] * 1e-3)
+            side[key] = {"workload": "%s %dx%d, %d points, %d events/window, %d sequences (%d distinct scenes x %d windows), B=%d, Huber+MAD, max_iter %d"
+                                     % (cfg, sc["W"], sc["H"], sc["N"], sc["E"], S_side, SIDE_SCENES, SIDE_WINDOWS, NUM_BLOCKS, MAX_ITER),
+                         "value": val, "unit": "windows/s", "mevents_per_s": val * sc["E"] / 1e6, "ms_per_step": sm["t_ms"] / steps, "steps": steps,
+                         "e2e": {"value": S_side * steps / sm["e2e_s"], "unit": "windows/s", "h2d_bytes_per_step": int(S_side * sc["E"] * 5),
+                                 "d2h_bytes_per_step": int(S_side * 14 * 8)},
+                         "mean_lm_iterations": sm["iters"], "usable": "%d/%d" % (sm["usable"], S_side), "launch_shape": sm["launch_shape"],
+                         "roofline": sm["roofline"], "event_frame": sm["event_frame"]}
+            srun.close()
     ba_line = bench_ba(ctx, stream) if (rank == 0 and not args.no_ba) else None
     coarse_line = bench_coarse(ctx, stream) if (rank == 0 and not args.no_ba) else None
     depth_line = bench_depth(ctx, stream) if (rank == 0 and not args.no_ba) else None
 
     if rank == 0:
-        windows = world * S * args.steps
-        value = windows / (t_ms_max * 1e-3)
-        e2e_value = windows / e2e_s
-        alg = algorithmic_bytes_lm(N, H, W, NUM_BLOCKS, evals) + 4 * N * S
-        achieved = alg / (lm_ms * 1e-3) / 1e9
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except (OSError, ValueError):
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("track_lm_kernel_dram_bytes_per_launch")
-        except (OSError, ValueError):
-            pass
+        S_local = len(ids)
+        windows = n_global * args.steps
+        value = windows / (m["t_ms"] * 1e-3)
+        e2e_value = windows / m["e2e_s"]
+        H, W, N, E = c["H"], c["W"], c["N"], c["E"]
+        ws = S_local * H * W * 12 + S_local * E * 5 + S_local * N * 48
         out = {
             "metric": "tracking_windows_per_s_640x480", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": m["t_ms"] / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32 (fp64 warp/projection, reductions and LM solve)", "data": "synthetic",
             "mevents_per_s": value * E / 1e6,
-            "config": {"workload": "config2 x %d sequences/GPU: Gen3 640x480, %d points, %d events/window, B=%d, Huber+MAD, max_iter %d"
-                                   % (S, N, E, NUM_BLOCKS, MAX_ITER),
-                       "sequences_per_gpu": S, "l2": "per-step working set ~%d MB (event accumulators + frames + keyframes) > 126 MB L2, no explicit flush"
-                                                   % int((S * H * W * 12 + S * E * 5 + n_sc * N * 48) / 1e6),
-                       "mean_lm_iterations": iters, "launch_shape": "%d evaluator CTAs + %d leader CTAs of 512 threads, %d problems in flight" % banks[0].launch_shape(), "usable": "%d/%d" % (usable, S), "parallelism": "sequences sharded, %d rank(s)" % world},
-            "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(S * E * 5), "d2h_bytes_per_step": int(S * 14 * 8),
-                    "ms_per_step": 1e3 * e2e_s / args.steps,
+            "config": {"workload": workload_string(c), "sequences": n_global, "sequences_per_gpu": S_local,
+                       "windows_per_sequence": "%d consecutive windows per sequence, then round again; every sequence has its own scene and key frame" % WINDOWS,
+                       "l2": "per-step working set ~%d MB per GPU (event accumulators + frames + key frames) %s 126 MB L2, no explicit flush"
+                             % (int(ws / 1e6), ">" if ws > 126e6 else "<= (the working set of a sharded batch fits L2: stated, not flushed)"),
+                       "mean_lm_iterations": m["iters"], "launch_shape": m["launch_shape"], "reserved_sms": int(os.environ["EDSGPU_RESERVE_SMS"]),
+                       "usable": "%d/%d" % (m["usable"], S_local), "parity": PARITY_NOTE,
+                       "parallelism": "%d sequences dealt round-robin to %d rank(s), no collective on the data path, one NCCL gather at the end" % (n_global, world)},
+            "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(S_local * E * 5), "d2h_bytes_per_step": int(S_local * 14 * 8),
+                    "ms_per_step": 1e3 * m["e2e_s"] / args.steps,
                     "how": "edsgpu_event_frame_create_batch (pinned host events) + edsgpu_batch_optimize + state read-back every step; "
-                           "next window's H2D copy and frame build (other bank of slots, build stream) overlap the current solve; the host reads step k's states while step k+1 is queued"},
-            "gpu_launches": int(launches),
+                           "next window's H2D copy and frame build (other bank of slots, build stream) overlap the current solve; the host reads step k's states while step k+1 is queued; bytes are per GPU"},
+            "gpu_launches": m["launches"],
             "clocks": clk,
-            "roofline": {"kernel": "track_lm_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "algorithmic_bytes_per_launch": alg, "launch_ms": lm_ms, "evaluations_per_launch": evals,
-                         "note": "launch_ms covers track_lm_kernel + mad_kernel; the working set is L2-resident (traffic << algorithmic bytes), "
-                                 "the kernel is bound by per-SM issue/latency of the sweep (~320 cycles per 32-point batch), see DESIGN.md 4.2"},
+            "roofline": m["roofline"],
+            "event_frame": m["event_frame"],
             "final_state_checksum": float(np.abs(final_states).sum()),
         }
+        if weak:
+            out["weak"] = weak
+        out.update(side)
         if ba_line:
             out["ba"] = ba_line
         if coarse_line:
@@ -532,12 +663,19 @@ def run_native(args):
         if depth_line:
             out["depth_filter"] = depth_line
         if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
             cores = os.cpu_count() or 1
-            n_cpu = 400  # ~10 s of CPU work
-            wps, dt = cpu_windows_per_s(data[:2], n_cpu, 1, min(NUM_BLOCKS, cores))
-            out["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": min(NUM_BLOCKS, cores), "kind": "port",
-                                   "sample": "%d windows of the same workload, one sequence, %d threads (one per residual block), dual-number Jacobians, %.1f s"
-                                             % (n_cpu, min(NUM_BLOCKS, cores), dt)}
+            th = min(NUM_BLOCKS, cores)
+            n_seq, per_seq = min(8, len(data)), 25  # ~10-20 s of CPU work: 200 windows
+            cdata = data[:n_seq]
+            wps, dt, n, it = cpu_windows_per_s(cdata, per_seq, 1, th)
+            wps_a, dt_a, n_a, it_a = cpu_windows_per_s(cdata, per_seq, 1, th, jacobian_mode=0)
+            out["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": th, "kind": "port",
+                                   "sample": "%d windows of the same workload (%d sequences x %d consecutive windows, warm-started, tau carried), one sequence at a time, "
+                                             "%d threads (one per residual block), dual-number Jacobians, %.1f s" % (n, n_seq, per_seq, th, dt),
+                                   "build": O.BUILD_FLAGS, "mean_lm_iterations": it,
+                                   "analytic_jacobian": {"value": wps_a, "unit": "windows/s", "seconds": dt_a, "mean_lm_iterations": it_a,
+                                                         "note": "C-analytic variant (hand Jacobian, same solver): the fairer best-CPU number, BASELINE.md section 3"}}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -549,13 +687,19 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--sequences", type=int, default=64, help="independent sequences per GPU (configs[4])")
+    ap.add_argument("--sequences", type=int, default=64, help="independent sequences: in total (strong, configs[4]) or per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling extra measurement")
+    ap.add_argument("--no-side", action="store_true", help="skip the config1 / config3 measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ba", action="store_true", help="skip the config-4 BA accumulation side measurement")
+    ap.add_argument("--no-ba", action="store_true", help="skip the BA / coarse tracker / depth filter side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
+        if not args.no_cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            from oracle import oracle as O  # cpu_baseline leg: the timing build of the checker, chosen before anything loads it
+            O.use_native_build()
         run_native(args)
 
 

@@ -76,6 +76,10 @@ edsgpu_status edsgpu_event_frame_create(edsgpu_ctx* ctx, edsgpu_frames* frames, 
                                         int num_events, int mode, int use_exp_weights, float sigma, double* norm_out,
                                         int64_t* time_us_out, int64_t* delta_time_us_out, double* host_frame_out);
 
+/* The CUDA stream (cudaStream_t) the library builds event frames on (created with the frames object).  Builds are ordered
+ * against the context's stream per slot by the library itself; the handle is for measurement (CUDA events around a build). */
+void* edsgpu_frames_build_stream(const edsgpu_frames* frames);
+
 /* `count` windows of num_events events each, into slots first_slot.. (x,y,polarity are
  * count*num_events long).  norms_out: count doubles or NULL.  Asynchronous if norms_out is NULL.
  * Frames are BUILT on a stream of their own, ordered per slot against the library's readers

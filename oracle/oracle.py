@@ -12,6 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libeds_oracle.so")
+BUILD_FLAGS = "-O3 -march=x86-64-v3 -ffp-contract=off"
 _lib = None
 
 REC = 76  # floats per RawResidualJacobian record (304 B)
@@ -39,6 +40,23 @@ class SolverInfo(C.Structure):
                 ("termination", C.c_int), ("solve_time_us", C.c_double), ("final_radius", C.c_double)]
 
 
+def use_native_build():
+    """bench.py's CPU arms: switch to a build tuned for THIS machine (-O3 -march=native, contraction allowed), compiled on
+    the spot into a per-host directory.  Must be called before the first use; returns the flags in effect."""
+    global _LIB_PATH, BUILD_FLAGS
+    assert _lib is None, "oracle already loaded"
+    import platform
+    d = os.path.join("_build", "native_" + platform.node().replace("/", "_"))
+    try:
+        subprocess.run(["make", "-C", _HERE, "native", "NATIVE_DIR=" + d], check=True, capture_output=True)
+        C.CDLL(os.path.join(_HERE, d, "libeds_oracle.so"))
+        _LIB_PATH = os.path.join(_HERE, d, "libeds_oracle.so")
+        BUILD_FLAGS = "-O3 -march=native -ffp-contract=fast"
+    except (subprocess.CalledProcessError, OSError):
+        pass  # keep the default build
+    return BUILD_FLAGS
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -47,7 +65,7 @@ def lib():
             _lib = C.CDLL(_LIB_PATH)
         except OSError:
             build(force=True)
-            _lib = C.CDLL(_LIB_PATH)
+            _lib = C.CDLL(os.path.join(_HERE, "_build", "libeds_oracle.so"))
         _lib.eds_oracle_mad_tau.restype = C.c_double
     return _lib
 

@@ -525,6 +525,8 @@ edsgpu_status edsgpu_event_frame_create(edsgpu_ctx* ctx, edsgpu_frames* frames, 
     return EDSGPU_OK;
 }
 
+void* edsgpu_frames_build_stream(const edsgpu_frames* frames) { return frames ? (void*)frames->build_stream : nullptr; }
+
 edsgpu_status edsgpu_frames_read(edsgpu_ctx* ctx, const edsgpu_frames* frames, int slot, double* image_out, double* norm_out) {
     if (!ctx) return EDSGPU_INVALID_ARGUMENT;
     EDS_REQUIRE(ctx, frames && slot >= 0 && slot < frames->capacity, "frames_read: bad slot");

@@ -27,7 +27,7 @@ SYMBOLS = [
     "edsgpu_version", "edsgpu_create", "edsgpu_destroy", "edsgpu_last_error_string", "edsgpu_synchronize",
     "edsgpu_launch_count", "edsgpu_lut_create", "edsgpu_lut_destroy", "edsgpu_frames_create", "edsgpu_frames_destroy",
     "edsgpu_event_frame_create", "edsgpu_event_frame_create_batch", "edsgpu_event_frame_create_batch_dev",
-    "edsgpu_frames_read", "edsgpu_frames_read_accumulator", "edsgpu_keyframe_create", "edsgpu_keyframe_destroy",
+    "edsgpu_frames_read", "edsgpu_frames_read_accumulator", "edsgpu_frames_build_stream", "edsgpu_keyframe_create", "edsgpu_keyframe_destroy",
     "edsgpu_tracker_create", "edsgpu_tracker_destroy", "edsgpu_tracker_set_state", "edsgpu_tracker_get_state",
     "edsgpu_tracker_optimize", "edsgpu_trackers_optimize_batch", "edsgpu_trackers_gather", "edsgpu_tracker_state_dev",
     "edsgpu_batch_create", "edsgpu_batch_destroy", "edsgpu_batch_optimize", "edsgpu_batch_pack_states_dev", "edsgpu_batch_launch_shape",
@@ -78,6 +78,8 @@ def load():
         lib.edsgpu_launch_count.argtypes = [C.c_void_p]
         lib.edsgpu_tracker_state_dev.restype = C.c_void_p
         lib.edsgpu_tracker_state_dev.argtypes = [C.c_void_p]
+        lib.edsgpu_frames_build_stream.restype = C.c_void_p
+        lib.edsgpu_frames_build_stream.argtypes = [C.c_void_p]
         for name in ("edsgpu_destroy", "edsgpu_lut_destroy", "edsgpu_frames_destroy", "edsgpu_keyframe_destroy",
                      "edsgpu_tracker_destroy", "edsgpu_batch_destroy", "edsgpu_ba_destroy"):
             getattr(lib, name).restype = None
@@ -148,6 +150,10 @@ class Frames:
         self.ctx.check(self.ctx.lib.edsgpu_frames_read(self.ctx.h, self.h, C.c_int(slot), _ptr(img, C.c_double),
                                                        C.byref(norm)))
         return img, norm.value
+
+    def build_stream(self):
+        """cudaStream_t (int) the frames of this bank are built on."""
+        return int(self.ctx.lib.edsgpu_frames_build_stream(self.h))
 
     def read_accumulator(self, slot=0):
         acc = np.zeros((self.H, self.W), np.int64)
@@ -268,6 +274,11 @@ class Tracker:
 def event_frames_batch(ctx, frames, first_slot, count, x, y, pol, num_events, lut=None, mode=DRAW_BILINEAR,
                        use_exp_weights=True, sigma=0.5, want_norms=False):
     """Host arrays (count*num_events) -> `count` device frames (edsgpu_event_frame_create_batch)."""
+    # the C ABI takes uint16 / uint16 / uint8 arrays: convert here rather than reinterpret whatever dtype came in
+    x, y = np.ascontiguousarray(x, np.uint16), np.ascontiguousarray(y, np.uint16)
+    pol = np.ascontiguousarray(pol, np.uint8)
+    if not (len(x) == len(y) == len(pol) == count * num_events):
+        raise ValueError("event_frames_batch: need count * num_events = %d events per array" % (count * num_events))
     norms = np.zeros(count) if want_norms else None
     ctx.check(ctx.lib.edsgpu_event_frame_create_batch(
         ctx.h, frames.h, C.c_int(first_slot), C.c_int(count), lut.h if lut else None, _ptr(x, C.c_uint16),
