@@ -580,7 +580,8 @@ def run_native(args):
     clocks = ClockSampler(local_rank)
     # ---- headline: strong scaling -- the `total` sequences dealt round-robin to the ranks --------------------------
     strong = args.scaling == "strong"
-    ids = shard.local_sequences(total, world, rank) if strong else [rank * total + s for s in range(total)]
+    n_global = total if strong else total * world
+    ids = shard.local_sequences(n_global, world, rank)  # sequence s runs on rank s mod world
     data = make_sequences(CONFIG, ids, WINDOWS, procs)
     run = TrackRun(ctx, torch, dev, stream, CONFIG, data, len(ids))
     barrier()
@@ -588,15 +589,17 @@ def run_native(args):
         clocks.start()
     m = measure(run, args.steps, args.warmup, barrier, max_over_ranks, peak, traffic)
     clk = clocks.stop() if rank == 0 else None
-    n_global = total if strong else total * world
-    # ---- the one collective of the path: gather the final states over NCCL ----------------------------------------
-    run.banks[(args.warmup + args.steps - 1) & 1].pack_states_dev(run.states_dev.data_ptr())
-    stream.synchronize()
-    final_states = shard.gather_states(run.states_dev, n_global if strong else None).cpu().numpy()
+    # ---- the one collective of the path: gather the final states with NCCL, from the C++ host layer (libedsgpu_nccl.so) ----
+    uid = [edsgpu.Comm.unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    comm = edsgpu.Comm(ctx, world, rank, uid[0])
+    final_states = comm.gather_batch(run.banks[(args.warmup + args.steps - 1) & 1], n_global)
+    comm.close()
     run.close()
     weak = None
     if world > 1 and strong and not args.no_weak:
-        wdata = make_sequences(CONFIG, [rank * total + s for s in range(total)], WINDOWS, procs)
+        wdata = make_sequences(CONFIG, shard.local_sequences(total * world, world, rank), WINDOWS, procs)
         wrun = TrackRun(ctx, torch, dev, stream, CONFIG, wdata, total)
         barrier()
         wm = measure(wrun, args.steps, args.warmup, barrier, max_over_ranks, peak, traffic)
@@ -642,7 +645,7 @@ def run_native(args):
                              % (int(ws / 1e6), ">" if ws > 126e6 else "<= (the working set of a sharded batch fits L2: stated, not flushed)"),
                        "mean_lm_iterations": m["iters"], "launch_shape": m["launch_shape"], "reserved_sms": int(os.environ["EDSGPU_RESERVE_SMS"]),
                        "usable": "%d/%d" % (m["usable"], S_local), "parity": PARITY_NOTE,
-                       "parallelism": "%d sequences dealt round-robin to %d rank(s), no collective on the data path, one NCCL gather at the end" % (n_global, world)},
+                       "parallelism": "%d sequences dealt round-robin to %d rank(s), no collective on the data path, one ncclAllGather of the state records at the end (edsgpu_batch_gather_states_nccl)" % (n_global, world)},
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(S_local * E * 5), "d2h_bytes_per_step": int(S_local * 14 * 8),
                     "ms_per_step": 1e3 * m["e2e_s"] / args.steps,
                     "how": "edsgpu_event_frame_create_batch (pinned host events) + edsgpu_batch_optimize + state read-back every step; "

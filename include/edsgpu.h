@@ -176,6 +176,7 @@ edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* tracke
                                   int count, const edsgpu_frames* frames, int first_slot, edsgpu_batch** out);
 void edsgpu_batch_destroy(edsgpu_batch* batch);
 edsgpu_status edsgpu_batch_optimize(edsgpu_batch* batch);
+edsgpu_status edsgpu_batch_count(const edsgpu_batch* batch, int* count); /* problems of the batch */
 /* How edsgpu_batch_optimize will launch: evaluator CTAs (they sweep residual blocks of any problem, taken from a
  * global task queue), leader CTAs (one warp per problem runs its Levenberg-Marquardt loop) and the number of problems
  * kept in flight at once (chosen when the batch is created; informational -- results do not depend on it). */

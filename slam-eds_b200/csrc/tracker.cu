@@ -2016,6 +2016,12 @@ edsgpu_status edsgpu_batch_launch_shape(const edsgpu_batch* b, int* evaluator_ct
     return EDSGPU_OK;
 }
 
+edsgpu_status edsgpu_batch_count(const edsgpu_batch* b, int* count) {
+    if (!b || !count) return EDSGPU_INVALID_ARGUMENT;
+    *count = b->count;
+    return EDSGPU_OK;
+}
+
 edsgpu_status edsgpu_batch_pack_states_dev(edsgpu_batch* b, double* states_dev) {
     if (!b || !states_dev) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = b->ctx;

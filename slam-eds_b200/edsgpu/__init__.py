@@ -30,7 +30,7 @@ SYMBOLS = [
     "edsgpu_frames_read", "edsgpu_frames_read_accumulator", "edsgpu_frames_build_stream", "edsgpu_keyframe_create", "edsgpu_keyframe_destroy",
     "edsgpu_tracker_create", "edsgpu_tracker_destroy", "edsgpu_tracker_set_state", "edsgpu_tracker_get_state",
     "edsgpu_tracker_optimize", "edsgpu_trackers_optimize_batch", "edsgpu_trackers_gather", "edsgpu_tracker_state_dev",
-    "edsgpu_batch_create", "edsgpu_batch_destroy", "edsgpu_batch_optimize", "edsgpu_batch_pack_states_dev", "edsgpu_batch_launch_shape",
+    "edsgpu_batch_create", "edsgpu_batch_destroy", "edsgpu_batch_optimize", "edsgpu_batch_count", "edsgpu_batch_pack_states_dev", "edsgpu_batch_launch_shape",
     "edsgpu_tracker_evaluate",
     "edsgpu_ba_create", "edsgpu_ba_destroy", "edsgpu_ba_set_residuals", "edsgpu_ba_set_points", "edsgpu_ba_set_frames",
     "edsgpu_ba_top_accumulate", "edsgpu_ba_top_stitch", "edsgpu_ba_sc_accumulate", "edsgpu_ba_sc_stitch", "edsgpu_ba_get_jpjd",
@@ -41,6 +41,29 @@ SYMBOLS = [
     "edsgpu_depth_points_create", "edsgpu_depth_points_destroy", "edsgpu_depth_points_update", "edsgpu_depth_points_get",
     "edsgpu_tracker_get_coord", "edsgpu_keyframe_refresh_idepth", "edsgpu_depth_points_update_from_tracker",
 ]
+
+
+NCCL_LIB_PATH = os.path.join(os.path.dirname(_PKG), "libedsgpu_nccl.so")
+NCCL_SYMBOLS = ["edsgpu_comm_unique_id", "edsgpu_comm_create", "edsgpu_comm_adopt", "edsgpu_comm_destroy",
+                "edsgpu_gather_states_nccl", "edsgpu_batch_gather_states_nccl"]
+_nccl_lib = None
+
+
+def load_nccl():
+    """libedsgpu_nccl.so: the final gather of a sharded batch (include/edsgpu_nccl.h).  Loaded on first use only."""
+    global _nccl_lib
+    if _nccl_lib is None:
+        load()
+        if not os.path.exists(NCCL_LIB_PATH):
+            raise ImportError("libedsgpu_nccl.so not built: run `make -C slam-eds_b200`")
+        # PyTorch bundles its own libnccl.so.2 (same SONAME, newer version).  Whichever copy is loaded first serves the
+        # whole process, and torch cannot start on an older one: let it load its copy before ours asks for the SONAME.
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
+        _nccl_lib = C.CDLL(NCCL_LIB_PATH)
+    return _nccl_lib
 
 
 class EdsGpuError(RuntimeError):
@@ -588,4 +611,37 @@ class DepthPoints:
     def close(self):
         if self.h:
             self.ctx.lib.edsgpu_depth_points_destroy(self.h)
+            self.h = None
+
+
+class Comm:
+    """One rank's end of the NCCL communicator used for the final gather (edsgpu_comm_*)."""
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        st = load_nccl().edsgpu_comm_unique_id(buf)
+        if st != OK:
+            raise EdsGpuError(st, "ncclGetUniqueId failed")
+        return buf.raw
+
+    def __init__(self, ctx, world_size, rank, unique_id):
+        self.ctx, self.world, self.rank = ctx, world_size, rank
+        self.lib = load_nccl()
+        self.h = C.c_void_p()
+        ctx.check(self.lib.edsgpu_comm_create(ctx.h, C.c_int(world_size), C.c_int(rank), C.c_char_p(unique_id), C.byref(self.h)))
+
+    def gather_states_dev(self, local_ptr, n_local, num_sequences, out_ptr):
+        """Device pointers (ints): [n_local x 14] -> [num_sequences x 14] in global order; asynchronous."""
+        self.ctx.check(self.lib.edsgpu_gather_states_nccl(self.h, C.c_void_p(local_ptr), C.c_int(n_local), C.c_int(num_sequences), C.c_void_p(out_ptr)))
+
+    def gather_batch(self, batch, num_sequences):
+        """States of a TrackerBatch's trackers from every rank -> [num_sequences x 14] host array (synchronises)."""
+        out = np.zeros((num_sequences, 14))
+        self.ctx.check(self.lib.edsgpu_batch_gather_states_nccl(batch.h, self.h, C.c_int(num_sequences), _ptr(out, C.c_double)))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.edsgpu_comm_destroy(self.h)
             self.h = None

@@ -19,8 +19,8 @@ def lib():
     return edsgpu.load()
 
 
-def header_symbols():
-    txt = open(os.path.join(ROOT, "include", "edsgpu.h")).read()
+def header_symbols(name="edsgpu.h"):
+    txt = open(os.path.join(ROOT, "include", name)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(edsgpu_[a-z_0-9]+)\s*\(", txt)))
 
@@ -31,6 +31,19 @@ def test_every_declared_symbol_is_exported(lib):
     for s in syms:
         assert hasattr(lib, s), "libedsgpu.so does not export %s" % s
     assert sorted(edsgpu.SYMBOLS) == syms, "python binding and header disagree"
+
+
+def test_nccl_gather_library_exports_its_header(lib):
+    """libedsgpu_nccl.so (the final gather of a sharded batch, in the C++ host layer) loads next to libedsgpu.so and
+    exports every symbol include/edsgpu_nccl.h declares; nothing is called (no GPU, no communicator)."""
+    nl = edsgpu.load_nccl()
+    syms = header_symbols("edsgpu_nccl.h")
+    assert sorted(edsgpu.NCCL_SYMBOLS) == syms
+    for s in syms:
+        assert hasattr(nl, s), "libedsgpu_nccl.so does not export %s" % s
+    needed = subprocess.run(["ldd", edsgpu.NCCL_LIB_PATH], capture_output=True, text=True).stdout
+    assert "libnccl.so" in needed and "libedsgpu.so" in needed
+    assert "libnccl" not in subprocess.run(["ldd", edsgpu.LIB_PATH], capture_output=True, text=True).stdout  # the core library stays NCCL-free
 
 
 def test_version_and_struct_sizes(lib):
