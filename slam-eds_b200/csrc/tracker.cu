@@ -26,6 +26,8 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "depth.cuh"
 #include "frames.cuh"
@@ -33,22 +35,24 @@
 namespace {
 
 #ifndef EDS_TRK_THREADS
-#define EDS_TRK_THREADS 512
+#define EDS_TRK_THREADS 768
 #endif
-constexpr int TRK_THREADS = EDS_TRK_THREADS;  // one CTA per SM
+constexpr int TRK_THREADS = EDS_TRK_THREADS;  // one CTA per SM; 24 warps = 6 per scheduler leave 80 registers per thread
 constexpr int TRK_WARPS = TRK_THREADS / 32;
 constexpr int JLD = 20;         // floats per point row in shared memory (80 B: conflict-free 128-bit access)
 #ifndef EDS_N_CONS
 #define EDS_N_CONS 3
 #endif
-constexpr int N_CONS = EDS_N_CONS;               // consumer warps: own the outer-product accumulators (batches j = c mod N_CONS)
+constexpr int N_CONS = EDS_N_CONS;               // consumer PAIRS: pair c owns the batches j = c mod N_CONS of a block, its two warps split the rows
+constexpr int N_CONS_WARPS = 2 * N_CONS;
 constexpr int CTRL_WARP = TRK_WARPS - 1;         // evaluator CTA: the warp that fetches tasks from the global queue
-constexpr int N_PROD = TRK_WARPS - 1 - N_CONS;   // producer warps of an evaluator CTA
-constexpr int N_EVAL_WARPS = TRK_WARPS - 1;      // producers + consumers
+constexpr int COMB_WARP = TRK_WARPS - 2;         // evaluator CTA: the warp that combines the consumers' block totals and publishes the block
+constexpr int N_PROD = TRK_WARPS - 2 - N_CONS_WARPS;  // producer warps of an evaluator CTA
+constexpr int N_EVAL_WARPS = TRK_WARPS - 1;      // producers + consumers + combiner
 #ifndef EDS_RING_DEPTH
 #define EDS_RING_DEPTH 3
 #endif
-constexpr int RING_DEPTH = EDS_RING_DEPTH;   // ring slots per producer warp (three absorb stragglers)
+constexpr int RING_DEPTH = EDS_RING_DEPTH;   // ring slots per producer warp
 constexpr int N_SLOTS = RING_DEPTH * N_PROD; // ring of 32-point batches
 constexpr int NSLOT = 92;       // 78 + 12 + cost + block squared norm
 constexpr int MAX_BLOCKS = 16;  // residual blocks per problem (config.options.num_threads)
@@ -214,9 +218,11 @@ struct EvalShared {
     alignas(16) float ring[N_SLOTS][32][JLD];
     alignas(8) unsigned long long full_bar[N_SLOTS];
     alignas(8) unsigned long long empty_bar[N_SLOTS];
-    // block totals of the consumer warps, added up by one of them in turn (double-buffered by block)
+    // block totals of the consumer warps (double-buffered by block), added up by the combiner warp
     float cons_part[2][N_CONS][96];
     double cons_s[2][N_CONS];
+    alignas(8) unsigned long long part_full[2];    // consumers -> combiner: every consumer warp has left its totals of the block
+    alignas(8) unsigned long long part_empty[2];   // combiner -> consumers: the buffer has been read
     // mailbox hand-over between the control warp and the evaluator warps
     alignas(8) unsigned long long task_full[MAILBOX];   // control warp -> evaluators: task[slot] is complete (1 arrival)
     alignas(8) unsigned long long task_empty[MAILBOX];  // evaluators -> control warp: every evaluator warp is done with task[slot]
@@ -492,32 +498,37 @@ __device__ __forceinline__ int reduce96_base(unsigned lane) {
 // an order every evaluator warp follows; the batches (32 points) of consecutive EVAL tasks carry one running number g,
 // from which both sides derive ring slot and phase without talking to each other:
 //   producers  sweep the points (residual + analytic Jacobian row -> ring slot g mod N_SLOTS, mbarrier "full").  Warp p
-//              takes the batches g = p (mod N_PROD) and treats the tasks as ONE stream: its three-stage software
-//              pipeline (3-D points in flight | fp64 geometry + texture gathers in flight | finish + hand over) runs
-//              across task boundaries whenever the next task is already in the mailbox, so a block of only ~3 batches
-//              per warp does not pay the pipeline fill for every task.
-//   consumers  own the outer-product accumulators (90 fp32 registers per lane): consumer c takes the batches
-//              j = c (mod N_CONS) of the block (a fixed summation order), the block ends with a halving warp butterfly,
-//              one of them (in turn) adds the three partial sums in index order, applies the per-block loss and stores
+//              takes the batches g = p (mod N_PROD), one at a time and start to finish: latency is hidden by the NUMBER
+//              of producer warps (18 at 80 registers), not by a software pipeline inside the warp -- the scoreboards a
+//              warp has are shared by all its loads in flight, so fetches issued for a later batch made the finish of
+//              the current one wait for them (measured in round 2: DEPBAR on the texture scoreboard).
+//   consumers  own the outer-product accumulators.  Consumer PAIR c takes the batches j = c (mod N_CONS) of the block (a
+//              fixed summation order); its two warps split the 90 entries by rows ([0,4): 46 entries, [4,12): 44), so a
+//              consumer fits in 80 registers as well.  A block ends with a halving warp butterfly per warp, one warp (in
+//              turn) adds the partial sums in index order, applies the per-block loss and stores
 //              [rho' * JtJ (78) | rho' * Jtr (12) | 0.5 rho(s) | s] into the problem's slot of that block, then bumps
 //              the counter the problem's leader polls.
 // The ring has a whole number of slots per producer warp, so that the successive occupants of a slot always belong to
 // the SAME producer: it passes through every "empty" wait of its slots in order and can never test a parity that is two
 // phases stale.  The mirror image on the "full" side: the successive occupants of a slot within a block are drained by
-// the same consumer (N_SLOTS is a multiple of N_CONS), and the consumers' end-of-block barrier keeps them within one
-// block of each other.
+// the same consumer pair (N_SLOTS is a multiple of N_CONS), and the consumers' end-of-block barrier keeps them within
+// one block of each other.
 struct Roles {
     int pidx;        // producer index of this warp, -1 if not a producer
-    int cidx;        // consumer index of this warp, -1 if not a consumer
+    int cidx;        // consumer pair of this warp, -1 if not a consumer
+    int half;        // which rows of the pair's batches this consumer warp accumulates
 };
 __device__ __forceinline__ Roles make_roles() {
     const int warp = threadIdx.x >> 5;
     Roles r;
     static_assert(MAILBOX >= 2, "the evaluate entry needs two mailbox slots");
-    static_assert(N_CONS >= 2 && N_CONS <= 4, "consumer warps");
-    static_assert(N_SLOTS % N_CONS == 0, "ring slots per CTA must be a multiple of the consumer warps");
+    static_assert(N_CONS >= 2 && N_CONS <= 4, "consumer pairs");
+    static_assert(N_SLOTS % N_CONS == 0, "ring slots per CTA must be a multiple of the consumer pairs");
+    static_assert(N_PROD >= 1, "no producer warps");
     r.pidx = warp < N_PROD ? warp : -1;
-    r.cidx = (warp >= N_PROD && warp < N_PROD + N_CONS) ? warp - N_PROD : -1;
+    const bool cons = warp >= N_PROD && warp < N_PROD + N_CONS_WARPS;
+    r.cidx = cons ? (warp - N_PROD) >> 1 : -1;
+    r.half = cons ? (warp - N_PROD) & 1 : 0;
     return r;
 }
 
@@ -553,141 +564,137 @@ __device__ void final_slice(const TaskShared& ts) {
 
 __device__ void producer_warp_main(EvalShared& sh, const int pidx) {
     const int lane = threadIdx.x & 31;
-    // ---- cursor over this warp's batches of the task stream ----
-    struct Cursor { unsigned ord, base; int nb, t, start, n; bool known; } cur = {0u, 0u, 0, 0, 0, 0, false};
-    struct Ref { unsigned ord, g; int first, count; };  // task ordinal (mailbox slot = ord mod MAILBOX), running batch number, first point, points
-    enum { GOT_BATCH, GOT_NONE, GOT_SPECIAL };
-    unsigned released = 0;  // tasks [0, released) have been given back to the control warp by this warp
-    auto release_upto = [&](unsigned ord) {
-        __syncwarp();
-        for (; released < ord; ++released)
-            if (lane == 0) mbar_arrive(&sh.task_empty[released % MAILBOX]);
-    };
-    auto advance = [&](bool blocking, Ref& r) -> int {
-        for (;;) {
-            const unsigned slot = cur.ord % MAILBOX;
-            if (!cur.known) {
-                const unsigned parity = (cur.ord / MAILBOX) & 1u;
-                if (blocking) mbar_wait(&sh.task_full[slot], parity, 3);
-                else if (!mbar_test(&sh.task_full[slot], parity)) return GOT_NONE;
-                const TaskShared& ts = sh.task[slot];
-                if (ts.cmd != CMD_EVAL) return GOT_SPECIAL;
-                block_extent(ts.P.kf, ts.block, cur.start, cur.n, cur.nb);
-                cur.t = (pidx + N_PROD - (int)(cur.base % (unsigned)N_PROD)) % N_PROD;  // this warp's batches have g = pidx (mod N_PROD)
-                cur.known = true;
-            }
-            if (cur.t < cur.nb) {
-                r.ord = cur.ord; r.g = cur.base + (unsigned)cur.t;
-                r.first = cur.start + (cur.t << 5); r.count = min(32, cur.n - (cur.t << 5));
-                cur.t += N_PROD;
-                return GOT_BATCH;
-            }
-            cur.base += (unsigned)cur.nb; cur.ord++; cur.known = false;  // nothing (left) for this warp in the task
-            // A blocking look-up runs with an empty pipeline: whatever the cursor passes is finished for this warp and must
-            // be given back at once -- the control warp cannot fetch the task this warp is about to wait for before
-            // every warp has released the mailbox slot it goes into.
-            if (blocking) release_upto(cur.ord);
+    unsigned base = 0;  // running batch number at the start of the current task
+#ifdef EDS_TIMING
+    unsigned long long t_wait = 0, t_work = 0;
+#endif
+    for (unsigned ord = 0;; ++ord) {
+        const unsigned tslot = ord % MAILBOX;
+#ifdef EDS_TIMING
+        const unsigned long long t0 = gtime();
+#endif
+        mbar_wait(&sh.task_full[tslot], (ord / MAILBOX) & 1u, 3);
+#ifdef EDS_TIMING
+        const unsigned long long t1 = gtime();
+        t_wait += t1 - t0;
+#endif
+        const TaskShared& ts = sh.task[tslot];
+        const int cmd = ts.cmd;
+        if (cmd == CMD_EXIT) {
+#ifdef EDS_TIMING
+            if (lane == 0 && g_timing_cta == (int)blockIdx.x && pidx == 0) { atomicAdd(&g_timing[13], t_work); atomicAdd(&g_timing[14], t_wait); }
+#endif
+            return;
         }
-    };
-    // ---- pipeline stages ----
-    struct Stage { Taps T; float4 g4; float2 dw; PointGeo G; Ref ref; bool present; };
-    const PointGeo G0 = {0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const Kp kp0 = {0.0, 0.0, 1.0};
-    auto stage_a = [&](const Ref& r) -> Kp {  // 3-D points in flight
-        return (lane < r.count) ? load_kp(sh.task[r.ord % MAILBOX].P.kf, r.first + lane) : kp0;
-    };
-    auto stage_b = [&](Stage& s, const Kp& kp) {  // geometry, then gathers + gradient record in flight
-        const TaskShared& ts = sh.task[s.ref.ord % MAILBOX];
-        const KfDev& kf = ts.P.kf;
-        s.G = G0;
-        s.g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        s.dw = make_float2(0.f, 0.f);
-        if (lane < s.ref.count) {
-            point_geometry(kf, ts.ec, kp, s.G);
-            s.g4 = __ldg(&kf.gxy[s.ref.first + lane]);
-            s.dw = __ldg(&kf.dw[s.ref.first + lane]);
-        }
-        s.T = fetch_taps(uniform_handle(ts.P.frame), s.G.col, s.G.row);
-    };
-    auto stage_c = [&](const Stage& s) {  // finish + hand over
-        const TaskShared& ts = sh.task[s.ref.ord % MAILBOX];
-        const ProblemDesc& P = ts.P;
-        if (s.ref.ord > released) release_upto(s.ref.ord);  // every batch of the earlier tasks has been handed over
-        float J[12], r = 0.f;
-        if (lane < s.ref.count) {
-            point_finish<true>(P.kf, ts.ec, ts.ec.blk[ts.block], ts.inv_norm, s.G, s.T, s.g4, s.dw, J, r);
-            if (P.eval_only) {  // parity/debug entry: residuals and Jacobian rows written out
-                const int idx = s.ref.first + lane;
-                P.residuals[idx] = r;
-                if (P.jac_out) {
-#pragma unroll
-                    for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * idx + k] = J[k];
-                }
-            }
+        if (cmd == CMD_FINAL) {
+            final_slice(ts);
         } else {
+            const ProblemDesc& P = ts.P;
+            const KfDev& kf = P.kf;
+            int start, n, nb;
+            block_extent(kf, ts.block, start, n, nb);
+            const cudaTextureObject_t frame = uniform_handle(P.frame);
+            const float* bc = ts.ec.blk[ts.block];
+            const float inv_norm = ts.inv_norm;
+            // this warp's batches have running number g = pidx (mod N_PROD)
+            for (int t = (pidx + N_PROD - (int)(base % (unsigned)N_PROD)) % N_PROD; t < nb; t += N_PROD) {
+                const int i = (t << 5) + lane;
+                const bool live = i < n;
+                const int idx = start + (live ? i : n - 1);  // idle lanes of a ragged batch repeat the block's last point, their row is zeroed
+#ifdef EDS_TIMING
+                const long long tp0 = clock64();
+#endif
+                const Kp kp = load_kp(kf, idx);
+                const float4 g4 = __ldg(&kf.gxy[idx]);
+                const float2 dw = __ldg(&kf.dw[idx]);
+                PointGeo G;
+                point_geometry(kf, ts.ec, kp, G);
+#ifdef EDS_TIMING
+                asm volatile("" ::"r"(G.col), "r"(G.row), "f"(G.tc), "f"(G.tr));
+                const long long tp1 = clock64();
+#endif
+                const Taps T = fetch_taps(frame, G.col, G.row);
+#ifdef EDS_TIMING
+                asm volatile("" ::"f"(T.q00.x), "f"(T.q10.x), "f"(T.q01.x), "f"(T.q11.x), "f"(g4.x), "f"(dw.x));
+                const long long tp2 = clock64();
+#endif
+                float J[12], r;
+                point_finish<true>(kf, ts.ec, bc, inv_norm, G, T, g4, dw, J, r);
+#ifdef EDS_TIMING
+                asm volatile("" ::"f"(J[0]), "f"(J[5]), "f"(J[11]), "f"(r));
+                const long long tp3 = clock64();
+#endif
+                if (P.eval_only && live) {  // parity/debug entry: residuals and Jacobian rows written out
+                    P.residuals[idx] = r;
+                    if (P.jac_out) {
 #pragma unroll
-            for (int k = 0; k < 12; ++k) J[k] = 0.f;
-        }
-        const unsigned slot = s.ref.g % (unsigned)N_SLOTS, phase = (s.ref.g / (unsigned)N_SLOTS) & 1u;
+                        for (int k = 0; k < 12; ++k) P.jac_out[(size_t)12 * idx + k] = J[k];
+                    }
+                }
+                const float keep = live ? 1.f : 0.f;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) J[k] *= keep;
+                r *= keep;
+                const unsigned g = base + (unsigned)t;
+                const unsigned slot = g % (unsigned)N_SLOTS, phase = (g / (unsigned)N_SLOTS) & 1u;
 #ifdef EDS_TIMING
-        const long long te0 = clock64();
+                const long long te0 = clock64();
 #endif
-        mbar_wait(&sh.empty_bar[slot], phase ^ 1u, 1);
+                mbar_wait(&sh.empty_bar[slot], phase ^ 1u, 1);
 #ifdef EDS_TIMING
-        if (lane == 0 && g_timing_cta == (int)blockIdx.x) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
+                if (lane == 0 && g_timing_cta == (int)blockIdx.x) { atomicAdd(&g_timing[18], (unsigned long long)(clock64() - te0)); atomicAdd(&g_timing[19], 1ull); }
 #endif
-        float4* dst = reinterpret_cast<float4*>(&sh.ring[slot][lane][0]);
-        dst[0] = make_float4(J[0], J[1], J[2], J[3]);
-        dst[1] = make_float4(J[4], J[5], J[6], J[7]);
-        dst[2] = make_float4(J[8], J[9], J[10], J[11]);
-        dst[3] = make_float4(r, 0.f, 0.f, 0.f);
-        __syncwarp();  // all 32 rows are written: one elected arrival publishes the slot
-        if (lane == 0) mbar_arrive(&sh.full_bar[slot]);
-    };
-    // one pipeline step: `cur_s` holds a batch with its gathers in flight, `nxt_s` (its reference already set) receives the
-    // geometry of the following batch whose 3-D points are in kp, and the batch after that is looked up without
-    // blocking: if its task has not arrived yet the pipeline simply runs dry
-    auto step = [&](Stage& cur_s, Stage& nxt_s, Kp& kp) {
-        const Kp kpb = kp;
-        Ref ra;
-        const bool got = advance(false, ra) == GOT_BATCH;
-        if (got) kp = stage_a(ra);
-        if (nxt_s.present) stage_b(nxt_s, kpb);
-        if (cur_s.present) stage_c(cur_s);
-        cur_s.present = got;  // the batch after next becomes the next one
-        cur_s.ref = ra;
-    };
-    for (;;) {
-        Stage s0, s1;
-        Kp kp = kp0;
-        const int got = advance(true, s0.ref);
-        if (got == GOT_SPECIAL) {  // the stream stops at a task that is not an evaluation: the pipeline is empty here
-            const TaskShared& ts = sh.task[cur.ord % MAILBOX];
-            const int cmd = ts.cmd;
-            release_upto(cur.ord);
-            if (cmd == CMD_FINAL) final_slice(ts);
-            cur.ord++;  // a special task has no batches: the running number stays
-            release_upto(cur.ord);
-            if (cmd == CMD_EXIT) return;
-            continue;
+                float4* dst = reinterpret_cast<float4*>(&sh.ring[slot][lane][0]);
+                dst[0] = make_float4(J[0], J[1], J[2], J[3]);
+                dst[1] = make_float4(J[4], J[5], J[6], J[7]);
+                dst[2] = make_float4(J[8], J[9], J[10], J[11]);
+                dst[3] = make_float4(r, 0.f, 0.f, 0.f);
+                __syncwarp();  // all 32 rows are written: one elected arrival publishes the slot
+                if (lane == 0) mbar_arrive(&sh.full_bar[slot]);
+#ifdef EDS_TIMING
+                if (lane == 0 && g_timing_cta == (int)blockIdx.x && pidx == 0) {
+                    atomicAdd(&g_timing[27], (unsigned long long)(tp1 - tp0)); atomicAdd(&g_timing[28], (unsigned long long)(tp2 - tp1));
+                    atomicAdd(&g_timing[29], (unsigned long long)(tp3 - tp2)); atomicAdd(&g_timing[30], (unsigned long long)(clock64() - tp3));
+                    atomicAdd(&g_timing[31], 1ull);
+                }
+#endif
+            }
+            base += (unsigned)nb;
         }
-        s0.present = true;
-        stage_b(s0, stage_a(s0.ref));
-        s1.present = advance(false, s1.ref) == GOT_BATCH;
-        if (s1.present) kp = stage_a(s1.ref);
-        // a stage may be absent (the look-ahead found nothing at that moment): the bubble travels through the pipeline,
-        // no batch the cursor has handed out is ever dropped
-        do {
-            step(s0, s1, kp);  // finishes s0, fills s1; s0 then describes the batch after s1
-            step(s1, s0, kp);
-        } while (s0.present || s1.present);
-        // ran dry (the look-ahead never skips a batch, it only stops early): everything before the cursor's task is handed over
-        release_upto(cur.ord);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.task_empty[tslot]);
+#ifdef EDS_TIMING
+        t_work += gtime() - t1;
+#endif
     }
 }
 
+// the two halves of a consumer pair: rows [0,4) of the upper triangle of [J r]^T [J r] (46 entries) and rows [4,12) (44)
+typedef RowBlock<0, 4> ConsLo;
+typedef RowBlock<4, 12> ConsHi;
+constexpr int CONS_LO = 46, CONS_HI = 44;
+static_assert(ConsLo::count() == CONS_LO && ConsHi::count() == CONS_HI, "row split");
+
+// 48 per-lane partial sums -> warp totals; lane l ends with entries base48(l)+{0,1,2} (lanes 2k and 2k+1 hold the same three)
+__device__ __forceinline__ void reduce48(float* acc, unsigned lane) {
+    butterfly_step<24, 16>(acc, lane);
+    butterfly_step<12, 8>(acc, lane);
+    butterfly_step<6, 4>(acc, lane);
+    butterfly_step<3, 2>(acc, lane);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+}
+__device__ __forceinline__ int reduce48_base(unsigned lane) {
+    return 24 * ((lane >> 4) & 1) + 12 * ((lane >> 3) & 1) + 6 * ((lane >> 2) & 1) + 3 * ((lane >> 1) & 1);
+}
+
+template <int HALF>
 __device__ void consumer_warp_main(EvalShared& sh, const int cidx) {
+    typedef typename std::conditional<HALF == 0, ConsLo, ConsHi>::type Rows;
+    constexpr int COUNT = HALF == 0 ? CONS_LO : CONS_HI;   // entries of this half
+    constexpr int FIRST = HALF == 0 ? 0 : CONS_LO;         // their position among the 90
     const int lane = threadIdx.x & 31;
+    const int widx = 2 * cidx + HALF;  // consumer warp number
     unsigned base = 0, block_counter = 0;  // running batch number, EVAL tasks seen
 #ifdef EDS_TIMING
     unsigned long long t_wait = 0, t_work = 0, n_work = 0;
@@ -710,10 +717,10 @@ __device__ void consumer_warp_main(EvalShared& sh, const int cidx) {
             const ProblemDesc& P = ts.P;
             int start, n, nb;
             block_extent(P.kf, ts.block, start, n, nb);
-            float acc[96];
+            float acc[48];
 #pragma unroll
-            for (int i = 0; i < 96; ++i) acc[i] = 0.f;
-            double s_acc = 0.0;  // sum of r^2 in fp64 (the cost decides accept / reject and the tolerances)
+            for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+            double s_acc = 0.0;  // sum of r^2 in fp64 (the cost decides accept / reject and the tolerances), kept by the upper half
             unsigned slot, phase;
             {
                 const unsigned g0 = base + (unsigned)cidx;
@@ -727,76 +734,33 @@ __device__ void consumer_warp_main(EvalShared& sh, const int cidx) {
 #endif
                 mbar_wait(&sh.full_bar[slot], phase, 2);
 #ifdef EDS_TIMING
-                if (lane == 0 && g_timing_cta == (int)blockIdx.x && cidx == 0) { atomicAdd(&g_timing[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_timing[17], 1ull); }
+                if (lane == 0 && g_timing_cta == (int)blockIdx.x && widx == 0) { atomicAdd(&g_timing[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&g_timing[17], 1ull); }
 #endif
                 float v[16];
-                ConsRows::load(sh.ring[slot], lane, v);
-                __syncwarp();  // every lane has its row in registers: one elected arrival frees the slot
+                Rows::load(sh.ring[slot], lane, v);
+                __syncwarp();  // every lane has its row in registers: one elected arrival per half frees the slot
                 if (lane == 0) mbar_arrive(&sh.empty_bar[slot]);
-                const float rr = ConsRows::accumulate(v, acc);
-                s_acc += (double)rr * (double)rr;
+                const float rr = Rows::accumulate(v, acc);
+                if (HALF == 1) s_acc += (double)rr * (double)rr;
             }
-            reduce96(acc, lane);
+            reduce48(acc, lane);
+            if (HALF == 1) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
-            // every consumer leaves its block totals in shared memory; they take turns at adding them up (always in
-            // index order, so the sum does not depend on whose turn it is) and publishing the block
-            const unsigned buf = block_counter & 1u;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) sh.cons_part[buf][cidx][3 * lane + i] = acc[i];
-            if (lane == 0) sh.cons_s[buf][cidx] = s_acc;
-            asm volatile("bar.sync 2, %0;" ::"n"(32 * N_CONS) : "memory");
-            if ((int)(block_counter % (unsigned)N_CONS) == cidx) {
-                float tot[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) tot[i] = sh.cons_part[buf][0][3 * lane + i];
-                double s_tot = sh.cons_s[buf][0];
-#pragma unroll
-                for (int c = 1; c < N_CONS; ++c) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) tot[i] += sh.cons_part[buf][c][3 * lane + i];
-                    s_tot += sh.cons_s[buf][c];
-                }
-                double rho0, rho1;
-                loss_eval(P.loss_type, ts.loss_a, s_tot, &rho0, &rho1);
-                const int base_e = reduce96_base(lane);
-                double* dst = ts.slots + ts.block * NSLOT;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int e = base_e + i;
-                    if (e < 90) dst[ConsRows::slot(e)] = rho1 * (double)tot[i];
-                }
-                if (lane == 0) { dst[90] = 0.5 * rho0; dst[91] = s_tot; }
-                // The lanes' stores happen before the warp barrier, the barrier before the elected lane's release: the
-                // release is cumulative over what the lane has synchronised with, so the leader that acquires the count
-                // sees every lane's sums (the CUTLASS semaphore pattern: barrier, then one thread's red.release.gpu).
-                __syncwarp();
-                if (!P.eval_only) {
-                    if (lane == 0) red_release_add(ts.done, 1u);
-                } else {
-                    // parity/debug entry (track_eval_kernel): the block that finishes last sums the blocks
-                    unsigned before = 0;
-                    if (lane == 0) { __threadfence(); before = atomicAdd(ts.done, 1u); }
-                    before = __shfl_sync(0xffffffffu, before, 0);
-                    if (before == (unsigned)(P.kf.B - 1) && P.eval_out) {
-                        __threadfence();
-                        const int B = P.kf.B;
-                        for (int e = lane; e < 91; e += 32) {
-                            double v = 0.0;
-                            for (int b = 0; b < B; ++b) v += __ldcg(&ts.slots[b * NSLOT + e]);
-                            if (e == 90) P.eval_out[0] = v;
-                            else if (e >= 78) P.eval_out[1 + 144 + (e - 78)] = v;
-                            else {
-                                int a = 0, rem = e;
-                                while (rem >= 12 - a) { rem -= 12 - a; ++a; }
-                                const int c2 = a + rem;
-                                P.eval_out[1 + 12 * a + c2] = v;
-                                P.eval_out[1 + 12 * c2 + a] = v;
-                            }
-                        }
-                    }
-                }
+                for (int o = 16; o > 0; o >>= 1) s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
             }
+            // every consumer leaves its block totals in shared memory (by entry number) for the combiner warp and moves on to
+            // the next block; the buffer of block k is reused by block k + 2, once the combiner has read it
+            const unsigned buf = block_counter & 1u, use = block_counter >> 1;
+            if (use > 0) mbar_wait(&sh.part_empty[buf], (use - 1u) & 1u, 6);
+            if ((lane & 1) == 0) {
+                const int b0 = reduce48_base(lane);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (b0 + i < COUNT) sh.cons_part[buf][cidx][FIRST + b0 + i] = acc[i];
+            }
+            if (HALF == 1 && lane == 0) sh.cons_s[buf][cidx] = s_acc;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.part_full[buf]);
             base += (unsigned)nb;
             block_counter++;
         }
@@ -807,8 +771,84 @@ __device__ void consumer_warp_main(EvalShared& sh, const int cidx) {
 #endif
     }
 #ifdef EDS_TIMING
-    if (lane == 0 && g_timing_cta == (int)blockIdx.x && cidx == 0) { atomicAdd(&g_timing[3], t_work); atomicAdd(&g_timing[4], t_wait); atomicAdd(&g_timing[5], n_work); }
+    if (lane == 0 && g_timing_cta == (int)blockIdx.x && widx == 0) { atomicAdd(&g_timing[3], t_work); atomicAdd(&g_timing[4], t_wait); atomicAdd(&g_timing[5], n_work); }
 #endif
+}
+
+// Combiner warp of an evaluator CTA: follows the task stream like the other evaluator warps; for every EVAL task it waits
+// for the consumers' block totals, adds them in index order (a fixed summation order), applies the per-block loss and
+// publishes the block to the problem's leader.  The consumers never wait for this: the loss (fp64 sqrt / division), the
+// global stores and the release run beside the accumulation of the next block.
+__device__ void combiner_warp_main(EvalShared& sh) {
+    const int lane = threadIdx.x & 31;
+    unsigned block_counter = 0;
+    for (unsigned ord = 0;; ++ord) {
+        const unsigned tslot = ord % MAILBOX;
+        mbar_wait(&sh.task_full[tslot], (ord / MAILBOX) & 1u, 3);
+        const TaskShared& ts = sh.task[tslot];
+        const int cmd = ts.cmd;
+        if (cmd == CMD_EXIT) break;
+        if (cmd == CMD_FINAL) {
+            final_slice(ts);
+        } else {
+            const ProblemDesc& P = ts.P;
+            const unsigned buf = block_counter & 1u, use = block_counter >> 1;
+            mbar_wait(&sh.part_full[buf], use & 1u, 7);
+            float tot[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) tot[i] = sh.cons_part[buf][0][3 * lane + i];
+            double s_tot = sh.cons_s[buf][0];
+#pragma unroll
+            for (int c = 1; c < N_CONS; ++c) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) tot[i] += sh.cons_part[buf][c][3 * lane + i];
+                s_tot += sh.cons_s[buf][c];
+            }
+            __syncwarp();  // every lane has read its entries: the buffer goes back to the consumers
+            if (lane == 0) mbar_arrive(&sh.part_empty[buf]);
+            double rho0, rho1;
+            loss_eval(P.loss_type, ts.loss_a, s_tot, &rho0, &rho1);
+            double* dst = ts.slots + ts.block * NSLOT;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int e = 3 * lane + i;
+                if (e < 90) dst[ConsRows::slot(e)] = rho1 * (double)tot[i];
+            }
+            if (lane == 0) { dst[90] = 0.5 * rho0; dst[91] = s_tot; }
+            // The lanes' stores happen before the warp barrier, the barrier before the elected lane's release: the
+            // release is cumulative over what the lane has synchronised with, so the leader that acquires the count
+            // sees every lane's sums (the CUTLASS semaphore pattern: barrier, then one thread's red.release.gpu).
+            __syncwarp();
+            if (!P.eval_only) {
+                if (lane == 0) red_release_add(ts.done, 1u);
+            } else {
+                // parity/debug entry (track_eval_kernel): the block that finishes last sums the blocks
+                unsigned before = 0;
+                if (lane == 0) { __threadfence(); before = atomicAdd(ts.done, 1u); }
+                before = __shfl_sync(0xffffffffu, before, 0);
+                if (before == (unsigned)(P.kf.B - 1) && P.eval_out) {
+                    __threadfence();
+                    const int B = P.kf.B;
+                    for (int e = lane; e < 91; e += 32) {
+                        double v = 0.0;
+                        for (int b = 0; b < B; ++b) v += __ldcg(&ts.slots[b * NSLOT + e]);
+                        if (e == 90) P.eval_out[0] = v;
+                        else if (e >= 78) P.eval_out[1 + 144 + (e - 78)] = v;
+                        else {
+                            int a = 0, rem = e;
+                            while (rem >= 12 - a) { rem -= 12 - a; ++a; }
+                            const int c2 = a + rem;
+                            P.eval_out[1 + 12 * a + c2] = v;
+                            P.eval_out[1 + 12 * c2 + a] = v;
+                        }
+                    }
+                }
+            }
+            block_counter++;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.task_empty[tslot]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1005,11 +1045,8 @@ __device__ int lm_advance_warp(LeaderProblem& sh, const ProblemWork* w) {
     const unsigned long long td1 = gtime();
     unsigned long long td2 = td1, td3 = td1, td4 = td1;
 #endif
-    // row `lane` of the scaled system once a new point has been taken (kept in registers for the solve)
-    double Hr[12];
-#pragma unroll
-    for (int q = 0; q < 12; ++q) Hr[q] = 0.0;
     if (take) {
+        double Hr[12];  // row `lane` of the system at the new point
         // EvaluateGradientAndJacobian: Jacobi scaling (iteration 0 only), scaled system,
         // gradient max norm || x - Plus(x, -g) ||_inf, ||x||
         // The unit-norm retraction makes n = [0(6), v/|v|] an exact null direction of J.
@@ -1098,19 +1135,16 @@ __device__ int lm_advance_warp(LeaderProblem& sh, const ProblemWork* w) {
         if (!reuse && lane < 12) lm.diag[lane] = fmin(fmax(lm.Hs[tri_index(lane, lane)], 1e-6), 1e32);
         __syncwarp();
         reuse = 1;
-        // lane i < 12 owns row i of the damped matrix (a) and of the un-damped one (h)
-        double a[12], h[12];
+        // lane i < 12 owns row i of the damped matrix; the un-damped scaled system stays in shared memory (lm.Hs), where this
+        // call or an earlier one left it: nothing of it is carried in registers across the solve
+        double a[12];
         const int li = lane < 12 ? lane : 0;
         const double damping = lm.diag[li] / radius;  // D^2 of this lane's diagonal entry
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
-            if (take) {
-                h[j] = Hr[j];  // this call has just formed the scaled system
-            } else {
-                const double v = lm.Hs[li <= j ? tri_index(li, j) : tri_index(j, li)];
-                h[j] = (lane < 12) ? v : 0.0;
-            }
-            a[j] = (j == lane) ? h[j] + damping : h[j];
+            const double v = lm.Hs[li <= j ? tri_index(li, j) : tri_index(j, li)];
+            const double hj = (lane < 12) ? v : 0.0;
+            a[j] = (j == lane) ? hj + damping : hj;
         }
         // Right-looking Cholesky in registers with the forward substitution L z = gs folded in.  After
         // step k lane i >= k holds L[i][k] in a[k]; lane k keeps its row j > k UNSCALED (L[k][k] L[j][k]),
@@ -1146,9 +1180,9 @@ __device__ int lm_advance_warp(LeaderProblem& sh, const ProblemWork* w) {
         ok = ok && __all_sync(FULL, isfinite(step));
         if (ok) {
             // model_cost_change = -step^T (gs + 0.5 Hs step)
-            double hv = 0.0;
+            double hv = 0.0;  // lanes >= 12 have step = 0 and gsl = 0: whatever they read drops out of the sum
 #pragma unroll
-            for (int j = 0; j < 12; ++j) hv += h[j] * __shfl_sync(FULL, step, j);
+            for (int j = 0; j < 12; ++j) hv += lm.Hs[li <= j ? tri_index(li, j) : tri_index(j, li)] * __shfl_sync(FULL, step, j);
             const double gsl = (lane < 12) ? lm.gs[li] : 0.0;
             mcc = -warp_sum(step * (gsl + 0.5 * hv));
             ok = mcc > 0.0;
@@ -1296,11 +1330,15 @@ __device__ void leader_warp_main(LeaderProblem& lp, const ProblemDesc* __restric
 __device__ __forceinline__ void init_barriers(EvalShared& sh) {
     if (threadIdx.x < N_SLOTS) {
         mbar_init(&sh.full_bar[threadIdx.x], 1);   // the elected lane of the producer warp that filled the slot
-        mbar_init(&sh.empty_bar[threadIdx.x], 1);  // the elected lane of the consumer warp that drained it
+        mbar_init(&sh.empty_bar[threadIdx.x], 2);  // the elected lanes of the two consumer warps (row halves) that drained it
     }
     if (threadIdx.x < MAILBOX) {
         mbar_init(&sh.task_full[threadIdx.x], 1);              // the elected lane of the control warp
         mbar_init(&sh.task_empty[threadIdx.x], N_EVAL_WARPS);  // one elected lane per evaluator warp
+    }
+    if (threadIdx.x < 2) {
+        mbar_init(&sh.part_full[threadIdx.x], N_CONS_WARPS);   // one elected lane per consumer warp
+        mbar_init(&sh.part_empty[threadIdx.x], 1);             // the elected lane of the combiner warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -1398,7 +1436,9 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
     }
     const Roles role = make_roles();
     if (role.pidx >= 0) producer_warp_main(sh, role.pidx);
-    else consumer_warp_main(sh, role.cidx);
+    else if (role.cidx < 0) combiner_warp_main(sh);
+    else if (role.half == 0) consumer_warp_main<0>(sh, role.cidx);
+    else consumer_warp_main<1>(sh, role.cidx);
 }
 
 // parity/debug entry (edsgpu_tracker_evaluate): one full evaluation at P.state, residuals and Jacobian rows written out,
@@ -1437,7 +1477,9 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_eval_kernel(const Proble
     }
     const Roles role = make_roles();
     if (role.pidx >= 0) producer_warp_main(sh, role.pidx);
-    else consumer_warp_main(sh, role.cidx);
+    else if (role.cidx < 0) combiner_warp_main(sh);
+    else if (role.half == 0) consumer_warp_main<0>(sh, role.cidx);
+    else consumer_warp_main<1>(sh, role.cidx);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -77,6 +77,8 @@ def main():
             t[3] / m / 1e3, t[4] / m / 1e3, t[13] / m / 1e3, t[14] / m / 1e3, m))
         print("  consumer 0 wait-full %.0f cycles/batch, producers wait-empty %.0f cycles/batch, control warp fetch %.2f us/task" % (
             t[16] / max(t[17], 1), t[18] / max(t[19], 1), t[20] / max(t[21], 1) / 1e3))
+        q = max(t[31], 1)
+        print("  producer 0, cycles per batch: loads+geometry %.0f  gathers %.0f  finish %.0f  ring %.0f  (%d batches)" % (t[27] / q, t[28] / q, t[29] / q, t[30] / q, q))
         k = max(t[10], 1)
         print("  leader step parts [us]: tree %.2f  decide %.2f  solve %.2f  plus %.2f  publish %.2f (steps %d)" % (
             t[6] / k / 1e3, t[7] / k / 1e3, t[8] / k / 1e3, t[9] / k / 1e3, t[15] / k / 1e3, k))
