@@ -64,7 +64,7 @@ constexpr int LEAD_WARPS = 16;             // leader warps of a leader CTA (its 
 constexpr int MAX_LEAD_CTAS = 8;
 constexpr double kEps = 1e-05;  // PhotometricError.hpp:200
 
-enum { CMD_EVAL = 1, CMD_FINAL = 2, CMD_DONE = 3, CMD_EXIT = 4 };
+enum { CMD_EVAL = 1, CMD_FINAL = 2, CMD_DONE = 3, CMD_EXIT = 4, CMD_NOP = 5 };  // NOP: a reserved queue ticket that turned out not to be needed
 
 #ifdef EDS_TIMING
 __device__ unsigned long long g_timing[32];
@@ -588,7 +588,7 @@ __device__ void producer_warp_main(EvalShared& sh, const int pidx) {
         }
         if (cmd == CMD_FINAL) {
             final_slice(ts);
-        } else {
+        } else if (cmd == CMD_EVAL) {
             const ProblemDesc& P = ts.P;
             const KfDev& kf = P.kf;
             int start, n, nb;
@@ -713,7 +713,7 @@ __device__ void consumer_warp_main(EvalShared& sh, const int cidx) {
         if (cmd == CMD_EXIT) break;
         if (cmd == CMD_FINAL) {
             final_slice(ts);
-        } else {
+        } else if (cmd == CMD_EVAL) {
             const ProblemDesc& P = ts.P;
             int start, n, nb;
             block_extent(P.kf, ts.block, start, n, nb);
@@ -790,7 +790,7 @@ __device__ void combiner_warp_main(EvalShared& sh) {
         if (cmd == CMD_EXIT) break;
         if (cmd == CMD_FINAL) {
             final_slice(ts);
-        } else {
+        } else if (cmd == CMD_EVAL) {
             const ProblemDesc& P = ts.P;
             const unsigned buf = block_counter & 1u, use = block_counter >> 1;
             mbar_wait(&sh.part_full[buf], use & 1u, 7);
@@ -923,10 +923,15 @@ struct LeaderLink {
 
 // Leader warp: append `n` tasks (block 0..n-1 of problem pid, or n CMD_EXIT tasks) to the queue.  Everything the tasks
 // refer to must have been written and fenced by the calling lanes before.
-__device__ void push_tasks(const LeaderLink& L, int n, int cmd) {
+// `reserved` (lane 0): first of n tickets taken earlier with reserve_tickets, or RESERVE_NOW.
+constexpr unsigned RESERVE_NOW = 0xffffffffu;
+__device__ __forceinline__ unsigned reserve_tickets(const LeaderLink& L, int n) {  // lane 0's return value counts
+    return ((threadIdx.x & 31) == 0) ? atomicAdd(&L.ctl->tail, (unsigned)n) : 0u;
+}
+__device__ void push_tasks(const LeaderLink& L, int n, int cmd, unsigned reserved = RESERVE_NOW) {
     const int lane = threadIdx.x & 31;
-    unsigned t0 = 0;
-    if (lane == 0) t0 = atomicAdd(&L.ctl->tail, (unsigned)n);
+    unsigned t0 = reserved;
+    if (__shfl_sync(0xffffffffu, reserved, 0) == RESERVE_NOW) t0 = reserve_tickets(L, n);
     t0 = __shfl_sync(0xffffffffu, t0, 0);
     for (int i = lane; i < n; i += 32) {
         const unsigned ticket = t0 + (unsigned)i;
@@ -939,6 +944,9 @@ __device__ void push_tasks(const LeaderLink& L, int n, int cmd) {
 __device__ void leader_publish(LeaderProblem& lp, const LeaderLink& L, const double* xe, int cmd) {
     const int lane = threadIdx.x & 31;
     const int B = lp.P.kf.B;
+    // the round trip of the ticket counter runs beside the computation of the constants.  Not earlier: an evaluator that
+    // draws a ticket waits for its entry, so a ticket must not stay unfilled for long
+    const unsigned reserved = (cmd != CMD_DONE) ? reserve_tickets(L, B) : 0u;
     compute_eval_const(lp.ec, xe, lp.A, B, cmd);
     if (cmd == CMD_DONE) return;  // nothing left to evaluate
     // the used prefix of EvalConst (R, t, v + B block records) and the command go to global memory
@@ -947,9 +955,10 @@ __device__ void leader_publish(LeaderProblem& lp, const LeaderLink& L, const dou
     int* dst = reinterpret_cast<int*>(&L.w->ec);
     for (int i = lane; i < nwords; i += 32) dst[i] = src[i];
     if (lane == 0) L.w->ec.cmd = cmd;
-    __threadfence();  // each lane orders its own stores before the queue entries any lane writes after the warp barrier
+    // the lanes' stores are ordered before the queue entries ANY lane writes after this barrier: the entries are stored with
+    // release semantics, which is cumulative over what the writing lane has synchronised with
     __syncwarp();
-    push_tasks(L, B, cmd);
+    push_tasks(L, B, cmd, reserved);
 }
 
 // Leader warp: wait until the problem's completion counter has reached `target`.
@@ -975,28 +984,38 @@ __device__ int lm_advance_warp(LeaderProblem& sh, const ProblemWork* w) {
 #ifdef EDS_TIMING
     unsigned long long tt0 = gtime();
 #endif
-    // fixed pairwise tree over the residual blocks: deterministic and independent of the launch shape
+    // fixed pairwise tree over the residual blocks: deterministic and independent of the launch shape.  The tree is over
+    // MAX_BLOCKS leaves, missing blocks are zeros; with B <= 8 its first level only adds zeros, so the 8-leaf tree gives the
+    // same bits with half the loads.  All loads of the three entries a lane owns are issued before the first addition.
     bool fin = true;
+    if (B <= MAX_BLOCKS / 2) {
+        double v[3][MAX_BLOCKS / 2];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int e = lane + 32 * k;
-        if (e < 91) {
-            // the tree is over MAX_BLOCKS leaves, missing blocks are zeros; with B <= 8 its first level only
-            // adds zeros, so the 8-leaf tree gives the same bits with half the loads
+        for (int k = 0; k < 3; ++k) {
+            const int e = min(lane + 32 * k, 90);
+#pragma unroll
+            for (int b = 0; b < MAX_BLOCKS / 2; ++b) v[k][b] = (b < B) ? __ldcg(&w->slots[b][e]) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int h = MAX_BLOCKS / 4; h > 0; h >>= 1)
+#pragma unroll
+                for (int b = 0; b < h; ++b) v[k][b] += v[k][b + h];
+            sh.sum[min(lane + 32 * k, 90)] = v[k][0];  // the surplus lanes of the last pass repeat entry 90
+            fin = fin && isfinite(v[k][0]);
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            const int e = min(lane + 32 * k, 90);
             double v[MAX_BLOCKS];
-            if (B <= MAX_BLOCKS / 2) {
 #pragma unroll
-                for (int b = 0; b < MAX_BLOCKS / 2; ++b) v[b] = (b < B) ? __ldcg(&w->slots[b][e]) : 0.0;
-            } else {
+            for (int b = 0; b < MAX_BLOCKS; ++b) v[b] = (b < B) ? __ldcg(&w->slots[b][e]) : 0.0;
 #pragma unroll
-                for (int b = 0; b < MAX_BLOCKS; ++b) v[b] = (b < B) ? __ldcg(&w->slots[b][e]) : 0.0;
+            for (int h = MAX_BLOCKS / 2; h > 0; h >>= 1)
 #pragma unroll
-                for (int b = 0; b < MAX_BLOCKS / 2; ++b) v[b] += v[b + MAX_BLOCKS / 2];
-            }
-#pragma unroll
-            for (int w = MAX_BLOCKS / 4; w > 0; w >>= 1)
-#pragma unroll
-                for (int b = 0; b < w; ++b) v[b] += v[b + w];
+                for (int b = 0; b < h; ++b) v[b] += v[b + h];
             sh.sum[e] = v[0];
             fin = fin && isfinite(v[0]);
         }
@@ -1371,7 +1390,7 @@ __device__ void control_warp_main(EvalShared& sh, const ProblemDesc* __restrict_
         }
         const int pid = (int)(payload & 0xfffffu), block = (int)((payload >> 20) & 63u), cmd = (int)(payload >> 26);
         TaskShared& ts = sh.task[slot];
-        if (cmd != CMD_EXIT) {
+        if (cmd != CMD_EXIT && cmd != CMD_NOP) {
             // one round trip: the descriptor (immutable during the launch) and the whole EvalConst the leader published
             // before the queue entry (acquired above; read past the non-coherent L1)
             ProblemWork* w = work + pid;
@@ -1424,7 +1443,8 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_lm_kernel(const ProblemD
     if ((int)blockIdx.x < n_lead) {
         LeadShared& ls = *reinterpret_cast<LeadShared*>(smem_raw);
         if (warp >= LEAD_WARPS) return;
-        leader_warp_main(ls.prob[warp], problems, work, ctl, entries, mask, count, (int)blockIdx.x * LEAD_WARPS + warp, n_lead * LEAD_WARPS,
+        // problems are dealt to the leader CTAs round-robin: a small batch spreads over all of them (fewer warps share an SM)
+        leader_warp_main(ls.prob[warp], problems, work, ctl, entries, mask, count, warp * n_lead + (int)blockIdx.x, n_lead * LEAD_WARPS,
                          (int)gridDim.x - n_lead);
         return;
     }
@@ -1765,7 +1785,9 @@ int env_int(const char* name, int lo, int hi) {  // tuning / debug overrides; -1
 // (one per residual block and problem).  EDSGPU_RESERVE_SMS leaves SMs to kernels of other streams (event-frame builds
 // of the next window); EDSGPU_LEADER_CTAS / EDSGPU_EVAL_CTAS force the two counts.  Results do not depend on the shape.
 LaunchShape pick_shape(edsgpu_ctx* ctx, int count, int B) {
-    int n_lead = std::max(1, std::min((count + LEAD_WARPS - 1) / LEAD_WARPS, MAX_LEAD_CTAS));
+    // four problems per leader CTA until all MAX_LEAD_CTAS are in use (leader warps that share an SM slow each other down;
+    // measured on the 64-window batch: 4 CTAs 0.603 ms, 8 CTAs 0.582 ms, 12 CTAs 0.596 ms -- beyond 8 the evaluators miss the SMs)
+    int n_lead = std::max(1, std::min((count + 3) / 4, MAX_LEAD_CTAS));
     const int force_lead = env_int("EDSGPU_LEADER_CTAS", 1, 64);
     if (force_lead > 0) n_lead = force_lead;
     const int reserve = std::max(0, env_int("EDSGPU_RESERVE_SMS", 0, 1024));
