@@ -74,8 +74,8 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 enum { PHASE_INIT = 0, PHASE_CAND = 1 };
 
 struct KfDev {
-    const float4* gxy;   // {Gx, Gy, X, Y}
-    const float2* dw;    // {idp, weight}
+    const float4* ga;    // model gradient of the point, g = -(Gx dflow_x/dv + Gy dflow_y/dv) (PhotometricError.hpp:114-122): {g0, g1, g2, g3}
+    const float4* gb;    // {g4, g5, weight, -}
     const double* kpx;   // 3-D point (X,Y,1)/(idp+eps)
     const double* kpy;
     const double* kpz;
@@ -83,6 +83,7 @@ struct KfDev {
     int N, B, H, W;
     int ne;              // N / B: points per residual block (the last block also takes the remainder)
     double fx, fy, cx, cy;
+    float fxf, fyf;      // (float)fx, (float)fy
 };
 
 struct ProblemDesc {
@@ -262,17 +263,20 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 // per-point residual + analytic tangent-space Jacobian
 // ------------------------------------------------------------------------------------------
 // Catmull-Rom weights of ceres' CubicHermiteSpline (call site PhotometricError.hpp:172) in basis
-// form: f = sum_k w_k(x) p_k, f' = sum_k dw_k(x) p_k  (same cubic as the Horner form a,b,c,d)
-__device__ __forceinline__ void cr_weights(float x, float* w, float* dw) {
+// form: f = sum_k w_k(x) p_k, f' = sum_k dw_k(x) p_k  (same cubic as the Horner form a,b,c,d).
+// TWICE the weights: the factor 1/2 of every weight (1/4 per tap of the separable window) is exact in binary floating
+// point, so it is applied once, to the sample, instead of sixteen times here -- same bits, fewer multiplications.
+__device__ __forceinline__ void cr_weights2(float x, float* w, float* dw) {
     const float x2 = x * x;
-    w[0] = 0.5f * x * ((2.0f - x) * x - 1.0f);
-    w[1] = 0.5f * (x2 * (3.0f * x - 5.0f) + 2.0f);
-    w[2] = 0.5f * x * ((4.0f - 3.0f * x) * x + 1.0f);
-    w[3] = 0.5f * x2 * (x - 1.0f);
-    dw[0] = 0.5f * ((4.0f - 3.0f * x) * x - 1.0f);
-    dw[1] = 0.5f * x * (9.0f * x - 10.0f);
-    dw[2] = 0.5f * ((8.0f - 9.0f * x) * x + 1.0f);
-    dw[3] = 0.5f * x * (3.0f * x - 2.0f);
+    const float b = fmaf(-3.0f, x, 4.0f);
+    w[0] = x * fmaf(2.0f - x, x, -1.0f);
+    w[1] = fmaf(x2, fmaf(3.0f, x, -5.0f), 2.0f);
+    w[2] = x * fmaf(b, x, 1.0f);
+    w[3] = x2 * (x - 1.0f);
+    dw[0] = fmaf(b, x, -1.0f);
+    dw[1] = x * fmaf(9.0f, x, -10.0f);
+    dw[2] = fmaf(fmaf(-9.0f, x, 8.0f), x, 1.0f);
+    dw[3] = x * fmaf(3.0f, x, -2.0f);
 }
 
 // Stage 1 of a point: warp into the event camera and project (PhotometricError.hpp:157-168) ->
@@ -284,19 +288,15 @@ struct PointGeo {
     float ax, ay, az;  // R kp
 };
 
-// (u - cell, cell) for u = f p / pz + c without an fp64 division on the critical path: the cell comes
-// from an fp32 estimate, the fraction from the exact fp64 numerator (f p + (c - cell) pz) times the
-// fp32 reciprocal, i.e. absolute error ~1e-7 px where plain fp32 projection would carry ~2e-5 px
-// (SURVEY.md section 7).  A cell guessed one off is repaired; at a cell boundary both choices give
-// the same interpolant.  Outside [-4, limit + 3] the clamped Grid2D is constant: fraction dropped.
-__device__ __forceinline__ void project_axis(double f, double c, double p, double pz, float pf, float izf, int limit, int& cell, float& frac) {
-    const float est = fmaf((float)f * pf, izf, (float)c);
-    int q = max(-6, min(__float2int_rd(est), limit + 5));  // saturating conversion, NaN -> 0
-    float t = (float)fma(f, p, (c - (double)q) * pz) * izf;
-    const int below = t < 0.f ? 1 : 0, above = t >= 1.f ? 1 : 0;  // at most one of them
-    q += above - below;
-    t += (float)(below - above);
+// (cell, u - cell) for u = f p / pz + c without an fp64 division: 1/pz comes from the fp32 reciprocal and one Newton step
+// in fp64 (relative error 2^-46), so u carries ~1e-11 px where plain fp32 projection would carry ~2e-5 px (SURVEY.md
+// section 7).  At a cell boundary both choices of the cell give the same interpolant.  Outside [-4, limit + 3] the clamped
+// Grid2D is constant: fraction dropped.  The conversion saturates (NaN -> 0).
+__device__ __forceinline__ void project_axis(double fp, double c, double rz, int limit, int& cell, float& frac) {
+    const double u = fma(fp, rz, c);
+    const int q = __double2int_rd(u);
     cell = max(-4, min(q, limit + 3));
+    const float t = (float)(u - (double)q);
     frac = (cell == q) ? t : 0.f;
 }
 
@@ -312,8 +312,10 @@ __device__ __forceinline__ void point_geometry(const KfDev& kf, const EvalConst&
     G.ax = (float)ax; G.ay = (float)ay; G.az = (float)az;
     G.px = (float)px; G.py = (float)py;
     G.iz = __frcp_rn((float)pz);
-    project_axis(kf.fx, kf.cx, px, pz, G.px, G.iz, kf.W, G.col, G.tc);
-    project_axis(kf.fy, kf.cy, py, pz, G.py, G.iz, kf.H, G.row, G.tr);
+    const double r0 = (double)G.iz;
+    const double rz = fma(r0, fma(-pz, r0, 1.0), r0);
+    project_axis(kf.fx * px, kf.cx, rz, kf.W, G.col, G.tc);
+    project_axis(kf.fy * py, kf.cy, rz, kf.H, G.row, G.tr);
 }
 
 // 4x4 taps as four 2x2 texture gathers. A gather at the corner shared by texels (i,j),(i+1,j),
@@ -335,25 +337,20 @@ __device__ __forceinline__ Taps fetch_taps(cudaTextureObject_t frame, int col, i
 // tangent-space velocity Jacobian  (w (g/M - m c/M^3)) (I - v v^T/|v|^2)/|v|  =  w (alpha g - m beta)
 //
 // Stage 2 of a point: bicubic sample + residual + Jacobian row from the geometry, the fetched taps and
-// the point's gradient record g4 = {Gx, Gy, X, Y}, dw = {inverse depth, weight}.
+// the point's model record ga = {g0..g3}, gb = {g4, g5, weight, -} (prepared once per key frame, kf_prepare_kernel).
 template <bool WANT_J>
 __device__ __forceinline__ void point_finish(const KfDev& kf, const EvalConst& K, const float* __restrict__ bc, float inv_norm,
-                                             const PointGeo& G, const Taps& T, float4 g4, float2 dw, float* __restrict__ J, float& r) {
-    const float Gx = g4.x, Gy = g4.y, X = g4.z, Y = g4.w, d = dw.x, w = dw.y;
+                                             const PointGeo& G, const Taps& T, float4 ga, float4 gb, float* __restrict__ J, float& r) {
     // model term: m = g . v with g = -(Gx dflow_x/dv + Gy dflow_y/dv), PhotometricError.hpp:114-122,145
-    float g[6];
-    g[0] = Gx * d;
-    g[1] = Gy * d;
-    g[2] = -(Gx * X + Gy * Y) * d;
-    g[3] = -(Gx * X * Y + Gy * (1.0f + Y * Y));
-    g[4] = Gx * (1.0f + X * X) + Gy * X * Y;
-    g[5] = Gy * X - Gx * Y;
+    const float g[6] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y};
+    const float w = gb.z;
     float m = 0.f;
 #pragma unroll
     for (int k = 0; k < 6; ++k) m += g[k] * K.vf[k];
     float wc[4], dwc[4], wr[4], dwr[4];
-    cr_weights(G.tc, wc, dwc);
-    cr_weights(G.tr, wr, dwr);
+    cr_weights2(G.tc, wc, dwc);
+    cr_weights2(G.tr, wr, dwr);
+    inv_norm *= 0.25f;  // the factor 1/2 of the column and of the row weights
     const float taps[4][4] = {{T.q00.w, T.q00.z, T.q10.w, T.q10.z}, {T.q00.x, T.q00.y, T.q10.x, T.q10.y},
                               {T.q01.w, T.q01.z, T.q11.w, T.q11.z}, {T.q01.x, T.q01.y, T.q11.x, T.q11.y}};
     float f = 0.f, dfdr = 0.f, dfdc = 0.f;
@@ -370,7 +367,7 @@ __device__ __forceinline__ void point_finish(const KfDev& kf, const EvalConst& K
     if (!WANT_J) return;
     const float er = inv_norm * dfdr, ec = inv_norm * dfdc;
     // d r / d P  (P = R kp + t)
-    const float fxf = (float)kf.fx, fyf = (float)kf.fy;
+    const float fxf = kf.fxf, fyf = kf.fyf;
     const float wiz = w * G.iz;
     const float dPx = -wiz * ec * fxf;
     const float dPy = -wiz * er * fyf;
@@ -394,7 +391,7 @@ __device__ __forceinline__ void eval_point(const KfDev& kf, const EvalConst& K, 
     PointGeo G;
     point_geometry(kf, K, load_kp(kf, idx), G);
     const Taps T = fetch_taps(frame, G.col, G.row);
-    point_finish<WANT_J>(kf, K, bc, inv_norm, G, T, __ldg(&kf.gxy[idx]), __ldg(&kf.dw[idx]), J, r);
+    point_finish<WANT_J>(kf, K, bc, inv_norm, G, T, __ldg(&kf.ga[idx]), __ldg(&kf.gb[idx]), J, r);
 }
 
 // ---- mbarrier helpers (shared::cta) ---------------------------------------------------------
@@ -605,8 +602,8 @@ __device__ void producer_warp_main(EvalShared& sh, const int pidx) {
                 const long long tp0 = clock64();
 #endif
                 const Kp kp = load_kp(kf, idx);
-                const float4 g4 = __ldg(&kf.gxy[idx]);
-                const float2 dw = __ldg(&kf.dw[idx]);
+                const float4 ga = __ldg(&kf.ga[idx]);
+                const float4 gb = __ldg(&kf.gb[idx]);
                 PointGeo G;
                 point_geometry(kf, ts.ec, kp, G);
 #ifdef EDS_TIMING
@@ -615,11 +612,11 @@ __device__ void producer_warp_main(EvalShared& sh, const int pidx) {
 #endif
                 const Taps T = fetch_taps(frame, G.col, G.row);
 #ifdef EDS_TIMING
-                asm volatile("" ::"f"(T.q00.x), "f"(T.q10.x), "f"(T.q01.x), "f"(T.q11.x), "f"(g4.x), "f"(dw.x));
+                asm volatile("" ::"f"(T.q00.x), "f"(T.q10.x), "f"(T.q01.x), "f"(T.q11.x), "f"(ga.x), "f"(gb.x));
                 const long long tp2 = clock64();
 #endif
                 float J[12], r;
-                point_finish<true>(kf, ts.ec, bc, inv_norm, G, T, g4, dw, J, r);
+                point_finish<true>(kf, ts.ec, bc, inv_norm, G, T, ga, gb, J, r);
 #ifdef EDS_TIMING
                 asm volatile("" ::"f"(J[0]), "f"(J[5]), "f"(J[11]), "f"(r));
                 const long long tp3 = clock64();
@@ -1671,7 +1668,7 @@ __global__ void get_coord_kernel(int N, const double* __restrict__ norm_xy, cons
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kf_prepare_kernel(const double* __restrict__ grad_xy, const double* __restrict__ norm_xy,
                                                          const double* __restrict__ idp, int idp_stride, const double* __restrict__ weights, int N, int B,
-                                                         float4* __restrict__ gxy, float2* __restrict__ dw, double* __restrict__ kpx,
+                                                         float4* __restrict__ ga, float4* __restrict__ gb, double* __restrict__ kpx,
                                                          double* __restrict__ kpy, double* __restrict__ kpz, double* __restrict__ A) {
     const int b = blockIdx.x;
     const int ne = N / B;
@@ -1684,8 +1681,6 @@ __global__ void __launch_bounds__(256) kf_prepare_kernel(const double* __restric
         const double Gx = grad_xy[2 * idx], Gy = grad_xy[2 * idx + 1];
         const double X = norm_xy[2 * idx], Y = norm_xy[2 * idx + 1];
         const double d = idp[(size_t)idp_stride * idx], w = weights[idx];
-        gxy[idx] = make_float4((float)Gx, (float)Gy, (float)X, (float)Y);
-        dw[idx] = make_float2((float)d, (float)w);
         const double z = 1.0 / (d + kEps);  // PhotometricError.hpp:97-99
         kpz[idx] = z;
         kpx[idx] = X * z;
@@ -1697,6 +1692,8 @@ __global__ void __launch_bounds__(256) kf_prepare_kernel(const double* __restric
         g[3] = -(Gx * X * Y + Gy * (1.0 + Y * Y));
         g[4] = Gx * (1.0 + X * X) + Gy * X * Y;
         g[5] = Gy * X - Gx * Y;
+        ga[idx] = make_float4((float)g[0], (float)g[1], (float)g[2], (float)g[3]);
+        gb[idx] = make_float4((float)g[4], (float)g[5], (float)w, 0.f);
         int k = 0;
         for (int p = 0; p < 6; ++p)
             for (int q = p; q < 6; ++q, ++k) a[k] += g[p] * g[q];
@@ -1859,23 +1856,24 @@ edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const doub
     const size_t N = (size_t)num_points;
     edsgpu_keyframe* kf = new edsgpu_keyframe();
     kf->ctx = ctx;
-    // layout: gxy | dw | kpx | kpy | kpz | A
+    // layout: ga | gb | kpx | kpy | kpz | A
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-    const size_t o_gxy = take(N * sizeof(float4)), o_dw = take(N * sizeof(float2)), o_kx = take(N * 8), o_ky = take(N * 8), o_kz = take(N * 8);
+    const size_t o_gxy = take(N * sizeof(float4)), o_dw = take(N * sizeof(float4)), o_kx = take(N * 8), o_ky = take(N * 8), o_kz = take(N * 8);
     const size_t o_A = take((size_t)num_blocks * 21 * 8);
     const size_t o_src = take(N * 6 * sizeof(double));  // kept: the inverse depths can be refreshed on the device
     cudaError_t e = cudaMalloc(&kf->block, off);
     if (e != cudaSuccess) { delete kf; return edsgpu_fail(ctx, EDSGPU_OUT_OF_MEMORY, cudaGetErrorString(e)); }
     char* base = (char*)kf->block;
     KfDev& d = kf->dev;
-    d.gxy = (float4*)(base + o_gxy); d.dw = (float2*)(base + o_dw);
+    d.ga = (float4*)(base + o_gxy); d.gb = (float4*)(base + o_dw);
     d.kpx = (double*)(base + o_kx); d.kpy = (double*)(base + o_ky); d.kpz = (double*)(base + o_kz);
     d.A = (double*)(base + o_A);
     kf->src = (double*)(base + o_src);
     d.N = num_points; d.B = num_blocks; d.H = height; d.W = width;
     d.ne = num_points / num_blocks;
     d.fx = fx; d.fy = fy; d.cx = cx; d.cy = cy;
+    d.fxf = (float)fx; d.fyf = (float)fy;
     // stage the double arrays: pinned -> device copy -> prepare kernel
     const size_t stage = N * 6 * sizeof(double);
     edsgpu_status st = edsgpu_ensure_pinned(ctx, stage);
@@ -1889,7 +1887,7 @@ edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const doub
     e = cudaMemcpyAsync(ds, hp, stage, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         kf_prepare_kernel<<<num_blocks, 256, 0, ctx->stream>>>(ds, ds + 2 * N, ds + 4 * N, 1, ds + 5 * N, num_points, num_blocks,
-                                                                (float4*)d.gxy, (float2*)d.dw, (double*)d.kpx, (double*)d.kpy, (double*)d.kpz,
+                                                                (float4*)d.ga, (float4*)d.gb, (double*)d.kpx, (double*)d.kpy, (double*)d.kpz,
                                                                 (double*)d.A);
         ctx->launches++;
         e = cudaGetLastError();
@@ -2255,7 +2253,7 @@ edsgpu_status edsgpu_keyframe_refresh_idepth(edsgpu_keyframe* kf, const edsgpu_d
     const size_t N = (size_t)kf->dev.N;
     KfDev& d = kf->dev;
     // same preparation as at upload, the inverse depths read from column 0 of the filter state (KeyFrame::inv_depth.getIDepth, Tracker.cpp:167)
-    kf_prepare_kernel<<<d.B, 256, 0, ctx->stream>>>(kf->src, kf->src + 2 * N, dp->state, 4, kf->src + 5 * N, d.N, d.B, (float4*)d.gxy, (float2*)d.dw,
+    kf_prepare_kernel<<<d.B, 256, 0, ctx->stream>>>(kf->src, kf->src + 2 * N, dp->state, 4, kf->src + 5 * N, d.N, d.B, (float4*)d.ga, (float4*)d.gb,
                                                    (double*)d.kpx, (double*)d.kpy, (double*)d.kpz, (double*)d.A);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());

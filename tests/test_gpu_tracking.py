@@ -298,7 +298,7 @@ def test_results_do_not_depend_on_launch_shape(gpu_ctx, problems, monkeypatch):
     for k in ("EDSGPU_EVAL_CTAS", "EDSGPU_LEADER_CTAS", "EDSGPU_RESERVE_SMS"):
         monkeypatch.delenv(k, raising=False)
     base_states, base_infos, shape = run()
-    assert shape[1] == 2 and shape[2] == n and 1 <= shape[0] <= 8 * n  # 21 problems: two leader CTAs, all in flight
+    assert shape[1] == 6 and shape[2] == n and 1 <= shape[0] <= 8 * n  # 21 problems: four per leader CTA, all in flight
     for evals, leads, reserve, repeat in ((1, 1, 0, 1), (2, 1, 0, 3), (7, 2, 0, 1), (64, 4, 0, 2), (0, 0, 40, 1), (200, 0, 0, 1)):
         for k, v in (("EDSGPU_EVAL_CTAS", evals), ("EDSGPU_LEADER_CTAS", leads), ("EDSGPU_RESERVE_SMS", reserve)):
             if v:
