@@ -263,6 +263,24 @@ def bench_ba(ctx, stream, reps=50):
         O.ba_linearize(F, pb["H"], pb["W"], pb["dI"], pb["precalc"], pb["calib"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"],
                        pb["color"], pb["weights"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["frame_energy_th"])
     lin_cpu_ms = 1e3 * (time.perf_counter() - t0) / 5
+    # one Gauss-Newton iteration's accumulation as the library now runs it: linearize FUSED with addPoint<0> (records of the
+    # residuals nothing reads later are never written), then the linearized side and the Schur complement
+    linearized = (pb["flags"] >> 1) & 1
+    w.linearize_accumulate(linearized=linearized, write_records=True, want_outputs=False)  # the linearized records exist once
+
+    def fused():
+        w.ctx.check(w.ctx.lib.edsgpu_ba_linearize_accumulate(w.h, None, None, None, 0, None, None))
+        w.top_accumulate(1, want_outputs=False)
+        w.sc_accumulate(True, want_outputs=False)
+
+    for _ in range(5):
+        fused()
+    a.record(stream)
+    for _ in range(reps):
+        fused()
+    b.record(stream)
+    stream.synchronize()
+    fused_ms = a.elapsed_time(b) / reps
     # per residual: 8 pattern pixels x 4 taps x 16 B gathered, 80 B of point state, 112 B of precalc, 304 B record + 32 B JpJdF
     # written (and the record read once more by takeDataF), 9 B of state / energy / flag
     lin_alg = R * (8 * 4 * 16 + 80 + 112 + 304 + 304 + 32 + 9)
@@ -287,6 +305,9 @@ def bench_ba(ctx, stream, reps=50):
                           "ms": lin_ms, "residuals_per_s": R / (lin_ms * 1e-3), "algorithmic_bytes": lin_alg,
                           "achieved_gbs": lin_alg / (lin_ms * 1e-3) / 1e9, "cpu_port_ms_1_thread": lin_cpu_ms,
                           "upload_avoided_bytes": 304 * R},
+            "gn_iteration": {"what": "linearize fused with addPoint<0> (edsgpu_ba_linearize_accumulate, records not materialised) + top<1> + SC "
+                                     "accumulate: everything one Gauss-Newton iteration accumulates, 5 launches",
+                             "ms": fused_ms, "unfused_ms": lin_ms + ms},
             "after_solve": {"what": "resubstituteF_MT (P steps back to the host) and calcLEnergyF_MT, wall clock per host-synchronous call",
                             "resubstitute_ms": resub_ms, "calc_l_energy_ms": energy_ms}}
 

@@ -270,6 +270,19 @@ edsgpu_status edsgpu_ba_set_linearize_inputs(edsgpu_ba* ba, const float* precalc
  * (visualisation only) are not produced. */
 edsgpu_status edsgpu_ba_linearize(edsgpu_ba* ba, const uint8_t* state_in, const uint8_t* linearized, const float* res_toZero,
                                   int32_t* state_out, float* energy_out);
+/* edsgpu_ba_linearize FUSED with edsgpu_ba_top_accumulate(mode 0): linearizeAll_Reductor followed by accumulateAF_MT
+ * (EnergyFunctional.cpp:838-860; Residuals.cpp:69-265 feeding AccumulatedTopHessian.cpp:102-135 and
+ * EnergyFunctionalStructs.cpp:38-48) in ONE kernel: the thread that linearises a residual accumulates it from its
+ * registers, so the 304-byte record is neither written nor re-read.  Results are bit-identical to the two-call sequence.
+ * write_records == 0 keeps only the records later stages read (the LINEARIZED residuals: mode-1 pass, linearised
+ * energy); pass 1 before edsgpu_ba_fix_linearization or edsgpu_ba_get_residuals, which need them all.  Asynchronous
+ * when every host pointer is NULL; the active-side accumulation (acc / Hdd / bd / Hcd) stays on the device for
+ * edsgpu_ba_top_stitch / edsgpu_ba_sc_accumulate (edsgpu_ba_top_read copies it out). */
+edsgpu_status edsgpu_ba_linearize_accumulate(edsgpu_ba* ba, const uint8_t* state_in, const uint8_t* linearized, const float* res_toZero,
+                                             int write_records, int32_t* state_out, float* energy_out);
+/* Read-back of an accumulation that is already on the device (by edsgpu_ba_top_accumulate or
+ * edsgpu_ba_linearize_accumulate): which = 0 (active side) or 1 (linearized side); same outputs as top_accumulate. */
+edsgpu_status edsgpu_ba_top_read(edsgpu_ba* ba, int which, double* acc_out, float* Hdd_out, float* bd_out, float* Hcd_out, int64_t* nres_out);
 /* ---- after the solve -------------------------------------------------
  * EnergyFunctional::resubstituteF_MT (EnergyFunctional.cpp:263-317): per-point inverse-depth step
  * from the solved update x (4 + 8F doubles).  Needs the adjoints (edsgpu_ba_set_frames) and the

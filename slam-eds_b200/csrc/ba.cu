@@ -45,6 +45,12 @@ struct BaDev {
     float* res_pt;        // R x 6: bd, Hdd, Hcd[4] of each residual (zero when filtered out)
     double* tile_partial; // num_tiles x 96
     int* tile_nres;       // num_tiles
+    // second phase of the accumulation kernels (after a grid-wide barrier): ordered sums over tiles and over a point's residuals
+    double* acc_out;      // F*F x 13x13 (AccumulatorApprox::finish layout)
+    long long* num_out;   // F*F
+    float *Hdd_out, *bd_out, *Hcd_out;  // P, P, P x 4
+    unsigned* grid_bar;   // arrival counter of the grid barrier, only ever grows
+    unsigned bar_target;  // its value once every CTA of this launch has arrived
 };
 
 template <int HALF, int OFFSET>
@@ -59,26 +65,6 @@ __device__ __forceinline__ void butterfly_step(float* a, unsigned lane) {
 }
 __device__ __forceinline__ int butterfly_base(unsigned lane) {
     return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
-}
-
-// EFResidual::takeDataF (EnergyFunctionalStructs.cpp:38-48)
-__global__ void ba_jpjd_kernel(const float* __restrict__ recs, int R, float* __restrict__ JpJdF) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const float* J = recs + (size_t)REC * r;
-    const float d0 = J[O_JPDD], d1 = J[O_JPDD + 1];
-    const float* M = J + O_JIDX2;  // Mat22f column-major
-    const float v0 = M[0] * d0 + M[2] * d1;
-    const float v1 = M[1] * d0 + M[3] * d1;
-    float out[8];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) out[i] = J[O_JPDXI0 + i] * v0 + J[O_JPDXI1 + i] * v1;
-    const float* N = J + O_JABJIDX;
-    out[6] = N[0] * d0 + N[2] * d1;
-    out[7] = N[1] * d0 + N[3] * d1;
-    float4* o = reinterpret_cast<float4*>(JpJdF + (size_t)8 * r);
-    o[0] = make_float4(out[0], out[1], out[2], out[3]);
-    o[1] = make_float4(out[4], out[5], out[6], out[7]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -113,14 +99,12 @@ struct LinDev {
     float* energy_new;
 };
 
-__global__ void __launch_bounds__(128) ba_linearize_kernel(LinDev d) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= d.R) return;
-    float rec[REC];
+// one residual: record (zero unless the residual is IN or an OUTLIER), new state (0 IN, 1 OOB, 2 OUTLIER) and energy
+__device__ __forceinline__ void linearize_one(const LinDev& d, int r, float* __restrict__ rec, int& state, float& energy) {
 #pragma unroll
     for (int i = 0; i < REC; ++i) rec[i] = 0.f;
-    int state = 1;  // OOB unless the residual survives
-    float energy = 0.f;
+    state = 1;  // OOB unless the residual survives
+    energy = 0.f;
     const int p = d.point_of_res[r];
     const int h = d.host_idx[r], t = d.target_idx[r];
     const bool skip = d.state_in && d.state_in[r] == 1;  // :73-74
@@ -233,6 +217,39 @@ __global__ void __launch_bounds__(128) ba_linearize_kernel(LinDev d) {
             energy = 0.f;
         }
     }
+}
+
+// EFResidual::takeDataF (EnergyFunctionalStructs.cpp:38-48) from a record in registers
+__device__ __forceinline__ void jpjd_one(const float* __restrict__ J, float* __restrict__ out) {
+    const float d0 = J[O_JPDD], d1 = J[O_JPDD + 1];
+    const float* M = J + O_JIDX2;  // Mat22f column-major
+    const float v0 = M[0] * d0 + M[2] * d1;
+    const float v1 = M[1] * d0 + M[3] * d1;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) out[i] = J[O_JPDXI0 + i] * v0 + J[O_JPDXI1 + i] * v1;
+    const float* N = J + O_JABJIDX;
+    out[6] = N[0] * d0 + N[2] * d1;
+    out[7] = N[1] * d0 + N[3] * d1;
+}
+
+__global__ void ba_jpjd_kernel(const float* __restrict__ recs, int R, float* __restrict__ JpJdF) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* J = recs + (size_t)REC * r;
+    float out[8];
+    jpjd_one(J, out);
+    float4* o = reinterpret_cast<float4*>(JpJdF + (size_t)8 * r);
+    o[0] = make_float4(out[0], out[1], out[2], out[3]);
+    o[1] = make_float4(out[4], out[5], out[6], out[7]);
+}
+
+__global__ void __launch_bounds__(128) ba_linearize_kernel(LinDev d) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.R) return;
+    float rec[REC];
+    int state;
+    float energy;
+    linearize_one(d, r, rec, state, energy);
     float4* out = reinterpret_cast<float4*>(d.recs + (size_t)REC * r);
 #pragma unroll
     for (int i = 0; i < REC / 4; ++i) out[i] = make_float4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
@@ -405,6 +422,139 @@ __device__ __forceinline__ void tma_load_record(void* dst_smem, const void* src_
 // 304-byte lane stride (conflict-free).
 constexpr int TOP_KMAX = TOP_STAGE / TOP_THREADS;  // records per thread per stage
 
+// AccumulatedTopHessianSSE::addPoint's accumulation of one residual (AccumulatedTopHessian.cpp:102-135): J = the record,
+// res = the (possibly re-linearised) residual vector; acc = the 91 AccumulatorApprox entries, pt = {bd, Hdd, Hcd[4]} terms
+__device__ __forceinline__ void top_add_point(const float* __restrict__ J, const float* __restrict__ res, float* __restrict__ acc, float* __restrict__ pt) {
+    // :102-112
+    float JIr0 = 0.f, JIr1 = 0.f, Jabr0 = 0.f, Jabr1 = 0.f, rsq = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        JIr0 += res[q] * J[O_JIDX0 + q];
+        JIr1 += res[q] * J[O_JIDX1 + q];
+        Jabr0 += res[q] * J[O_JAB0 + q];
+        Jabr1 += res[q] * J[O_JAB1 + q];
+        rsq += res[q] * res[q];
+    }
+    // x = [Jpdc[0] Jpdxi[0]], y = [Jpdc[1] Jpdxi[1]]  (:115-129)
+    float x[10], y[10];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { x[q] = J[O_JPDC0 + q]; y[q] = J[O_JPDC1 + q]; }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { x[4 + q] = J[O_JPDXI0 + q]; y[4 + q] = J[O_JPDXI1 + q]; }
+    const float a = J[O_JIDX2], b = J[O_JIDX2 + 2], c = J[O_JIDX2 + 3];  // (0,0) (0,1) (1,1), column-major
+    // AccumulatorApprox::update: a x x^T + c y y^T + b (x y^T + y x^T) = x (a x + b y)^T + y (b x + c y)^T
+    float px[10], py[10];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) { px[q] = a * x[q] + b * y[q]; py[q] = b * x[q] + c * y[q]; }
+    int e = 0;
+#pragma unroll
+    for (int p = 0; p < 10; ++p)
+#pragma unroll
+        for (int q = p; q < 10; ++q) acc[e++] += x[p] * px[q] + y[p] * py[q];
+    // updateTopRight: TR00,TR10 = JabJIdx(0,0),(0,1); TR01,TR11 = JabJIdx(1,0),(1,1); TR02,TR12 = JI_r
+    const float t00 = J[O_JABJIDX], t10 = J[O_JABJIDX + 2], t01 = J[O_JABJIDX + 1], t11 = J[O_JABJIDX + 3];
+#pragma unroll
+    for (int p = 0; p < 10; ++p) {
+        acc[55 + 3 * p] += x[p] * t00 + y[p] * t10;
+        acc[55 + 3 * p + 1] += x[p] * t01 + y[p] * t11;
+        acc[55 + 3 * p + 2] += x[p] * JIr0 + y[p] * JIr1;
+    }
+    // updateBotRight
+    acc[85] += J[O_JAB2]; acc[86] += J[O_JAB2 + 2]; acc[87] += Jabr0;
+    acc[88] += J[O_JAB2 + 3]; acc[89] += Jabr1; acc[90] += rsq;
+    // :132-135
+    const float d0 = J[O_JPDD], d1 = J[O_JPDD + 1];
+    const float q0 = a * d0 + b * d1, q1 = b * d0 + c * d1;
+    pt[0] = JIr0 * d0 + JIr1 * d1;
+    pt[1] = q0 * d0 + q1 * d1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pt[2 + q] = J[O_JPDC0 + q] * q0 + J[O_JPDC1 + q] * q1;
+}
+
+// Grid-wide barrier of a cooperatively launched kernel (all CTAs resident).  The counter only grows; `target` is its
+// value once every CTA of this launch has arrived.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if ((int)(v - target) < 0) __nanosleep(40);
+        } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+// Second phase of an accumulation kernel, by the whole grid once every tile partial and per-residual term is in memory:
+//  * ordered fp64 sum of the tile partials of each (host,target) key -> 13x13 (AccumulatorApprox::finish layout),
+//  * per point Hdd_acc, bd_acc, Hcd_acc (AccumulatedTopHessian.cpp:132-157), residuals in their stored order.
+__device__ void top_second_phase(const BaDev& W) {
+    const int nthreads = gridDim.x * blockDim.x, g = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int idx = g; idx < W.F * W.F * NACC; idx += nthreads) {
+        const int key = idx / NACC, e = idx % NACC;
+        const int t0 = W.key_tile_begin[key], t1 = W.key_tile_begin[key + 1];
+        if (e < 91) {
+            double s = 0.0;
+            for (int t = t0; t < t1; ++t) s += __ldcg(&W.tile_partial[(size_t)NACC * t + e]);
+            int r, c;
+            if (e < 55) {
+                int p = 0, rem = e;
+                while (rem >= 10 - p) { rem -= 10 - p; ++p; }
+                r = p; c = p + rem;
+            } else if (e < 85) { r = (e - 55) / 3; c = 10 + (e - 55) % 3; }
+            else { const int br[6][2] = {{10, 10}, {10, 11}, {10, 12}, {11, 11}, {11, 12}, {12, 12}}; r = br[e - 85][0]; c = br[e - 85][1]; }
+            double* H = W.acc_out + (size_t)169 * key;
+            H[13 * r + c] = s;
+            H[13 * c + r] = s;
+        } else if (e == 95) {
+            long long n = 0;
+            for (int t = t0; t < t1; ++t) n += __ldcg(&W.tile_nres[t]);
+            W.num_out[key] = n;
+        }
+    }
+    for (int p = g; p < W.P; p += nthreads) {
+        float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int r = W.res_begin[p]; r < W.res_begin[p + 1]; ++r) {
+            const float2* v = reinterpret_cast<const float2*>(W.res_pt + (size_t)6 * r);
+            const float2 a = __ldcg(v), b = __ldcg(v + 1), c = __ldcg(v + 2);
+            s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y;
+        }
+        W.bd_out[p] = s[0];
+        W.Hdd_out[p] = s[1];
+        reinterpret_cast<float4*>(W.Hcd_out)[p] = make_float4(s[2], s[3], s[4], s[5]);
+    }
+}
+
+// warp butterfly + fp64 across warps -> this tile's partial (fixed order)
+__device__ __forceinline__ void top_tile_partial(const BaDev& W, float* acc, int nres, double (*warp_part)[NACC], int* warp_n) {
+    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    butterfly_step<48, 16>(acc, lane);
+    butterfly_step<24, 8>(acc, lane);
+    butterfly_step<12, 4>(acc, lane);
+    butterfly_step<6, 2>(acc, lane);
+    butterfly_step<3, 1>(acc, lane);
+    const int base = butterfly_base(lane);
+    warp_part[warp][base] = (double)acc[0];
+    warp_part[warp][base + 1] = (double)acc[1];
+    warp_part[warp][base + 2] = (double)acc[2];
+    for (int o = 16; o > 0; o >>= 1) nres += __shfl_xor_sync(0xffffffffu, nres, o);
+    if (lane == 0) warp_n[warp] = nres;
+    __syncthreads();
+    if (tid < NACC) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < TOP_THREADS / 32; ++w) s += warp_part[w][tid];
+        W.tile_partial[(size_t)NACC * tile + tid] = s;
+    }
+    if (tid == 0) {
+        int n = 0;
+        for (int w = 0; w < TOP_THREADS / 32; ++w) n += warp_n[w];
+        W.tile_nres[tile] = n;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(BaDev W) {
     extern __shared__ __align__(16) unsigned char top_smem[];
@@ -412,7 +562,7 @@ __global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(BaDev W) {
     __shared__ __align__(8) unsigned long long bar;
     __shared__ double warp_part[TOP_THREADS / 32][NACC];
     __shared__ int warp_n[TOP_THREADS / 32];
-    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, tid = threadIdx.x;
     const int key = W.tile_key[tile], start = W.tile_start[tile], count = W.tile_count[tile];
     if (tid == 0) mbar_init(&bar, TOP_THREADS);
     float dp[8], dc[4];
@@ -487,50 +637,7 @@ __global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(BaDev W) {
                             res[q] = res[q] + J[O_JIDX0 + q] * jx + J[O_JIDX1 + q] * jy + J[O_JAB0 + q] * dp[6] + J[O_JAB1 + q] * dp[7];
                     }
                 }
-                // :102-112
-                float JIr0 = 0.f, JIr1 = 0.f, Jabr0 = 0.f, Jabr1 = 0.f, rsq = 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    JIr0 += res[q] * J[O_JIDX0 + q];
-                    JIr1 += res[q] * J[O_JIDX1 + q];
-                    Jabr0 += res[q] * J[O_JAB0 + q];
-                    Jabr1 += res[q] * J[O_JAB1 + q];
-                    rsq += res[q] * res[q];
-                }
-                // x = [Jpdc[0] Jpdxi[0]], y = [Jpdc[1] Jpdxi[1]]  (:115-129)
-                float x[10], y[10];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { x[q] = J[O_JPDC0 + q]; y[q] = J[O_JPDC1 + q]; }
-#pragma unroll
-                for (int q = 0; q < 6; ++q) { x[4 + q] = J[O_JPDXI0 + q]; y[4 + q] = J[O_JPDXI1 + q]; }
-                const float a = J[O_JIDX2], b = J[O_JIDX2 + 2], c = J[O_JIDX2 + 3];  // (0,0) (0,1) (1,1), column-major
-                // AccumulatorApprox::update: a x x^T + c y y^T + b (x y^T + y x^T) = x (a x + b y)^T + y (b x + c y)^T
-                float px[10], py[10];
-#pragma unroll
-                for (int q = 0; q < 10; ++q) { px[q] = a * x[q] + b * y[q]; py[q] = b * x[q] + c * y[q]; }
-                int e = 0;
-#pragma unroll
-                for (int p = 0; p < 10; ++p)
-#pragma unroll
-                    for (int q = p; q < 10; ++q) acc[e++] += x[p] * px[q] + y[p] * py[q];
-                // updateTopRight: TR00,TR10 = JabJIdx(0,0),(0,1); TR01,TR11 = JabJIdx(1,0),(1,1); TR02,TR12 = JI_r
-                const float t00 = J[O_JABJIDX], t10 = J[O_JABJIDX + 2], t01 = J[O_JABJIDX + 1], t11 = J[O_JABJIDX + 3];
-#pragma unroll
-                for (int p = 0; p < 10; ++p) {
-                    acc[55 + 3 * p] += x[p] * t00 + y[p] * t10;
-                    acc[55 + 3 * p + 1] += x[p] * t01 + y[p] * t11;
-                    acc[55 + 3 * p + 2] += x[p] * JIr0 + y[p] * JIr1;
-                }
-                // updateBotRight
-                acc[85] += J[O_JAB2]; acc[86] += J[O_JAB2 + 2]; acc[87] += Jabr0;
-                acc[88] += J[O_JAB2 + 3]; acc[89] += Jabr1; acc[90] += rsq;
-                // :132-135
-                const float d0 = J[O_JPDD], d1 = J[O_JPDD + 1];
-                const float q0 = a * d0 + b * d1, q1 = b * d0 + c * d1;
-                pt[0] = JIr0 * d0 + JIr1 * d1;
-                pt[1] = q0 * d0 + q1 * d1;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) pt[2 + q] = J[O_JPDC0 + q] * q0 + J[O_JPDC1 + q] * q1;
+                top_add_point(J, res, acc, pt);
                 nres++;
             }
             float2* o = reinterpret_cast<float2*>(W.res_pt + (size_t)6 * r);
@@ -538,70 +645,59 @@ __global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(BaDev W) {
         }
         if (s0 + TOP_STAGE < count) __syncthreads();  // the stage is overwritten by the next round
     }
-    butterfly_step<48, 16>(acc, lane);
-    butterfly_step<24, 8>(acc, lane);
-    butterfly_step<12, 4>(acc, lane);
-    butterfly_step<6, 2>(acc, lane);
-    butterfly_step<3, 1>(acc, lane);
-    const int base = butterfly_base(lane);
-    warp_part[warp][base] = (double)acc[0];
-    warp_part[warp][base + 1] = (double)acc[1];
-    warp_part[warp][base + 2] = (double)acc[2];
-    for (int o = 16; o > 0; o >>= 1) nres += __shfl_xor_sync(0xffffffffu, nres, o);
-    if (lane == 0) warp_n[warp] = nres;
-    __syncthreads();
-    if (tid < NACC) {
-        double s = 0.0;
+    top_tile_partial(W, acc, nres, warp_part, warp_n);
+    grid_barrier(W.grid_bar, W.bar_target);
+    top_second_phase(W);
+}
+
+// PointFrameResidual::linearize FUSED with addPoint<0>: the thread that linearises a residual
+// accumulates it straight from registers, in the tile structure and summation order of ba_top_kernel<0> (the results are
+// bit-identical to linearize -> top_accumulate(0)).  The 304-byte record only goes to memory for the residuals that need
+// it later (the linearized ones, which the mode-1 pass and the linearised energy read) unless the caller asks for all of
+// them; state, energy, flags and JpJdF (takeDataF) are always written.
+__global__ void __launch_bounds__(TOP_THREADS, 1) ba_lin_top_kernel(LinDev d, BaDev W, float* __restrict__ JpJdF, int write_all) {
+    __shared__ double warp_part[TOP_THREADS / 32][NACC];
+    __shared__ int warp_n[TOP_THREADS / 32];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int start = W.tile_start[tile], count = W.tile_count[tile];
+    float acc[NACC];
 #pragma unroll
-        for (int w = 0; w < TOP_THREADS / 32; ++w) s += warp_part[w][tid];
-        W.tile_partial[(size_t)NACC * tile + tid] = s;
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    int nres = 0;
+#pragma unroll 1
+    for (int i = tid; i < count; i += TOP_THREADS) {
+        const int r = W.perm[start + i];
+        float rec[REC];
+        int state;
+        float energy;
+        linearize_one(d, r, rec, state, energy);
+        const bool lin = d.linearized && d.linearized[r];
+        d.state_new[r] = state;
+        d.energy_new[r] = energy;
+        d.flags[r] = (uint8_t)((state == 0 ? EDSGPU_RES_ACTIVE : 0) | (lin ? EDSGPU_RES_LINEARIZED : 0));
+        {
+            float o8[8];
+            jpjd_one(rec, o8);
+            float4* o = reinterpret_cast<float4*>(JpJdF + (size_t)8 * r);
+            o[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+            o[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+        }
+        if (write_all || lin) {
+            float4* out = reinterpret_cast<float4*>(d.recs + (size_t)REC * r);
+#pragma unroll
+            for (int q = 0; q < REC / 4; ++q) out[q] = make_float4(rec[4 * q], rec[4 * q + 1], rec[4 * q + 2], rec[4 * q + 3]);
+        }
+        float pt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (state == 0 && !lin) {  // AccumulatedTopHessian.cpp:55-58
+            top_add_point(rec, rec + O_RES, acc, pt);
+            nres++;
+        }
+        float2* o = reinterpret_cast<float2*>(W.res_pt + (size_t)6 * r);
+        o[0] = make_float2(pt[0], pt[1]); o[1] = make_float2(pt[2], pt[3]); o[2] = make_float2(pt[4], pt[5]);
     }
-    if (tid == 0) {
-        int n = 0;
-        for (int w = 0; w < TOP_THREADS / 32; ++w) n += warp_n[w];
-        W.tile_nres[tile] = n;
-    }
-}
-
-// ordered fp64 sum of the tile partials of each key -> 13x13 (AccumulatorApprox::finish layout)
-__global__ void ba_top_finalize_kernel(BaDev W, double* __restrict__ acc /*F*F x 169*/, long long* __restrict__ num /*F*F*/) {
-    const int key = blockIdx.x, e = threadIdx.x;
-    const int t0 = W.key_tile_begin[key], t1 = W.key_tile_begin[key + 1];
-    if (e < 91) {
-        double s = 0.0;
-        for (int t = t0; t < t1; ++t) s += W.tile_partial[(size_t)NACC * t + e];
-        int r, c;
-        if (e < 55) {
-            int p = 0, rem = e;
-            while (rem >= 10 - p) { rem -= 10 - p; ++p; }
-            r = p; c = p + rem;
-        } else if (e < 85) { r = (e - 55) / 3; c = 10 + (e - 55) % 3; }
-        else { const int br[6][2] = {{10, 10}, {10, 11}, {10, 12}, {11, 11}, {11, 12}, {12, 12}}; r = br[e - 85][0]; c = br[e - 85][1]; }
-        double* H = acc + (size_t)169 * key;
-        H[13 * r + c] = s;
-        H[13 * c + r] = s;
-    }
-    if (e == 95) {
-        long long n = 0;
-        for (int t = t0; t < t1; ++t) n += W.tile_nres[t];
-        num[key] = n;
-    }
-}
-
-// per point: Hdd_acc, bd_acc, Hcd_acc (AccumulatedTopHessian.cpp:132-157), residuals in their stored order
-__global__ void ba_point_sum_kernel(const float* __restrict__ res_pt, const int32_t* __restrict__ res_begin, int P,
-                                    float* __restrict__ Hdd, float* __restrict__ bd, float* __restrict__ Hcd) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int r = res_begin[p]; r < res_begin[p + 1]; ++r) {
-        const float2* v = reinterpret_cast<const float2*>(res_pt + (size_t)6 * r);
-        const float2 a = __ldg(v), b = __ldg(v + 1), c = __ldg(v + 2);
-        s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y;
-    }
-    bd[p] = s[0];
-    Hdd[p] = s[1];
-    reinterpret_cast<float4*>(Hcd)[p] = make_float4(s[2], s[3], s[4], s[5]);
+    top_tile_partial(W, acc, nres, warp_part, warp_n);
+    grid_barrier(W.grid_bar, W.bar_target);
+    top_second_phase(W);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -912,6 +1008,8 @@ struct edsgpu_ba {
     float calib[4] = {0, 0, 0, 0};
     bool lin_inputs_set = false;
     unsigned images_set = 0;  // bit per frame
+    unsigned* grid_bar = nullptr;   // arrival counter of the accumulation kernels' grid barrier (device, only grows)
+    unsigned bar_count = 0;         // its value after the launches queued so far
     bool have_top[2] = {false, false}, have_sc = false;  // which accumulations of the current linearisation are on the device
     std::vector<double> adHost_h, adTarget_h;  // host copies for xAd of the back-substitution
     void* post_block = nullptr;                // xAd (F*F*8 floats), cstep (4), step (P), energy partials
@@ -926,7 +1024,37 @@ BaDev ba_dev(const edsgpu_ba* w) {
     d.perm = w->perm; d.tile_key = w->tile_key; d.tile_start = w->tile_start; d.tile_count = w->tile_count; d.key_tile_begin = w->key_tile_begin;
     d.recs = w->recs; d.res_toZero = w->res_toZero; d.deltaF = w->deltaF; d.priorF = w->priorF; d.adHTdeltaF = w->adHTdeltaF; d.cDeltaF = w->cDeltaF;
     d.flags = w->flags; d.res_pt = w->res_pt; d.tile_partial = w->tile_partial; d.tile_nres = w->tile_nres;
+    d.grid_bar = w->grid_bar;
     return d;
+}
+
+// output slot and barrier target of the next accumulation launch (every CTA of the launch arrives once)
+void ba_dev_outputs(edsgpu_ba* w, BaDev& d, int slot) {
+    d.acc_out = w->acc[slot]; d.num_out = w->num[slot];
+    d.Hdd_out = w->Hdd[slot]; d.bd_out = w->bd[slot]; d.Hcd_out = w->Hcd[slot];
+    w->bar_count += (unsigned)w->num_tiles;
+    d.bar_target = w->bar_count;
+}
+
+LinDev lin_dev(const edsgpu_ba* w, bool have_state_in, bool have_linearized) {
+    LinDev d{};
+    d.F = w->F; d.P = w->P; d.R = w->R; d.H = w->H; d.W = w->W;
+    d.images = w->images; d.precalc = w->precalc;
+    d.fxl = w->calib[0]; d.fyl = w->calib[1]; d.cxl = w->calib[2]; d.cyl = w->calib[3];
+    d.frame_energy_th = w->frame_energy_th;
+    d.pu = w->pu; d.pv = w->pv; d.idepth_zero = w->idepth_zero; d.idepth = w->idepth; d.color = w->color; d.weights = w->weights;
+    d.host_idx = w->host_idx; d.target_idx = w->target_idx; d.point_of_res = w->point_of_res;
+    d.state_in = have_state_in ? w->state_in : nullptr;
+    d.linearized = have_linearized ? w->linearized : nullptr;
+    d.recs = w->recs; d.flags = w->flags; d.state_new = w->state_new; d.energy_new = w->energy_new;
+    return d;
+}
+
+// The accumulation kernels end with a grid-wide barrier: cooperative launch (every CTA resident, or the launch fails).
+template <typename... Args>
+cudaError_t launch_cooperative(void (*kernel)(Args...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+    void* argv[] = {(void*)&args...};
+    return cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(block), argv, smem, stream);
 }
 
 edsgpu_status d2h(edsgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -1007,7 +1135,7 @@ edsgpu_status edsgpu_ba_create(edsgpu_ctx* ctx, int F, int P, int R, const int32
     for (int s = 0; s < 2; ++s) { o_Hdd[s] = take(4 * (size_t)P); o_bd[s] = take(4 * (size_t)P); o_Hcd[s] = take(16 * (size_t)P); o_acc[s] = take(8 * 169 * (size_t)F2); o_num[s] = take(8 * (size_t)F2); }
     const size_t o_hdi = take(4 * (size_t)P), o_bds = take(4 * (size_t)P), o_scp = take(4 * (size_t)C * Msc * Nsc), o_tp = take(8 * (size_t)NACC * T), o_tn = take(4 * (size_t)T);
     const size_t o_D = take(8 * 64 * (size_t)F2 * F), o_E = take(8 * 32 * (size_t)F2), o_EB = take(8 * 8 * (size_t)F2), o_Hcc = take(128), o_bc = take(32), o_hh = take(8 * 20 * (size_t)F);
-    const size_t o_Hm = take(8 * (size_t)n * n), o_bv = take(8 * (size_t)n), o_pr = take(8 * (size_t)(4 + 16 * F));
+    const size_t o_Hm = take(8 * (size_t)n * n), o_bv = take(8 * (size_t)n), o_pr = take(8 * (size_t)(4 + 16 * F)), o_gb = take(16);
     cudaError_t e = cudaMalloc(&w->block, off);
     if (e != cudaSuccess) { delete w; return edsgpu_fail(ctx, EDSGPU_OUT_OF_MEMORY, cudaGetErrorString(e)); }
     char* base = (char*)w->block;
@@ -1029,6 +1157,7 @@ edsgpu_status edsgpu_ba_create(edsgpu_ctx* ctx, int F, int P, int R, const int32
     w->accD = (double*)(base + o_D); w->accE = (double*)(base + o_E); w->accEB = (double*)(base + o_EB); w->accHcc = (double*)(base + o_Hcc);
     w->accbc = (double*)(base + o_bc); w->hcc_host = (double*)(base + o_hh); w->Hmat = (double*)(base + o_Hm); w->bvec = (double*)(base + o_bv);
     w->prior_buf = (double*)(base + o_pr);
+    w->grid_bar = (unsigned*)(base + o_gb);
     e = cudaMemsetAsync(w->block, 0, off, ctx->stream);
     auto up = [&](void* dst, const void* src, size_t bytes) { if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream); };
     up(w->host_idx, host_idx, 4 * (size_t)R); up(w->target_idx, target_idx, 4 * (size_t)R); up(w->point_of_res, point_of_res.data(), 4 * (size_t)R);
@@ -1109,22 +1238,21 @@ edsgpu_status edsgpu_ba_top_accumulate(edsgpu_ba* w, int mode, double* acc_out, 
     w->have_top[slot] = false;
     w->have_sc = false;
     if (mode == 2) w->have_top[0] = false;
-    const BaDev d = ba_dev(w);
+    BaDev d = ba_dev(w);
+    ba_dev_outputs(w, d, slot);
     const size_t stage_bytes = (size_t)TOP_STAGE * REC * sizeof(float);
+    // one kernel: tile partials, grid barrier, ordered sums over tiles and over each point's residuals
     if (mode == 0) {
         EDS_CUDA(ctx, cudaFuncSetAttribute(ba_top_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
-        ba_top_kernel<0><<<w->num_tiles, TOP_THREADS, stage_bytes, ctx->stream>>>(d);
+        EDS_CUDA(ctx, launch_cooperative(ba_top_kernel<0>, w->num_tiles, TOP_THREADS, stage_bytes, ctx->stream, d));
     } else if (mode == 1) {
         EDS_CUDA(ctx, cudaFuncSetAttribute(ba_top_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
-        ba_top_kernel<1><<<w->num_tiles, TOP_THREADS, stage_bytes, ctx->stream>>>(d);
+        EDS_CUDA(ctx, launch_cooperative(ba_top_kernel<1>, w->num_tiles, TOP_THREADS, stage_bytes, ctx->stream, d));
     } else {
         EDS_CUDA(ctx, cudaFuncSetAttribute(ba_top_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
-        ba_top_kernel<2><<<w->num_tiles, TOP_THREADS, stage_bytes, ctx->stream>>>(d);
+        EDS_CUDA(ctx, launch_cooperative(ba_top_kernel<2>, w->num_tiles, TOP_THREADS, stage_bytes, ctx->stream, d));
     }
-    EDS_CUDA(ctx, cudaGetLastError());
-    ba_top_finalize_kernel<<<w->F * w->F, 96, 0, ctx->stream>>>(d, w->acc[slot], w->num[slot]);
-    ba_point_sum_kernel<<<(w->P + 255) / 256, 256, 0, ctx->stream>>>(w->res_pt, w->res_begin, w->P, w->Hdd[slot], w->bd[slot], w->Hcd[slot]);
-    ctx->launches += 3;
+    ctx->launches += 1;
     EDS_CUDA(ctx, cudaGetLastError());
     if (mode == 2) {  // AccumulatedTopHessian.cpp:152-157: marginalisation zeroes the active-side point terms
         EDS_CUDA(ctx, cudaMemsetAsync(w->Hdd[0], 0, 4 * (size_t)w->P, ctx->stream));
@@ -1136,18 +1264,27 @@ edsgpu_status edsgpu_ba_top_accumulate(edsgpu_ba* w, int mode, double* acc_out, 
     // (EnergyFunctional.cpp:538-560) needs no separate active pass.
     w->have_top[slot] = true;
     if (mode == 2) w->have_top[0] = true;
-    if (acc_out || Hdd_out || bd_out || Hcd_out || nres_out) {
-        const size_t F2 = (size_t)w->F * w->F;
-        edsgpu_status st = edsgpu_ensure_pinned(ctx, 8 * F2);
-        if (st != EDSGPU_OK) return st;
-        if ((st = d2h(ctx, acc_out, w->acc[slot], 8 * 169 * F2)) != EDSGPU_OK) return st;
-        if ((st = d2h(ctx, Hdd_out, w->Hdd[slot], 4 * (size_t)w->P)) != EDSGPU_OK) return st;
-        if ((st = d2h(ctx, bd_out, w->bd[slot], 4 * (size_t)w->P)) != EDSGPU_OK) return st;
-        if ((st = d2h(ctx, Hcd_out, w->Hcd[slot], 16 * (size_t)w->P)) != EDSGPU_OK) return st;
-        if (nres_out) EDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, w->num[slot], 8 * F2, cudaMemcpyDeviceToHost, ctx->stream));
-        EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (nres_out) { int64_t n = 0; for (size_t k = 0; k < F2; ++k) n += ((long long*)ctx->pinned)[k]; *nres_out = n; }
-    }
+    if (acc_out || Hdd_out || bd_out || Hcd_out || nres_out) return edsgpu_ba_top_read(w, slot, acc_out, Hdd_out, bd_out, Hcd_out, nres_out);
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_top_read(edsgpu_ba* w, int which, double* acc_out, float* Hdd_out, float* bd_out, float* Hcd_out, int64_t* nres_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, which == 0 || which == 1, "ba_top_read: which must be 0 (active) or 1 (linearized)");
+    EDS_REQUIRE(ctx, w->have_top[which], "ba_top_read: this side has not been accumulated for the current linearisation");
+    DeviceGuard g(ctx->device);
+    const int slot = which;
+    const size_t F2 = (size_t)w->F * w->F;
+    edsgpu_status st = edsgpu_ensure_pinned(ctx, 8 * F2);
+    if (st != EDSGPU_OK) return st;
+    if ((st = d2h(ctx, acc_out, w->acc[slot], 8 * 169 * F2)) != EDSGPU_OK) return st;
+    if ((st = d2h(ctx, Hdd_out, w->Hdd[slot], 4 * (size_t)w->P)) != EDSGPU_OK) return st;
+    if ((st = d2h(ctx, bd_out, w->bd[slot], 4 * (size_t)w->P)) != EDSGPU_OK) return st;
+    if ((st = d2h(ctx, Hcd_out, w->Hcd[slot], 16 * (size_t)w->P)) != EDSGPU_OK) return st;
+    if (nres_out) EDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, w->num[slot], 8 * F2, cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nres_out) { int64_t n = 0; for (size_t k = 0; k < F2; ++k) n += ((long long*)ctx->pinned)[k]; *nres_out = n; }
     return EDSGPU_OK;
 }
 
@@ -1311,22 +1448,38 @@ edsgpu_status edsgpu_ba_linearize(edsgpu_ba* w, const uint8_t* state_in, const u
     if (linearized) EDS_CUDA(ctx, cudaMemcpyAsync(w->linearized, linearized, (size_t)w->R, cudaMemcpyHostToDevice, s));
     if (res_toZero) EDS_CUDA(ctx, cudaMemcpyAsync(w->res_toZero, res_toZero, 32 * (size_t)w->R, cudaMemcpyHostToDevice, s));
     w->have_top[0] = w->have_top[1] = w->have_sc = false;
-    LinDev d{};
-    d.F = w->F; d.P = w->P; d.R = w->R; d.H = w->H; d.W = w->W;
-    d.images = w->images; d.precalc = w->precalc;
-    d.fxl = w->calib[0]; d.fyl = w->calib[1]; d.cxl = w->calib[2]; d.cyl = w->calib[3];
-    d.frame_energy_th = w->frame_energy_th;
-    d.pu = w->pu; d.pv = w->pv; d.idepth_zero = w->idepth_zero; d.idepth = w->idepth; d.color = w->color; d.weights = w->weights;
-    d.host_idx = w->host_idx; d.target_idx = w->target_idx; d.point_of_res = w->point_of_res;
-    d.state_in = state_in ? w->state_in : nullptr;
-    d.linearized = linearized ? w->linearized : nullptr;
-    d.recs = w->recs; d.flags = w->flags; d.state_new = w->state_new; d.energy_new = w->energy_new;
+    const LinDev d = lin_dev(w, state_in != nullptr, linearized != nullptr);
     ba_linearize_kernel<<<(w->R + 127) / 128, 128, 0, s>>>(d);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
     ba_jpjd_kernel<<<(w->R + 255) / 256, 256, 0, s>>>(w->recs, w->R, w->JpJdF);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
+    if (state_out) EDS_CUDA(ctx, cudaMemcpyAsync(state_out, w->state_new, 4 * (size_t)w->R, cudaMemcpyDeviceToHost, s));
+    if (energy_out) EDS_CUDA(ctx, cudaMemcpyAsync(energy_out, w->energy_new, 4 * (size_t)w->R, cudaMemcpyDeviceToHost, s));
+    if (state_in || linearized || res_toZero || state_out || energy_out) EDS_CUDA(ctx, cudaStreamSynchronize(s));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_linearize_accumulate(edsgpu_ba* w, const uint8_t* state_in, const uint8_t* linearized, const float* res_toZero,
+                                             int write_records, int32_t* state_out, float* energy_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    EDS_REQUIRE(ctx, w->lin_inputs_set, "ba_linearize_accumulate: call edsgpu_ba_set_linearize_inputs first");
+    EDS_REQUIRE(ctx, w->images && w->images_set == (1u << w->F) - 1u, "ba_linearize_accumulate: call edsgpu_ba_set_image for every frame first");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    if (state_in) EDS_CUDA(ctx, cudaMemcpyAsync(w->state_in, state_in, (size_t)w->R, cudaMemcpyHostToDevice, s));
+    if (linearized) EDS_CUDA(ctx, cudaMemcpyAsync(w->linearized, linearized, (size_t)w->R, cudaMemcpyHostToDevice, s));
+    if (res_toZero) EDS_CUDA(ctx, cudaMemcpyAsync(w->res_toZero, res_toZero, 32 * (size_t)w->R, cudaMemcpyHostToDevice, s));
+    w->have_top[0] = w->have_top[1] = w->have_sc = false;
+    const LinDev d = lin_dev(w, state_in != nullptr, linearized != nullptr);
+    BaDev t = ba_dev(w);
+    ba_dev_outputs(w, t, 0);
+    EDS_CUDA(ctx, launch_cooperative(ba_lin_top_kernel, w->num_tiles, TOP_THREADS, (size_t)0, s, d, t, w->JpJdF, write_records ? 1 : 0));
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaGetLastError());
+    w->have_top[0] = true;
     if (state_out) EDS_CUDA(ctx, cudaMemcpyAsync(state_out, w->state_new, 4 * (size_t)w->R, cudaMemcpyDeviceToHost, s));
     if (energy_out) EDS_CUDA(ctx, cudaMemcpyAsync(energy_out, w->energy_new, 4 * (size_t)w->R, cudaMemcpyDeviceToHost, s));
     if (state_in || linearized || res_toZero || state_out || energy_out) EDS_CUDA(ctx, cudaStreamSynchronize(s));

@@ -37,8 +37,8 @@ struct CoarseArgs {
     double* partials;     // [gridDim.x][CT_NPART]
 };
 
-__global__ void __launch_bounds__(CT_THREADS) coarse_res_gs_kernel(CoarseArgs a) {
-    __shared__ double red[CT_THREADS / 32][CT_NPART];
+// one CTA's share of an evaluation: points blockIdx.x * blockDim.x + threadIdx.x (+ grid stride) -> partial[CT_NPART]
+__device__ __forceinline__ void coarse_sweep(const CoarseArgs& a, double (*red)[CT_NPART], double* __restrict__ partial) {
     float acc[CT_NACC];
 #pragma unroll
     for (int i = 0; i < CT_NACC; ++i) acc[i] = 0.f;
@@ -136,8 +136,13 @@ __global__ void __launch_bounds__(CT_THREADS) coarse_res_gs_kernel(CoarseArgs a)
     if (threadIdx.x < CT_NPART) {
         double s = 0.0;
         for (int w = 0; w < CT_THREADS / 32; ++w) s += red[w][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * CT_NPART + threadIdx.x] = s;
+        partial[threadIdx.x] = s;
     }
+}
+
+__global__ void __launch_bounds__(CT_THREADS) coarse_res_gs_kernel(CoarseArgs a) {
+    __shared__ double red[CT_THREADS / 32][CT_NPART];
+    coarse_sweep(a, red, a.partials + (size_t)blockIdx.x * CT_NPART);
 }
 
 __global__ void coarse_finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
@@ -164,11 +169,17 @@ struct Level {
 
 }  // namespace
 
+namespace {
+__host__ __device__ void coarse_outputs(const double* v, double* rs, double* H, double* b);
+}
+
 struct edsgpu_coarse {
     edsgpu_ctx* ctx = nullptr;
     std::vector<Level> levels;
     double* partials = nullptr;  // [max grid][CT_NPART] + CT_NPART result
     int max_grid = 0;
+    void* track_io = nullptr;        // TrackIO of edsgpu_coarse_track (device)
+    unsigned* track_bar = nullptr;   // {arrivals, generation} of its grid barrier
 };
 
 extern "C" {
@@ -182,7 +193,10 @@ edsgpu_status edsgpu_coarse_create(edsgpu_ctx* ctx, int num_levels, edsgpu_coars
     c->levels.resize(num_levels);
     c->max_grid = 2 * ctx->num_sms;
     cudaError_t e = cudaMalloc(&c->partials, sizeof(double) * CT_NPART * ((size_t)c->max_grid + 1));
-    if (e != cudaSuccess) { delete c; return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaMalloc(&c->track_io, 1024);
+    if (e == cudaSuccess) e = cudaMalloc(&c->track_bar, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->track_bar, 0, 2 * sizeof(unsigned), ctx->stream);
+    if (e != cudaSuccess) { edsgpu_coarse_destroy(c); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
     *out = c;
     return EDSGPU_OK;
 }
@@ -196,6 +210,8 @@ void edsgpu_coarse_destroy(edsgpu_coarse* c) {
         if (l.pc) cudaFree(l.pc);
     }
     if (c->partials) cudaFree(c->partials);
+    if (c->track_io) cudaFree(c->track_io);
+    if (c->track_bar) cudaFree(c->track_bar);
     delete c;
 }
 
@@ -295,36 +311,17 @@ edsgpu_status edsgpu_coarse_calc_res_gs(edsgpu_coarse* c, int lvl, const double 
     EDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_out, sizeof(double) * CT_NPART, cudaMemcpyDeviceToHost, ctx->stream));
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const double* v = (const double*)ctx->pinned;
-    const double E = v[CT_NACC], nE = v[CT_NACC + 1], nW = v[CT_NACC + 2], nSat = v[CT_NACC + 3];
-    const float shT = (float)v[CT_NACC + 4], shRT = (float)v[CT_NACC + 5], shNum = (float)v[CT_NACC + 6];
-    rs[0] = E;
-    rs[1] = nE;
-    rs[2] = shT / (shNum + 0.1);
-    rs[3] = 0;
-    rs[4] = shRT / (shNum + 0.1);
-    rs[5] = (float)nSat / (float)nE;
-    if (H && b) {
-        // H_out = acc.H.topLeftCorner<8,8>().cast<double>() * (1.0f / n), n padded to a multiple of 4 (:466-478, :332-344)
-        const long long npad = ((long long)nW + 3) / 4 * 4;
-        const float inv_n = 1.0f / (float)npad;
-        const double sc[8] = {1, 1, 1, 1, 1, 1, 10.0f, 1000.0f};  // SCALE_XI_ROT, SCALE_XI_TRANS, SCALE_A, SCALE_B
-        double full[9][9];
-        int e = 0;
-        for (int r = 0; r < 9; ++r)
-            for (int q = r; q < 9; ++q) { full[r][q] = full[q][r] = v[e++]; }
-        for (int r = 0; r < 8; ++r) {
-            for (int q = 0; q < 8; ++q) H[8 * r + q] = (double)(float)full[r][q] * inv_n * (sc[r] * sc[q]);
-            b[r] = (double)(float)full[r][8] * inv_n * sc[r];
-        }
-    }
+    coarse_outputs(v, rs, H, b);
     return EDSGPU_OK;
 }
 
-// ---- trackNewestCoarse: the coarse-to-fine Gauss-Newton loop on the host around the device evaluation ----------
+}  // extern "C"
+
+// ---- trackNewestCoarse ---------------------------------------------------------------------------------------
 namespace {
 
 // Sophus SO3::exp (quaternion form) -> rotation matrix, row-major
-void so3_exp(const double* w, double* R) {
+__host__ __device__ void so3_exp(const double* w, double* R) {
     const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
     double imag, real;
     if (th < 1e-10) {
@@ -342,7 +339,7 @@ void so3_exp(const double* w, double* R) {
 }
 
 // (R, t) <- SE3::exp(inc) * (R, t), inc = [translation part, rotation part]
-void se3_left_update(const double* inc6, double* R, double* t) {
+__host__ __device__ void se3_left_update(const double* inc6, double* R, double* t) {
     const double* u = inc6;
     const double* w = inc6 + 3;
     double Re[9], V[9];
@@ -366,12 +363,12 @@ void se3_left_update(const double* inc6, double* R, double* t) {
         for (int c = 0; c < 3; ++c) Rn[3 * r + c] = Re[3 * r] * R[c] + Re[3 * r + 1] * R[3 + c] + Re[3 * r + 2] * R[6 + c];
         tn[r] = Re[3 * r] * t[0] + Re[3 * r + 1] * t[1] + Re[3 * r + 2] * t[2] + te[r];
     }
-    memcpy(R, Rn, sizeof(Rn));
-    memcpy(t, tn, sizeof(tn));
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+    for (int i = 0; i < 3; ++i) t[i] = tn[i];
 }
 
 // x = A^-1 rhs, A symmetric positive definite 8x8 (LDL^T; the reference calls Eigen's ldlt().solve)
-void solve8(const double* A, const double* rhs, double* x) {
+__host__ __device__ void solve8(const double* A, const double* rhs, double* x) {
     double L[64] = {0}, D[8], y[8];
     for (int j = 0; j < 8; ++j) {
         double d = A[8 * j + j];
@@ -389,7 +386,256 @@ void solve8(const double* A, const double* rhs, double* x) {
     for (int i = 7; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 8; ++k) v -= L[8 * k + i] * x[k]; x[i] = v; }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// trackNewestCoarse on the device: ONE cooperative launch runs the whole coarse-to-fine loop.  Every evaluation is a
+// sweep of the level's points by all CTAs, one grid barrier, then every CTA adds the per-CTA partials in order and its
+// thread 0 advances the (identical) state machine: Levenberg damping, 8x8 LDL^T, SE3::exp update, accept / reject,
+// cutoff repeat, level change.  No host round trip inside the loop (it cost ~40 us per evaluation).
+// ------------------------------------------------------------------------------------------
+constexpr int CT_MAX_LEVELS = 5;  // PYR_LEVELS the loop can visit (coarsest_lvl < 5, CoarseTracker.cpp:540)
+
+struct LevelDev {
+    int w, h, n;
+    float fx, fy, cx, cy;
+    float Ki[9];  // column-major as given
+    const float4* image;
+    const float *u, *v, *idepth, *color;
+};
+
+struct TrackIO {  // global memory, in-out
+    double R[9], t[3], aff[2];
+    double ref_aff[2], min_res[5];
+    double last_residuals[5], last_flow[3];
+    float ref_exposure, new_exposure;
+    int has_min_res, coarsest;
+    int evaluations, status;  // status: 0 = tracked, 1 = residual above the abort threshold, 2 = affine parameters out of range
+};
+
+struct TrackArgs {
+    LevelDev lv[CT_MAX_LEVELS];
+    TrackIO* io;
+    double* partials;  // [2][gridDim.x][CT_NPART], double-buffered by evaluation
+    unsigned* bar;     // {arrivals, generation} of the grid barrier
+};
+
+struct TrackCtl {  // shared memory; written by thread 0 only
+    double Rc[9], tc[3], affc[2];   // accepted pose
+    double Rn[9], tn[3], affn[2];   // proposal under evaluation
+    double H[64], b[8], resOld[6], inc[8];
+    float lambda, repeat;
+    int lvl, iteration, state, haveRepeated, ok, evaluations, done;
+    CoarseArgs a;                   // the evaluation every thread sweeps next
+};
+enum { TS_FIRST = 0, TS_ITER = 1 };
+
+// sense-reversing grid barrier (cooperative launch: every CTA is resident)
+__device__ __forceinline__ void track_grid_barrier(unsigned* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned gen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+        __threadfence();
+        if (atomicAdd(bar, 1u) == gridDim.x - 1u) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            unsigned g2;
+            do {
+                __nanosleep(30);
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(bar + 1) : "memory");
+            } while (g2 == gen);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// the evaluation request of (lvl, R, t, aff): what edsgpu_coarse_calc_res_gs sets up on the host
+__device__ void track_request(TrackCtl& c, const TrackArgs& A, const TrackIO& io, int lvl, const double* R, const double* t, const double* aff) {
+    const LevelDev& l = A.lv[lvl];
+    CoarseArgs& a = c.a;
+    a.lvl = lvl; a.wl = l.w; a.hl = l.h; a.n = l.n;
+    a.fxl = l.fx; a.fyl = l.fy; a.cxl = l.cx; a.cyl = l.cy;
+    for (int i = 0; i < 3; ++i) {
+        a.t[i] = (float)t[i];
+        for (int j = 0; j < 3; ++j) {
+            a.Ki[3 * i + j] = l.Ki[3 * j + i];
+            a.RKi[3 * i + j] = fa(fa(fm((float)R[3 * i + 0], l.Ki[3 * j + 0]), fm((float)R[3 * i + 1], l.Ki[3 * j + 1])), fm((float)R[3 * i + 2], l.Ki[3 * j + 2]));
+        }
+    }
+    // AffLight::fromToVecExposure, NumType.h:175-187
+    float eF = io.ref_exposure, eT = io.new_exposure;
+    if (eF == 0 || eT == 0) eF = eT = 1;
+    const double e = exp(aff[0] - io.ref_aff[0]) * eT / eF;
+    a.aff0 = (float)e;
+    a.aff1 = (float)(aff[1] - e * io.ref_aff[1]);
+    a.b0 = (float)io.ref_aff[1];
+    a.cutoffTH = 20.0f * c.repeat;  // setting_coarseCutoffTH, settings.cpp:138
+    a.image = l.image;
+    a.pc_u = l.u; a.pc_v = l.v; a.pc_idepth = l.idepth; a.pc_color = l.color;
+    a.partials = nullptr;
+    c.evaluations++;
+}
+
+// reduced sums -> calcRes' Vec6 and calcGSSSE's H, b (same arithmetic as the host entry point)
+__host__ __device__ void coarse_outputs(const double* v, double* rs, double* H, double* b) {
+    const double E = v[CT_NACC], nE = v[CT_NACC + 1], nW = v[CT_NACC + 2], nSat = v[CT_NACC + 3];
+    const float shT = (float)v[CT_NACC + 4], shRT = (float)v[CT_NACC + 5], shNum = (float)v[CT_NACC + 6];
+    rs[0] = E;
+    rs[1] = nE;
+    rs[2] = shT / (shNum + 0.1);
+    rs[3] = 0;
+    rs[4] = shRT / (shNum + 0.1);
+    rs[5] = (float)nSat / (float)nE;
+    if (H && b) {
+        // H_out = acc.H.topLeftCorner<8,8>().cast<double>() * (1.0f / n), n padded to a multiple of 4 (:466-478, :332-344)
+        const long long npad = ((long long)nW + 3) / 4 * 4;
+        const float inv_n = 1.0f / (float)npad;
+        const double sc[8] = {1, 1, 1, 1, 1, 1, 10.0f, 1000.0f};  // SCALE_XI_ROT, SCALE_XI_TRANS, SCALE_A, SCALE_B
+        double full[9][9];
+        int e = 0;
+        for (int r = 0; r < 9; ++r)
+            for (int q = r; q < 9; ++q) { full[r][q] = full[q][r] = v[e++]; }
+        for (int r = 0; r < 8; ++r) {
+            for (int q = 0; q < 8; ++q) H[8 * r + q] = (double)(float)full[r][q] * inv_n * (sc[r] * sc[q]);
+            b[r] = (double)(float)full[r][8] * inv_n * sc[r];
+        }
+    }
+}
+
+// thread 0: consume the evaluation that has just been reduced into `sums`, decide what happens next (CoarseTracker.cpp:540-701)
+__device__ void track_advance(TrackCtl& c, const TrackArgs& A, TrackIO& io, const double* sums) {
+    const int maxIterations[5] = {10, 20, 100, 100, 100};
+    const float lambdaExtrapolationLimit = 0.001f;
+    double rs[6], Hn[64], bn[8];
+    coarse_outputs(sums, rs, Hn, bn);
+    bool level_end = false;
+    if (c.state == TS_FIRST) {
+        for (int i = 0; i < 6; ++i) c.resOld[i] = rs[i];
+        for (int i = 0; i < 64; ++i) c.H[i] = Hn[i];
+        for (int i = 0; i < 8; ++i) c.b[i] = bn[i];
+        if (c.resOld[5] > 0.6 && c.repeat < 50) {
+            c.repeat *= 2;
+            track_request(c, A, io, c.lvl, c.Rc, c.tc, c.affc);
+            return;
+        }
+        c.lambda = 0.01f;
+        c.iteration = 0;
+    } else {
+        const bool accept = (rs[0] / rs[1]) < (c.resOld[0] / c.resOld[1]);
+        if (accept) {
+            for (int i = 0; i < 64; ++i) c.H[i] = Hn[i];
+            for (int i = 0; i < 8; ++i) c.b[i] = bn[i];
+            for (int i = 0; i < 6; ++i) c.resOld[i] = rs[i];
+            c.affc[0] = c.affn[0]; c.affc[1] = c.affn[1];
+            for (int i = 0; i < 9; ++i) c.Rc[i] = c.Rn[i];
+            for (int i = 0; i < 3; ++i) c.tc[i] = c.tn[i];
+            c.lambda *= 0.5f;
+        } else {
+            c.lambda *= 4;
+            if (c.lambda < lambdaExtrapolationLimit) c.lambda = lambdaExtrapolationLimit;
+        }
+        double norm2 = 0;
+        for (int i = 0; i < 8; ++i) norm2 += c.inc[i] * c.inc[i];
+        if (!(sqrt(norm2) > 1e-3)) level_end = true;
+        c.iteration++;
+    }
+    for (;;) {
+        if (!level_end && c.iteration < maxIterations[c.lvl]) {
+            // propose a step
+            double Hl[64], nb[8];
+            for (int i = 0; i < 64; ++i) Hl[i] = c.H[i];
+            for (int i = 0; i < 8; ++i) { Hl[9 * i] *= (1 + c.lambda); nb[i] = -c.b[i]; }
+            solve8(Hl, nb, c.inc);  // both affine parameters are optimised (setting_affineOptModeA/B >= 0, settings.cpp:119-120)
+            float extrapFac = 1;
+            if (c.lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / c.lambda));
+            for (int i = 0; i < 8; ++i) c.inc[i] *= extrapFac;
+            double incScaled[8];
+            for (int i = 0; i < 8; ++i) incScaled[i] = c.inc[i];
+            incScaled[6] *= 10.0f;    // SCALE_A (SCALE_XI_ROT = SCALE_XI_TRANS = 1)
+            incScaled[7] *= 1000.0f;  // SCALE_B
+            double sum = 0;
+            for (int i = 0; i < 8; ++i) sum += incScaled[i];
+            if (!isfinite(sum))
+                for (int i = 0; i < 8; ++i) incScaled[i] = 0;
+            c.affn[0] = c.affc[0] + incScaled[6];
+            c.affn[1] = c.affc[1] + incScaled[7];
+            for (int i = 0; i < 9; ++i) c.Rn[i] = c.Rc[i];
+            for (int i = 0; i < 3; ++i) c.tn[i] = c.tc[i];
+            se3_left_update(incScaled, c.Rn, c.tn);
+            c.state = TS_ITER;
+            track_request(c, A, io, c.lvl, c.Rn, c.tn, c.affn);  // the fused evaluation already has the system the reference recomputes on accept
+            return;
+        }
+        // the level is finished
+        io.last_residuals[c.lvl] = sqrtf((float)(c.resOld[0] / c.resOld[1]));
+        for (int i = 0; i < 3; ++i) io.last_flow[i] = c.resOld[2 + i];
+        if (io.has_min_res && io.last_residuals[c.lvl] > 1.5 * io.min_res[c.lvl]) c.ok = 0;
+        if (c.ok && c.repeat > 1 && !c.haveRepeated) { c.lvl++; c.haveRepeated = 1; }
+        c.lvl--;
+        if (c.lvl < 0 || !c.ok) { c.done = 1; return; }
+        c.repeat = 1;
+        c.state = TS_FIRST;
+        track_request(c, A, io, c.lvl, c.Rc, c.tc, c.affc);
+        return;
+    }
+}
+
+__global__ void __launch_bounds__(CT_THREADS) coarse_track_kernel(TrackArgs A) {
+    __shared__ double red[CT_THREADS / 32][CT_NPART];
+    __shared__ double sums[CT_NPART];
+    __shared__ TrackCtl c;
+    TrackIO& io = *A.io;
+    if (threadIdx.x == 0) {
+        // every CTA runs the same state machine on the same numbers; only CTA 0 writes results
+        for (int i = 0; i < 9; ++i) c.Rc[i] = io.R[i];
+        for (int i = 0; i < 3; ++i) c.tc[i] = io.t[i];
+        c.affc[0] = io.aff[0]; c.affc[1] = io.aff[1];
+        c.lvl = io.coarsest; c.haveRepeated = 0; c.ok = 1; c.evaluations = 0; c.done = 0;
+        c.repeat = 1; c.state = TS_FIRST; c.lambda = 0.01f; c.iteration = 0;
+        track_request(c, A, io, c.lvl, c.Rc, c.tc, c.affc);
+    }
+    __syncthreads();
+    for (unsigned k = 0;; ++k) {
+        double* buf = A.partials + (size_t)(k & 1u) * gridDim.x * CT_NPART;
+        coarse_sweep(c.a, red, buf + (size_t)blockIdx.x * CT_NPART);
+        track_grid_barrier(A.bar);
+        if (threadIdx.x < CT_NPART) {
+            double s = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(buf + (size_t)b * CT_NPART + threadIdx.x);
+            sums[threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) {
+                track_advance(c, A, io, sums);
+            } else {
+                // the other CTAs must not write the shared outputs: they advance a private copy of the bookkeeping
+                TrackIO scratch = io;
+                track_advance(c, A, scratch, sums);
+            }
+        }
+        __syncthreads();
+        if (c.done) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        io.evaluations = c.evaluations;
+        io.status = 0;
+        if (!c.ok) io.status = 1;
+        else {
+            for (int i = 0; i < 9; ++i) io.R[i] = c.Rc[i];
+            for (int i = 0; i < 3; ++i) io.t[i] = c.tc[i];
+            io.aff[0] = c.affc[0]; io.aff[1] = c.affc[1];
+            if (fabsf((float)c.affc[0]) > 1.2f || fabsf((float)c.affc[1]) > 200.f) io.status = 2;  // :683-685
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" {
 
 edsgpu_status edsgpu_coarse_track(edsgpu_coarse* c, int coarsest_lvl, double R[9], double t[3], double aff_g2l[2], const double ref_aff_g2l[2],
                                   float ref_exposure, float new_exposure, const double min_res_for_abort[5], double last_residuals[5],
@@ -397,83 +643,52 @@ edsgpu_status edsgpu_coarse_track(edsgpu_coarse* c, int coarsest_lvl, double R[9
     if (!c) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = c->ctx;
     EDS_REQUIRE(ctx, R && t && aff_g2l && ref_aff_g2l && last_residuals && last_flow, "coarse_track: null argument");
-    EDS_REQUIRE(ctx, coarsest_lvl >= 0 && coarsest_lvl < 5 && coarsest_lvl < (int)c->levels.size(), "coarse_track: coarsest level out of range");
-    const float setting_coarseCutoffTH = 20.0f;  // settings.cpp:138
-    const int maxIterations[5] = {10, 20, 100, 100, 100};
-    const float lambdaExtrapolationLimit = 0.001f;
-    int evaluations = 0;
-    edsgpu_status st = EDSGPU_OK;
-    auto eval = [&](int lvl, const double* Rc, const double* tc, const double* affc, float cutoff, double* rs, double* H, double* b) {
-        // AffLight::fromToVecExposure, NumType.h:175-187
-        float eF = ref_exposure, eT = new_exposure;
-        if (eF == 0 || eT == 0) eF = eT = 1;
-        const double a = exp(affc[0] - ref_aff_g2l[0]) * eT / eF;
-        const float ll[2] = {(float)a, (float)(affc[1] - a * ref_aff_g2l[1])};
-        ++evaluations;
-        return edsgpu_coarse_calc_res_gs(c, lvl, Rc, tc, ll, (float)ref_aff_g2l[1], cutoff, rs, H, b);
-    };
-    for (int i = 0; i < 5; ++i) last_residuals[i] = NAN;
-    for (int i = 0; i < 3; ++i) last_flow[i] = 1000;
-    double Rc[9], tc[3], affc[2] = {aff_g2l[0], aff_g2l[1]};
-    memcpy(Rc, R, sizeof(Rc));
-    memcpy(tc, t, sizeof(tc));
-    bool haveRepeated = false, ok = true;
-    for (int lvl = coarsest_lvl; lvl >= 0 && ok; lvl--) {
-        double H[64], b[8], resOld[6];
-        float levelCutoffRepeat = 1;
-        if ((st = eval(lvl, Rc, tc, affc, setting_coarseCutoffTH * levelCutoffRepeat, resOld, H, b)) != EDSGPU_OK) return st;
-        while (resOld[5] > 0.6 && levelCutoffRepeat < 50) {
-            levelCutoffRepeat *= 2;
-            if ((st = eval(lvl, Rc, tc, affc, setting_coarseCutoffTH * levelCutoffRepeat, resOld, H, b)) != EDSGPU_OK) return st;
-        }
-        float lambda = 0.01f;
-        for (int iteration = 0; iteration < maxIterations[lvl]; iteration++) {
-            double Hl[64], nb[8], inc[8];
-            memcpy(Hl, H, sizeof(Hl));
-            for (int i = 0; i < 8; ++i) { Hl[9 * i] *= (1 + lambda); nb[i] = -b[i]; }
-            solve8(Hl, nb, inc);  // both affine parameters are optimised (setting_affineOptModeA/B >= 0, settings.cpp:119-120)
-            float extrapFac = 1;
-            if (lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / lambda));
-            for (int i = 0; i < 8; ++i) inc[i] *= extrapFac;
-            double incScaled[8];
-            memcpy(incScaled, inc, sizeof(inc));
-            incScaled[6] *= 10.0f;    // SCALE_A (SCALE_XI_ROT = SCALE_XI_TRANS = 1)
-            incScaled[7] *= 1000.0f;  // SCALE_B
-            double sum = 0;
-            for (int i = 0; i < 8; ++i) sum += incScaled[i];
-            if (!std::isfinite(sum)) memset(incScaled, 0, sizeof(incScaled));
-            double Rn[9], tn[3], affn[2] = {affc[0] + incScaled[6], affc[1] + incScaled[7]};
-            memcpy(Rn, Rc, sizeof(Rn));
-            memcpy(tn, tc, sizeof(tn));
-            se3_left_update(incScaled, Rn, tn);
-            double resNew[6], Hn[64], bn[8];  // the fused evaluation already has the system the reference recomputes on accept
-            if ((st = eval(lvl, Rn, tn, affn, setting_coarseCutoffTH * levelCutoffRepeat, resNew, Hn, bn)) != EDSGPU_OK) return st;
-            const bool accept = (resNew[0] / resNew[1]) < (resOld[0] / resOld[1]);
-            if (accept) {
-                memcpy(H, Hn, sizeof(H)); memcpy(b, bn, sizeof(b)); memcpy(resOld, resNew, sizeof(resOld));
-                affc[0] = affn[0]; affc[1] = affn[1];
-                memcpy(Rc, Rn, sizeof(Rc)); memcpy(tc, tn, sizeof(tc));
-                lambda *= 0.5f;
-            } else {
-                lambda *= 4;
-                if (lambda < lambdaExtrapolationLimit) lambda = lambdaExtrapolationLimit;
-            }
-            double norm2 = 0;
-            for (int i = 0; i < 8; ++i) norm2 += inc[i] * inc[i];
-            if (!(sqrt(norm2) > 1e-3)) break;
-        }
-        last_residuals[lvl] = sqrtf((float)(resOld[0] / resOld[1]));
-        for (int i = 0; i < 3; ++i) last_flow[i] = resOld[2 + i];
-        if (min_res_for_abort && last_residuals[lvl] > 1.5 * min_res_for_abort[lvl]) ok = false;
-        if (ok && levelCutoffRepeat > 1 && !haveRepeated) { lvl++; haveRepeated = true; }
+    EDS_REQUIRE(ctx, coarsest_lvl >= 0 && coarsest_lvl < CT_MAX_LEVELS && coarsest_lvl < (int)c->levels.size(), "coarse_track: coarsest level out of range");
+    DeviceGuard g(ctx->device);
+    TrackArgs A{};
+    int nmax = 1;
+    for (int lvl = 0; lvl <= coarsest_lvl; ++lvl) {
+        const Level& l = c->levels[lvl];
+        EDS_REQUIRE(ctx, l.has_image && l.n > 0, "coarse_track: every level needs a reference point cloud and a new frame");
+        LevelDev& d = A.lv[lvl];
+        d.w = l.w; d.h = l.h; d.n = l.n; d.fx = l.fx; d.fy = l.fy; d.cx = l.cx; d.cy = l.cy;
+        memcpy(d.Ki, l.Ki, sizeof(d.Ki));
+        d.image = l.image;
+        d.u = l.pc; d.v = l.pc + l.cap; d.idepth = l.pc + 2 * (size_t)l.cap; d.color = l.pc + 3 * (size_t)l.cap;
+        nmax = std::max(nmax, l.n);
     }
-    if (evaluations_out) *evaluations_out = evaluations;
-    if (!ok) return edsgpu_fail(ctx, EDSGPU_NOT_USABLE, "coarse_track: residual above the abort threshold");
-    memcpy(R, Rc, sizeof(Rc));
-    memcpy(t, tc, sizeof(tc));
-    aff_g2l[0] = affc[0]; aff_g2l[1] = affc[1];
-    if (fabsf((float)affc[0]) > 1.2f || fabsf((float)affc[1]) > 200.f)  // :683-685
-        return edsgpu_fail(ctx, EDSGPU_NOT_USABLE, "coarse_track: affine brightness parameters out of range");
+    edsgpu_status st = edsgpu_ensure_pinned(ctx, sizeof(TrackIO));
+    if (st != EDSGPU_OK) return st;
+    TrackIO* h = (TrackIO*)ctx->pinned;
+    memset(h, 0, sizeof(TrackIO));
+    memcpy(h->R, R, sizeof(h->R)); memcpy(h->t, t, sizeof(h->t));
+    h->aff[0] = aff_g2l[0]; h->aff[1] = aff_g2l[1];
+    h->ref_aff[0] = ref_aff_g2l[0]; h->ref_aff[1] = ref_aff_g2l[1];
+    h->ref_exposure = ref_exposure; h->new_exposure = new_exposure;
+    h->has_min_res = min_res_for_abort ? 1 : 0;
+    if (min_res_for_abort) memcpy(h->min_res, min_res_for_abort, sizeof(h->min_res));
+    h->coarsest = coarsest_lvl;
+    for (int i = 0; i < 5; ++i) h->last_residuals[i] = NAN;
+    for (int i = 0; i < 3; ++i) h->last_flow[i] = 1000;
+    EDS_CUDA(ctx, cudaMemcpyAsync(c->track_io, h, sizeof(TrackIO), cudaMemcpyHostToDevice, ctx->stream));
+    A.io = (TrackIO*)c->track_io;
+    A.partials = c->partials;
+    A.bar = c->track_bar;
+    // one CTA per 256 points of the largest level, at most one per SM (cooperative launch: all resident)
+    const int grid = std::max(1, std::min((nmax + CT_THREADS - 1) / CT_THREADS, std::min(ctx->num_sms, c->max_grid / 2)));
+    void* argv[] = {(void*)&A};
+    EDS_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)coarse_track_kernel, dim3(grid), dim3(CT_THREADS), argv, 0, ctx->stream));
+    ctx->launches++;
+    EDS_CUDA(ctx, cudaMemcpyAsync(h, c->track_io, sizeof(TrackIO), cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 5; ++i) last_residuals[i] = h->last_residuals[i];
+    for (int i = 0; i < 3; ++i) last_flow[i] = h->last_flow[i];
+    if (evaluations_out) *evaluations_out = h->evaluations;
+    if (h->status == 1) return edsgpu_fail(ctx, EDSGPU_NOT_USABLE, "coarse_track: residual above the abort threshold");
+    memcpy(R, h->R, sizeof(h->R));
+    memcpy(t, h->t, sizeof(h->t));
+    aff_g2l[0] = h->aff[0]; aff_g2l[1] = h->aff[1];
+    if (h->status == 2) return edsgpu_fail(ctx, EDSGPU_NOT_USABLE, "coarse_track: affine brightness parameters out of range");
     return EDSGPU_OK;
 }
 

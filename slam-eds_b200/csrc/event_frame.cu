@@ -11,13 +11,19 @@
 //                               the last CTA of each frame reduces the per-tile partials in a
 //                               fixed order and publishes norm and 1/norm.
 // The frame is stored un-normalised in fp32; consumers multiply by 1/norm when sampling.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "frames.cuh"
 
 namespace {
 
 constexpr double kQ = 1099511627776.0;  // 2^40
-constexpr int TILE_W = 64, TILE_H = 16, BLUR_THREADS = 256;
+// blur: a warp owns a strip of BLUR_COLS output columns (its two outer lanes only carry the halo columns) by BLUR_ROWS rows
+constexpr int BLUR_THREADS = 256, BLUR_WARPS = BLUR_THREADS / 32, BLUR_COLS = 30, BLUR_ROWS = 64;
+__host__ __device__ constexpr int blur_strips_x(int W) { return (W + BLUR_COLS - 1) / BLUR_COLS; }
+__host__ __device__ constexpr int blur_strips_y(int H) { return (H + BLUR_ROWS - 1) / BLUR_ROWS; }
+__host__ __device__ constexpr int blur_ctas(int H, int W) { return (blur_strips_x(W) * blur_strips_y(H) + BLUR_WARPS - 1) / BLUR_WARPS; }
 
 // Utils.hpp:542-546 with idx = i / E, window_size = 1 (Utils.cpp:72).
 __device__ __forceinline__ double exp_weight(int i, int E) {
@@ -124,76 +130,77 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-// OUT64 == false: write the fp32 frame + per-tile sum of squares, last CTA publishes norm.
+// 3x3 separable Gaussian (cv::GaussianBlur, BORDER_REFLECT_101, Utils.cpp:113-119) + sum of squares (cv::norm L2,
+// EventFrame.cpp:360-364).  One thread per column of a strip, walking down the rows: the accumulator is read ONCE per
+// pixel (coalesced 64-bit loads), the row pass takes its neighbours from the adjacent lanes by shuffle, the column pass
+// keeps the last three row-filtered values in registers -- no shared-memory tile, no CTA barrier in the sweep.  fp64 in
+// OpenCV's operation order (explicit mul / add, no FMA contraction): bit-exact against the oracle on exactly
+// representable input.
+// OUT64 == false: write the fp32 frame + per-CTA sum of squares, the last CTA of a window publishes norm and 1/norm.
 // OUT64 == true : write out64 = blurred * scale (debug / host read-back path).
 template <bool OUT64>
 __global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long* __restrict__ acc, int H, int W, double k0, double k1,
                                                                  const cudaSurfaceObject_t* __restrict__ surfs, double* __restrict__ partials,
                                                                  unsigned* __restrict__ tickets, double* __restrict__ norms,
-                                                                 int first_slot, double* __restrict__ out64,
+                                                                 int first_slot, int first_acc, double* __restrict__ out64,
                                                                  const double* __restrict__ scale_ptr) {
-    __shared__ double src[TILE_H + 2][TILE_W + 2];
-    __shared__ double tmp[TILE_H + 2][TILE_W];
-    __shared__ double wsum[BLUR_THREADS / 32];
+    __shared__ double wsum[BLUR_WARPS];
     __shared__ bool is_last;
     const int win = blockIdx.z;
     const int slot = first_slot + win;
-    const long long* img = acc + (size_t)slot * H * W;
-    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (TILE_H + 2) * (TILE_W + 2); i += BLUR_THREADS) {
-        int ly = i / (TILE_W + 2), lx = i % (TILE_W + 2);
-        int gy = reflect101(min(y0 + ly - 1, H), H), gx = reflect101(min(x0 + lx - 1, W), W);
-        // min(.., H): tiles hanging over the border may index one past the reflection range
-        gy = max(0, min(gy, H - 1));
-        gx = max(0, min(gx, W - 1));
-        src[ly][lx] = (double)img[(size_t)gy * W + gx] * (1.0 / kQ);
-    }
-    __syncthreads();
-    // row pass, generic cv::RowFilter order: left, centre, right (Utils.cpp:118)
-    for (int i = tid; i < (TILE_H + 2) * TILE_W; i += BLUR_THREADS) {
-        int ly = i / TILE_W, lx = i % TILE_W;
-        double v = __dadd_rn(__dadd_rn(__dmul_rn(src[ly][lx], k0), __dmul_rn(src[ly][lx + 1], k1)), __dmul_rn(src[ly][lx + 2], k0));
-        tmp[ly][lx] = v;
-    }
-    __syncthreads();
+    const long long* img = acc + (size_t)(first_acc + win) * H * W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sx = blur_strips_x(W), strip = blockIdx.x * BLUR_WARPS + warp;
     double sq = 0.0;
-    const double scale = OUT64 ? (scale_ptr ? scale_ptr[2 * slot + 1] : 1.0) : 1.0;
-    for (int i = tid; i < TILE_H * TILE_W; i += BLUR_THREADS) {
-        int ly = i / TILE_W, lx = i % TILE_W;
-        int gy = y0 + ly, gx = x0 + lx;
-        if (gy < H && gx < W) {
-            // cv::SymmColumnFilter order: centre, then k*(up+down)
-            double v = __dadd_rn(__dmul_rn(k1, tmp[ly + 1][lx]), __dmul_rn(k0, __dadd_rn(tmp[ly][lx], tmp[ly + 2][lx])));
-            if (OUT64) {
-                out64[(size_t)win * H * W + (size_t)gy * W + gx] = v * scale;
-            } else {
-                surf2Dwrite((float)v, surfs[slot], gx * (int)sizeof(float), gy);
-                sq += v * v;
+    if (strip < sx * blur_strips_y(H)) {
+        const int x = (strip % sx) * BLUR_COLS + lane - 1;          // this lane's column; lanes 0 and 31 are halo columns
+        const int y0 = (strip / sx) * BLUR_ROWS, y1 = min(y0 + BLUR_ROWS, H);
+        const int xs = reflect101(min(max(x, -1), W), W);           // source column (reflected at the border, clamped for idle lanes)
+        const bool out_col = lane >= 1 && lane <= BLUR_COLS && x < W;
+        const double scale = OUT64 ? (scale_ptr ? scale_ptr[2 * slot + 1] : 1.0) : 1.0;
+        cudaSurfaceObject_t surf = 0;
+        if (!OUT64) surf = surfs[slot];
+        double up = 0.0, mid = 0.0;  // row-filtered values of rows y - 2 and y - 1
+        for (int y = y0 - 1; y <= y1; ++y) {
+            const int ys = reflect101(min(y, H), H);                // warp-uniform
+            const double c = (double)__ldg(img + (size_t)ys * W + xs) * (1.0 / kQ);
+            const double l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
+            // row pass, generic cv::RowFilter order: left, centre, right
+            const double down = __dadd_rn(__dadd_rn(__dmul_rn(l, k0), __dmul_rn(c, k1)), __dmul_rn(r, k0));
+            if (y > y0 && out_col) {
+                // cv::SymmColumnFilter order: centre, then k*(up+down); the value of output row y - 1
+                const double v = __dadd_rn(__dmul_rn(k1, mid), __dmul_rn(k0, __dadd_rn(up, down)));
+                if (OUT64) {
+                    out64[(size_t)win * H * W + (size_t)(y - 1) * W + x] = v * scale;
+                } else {
+                    surf2Dwrite((float)v, surf, x * (int)sizeof(float), y - 1);
+                    sq += v * v;
+                }
             }
+            up = mid;
+            mid = down;
         }
     }
     if constexpr (!OUT64) {
-        // fused sum of squares (cv::norm L2, EventFrame.cpp:360-364): warp -> CTA -> ordered final pass
+        // fused sum of squares: warp -> CTA -> ordered final pass over the CTAs of the window
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if ((tid & 31) == 0) wsum[tid >> 5] = sq;
+        if (lane == 0) wsum[warp] = sq;
         __syncthreads();
-        const int ntiles = gridDim.x * gridDim.y;
-        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        const int nctas = gridDim.x;
         if (tid == 0) {
             double s = 0.0;
-            for (int w = 0; w < BLUR_THREADS / 32; ++w) s += wsum[w];
-            partials[(size_t)win * ntiles + tile] = s;
+            for (int w = 0; w < BLUR_WARPS; ++w) s += wsum[w];
+            partials[(size_t)win * nctas + blockIdx.x] = s;
             __threadfence();
             unsigned t = atomicAdd(&tickets[win], 1u);
-            is_last = (t == (unsigned)ntiles - 1);
+            is_last = (t == (unsigned)nctas - 1);
         }
         __syncthreads();
         if (is_last && tid < 32) {
             __threadfence();
-            const volatile double* p = partials + (size_t)win * ntiles;
+            const volatile double* p = partials + (size_t)win * nctas;
             double s = 0.0;
-            for (int i = tid; i < ntiles; i += 32) s += p[i];
+            for (int i = tid; i < nctas; i += 32) s += p[i];
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (tid == 0) {
                 double nrm = sqrt(s);
@@ -218,34 +225,44 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
             prev = e;
         }
     }
-    EDS_CUDA(ctx, cudaMemsetAsync(fr->acc + (size_t)first_slot * npix, 0, sizeof(long long) * npix * count, bs));
-    {
-        int threads = 256;
-        int bx = (E + threads - 1) / threads;
-        bx = max(1, min(bx, 4 * ctx->num_sms));
-        dim3 grid(bx, count);
-        scatter_events_kernel<<<grid, threads, 0, bs>>>(x_dev, y_dev, pol_dev, E, H, W, lut ? lut->mapx : nullptr,
-                                                                  lut ? lut->mapy : nullptr, mode, use_exp,
-                                                                  fr->acc + (size_t)first_slot * npix);
-        ctx->launches++;
-        EDS_CUDA(ctx, cudaGetLastError());
+    double k0 = 0.0, k1 = 1.0;
+    if (sigma > 0.f) {  // cv::getGaussianKernel(3, sigma), Utils.cpp:113-119
+        double s = (double)sigma;
+        k0 = exp(-1.0 / (2.0 * s * s));
+        double sum = k0 + 1.0 + k0;
+        k0 /= sum;
+        k1 = 1.0 / sum;
     }
-    {
-        double k0 = 0.0, k1 = 1.0;
-        if (sigma > 0.f) {  // cv::getGaussianKernel(3, sigma), Utils.cpp:113-119
-            double s = (double)sigma;
-            k0 = exp(-1.0 / (2.0 * s * s));
-            double sum = k0 + 1.0 + k0;
-            k0 /= sum;
-            k1 = 1.0 / sum;
+    fr->k0 = k0;
+    fr->k1 = k1;
+    const bool ring = fr->acc_slots < fr->capacity;
+    for (int c0 = 0; c0 < count; c0 += fr->acc_slots) {
+        // one chunk of windows: clear -> scatter -> blur on accumulators that stay in L2 (see frames.cuh)
+        const int n = std::min(fr->acc_slots, count - c0);
+        const int acc0 = ring ? 0 : first_slot + c0;
+        if (ring)
+            for (int s = 0; s < fr->capacity; ++s)
+                if (fr->slot_acc[s] >= 0 && fr->slot_acc[s] < n) fr->slot_acc[s] = -1;
+        for (int w = 0; w < n; ++w) fr->slot_acc[first_slot + c0 + w] = acc0 + w;
+        EDS_CUDA(ctx, cudaMemsetAsync(fr->acc + (size_t)acc0 * npix, 0, sizeof(long long) * npix * n, bs));
+        {
+            int threads = 256;
+            int bx = (E + threads - 1) / threads;
+            bx = max(1, min(bx, 4 * ctx->num_sms));
+            dim3 grid(bx, n);
+            const size_t eoff = (size_t)c0 * E;
+            scatter_events_kernel<<<grid, threads, 0, bs>>>(x_dev + eoff, y_dev + eoff, pol_dev + eoff, E, H, W, lut ? lut->mapx : nullptr,
+                                                            lut ? lut->mapy : nullptr, mode, use_exp, fr->acc + (size_t)acc0 * npix);
+            ctx->launches++;
+            EDS_CUDA(ctx, cudaGetLastError());
         }
-        dim3 grid((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, count);
-        blur_norm_kernel<false><<<grid, BLUR_THREADS, 0, bs>>>(fr->acc, H, W, k0, k1, fr->surf_dev, fr->partials, fr->tickets,
-                                                                         fr->norms, first_slot, nullptr, nullptr);
-        ctx->launches++;
-        EDS_CUDA(ctx, cudaGetLastError());
-        fr->k0 = k0;
-        fr->k1 = k1;
+        {
+            dim3 grid(blur_ctas(H, W), 1, n);
+            blur_norm_kernel<false><<<grid, BLUR_THREADS, 0, bs>>>(fr->acc, H, W, k0, k1, fr->surf_dev, fr->partials, fr->tickets, fr->norms,
+                                                                    first_slot + c0, acc0, nullptr, nullptr);
+            ctx->launches++;
+            EDS_CUDA(ctx, cudaGetLastError());
+        }
     }
     {   // readers of these slots wait for this build
         cudaEvent_t e = fr->built_pool[fr->built_next];
@@ -260,12 +277,13 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
 edsgpu_status read_image64(edsgpu_ctx* ctx, const edsgpu_frames* fr, int slot, bool normalised, double* host_out) {
     const int H = fr->H, W = fr->W;
     const size_t npix = (size_t)H * W;
+    EDS_REQUIRE(ctx, fr->slot_acc[slot] >= 0, "frames_read: the accumulator of this slot was never filled or has been recycled (large sets of slots share a ring of accumulators)");
     edsgpu_status st = edsgpu_ensure_scratch(ctx, npix * sizeof(double));
     if (st == EDSGPU_OK) st = edsgpu_frames_wait_built(fr, slot, 1, ctx->stream);
     if (st != EDSGPU_OK) return st;
-    dim3 grid((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, 1);
+    dim3 grid(blur_ctas(H, W), 1, 1);
     blur_norm_kernel<true><<<grid, BLUR_THREADS, 0, ctx->stream>>>(fr->acc, H, W, fr->k0, fr->k1, nullptr, nullptr, nullptr, nullptr, slot,
-                                                                    (double*)ctx->scratch, normalised ? fr->norms : nullptr);
+                                                                    fr->slot_acc[slot], (double*)ctx->scratch, normalised ? fr->norms : nullptr);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
     EDS_CUDA(ctx, cudaMemcpyAsync(host_out, ctx->scratch, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -334,8 +352,20 @@ edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int c
     edsgpu_frames* fr = new edsgpu_frames();
     fr->ctx = ctx; fr->H = height; fr->W = width; fr->capacity = capacity;
     const size_t npix = (size_t)height * width;
-    const int ntiles = ((width + TILE_W - 1) / TILE_W) * ((height + TILE_H - 1) / TILE_H);
-    cudaError_t e = cudaMalloc(&fr->acc, sizeof(long long) * npix * capacity);
+    const int ntiles = blur_ctas(height, width);
+    {
+        // one accumulator per slot while they all fit the budget, otherwise a ring that stays resident in L2
+        // EDSGPU_ACC_RING_MB: size of the ring; 0 (the default) = always one accumulator per slot.  Measured on the 64-window
+        // 640x480 benchmark step: the ring keeps the accumulators out of HBM but its chunked launches cost more than they save
+        // (0.750 ms per step with a 32 MB ring against 0.733 ms without).
+        size_t ring_mb = 0;
+        if (const char* e = getenv("EDSGPU_ACC_RING_MB")) ring_mb = (size_t)std::max(0, atoi(e));
+        const size_t budget = (size_t)48 << 20, per = sizeof(long long) * npix;
+        fr->acc_slots = ((size_t)capacity * per <= budget || ring_mb == 0) ? capacity
+                                                                            : (int)std::max<size_t>(1, std::min<size_t>(capacity, (ring_mb << 20) / per));
+        fr->slot_acc.assign(capacity, -1);
+    }
+    cudaError_t e = cudaMalloc(&fr->acc, sizeof(long long) * npix * fr->acc_slots);
     fr->arrays = new cudaArray_t[capacity]();
     fr->tex = new cudaTextureObject_t[capacity]();
     fr->surf = new cudaSurfaceObject_t[capacity]();
@@ -367,7 +397,7 @@ edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int c
     if (e == cudaSuccess) e = cudaMalloc(&fr->norms, sizeof(double) * 2 * capacity);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->tickets, 0, sizeof(unsigned) * capacity, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->norms, 0, sizeof(double) * 2 * capacity, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(fr->acc, 0, sizeof(long long) * npix * capacity, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fr->acc, 0, sizeof(long long) * npix * fr->acc_slots, ctx->stream);
     fr->slot_built.assign(capacity, nullptr);
     fr->slot_read.assign(capacity, nullptr);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&fr->build_stream, cudaStreamNonBlocking);
@@ -549,9 +579,10 @@ edsgpu_status edsgpu_frames_read_accumulator(edsgpu_ctx* ctx, const edsgpu_frame
     EDS_REQUIRE(ctx, frames && acc_out && slot >= 0 && slot < frames->capacity, "frames_read_accumulator: bad arguments");
     DeviceGuard g(ctx->device);
     const size_t npix = (size_t)frames->H * frames->W;
+    EDS_REQUIRE(ctx, frames->slot_acc[slot] >= 0, "frames_read_accumulator: the accumulator of this slot was never filled or has been recycled (large sets of slots share a ring of accumulators)");
     edsgpu_status st = edsgpu_frames_wait_built(frames, slot, 1, ctx->stream);
     if (st != EDSGPU_OK) return st;
-    EDS_CUDA(ctx, cudaMemcpyAsync(acc_out, frames->acc + (size_t)slot * npix, sizeof(int64_t) * npix, cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaMemcpyAsync(acc_out, frames->acc + (size_t)frames->slot_acc[slot] * npix, sizeof(int64_t) * npix, cudaMemcpyDeviceToHost, ctx->stream));
     st = edsgpu_frames_mark_read(frames, slot, 1, ctx->stream);
     if (st != EDSGPU_OK) return st;
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

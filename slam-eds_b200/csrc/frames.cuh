@@ -16,7 +16,13 @@ struct edsgpu_frames {
     edsgpu_ctx* ctx = nullptr;
     uint64_t uid = edsgpu_next_uid();
     int H = 0, W = 0, capacity = 0;
-    long long* acc = nullptr;     // [capacity][H*W] fixed-point (2^-40) brightness increments
+    // Fixed-point (2^-40) brightness increments, [acc_slots][H*W].  An accumulator only lives from the scatter of a window to
+    // its blur, so a large set of slots shares a RING of accumulators sized to stay resident in L2 (acc_slots < capacity): a
+    // build runs in chunks of acc_slots windows, clear -> scatter -> blur, and the 8 bytes per pixel never travel to HBM.
+    // Small sets keep one accumulator per slot (acc_slots == capacity), which is what the read-back entry points need.
+    long long* acc = nullptr;
+    int acc_slots = 0;
+    std::vector<int> slot_acc;    // [capacity] accumulator that still holds the slot's window, -1 = recycled
     // blurred, un-normalised fp32 frames: one block-linear CUDA array per slot, written through a
     // surface by the blur kernel and sampled by the tracker with 2x2 texture gathers (clamp-to-edge
     // addressing = the clamped ceres::Grid2D)

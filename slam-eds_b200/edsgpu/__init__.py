@@ -34,7 +34,7 @@ SYMBOLS = [
     "edsgpu_tracker_evaluate",
     "edsgpu_ba_create", "edsgpu_ba_destroy", "edsgpu_ba_set_residuals", "edsgpu_ba_set_points", "edsgpu_ba_set_frames",
     "edsgpu_ba_top_accumulate", "edsgpu_ba_top_stitch", "edsgpu_ba_sc_accumulate", "edsgpu_ba_sc_stitch", "edsgpu_ba_get_jpjd",
-    "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_get_residuals",
+    "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_linearize_accumulate", "edsgpu_ba_top_read", "edsgpu_ba_get_residuals",
     "edsgpu_ba_resubstitute", "edsgpu_ba_fix_linearization", "edsgpu_ba_calc_l_energy",
     "edsgpu_coarse_create", "edsgpu_coarse_destroy", "edsgpu_coarse_set_level", "edsgpu_coarse_set_reference",
     "edsgpu_coarse_set_new_frame", "edsgpu_coarse_calc_res_gs", "edsgpu_coarse_track",
@@ -421,6 +421,18 @@ class BaWindow:
                                                         _ptr(st, C.c_int32), _ptr(en, C.c_float)))
         return (st, en) if want_outputs else None
 
+    def linearize_accumulate(self, state_in=None, linearized=None, res_toZero=None, write_records=False, want_outputs=True):
+        """linearize fused with top_accumulate(0): one kernel, the 304-byte records of the residuals nothing reads later are
+        not written.  -> (state_new, energy_new) or None; read the accumulation with top_result(0)."""
+        u8 = lambda a: np.ascontiguousarray(a, np.uint8) if a is not None else None  # noqa: E731
+        si, li = u8(state_in), u8(linearized)
+        rtz = np.ascontiguousarray(res_toZero, np.float32) if res_toZero is not None else None
+        st = np.zeros(self.R, np.int32) if want_outputs else None
+        en = np.zeros(self.R, np.float32) if want_outputs else None
+        self.ctx.check(self.ctx.lib.edsgpu_ba_linearize_accumulate(self.h, _ptr(si, C.c_uint8), _ptr(li, C.c_uint8), _ptr(rtz, C.c_float),
+                                                                   C.c_int(1 if write_records else 0), _ptr(st, C.c_int32), _ptr(en, C.c_float)))
+        return (st, en) if want_outputs else None
+
     # ---- after the solve (EnergyFunctional.cpp:263-415, EnergyFunctionalStructs.cpp:87-113) ----
     def resubstitute(self, x):
         """resubstituteF_MT: per-point step from the solved update x (4 + 8F)."""
@@ -470,6 +482,15 @@ class BaWindow:
         nres = C.c_int64(0)
         self.ctx.check(self.ctx.lib.edsgpu_ba_top_accumulate(self.h, C.c_int(mode), _ptr(acc, C.c_double), _ptr(Hdd, C.c_float),
                                                              _ptr(bd, C.c_float), _ptr(Hcd, C.c_float), C.byref(nres)))
+        return dict(acc=acc, Hdd=Hdd, bd=bd, Hcd=Hcd, nres=nres.value)
+
+    def top_result(self, which):
+        """the accumulation of side `which` (0 active, 1 linearized) that is already on the device"""
+        acc = np.zeros((self.F * self.F, 13, 13))
+        Hdd, bd, Hcd = np.zeros(self.P, np.float32), np.zeros(self.P, np.float32), np.zeros((self.P, 4), np.float32)
+        nres = C.c_int64(0)
+        self.ctx.check(self.ctx.lib.edsgpu_ba_top_read(self.h, C.c_int(which), _ptr(acc, C.c_double), _ptr(Hdd, C.c_float), _ptr(bd, C.c_float),
+                                                       _ptr(Hcd, C.c_float), C.byref(nres)))
         return dict(acc=acc, Hdd=Hdd, bd=bd, Hcd=Hcd, nres=nres.value)
 
     def top_stitch(self, which, use_prior=False, cPrior=None, frame_prior=None, frame_delta_prior=None):

@@ -202,6 +202,56 @@ def test_device_linearize_is_bit_exact_and_feeds_the_accumulators(gpu_ctx, cfg):
     w.close(); w2.close()
 
 
+@pytest.mark.parametrize("cfg", ["small", "config4"])
+def test_fused_linearize_accumulate_is_bit_identical_to_the_two_calls(gpu_ctx, cfg):
+    """edsgpu_ba_linearize_accumulate (linearize + addPoint<0> in one kernel): every output equals the
+    output of linearize followed by top_accumulate(0) bit for bit; without write_records only the linearized residuals'
+    records reach memory, and the rest of the chain (mode 1, Schur complement) gives the same result."""
+    pb = SB.make_ba_problem(F=4, points_per_frame=250, H=120, W=160) if cfg == "small" else SB.make_ba_problem()
+    linearized = (pb["flags"] >> 1) & 1
+    rtz = O.ba_fix_linearization(pb["F"], pb["recs"], pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["deltaF"], pb["adHTdeltaF"],
+                                 pb["cDeltaF"])
+
+    def window():
+        w = edsgpu.BaWindow(gpu_ctx, pb["F"], pb["host_idx"], pb["target_idx"], pb["res_begin"])
+        w.set_images(pb["dI"])
+        w.set_linearize_inputs(pb["precalc"], pb["calib"], pb["frame_energy_th"], pb["pu"], pb["pv"], pb["idepth"], pb["idepth"],
+                               pb["color"], pb["weights"])
+        w.set_points(pb["deltaF"], pb["priorF"])
+        w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+        return w
+
+    a, b = window(), window()
+    sa, ea = a.linearize(linearized=linearized, res_toZero=rtz)
+    ta = a.top_accumulate(0)
+    for write_all in (True, False):
+        sb, eb = b.linearize_accumulate(linearized=linearized, res_toZero=rtz, write_records=write_all)
+        tb = b.top_result(0)
+        assert np.array_equal(sa, sb) and np.array_equal(ea, eb)
+        for k in ("acc", "Hdd", "bd", "Hcd"):
+            assert np.array_equal(ta[k], tb[k]), k
+        assert ta["nres"] == tb["nres"] and ta["nres"] > 0
+        assert np.array_equal(a.jpjd(), b.jpjd())
+        ra, fa = a.get_residuals()
+        rb, fb = b.get_residuals()
+        assert np.array_equal(fa, fb)
+        if write_all:
+            assert np.array_equal(ra, rb)
+        else:
+            assert np.array_equal(ra[linearized == 1], rb[linearized == 1])
+        # the rest of the chain
+        la, lb = a.top_accumulate(1), b.top_accumulate(1)
+        for k in ("acc", "Hdd", "bd", "Hcd"):
+            assert np.array_equal(la[k], lb[k]), k
+        ca, cb = a.sc_accumulate(True), b.sc_accumulate(True)
+        for k in ca:
+            assert np.array_equal(ca[k], cb[k]), k
+        if write_all:  # a fresh window for the sparse-record pass: no record left over from this one
+            b.close()
+            b = window()
+    a.close(); b.close()
+
+
 def test_back_substitution_energy_and_fix_linearization(solved):
     """The steps right after the solve on data that is still on the device:
     resubstituteF_MT, calcLEnergyF_MT, fixLinearizationF against the CPU oracle."""
