@@ -62,6 +62,11 @@ void edsgpu_lut_destroy(edsgpu_lut* lut);
 
 /* capacity event frames of height x width, resident on the device for the tracker. */
 edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int capacity, edsgpu_frames** out);
+/* The same with the pyramid of EventFrame::create (EventFrame.cpp:342-357, num_levels of the reference's signature):
+ * level 0 is the event frame, level i >= 1 is cv::dilate + cv::erode of level 0 with a (2i+1) x (2i+1) rectangle (same
+ * resolution), every level with its own L2 norm (:360-364).  Every edsgpu_event_frame_create* call then builds all levels
+ * of the slots it fills.  num_levels in [1,5]. */
+edsgpu_status edsgpu_frames_create_pyramid(edsgpu_ctx* ctx, int height, int width, int capacity, int num_levels, edsgpu_frames** out);
 void edsgpu_frames_destroy(edsgpu_frames* frames);
 
 /* EventFrame::create (EventFrame.cpp:302-389), pyramid level 0, out_scale 1:
@@ -101,6 +106,9 @@ edsgpu_status edsgpu_event_frame_create_batch_dev(edsgpu_ctx* ctx, edsgpu_frames
  * fixed-point accumulator (value * 2^40) before the blur. */
 edsgpu_status edsgpu_frames_read(edsgpu_ctx* ctx, const edsgpu_frames* frames, int slot, double* image_out /*H*W*/,
                                  double* norm_out);
+/* frame[level] as stored on the device (fp32, un-normalised, widened to double) and norm[level]; either may be NULL. */
+edsgpu_status edsgpu_frames_read_level(edsgpu_ctx* ctx, const edsgpu_frames* frames, int slot, int level, double* image_out /*H*W*/,
+                                       double* norm_out);
 edsgpu_status edsgpu_frames_read_accumulator(edsgpu_ctx* ctx, const edsgpu_frames* frames, int slot, int64_t* acc_out /*H*W*/);
 #define EDSGPU_ACC_FRACTION_BITS 40
 
@@ -162,6 +170,15 @@ edsgpu_status edsgpu_tracker_get_state(edsgpu_tracker* tracker, double px[3], do
 edsgpu_status edsgpu_tracker_optimize(edsgpu_tracker* tracker, const edsgpu_keyframe* kf, const edsgpu_frames* frames,
                                       int slot, double px[3], double qx_xyzw[4], double vx[6], double* residuals_out,
                                       double* next_loss_param_out, edsgpu_tracker_info* info);
+/* Tracker::optimize(id, &event_frame[id], ...) (Tracker.cpp:85-241) at pyramid level id of frames made with
+ * edsgpu_frames_create_pyramid: the solve samples event_frame[level] (with norm[level]) and runs at most
+ * config.options.max_num_iterations[level] iterations (Tracker.cpp:139), set per tracker with
+ * edsgpu_tracker_set_level_iterations (without it every level uses edsgpu_tracker_config::max_iterations).
+ * The reference's caller goes coarse to fine: level num_levels-1 down to 0, each solve warm-started by the last. */
+edsgpu_status edsgpu_tracker_set_level_iterations(edsgpu_tracker* tracker, const int* max_num_iterations, int num_levels);
+edsgpu_status edsgpu_tracker_optimize_level(edsgpu_tracker* tracker, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot,
+                                            int level, double px[3], double qx_xyzw[4], double vx[6], double* residuals_out,
+                                            double* next_loss_param_out, edsgpu_tracker_info* info);
 
 /* `count` independent trackers (sequences), tracker i against keyframe i and frame slot
  * first_slot+i, in one launch.  Asynchronous; read results with edsgpu_tracker_get_state
@@ -174,6 +191,9 @@ edsgpu_status edsgpu_trackers_optimize_batch(edsgpu_ctx* ctx, edsgpu_tracker* co
 typedef struct edsgpu_batch edsgpu_batch;
 edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes,
                                   int count, const edsgpu_frames* frames, int first_slot, edsgpu_batch** out);
+/* the same against pyramid level `level` of the frames (see edsgpu_tracker_optimize_level) */
+edsgpu_status edsgpu_batch_create_level(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes,
+                                        int count, const edsgpu_frames* frames, int first_slot, int level, edsgpu_batch** out);
 void edsgpu_batch_destroy(edsgpu_batch* batch);
 edsgpu_status edsgpu_batch_optimize(edsgpu_batch* batch);
 edsgpu_status edsgpu_batch_count(const edsgpu_batch* batch, int* count); /* problems of the batch */

@@ -117,6 +117,30 @@ def event_frame(x, y, pol, ts_us, H, W, mapx=None, mapy=None, method="bilinear",
     return dict(img=img, frame=frame, norm=norm.value, time=t.value, delta=d.value, status=rc)
 
 
+def event_frame_levels(img, num_levels):
+    """Pyramid of EventFrame::create (reference src/tracking/EventFrame.cpp:342-364) from the level-0 image `img`
+    (un-normalised): frame[0] = img, frame[i] = cv::dilate(img, rect(2i+1)) + cv::erode(img, rect(2i+1)) at the same
+    resolution, norm[i] = cv::norm(frame[i]) (L2).  The default border of cv::dilate / cv::erode keeps pixels outside
+    the image out of the maximum / minimum: windows are clipped.  Arithmetic in the dtype of `img` (the reference: double).
+    Pinned against cv2.dilate / cv2.erode in tests/test_oracle_tracking.py.  -> (frames, norms)"""
+    img = np.asarray(img)
+    H, W = img.shape
+    frames, norms = [img.copy()], []
+    for i in range(1, num_levels):
+        hi = np.pad(img, i, constant_values=-np.inf)
+        lo = np.pad(img, i, constant_values=np.inf)
+        mx = np.full_like(img, -np.inf)
+        mn = np.full_like(img, np.inf)
+        for dy in range(2 * i + 1):
+            for dx in range(2 * i + 1):
+                mx = np.maximum(mx, hi[dy:dy + H, dx:dx + W])
+                mn = np.minimum(mn, lo[dy:dy + H, dx:dx + W])
+        frames.append(mx + mn)
+    for f in frames:
+        norms.append(float(np.sqrt(np.sum(np.asarray(f, np.float64) ** 2))))
+    return frames, norms
+
+
 def bicubic(grid, rows, cols):
     grid = _f64(grid)
     rows, cols = _f64(rows), _f64(cols)

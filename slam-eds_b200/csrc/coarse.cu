@@ -38,6 +38,7 @@ struct CoarseArgs {
 };
 
 // one CTA's share of an evaluation: points blockIdx.x * blockDim.x + threadIdx.x (+ grid stride) -> partial[CT_NPART]
+template <int THREADS>
 __device__ __forceinline__ void coarse_sweep(const CoarseArgs& a, double (*red)[CT_NPART], double* __restrict__ partial) {
     float acc[CT_NACC];
 #pragma unroll
@@ -135,14 +136,14 @@ __device__ __forceinline__ void coarse_sweep(const CoarseArgs& a, double (*red)[
     __syncthreads();
     if (threadIdx.x < CT_NPART) {
         double s = 0.0;
-        for (int w = 0; w < CT_THREADS / 32; ++w) s += red[w][threadIdx.x];
+        for (int w = 0; w < THREADS / 32; ++w) s += red[w][threadIdx.x];
         partial[threadIdx.x] = s;
     }
 }
 
 __global__ void __launch_bounds__(CT_THREADS) coarse_res_gs_kernel(CoarseArgs a) {
     __shared__ double red[CT_THREADS / 32][CT_NPART];
-    coarse_sweep(a, red, a.partials + (size_t)blockIdx.x * CT_NPART);
+    coarse_sweep<CT_THREADS>(a, red, a.partials + (size_t)blockIdx.x * CT_NPART);
 }
 
 __global__ void coarse_finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
@@ -369,21 +370,39 @@ __host__ __device__ void se3_left_update(const double* inc6, double* R, double* 
 
 // x = A^-1 rhs, A symmetric positive definite 8x8 (LDL^T; the reference calls Eigen's ldlt().solve)
 __host__ __device__ void solve8(const double* A, const double* rhs, double* x) {
+    // fully unrolled: on the device every index is a compile-time constant and L, D, y live in registers
     double L[64] = {0}, D[8], y[8];
+#pragma unroll
     for (int j = 0; j < 8; ++j) {
         double d = A[8 * j + j];
+#pragma unroll
         for (int k = 0; k < j; ++k) d -= L[8 * j + k] * L[8 * j + k] * D[k];
         D[j] = d;
         L[8 * j + j] = 1.0;
+#pragma unroll
         for (int i = j + 1; i < 8; ++i) {
             double v = A[8 * i + j];
+#pragma unroll
             for (int k = 0; k < j; ++k) v -= L[8 * i + k] * L[8 * j + k] * D[k];
             L[8 * i + j] = v / d;
         }
     }
-    for (int i = 0; i < 8; ++i) { double v = rhs[i]; for (int k = 0; k < i; ++k) v -= L[8 * i + k] * y[k]; y[i] = v; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double v = rhs[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) v -= L[8 * i + k] * y[k];
+        y[i] = v;
+    }
+#pragma unroll
     for (int i = 0; i < 8; ++i) y[i] /= D[i];
-    for (int i = 7; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 8; ++k) v -= L[8 * k + i] * x[k]; x[i] = v; }
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 8; ++k) v -= L[8 * k + i] * x[k];
+        x[i] = v;
+    }
 }
 
 
@@ -393,7 +412,7 @@ __host__ __device__ void solve8(const double* A, const double* rhs, double* x) {
 // thread 0 advances the (identical) state machine: Levenberg damping, 8x8 LDL^T, SE3::exp update, accept / reject,
 // cutoff repeat, level change.  No host round trip inside the loop (it cost ~40 us per evaluation).
 // ------------------------------------------------------------------------------------------
-constexpr int CT_MAX_LEVELS = 5;  // PYR_LEVELS the loop can visit (coarsest_lvl < 5, CoarseTracker.cpp:540)
+constexpr int CT_MAX_LEVELS = 5, CT_TRACK_THREADS = 512;  // wide CTAs: fewer of them at the grid barrier and in the ordered sum  // PYR_LEVELS the loop can visit (coarsest_lvl < 5, CoarseTracker.cpp:540)
 
 struct LevelDev {
     int w, h, n;
@@ -426,6 +445,7 @@ struct TrackCtl {  // shared memory; written by thread 0 only
     float lambda, repeat;
     int lvl, iteration, state, haveRepeated, ok, evaluations, done;
     CoarseArgs a;                   // the evaluation every thread sweeps next
+    double out[8];                  // lastResiduals (5), lastFlowIndicators (3): every CTA keeps its own copy, CTA 0 writes them out
 };
 enum { TS_FIRST = 0, TS_ITER = 1 };
 
@@ -506,7 +526,7 @@ __host__ __device__ void coarse_outputs(const double* v, double* rs, double* H, 
 }
 
 // thread 0: consume the evaluation that has just been reduced into `sums`, decide what happens next (CoarseTracker.cpp:540-701)
-__device__ void track_advance(TrackCtl& c, const TrackArgs& A, TrackIO& io, const double* sums) {
+__device__ void track_advance(TrackCtl& c, const TrackArgs& A, const TrackIO& io, double* out, const double* sums) {
     const int maxIterations[5] = {10, 20, 100, 100, 100};
     const float lambdaExtrapolationLimit = 0.001f;
     double rs[6], Hn[64], bn[8];
@@ -570,9 +590,9 @@ __device__ void track_advance(TrackCtl& c, const TrackArgs& A, TrackIO& io, cons
             return;
         }
         // the level is finished
-        io.last_residuals[c.lvl] = sqrtf((float)(c.resOld[0] / c.resOld[1]));
-        for (int i = 0; i < 3; ++i) io.last_flow[i] = c.resOld[2 + i];
-        if (io.has_min_res && io.last_residuals[c.lvl] > 1.5 * io.min_res[c.lvl]) c.ok = 0;
+        out[c.lvl] = sqrtf((float)(c.resOld[0] / c.resOld[1]));
+        for (int i = 0; i < 3; ++i) out[5 + i] = c.resOld[2 + i];
+        if (io.has_min_res && out[c.lvl] > 1.5 * io.min_res[c.lvl]) c.ok = 0;
         if (c.ok && c.repeat > 1 && !c.haveRepeated) { c.lvl++; c.haveRepeated = 1; }
         c.lvl--;
         if (c.lvl < 0 || !c.ok) { c.done = 1; return; }
@@ -583,45 +603,49 @@ __device__ void track_advance(TrackCtl& c, const TrackArgs& A, TrackIO& io, cons
     }
 }
 
-__global__ void __launch_bounds__(CT_THREADS) coarse_track_kernel(TrackArgs A) {
-    __shared__ double red[CT_THREADS / 32][CT_NPART];
+__global__ void __launch_bounds__(CT_TRACK_THREADS) coarse_track_kernel(TrackArgs A) {
+    __shared__ double red[CT_TRACK_THREADS / 32][CT_NPART];
+    __shared__ double quarter[4][CT_NPART];
     __shared__ double sums[CT_NPART];
     __shared__ TrackCtl c;
-    TrackIO& io = *A.io;
+    TrackIO& io = *A.io;  // inputs are only read inside the loop; CTA 0 writes the outputs once, at the end
     if (threadIdx.x == 0) {
-        // every CTA runs the same state machine on the same numbers; only CTA 0 writes results
+        // every CTA runs the same state machine on the same numbers
         for (int i = 0; i < 9; ++i) c.Rc[i] = io.R[i];
         for (int i = 0; i < 3; ++i) c.tc[i] = io.t[i];
         c.affc[0] = io.aff[0]; c.affc[1] = io.aff[1];
         c.lvl = io.coarsest; c.haveRepeated = 0; c.ok = 1; c.evaluations = 0; c.done = 0;
         c.repeat = 1; c.state = TS_FIRST; c.lambda = 0.01f; c.iteration = 0;
+        for (int i = 0; i < 5; ++i) c.out[i] = io.last_residuals[i];
+        for (int i = 0; i < 3; ++i) c.out[5 + i] = io.last_flow[i];
         track_request(c, A, io, c.lvl, c.Rc, c.tc, c.affc);
     }
     __syncthreads();
     for (unsigned k = 0;; ++k) {
         double* buf = A.partials + (size_t)(k & 1u) * gridDim.x * CT_NPART;
-        coarse_sweep(c.a, red, buf + (size_t)blockIdx.x * CT_NPART);
+        coarse_sweep<CT_TRACK_THREADS>(c.a, red, buf + (size_t)blockIdx.x * CT_NPART);
         track_grid_barrier(A.bar);
-        if (threadIdx.x < CT_NPART) {
+        // ordered sum over the CTAs: four threads per entry take a quarter of them each (fixed partition), then the quarters in order
+        if (threadIdx.x < 4 * CT_NPART) {
+            const int e = threadIdx.x % CT_NPART, q = threadIdx.x / CT_NPART;
+            const unsigned per = (gridDim.x + 3u) / 4u, b0 = q * per, b1 = min(gridDim.x, b0 + per);
             double s = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(buf + (size_t)b * CT_NPART + threadIdx.x);
-            sums[threadIdx.x] = s;
+            for (unsigned b = b0; b < b1; ++b) s += __ldcg(buf + (size_t)b * CT_NPART + e);
+            quarter[q][e] = s;
         }
         __syncthreads();
+        if (threadIdx.x < CT_NPART) sums[threadIdx.x] = ((quarter[0][threadIdx.x] + quarter[1][threadIdx.x]) + quarter[2][threadIdx.x]) + quarter[3][threadIdx.x];
+        __syncthreads();
         if (threadIdx.x == 0) {
-            if (blockIdx.x == 0) {
-                track_advance(c, A, io, sums);
-            } else {
-                // the other CTAs must not write the shared outputs: they advance a private copy of the bookkeeping
-                TrackIO scratch = io;
-                track_advance(c, A, scratch, sums);
-            }
+            track_advance(c, A, io, c.out, sums);
         }
         __syncthreads();
         if (c.done) break;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         io.evaluations = c.evaluations;
+        for (int i = 0; i < 5; ++i) io.last_residuals[i] = c.out[i];
+        for (int i = 0; i < 3; ++i) io.last_flow[i] = c.out[5 + i];
         io.status = 0;
         if (!c.ok) io.status = 1;
         else {
@@ -674,10 +698,10 @@ edsgpu_status edsgpu_coarse_track(edsgpu_coarse* c, int coarsest_lvl, double R[9
     A.io = (TrackIO*)c->track_io;
     A.partials = c->partials;
     A.bar = c->track_bar;
-    // one CTA per 256 points of the largest level, at most one per SM (cooperative launch: all resident)
-    const int grid = std::max(1, std::min((nmax + CT_THREADS - 1) / CT_THREADS, std::min(ctx->num_sms, c->max_grid / 2)));
+    // one CTA per 512 points of the largest level, at most one per SM (cooperative launch: all resident)
+    const int grid = std::max(1, std::min((nmax + CT_TRACK_THREADS - 1) / CT_TRACK_THREADS, std::min(ctx->num_sms, c->max_grid / 2)));
     void* argv[] = {(void*)&A};
-    EDS_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)coarse_track_kernel, dim3(grid), dim3(CT_THREADS), argv, 0, ctx->stream));
+    EDS_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)coarse_track_kernel, dim3(grid), dim3(CT_TRACK_THREADS), argv, 0, ctx->stream));
     ctx->launches++;
     EDS_CUDA(ctx, cudaMemcpyAsync(h, c->track_io, sizeof(TrackIO), cudaMemcpyDeviceToHost, ctx->stream));
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

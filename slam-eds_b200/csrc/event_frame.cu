@@ -134,7 +134,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // EventFrame.cpp:360-364).  One thread per column of a strip, walking down the rows: the accumulator is read ONCE per
 // pixel (coalesced 64-bit loads), the row pass takes its neighbours from the adjacent lanes by shuffle, the column pass
 // keeps the last three row-filtered values in registers -- no shared-memory tile, no CTA barrier in the sweep.  fp64 in
-// OpenCV's operation order (explicit mul / add, no FMA contraction): bit-exact against the oracle on exactly
+// OpenCV's operation order (explicit mul / add, no FMA contraction): bit-exact against cv::GaussianBlur (CV_64F) on exactly
 // representable input.
 // OUT64 == false: write the fp32 frame + per-CTA sum of squares, the last CTA of a window publishes norm and 1/norm.
 // OUT64 == true : write out64 = blurred * scale (debug / host read-back path).
@@ -161,24 +161,35 @@ __global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long
         cudaSurfaceObject_t surf = 0;
         if (!OUT64) surf = surfs[slot];
         double up = 0.0, mid = 0.0;  // row-filtered values of rows y - 2 and y - 1
-        for (int y = y0 - 1; y <= y1; ++y) {
-            const int ys = reflect101(min(y, H), H);                // warp-uniform
-            const double c = (double)__ldg(img + (size_t)ys * W + xs) * (1.0 / kQ);
-            const double l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
-            // row pass, generic cv::RowFilter order: left, centre, right
-            const double down = __dadd_rn(__dadd_rn(__dmul_rn(l, k0), __dmul_rn(c, k1)), __dmul_rn(r, k0));
-            if (y > y0 && out_col) {
-                // cv::SymmColumnFilter order: centre, then k*(up+down); the value of output row y - 1
-                const double v = __dadd_rn(__dmul_rn(k1, mid), __dmul_rn(k0, __dadd_rn(up, down)));
-                if (OUT64) {
-                    out64[(size_t)win * H * W + (size_t)(y - 1) * W + x] = v * scale;
-                } else {
-                    surf2Dwrite((float)v, surf, x * (int)sizeof(float), y - 1);
-                    sq += v * v;
-                }
+        constexpr int RB = 8;        // rows in flight: their loads are issued together, ahead of the arithmetic
+        for (int yb = y0 - 1; yb <= y1; yb += RB) {
+            double cs[RB];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                const int ys = reflect101(min(yb + j, min(y1, H)), H);  // warp-uniform; rows past the strip repeat its last one (unused)
+                cs[j] = (double)__ldg(img + (size_t)ys * W + xs);
             }
-            up = mid;
-            mid = down;
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                const int y = yb + j;
+                if (y > y1) break;
+                const double c = cs[j] * (1.0 / kQ);
+                const double l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
+                // row pass, generic cv::RowFilter order: left, centre, right
+                const double down = __dadd_rn(__dadd_rn(__dmul_rn(l, k0), __dmul_rn(c, k1)), __dmul_rn(r, k0));
+                if (y > y0 && out_col) {
+                    // cv::SymmColumnFilter order: centre, then k*(up+down); the value of output row y - 1
+                    const double v = __dadd_rn(__dmul_rn(k1, mid), __dmul_rn(k0, __dadd_rn(up, down)));
+                    if (OUT64) {
+                        out64[(size_t)win * H * W + (size_t)(y - 1) * W + x] = v * scale;
+                    } else {
+                        surf2Dwrite((float)v, surf, x * (int)sizeof(float), y - 1);
+                        sq += v * v;
+                    }
+                }
+                up = mid;
+                mid = down;
+            }
         }
     }
     if constexpr (!OUT64) {
@@ -208,6 +219,80 @@ __global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long
                 norms[2 * slot + 1] = 1.0 / nrm;
                 tickets[win] = 0;
             }
+        }
+    }
+}
+
+// Pyramid level i >= 1 of EventFrame::create (EventFrame.cpp:349-357): cv::dilate + cv::erode of the level-0 frame with a
+// (2i+1) x (2i+1) rectangle, same resolution, and the level's own L2 norm (:360-364).  The default border of cv::dilate /
+// cv::erode leaves pixels outside the image out of the maximum / minimum; clamp-to-edge sampling does the same (the
+// replicated edge texel is already inside every clipped window).  Separable: row maxima / minima of a tile with halo in
+// shared memory, then columns.  The level is stored like level 0: fp32, un-normalised, {norm, 1/norm} beside it.
+constexpr int MORPH_TILE = 32, MORPH_THREADS = 256, MORPH_MAX_R = 4;
+__host__ __device__ constexpr int morph_ctas_x(int W) { return (W + MORPH_TILE - 1) / MORPH_TILE; }
+__host__ __device__ constexpr int morph_ctas_y(int H) { return (H + MORPH_TILE - 1) / MORPH_TILE; }
+
+__global__ void __launch_bounds__(MORPH_THREADS) morph_level_kernel(const cudaTextureObject_t* __restrict__ tex0, const cudaSurfaceObject_t* __restrict__ surfs,
+                                                                    int H, int W, int R, int first_slot, double* __restrict__ partials,
+                                                                    unsigned* __restrict__ tickets, double* __restrict__ norms) {
+    constexpr int TS = MORPH_TILE + 2 * MORPH_MAX_R;
+    __shared__ float tile[TS][TS + 1];
+    __shared__ float rmax[TS][MORPH_TILE + 1], rmin[TS][MORPH_TILE + 1];
+    __shared__ double wsum[MORPH_THREADS / 32];
+    __shared__ bool is_last;
+    const int win = blockIdx.z, slot = first_slot + win, tid = threadIdx.x;
+    const int x0 = blockIdx.x * MORPH_TILE, y0 = blockIdx.y * MORPH_TILE;
+    const int span = MORPH_TILE + 2 * R;
+    const cudaTextureObject_t src = tex0[slot];
+    for (int i = tid; i < span * span; i += MORPH_THREADS) {
+        const int ly = i / span, lx = i - ly * span;
+        tile[ly][lx] = tex2D<float>(src, (float)(x0 + lx - R) + 0.5f, (float)(y0 + ly - R) + 0.5f);
+    }
+    __syncthreads();
+    for (int i = tid; i < span * MORPH_TILE; i += MORPH_THREADS) {
+        const int ly = i / MORPH_TILE, lx = i % MORPH_TILE;
+        float mx = tile[ly][lx], mn = mx;
+        for (int k = 1; k <= 2 * R; ++k) { const float v = tile[ly][lx + k]; mx = fmaxf(mx, v); mn = fminf(mn, v); }
+        rmax[ly][lx] = mx;
+        rmin[ly][lx] = mn;
+    }
+    __syncthreads();
+    double sq = 0.0;
+    for (int i = tid; i < MORPH_TILE * MORPH_TILE; i += MORPH_THREADS) {
+        const int ly = i / MORPH_TILE, lx = i % MORPH_TILE;
+        const int gx = x0 + lx, gy = y0 + ly;
+        if (gx < W && gy < H) {
+            float mx = rmax[ly][lx], mn = rmin[ly][lx];
+            for (int k = 1; k <= 2 * R; ++k) { mx = fmaxf(mx, rmax[ly + k][lx]); mn = fminf(mn, rmin[ly + k][lx]); }
+            const float v = mx + mn;
+            surf2Dwrite(v, surfs[slot], gx * (int)sizeof(float), gy);
+            sq += (double)v * (double)v;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((tid & 31) == 0) wsum[tid >> 5] = sq;
+    __syncthreads();
+    const int nctas = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < MORPH_THREADS / 32; ++w) s += wsum[w];
+        partials[(size_t)win * nctas + cta] = s;
+        __threadfence();
+        const unsigned t = atomicAdd(&tickets[win], 1u);
+        is_last = (t == (unsigned)nctas - 1);
+    }
+    __syncthreads();
+    if (is_last && tid < 32) {
+        __threadfence();
+        const volatile double* p = partials + (size_t)win * nctas;
+        double s = 0.0;
+        for (int i = tid; i < nctas; i += 32) s += p[i];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) {
+            const double nrm = sqrt(s);
+            norms[2 * slot] = nrm;
+            norms[2 * slot + 1] = 1.0 / nrm;
+            tickets[win] = 0;
         }
     }
 }
@@ -263,6 +348,14 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
             ctx->launches++;
             EDS_CUDA(ctx, cudaGetLastError());
         }
+    }
+    for (int lvl = 1; lvl < fr->levels; ++lvl) {
+        dim3 grid(morph_ctas_x(W), morph_ctas_y(H), count);
+        const size_t base = (size_t)lvl * fr->capacity;
+        morph_level_kernel<<<grid, MORPH_THREADS, 0, bs>>>(fr->tex_dev, fr->surf_dev + base, H, W, lvl, first_slot, fr->partials, fr->tickets,
+                                                           fr->norms + 2 * base);
+        ctx->launches++;
+        EDS_CUDA(ctx, cudaGetLastError());
     }
     {   // readers of these slots wait for this build
         cudaEvent_t e = fr->built_pool[fr->built_next];
@@ -345,14 +438,20 @@ void edsgpu_lut_destroy(edsgpu_lut* lut) {
 }
 
 edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int capacity, edsgpu_frames** out) {
+    return edsgpu_frames_create_pyramid(ctx, height, width, capacity, 1, out);
+}
+
+edsgpu_status edsgpu_frames_create_pyramid(edsgpu_ctx* ctx, int height, int width, int capacity, int num_levels, edsgpu_frames** out) {
     if (!ctx || !out) return EDSGPU_INVALID_ARGUMENT;
     EDS_REQUIRE(ctx, height > 0 && width > 0 && capacity > 0, "frames_create: bad size");
     EDS_REQUIRE(ctx, (size_t)height * width < (1ull << 31), "frames_create: image too large");
+    EDS_REQUIRE(ctx, num_levels >= 1 && num_levels <= MORPH_MAX_R + 1, "frames_create: num_levels must be in [1,5]");
     DeviceGuard g(ctx->device);
     edsgpu_frames* fr = new edsgpu_frames();
-    fr->ctx = ctx; fr->H = height; fr->W = width; fr->capacity = capacity;
+    fr->ctx = ctx; fr->H = height; fr->W = width; fr->capacity = capacity; fr->levels = num_levels;
     const size_t npix = (size_t)height * width;
-    const int ntiles = blur_ctas(height, width);
+    const int ntiles = std::max(blur_ctas(height, width), morph_ctas_x(width) * morph_ctas_y(height));
+    const int nimg = capacity * num_levels;  // one fp32 image per (level, slot)
     {
         // one accumulator per slot while they all fit the budget, otherwise a ring that stays resident in L2
         // EDSGPU_ACC_RING_MB: size of the ring; 0 (the default) = always one accumulator per slot.  Measured on the 64-window
@@ -366,13 +465,13 @@ edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int c
         fr->slot_acc.assign(capacity, -1);
     }
     cudaError_t e = cudaMalloc(&fr->acc, sizeof(long long) * npix * fr->acc_slots);
-    fr->arrays = new cudaArray_t[capacity]();
-    fr->tex = new cudaTextureObject_t[capacity]();
-    fr->surf = new cudaSurfaceObject_t[capacity]();
+    fr->arrays = new cudaArray_t[nimg]();
+    fr->tex = new cudaTextureObject_t[nimg]();
+    fr->surf = new cudaSurfaceObject_t[nimg]();
     float* zeros = nullptr;
     if (e == cudaSuccess) e = cudaMalloc(&zeros, sizeof(float) * npix);
     if (e == cudaSuccess) e = cudaMemsetAsync(zeros, 0, sizeof(float) * npix, ctx->stream);
-    for (int i = 0; i < capacity && e == cudaSuccess; ++i) {
+    for (int i = 0; i < nimg && e == cudaSuccess; ++i) {
         const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float>();
         e = cudaMallocArray(&fr->arrays[i], &fmt, width, height, cudaArraySurfaceLoadStore | cudaArrayTextureGather);
         cudaResourceDesc res{};
@@ -389,14 +488,17 @@ edsgpu_status edsgpu_frames_create(edsgpu_ctx* ctx, int height, int width, int c
             e = cudaMemcpy2DToArrayAsync(fr->arrays[i], 0, 0, zeros, sizeof(float) * width, sizeof(float) * width, height,
                                          cudaMemcpyDeviceToDevice, ctx->stream);
     }
-    if (e == cudaSuccess) e = cudaMalloc(&fr->surf_dev, sizeof(cudaSurfaceObject_t) * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&fr->surf_dev, sizeof(cudaSurfaceObject_t) * nimg);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(fr->surf_dev, fr->surf, sizeof(cudaSurfaceObject_t) * capacity, cudaMemcpyHostToDevice, ctx->stream);
+        e = cudaMemcpyAsync(fr->surf_dev, fr->surf, sizeof(cudaSurfaceObject_t) * nimg, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&fr->tex_dev, sizeof(cudaTextureObject_t) * nimg);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(fr->tex_dev, fr->tex, sizeof(cudaTextureObject_t) * nimg, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc(&fr->partials, sizeof(double) * (size_t)ntiles * capacity);
     if (e == cudaSuccess) e = cudaMalloc(&fr->tickets, sizeof(unsigned) * capacity);
-    if (e == cudaSuccess) e = cudaMalloc(&fr->norms, sizeof(double) * 2 * capacity);
+    if (e == cudaSuccess) e = cudaMalloc(&fr->norms, sizeof(double) * 2 * nimg);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->tickets, 0, sizeof(unsigned) * capacity, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(fr->norms, 0, sizeof(double) * 2 * capacity, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fr->norms, 0, sizeof(double) * 2 * nimg, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(fr->acc, 0, sizeof(long long) * npix * fr->acc_slots, ctx->stream);
     fr->slot_built.assign(capacity, nullptr);
     fr->slot_read.assign(capacity, nullptr);
@@ -436,7 +538,7 @@ void edsgpu_frames_destroy(edsgpu_frames* fr) {
         if (fr->read_pool[i]) cudaEventDestroy(fr->read_pool[i]);
     }
     if (fr->acc) cudaFree(fr->acc);
-    for (int i = 0; i < fr->capacity && fr->arrays; ++i) {
+    for (int i = 0; i < fr->capacity * fr->levels && fr->arrays; ++i) {
         if (fr->tex[i]) cudaDestroyTextureObject(fr->tex[i]);
         if (fr->surf[i]) cudaDestroySurfaceObject(fr->surf[i]);
         if (fr->arrays[i]) cudaFreeArray(fr->arrays[i]);
@@ -445,6 +547,7 @@ void edsgpu_frames_destroy(edsgpu_frames* fr) {
     delete[] fr->tex;
     delete[] fr->surf;
     if (fr->surf_dev) cudaFree(fr->surf_dev);
+    if (fr->tex_dev) cudaFree(fr->tex_dev);
     if (fr->partials) cudaFree(fr->partials);
     if (fr->tickets) cudaFree(fr->tickets);
     if (fr->norms) cudaFree(fr->norms);
@@ -571,6 +674,36 @@ edsgpu_status edsgpu_frames_read(edsgpu_ctx* ctx, const edsgpu_frames* frames, i
         EDS_CUDA(ctx, cudaMemcpyAsync(norm_out, frames->norms + 2 * slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return EDSGPU_OK;
+}
+
+namespace {
+__global__ void read_level_kernel(cudaTextureObject_t tex, int H, int W, double* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < W && y < H) out[(size_t)y * W + x] = (double)tex2D<float>(tex, (float)x + 0.5f, (float)y + 0.5f);
+}
+}  // namespace
+
+edsgpu_status edsgpu_frames_read_level(edsgpu_ctx* ctx, const edsgpu_frames* frames, int slot, int level, double* image_out, double* norm_out) {
+    if (!ctx) return EDSGPU_INVALID_ARGUMENT;
+    EDS_REQUIRE(ctx, frames && slot >= 0 && slot < frames->capacity && level >= 0 && level < frames->levels, "frames_read_level: bad slot or level");
+    DeviceGuard g(ctx->device);
+    const int H = frames->H, W = frames->W;
+    const size_t npix = (size_t)H * W, idx = (size_t)level * frames->capacity + slot;
+    edsgpu_status st = edsgpu_frames_wait_built(frames, slot, 1, ctx->stream);
+    if (st != EDSGPU_OK) return st;
+    if (image_out) {
+        st = edsgpu_ensure_scratch(ctx, npix * sizeof(double));
+        if (st != EDSGPU_OK) return st;
+        read_level_kernel<<<dim3((W + 127) / 128, H), 128, 0, ctx->stream>>>(frames->tex[idx], H, W, (double*)ctx->scratch);
+        ctx->launches++;
+        EDS_CUDA(ctx, cudaGetLastError());
+        EDS_CUDA(ctx, cudaMemcpyAsync(image_out, ctx->scratch, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (norm_out) EDS_CUDA(ctx, cudaMemcpyAsync(norm_out, frames->norms + 2 * idx, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    st = edsgpu_frames_mark_read(frames, slot, 1, ctx->stream);
+    if (st != EDSGPU_OK) return st;
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EDSGPU_OK;
 }
 

@@ -16,6 +16,7 @@ struct edsgpu_frames {
     edsgpu_ctx* ctx = nullptr;
     uint64_t uid = edsgpu_next_uid();
     int H = 0, W = 0, capacity = 0;
+    int levels = 1;  // pyramid levels (EventFrame.cpp:342-357); per-level arrays below are indexed [level * capacity + slot]
     // Fixed-point (2^-40) brightness increments, [acc_slots][H*W].  An accumulator only lives from the scatter of a window to
     // its blur, so a large set of slots shares a RING of accumulators sized to stay resident in L2 (acc_slots < capacity): a
     // build runs in chunks of acc_slots windows, clear -> scatter -> blur, and the 8 bytes per pixel never travel to HBM.
@@ -26,13 +27,14 @@ struct edsgpu_frames {
     // blurred, un-normalised fp32 frames: one block-linear CUDA array per slot, written through a
     // surface by the blur kernel and sampled by the tracker with 2x2 texture gathers (clamp-to-edge
     // addressing = the clamped ceres::Grid2D)
-    cudaArray_t* arrays = nullptr;            // [capacity] host
-    cudaTextureObject_t* tex = nullptr;       // [capacity] host
-    cudaSurfaceObject_t* surf = nullptr;      // [capacity] host
-    cudaSurfaceObject_t* surf_dev = nullptr;  // [capacity] device copy for the blur kernel
-    double* partials = nullptr;   // [capacity][ntiles] per-tile sum of squares
+    cudaArray_t* arrays = nullptr;            // [levels * capacity] host
+    cudaTextureObject_t* tex = nullptr;       // [levels * capacity] host
+    cudaSurfaceObject_t* surf = nullptr;      // [levels * capacity] host
+    cudaSurfaceObject_t* surf_dev = nullptr;  // [levels * capacity] device copy for the blur / morphology kernels
+    cudaTextureObject_t* tex_dev = nullptr;   // [levels * capacity] device copy (the morphology kernel samples level 0)
+    double* partials = nullptr;   // [capacity][ntiles] per-CTA sum of squares of the kernel that is building a level
     unsigned* tickets = nullptr;  // [capacity] last-CTA election
-    double* norms = nullptr;      // [capacity][2] = {norm, 1/norm}
+    double* norms = nullptr;      // [levels * capacity][2] = {norm, 1/norm}
     double k0 = 0.0, k1 = 1.0;    // Gaussian taps of the last create (for read-back)
     // host-facing create: two device staging buffers filled by a copy stream, so that the H2D copy of
     // the next batch of events overlaps the kernels still working on the current one

@@ -1747,7 +1747,8 @@ struct edsgpu_tracker {
     // one-problem batch cached for repeated optimize() calls against the same keyframe / frame slot
     struct edsgpu_batch* cached = nullptr;
     uint64_t cached_kf = 0, cached_frames = 0;
-    int cached_slot = -1;
+    int cached_slot = -1, cached_level = -1;
+    std::vector<int> level_iterations;  // config.options.max_num_iterations[id] (Tracker.cpp:139); empty = cfg.max_iterations at every level
 };
 
 struct LaunchShape { int n_lead, n_eval; };  // leader CTAs, evaluator CTAs
@@ -1760,6 +1761,7 @@ struct edsgpu_batch {
     unsigned queue_mask = 0;
     const edsgpu_frames* frames = nullptr;  // slots first_slot .. first_slot + count - 1
     int first_slot = 0;
+    int level = 0;                          // pyramid level of the frames the batch samples (Tracker::optimize(id, ...))
     ProblemDesc* desc = nullptr;  // device
     std::vector<edsgpu_tracker*> trackers;
     std::vector<const edsgpu_keyframe*> keyframes;  // must outlive the batch (the descriptors hold their device arrays)
@@ -1795,16 +1797,17 @@ LaunchShape pick_shape(edsgpu_ctx* ctx, int count, int B) {
     return LaunchShape{n_lead, n_eval};
 }
 
-ProblemDesc make_desc(const edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot) {
+ProblemDesc make_desc(const edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot, int level) {
     ProblemDesc d{};
     d.kf = kf->dev;
-    d.frame = frames->tex[slot];
-    d.norms = frames->norms + 2 * slot;
+    const size_t img = (size_t)level * frames->capacity + slot;  // event_frame[id] of the slot
+    d.frame = frames->tex[img];
+    d.norms = frames->norms + 2 * img;
     d.state = tr->state;
     d.residuals = tr->residuals;
     d.info = tr->info;
     d.loss_type = tr->cfg.loss_type;
-    d.max_iter = tr->cfg.max_iterations;
+    d.max_iter = level < (int)tr->level_iterations.size() ? tr->level_iterations[level] : tr->cfg.max_iterations;
     d.loss_param_method = tr->cfg.loss_param_method;
     d.eval_only = 0;
     d.ftol = tr->cfg.function_tolerance;
@@ -1822,7 +1825,7 @@ edsgpu_status upload_descriptors(edsgpu_batch* b) {
     b->res_generation.resize(b->count);
     for (int i = 0; i < b->count; ++i) {
         EDS_REQUIRE(ctx, b->trackers[i]->res_capacity >= b->keyframes[i]->dev.N, "batch: a tracker's residual buffer is smaller than its key frame");
-        hd[i] = make_desc(b->trackers[i], b->keyframes[i], b->frames, b->first_slot + i);
+        hd[i] = make_desc(b->trackers[i], b->keyframes[i], b->frames, b->first_slot + i, b->level);
         b->res_generation[i] = b->trackers[i]->res_generation;
     }
     EDS_CUDA(ctx, cudaMemcpyAsync(b->desc, hd.data(), sizeof(ProblemDesc) * (size_t)b->count, cudaMemcpyHostToDevice, ctx->stream));
@@ -1981,8 +1984,14 @@ void edsgpu_debug_timing(unsigned long long* out, int reset) {
 
 edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes, int count,
                                   const edsgpu_frames* frames, int first_slot, edsgpu_batch** out) {
+    return edsgpu_batch_create_level(ctx, trackers, keyframes, count, frames, first_slot, 0, out);
+}
+
+edsgpu_status edsgpu_batch_create_level(edsgpu_ctx* ctx, edsgpu_tracker* const* trackers, const edsgpu_keyframe* const* keyframes, int count,
+                                        const edsgpu_frames* frames, int first_slot, int level, edsgpu_batch** out) {
     if (!ctx || !out) return EDSGPU_INVALID_ARGUMENT;
     EDS_REQUIRE(ctx, trackers && keyframes && count > 0, "batch_create: bad arguments");
+    EDS_REQUIRE(ctx, frames && level >= 0 && level < frames->levels, "batch_create: the frames have no such pyramid level");
     DeviceGuard g(ctx->device);
     int B = 0;
     for (int i = 0; i < count; ++i) {
@@ -2008,6 +2017,7 @@ edsgpu_status edsgpu_batch_create(edsgpu_ctx* ctx, edsgpu_tracker* const* tracke
     b->shape = pick_shape(ctx, count, B);
     b->frames = frames;
     b->first_slot = first_slot;
+    b->level = level;
     b->trackers.assign(trackers, trackers + count);
     b->keyframes.assign(keyframes, keyframes + count);
     cudaError_t e = cudaMalloc(&b->desc, sizeof(ProblemDesc) * (size_t)count);
@@ -2120,17 +2130,36 @@ edsgpu_status edsgpu_trackers_gather(edsgpu_ctx* ctx, edsgpu_tracker* const* tra
 
 edsgpu_status edsgpu_tracker_optimize(edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot, double px[3],
                                       double qx[4], double vx[6], double* residuals_out, double* next_loss_param_out, edsgpu_tracker_info* info) {
+    return edsgpu_tracker_optimize_level(tr, kf, frames, slot, 0, px, qx, vx, residuals_out, next_loss_param_out, info);
+}
+
+edsgpu_status edsgpu_tracker_set_level_iterations(edsgpu_tracker* tr, const int* max_num_iterations, int num_levels) {
+    if (!tr) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = tr->ctx;
+    EDS_REQUIRE(ctx, num_levels >= 0 && (num_levels == 0 || max_num_iterations), "tracker_set_level_iterations: bad arguments");
+    for (int i = 0; i < num_levels; ++i) EDS_REQUIRE(ctx, max_num_iterations[i] >= 0, "tracker_set_level_iterations: negative iteration cap");
+    tr->level_iterations.assign(max_num_iterations, max_num_iterations + num_levels);
+    if (tr->cached) {  // its descriptor carries the old cap
+        edsgpu_batch_destroy(tr->cached);
+        tr->cached = nullptr;
+    }
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_tracker_optimize_level(edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot, int level,
+                                            double px[3], double qx[4], double vx[6], double* residuals_out, double* next_loss_param_out,
+                                            edsgpu_tracker_info* info) {
     if (!tr) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = tr->ctx;
     EDS_REQUIRE(ctx, kf && frames, "tracker_optimize: null handle");
-    if (!tr->cached || tr->cached_kf != kf->uid || tr->cached_frames != frames->uid || tr->cached_slot != slot) {
+    if (!tr->cached || tr->cached_kf != kf->uid || tr->cached_frames != frames->uid || tr->cached_slot != slot || tr->cached_level != level) {
         if (tr->cached) edsgpu_batch_destroy(tr->cached);
         tr->cached = nullptr;
         const edsgpu_keyframe* kfs[1] = {kf};
         edsgpu_tracker* trs[1] = {tr};
-        edsgpu_status stc = edsgpu_batch_create(ctx, trs, kfs, 1, frames, slot, &tr->cached);
+        edsgpu_status stc = edsgpu_batch_create_level(ctx, trs, kfs, 1, frames, slot, level, &tr->cached);
         if (stc != EDSGPU_OK) return stc;
-        tr->cached_kf = kf->uid; tr->cached_frames = frames->uid; tr->cached_slot = slot;
+        tr->cached_kf = kf->uid; tr->cached_frames = frames->uid; tr->cached_slot = slot; tr->cached_level = level;
     }
     edsgpu_status st = edsgpu_batch_optimize(tr->cached);
     if (st != EDSGPU_OK) return st;

@@ -27,7 +27,8 @@ SYMBOLS = [
     "edsgpu_version", "edsgpu_create", "edsgpu_destroy", "edsgpu_last_error_string", "edsgpu_synchronize",
     "edsgpu_launch_count", "edsgpu_lut_create", "edsgpu_lut_destroy", "edsgpu_frames_create", "edsgpu_frames_destroy",
     "edsgpu_event_frame_create", "edsgpu_event_frame_create_batch", "edsgpu_event_frame_create_batch_dev",
-    "edsgpu_frames_read", "edsgpu_frames_read_accumulator", "edsgpu_frames_build_stream", "edsgpu_keyframe_create", "edsgpu_keyframe_destroy",
+    "edsgpu_frames_read", "edsgpu_frames_read_accumulator", "edsgpu_frames_create_pyramid", "edsgpu_frames_read_level",
+    "edsgpu_tracker_set_level_iterations", "edsgpu_tracker_optimize_level", "edsgpu_batch_create_level", "edsgpu_frames_build_stream", "edsgpu_keyframe_create", "edsgpu_keyframe_destroy",
     "edsgpu_tracker_create", "edsgpu_tracker_destroy", "edsgpu_tracker_set_state", "edsgpu_tracker_get_state",
     "edsgpu_tracker_optimize", "edsgpu_trackers_optimize_batch", "edsgpu_trackers_gather", "edsgpu_tracker_state_dev",
     "edsgpu_batch_create", "edsgpu_batch_destroy", "edsgpu_batch_optimize", "edsgpu_batch_count", "edsgpu_batch_pack_states_dev", "edsgpu_batch_launch_shape",
@@ -160,12 +161,20 @@ class Lut:
 
 
 class Frames:
-    """A bank of device event frames (EventFrame::event_frame[0] of several windows)."""
+    """A bank of device event frames (EventFrame::event_frame[0 .. levels-1] of several windows)."""
 
-    def __init__(self, ctx, H, W, capacity=1):
-        self.ctx, self.H, self.W, self.capacity = ctx, H, W, capacity
+    def __init__(self, ctx, H, W, capacity=1, levels=1):
+        self.ctx, self.H, self.W, self.capacity, self.levels = ctx, H, W, capacity, levels
         self.h = C.c_void_p()
-        ctx.check(ctx.lib.edsgpu_frames_create(ctx.h, C.c_int(H), C.c_int(W), C.c_int(capacity), C.byref(self.h)))
+        ctx.check(ctx.lib.edsgpu_frames_create_pyramid(ctx.h, C.c_int(H), C.c_int(W), C.c_int(capacity), C.c_int(levels), C.byref(self.h)))
+
+    def read_level(self, slot=0, level=0):
+        """frame[level] of the slot as it is stored (fp32 widened to double, un-normalised) and norm[level]"""
+        img = np.zeros((self.H, self.W), np.float64)
+        norm = C.c_double(0)
+        self.ctx.check(self.ctx.lib.edsgpu_frames_read_level(self.ctx.h, self.h, C.c_int(slot), C.c_int(level), _ptr(img, C.c_double),
+                                                             C.byref(norm)))
+        return img, norm.value
 
     def read(self, slot=0):
         img = np.zeros((self.H, self.W), np.float64)
@@ -269,16 +278,21 @@ class Tracker:
                                                              _ptr(vx, C.c_double), C.byref(lp), C.byref(info)))
         return px, qx, vx, lp.value, info.as_dict()
 
-    def optimize(self, kf, frames, slot=0, want_residuals=False):
-        """bool Tracker::optimize(id, event_frame, T_kf_ef, MAD) (Tracker.cpp:104-241).
+    def set_level_iterations(self, max_num_iterations):
+        """config.options.max_num_iterations: one cap per pyramid level (Tracker.cpp:139)"""
+        a = (C.c_int * len(max_num_iterations))(*[int(v) for v in max_num_iterations])
+        self.ctx.check(self.ctx.lib.edsgpu_tracker_set_level_iterations(self.h, a, C.c_int(len(max_num_iterations))))
+
+    def optimize(self, kf, frames, slot=0, want_residuals=False, level=0):
+        """bool Tracker::optimize(id, event_frame, T_kf_ef, MAD) (Tracker.cpp:104-241), id = level.
         Returns dict(usable, px, qx, vx, residuals, next_loss_param, info)."""
         px, qx, vx = np.zeros(3), np.zeros(4), np.zeros(6)
         res = np.zeros(kf.N) if want_residuals else None
         tau = C.c_double(0)
         info = TrackerInfo()
-        st = self.ctx.lib.edsgpu_tracker_optimize(self.h, kf.h, frames.h, C.c_int(slot), _ptr(px, C.c_double),
-                                                  _ptr(qx, C.c_double), _ptr(vx, C.c_double), _ptr(res, C.c_double),
-                                                  C.byref(tau), C.byref(info))
+        st = self.ctx.lib.edsgpu_tracker_optimize_level(self.h, kf.h, frames.h, C.c_int(slot), C.c_int(level), _ptr(px, C.c_double),
+                                                        _ptr(qx, C.c_double), _ptr(vx, C.c_double), _ptr(res, C.c_double),
+                                                        C.byref(tau), C.byref(info))
         if st not in (OK, NOT_USABLE):
             self.ctx.check(st)
         self.info = info.as_dict()
@@ -323,15 +337,15 @@ class TrackerBatch:
     """`count` independent trackers advanced by one launch (edsgpu_batch_*): tracker i runs against
     keyframe i and frame slot first_slot+i; descriptors are built once."""
 
-    def __init__(self, ctx, trackers, keyframes, frames, first_slot=0):
+    def __init__(self, ctx, trackers, keyframes, frames, first_slot=0, level=0):
         self.ctx, self.trackers, self.keyframes, self.frames = ctx, trackers, keyframes, frames
         n = len(trackers)
         self._tr = (C.c_void_p * n)(*[t.h for t in trackers])
         self._kf = (C.c_void_p * n)(*[k.h for k in keyframes])
         self.count = n
         self.h = C.c_void_p()
-        ctx.check(ctx.lib.edsgpu_batch_create(ctx.h, self._tr, self._kf, C.c_int(n), frames.h, C.c_int(first_slot),
-                                              C.byref(self.h)))
+        ctx.check(ctx.lib.edsgpu_batch_create_level(ctx.h, self._tr, self._kf, C.c_int(n), frames.h, C.c_int(first_slot), C.c_int(level),
+                                                    C.byref(self.h)))
 
     def optimize(self):
         self.ctx.check(self.ctx.lib.edsgpu_batch_optimize(self.h))

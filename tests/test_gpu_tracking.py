@@ -440,3 +440,48 @@ def test_gpu_against_golden(gpu_ctx, name):
         ef2 = edsgpu.EventFrame(gpu_ctx, H, W, g["lut_x"], g["lut_y"]).create(g["ev_x"], g["ev_y"], g["ev_pol"], g["ev_ts"])
         img, norm = ef2.frames.read(0)
         assert np.abs(img - g["lut_img"]).max() < 1e-10 and abs(norm - float(g["lut_norm"])) < 1e-11 * norm
+
+
+def test_pyramid_levels_and_per_level_solve(gpu_ctx, problems):
+    """EventFrame pyramid (EventFrame.cpp:342-364) and Tracker::optimize(id, &event_frame[id]) with
+    max_num_iterations[id] (Tracker.cpp:85-241): levels >= 1 are dilate + erode of level 0, each with its own norm; the
+    solve at a level samples that level's frame and stops at that level's iteration cap."""
+    kf, wins = problems["davis240c"]
+    w = wins[0]
+    H, W, L = kf["H"], kf["W"], 3
+    fr = edsgpu.Frames(gpu_ctx, H, W, 2, levels=L)
+    ef = edsgpu.EventFrame(gpu_ctx, H, W, frames=fr, slot=1).create(w["x"], w["y"], w["pol"], w["ts"])
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], H, W)
+    img0, n0 = fr.read_level(1, 0)
+    assert n0 == ef.norm and np.abs(img0 - o["img"]).max() <= 1e-6 * np.abs(o["img"]).max()
+    # the device levels are exactly dilate + erode of the device's own (fp32) level 0 ...
+    f32, _ = O.event_frame_levels(img0.astype(np.float32), L)
+    # ... and agree with the double-precision pyramid of the oracle's level 0 to fp32 storage accuracy
+    f64, n64 = O.event_frame_levels(o["img"], L)
+    for lvl in range(1, L):
+        img, nrm = fr.read_level(1, lvl)
+        assert np.array_equal(img.astype(np.float32), f32[lvl])
+        assert abs(nrm - np.sqrt(np.sum(img ** 2))) <= 1e-12 * nrm
+        assert np.abs(img - f64[lvl]).max() <= 1e-6 * np.abs(f64[lvl]).max() and abs(nrm - n64[lvl]) <= 1e-6 * n64[lvl]
+    # coarse-to-fine solve, warm-started from level to level, against the oracle run on the oracle's pyramid
+    caps = [9, 6, 4]
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, 8)
+    tr = edsgpu.Tracker(gpu_ctx, num_blocks=8, max_iterations=30)
+    tr.set_level_iterations(caps)
+    x, tau = w["x_init"].copy(), 0.05
+    tr.set_state(x[:3], x[3:7], x[7:], tau)
+    for lvl in (2, 1, 0):
+        r = tr.optimize(kfd, fr, 1, level=lvl)
+        s = O.tracker_solve(kf, f64[lvl] / n64[lvl], x, num_blocks=8, loss_param=tau, max_iterations=caps[lvl])
+        assert r["usable"] and s["status"] == 0
+        assert r["info"]["iterations"] == s["info"]["iterations"] <= caps[lvl]
+        assert synth.quat_angle(r["qx"], s["x"][3:7]) < ANGLE_TOL and np.linalg.norm(r["px"] - s["x"][:3]) < DEPTH_TOL
+        assert abs(r["info"]["final_cost"] - s["info"]["final_cost"]) < 1e-5 * s["info"]["final_cost"]
+        x, tau = s["x"], s["next_loss_param"]
+        tr.set_state(x[:3], x[3:7], x[7:], tau)  # both sides continue from the oracle's state
+    # level arguments are validated
+    with pytest.raises(edsgpu.EdsGpuError):
+        tr.optimize(kfd, fr, 1, level=L)
+    with pytest.raises(edsgpu.EdsGpuError):
+        edsgpu.Frames(gpu_ctx, H, W, 1, levels=9)
+    tr.close(); kfd.close(); fr.close()

@@ -277,3 +277,18 @@ def test_oracle_self_drift_bounds_the_pose_gate(config):
     c = [O.tracker_solve(k2, f2, w["x_init"], num_blocks=8, max_iterations=30, threads=8)["info"]["final_cost"]
          for _, k2, f2 in drift.perturbed_inputs(kf, frame)[:3]]
     assert max(abs(v - ref30["info"]["final_cost"]) for v in c) < 5e-4 * ref30["info"]["final_cost"]
+
+
+def test_pyramid_levels_match_opencv_morphology():
+    """EventFrame.cpp:349-357: level i = dilate + erode with a (2i+1)^2 rectangle.  The numpy restatement against real
+    OpenCV, bit for bit (selection of existing values plus one addition), on a frame with flat regions and on noise."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for img in (rng.normal(size=(37, 53)), np.round(rng.normal(size=(24, 31)) * 2) / 2):
+        frames, norms = O.event_frame_levels(img, 4)
+        assert np.array_equal(frames[0], img)
+        for i in range(1, 4):
+            el = cv2.getStructuringElement(cv2.MORPH_RECT, (2 * i + 1, 2 * i + 1), (i, i))
+            ref = cv2.dilate(img, el) + cv2.erode(img, el)
+            assert np.array_equal(frames[i], ref)
+            assert abs(norms[i] - cv2.norm(ref)) <= 1e-12 * norms[i]
