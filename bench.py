@@ -537,7 +537,7 @@ def measure(run, steps, warmup, barrier, max_over_ranks, peak, traffic):
     shape = run.banks[0].launch_shape()
     return {
         "t_ms": t_ms, "e2e_s": e2e_s, "launches": int(launches), "iters": iters, "usable": usable, "states": states,
-        "launch_shape": "%d evaluator CTAs + %d leader CTAs of 512 threads, %d problems in flight" % shape,
+        "launch_shape": "%d evaluator CTAs + %d leader CTAs of 768 threads, %d problems in flight" % shape,
         "roofline": {"kernel": "track_lm_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic or {}).get("track_lm_kernel_dram_bytes_per_launch"),
                      "l2_bytes": (traffic or {}).get("track_lm_kernel_lts_bytes_per_launch"),

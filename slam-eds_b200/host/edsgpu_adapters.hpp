@@ -71,14 +71,16 @@ struct TrackerInfo {  // tracking/Config.hpp:60-68
     uint8_t success = 0;
 };
 
-// EventFrame (EventFrame.hpp:31-107), pyramid level 0.
+// EventFrame (EventFrame.hpp:31-107) with its pyramid (EventFrame.cpp:342-364).
 class EventFrame {
   public:
-    // EventFrame(cam, newcam, ...): the forward undistortion LUT is built once (EventFrame.cpp:53-81).
-    EventFrame(const edsgpu_host::Context& ctx, uint16_t height, uint16_t width, const float* fwd_mapx = nullptr, const float* fwd_mapy = nullptr)
-        : ctx_(ctx), height(height), width(width) {
+    // EventFrame(cam, newcam, ...): the forward undistortion LUT is built once (EventFrame.cpp:53-81).  num_levels is the
+    // argument the reference passes to create(); the device images are allocated once, here.
+    EventFrame(const edsgpu_host::Context& ctx, uint16_t height, uint16_t width, const float* fwd_mapx = nullptr, const float* fwd_mapy = nullptr,
+               int num_levels = 1)
+        : ctx_(ctx), height(height), width(width), num_levels(num_levels) {
         if (fwd_mapx) ctx_.check(edsgpu_lut_create(ctx_.get(), height, width, fwd_mapx, fwd_mapy, &lut_));
-        ctx_.check(edsgpu_frames_create(ctx_.get(), height, width, 1, &frames_));
+        ctx_.check(edsgpu_frames_create_pyramid(ctx_.get(), height, width, 1, num_levels, &frames_));
     }
     ~EventFrame() { edsgpu_frames_destroy(frames_); edsgpu_lut_destroy(lut_); }
     EventFrame(const EventFrame&) = delete;
@@ -99,12 +101,16 @@ class EventFrame {
         if (st == EDSGPU_NON_MONOTONIC_TIME) throw std::runtime_error("[EVENT_FRAME] FATAL ERROR Event time[0] > event time [N-1] ");
         ctx_.check(st);
         norm = nrm;
+        norms.assign(num_levels, nrm);
+        for (int l = 1; l < num_levels; ++l) ctx_.check(edsgpu_frames_read_level(ctx_.get(), frames_, 0, l, nullptr, &norms[l]));
     }
     const edsgpu_frames* frames() const { return frames_; }
 
     uint64_t idx = 0;
     uint16_t height, width;
+    int num_levels;
     double norm = 0;                   // EventFrame::norm[0]
+    std::vector<double> norms;         // EventFrame::norm
     int64_t time_us = 0, delta_time_us = 0;
     std::vector<double> event_frame;   // EventFrame::event_frame[0], filled on request
 
@@ -149,11 +155,13 @@ class Tracker {
         c.num_blocks = config.options.num_threads;
         c.loss_type = (int)config.loss_type;
         c.max_iterations = config.options.max_num_iterations.at(level);
+        level_iterations_ = config.options.max_num_iterations;
         c.loss_param_method = MAD;
         c.function_tolerance = config.options.function_tolerance;
         c.gradient_tolerance = 1e-08;   // Tracker.cpp:142
         c.parameter_tolerance = 1e-06;  // Tracker.cpp:143
         ctx_.check(edsgpu_tracker_create(ctx_.get(), &c, config.loss_params.at(0), &tr_));
+        ctx_.check(edsgpu_tracker_set_level_iterations(tr_, level_iterations_.data(), (int)level_iterations_.size()));  // Tracker.cpp:139
     }
     ~Tracker() { edsgpu_tracker_destroy(tr_); }
     Tracker(const Tracker&) = delete;
@@ -174,11 +182,11 @@ class Tracker {
     // bool optimize(id, event_frame, T_kf_ef, loss_param_method) (Tracker.cpp:104-241)
     bool optimize(const int& id, const EventFrame& ef, std::array<double, 3>& t_kf_ef, std::array<double, 4>& q_kf_ef_xyzw,
                   const LOSS_PARAM_METHOD loss_param_method = MAD) {
-        (void)id;
         (void)loss_param_method;  // fixed at construction in this adapter
         edsgpu_tracker_info inf{};
         double tau = 0.0;
-        edsgpu_status st = edsgpu_tracker_optimize(tr_, kf_->get(), ef.frames(), 0, px.data(), qx.data(), vx.data(), kf_->residuals.data(), &tau, &inf);
+        // id = pyramid level: event_frame[id], max_num_iterations[id]
+        edsgpu_status st = edsgpu_tracker_optimize_level(tr_, kf_->get(), ef.frames(), 0, id, px.data(), qx.data(), vx.data(), kf_->residuals.data(), &tau, &inf);
         info.num_points = (uint32_t)inf.num_points;
         info.num_iterations = inf.iterations;
         info.success = (uint8_t)inf.usable;
@@ -208,6 +216,7 @@ class Tracker {
     const edsgpu_host::Context& ctx_;
     std::shared_ptr<KeyFrame> kf_;
     edsgpu_tracker* tr_ = nullptr;
+    std::vector<int> level_iterations_;
     TrackerInfo info;
 };
 
@@ -273,6 +282,14 @@ class HessianAccumulators {
     void linearizeAll(const uint8_t* state_state, const uint8_t* isLinearized, const float* res_toZeroF, int32_t* state_NewState,
                       float* state_NewEnergy) {
         ctx_.check(edsgpu_ba_linearize(ba_, state_state, isLinearized, res_toZeroF, state_NewState, state_NewEnergy));
+    }
+    // linearizeAll() + accumulateAF_MT() as ONE kernel (EnergyFunctional.cpp:838-860): the record of a residual nothing reads later
+    // is never written; keepRecords = true before fixLinearizationF / marginalisation, which read them all
+    void linearizeAllAndAccumulateAF_MT(const uint8_t* state_state, const uint8_t* isLinearized, const float* res_toZeroF, bool keepRecords,
+                                        int32_t* state_NewState, float* state_NewEnergy, std::vector<double>& H, std::vector<double>& b) {
+        ctx_.check(edsgpu_ba_linearize_accumulate(ba_, state_state, isLinearized, res_toZeroF, keepRecords ? 1 : 0, state_NewState, state_NewEnergy));
+        H.assign((size_t)n * n, 0.0); b.assign(n, 0.0);
+        ctx_.check(edsgpu_ba_top_stitch(ba_, 0, 0, nullptr, nullptr, nullptr, H.data(), b.data()));
     }
     // setAdjointsF / setDeltaF results (EnergyFunctional.cpp:46-106,171-194)
     void setFrames(const float* adHTdeltaF, const float* cDeltaF, const double* adHost, const double* adTarget) {

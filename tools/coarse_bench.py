@@ -1,4 +1,4 @@
-"""Developer tool: the BA side line of bench.py on its own (also the workload of the BA ncu captures)."""
+"""Developer tool: the coarse-tracker side line of bench.py on its own (also the workload of its ncu capture)."""
 import json
 import os
 import sys
@@ -14,4 +14,4 @@ import edsgpu  # noqa: E402
 s = torch.cuda.Stream()
 torch.cuda.set_stream(s)
 ctx = edsgpu.Context(0, s.cuda_stream)
-print(json.dumps(bench.bench_ba(ctx, s, reps=int(sys.argv[1]) if len(sys.argv) > 1 else 5), indent=1))
+print(json.dumps(bench.bench_coarse(ctx, s, reps=int(sys.argv[1]) if len(sys.argv) > 1 else 5), indent=1))
