@@ -25,6 +25,18 @@ __device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); 
 __device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fs(float a, float b) { return __fadd_rn(a, -b); }
 
+// halving butterfly: 2*HALF per-lane values -> HALF, lanes with bit OFFSET keep the upper half
+template <int HALF, int OFFSET>
+__device__ __forceinline__ void halving_step(float* a, unsigned lane) {
+    const bool upper = (lane & OFFSET) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        const float send = upper ? a[i] : a[i + HALF];
+        const float keep = upper ? a[i + HALF] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFFSET);
+    }
+}
+
 struct CoarseArgs {
     int lvl, wl, hl, n;
     float fxl, fyl, cxl, cyl;
@@ -119,19 +131,33 @@ __device__ __forceinline__ void coarse_sweep(const CoarseArgs& a, double (*red)[
             for (int c = r; c < 9; ++c) acc[e++] += Jw * J[c];
         }
     }
-    // warp -> CTA -> one partial per CTA, all in double
+    // warp -> CTA -> one partial per CTA.  The 45 fp32 accumulators go through a halving butterfly (48 shuffles instead of
+    // 45 x 5: every step halves the values a lane holds), the seven statistics through plain butterflies; fp64 across warps.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double vals[CT_NPART];
+    {
+        float a48[48];
 #pragma unroll
-    for (int i = 0; i < CT_NACC; ++i) vals[i] = (double)acc[i];
-    vals[CT_NACC] = E; vals[CT_NACC + 1] = nE; vals[CT_NACC + 2] = nW; vals[CT_NACC + 3] = nSat;
-    vals[CT_NACC + 4] = (double)shT; vals[CT_NACC + 5] = (double)shRT; vals[CT_NACC + 6] = nShift;
+        for (int i = 0; i < 48; ++i) a48[i] = i < CT_NACC ? acc[i] : 0.f;
+        halving_step<24, 16>(a48, lane);
+        halving_step<12, 8>(a48, lane);
+        halving_step<6, 4>(a48, lane);
+        halving_step<3, 2>(a48, lane);
 #pragma unroll
-    for (int i = 0; i < CT_NPART; ++i) {
-        double s = vals[i];
+        for (int i = 0; i < 3; ++i) a48[i] += __shfl_xor_sync(0xffffffffu, a48[i], 1);
+        if ((lane & 1) == 0) {
+            const int b0 = 24 * ((lane >> 4) & 1) + 12 * ((lane >> 3) & 1) + 6 * ((lane >> 2) & 1) + 3 * ((lane >> 1) & 1);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) red[warp][i] = s;
+            for (int i = 0; i < 3; ++i)
+                if (b0 + i < CT_NACC) red[warp][b0 + i] = (double)a48[i];
+        }
+        double st[7] = {E, (double)nE, (double)nW, (double)nSat, (double)shT, (double)shRT, (double)nShift};
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            double s = st[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) red[warp][CT_NACC + i] = s;
+        }
     }
     __syncthreads();
     if (threadIdx.x < CT_NPART) {
@@ -462,8 +488,7 @@ __device__ __forceinline__ void track_grid_barrier(unsigned* bar) {
             atomicAdd(bar + 1, 1u);
         } else {
             unsigned g2;
-            do {
-                __nanosleep(30);
+            do {  // spin: a handful of CTAs poll one word, the wait is a few microseconds at most
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(bar + 1) : "memory");
             } while (g2 == gen);
         }

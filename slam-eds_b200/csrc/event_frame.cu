@@ -459,9 +459,9 @@ edsgpu_status edsgpu_frames_create_pyramid(edsgpu_ctx* ctx, int height, int widt
         // (0.750 ms per step with a 32 MB ring against 0.733 ms without).
         size_t ring_mb = 0;
         if (const char* e = getenv("EDSGPU_ACC_RING_MB")) ring_mb = (size_t)std::max(0, atoi(e));
-        const size_t budget = (size_t)48 << 20, per = sizeof(long long) * npix;
-        fr->acc_slots = ((size_t)capacity * per <= budget || ring_mb == 0) ? capacity
-                                                                            : (int)std::max<size_t>(1, std::min<size_t>(capacity, (ring_mb << 20) / per));
+        const size_t per = sizeof(long long) * npix;
+        fr->acc_slots = (ring_mb == 0 || (size_t)capacity * per <= (ring_mb << 20)) ? capacity
+                                                                                    : (int)std::max<size_t>(1, std::min<size_t>(capacity, (ring_mb << 20) / per));
         fr->slot_acc.assign(capacity, -1);
     }
     cudaError_t e = cudaMalloc(&fr->acc, sizeof(long long) * npix * fr->acc_slots);

@@ -485,3 +485,31 @@ def test_pyramid_levels_and_per_level_solve(gpu_ctx, problems):
     with pytest.raises(edsgpu.EdsGpuError):
         edsgpu.Frames(gpu_ctx, H, W, 1, levels=9)
     tr.close(); kfd.close(); fr.close()
+
+
+def test_accumulator_ring_builds_the_same_frames(gpu_ctx, problems, monkeypatch):
+    """EDSGPU_ACC_RING_MB: a large set of slots may share a ring of accumulators that stays in L2 (frames.cuh); the build then
+    runs in chunks.  Frames and norms are bit-identical to the one-accumulator-per-slot layout; the accumulator of a slot
+    whose ring entry was reused is reported as recycled instead of returning another window's data."""
+    kf, wins = problems["davis240c"]
+    H, W, n = kf["H"], kf["W"], 7
+    E = len(wins[0]["x"])
+    ev = [np.concatenate([wins[i % 2][k] for i in range(n)]) for k in ("x", "y", "pol")]
+
+    def build():
+        fr = edsgpu.Frames(gpu_ctx, H, W, n)
+        edsgpu.event_frames_batch(gpu_ctx, fr, 0, n, *ev, E)
+        return fr
+
+    monkeypatch.delenv("EDSGPU_ACC_RING_MB", raising=False)
+    a = build()
+    monkeypatch.setenv("EDSGPU_ACC_RING_MB", "1")  # 240 x 180 x 8 B = 345 kB per window: a ring of three for seven slots
+    b = build()
+    for s in range(n):
+        ia, na = a.read_level(s, 0)
+        ib, nb = b.read_level(s, 0)
+        assert np.array_equal(ia, ib) and na == nb
+    assert np.array_equal(a.read_accumulator(6), b.read_accumulator(6))  # the last chunk is still in the ring
+    with pytest.raises(edsgpu.EdsGpuError):
+        b.read_accumulator(0)
+    a.close(); b.close()
