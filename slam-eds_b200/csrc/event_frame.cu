@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(256) scatter_events_kernel(const uint16_t* __r
         const bool live = i < E;
         const unsigned active = __ballot_sync(0xffffffffu, live);
         if (!live) continue;
-        const int x = ex[ebase + i], y = ey[ebase + i];
+        const int x = __ldcs(ex + ebase + i), y = __ldcs(ey + ebase + i);  // streaming: every event is read once
         const bool inside = (x < W) && (y < H);
-        const double pol = epol[ebase + i] ? 1.0 : -1.0;  // EventFrame.cpp:318
+        const double pol = __ldcs(epol + ebase + i) ? 1.0 : -1.0;  // EventFrame.cpp:318
         const double wt = use_exp ? exp_weight(i, E) : 1.0;
         double ux = x, uy = y;
         if (mapx != nullptr && inside) {  // EventFrame.cpp:316-317
@@ -123,6 +123,14 @@ __global__ void __launch_bounds__(256) scatter_events_kernel(const uint16_t* __r
     }
 }
 
+// accumulator clear with streaming stores (evict-first in L2): the zeros are consumed by the scatter and the blur of the same
+// build and never again
+__global__ void clear_acc_kernel(ulonglong2* __restrict__ p, size_t n16, long long* __restrict__ tail) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) __stcs(p + i, make_ulonglong2(0ull, 0ull));
+    if (tail && blockIdx.x == 0 && threadIdx.x == 0) *tail = 0;
+}
+
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
     if (i < 0) return -i;
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
                 const int ys = reflect101(min(yb + j, min(y1, H)), H);  // warp-uniform; rows past the strip repeat its last one (unused)
-                cs[j] = (double)__ldg(img + (size_t)ys * W + xs);
+                cs[j] = (double)__ldcs(img + (size_t)ys * W + xs);  // streaming: read once, must not push the tracker's working set out of L2
             }
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
@@ -329,7 +337,16 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
             for (int s = 0; s < fr->capacity; ++s)
                 if (fr->slot_acc[s] >= 0 && fr->slot_acc[s] < n) fr->slot_acc[s] = -1;
         for (int w = 0; w < n; ++w) fr->slot_acc[first_slot + c0 + w] = acc0 + w;
-        EDS_CUDA(ctx, cudaMemsetAsync(fr->acc + (size_t)acc0 * npix, 0, sizeof(long long) * npix * n, bs));
+        if (getenv("EDSGPU_CLEAR_MEMSET") || (((uintptr_t)(fr->acc + (size_t)acc0 * npix)) & 15u)) {
+            EDS_CUDA(ctx, cudaMemsetAsync(fr->acc + (size_t)acc0 * npix, 0, sizeof(long long) * npix * n, bs));
+        } else {
+            const size_t n16 = npix * n / 2, tail = (npix * n) & 1;  // 16-byte stores (the block is 256-byte aligned)
+            const int blocks = (int)std::min<size_t>((n16 + 255) / 256, (size_t)8 * ctx->num_sms);
+            clear_acc_kernel<<<std::max(1, blocks), 256, 0, bs>>>(reinterpret_cast<ulonglong2*>(fr->acc + (size_t)acc0 * npix), n16,
+                                                                   tail ? fr->acc + (size_t)acc0 * npix + 2 * n16 : nullptr);
+            ctx->launches++;
+            EDS_CUDA(ctx, cudaGetLastError());
+        }
         {
             int threads = 256;
             int bx = (E + threads - 1) / threads;
