@@ -297,6 +297,12 @@ def bench_ba(ctx, stream, reps=50):
     for _ in range(20):
         w.calc_l_energy()
     energy_ms = 1e3 * (time.perf_counter() - t0) / 20
+    for _ in range(3):
+        w.solve_system(1e-5, want_step=False)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        w.solve_system(1e-5, want_step=False)
+    solve_ms = 1e3 * (time.perf_counter() - t0) / 20
     w.close()
     return {"workload": "config4: F=7, P=%d, R=%d; top<0> + top<1> + SC accumulate, device-resident" % (P, R),
             "accumulations_per_s": 1e3 / ms, "ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
@@ -309,7 +315,9 @@ def bench_ba(ctx, stream, reps=50):
                                      "accumulate: everything one Gauss-Newton iteration accumulates, 5 launches",
                              "ms": fused_ms, "unfused_ms": lin_ms + ms},
             "after_solve": {"what": "resubstituteF_MT (P steps back to the host) and calcLEnergyF_MT, wall clock per host-synchronous call",
-                            "resubstitute_ms": resub_ms, "calc_l_energy_ms": energy_ms}}
+                            "resubstitute_ms": resub_ms, "calc_l_energy_ms": energy_ms,
+                            "solve_system_ms": solve_ms,
+                            "solve_system": "solveSystemF on the device (three stitches, %d x %d LDL^T, resubstituteF_MT), only x comes back" % (4 + 8 * F, 4 + 8 * F)}}
 
 
 def bench_coarse(ctx, stream, reps=200):

@@ -309,6 +309,20 @@ edsgpu_status edsgpu_ba_top_read(edsgpu_ba* ba, int which, double* acc_out, floa
  * results of top_accumulate(0), top_accumulate(1) and sc_accumulate of this linearisation, which
  * are still on the device.  point_step_out: PointHessian::step, P floats. */
 edsgpu_status edsgpu_ba_resubstitute(edsgpu_ba* ba, const double* x, float* point_step_out);
+/* EnergyFunctional::solveSystemF (EnergyFunctional.cpp:775-912) on the device, default solver mode (setting_solverMode =
+ * SOLVER_FIX_LAMBDA | SOLVER_ORTHOGONALIZE_X_LATER, settings.cpp:60 -- the caller passes the lambda that mode fixes, 1e-5):
+ * the three stitches, HFinal = HL + HM + HA with diag * (1 + lambda) - H_sc / (1 + lambda), bFinal = bL + (bM + HM delta) +
+ * bA - b_sc, the diagonally scaled (4+8F)^2 LDL^T solve, orthogonalize(&x, 0) if a projector is given, then
+ * resubstituteF_MT with the x that never left the device.  Closes a Gauss-Newton iteration of the window optimiser: after
+ * edsgpu_ba_linearize_accumulate, edsgpu_ba_top_accumulate(1) and edsgpu_ba_sc_accumulate this is the only call, and
+ * only x (4+8F doubles) and, on request, the P point steps come back.
+ * HM (n x n, column-major), bM: the marginalisation prior, or both NULL; delta: getStitchedDeltaF() (n) or NULL = 0;
+ * cPrior (4), frame_prior / frame_delta_prior (8F each): the priors of accumulateLF_MT's stitch, or all NULL;
+ * nullspace_projector: N (N^T N)^-1 N^T (n x n) of EnergyFunctional::orthogonalize (:718-772), which depends on the frames'
+ * null spaces only and is made by the host, or NULL (iterations 0 and 1).  Needs edsgpu_ba_set_frames with the adjoints. */
+edsgpu_status edsgpu_ba_solve_system(edsgpu_ba* ba, double lambda, const double* HM, const double* bM, const double* delta,
+                                     const double* cPrior, const double* frame_prior, const double* frame_delta_prior,
+                                     const double* nullspace_projector, double* x_out, float* point_step_out);
 /* EFResidual::fixLinearizationF (EnergyFunctionalStructs.cpp:87-113) for the residuals with
  * select[r] != 0 (NULL = every active residual): res_toZero = resF - J delta with the current
  * deltas, isLinearized = true.  res_toZero_out: R x 8 floats or NULL. */

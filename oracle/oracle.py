@@ -257,6 +257,42 @@ def ba_resubstitute(F, x, adHost, adTarget, host_idx, target_idx, res_begin, fla
     return out
 
 
+def ba_nullspace_projector(nullspaces, delta=1e-5):
+    """N (N^T N)^-1 N^T as EnergyFunctional::orthogonalize builds it (reference src/bundles/EnergyFunctional.cpp:738-760):
+    columns normalised, pseudo-inverse by SVD with singular values below setting_solverModeDelta * max cut, symmetrised."""
+    N = np.stack([np.asarray(v, np.float64) / np.linalg.norm(v) for v in nullspaces], axis=1)
+    U, S, Vt = np.linalg.svd(N, full_matrices=False)
+    Si = np.where(S > delta * S.max(), 1.0 / S, 0.0)
+    Npi = U @ np.diag(Si) @ Vt
+    NNpiT = N @ Npi.T
+    return 0.5 * (NNpiT + NNpiT.T)
+
+
+def ba_solve_system(HA, bA, HL, bL, Hsc, bsc, lam=1e-5, HM=None, bM=None, delta=None, projector=None):
+    """EnergyFunctional::solveSystemF (reference src/bundles/EnergyFunctional.cpp:775-905) in the default solver mode
+    (setting_solverMode = SOLVER_FIX_LAMBDA | SOLVER_ORTHOGONALIZE_X_LATER, settings.cpp:60): the non-orthogonalised, non-SVD
+    branch (:838-893) and orthogonalize(&x, 0) (:898-902) when a projector is given.  numpy float64; np.linalg.solve (LU with
+    partial pivoting) on the lower-triangle-symmetrised matrix stands for Eigen's pivoted LDLT (which reads the lower triangle):
+    both are backward stable on the scaled SPD system.  -> x"""
+    n = len(bA)
+    HM = np.zeros((n, n)) if HM is None else np.asarray(HM, np.float64)
+    bM = np.zeros(n) if bM is None else np.asarray(bM, np.float64)
+    bM_top = bM + (HM @ np.asarray(delta, np.float64) if delta is not None else 0.0)
+    H = np.asarray(HL, np.float64) + HM + np.asarray(HA, np.float64)
+    b = np.asarray(bL, np.float64) + bM_top + np.asarray(bA, np.float64) - np.asarray(bsc, np.float64)
+    H[np.diag_indices(n)] *= (1.0 + lam)
+    H = H - np.asarray(Hsc, np.float64) * (1.0 / (1.0 + lam))
+    sv = 1.0 / np.sqrt(np.diag(H) + 10.0)
+    Hs = sv[:, None] * H * sv[None, :]
+    # Eigen's LDLT reads the LOWER triangle only; H_sc is symmetric only up to float32 rounding (its float accumulators reach
+    # D_ijk and D_ikj^T through different summation orders), so the triangle that is read matters at the 1e-6 level
+    Hs = np.tril(Hs) + np.tril(Hs, -1).T
+    x = sv * np.linalg.solve(Hs, sv * b)
+    if projector is not None:
+        x = x - np.asarray(projector, np.float64) @ x
+    return x
+
+
 def ba_calc_l_energy(F, recs, host_idx, target_idx, res_begin, flags, res_toZero, deltaF, priorF, adHTdeltaF, cDeltaF, cPrior=None,
                      frame_prior=None, frame_delta_prior=None):
     """calcLEnergyF_MT (double)."""

@@ -978,6 +978,109 @@ __global__ void ba_sc_stitch_kernel(int F, const double* __restrict__ accD, cons
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------
+// EnergyFunctional::solveSystemF (EnergyFunctional.cpp:775-912) in its default solver mode (setting_solverMode =
+// SOLVER_FIX_LAMBDA | SOLVER_ORTHOGONALIZE_X_LATER, settings.cpp:60): one CTA, the (4+8F)^2 system in shared memory.
+//   HFinal = HL + HM + HA, bFinal = bL + (bM + HM delta) + bA - b_sc;  diag *= (1 + lambda);  HFinal -= H_sc / (1 + lambda)
+//   SVecI = 1 / sqrt(diag + 10);  x = SVecI . (SVecI HFinal SVecI)^-1 (SVecI . bFinal)   (LDL^T: the scaled matrix is SPD)
+//   optional orthogonalize(&x, 0): x -= N (N^T N)^-1 N^T x with the projector the host made from the frames' null spaces
+// then the per-frame-pair row vectors xAd of resubstituteF_MT (:272-281, float like the reference) for the point pass.
+// ------------------------------------------------------------------------------------------
+constexpr int SOLVE_MAXN = CPARS + 8 * MAXF, SOLVE_LD = SOLVE_MAXN + 1, SOLVE_THREADS = 256;
+
+__global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_kernel(int F, double lambda, const double* __restrict__ HA, const double* __restrict__ bA,
+                                                                  const double* __restrict__ HL, const double* __restrict__ bL,
+                                                                  const double* __restrict__ Hsc, const double* __restrict__ bsc,
+                                                                  const double* __restrict__ HM, const double* __restrict__ bM,
+                                                                  const double* __restrict__ delta, const double* __restrict__ projector,
+                                                                  const double* __restrict__ adHost, const double* __restrict__ adTarget,
+                                                                  double* __restrict__ x_out, float* __restrict__ xAd, float* __restrict__ cstep) {
+    __shared__ double A[SOLVE_MAXN][SOLVE_LD];
+    __shared__ double rhs[SOLVE_MAXN], sv[SOLVE_MAXN], xs[SOLVE_MAXN], col[SOLVE_MAXN];
+    __shared__ float xF[SOLVE_MAXN];
+    const int n = CPARS + 8 * F, tid = threadIdx.x;
+    const double inv1l = 1.0 / (1.0 + lambda);
+    // assemble (column-major inputs; A is symmetric, both triangles are filled)
+    for (int e = tid; e < n * n; e += SOLVE_THREADS) {
+        const int r = e % n, c = e / n;
+        double v = HL[e] + (HM ? HM[e] : 0.0) + HA[e];
+        if (r == c) v *= (1.0 + lambda);
+        A[r][c] = v - Hsc[e] * inv1l;
+    }
+    for (int r = tid; r < n; r += SOLVE_THREADS) {
+        double bm = bM ? bM[r] : 0.0;
+        if (HM && delta)
+            for (int c = 0; c < n; ++c) bm += HM[(size_t)c * n + r] * delta[c];
+        rhs[r] = bL[r] + bm + bA[r] - bsc[r];
+    }
+    __syncthreads();
+    for (int r = tid; r < n; r += SOLVE_THREADS) sv[r] = 1.0 / sqrt(A[r][r] + 10.0);
+    __syncthreads();
+    for (int e = tid; e < n * n; e += SOLVE_THREADS) {
+        const int r = e % n, c = e / n;
+        A[r][c] = sv[r] * A[r][c] * sv[c];
+    }
+    for (int r = tid; r < n; r += SOLVE_THREADS) rhs[r] *= sv[r];
+    __syncthreads();
+    // right-looking LDL^T on the lower triangle: after step k column k holds L(:,k) below the diagonal, A[k][k] = D_k
+    for (int k = 0; k < n; ++k) {
+        const double d = A[k][k];
+        for (int i = k + 1 + tid; i < n; i += SOLVE_THREADS) col[i] = A[i][k];  // the unscaled column: L(i,k) D_k
+        __syncthreads();
+        const int m = n - k - 1;
+        for (int e = tid; e < m * m; e += SOLVE_THREADS) {
+            const int i = k + 1 + e / m, j = k + 1 + e % m;
+            if (j <= i) A[i][j] -= col[i] * (col[j] / d);
+        }
+        for (int i = k + 1 + tid; i < n; i += SOLVE_THREADS) A[i][k] = col[i] / d;
+        __syncthreads();
+    }
+    // L z = rhs, D y = z, L^T w = y: by the first warp (n <= 68 dependent steps, trivially cheap)
+    if (tid < 32) {
+        for (int i = 0; i < n; ++i) {
+            double part = 0.0;
+            for (int j = tid; j < i; j += 32) part += A[i][j] * xs[j];
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (tid == 0) xs[i] = rhs[i] - part;
+            __syncwarp();
+        }
+        for (int i = tid; i < n; i += 32) xs[i] /= A[i][i];
+        __syncwarp();
+        for (int i = n - 1; i >= 0; --i) {
+            double part = 0.0;
+            for (int j = i + 1 + tid; j < n; j += 32) part += A[j][i] * xs[j];
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (tid == 0) xs[i] -= part;
+            __syncwarp();
+        }
+        for (int i = tid; i < n; i += 32) xs[i] *= sv[i];
+    }
+    __syncthreads();
+    if (projector) {  // orthogonalize(&x, 0)
+        for (int r = tid; r < n; r += SOLVE_THREADS) {
+            double p = 0.0;
+            for (int c = 0; c < n; ++c) p += projector[(size_t)c * n + r] * xs[c];
+            col[r] = xs[r] - p;
+        }
+        __syncthreads();
+        for (int r = tid; r < n; r += SOLVE_THREADS) xs[r] = col[r];
+        __syncthreads();
+    }
+    for (int r = tid; r < n; r += SOLVE_THREADS) { x_out[r] = xs[r]; xF[r] = (float)xs[r]; }
+    __syncthreads();
+    // xAd[F*h + t] = xF_h^T adHostF[h + F*t] + xF_t^T adTargetF[h + F*t], float in the reference's order (no FMA contraction)
+    for (int e = tid; e < F * F * 8; e += SOLVE_THREADS) {
+        const int c = e % 8, ht = e / 8, h = ht / F, t = ht % F;
+        const double* AH = adHost + 64 * (size_t)(h + F * t);
+        const double* AT = adTarget + 64 * (size_t)(h + F * t);
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < 8; ++k) a = __fadd_rn(a, __fmul_rn(xF[CPARS + 8 * h + k], (float)AH[c * 8 + k]));
+        for (int k = 0; k < 8; ++k) b = __fadd_rn(b, __fmul_rn(xF[CPARS + 8 * t + k], (float)AT[c * 8 + k]));
+        xAd[8 * (F * h + t) + c] = __fadd_rn(a, b);
+    }
+    if (tid < CPARS) cstep[tid] = xF[tid];
+}
+
 // ==========================================================================================
 // host side
 // ==========================================================================================
@@ -1008,6 +1111,7 @@ struct edsgpu_ba {
     float calib[4] = {0, 0, 0, 0};
     bool lin_inputs_set = false;
     unsigned images_set = 0;  // bit per frame
+    double* solve_block = nullptr;  // edsgpu_ba_solve_system: three stitched systems, HM, bM, delta, projector, x (device)
     unsigned* grid_bar = nullptr;   // arrival counter of the accumulation kernels' grid barrier (device, only grows)
     unsigned bar_count = 0;         // its value after the launches queued so far
     bool have_top[2] = {false, false}, have_sc = false;  // which accumulations of the current linearisation are on the device
@@ -1180,6 +1284,7 @@ void edsgpu_ba_destroy(edsgpu_ba* w) {
     if (w->images) cudaFree(w->images);
     if (w->lin_block) cudaFree(w->lin_block);
     if (w->post_block) cudaFree(w->post_block);
+    if (w->solve_block) cudaFree(w->solve_block);
     delete w;
 }
 
@@ -1571,6 +1676,68 @@ edsgpu_status edsgpu_ba_fix_linearization(edsgpu_ba* w, const uint8_t* select, f
     w->have_top[0] = w->have_top[1] = w->have_sc = false;  // flags (isLinearized) and res_toZero changed under every accumulation
     if (res_toZero_out) EDS_CUDA(ctx, cudaMemcpyAsync(res_toZero_out, w->res_toZero, 32 * (size_t)w->R, cudaMemcpyDeviceToHost, ctx->stream));
     if (select || res_toZero_out) EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_ba_solve_system(edsgpu_ba* w, double lambda, const double* HM, const double* bM, const double* delta, const double* cPrior,
+                                     const double* frame_prior, const double* frame_delta_prior, const double* nullspace_projector, double* x_out,
+                                     float* point_step_out) {
+    if (!w) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = w->ctx;
+    const int F = w->F, n = CPARS + 8 * F;
+    const size_t F2 = (size_t)F * F, nn = (size_t)n * n;
+    EDS_REQUIRE(ctx, x_out != nullptr, "ba_solve_system: null x_out");
+    EDS_REQUIRE(ctx, (HM == nullptr) == (bM == nullptr), "ba_solve_system: give HM and bM or neither");
+    EDS_REQUIRE(ctx, (cPrior == nullptr) == (frame_prior == nullptr) && (cPrior == nullptr) == (frame_delta_prior == nullptr),
+                "ba_solve_system: give all three priors or none");
+    EDS_REQUIRE(ctx, w->adHost_h.size() == 64 * F2 && w->adTarget_h.size() == 64 * F2, "ba_solve_system: call edsgpu_ba_set_frames with the adjoints first");
+    EDS_REQUIRE(ctx, w->have_top[0] && w->have_top[1] && w->have_sc, "ba_solve_system: needs the active, the linearized and the Schur accumulation of this linearisation");
+    DeviceGuard g(ctx->device);
+    edsgpu_status st = ensure_post_block(w);
+    if (st != EDSGPU_OK) return st;
+    // device block: three stitched systems (H n*n, b n) | HM | bM | delta | projector | x
+    const size_t sys = nn + (size_t)n, total = 3 * sys + nn + n + n + nn + n;
+    if (!w->solve_block) {
+        cudaError_t e = cudaMalloc(&w->solve_block, sizeof(double) * total);
+        if (e != cudaSuccess) return edsgpu_fail(ctx, e == cudaErrorMemoryAllocation ? EDSGPU_OUT_OF_MEMORY : EDSGPU_CUDA_ERROR, cudaGetErrorString(e));
+    }
+    double* S = w->solve_block;
+    double *HAd = S, *bAd = S + nn, *HLd = S + sys, *bLd = S + sys + nn, *Hsd = S + 2 * sys, *bsd = S + 2 * sys + nn;
+    double *HMd = S + 3 * sys, *bMd = HMd + nn, *dld = bMd + n, *prd = dld + n, *xd = prd + nn;
+    cudaStream_t s = ctx->stream;
+    if (HM) {
+        EDS_CUDA(ctx, cudaMemcpyAsync(HMd, HM, 8 * nn, cudaMemcpyHostToDevice, s));
+        EDS_CUDA(ctx, cudaMemcpyAsync(bMd, bM, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+        if (delta) EDS_CUDA(ctx, cudaMemcpyAsync(dld, delta, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+    }
+    if (nullspace_projector) EDS_CUDA(ctx, cudaMemcpyAsync(prd, nullspace_projector, 8 * nn, cudaMemcpyHostToDevice, s));
+    double* pr = w->prior_buf;  // cPrior(4) | frame_prior(8F) | frame_delta_prior(8F)
+    if (cPrior) {
+        EDS_CUDA(ctx, cudaMemcpyAsync(pr, cPrior, 32, cudaMemcpyHostToDevice, s));
+        EDS_CUDA(ctx, cudaMemcpyAsync(pr + 4, frame_prior, 64 * (size_t)F, cudaMemcpyHostToDevice, s));
+        EDS_CUDA(ctx, cudaMemcpyAsync(pr + 4 + 8 * F, frame_delta_prior, 64 * (size_t)F, cudaMemcpyHostToDevice, s));
+    }
+    // accumulateAF_MT / accumulateLF_MT / accumulateSCF_MT's stitches (:790-800), results stay on the device
+    ba_top_stitch_kernel<<<F * F, 64, 0, s>>>(F, w->acc[0], w->adHost, w->adTarget, 0, pr, w->cDeltaF, pr + 4, pr + 4 + 8 * F, HAd, bAd);
+    ba_top_symmetrise_kernel<<<F * F, 64, 0, s>>>(F, 0, pr + 4, HAd);
+    ba_top_stitch_kernel<<<F * F, 64, 0, s>>>(F, w->acc[1], w->adHost, w->adTarget, cPrior ? 1 : 0, pr, w->cDeltaF, pr + 4, pr + 4 + 8 * F, HLd, bLd);
+    ba_top_symmetrise_kernel<<<F * F, 64, 0, s>>>(F, cPrior ? 1 : 0, pr + 4, HLd);
+    ba_sc_stitch_kernel<<<F * F, 64, 0, s>>>(F, w->accD, w->accE, w->accEB, w->accHcc, w->accbc, w->adHost, w->adTarget, Hsd, bsd);
+    char* pb = (char*)w->post_block;
+    float* d_xAd = (float*)pb;
+    float* d_cstep = (float*)(pb + align_up(32 * F2, 256));
+    float* d_step = (float*)(pb + align_up(32 * F2, 256) + 256);
+    ba_solve_kernel<<<1, SOLVE_THREADS, 0, s>>>(F, lambda, HAd, bAd, HLd, bLd, Hsd, bsd, HM ? HMd : nullptr, HM ? bMd : nullptr,
+                                                (HM && delta) ? dld : nullptr, nullspace_projector ? prd : nullptr, w->adHost, w->adTarget, xd, d_xAd,
+                                                d_cstep);
+    // resubstituteF_MT(x) (:907-909): the point steps from the device-resident x
+    ba_resubstitute_kernel<<<(w->P + 127) / 128, 128, 0, s>>>(w->F, w->P, w->res_begin, w->host_idx, w->target_idx, w->flags, w->JpJdF, w->bdSum,
+                                                              w->Hcd[0], w->Hcd[1], w->HdiF, d_xAd, d_cstep, d_step);
+    ctx->launches += 7;
+    EDS_CUDA(ctx, cudaGetLastError());
+    EDS_CUDA(ctx, cudaMemcpyAsync(x_out, xd, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (point_step_out) EDS_CUDA(ctx, cudaMemcpyAsync(point_step_out, d_step, 4 * (size_t)w->P, cudaMemcpyDeviceToHost, s));
+    EDS_CUDA(ctx, cudaStreamSynchronize(s));
     return EDSGPU_OK;
 }
 

@@ -35,7 +35,7 @@ SYMBOLS = [
     "edsgpu_tracker_evaluate",
     "edsgpu_ba_create", "edsgpu_ba_destroy", "edsgpu_ba_set_residuals", "edsgpu_ba_set_points", "edsgpu_ba_set_frames",
     "edsgpu_ba_top_accumulate", "edsgpu_ba_top_stitch", "edsgpu_ba_sc_accumulate", "edsgpu_ba_sc_stitch", "edsgpu_ba_get_jpjd",
-    "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_linearize_accumulate", "edsgpu_ba_top_read", "edsgpu_ba_get_residuals",
+    "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_linearize_accumulate", "edsgpu_ba_top_read", "edsgpu_ba_solve_system", "edsgpu_ba_get_residuals",
     "edsgpu_ba_resubstitute", "edsgpu_ba_fix_linearization", "edsgpu_ba_calc_l_energy",
     "edsgpu_coarse_create", "edsgpu_coarse_destroy", "edsgpu_coarse_set_level", "edsgpu_coarse_set_reference",
     "edsgpu_coarse_set_new_frame", "edsgpu_coarse_calc_res_gs", "edsgpu_coarse_track",
@@ -455,6 +455,19 @@ class BaWindow:
         step = np.zeros(self.P, np.float32)
         self.ctx.check(self.ctx.lib.edsgpu_ba_resubstitute(self.h, _ptr(x, C.c_double), _ptr(step, C.c_float)))
         return step
+
+    def solve_system(self, lam=1e-5, HM=None, bM=None, delta=None, cPrior=None, frame_prior=None, frame_delta_prior=None, projector=None,
+                     want_step=True):
+        """solveSystemF (default solver mode) + resubstituteF_MT on the device -> (x, point steps)"""
+        f64 = lambda a, order="C": np.ascontiguousarray(np.asarray(a, np.float64).ravel(order=order)) if a is not None else None  # noqa: E731
+        hm, pr = f64(HM, "F"), f64(projector, "F")
+        bm, dl, cp, fp, fd = f64(bM), f64(delta), f64(cPrior), f64(frame_prior), f64(frame_delta_prior)
+        x = np.zeros(self.n)
+        step = np.zeros(self.P, np.float32) if want_step else None
+        self.ctx.check(self.ctx.lib.edsgpu_ba_solve_system(self.h, C.c_double(lam), _ptr(hm, C.c_double), _ptr(bm, C.c_double), _ptr(dl, C.c_double),
+                                                           _ptr(cp, C.c_double), _ptr(fp, C.c_double), _ptr(fd, C.c_double), _ptr(pr, C.c_double),
+                                                           _ptr(x, C.c_double), _ptr(step, C.c_float)))
+        return x, step
 
     def fix_linearization(self, select=None, want_output=True):
         sel = np.ascontiguousarray(select, np.uint8) if select is not None else None

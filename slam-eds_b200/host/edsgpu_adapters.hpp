@@ -307,6 +307,16 @@ class HessianAccumulators {
         H.assign((size_t)n * n, 0.0); b.assign(n, 0.0);
         ctx_.check(edsgpu_ba_top_stitch(ba_, 1, 1, cPrior, framePrior, frameDeltaPrior, H.data(), b.data()));
     }
+    // solveSystemF(iteration, lambda, HCalib) (EnergyFunctional.cpp:775-912, default solver mode) after the three accumulations:
+    // stitches, damped Schur-reduced system, scaled LDL^T, orthogonalize(&x, 0) when a projector is given, resubstituteF_MT
+    void solveSystemF(double lambda, const double* HM, const double* bM, const double* stitchedDeltaF, const double cPrior[4],
+                      const double* framePrior, const double* frameDeltaPrior, const double* nullspaceProjector, std::vector<double>& x,
+                      std::vector<float>* pointStep = nullptr, int P = 0) {
+        x.assign(n, 0.0);
+        if (pointStep) pointStep->assign(P, 0.f);
+        ctx_.check(edsgpu_ba_solve_system(ba_, lambda, HM, bM, stitchedDeltaF, cPrior, framePrior, frameDeltaPrior, nullspaceProjector, x.data(),
+                                          pointStep ? pointStep->data() : nullptr));
+    }
     // accumulateSCF_MT(H, b): addPoint(p, shiftPriorToZero = true) + stitchDoubleMT; also EFPoint::HdiF, bdSumF
     void accumulateSCF_MT(std::vector<double>& H, std::vector<double>& b, std::vector<float>* HdiF = nullptr, std::vector<float>* bdSumF = nullptr, int P = 0) {
         if (HdiF) HdiF->assign(P, 0.f);

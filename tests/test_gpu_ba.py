@@ -287,6 +287,35 @@ def test_back_substitution_energy_and_fix_linearization(solved):
     w.set_residuals(pb["recs"], pb["flags"], rtz)  # restore for the other tests of the module
 
 
+@pytest.mark.parametrize("with_prior", [False, True])
+def test_device_solve_closes_the_gauss_newton_iteration(solved, with_prior):
+    """edsgpu_ba_solve_system = EnergyFunctional::solveSystemF (default solver mode) + resubstituteF_MT without x leaving the
+    device: against the restatement fed with the GPU's own stitched systems, and the point steps against resubstitute(x)."""
+    pb, rtz, w = solved
+    F, n = pb["F"], 4 + 8 * pb["F"]
+    rng = np.random.default_rng(23)
+    w.top_accumulate(0); w.top_accumulate(1); w.sc_accumulate(True)
+    pri = (pb["cPrior"], pb["frame_prior"], pb["frame_delta_prior"]) if with_prior else (None, None, None)
+    HA, bA = w.top_stitch(0)
+    HL, bL = w.top_stitch(1, with_prior, *pri)
+    Hsc, bsc = w.sc_stitch()
+    HM = bM = delta = P = None
+    if with_prior:
+        a = rng.normal(size=(n, n))
+        HM = 1e-2 * np.abs(HA).max() * (a @ a.T) / n
+        bM = 1e-2 * np.abs(bA).max() * rng.normal(size=n)
+        delta = 1e-3 * rng.normal(size=n)
+        P = O.ba_nullspace_projector([rng.normal(size=n) for _ in range(7)])
+    x, step = w.solve_system(1e-5, HM, bM, delta, *pri, projector=P)
+    ref = O.ba_solve_system(HA, bA, HL, bL, Hsc, bsc, 1e-5, HM, bM, delta, P)
+    assert np.isfinite(x).all() and np.abs(x).max() > 0
+    assert np.abs(x - ref).max() <= 1e-8 * np.abs(ref).max()
+    # the point steps are those of resubstituteF_MT for this x (same float arithmetic on the device as on the host path)
+    assert np.array_equal(step, w.resubstitute(x))
+    with pytest.raises(edsgpu.EdsGpuError):
+        w.solve_system(1e-5, HM=np.eye(n))  # HM without bM
+
+
 def test_gpu_against_committed_ba_fixture(gpu_ctx):
     """The CUDA path against tests/golden/ba_small.npz, without rebuilding or calling the oracle."""
     import os

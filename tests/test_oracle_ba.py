@@ -303,3 +303,36 @@ def test_oracle_against_committed_ba_fixture():
     e = O.ba_calc_l_energy(F, recs, pb["host_idx"], pb["target_idx"], pb["res_begin"], pb["flags"], rtz, pb["deltaF"], pb["priorF"],
                            pb["adHTdeltaF"], pb["cDeltaF"], pb["cPrior"], pb["frame_prior"], pb["frame_delta_prior"])
     assert e == float(g["l_energy"])
+
+
+def test_solve_system_restatement_properties():
+    """solveSystemF (EnergyFunctional.cpp:775-905, default solver mode): the restatement solves the system it states (residual of
+    the damped, Schur-reduced equations at rounding level), the marginalisation prior enters as bM + HM delta, and the
+    null-space projector is an orthogonal projector that removes exactly the given directions from x."""
+    rng = np.random.default_rng(3)
+    n = 4 + 8 * 5
+
+    def spd(scale):
+        a = rng.normal(size=(n, n))
+        return scale * (a @ a.T + n * np.eye(n))
+
+    HA, HL, HM, Hsc = spd(1.0), spd(0.3), spd(0.1), spd(0.02)
+    bA, bL, bM, bsc, delta = (rng.normal(size=n) for _ in range(5))
+    lam = 1e-5
+    x = O.ba_solve_system(HA, bA, HL, bL, Hsc, bsc, lam, HM, bM, delta)
+    Hf = HL + HM + HA
+    Hf[np.diag_indices(n)] *= 1 + lam
+    Hf -= Hsc / (1 + lam)
+    bf = bL + (bM + HM @ delta) + bA - bsc
+    assert np.abs(Hf @ x - bf).max() < 1e-9 * np.abs(bf).max()
+    x0 = O.ba_solve_system(HA, bA, HL, bL, Hsc, bsc, lam)
+    H0 = HL + HA
+    H0[np.diag_indices(n)] *= 1 + lam
+    H0 -= Hsc / (1 + lam)
+    assert np.abs(H0 @ x0 - (bL + bA - bsc)).max() < 1e-9 * np.abs(bL + bA - bsc).max()  # no marginalisation prior
+    ns = [rng.normal(size=n) for _ in range(7)]
+    P = O.ba_nullspace_projector(ns)
+    assert np.allclose(P, P.T, atol=1e-14) and np.allclose(P @ P, P, atol=1e-12) and abs(np.trace(P) - 7) < 1e-10
+    xo = O.ba_solve_system(HA, bA, HL, bL, Hsc, bsc, lam, HM, bM, delta, projector=P)
+    assert max(abs(np.dot(v, xo)) / np.linalg.norm(v) for v in ns) < 1e-12 * np.linalg.norm(x)
+    assert np.allclose(xo, x - P @ x, atol=1e-15)
