@@ -1334,6 +1334,7 @@ edsgpu_status edsgpu_ba_set_frames(edsgpu_ba* w, const float* adHTdeltaF, const 
 }
 
 edsgpu_status edsgpu_ba_top_accumulate(edsgpu_ba* w, int mode, double* acc_out, float* Hdd_out, float* bd_out, float* Hcd_out, int64_t* nres_out) {
+    EDS_RANGE("edsgpu_ba_top_accumulate");
     if (!w) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = w->ctx;
     EDS_REQUIRE(ctx, mode >= 0 && mode <= 2, "ba_top_accumulate: mode must be 0 (active), 1 (linearized) or 2 (marginalize)");
@@ -1421,6 +1422,7 @@ edsgpu_status edsgpu_ba_top_stitch(edsgpu_ba* w, int which, int use_prior, const
 
 edsgpu_status edsgpu_ba_sc_accumulate(edsgpu_ba* w, int shift_prior_to_zero, double* accD, double* accE, double* accEB, double* accHcc,
                                       double* accbc, float* HdiF_out, float* bdSum_out) {
+    EDS_RANGE("edsgpu_ba_sc_accumulate");
     if (!w) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = w->ctx;
     DeviceGuard g(ctx->device);
@@ -1543,6 +1545,7 @@ edsgpu_status edsgpu_ba_set_linearize_inputs(edsgpu_ba* w, const float* precalc,
 
 edsgpu_status edsgpu_ba_linearize(edsgpu_ba* w, const uint8_t* state_in, const uint8_t* linearized, const float* res_toZero,
                                   int32_t* state_out, float* energy_out) {
+    EDS_RANGE("edsgpu_ba_linearize");
     if (!w) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = w->ctx;
     EDS_REQUIRE(ctx, w->lin_inputs_set, "ba_linearize: call edsgpu_ba_set_linearize_inputs first");
@@ -1568,6 +1571,7 @@ edsgpu_status edsgpu_ba_linearize(edsgpu_ba* w, const uint8_t* state_in, const u
 
 edsgpu_status edsgpu_ba_linearize_accumulate(edsgpu_ba* w, const uint8_t* state_in, const uint8_t* linearized, const float* res_toZero,
                                              int write_records, int32_t* state_out, float* energy_out) {
+    EDS_RANGE("edsgpu_ba_linearize_accumulate");
     if (!w) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = w->ctx;
     EDS_REQUIRE(ctx, w->lin_inputs_set, "ba_linearize_accumulate: call edsgpu_ba_set_linearize_inputs first");
@@ -1682,6 +1686,7 @@ edsgpu_status edsgpu_ba_fix_linearization(edsgpu_ba* w, const uint8_t* select, f
 edsgpu_status edsgpu_ba_solve_system(edsgpu_ba* w, double lambda, const double* HM, const double* bM, const double* delta, const double* cPrior,
                                      const double* frame_prior, const double* frame_delta_prior, const double* nullspace_projector, double* x_out,
                                      float* point_step_out) {
+    EDS_RANGE("edsgpu_ba_solve_system");
     if (!w) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = w->ctx;
     const int F = w->F, n = CPARS + 8 * F;

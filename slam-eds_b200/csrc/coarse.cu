@@ -305,6 +305,7 @@ edsgpu_status edsgpu_coarse_set_new_frame(edsgpu_coarse* c, int lvl, const float
 
 edsgpu_status edsgpu_coarse_calc_res_gs(edsgpu_coarse* c, int lvl, const double R[9], const double t[3], const float affLL[2], float b0,
                                         float cutoffTH, double rs[6], double H[64], double b[8]) {
+    EDS_RANGE("edsgpu_coarse_calc_res_gs");
     if (!c) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = c->ctx;
     EDS_REQUIRE(ctx, lvl >= 0 && lvl < (int)c->levels.size() && R && t && affLL && rs, "coarse_calc_res_gs: bad arguments");
@@ -689,6 +690,7 @@ extern "C" {
 edsgpu_status edsgpu_coarse_track(edsgpu_coarse* c, int coarsest_lvl, double R[9], double t[3], double aff_g2l[2], const double ref_aff_g2l[2],
                                   float ref_exposure, float new_exposure, const double min_res_for_abort[5], double last_residuals[5],
                                   double last_flow[3], int* evaluations_out) {
+    EDS_RANGE("edsgpu_coarse_track");
     if (!c) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = c->ctx;
     EDS_REQUIRE(ctx, R && t && aff_g2l && ref_aff_g2l && last_residuals && last_flow, "coarse_track: null argument");

@@ -1,6 +1,7 @@
 // Shared host-side plumbing of libedsgpu.so (context, error handling, buffers).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost a pointer test unless a profiler is attached
 #include <stdint.h>
 
 #include <cstdio>
@@ -59,6 +60,13 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+// NVTX range over an entry point of the C ABI (shows up in Nsight Systems timelines; SURVEY.md section 5, tracing)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define EDS_RANGE(name) NvtxRange nvtx_range__(name)
 
 edsgpu_status edsgpu_ensure_pinned(edsgpu_ctx* ctx, size_t bytes);
 edsgpu_status edsgpu_ensure_scratch(edsgpu_ctx* ctx, size_t bytes);

@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(MORPH_THREADS) morph_level_kernel(const cudaTe
 
 edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, int count, const edsgpu_lut* lut,
                             const uint16_t* x_dev, const uint16_t* y_dev, const uint8_t* pol_dev, int E, int mode, int use_exp, float sigma) {
+    EDS_RANGE("edsgpu_event_frame_create (launch)");
     const int H = fr->H, W = fr->W;
     const size_t npix = (size_t)H * W;
     cudaStream_t bs = fr->build_stream;

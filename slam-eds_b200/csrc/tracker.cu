@@ -1849,6 +1849,7 @@ extern "C" {
 edsgpu_status edsgpu_keyframe_create(edsgpu_ctx* ctx, int num_points, const double* grad_xy, const double* norm_xy, const double* idp,
                                      const double* weights, int height, int width, double fx, double fy, double cx, double cy, int num_blocks,
                                      edsgpu_keyframe** out) {
+    EDS_RANGE("edsgpu_keyframe_create");
     if (!ctx || !out) return EDSGPU_INVALID_ARGUMENT;
     EDS_REQUIRE(ctx, grad_xy && norm_xy && idp && weights, "keyframe_create: null array");
     EDS_REQUIRE(ctx, height > 0 && width > 0, "keyframe_create: bad image size");
@@ -2049,6 +2050,7 @@ void edsgpu_batch_destroy(edsgpu_batch* b) {
 }
 
 edsgpu_status edsgpu_batch_optimize(edsgpu_batch* b) {
+    EDS_RANGE("edsgpu_batch_optimize");
     if (!b) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = b->ctx;
     DeviceGuard g(ctx->device);
@@ -2149,6 +2151,7 @@ edsgpu_status edsgpu_tracker_set_level_iterations(edsgpu_tracker* tr, const int*
 edsgpu_status edsgpu_tracker_optimize_level(edsgpu_tracker* tr, const edsgpu_keyframe* kf, const edsgpu_frames* frames, int slot, int level,
                                             double px[3], double qx[4], double vx[6], double* residuals_out, double* next_loss_param_out,
                                             edsgpu_tracker_info* info) {
+    EDS_RANGE("edsgpu_tracker_optimize");
     if (!tr) return EDSGPU_INVALID_ARGUMENT;
     edsgpu_ctx* ctx = tr->ctx;
     EDS_REQUIRE(ctx, kf && frames, "tracker_optimize: null handle");
