@@ -349,6 +349,18 @@ edsgpu_status edsgpu_coarse_set_level(edsgpu_coarse* coarse, int lvl, int width,
 /* setCoarseTrackingRef / makeCoarseDepthL0 output (:103-283): pc_u, pc_v, pc_idepth, pc_color of level lvl. */
 edsgpu_status edsgpu_coarse_set_reference(edsgpu_coarse* coarse, int lvl, int n, const float* pc_u, const float* pc_v,
                                           const float* pc_idepth, const float* pc_color);
+/* CoarseTracker::makeCoarseDepthL0 (:127-283) on the device: the reference frame's inverse-depth map from the points projected
+ * into it (proj_u, proj_v, proj_idepth = PointFrameResidual::centerProjectedTo of the n points whose last residual is IN, HdiF =
+ * EFPoint::HdiF), summed down the pyramid, dilated by one pixel, normalised and compacted in scan-line order into pc_u / pc_v /
+ * pc_idepth / pc_color of levels 0 .. levels_used-1 -- the level's reference point cloud is then in place for
+ * edsgpu_coarse_calc_res_gs / edsgpu_coarse_track, as after edsgpu_coarse_set_reference.  Needs edsgpu_coarse_set_level (levels
+ * must halve, makeK) and edsgpu_coarse_set_reference_frame (lastRef->dIp[lvl], height*width Vec3f) for every level used.
+ * pc_n_out: pc_n of every level or NULL; edsgpu_coarse_get_reference reads a level's point cloud back (any pointer may be NULL). */
+edsgpu_status edsgpu_coarse_set_reference_frame(edsgpu_coarse* coarse, int lvl, const float* dI);
+edsgpu_status edsgpu_coarse_make_depth_l0(edsgpu_coarse* coarse, int levels_used, int n, const float* proj_u, const float* proj_v,
+                                          const float* proj_idepth, const float* HdiF, int* pc_n_out);
+edsgpu_status edsgpu_coarse_get_reference(edsgpu_coarse* coarse, int lvl, int* n_out, float* pc_u, float* pc_v, float* pc_idepth,
+                                          float* pc_color);
 /* newFrame->dIp[lvl]: height*width Vec3f {I, dx, dy}. */
 edsgpu_status edsgpu_coarse_set_new_frame(edsgpu_coarse* coarse, int lvl, const float* dI);
 /* R (row-major), t: refToNew; affLL = AffLight::fromToVecExposure(...) as floats, b0 = lastRef_aff_g2l.b.

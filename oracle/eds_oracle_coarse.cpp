@@ -286,4 +286,80 @@ int eds_oracle_coarse_track(int coarsest_lvl, const int* wl, const int* hl, cons
     return 1;
 }
 
+
+// CoarseTracker::makeCoarseDepthL0, src/tracking/CoarseTracker.cpp:127-283: the reference frame's inverse-depth map from the
+// active points projected into it (weighted by their Hessian inverse), summed down the pyramid, dilated by one pixel where a
+// pixel has no point (diagonal neighbours on levels 0-1, axis neighbours below), normalised, and compacted in scan-line order
+// into the per-level point cloud pc_u / pc_v / pc_idepth / pc_color that calcRes reads.  float arithmetic in the reference's
+// order.  One deviation: the dilation loops of the reference index one element before / past the image at its first and last
+// pixel (i - 1 - wl = -1, i + 1 + wl = w*h); such reads count as "no point" here.
+//   cu, cv, cid: PointFrameResidual::centerProjectedTo of the n points whose last residual is IN; HdiF: EFPoint::HdiF
+//   dIRef[lvl]: lastRef->dIp[lvl], h*w Vec3f;  out per level: idepth, weightSums (h*w), pc_* (capacity h*w), pc_n
+void eds_oracle_make_coarse_depth_l0(int L, const int* w, const int* h, int n, const float* cu, const float* cv, const float* cid, const float* HdiF,
+                                     const float* const* dIRef, float* const* idepth, float* const* weightSums, float* const* pc_u,
+                                     float* const* pc_v, float* const* pc_idepth, float* const* pc_color, int* pc_n) {
+    memset(idepth[0], 0, sizeof(float) * w[0] * h[0]);
+    memset(weightSums[0], 0, sizeof(float) * w[0] * h[0]);
+    for (int p = 0; p < n; ++p) {
+        const int u = (int)(cu[p] + 0.5f), v = (int)(cv[p] + 0.5f);
+        const float weight = sqrtf((float)(1e-3 / ((double)HdiF[p] + 1e-12)));
+        idepth[0][u + w[0] * v] += cid[p] * weight;
+        weightSums[0][u + w[0] * v] += weight;
+    }
+    for (int lvl = 1; lvl < L; ++lvl) {
+        const int wl = w[lvl], hl = h[lvl], wlm1 = w[lvl - 1];
+        for (int y = 0; y < hl; ++y)
+            for (int x = 0; x < wl; ++x) {
+                const int b = 2 * x + 2 * y * wlm1;
+                idepth[lvl][x + y * wl] = idepth[lvl - 1][b] + idepth[lvl - 1][b + 1] + idepth[lvl - 1][b + wlm1] + idepth[lvl - 1][b + wlm1 + 1];
+                weightSums[lvl][x + y * wl] = weightSums[lvl - 1][b] + weightSums[lvl - 1][b + 1] + weightSums[lvl - 1][b + wlm1] + weightSums[lvl - 1][b + wlm1 + 1];
+            }
+    }
+    for (int lvl = 0; lvl < L; ++lvl) {
+        const int wl = w[lvl], total = w[lvl] * h[lvl], wh = total - wl;
+        float* ws = weightSums[lvl];
+        float* id = idepth[lvl];
+        float* bak = new float[total];
+        memcpy(bak, ws, sizeof(float) * total);
+        const int off[2][4] = {{1 + wl, -1 - wl, wl - 1, -wl + 1}, {1, -1, wl, -wl}};
+        const int* o = off[lvl < 2 ? 0 : 1];
+        for (int i = wl; i < wh; ++i)
+            if (bak[i] <= 0) {
+                float sum = 0, num = 0, numn = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const int j = i + o[k];
+                    if (j >= 0 && j < total && bak[j] > 0) { sum += id[j]; num += bak[j]; numn++; }
+                }
+                if (numn > 0) { id[i] = sum / numn; ws[i] = num / numn; }
+            }
+        delete[] bak;
+    }
+    for (int lvl = 0; lvl < L; ++lvl) {
+        const int wl = w[lvl], hl = h[lvl];
+        float* ws = weightSums[lvl];
+        float* id = idepth[lvl];
+        int cnt = 0;
+        for (int y = 2; y < hl - 2; ++y)
+            for (int x = 2; x < wl - 2; ++x) {
+                const int i = x + y * wl;
+                if (ws[i] > 0) {
+                    id[i] /= ws[i];
+                    pc_u[lvl][cnt] = (float)x;
+                    pc_v[lvl][cnt] = (float)y;
+                    pc_idepth[lvl][cnt] = id[i];
+                    pc_color[lvl][cnt] = dIRef[lvl][3 * i];
+                    if (!std::isfinite(pc_color[lvl][cnt]) || !(id[i] > 0)) {
+                        id[i] = -1;
+                        continue;
+                    }
+                    cnt++;
+                } else {
+                    id[i] = -1;
+                }
+                ws[i] = 1;
+            }
+        pc_n[lvl] = cnt;
+    }
+}
+
 }  // extern "C"

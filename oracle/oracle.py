@@ -455,3 +455,28 @@ def coarse_track(pb, coarsest_lvl, R, t, aff=(0.0, 0.0), ref_aff=(0.0, 0.0), ref
            arr_of_ptrs("pc_idepth"), arr_of_ptrs("pc_color"), _p(Rm, C.c_double), _p(tv, C.c_double), _p(af, C.c_double), _p(raf, C.c_double),
            C.c_float(ref_exposure), C.c_float(new_exposure), _p(mra, C.c_double), _p(lr, C.c_double), _p(lf, C.c_double), C.byref(ev))
     return dict(ok=bool(ok), R=Rm.reshape(3, 3), t=tv, aff=af, last_residuals=lr, last_flow=lf, evaluations=ev.value)
+
+
+def make_coarse_depth_l0(levels, cu, cv, cid, HdiF):
+    """CoarseTracker::makeCoarseDepthL0.  levels: list of dict(w, h, dI_ref (h, w, 3) float32).  -> list of dict(n, pc_u, pc_v,
+    pc_idepth, pc_color, idepth, weightSums) per level."""
+    L = len(levels)
+    w = (C.c_int * L)(*[int(l["w"]) for l in levels])
+    h = (C.c_int * L)(*[int(l["h"]) for l in levels])
+    cu, cv, cid, HdiF = _f32(cu), _f32(cv), _f32(cid), _f32(HdiF)
+    dI = [_f32(l["dI_ref"]) for l in levels]
+    bufs = {k: [np.zeros(int(l["w"]) * int(l["h"]), np.float32) for l in levels] for k in ("idepth", "weightSums", "pc_u", "pc_v", "pc_idepth", "pc_color")}
+    PP = C.POINTER(C.c_float) * L
+    ptrs = {k: PP(*[_p(a, C.c_float) for a in v]) for k, v in bufs.items()}
+    dIp = PP(*[_p(a, C.c_float) for a in dI])
+    pc_n = (C.c_int * L)()
+    lib().eds_oracle_make_coarse_depth_l0(C.c_int(L), w, h, C.c_int(len(cu)), _p(cu, C.c_float), _p(cv, C.c_float), _p(cid, C.c_float),
+                                          _p(HdiF, C.c_float), dIp, ptrs["idepth"], ptrs["weightSums"], ptrs["pc_u"], ptrs["pc_v"],
+                                          ptrs["pc_idepth"], ptrs["pc_color"], pc_n)
+    out = []
+    for i, l in enumerate(levels):
+        n = pc_n[i]
+        out.append(dict(n=n, pc_u=bufs["pc_u"][i][:n].copy(), pc_v=bufs["pc_v"][i][:n].copy(), pc_idepth=bufs["pc_idepth"][i][:n].copy(),
+                        pc_color=bufs["pc_color"][i][:n].copy(), idepth=bufs["idepth"][i].reshape(int(l["h"]), int(l["w"])),
+                        weightSums=bufs["weightSums"][i].reshape(int(l["h"]), int(l["w"]))))
+    return out

@@ -185,6 +185,89 @@ __global__ void coarse_pad_image_kernel(const float* __restrict__ src, float4* _
     if (i < npix) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
 }
 
+// ---- CoarseTracker::makeCoarseDepthL0 (CoarseTracker.cpp:127-283) ---------------------------------------------------
+__global__ void cd_scatter_kernel(int n, const float* __restrict__ cu, const float* __restrict__ cv, const float* __restrict__ cid,
+                                  const float* __restrict__ HdiF, int w, int h, float* __restrict__ idepth, float* __restrict__ wsum) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int u = (int)fa(cu[p], 0.5f), v = (int)fa(cv[p], 0.5f);
+    if (u < 0 || v < 0 || u >= w || v >= h) return;  // the reference trusts centerProjectedTo; out-of-image points are dropped here
+    const float weight = sqrtf((float)(1e-3 / ((double)HdiF[p] + 1e-12)));
+    // two points in one pixel are rare; their sum is taken in the order the atomics arrive (the reference: point order)
+    atomicAdd(&idepth[u + w * v], fm(cid[p], weight));
+    atomicAdd(&wsum[u + w * v], weight);
+}
+
+__global__ void cd_pyr_down_kernel(int wl, int hl, int wlm1, const float* __restrict__ id_in, const float* __restrict__ ws_in,
+                                   float* __restrict__ id_out, float* __restrict__ ws_out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= wl || y >= hl) return;
+    const int b = 2 * x + 2 * y * wlm1;
+    id_out[x + y * wl] = fa(fa(fa(id_in[b], id_in[b + 1]), id_in[b + wlm1]), id_in[b + wlm1 + 1]);
+    ws_out[x + y * wl] = fa(fa(fa(ws_in[b], ws_in[b + 1]), ws_in[b + wlm1]), ws_in[b + wlm1 + 1]);
+}
+
+// dilation by one pixel where a pixel has no point: diagonal neighbours on levels 0-1, axis neighbours below (:182-233).
+// Reads the weights of before the pass (bak); inverse depths are only read where bak > 0 and only written where bak <= 0.
+__global__ void cd_dilate_kernel(int wl, int hl, int diagonal, const float* __restrict__ bak, float* __restrict__ idepth, float* __restrict__ wsum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, total = wl * hl;
+    if (i < wl || i >= total - wl) return;
+    if (bak[i] > 0) return;
+    const int o[4] = {diagonal ? 1 + wl : 1, diagonal ? -1 - wl : -1, diagonal ? wl - 1 : wl, diagonal ? -wl + 1 : -wl};
+    float sum = 0, num = 0, numn = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j = i + o[k];
+        if (j >= 0 && j < total && bak[j] > 0) { sum = fa(sum, idepth[j]); num = fa(num, bak[j]); numn = fa(numn, 1.0f); }
+    }
+    if (numn > 0) { idepth[i] = __fdiv_rn(sum, numn); wsum[i] = __fdiv_rn(num, numn); }
+}
+
+// normalisation + scan-line ordered compaction (:236-281), one warp per image row.  PASS 0 counts the row's points, PASS 1
+// writes them at the row's offset (and finishes idepth / weightSums like the reference).
+template <int PASS>
+__global__ void cd_rows_kernel(int wl, int hl, float* __restrict__ idepth, float* __restrict__ wsum, const float* __restrict__ color, int* __restrict__ rows,
+                               float* __restrict__ pc_u, float* __restrict__ pc_v, float* __restrict__ pc_id, float* __restrict__ pc_col) {
+    const int y = 2 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (y >= hl - 2) return;
+    int run = PASS ? rows[y] : 0;
+    for (int x0 = 2; x0 < wl - 2; x0 += 32) {
+        const int x = x0 + lane, i = x + y * wl;
+        bool in = x < wl - 2, have = false, good = false;
+        float q = 0.f, c = 0.f;
+        if (in) {
+            const float ws = wsum[i];
+            have = ws > 0;
+            if (have) {
+                q = __fdiv_rn(idepth[i], ws);
+                c = color[i];
+                good = isfinite(c) && q > 0;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, good);
+        if (PASS) {
+            if (good) {
+                const int k = run + __popc(m & ((1u << lane) - 1u));
+                pc_u[k] = (float)x; pc_v[k] = (float)y; pc_id[k] = q; pc_col[k] = c;
+            }
+            if (in) {
+                idepth[i] = good ? q : -1.0f;
+                if (good || !have) wsum[i] = 1.0f;  // the reference's `continue` leaves the weight of a rejected pixel as it is
+            }
+        }
+        run += __popc(m);
+    }
+    if (!PASS && lane == 0) rows[y] = run;
+}
+
+// exclusive scan of the row counts (a few hundred rows: one thread), rows[hl] = number of points of the level
+__global__ void cd_row_scan_kernel(int hl, int* __restrict__ rows) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int acc = 0;
+    for (int y = 2; y < hl - 2; ++y) { const int c = rows[y]; rows[y] = acc; acc += c; }
+    rows[hl] = acc;
+}
+
 struct Level {
     int w = 0, h = 0, n = 0, cap = 0;
     float fx = 0, fy = 0, cx = 0, cy = 0;
@@ -192,6 +275,10 @@ struct Level {
     float4* image = nullptr;
     float* pc = nullptr;  // [4][cap]: u, v, idepth, color
     bool has_image = false;
+    // makeCoarseDepthL0: the reference frame's intensity plane and the inverse-depth map under construction
+    float* ref_color = nullptr;  // [h*w] lastRef->dIp[lvl][.][0]
+    float* depth = nullptr;      // idepth | weightSums | weightSums_bak, h*w each
+    int* rows = nullptr;         // per image row: points of the row, then their offset in the level's point cloud; [h] = total
 };
 
 }  // namespace
@@ -235,6 +322,9 @@ void edsgpu_coarse_destroy(edsgpu_coarse* c) {
     for (Level& l : c->levels) {
         if (l.image) cudaFree(l.image);
         if (l.pc) cudaFree(l.pc);
+        if (l.ref_color) cudaFree(l.ref_color);
+        if (l.depth) cudaFree(l.depth);
+        if (l.rows) cudaFree(l.rows);
     }
     if (c->partials) cudaFree(c->partials);
     if (c->track_io) cudaFree(c->track_io);
@@ -253,6 +343,11 @@ edsgpu_status edsgpu_coarse_set_level(edsgpu_coarse* c, int lvl, int width, int 
         cudaFree(l.image);
         l.image = nullptr;
         l.has_image = false;
+        if (l.ref_color) cudaFree(l.ref_color);
+        if (l.depth) cudaFree(l.depth);
+        if (l.rows) cudaFree(l.rows);
+        l.ref_color = l.depth = nullptr;
+        l.rows = nullptr;
     }
     l.w = width; l.h = height; l.fx = fx; l.fy = fy; l.cx = cx; l.cy = cy;
     memcpy(l.Ki, Ki, sizeof(l.Ki));
@@ -300,6 +395,105 @@ edsgpu_status edsgpu_coarse_set_new_frame(edsgpu_coarse* c, int lvl, const float
     EDS_CUDA(ctx, cudaGetLastError());
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     l.has_image = true;
+    return EDSGPU_OK;
+}
+
+// lastRef->dIp[lvl] of the reference frame (makeCoarseDepthL0 takes the point colours from it)
+edsgpu_status edsgpu_coarse_set_reference_frame(edsgpu_coarse* c, int lvl, const float* dI) {
+    if (!c) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = c->ctx;
+    EDS_REQUIRE(ctx, lvl >= 0 && lvl < (int)c->levels.size() && dI, "coarse_set_reference_frame: bad arguments");
+    Level& l = c->levels[lvl];
+    EDS_REQUIRE(ctx, l.w > 0, "coarse_set_reference_frame: call edsgpu_coarse_set_level first");
+    DeviceGuard g(ctx->device);
+    const size_t npix = (size_t)l.w * l.h;
+    if (!l.ref_color) EDS_CUDA(ctx, cudaMalloc(&l.ref_color, sizeof(float) * npix));
+    // strided copy of channel 0 of the Vec3f image
+    EDS_CUDA(ctx, cudaMemcpy2DAsync(l.ref_color, sizeof(float), dI, 3 * sizeof(float), sizeof(float), npix, cudaMemcpyHostToDevice, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_coarse_make_depth_l0(edsgpu_coarse* c, int levels_used, int n, const float* proj_u, const float* proj_v, const float* proj_idepth,
+                                          const float* HdiF, int* pc_n_out) {
+    if (!c) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = c->ctx;
+    EDS_RANGE("edsgpu_coarse_make_depth_l0");
+    EDS_REQUIRE(ctx, levels_used >= 1 && levels_used <= (int)c->levels.size() && n >= 0, "coarse_make_depth_l0: bad arguments");
+    EDS_REQUIRE(ctx, n == 0 || (proj_u && proj_v && proj_idepth && HdiF), "coarse_make_depth_l0: null array");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->stream;
+    for (int lvl = 0; lvl < levels_used; ++lvl) {
+        Level& l = c->levels[lvl];
+        EDS_REQUIRE(ctx, l.w > 4 && l.h > 4 && l.ref_color, "coarse_make_depth_l0: every level needs edsgpu_coarse_set_level and edsgpu_coarse_set_reference_frame");
+        if (lvl > 0) EDS_REQUIRE(ctx, l.w == c->levels[lvl - 1].w >> 1 && l.h == c->levels[lvl - 1].h >> 1, "coarse_make_depth_l0: levels must halve (makeK)");
+        const size_t npix = (size_t)l.w * l.h;
+        if (!l.depth) EDS_CUDA(ctx, cudaMalloc(&l.depth, sizeof(float) * 3 * npix));
+        if (!l.rows) EDS_CUDA(ctx, cudaMalloc(&l.rows, sizeof(int) * ((size_t)l.h + 1)));
+        if (l.cap < (int)npix) {  // the point cloud of a level can hold every pixel
+            EDS_CUDA(ctx, cudaStreamSynchronize(s));
+            if (l.pc) cudaFree(l.pc);
+            l.pc = nullptr; l.cap = 0;
+            EDS_CUDA(ctx, cudaMalloc(&l.pc, sizeof(float) * 4 * npix));
+            l.cap = (int)npix;
+        }
+    }
+    // the projected points: u | v | idepth | HdiF staged through the context's scratch
+    edsgpu_status st = edsgpu_ensure_scratch(ctx, sizeof(float) * 4 * (size_t)std::max(n, 1));
+    if (st != EDSGPU_OK) return st;
+    float* d = (float*)ctx->scratch;
+    const float* src[4] = {proj_u, proj_v, proj_idepth, HdiF};
+    for (int k = 0; k < 4 && n > 0; ++k) EDS_CUDA(ctx, cudaMemcpyAsync(d + (size_t)k * n, src[k], sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s));
+    {
+        Level& l0 = c->levels[0];
+        const size_t npix = (size_t)l0.w * l0.h;
+        EDS_CUDA(ctx, cudaMemsetAsync(l0.depth, 0, sizeof(float) * 2 * npix, s));
+        if (n > 0) cd_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, l0.w, l0.h, l0.depth, l0.depth + npix);
+    }
+    for (int lvl = 1; lvl < levels_used; ++lvl) {
+        Level& l = c->levels[lvl];
+        Level& m = c->levels[lvl - 1];
+        const size_t npix = (size_t)l.w * l.h, npm = (size_t)m.w * m.h;
+        cd_pyr_down_kernel<<<dim3((l.w + 127) / 128, l.h), 128, 0, s>>>(l.w, l.h, m.w, m.depth, m.depth + npm, l.depth, l.depth + npix);
+    }
+    for (int lvl = 0; lvl < levels_used; ++lvl) {
+        Level& l = c->levels[lvl];
+        const size_t npix = (size_t)l.w * l.h;
+        float *id = l.depth, *ws = l.depth + npix, *bak = l.depth + 2 * npix;
+        EDS_CUDA(ctx, cudaMemcpyAsync(bak, ws, sizeof(float) * npix, cudaMemcpyDeviceToDevice, s));
+        cd_dilate_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(l.w, l.h, lvl < 2 ? 1 : 0, bak, id, ws);
+        const int rows = l.h - 4, rpb = 8;  // eight warps (rows) per CTA
+        float *pu = l.pc, *pv = l.pc + l.cap, *pi = l.pc + 2 * (size_t)l.cap, *pcol = l.pc + 3 * (size_t)l.cap;
+        cd_rows_kernel<0><<<(rows + rpb - 1) / rpb, 32 * rpb, 0, s>>>(l.w, l.h, id, ws, l.ref_color, l.rows, pu, pv, pi, pcol);
+        cd_row_scan_kernel<<<1, 32, 0, s>>>(l.h, l.rows);
+        cd_rows_kernel<1><<<(rows + rpb - 1) / rpb, 32 * rpb, 0, s>>>(l.w, l.h, id, ws, l.ref_color, l.rows, pu, pv, pi, pcol);
+        ctx->launches += 4;
+    }
+    EDS_CUDA(ctx, cudaGetLastError());
+    st = edsgpu_ensure_pinned(ctx, sizeof(int) * (size_t)levels_used);
+    if (st != EDSGPU_OK) return st;
+    int* hn = (int*)ctx->pinned;
+    for (int lvl = 0; lvl < levels_used; ++lvl)
+        EDS_CUDA(ctx, cudaMemcpyAsync(hn + lvl, c->levels[lvl].rows + c->levels[lvl].h, sizeof(int), cudaMemcpyDeviceToHost, s));
+    EDS_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int lvl = 0; lvl < levels_used; ++lvl) {
+        c->levels[lvl].n = hn[lvl];  // pc_n[lvl]: the level is ready for calcRes / trackNewestCoarse
+        if (pc_n_out) pc_n_out[lvl] = hn[lvl];
+    }
+    return EDSGPU_OK;
+}
+
+edsgpu_status edsgpu_coarse_get_reference(edsgpu_coarse* c, int lvl, int* n_out, float* pc_u, float* pc_v, float* pc_idepth, float* pc_color) {
+    if (!c) return EDSGPU_INVALID_ARGUMENT;
+    edsgpu_ctx* ctx = c->ctx;
+    EDS_REQUIRE(ctx, lvl >= 0 && lvl < (int)c->levels.size(), "coarse_get_reference: bad level");
+    DeviceGuard g(ctx->device);
+    const Level& l = c->levels[lvl];
+    if (n_out) *n_out = l.n;
+    float* dst[4] = {pc_u, pc_v, pc_idepth, pc_color};
+    for (int k = 0; k < 4; ++k)
+        if (dst[k] && l.n > 0) EDS_CUDA(ctx, cudaMemcpyAsync(dst[k], l.pc + (size_t)k * l.cap, sizeof(float) * (size_t)l.n, cudaMemcpyDeviceToHost, ctx->stream));
+    EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EDSGPU_OK;
 }
 

@@ -35,7 +35,7 @@ SYMBOLS = [
     "edsgpu_tracker_evaluate",
     "edsgpu_ba_create", "edsgpu_ba_destroy", "edsgpu_ba_set_residuals", "edsgpu_ba_set_points", "edsgpu_ba_set_frames",
     "edsgpu_ba_top_accumulate", "edsgpu_ba_top_stitch", "edsgpu_ba_sc_accumulate", "edsgpu_ba_sc_stitch", "edsgpu_ba_get_jpjd",
-    "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_linearize_accumulate", "edsgpu_ba_top_read", "edsgpu_ba_solve_system", "edsgpu_ba_get_residuals",
+    "edsgpu_ba_set_image", "edsgpu_ba_set_linearize_inputs", "edsgpu_ba_linearize", "edsgpu_ba_linearize_accumulate", "edsgpu_ba_top_read", "edsgpu_ba_solve_system", "edsgpu_coarse_set_reference_frame", "edsgpu_coarse_make_depth_l0", "edsgpu_coarse_get_reference", "edsgpu_ba_get_residuals",
     "edsgpu_ba_resubstitute", "edsgpu_ba_fix_linearization", "edsgpu_ba_calc_l_energy",
     "edsgpu_coarse_create", "edsgpu_coarse_destroy", "edsgpu_coarse_set_level", "edsgpu_coarse_set_reference",
     "edsgpu_coarse_set_new_frame", "edsgpu_coarse_calc_res_gs", "edsgpu_coarse_track",
@@ -579,6 +579,25 @@ class CoarseTracker:
     def set_reference(self, lvl, pc_u, pc_v, pc_idepth, pc_color):
         a = [np.ascontiguousarray(x, np.float32) for x in (pc_u, pc_v, pc_idepth, pc_color)]
         self.ctx.check(self.ctx.lib.edsgpu_coarse_set_reference(self.h, C.c_int(lvl), C.c_int(len(a[0])), *[_ptr(x, C.c_float) for x in a]))
+
+    def set_reference_frame(self, lvl, dI):
+        """lastRef->dIp[lvl] (h, w, 3): makeCoarseDepthL0 takes the point colours from it"""
+        d = np.ascontiguousarray(dI, np.float32)
+        self.ctx.check(self.ctx.lib.edsgpu_coarse_set_reference_frame(self.h, C.c_int(lvl), _ptr(d, C.c_float)))
+
+    def make_depth_l0(self, levels_used, proj_u, proj_v, proj_idepth, HdiF):
+        """CoarseTracker::makeCoarseDepthL0 on the device -> pc_n per level; the levels' reference point clouds are in place"""
+        a = [np.ascontiguousarray(x, np.float32) for x in (proj_u, proj_v, proj_idepth, HdiF)]
+        n = (C.c_int * levels_used)()
+        self.ctx.check(self.ctx.lib.edsgpu_coarse_make_depth_l0(self.h, C.c_int(levels_used), C.c_int(len(a[0])), *[_ptr(x, C.c_float) for x in a], n))
+        return list(n)
+
+    def get_reference(self, lvl):
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.edsgpu_coarse_get_reference(self.h, C.c_int(lvl), C.byref(n), None, None, None, None))
+        out = [np.zeros(n.value, np.float32) for _ in range(4)]
+        self.ctx.check(self.ctx.lib.edsgpu_coarse_get_reference(self.h, C.c_int(lvl), C.byref(n), *[_ptr(x, C.c_float) for x in out]))
+        return dict(n=n.value, pc_u=out[0], pc_v=out[1], pc_idepth=out[2], pc_color=out[3])
 
     def set_new_frame(self, lvl, dI):
         d = np.ascontiguousarray(dI, np.float32)

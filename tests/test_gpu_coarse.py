@@ -105,3 +105,42 @@ def test_track_newest_coarse_matches_the_oracle_loop(gpu_ctx):
     bad = ct.track(3, pb["R"], pb["t"], min_res_for_abort=[1e-3] * 5)
     assert not bad["ok"] and np.array_equal(bad["R"], np.asarray(pb["R"], np.float64)) and np.array_equal(bad["t"], pb["t"])
     ct.close()
+
+
+@pytest.mark.parametrize("size", ["small", "vga"])
+def test_make_coarse_depth_l0_matches_oracle(gpu_ctx, size):
+    """CoarseTracker::makeCoarseDepthL0 on the device against the CPU restatement: the per-level point clouds have the same
+    points in the same (scan-line) order, colours bit for bit, inverse depths to float rounding (two points in one pixel are
+    summed in arrival order on the device), and the levels are ready for calcRes afterwards."""
+    pb = SC.make_coarse_problem(W=160, H=120, levels=3, points=3000) if size == "small" else SC.make_coarse_problem()
+    L = len(pb["levels"])
+    rng = np.random.default_rng(17)
+    W0, H0 = pb["levels"][0]["w"], pb["levels"][0]["h"]
+    n = 2500 if size == "small" else 14000
+    cu = rng.uniform(3.0, W0 - 4.0, n).astype(np.float32)
+    cv = rng.uniform(3.0, H0 - 4.0, n).astype(np.float32)
+    cid = rng.uniform(0.2, 1.5, n).astype(np.float32)
+    cid[::211] = -0.3  # rejected: not a positive inverse depth
+    hdi = rng.uniform(1e-4, 1e-2, n).astype(np.float32)
+    levels = [dict(w=Lv["w"], h=Lv["h"], dI_ref=Lv["dI_new"]) for Lv in pb["levels"]]  # any image serves as the reference frame
+    ref = O.make_coarse_depth_l0(levels, cu, cv, cid, hdi)
+    ct = edsgpu.CoarseTracker(gpu_ctx, L)
+    for lvl, Lv in enumerate(pb["levels"]):
+        ct.set_level(lvl, Lv["w"], Lv["h"], Lv["fx"], Lv["fy"], Lv["cx"], Lv["cy"], Lv["Ki"])
+        ct.set_reference_frame(lvl, Lv["dI_new"])
+        ct.set_new_frame(lvl, Lv["dI_new"])
+    pc_n = ct.make_depth_l0(L, cu, cv, cid, hdi)
+    assert pc_n == [r["n"] for r in ref] and pc_n[0] > n
+    for lvl in range(L):
+        g = ct.get_reference(lvl)
+        r = ref[lvl]
+        assert np.array_equal(g["pc_u"], r["pc_u"]) and np.array_equal(g["pc_v"], r["pc_v"]) and np.array_equal(g["pc_color"], r["pc_color"])
+        assert np.abs(g["pc_idepth"] - r["pc_idepth"]).max() <= 2e-6 * np.abs(r["pc_idepth"]).max()
+        # the level can be evaluated right away, and gives what an upload of the oracle's point cloud gives
+        a = ct.calc_res_gs(lvl, pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"])
+        o = O.coarse_calc_res_gs(lvl, pb["levels"][lvl]["dI_new"], pb["levels"][lvl]["fx"], pb["levels"][lvl]["fy"], pb["levels"][lvl]["cx"],
+                                 pb["levels"][lvl]["cy"], pb["levels"][lvl]["Ki"], pb["R"], pb["t"], pb["affLL"], pb["b0"], pb["cutoffTH"],
+                                 r["pc_u"], r["pc_v"], r["pc_idepth"], r["pc_color"])
+        assert abs(a["rs"][1] - o["rs"][1]) <= 2 and abs(a["rs"][0] - o["rs"][0]) <= 1e-4 * o["rs"][0]
+    with pytest.raises(edsgpu.EdsGpuError):
+        edsgpu.CoarseTracker(gpu_ctx, 2).make_depth_l0(1, cu, cv, cid, hdi)  # no level set

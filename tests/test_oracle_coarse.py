@@ -76,3 +76,30 @@ def test_track_newest_coarse_recovers_the_pose():
     # the abort threshold of the caller is honoured (:668)
     bad = O.coarse_track(pb, 3, pb["R"], pb["t"], min_res_for_abort=[1e-3] * 5)
     assert not bad["ok"]
+
+
+def test_make_coarse_depth_l0_hand_checked():
+    """makeCoarseDepthL0 (CoarseTracker.cpp:127-283) on a case small enough to follow by hand: one point -> its pixel at level 0,
+    the 2x2 sum at level 1, the diagonal dilation ring on levels 0-1, weight-independent normalisation, scan-line order, and
+    a point with a non-finite reference colour dropped."""
+    W, H, L = 32, 24, 3
+    levels = [dict(w=W >> l, h=H >> l, dI_ref=np.full((H >> l, W >> l, 3), 7.0 + l, np.float32)) for l in range(L)]
+    out = O.make_coarse_depth_l0(levels, [10.2], [8.4], [0.5], [1e-3])
+    l0 = out[0]
+    # level 0: the point at (10, 8) and its four diagonal neighbours (dilation), in scan-line order
+    assert l0["n"] == 5
+    assert list(zip(l0["pc_u"], l0["pc_v"])) == [(9, 7), (11, 7), (10, 8), (9, 9), (11, 9)]
+    assert np.allclose(l0["pc_idepth"], 0.5, rtol=1e-6) and np.all(l0["pc_color"] == 7.0)
+    # level 1: pixel (5, 4) + diagonal ring; level 2: pixel (2, 2) + axis neighbours, of which only those inside [2, w-2) x [2, h-2)
+    assert (5.0, 4.0) in list(zip(out[1]["pc_u"], out[1]["pc_v"])) and out[1]["n"] == 5
+    assert list(zip(out[2]["pc_u"], out[2]["pc_v"])) == [(2, 2), (3, 2), (2, 3)]
+    assert np.allclose(out[2]["pc_idepth"], 0.5, rtol=1e-6)
+    # two points in one pixel: weighted mean with weights sqrt(1e-3 / HdiF)
+    out = O.make_coarse_depth_l0(levels, [10.0, 10.3], [8.0, 8.2], [0.4, 0.8], [1e-3, 4e-3])
+    w1, w2 = np.sqrt(1.0), np.sqrt(0.25)
+    k = list(zip(out[0]["pc_u"], out[0]["pc_v"])).index((10, 8))
+    assert abs(out[0]["pc_idepth"][k] - (0.4 * w1 + 0.8 * w2) / (w1 + w2)) < 1e-6
+    # non-finite reference colour: the pixel is skipped
+    levels[0]["dI_ref"][8, 10, 0] = np.nan
+    out = O.make_coarse_depth_l0(levels, [10.2], [8.4], [0.5], [1e-3])
+    assert out[0]["n"] == 4 and (10, 8) not in list(zip(out[0]["pc_u"], out[0]["pc_v"]))
