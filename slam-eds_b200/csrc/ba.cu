@@ -49,8 +49,7 @@ struct BaDev {
     double* acc_out;      // F*F x 13x13 (AccumulatorApprox::finish layout)
     long long* num_out;   // F*F
     float *Hdd_out, *bd_out, *Hcd_out;  // P, P, P x 4
-    unsigned* grid_bar;   // arrival counter of the grid barrier, only ever grows
-    unsigned bar_target;  // its value once every CTA of this launch has arrived
+    unsigned* grid_bar;   // {arrivals, generation} of the grid barrier
 };
 
 template <int HALF, int OFFSET>
@@ -471,18 +470,25 @@ __device__ __forceinline__ void top_add_point(const float* __restrict__ J, const
     for (int q = 0; q < 4; ++q) pt[2 + q] = J[O_JPDC0 + q] * q0 + J[O_JPDC1 + q] * q1;
 }
 
-// Grid-wide barrier of a cooperatively launched kernel (all CTAs resident).  The counter only grows; `target` is its
-// value once every CTA of this launch has arrived.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+// Grid-wide barrier of a cooperatively launched kernel (all CTAs resident), sense reversing: bar[0] counts arrivals, bar[1] is
+// the generation.  No host-side state: a launch that fails leaves nothing behind that a later launch could wait for.
+__device__ __forceinline__ void grid_barrier(unsigned* bar) {
     __syncthreads();
     if (threadIdx.x == 0) {
+        unsigned gen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
         __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if ((int)(v - target) < 0) __nanosleep(40);
-        } while ((int)(v - target) < 0);
+        if (atomicAdd(bar, 1u) == gridDim.x - 1u) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            unsigned g2;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(bar + 1) : "memory");
+            } while (g2 == gen);
+        }
+        __threadfence();
     }
     __syncthreads();
 }
@@ -646,7 +652,7 @@ __global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(BaDev W) {
         if (s0 + TOP_STAGE < count) __syncthreads();  // the stage is overwritten by the next round
     }
     top_tile_partial(W, acc, nres, warp_part, warp_n);
-    grid_barrier(W.grid_bar, W.bar_target);
+    grid_barrier(W.grid_bar);
     top_second_phase(W);
 }
 
@@ -696,7 +702,7 @@ __global__ void __launch_bounds__(TOP_THREADS, 1) ba_lin_top_kernel(LinDev d, Ba
         o[0] = make_float2(pt[0], pt[1]); o[1] = make_float2(pt[2], pt[3]); o[2] = make_float2(pt[4], pt[5]);
     }
     top_tile_partial(W, acc, nres, warp_part, warp_n);
-    grid_barrier(W.grid_bar, W.bar_target);
+    grid_barrier(W.grid_bar);
     top_second_phase(W);
 }
 
@@ -1112,8 +1118,7 @@ struct edsgpu_ba {
     bool lin_inputs_set = false;
     unsigned images_set = 0;  // bit per frame
     double* solve_block = nullptr;  // edsgpu_ba_solve_system: three stitched systems, HM, bM, delta, projector, x (device)
-    unsigned* grid_bar = nullptr;   // arrival counter of the accumulation kernels' grid barrier (device, only grows)
-    unsigned bar_count = 0;         // its value after the launches queued so far
+    unsigned* grid_bar = nullptr;   // {arrivals, generation} of the accumulation kernels' grid barrier (device)
     bool have_top[2] = {false, false}, have_sc = false;  // which accumulations of the current linearisation are on the device
     std::vector<double> adHost_h, adTarget_h;  // host copies for xAd of the back-substitution
     void* post_block = nullptr;                // xAd (F*F*8 floats), cstep (4), step (P), energy partials
@@ -1132,12 +1137,10 @@ BaDev ba_dev(const edsgpu_ba* w) {
     return d;
 }
 
-// output slot and barrier target of the next accumulation launch (every CTA of the launch arrives once)
+// output slot of the next accumulation launch
 void ba_dev_outputs(edsgpu_ba* w, BaDev& d, int slot) {
     d.acc_out = w->acc[slot]; d.num_out = w->num[slot];
     d.Hdd_out = w->Hdd[slot]; d.bd_out = w->bd[slot]; d.Hcd_out = w->Hcd[slot];
-    w->bar_count += (unsigned)w->num_tiles;
-    d.bar_target = w->bar_count;
 }
 
 LinDev lin_dev(const edsgpu_ba* w, bool have_state_in, bool have_linearized) {
