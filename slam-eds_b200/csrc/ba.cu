@@ -848,17 +848,24 @@ __global__ void ba_sc_hcc_kernel(int F, const double* __restrict__ hcc_host, dou
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double adj(const double* A, int r, int c) { return A[c * 8 + r]; }  // Mat88 column-major
 
-// out(i,j) += sum_m sum_n L(i,m) C(m,n) Rt(j,n), C given by functor c(m,n); thread (i,j)
+// out(i,j) += sum_m L(i,m) T(m,j), T(m,j) = sum_n C(m,n) Rt(j,n), C given by functor c(m,n); thread (i,j) of a 64-thread CTA.
+// The CTA forms T once (thread (i,j) computes T(i,j)) and shares it through `sh` (two 8x8 buffers used alternately, `turn`
+// counts the calls: one barrier per sandwich) instead of every thread recomputing the column of T it needs from global
+// memory -- same products in the same order, an eighth of the loads and a quarter of the multiplications.  Must be called by
+// all 64 threads.
+struct SandwichShared { double T[2][64]; };
 template <typename CF>
-__device__ __forceinline__ double sandwich(const double* L, CF c, const double* Rm, int i, int j) {
+__device__ __forceinline__ double sandwich(SandwichShared& sh, int& turn, const double* L, CF c, const double* Rm, int i, int j) {
+    double t = 0.0;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) t += c(i, n) * adj(Rm, j, n);
+    double* T = sh.T[turn & 1];
+    ++turn;
+    T[8 * i + j] = t;
+    __syncthreads();  // the buffer of two calls ago is free again: every thread has passed the barrier of the call in between
     double s = 0.0;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        double t = 0.0;
-#pragma unroll
-        for (int n = 0; n < 8; ++n) t += c(m, n) * adj(Rm, j, n);
-        s += adj(L, i, m) * t;
-    }
+    for (int m = 0; m < 8; ++m) s += adj(L, i, m) * T[8 * m + j];
     return s;
 }
 
@@ -867,6 +874,8 @@ __global__ void ba_top_stitch_kernel(int F, const double* __restrict__ acc, cons
                                      const double* __restrict__ adTarget, int use_prior, const double* __restrict__ cPrior,
                                      const float* __restrict__ cDeltaF, const double* __restrict__ frame_prior,
                                      const double* __restrict__ frame_delta_prior, double* __restrict__ H, double* __restrict__ bvec) {
+    __shared__ SandwichShared ssh;
+    int turn = 0;
     const int a = blockIdx.x % F, b = blockIdx.x / F, n = CPARS + 8 * F;
     const int i = threadIdx.x / 8, j = threadIdx.x % 8;
     auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
@@ -875,18 +884,18 @@ __global__ void ba_top_stitch_kernel(int F, const double* __restrict__ acc, cons
         for (int t = 0; t < F; ++t) {  // k = (h=a, t): adHost A88 adHost^T
             const int k = a + F * t;
             const double* A = acc + (size_t)169 * k;
-            s += sandwich(adHost + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adHost + 64 * k, i, j);
+            s += sandwich(ssh, turn, adHost + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adHost + 64 * k, i, j);
         }
         for (int h = 0; h < F; ++h) {  // k = (h, t=a): adTarget A88 adTarget^T
             const int k = h + F * a;
             const double* A = acc + (size_t)169 * k;
-            s += sandwich(adTarget + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adTarget + 64 * k, i, j);
+            s += sandwich(ssh, turn, adTarget + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adTarget + 64 * k, i, j);
         }
     }
     {  // H(hIdx,tIdx) += adHost A88 adTarget^T for k = (h=a, t=b)
         const int k = a + F * b;
         const double* A = acc + (size_t)169 * k;
-        s += sandwich(adHost + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adTarget + 64 * k, i, j);
+        s += sandwich(ssh, turn, adHost + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adTarget + 64 * k, i, j);
     }
     Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
     if (a == b) {
@@ -934,6 +943,8 @@ __global__ void ba_top_symmetrise_kernel(int F, int use_prior, const double* __r
 __global__ void ba_sc_stitch_kernel(int F, const double* __restrict__ accD, const double* __restrict__ accE, const double* __restrict__ accEB,
                                     const double* __restrict__ accHcc, const double* __restrict__ accbc, const double* __restrict__ adHost,
                                     const double* __restrict__ adTarget, double* __restrict__ H, double* __restrict__ bvec) {
+    __shared__ SandwichShared ssh;
+    int turn = 0;
     const int a = blockIdx.x % F, b = blockIdx.x / F, n = CPARS + 8 * F, F2 = F * F;
     const int i = threadIdx.x / 8, j = threadIdx.x % 8;
     auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
@@ -943,20 +954,20 @@ __global__ void ba_sc_stitch_kernel(int F, const double* __restrict__ accD, cons
         for (int jj = 0; jj < F; ++jj)
             for (int kk = 0; kk < F; ++kk) {
                 const double* d = D(a, jj, kk);
-                s += sandwich(adHost + 64 * (a + F * jj), [&](int m, int nn) { return d[8 * m + nn]; }, adHost + 64 * (a + F * kk), i, j);
+                s += sandwich(ssh, turn, adHost + 64 * (a + F * jj), [&](int m, int nn) { return d[8 * m + nn]; }, adHost + 64 * (a + F * kk), i, j);
             }
     }
     for (int ii = 0; ii < F; ++ii) {  // H(jIdx,kIdx) += adTarget[ij] D[ijk] adTarget[ik]^T, j = a, k = b
         const double* d = D(ii, a, b);
-        s += sandwich(adTarget + 64 * (ii + F * a), [&](int m, int nn) { return d[8 * m + nn]; }, adTarget + 64 * (ii + F * b), i, j);
+        s += sandwich(ssh, turn, adTarget + 64 * (ii + F * a), [&](int m, int nn) { return d[8 * m + nn]; }, adTarget + 64 * (ii + F * b), i, j);
     }
     for (int kk = 0; kk < F; ++kk) {  // H(jIdx,iIdx) += adTarget[ij] D[ijk] adHost[ik]^T, j = a, i = b
         const double* d = D(b, a, kk);
-        s += sandwich(adTarget + 64 * (b + F * a), [&](int m, int nn) { return d[8 * m + nn]; }, adHost + 64 * (b + F * kk), i, j);
+        s += sandwich(ssh, turn, adTarget + 64 * (b + F * a), [&](int m, int nn) { return d[8 * m + nn]; }, adHost + 64 * (b + F * kk), i, j);
     }
     for (int jj = 0; jj < F; ++jj) {  // H(iIdx,kIdx) += adHost[ij] D[ijk] adTarget[ik]^T, i = a, k = b
         const double* d = D(a, jj, b);
-        s += sandwich(adHost + 64 * (a + F * jj), [&](int m, int nn) { return d[8 * m + nn]; }, adTarget + 64 * (a + F * b), i, j);
+        s += sandwich(ssh, turn, adHost + 64 * (a + F * jj), [&](int m, int nn) { return d[8 * m + nn]; }, adTarget + 64 * (a + F * b), i, j);
     }
     Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
     if (a == b) {
@@ -1028,35 +1039,38 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_kernel(int F, double l
     }
     for (int r = tid; r < n; r += SOLVE_THREADS) rhs[r] *= sv[r];
     __syncthreads();
-    // right-looking LDL^T on the lower triangle: after step k column k holds L(:,k) below the diagonal, A[k][k] = D_k
-    for (int k = 0; k < n; ++k) {
-        const double d = A[k][k];
-        for (int i = k + 1 + tid; i < n; i += SOLVE_THREADS) col[i] = A[i][k];  // the unscaled column: L(i,k) D_k
-        __syncthreads();
-        const int m = n - k - 1;
-        for (int e = tid; e < m * m; e += SOLVE_THREADS) {
-            const int i = k + 1 + e / m, j = k + 1 + e % m;
-            if (j <= i) A[i][j] -= col[i] * (col[j] / d);
+    // right-looking LDL^T on the lower triangle.  Column k is final when step k starts and is not touched by it, so the update
+    // reads it in place (A[i][j] -= A[i][k] A[j][k] / D_k): one barrier per step.  Thread (ty, tx) of a 16 x 16 arrangement
+    // walks the trailing block in 16 x 16 tiles.  The columns are scaled to L(:,k) = A(:,k) / D_k in one pass at the end.
+    const int tx = tid & 15, ty = tid >> 4;
+    for (int k = 0; k < n - 1; ++k) {
+        const double rd = 1.0 / A[k][k];
+        for (int i = k + 1 + ty; i < n; i += 16) {
+            const double ci = A[i][k] * rd;
+            for (int j = k + 1 + tx; j <= i; j += 16) A[i][j] -= ci * A[j][k];
         }
-        for (int i = k + 1 + tid; i < n; i += SOLVE_THREADS) A[i][k] = col[i] / d;
         __syncthreads();
     }
-    // L z = rhs, D y = z, L^T w = y: by the first warp (n <= 68 dependent steps, trivially cheap)
+    for (int e = tid; e < n * n; e += SOLVE_THREADS) {
+        const int i = e / n, k = e - i * n;
+        if (k < i) A[i][k] /= A[k][k];  // reads the diagonal, writes strictly below it
+    }
+    __syncthreads();
+    // L z = rhs, D y = z, L^T w = y by the first warp, column oriented: once z_j is final every later row takes its term
+    // (two rows per lane, one warp barrier per column -- no reduction across lanes)
     if (tid < 32) {
-        for (int i = 0; i < n; ++i) {
-            double part = 0.0;
-            for (int j = tid; j < i; j += 32) part += A[i][j] * xs[j];
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if (tid == 0) xs[i] = rhs[i] - part;
+        for (int i = tid; i < n; i += 32) xs[i] = rhs[i];
+        __syncwarp();
+        for (int j = 0; j < n; ++j) {
+            const double zj = xs[j];
+            for (int i = j + 1 + tid; i < n; i += 32) xs[i] -= A[i][j] * zj;
             __syncwarp();
         }
         for (int i = tid; i < n; i += 32) xs[i] /= A[i][i];
         __syncwarp();
-        for (int i = n - 1; i >= 0; --i) {
-            double part = 0.0;
-            for (int j = i + 1 + tid; j < n; j += 32) part += A[j][i] * xs[j];
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if (tid == 0) xs[i] -= part;
+        for (int j = n - 1; j > 0; --j) {
+            const double wj = xs[j];
+            for (int i = tid; i < j; i += 32) xs[i] -= A[j][i] * wj;
             __syncwarp();
         }
         for (int i = tid; i < n; i += 32) xs[i] *= sv[i];
