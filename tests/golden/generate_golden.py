@@ -5,7 +5,8 @@ The reference ships no golden vectors and cannot be built 
 they catch regressions of the oracle itself (-m "not gpu") and give the GPU tests a
 committed target that does not depend on rebuilding the oracle (-m gpu).
 
-    python tests/golden/generate_golden.py
+    python tests/golden/generate_golden.py            # everything
+    python tests/golden/generate_golden.py round2     # only round2_small.npz (pyramid, per-level solve, makeCoarseDepthL0, solveSystemF)
 """
 import os
 import sys
@@ -84,8 +85,72 @@ def coarse_fixture(name):
     print(name, [out["counts%d" % l].tolist() for l in range(kw["levels"])])
 
 
+def round2_fixture(name):
+    """The paths added in round 2, all from the oracle: the event-frame pyramid (levels 1-2 of the tiny window), the
+    coarse-to-fine per-level solve, makeCoarseDepthL0 on a small pyramid, and solveSystemF on the small BA window
+    (the oracle's own accumulators and stitches feed the oracle's solve)."""
+    out = {}
+    scene, kf, wins = synth.make_problem("tiny", 0, 1)
+    w = wins[0]
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])
+    frames, norms = O.event_frame_levels(o["img"], 3)
+    out["pyr_norms"] = np.array(norms)
+    out["pyr_level1"], out["pyr_level2"] = frames[1], frames[2]
+    caps = [6, 4, 3]
+    x, tau = w["x_init"].copy(), 0.05
+    xs = []
+    for lvl in (2, 1, 0):
+        so = O.tracker_solve(kf, frames[lvl] / norms[lvl], x, num_blocks=4, loss_param=tau, max_iterations=caps[lvl])
+        x, tau = so["x"], so["next_loss_param"]
+        xs.append(np.concatenate([x, [tau, so["info"]["iterations"], so["info"]["final_cost"]]]))
+    out["pyr_caps"], out["pyr_solves"] = np.array(caps), np.array(xs)
+    # makeCoarseDepthL0
+    kw = dict(W=128, H=96, levels=3, points=2000, seed=13)
+    pb = synth_coarse.make_coarse_problem(**kw)
+    rng = np.random.default_rng(29)
+    n = 1500
+    cu = rng.uniform(3.0, kw["W"] - 4.0, n).astype(np.float32)
+    cv = rng.uniform(3.0, kw["H"] - 4.0, n).astype(np.float32)
+    cid = rng.uniform(0.2, 1.5, n).astype(np.float32)
+    hdi = rng.uniform(1e-4, 1e-2, n).astype(np.float32)
+    ref = O.make_coarse_depth_l0([dict(w=L["w"], h=L["h"], dI_ref=L["dI_new"]) for L in pb["levels"]], cu, cv, cid, hdi)
+    out["cd_kw"] = np.array([kw["W"], kw["H"], kw["levels"], kw["points"], kw["seed"]])
+    out["cd_points"] = np.stack([cu, cv, cid, hdi])
+    for lvl, r in enumerate(ref):
+        out["cd_pc%d" % lvl] = np.stack([r["pc_u"], r["pc_v"], r["pc_idepth"], r["pc_color"]])
+    # solveSystemF on the small BA window
+    kb = dict(F=4, points_per_frame=120, H=96, W=128, seed=21)
+    pbb = synth_ba.make_ba_problem(**kb)
+    F = pbb["F"]
+    g = np.load(os.path.join(HERE, "ba_small.npz"))
+    top = [O.ba_top_accumulate(m, F, g["recs"], pbb["host_idx"], pbb["target_idx"], pbb["res_begin"], pbb["flags"], g["res_toZero"], pbb["deltaF"],
+                               pbb["adHTdeltaF"], pbb["cDeltaF"], threads=1) for m in (0, 1)]
+    sc = O.ba_sc_accumulate(F, pbb["host_idx"], pbb["target_idx"], pbb["res_begin"], pbb["flags"], g["JpJdF"], top[0]["Hdd"], top[1]["Hdd"],
+                            top[0]["bd"], top[1]["bd"], top[0]["Hcd"], top[1]["Hcd"], pbb["priorF"], pbb["deltaF"], True)
+    ah, at = synth_ba.col_major(pbb["adHost"]), synth_ba.col_major(pbb["adTarget"])
+    HA, bA = O.ba_top_stitch(F, top[0]["acc"], ah, at)
+    HL, bL = O.ba_top_stitch(F, top[1]["acc"], ah, at, True, pbb["cPrior"], pbb["cDeltaF"], pbb["frame_prior"], pbb["frame_delta_prior"])
+    Hs, bs = O.ba_sc_stitch(F, sc, ah, at)
+    nn = 4 + 8 * F
+    r2 = np.random.default_rng(31)
+    a = r2.normal(size=(nn, nn))
+    HM = 1e-2 * np.abs(HA).max() * (a @ a.T) / nn
+    bM = 1e-2 * np.abs(bA).max() * r2.normal(size=nn)
+    delta = 1e-3 * r2.normal(size=nn)
+    P = O.ba_nullspace_projector([r2.normal(size=nn) for _ in range(7)])
+    out["solve_HM"], out["solve_bM"], out["solve_delta"], out["solve_P"] = HM, bM, delta, P
+    out["solve_x_plain"] = O.ba_solve_system(HA, bA, HL, bL, Hs, bs, 1e-5)
+    out["solve_x_full"] = O.ba_solve_system(HA, bA, HL, bL, Hs, bs, 1e-5, HM, bM, delta, P)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "pyramid norms", norms, "coarse depth points", [r["n"] for r in ref], "|x|", np.abs(out["solve_x_plain"]).max())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":  # the round-1 fixtures stay byte-identical
+        round2_fixture("round2_small.npz")
+        sys.exit(0)
     ba_fixture("ba_small.npz")
     coarse_fixture("coarse_small.npz")
     tracking_fixture("tiny", "tracking_tiny.npz", 4, 20)
     tracking_fixture("davis240c", "tracking_davis240c.npz", 8, 30, with_lut=False)
+    round2_fixture("round2_small.npz")

@@ -339,6 +339,27 @@ def test_gpu_against_committed_ba_fixture(gpu_ctx):
     w.close()
 
 
+def test_device_solve_against_round2_fixture(gpu_ctx):
+    """edsgpu_ba_solve_system on the committed small window against tests/golden/round2_small.npz (the oracle's accumulators,
+    stitches and solve), without calling the oracle: float accumulators on both sides, so the gate is the accumulators' 1e-5
+    scaled by the conditioning the solve adds."""
+    import os
+    gb = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_small.npz"))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "round2_small.npz"))
+    F, ppf, H, W, seed = [int(v) for v in gb["kw"]]
+    pb = SB.make_ba_problem(F=F, points_per_frame=ppf, H=H, W=W, seed=seed)
+    w = edsgpu.BaWindow(gpu_ctx, F, pb["host_idx"], pb["target_idx"], pb["res_begin"])
+    w.set_residuals(gb["recs"], pb["flags"], gb["res_toZero"])
+    w.set_points(pb["deltaF"], pb["priorF"])
+    w.set_frames(pb["adHTdeltaF"], pb["cDeltaF"], SB.col_major(pb["adHost"]), SB.col_major(pb["adTarget"]))
+    w.top_accumulate(0); w.top_accumulate(1); w.sc_accumulate(True)
+    pri = (pb["cPrior"], pb["frame_prior"], pb["frame_delta_prior"])
+    x_plain, _ = w.solve_system(1e-5, None, None, None, *pri)
+    x_full, _ = w.solve_system(1e-5, g["solve_HM"], g["solve_bM"], g["solve_delta"], *pri, projector=g["solve_P"])
+    assert rel(x_plain, g["solve_x_plain"]) < 1e-3 and rel(x_full, g["solve_x_full"]) < 1e-3
+    w.close()
+
+
 def test_linearize_needs_its_inputs(gpu_ctx):
     pb = SB.make_ba_problem(F=3, points_per_frame=50, H=64, W=80)
     w = edsgpu.BaWindow(gpu_ctx, pb["F"], pb["host_idx"], pb["target_idx"], pb["res_begin"])

@@ -144,3 +144,22 @@ def test_make_coarse_depth_l0_matches_oracle(gpu_ctx, size):
         assert abs(a["rs"][1] - o["rs"][1]) <= 2 and abs(a["rs"][0] - o["rs"][0]) <= 1e-4 * o["rs"][0]
     with pytest.raises(edsgpu.EdsGpuError):
         edsgpu.CoarseTracker(gpu_ctx, 2).make_depth_l0(1, cu, cv, cid, hdi)  # no level set
+
+
+def test_make_coarse_depth_l0_against_round2_fixture(gpu_ctx):
+    """makeCoarseDepthL0 on the device against tests/golden/round2_small.npz, without calling the oracle."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "round2_small.npz"))
+    W, H, L, pts, seed = [int(v) for v in g["cd_kw"]]
+    pb = SC.make_coarse_problem(W=W, H=H, levels=L, points=pts, seed=seed)
+    ct = edsgpu.CoarseTracker(gpu_ctx, L)
+    for lvl, Lv in enumerate(pb["levels"]):
+        ct.set_level(lvl, Lv["w"], Lv["h"], Lv["fx"], Lv["fy"], Lv["cx"], Lv["cy"], Lv["Ki"])
+        ct.set_reference_frame(lvl, Lv["dI_new"])
+    pc_n = ct.make_depth_l0(L, *g["cd_points"])
+    for lvl in range(L):
+        ref = g["cd_pc%d" % lvl]
+        got = ct.get_reference(lvl)
+        assert pc_n[lvl] == ref.shape[1] == got["n"]
+        assert np.array_equal(got["pc_u"], ref[0]) and np.array_equal(got["pc_v"], ref[1]) and np.array_equal(got["pc_color"], ref[3])
+        assert np.abs(got["pc_idepth"] - ref[2]).max() <= 2e-6 * np.abs(ref[2]).max()

@@ -513,3 +513,29 @@ def test_accumulator_ring_builds_the_same_frames(gpu_ctx, problems, monkeypatch)
     with pytest.raises(edsgpu.EdsGpuError):
         b.read_accumulator(0)
     a.close(); b.close()
+
+
+def test_gpu_against_round2_fixture(gpu_ctx):
+    """The CUDA pyramid and per-level solve against tests/golden/round2_small.npz, without calling the oracle."""
+    g = np.load(os.path.join(GOLD, "round2_small.npz"))
+    scene, kf, wins = synth.make_problem("tiny", 0, 1)
+    w = wins[0]
+    fr = edsgpu.Frames(gpu_ctx, kf["H"], kf["W"], 1, levels=3)
+    edsgpu.EventFrame(gpu_ctx, kf["H"], kf["W"], frames=fr).create(w["x"], w["y"], w["pol"], w["ts"])
+    for lvl in (1, 2):
+        img, nrm = fr.read_level(0, lvl)
+        ref = g["pyr_level%d" % lvl]
+        assert np.abs(img - ref).max() <= 1e-6 * np.abs(ref).max() and abs(nrm - g["pyr_norms"][lvl]) <= 1e-6 * g["pyr_norms"][lvl]
+    kfd = edsgpu.KeyFrame(gpu_ctx, kf, 4)
+    tr = edsgpu.Tracker(gpu_ctx, num_blocks=4, max_iterations=30)
+    tr.set_level_iterations([int(v) for v in g["pyr_caps"]])
+    x, tau = w["x_init"].copy(), 0.05
+    for k, lvl in enumerate((2, 1, 0)):
+        tr.set_state(x[:3], x[3:7], x[7:], tau)
+        r = tr.optimize(kfd, fr, 0, level=lvl)
+        ref = g["pyr_solves"][k]
+        assert r["usable"] and r["info"]["iterations"] == int(ref[14])
+        assert synth.quat_angle(r["qx"], ref[3:7]) < ANGLE_TOL and np.linalg.norm(r["px"] - ref[:3]) < DEPTH_TOL
+        assert abs(r["info"]["final_cost"] - ref[15]) < 1e-5 * ref[15]
+        x, tau = ref[:13], ref[13]
+    tr.close(); kfd.close(); fr.close()

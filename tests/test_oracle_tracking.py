@@ -292,3 +292,25 @@ def test_pyramid_levels_match_opencv_morphology():
             ref = cv2.dilate(img, el) + cv2.erode(img, el)
             assert np.array_equal(frames[i], ref)
             assert abs(norms[i] - cv2.norm(ref)) <= 1e-12 * norms[i]
+
+
+def test_oracle_reproduces_round2_fixture():
+    """tests/golden/round2_small.npz: the oracle's outputs for the paths added in round 2 (event-frame pyramid, per-level solve,
+    makeCoarseDepthL0, solveSystemF) are frozen; regenerating them here must give the committed numbers."""
+    from edsgpu import synth_ba as SB, synth_coarse as SCo
+    g = np.load(os.path.join(GOLD, "round2_small.npz"))
+    scene, kf, wins = synth.make_problem("tiny", 0, 1)
+    w = wins[0]
+    o = O.event_frame(w["x"], w["y"], w["pol"], w["ts"], kf["H"], kf["W"])
+    frames, norms = O.event_frame_levels(o["img"], 3)
+    assert np.array_equal(frames[1], g["pyr_level1"]) and np.array_equal(frames[2], g["pyr_level2"]) and np.array_equal(np.array(norms), g["pyr_norms"])
+    x, tau = w["x_init"].copy(), 0.05
+    for k, lvl in enumerate((2, 1, 0)):
+        so = O.tracker_solve(kf, frames[lvl] / norms[lvl], x, num_blocks=4, loss_param=tau, max_iterations=int(g["pyr_caps"][lvl]))
+        x, tau = so["x"], so["next_loss_param"]
+        assert np.allclose(np.concatenate([x, [tau, so["info"]["iterations"], so["info"]["final_cost"]]]), g["pyr_solves"][k], rtol=1e-12, atol=1e-14)
+    W, H, L, pts, seed = [int(v) for v in g["cd_kw"]]
+    pb = SCo.make_coarse_problem(W=W, H=H, levels=L, points=pts, seed=seed)
+    ref = O.make_coarse_depth_l0([dict(w=Lv["w"], h=Lv["h"], dI_ref=Lv["dI_new"]) for Lv in pb["levels"]], *g["cd_points"])
+    for lvl, r in enumerate(ref):
+        assert np.array_equal(np.stack([r["pc_u"], r["pc_v"], r["pc_idepth"], r["pc_color"]]), g["cd_pc%d" % lvl])
