@@ -39,20 +39,31 @@ __device__ __forceinline__ long long warp_aggregate(unsigned active, unsigned ke
     unsigned peers = __match_any_sync(active, key);
     int leader = __ffs(peers) - 1;
     *is_leader = ((int)lane == leader);
-    bool multi = __any_sync(active, __popc(peers) > 1);
-    if (!multi) return val;
+    // as many rounds as the largest group of the warp has members (usually 1-3): in round k every lane fetches the value of
+    // its k-th peer, in ascending lane order (the order of the sum is fixed)
+    const int rounds = __reduce_max_sync(active, __popc(peers));
+    if (rounds <= 1) return val;
     long long sum = 0;
-    for (int src = 0; src < 32; ++src) {
-        long long o = __shfl_sync(active, val, src);
-        if ((peers >> src) & 1u) sum += o;
+    unsigned m = peers;
+    for (int k = 0; k < rounds; ++k) {
+        const int src = m ? __ffs(m) - 1 : (int)lane;
+        const long long o = __shfl_sync(active, val, src);
+        if (m) { sum += o; m &= m - 1u; }
     }
     return sum;
+}
+
+// exp_weight(i, E) for i < E: depends on the window length only, so it is tabulated once per E instead of evaluated (a double
+// division and a double exp) for every event of every window
+__global__ void exp_table_kernel(int E, double* __restrict__ tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < E) tab[i] = exp_weight(i, E);
 }
 
 __global__ void __launch_bounds__(256) scatter_events_kernel(const uint16_t* __restrict__ ex, const uint16_t* __restrict__ ey,
                                                              const uint8_t* __restrict__ epol, int E, int H, int W,
                                                              const float* __restrict__ mapx, const float* __restrict__ mapy,
-                                                             int mode, int use_exp, long long* __restrict__ acc) {
+                                                             int mode, const double* __restrict__ exp_tab, long long* __restrict__ acc) {
     const int win = blockIdx.y;
     const size_t ebase = (size_t)win * E;
     long long* img = acc + (size_t)win * H * W;
@@ -68,7 +79,7 @@ __global__ void __launch_bounds__(256) scatter_events_kernel(const uint16_t* __r
         const int x = __ldcs(ex + ebase + i), y = __ldcs(ey + ebase + i);  // streaming: every event is read once
         const bool inside = (x < W) && (y < H);
         const double pol = __ldcs(epol + ebase + i) ? 1.0 : -1.0;  // EventFrame.cpp:318
-        const double wt = use_exp ? exp_weight(i, E) : 1.0;
+        const double wt = exp_tab ? __ldg(exp_tab + i) : 1.0;  // Utils.hpp:542-546
         double ux = x, uy = y;
         if (mapx != nullptr && inside) {  // EventFrame.cpp:316-317
             ux = (double)mapx[(size_t)y * W + x];
@@ -104,11 +115,14 @@ __global__ void __launch_bounds__(256) scatter_events_kernel(const uint16_t* __r
             unsigned peers = __match_any_sync(active, key);
             leader = ((int)(threadIdx.x & 31) == __ffs(peers) - 1);
             double sum = s;
-            if (__any_sync(active, __popc(peers) > 1)) {
+            const int rounds = __reduce_max_sync(active, __popc(peers));
+            if (rounds > 1) {  // see warp_aggregate
                 sum = 0.0;
-                for (int src = 0; src < 32; ++src) {
-                    double o = __shfl_sync(active, s, src);
-                    if ((peers >> src) & 1u) sum += o;
+                unsigned m = peers;
+                for (int k = 0; k < rounds; ++k) {
+                    const int src = m ? __ffs(m) - 1 : (int)(threadIdx.x & 31);
+                    const double o = __shfl_sync(active, s, src);
+                    if (m) { sum += o; m &= m - 1u; }
                 }
             }
             if (leader && inside) {
@@ -329,6 +343,14 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
     }
     fr->k0 = k0;
     fr->k1 = k1;
+    if (use_exp && fr->exp_E != E) {  // the time weights of a window of E events
+        if (fr->exp_table) { EDS_CUDA(ctx, cudaStreamSynchronize(bs)); cudaFree(fr->exp_table); fr->exp_table = nullptr; fr->exp_E = 0; }
+        EDS_CUDA(ctx, cudaMalloc(&fr->exp_table, sizeof(double) * (size_t)E));
+        exp_table_kernel<<<(E + 255) / 256, 256, 0, bs>>>(E, fr->exp_table);
+        ctx->launches++;
+        EDS_CUDA(ctx, cudaGetLastError());
+        fr->exp_E = E;
+    }
     const bool ring = fr->acc_slots < fr->capacity;
     for (int c0 = 0; c0 < count; c0 += fr->acc_slots) {
         // one chunk of windows: clear -> scatter -> blur on accumulators that stay in L2 (see frames.cuh)
@@ -355,7 +377,8 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
             dim3 grid(bx, n);
             const size_t eoff = (size_t)c0 * E;
             scatter_events_kernel<<<grid, threads, 0, bs>>>(x_dev + eoff, y_dev + eoff, pol_dev + eoff, E, H, W, lut ? lut->mapx : nullptr,
-                                                            lut ? lut->mapy : nullptr, mode, use_exp, fr->acc + (size_t)acc0 * npix);
+                                                            lut ? lut->mapy : nullptr, mode, use_exp ? fr->exp_table : nullptr,
+                                                            fr->acc + (size_t)acc0 * npix);
             ctx->launches++;
             EDS_CUDA(ctx, cudaGetLastError());
         }
@@ -564,6 +587,7 @@ void edsgpu_frames_destroy(edsgpu_frames* fr) {
     delete[] fr->arrays;
     delete[] fr->tex;
     delete[] fr->surf;
+    if (fr->exp_table) cudaFree(fr->exp_table);
     if (fr->surf_dev) cudaFree(fr->surf_dev);
     if (fr->tex_dev) cudaFree(fr->tex_dev);
     if (fr->partials) cudaFree(fr->partials);

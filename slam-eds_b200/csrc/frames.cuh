@@ -36,6 +36,8 @@ struct edsgpu_frames {
     unsigned* tickets = nullptr;  // [capacity] last-CTA election
     double* norms = nullptr;      // [levels * capacity][2] = {norm, 1/norm}
     double k0 = 0.0, k1 = 1.0;    // Gaussian taps of the last create (for read-back)
+    double* exp_table = nullptr;  // [exp_E] Gaussian-in-time weight of event i of a window of exp_E events (Utils.hpp:542-546)
+    int exp_E = 0;
     // host-facing create: two device staging buffers filled by a copy stream, so that the H2D copy of
     // the next batch of events overlaps the kernels still working on the current one
     void* events_dev[2] = {nullptr, nullptr};
