@@ -543,7 +543,7 @@ edsgpu_status edsgpu_coarse_calc_res_gs(edsgpu_coarse* c, int lvl, const double 
 namespace {
 
 // Sophus SO3::exp (quaternion form) -> rotation matrix, row-major
-__host__ __device__ void so3_exp(const double* w, double* R) {
+__device__ void so3_exp(const double* w, double* R) {
     const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
     double imag, real;
     if (th < 1e-10) {
@@ -561,7 +561,7 @@ __host__ __device__ void so3_exp(const double* w, double* R) {
 }
 
 // (R, t) <- SE3::exp(inc) * (R, t), inc = [translation part, rotation part]
-__host__ __device__ void se3_left_update(const double* inc6, double* R, double* t) {
+__device__ void se3_left_update(const double* inc6, double* R, double* t) {
     const double* u = inc6;
     const double* w = inc6 + 3;
     double Re[9], V[9];
@@ -590,7 +590,7 @@ __host__ __device__ void se3_left_update(const double* inc6, double* R, double* 
 }
 
 // x = A^-1 rhs, A symmetric positive definite 8x8 (LDL^T; the reference calls Eigen's ldlt().solve)
-__host__ __device__ void solve8(const double* A, const double* rhs, double* x) {
+__device__ void solve8(const double* A, const double* rhs, double* x) {
     // fully unrolled: on the device every index is a compile-time constant and L, D, y live in registers
     double L[64] = {0}, D[8], y[8];
 #pragma unroll

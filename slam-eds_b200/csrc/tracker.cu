@@ -46,7 +46,7 @@ constexpr int JLD = 20;         // floats per point row in shared memory (80 B: 
 constexpr int N_CONS = EDS_N_CONS;               // consumer PAIRS: pair c owns the batches j = c mod N_CONS of a block, its two warps split the rows
 constexpr int N_CONS_WARPS = 2 * N_CONS;
 constexpr int CTRL_WARP = TRK_WARPS - 1;         // evaluator CTA: the warp that fetches tasks from the global queue
-constexpr int COMB_WARP = TRK_WARPS - 2;         // evaluator CTA: the warp that combines the consumers' block totals and publishes the block
+// (warp TRK_WARPS - 2 of an evaluator CTA is the combiner: it adds the consumers' block totals and publishes the block)
 constexpr int N_PROD = TRK_WARPS - 2 - N_CONS_WARPS;  // producer warps of an evaluator CTA
 constexpr int N_EVAL_WARPS = TRK_WARPS - 1;      // producers + consumers + combiner
 #ifndef EDS_RING_DEPTH
@@ -424,15 +424,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #endif
     } while (!ok);
 }
-__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {  // non-blocking
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-
 // halving butterfly: 2*HALF per-lane values -> HALF, lanes with bit OFFSET keep the upper half
 template <int HALF, int OFFSET>
 __device__ __forceinline__ void butterfly_step(float* a, unsigned lane) {
@@ -475,18 +466,6 @@ struct RowBlock {
     }
 };
 typedef RowBlock<0, 12> ConsRows;  // all 90 entries per consumer warp; the consumers split the batches, not the rows
-
-// 96 per-lane partial sums -> warp totals; lane l ends with entries base(l)+{0,1,2}
-__device__ __forceinline__ void reduce96(float* acc, unsigned lane) {
-    butterfly_step<48, 16>(acc, lane);
-    butterfly_step<24, 8>(acc, lane);
-    butterfly_step<12, 4>(acc, lane);
-    butterfly_step<6, 2>(acc, lane);
-    butterfly_step<3, 1>(acc, lane);
-}
-__device__ __forceinline__ int reduce96_base(unsigned lane) {
-    return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
-}
 
 // ------------------------------------------------------------------------------------------
 // evaluator CTA: producer warps -> ring -> consumer warps
@@ -691,7 +670,9 @@ __device__ void consumer_warp_main(EvalShared& sh, const int cidx) {
     constexpr int COUNT = HALF == 0 ? CONS_LO : CONS_HI;   // entries of this half
     constexpr int FIRST = HALF == 0 ? 0 : CONS_LO;         // their position among the 90
     const int lane = threadIdx.x & 31;
+#ifdef EDS_TIMING
     const int widx = 2 * cidx + HALF;  // consumer warp number
+#endif
     unsigned base = 0, block_counter = 0;  // running batch number, EVAL tasks seen
 #ifdef EDS_TIMING
     unsigned long long t_wait = 0, t_work = 0, n_work = 0;
