@@ -4,22 +4,21 @@
 // functor PhotometricError (src/tracking/PhotometricError.hpp:56-214) and ceres::Solve
 // (un-vendored; trust-region LM restated from ceres-solver 1.14..2.1 semantics).
 //
-//   track_lm_kernel   persistent dataflow over global memory, 512-thread CTAs, one per SM.  A few LEADER CTAs: each of
-//                     their warps runs the whole Levenberg-Marquardt state machine of one problem (Jacobi scaling,
-//                     damping, register-resident 12x12 Cholesky, retractions, accept/reject, tolerances) and turns
+//   track_lm_kernel   persistent dataflow over global memory, 768-thread CTAs (24 warps at 80 registers), one per SM.  A few
+//                     LEADER CTAs: each of their warps runs the whole Levenberg-Marquardt state machine of one problem (Jacobi
+//                     scaling, damping, register-resident 12x12 Cholesky, retractions, accept/reject, tolerances) and turns
 //                     every evaluation into one task per residual block (Tracker.cpp:178-195) in a global queue.
-//                     All other CTAs are EVALUATORS: a control warp pops tasks (running ahead through a mailbox),
-//                     producer warps evaluate 32 points at a time (division-free fp64-exact projection, bicubic
-//                     window as four texture gathers, analytic Jacobian in fp32; software-pipelined) into a
-//                     shared-memory ring guarded by mbarriers, consumer warps own the 90 fp32 outer-product
-//                     accumulators, reduce the block with a halving warp butterfly, apply the per-block loss (rho')
-//                     and store 92 doubles into the problem's slot, then bump the counter its leader polls.  Any
-//                     evaluator serves any problem: every SM stays busy whatever the batch size, and the serial LM
-//                     step of one problem overlaps the sweeps of all the others.  The LM loop never returns to the
-//                     host: one launch per batch of windows.
+//                     All other CTAs are EVALUATORS: a control warp pops tasks (running ahead through a mailbox), 16
+//                     producer warps evaluate 32 points at a time, start to finish (division-free fp64-exact projection,
+//                     bicubic window as four texture gathers, analytic Jacobian in fp32) into a shared-memory ring guarded
+//                     by mbarriers, three consumer PAIRS own the 90 fp32 outer-product accumulators (split by rows), reduce
+//                     the block with a halving warp butterfly, and a combiner warp applies the per-block loss (rho'), stores
+//                     92 doubles into the problem's slot and bumps the counter its leader polls.  Any evaluator serves any
+//                     problem: every SM stays busy whatever the batch size, and the serial LM step of one problem overlaps
+//                     the sweeps of all the others.  The LM loop never returns to the host: one launch per batch of windows.
 //   mad_kernel        next loss parameter (MAD / STD) from the written-back residuals
 //                     (Tracker.cpp:281-317) by radix select.
-//   kf_prepare_kernel keyframe upload: fp32 SoA gather streams, fp64 3-D points
+//   kf_prepare_kernel keyframe upload: the per-point model gradient g (fp32, two float4), fp64 3-D points
 //                     (PhotometricError.hpp:94-105) and the per-block 6x6 model Gram matrix
 //                     A_b = sum g_i g_i^T (m_i = g_i . v is linear in v, so
 //                     ||m||^2 = v^T A_b v and sum m_i g_i = A_b v need no sweep).
