@@ -22,6 +22,8 @@ struct DepthArgs {
     const double* ef_coord;
     double* state;  // [N][4]
     unsigned char* ok;
+    const unsigned char* skip;  // or null: points that left the event frame (Tracker::getCoord erases them before the update,
+                                // Tracker.cpp:356-372; here they keep their state and report ok = 0)
 };
 
 __device__ __forceinline__ void cross3(const double* a, const double* b, double* o) {
@@ -52,6 +54,10 @@ __global__ void __launch_bounds__(128) depth_update_kernel(DepthArgs d) {
 __global__ void __launch_bounds__(128) depth_update_tracked_kernel(DepthArgs d, const double* __restrict__ tracker_state) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.N) return;
+    if (d.skip && d.skip[i]) {
+        if (d.ok) d.ok[i] = 0;
+        return;
+    }
     double R[9];
     quat_rot(tracker_state + 3, R);
     const double px[3] = {tracker_state[0], tracker_state[1], tracker_state[2]};
@@ -145,7 +151,7 @@ edsgpu_status edsgpu_depth_update_tracked(edsgpu_depth_points* d, const double* 
     a.N = d->N; a.tracks = 0;
     a.fx = d->fx; a.fy = d->fy; a.cx = d->cx; a.cy = d->cy; a.mu_range = d->mu_range; a.px_error_angle = d->px_error_angle;
     a.kf_coord = kf_coord_dev; a.ef_coord = ef_coord_dev;
-    a.state = d->state; a.ok = d->ok;
+    a.state = d->state; a.ok = d->ok; a.skip = d->outlier;
     depth_update_tracked_kernel<<<(d->N + 127) / 128, 128, 0, ctx->stream>>>(a, tracker_state_dev);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
@@ -167,6 +173,8 @@ edsgpu_status edsgpu_depth_points_create(edsgpu_ctx* ctx, int num_points, double
     cudaError_t e = cudaMalloc(&d->state, sizeof(double) * 4 * (size_t)num_points);
     if (e == cudaSuccess) e = cudaMalloc(&d->coords, sizeof(double) * 4 * (size_t)num_points);
     if (e == cudaSuccess) e = cudaMalloc(&d->ok, (size_t)num_points);
+    if (e == cudaSuccess) e = cudaMalloc(&d->outlier, (size_t)num_points);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d->outlier, 0, (size_t)num_points, ctx->stream);
     if (e != cudaSuccess) { edsgpu_depth_points_destroy(d); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
     // init (:52-91): without inverse depths every point starts at the mean depth with sigma2 = mu_range^2,
     // with inverse depths (from the global map) at them with sigma2 = mu_range^2 / 36
@@ -190,6 +198,7 @@ void edsgpu_depth_points_destroy(edsgpu_depth_points* d) {
     if (d->state) cudaFree(d->state);
     if (d->coords) cudaFree(d->coords);
     if (d->ok) cudaFree(d->ok);
+    if (d->outlier) cudaFree(d->outlier);
     delete d;
 }
 

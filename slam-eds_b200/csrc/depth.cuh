@@ -8,7 +8,9 @@ struct edsgpu_depth_points {
     double fx = 0, fy = 0, cx = 0, cy = 0, mu_range = 0, px_error_angle = 0;
     double* state = nullptr;   // [N][4]
     double* coords = nullptr;  // [2][N][2] staging: kf, ef
-    unsigned char* ok = nullptr;
+    unsigned char* ok = nullptr;        // filter result per point: 1 = updated and valid
+    unsigned char* outlier = nullptr;   // Tracker::getCoord: 1 = the point projects outside the event frame (its own buffer: the
+                                        // flags have the opposite sense of `ok`)
     bool kf_coord_set = false;  // coords[0..2N) holds KeyFrame::coord
 };
 

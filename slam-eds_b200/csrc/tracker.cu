@@ -2248,11 +2248,11 @@ edsgpu_status edsgpu_tracker_get_coord(edsgpu_tracker* tr, const edsgpu_keyframe
     const size_t N = (size_t)kf->dev.N;
     double* coord_dev = dp->coords + 2 * N;  // the filter's event-frame coordinate buffer
     get_coord_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(kf->dev.N, kf->src + 2 * N, dp->state, tr->state, kf->dev.fx, kf->dev.fy,
-                                                                           kf->dev.cx, kf->dev.cy, kf->dev.W, kf->dev.H, coord_dev, dp->ok);
+                                                                           kf->dev.cx, kf->dev.cy, kf->dev.W, kf->dev.H, coord_dev, dp->outlier);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
     if (coord_out) EDS_CUDA(ctx, cudaMemcpyAsync(coord_out, coord_dev, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, ctx->stream));
-    if (outlier_out) EDS_CUDA(ctx, cudaMemcpyAsync(outlier_out, dp->ok, N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (outlier_out) EDS_CUDA(ctx, cudaMemcpyAsync(outlier_out, dp->outlier, N, cudaMemcpyDeviceToHost, ctx->stream));
     if (coord_out || outlier_out) EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EDSGPU_OK;
 }

@@ -80,7 +80,10 @@ def test_tracking_loop_with_the_depth_filter_stays_on_the_device(gpu_ctx):
                                     [2 * (xq * yq + zq * wq), 1 - 2 * (xq * xq + zq * zq), 2 * (yq * zq - xq * wq)],
                                     [2 * (xq * zq - yq * wq), 2 * (yq * zq + xq * wq), 1 - 2 * (xq * xq + yq * yq)]])
         T_ef_kf[:3, 3] = x[:3]
-        st, _ = O.depth_update(kf["fx"], kf["fy"], kf["cx"], kf["cy"], 5.0, px_ang, np.linalg.inv(T_ef_kf), kf_coord, coord, st)
+        st_new, _ = O.depth_update(kf["fx"], kf["fy"], kf["cx"], kf["cy"], 5.0, px_ang, np.linalg.inv(T_ef_kf), kf_coord, coord, st)
+        # points that left the event frame are erased by the reference before the update (Tracker.cpp:356-372); the device
+        # keeps them in place with their state untouched
+        st = np.where(np.asarray(outl, bool)[:, None], st, st_new)
         kf_cpu["idp"] = st[:, 0].copy()
         # pose of this window, warped coordinates, filter state
         assert synth.quat_angle(r["qx"], x[3:7]) < 1e-4 and np.linalg.norm(r["px"] - x[:3]) < 1e-4 * 2.0
