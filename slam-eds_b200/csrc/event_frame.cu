@@ -171,14 +171,20 @@ __global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long
     const int win = blockIdx.z;
     const int slot = first_slot + win;
     const long long* img = acc + (size_t)(first_acc + win) * H * W;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler too: the loops below get uniform trip counts
     const int sx = blur_strips_x(W), strip = blockIdx.x * BLUR_WARPS + warp;
     double sq = 0.0;
-    if (strip < sx * blur_strips_y(H)) {
-        const int x = (strip % sx) * BLUR_COLS + lane - 1;          // this lane's column; lanes 0 and 31 are halo columns
-        const int y0 = (strip / sx) * BLUR_ROWS, y1 = min(y0 + BLUR_ROWS, H);
+    {
+        // a warp beyond the last strip (tail of the last CTA) repeats the last strip and stores nothing: no branch around the
+        // shuffles, so they need no divergence handling
+        const int nstrips = sx * blur_strips_y(H);
+        const bool live = strip < nstrips;
+        const int st = live ? strip : nstrips - 1;
+        const int x = (st % sx) * BLUR_COLS + lane - 1;             // this lane's column; lanes 0 and 31 are halo columns
+        const int y0 = (st / sx) * BLUR_ROWS, y1 = min(y0 + BLUR_ROWS, H);
         const int xs = reflect101(min(max(x, -1), W), W);           // source column (reflected at the border, clamped for idle lanes)
-        const bool out_col = lane >= 1 && lane <= BLUR_COLS && x < W;
+        const bool out_col = live && lane >= 1 && lane <= BLUR_COLS && x < W;
         const double scale = OUT64 ? (scale_ptr ? scale_ptr[2 * slot + 1] : 1.0) : 1.0;
         cudaSurfaceObject_t surf = 0;
         if (!OUT64) surf = surfs[slot];
@@ -193,13 +199,14 @@ __global__ void __launch_bounds__(BLUR_THREADS) blur_norm_kernel(const long long
             }
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
+                // (rows past the strip, in its last chunk only, run through the arithmetic too and store nothing: a uniform
+                // trip count keeps the shuffles free of divergence handling)
                 const int y = yb + j;
-                if (y > y1) break;
                 const double c = cs[j] * (1.0 / kQ);
                 const double l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
                 // row pass, generic cv::RowFilter order: left, centre, right
                 const double down = __dadd_rn(__dadd_rn(__dmul_rn(l, k0), __dmul_rn(c, k1)), __dmul_rn(r, k0));
-                if (y > y0 && out_col) {
+                if (y > y0 && y <= y1 && out_col) {
                     // cv::SymmColumnFilter order: centre, then k*(up+down); the value of output row y - 1
                     const double v = __dadd_rn(__dmul_rn(k1, mid), __dmul_rn(k0, __dadd_rn(up, down)));
                     if (OUT64) {
@@ -319,6 +326,23 @@ __global__ void __launch_bounds__(MORPH_THREADS) morph_level_kernel(const cudaTe
     }
 }
 
+// Unused dynamic shared memory requested by the blur launch (EDSGPU_BUILD_PAD_KB tunes it, 0 = none).  Measured on the
+// benchmark step, where the build of the next window runs beside the batched solve: with the 40-register blur kernel and no
+// dynamic shared memory the step takes 0.699 ms, with 1 / 4 / 8-25 / 50 / 100 KB per CTA 0.679 / 0.668 / 0.660 / 0.669 /
+// 0.688 ms, although the kernel alone runs equally fast either way; padding the clear and scatter launches as well loses
+// 0.010 ms again.  The request changes the shared-memory / L1 split the driver configures on
+// the SMs that alternate between build CTAs and the solve's CTAs; asking for the maximum carveout everywhere instead costs
+// the solve its L1 (0.72-0.75 ms).
+size_t build_pad_bytes() {
+    static long kb = -1;
+    if (kb < 0) {
+        const char* e = getenv("EDSGPU_BUILD_PAD_KB");
+        kb = e ? std::max(0, atoi(e)) : 16;
+        if (kb > 40) kb = 40;
+    }
+    return (size_t)kb * 1024;
+}
+
 edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, int count, const edsgpu_lut* lut,
                             const uint16_t* x_dev, const uint16_t* y_dev, const uint8_t* pol_dev, int E, int mode, int use_exp, float sigma) {
     EDS_RANGE("edsgpu_event_frame_create (launch)");
@@ -384,7 +408,8 @@ edsgpu_status launch_frames(edsgpu_ctx* ctx, edsgpu_frames* fr, int first_slot, 
         }
         {
             dim3 grid(blur_ctas(H, W), 1, n);
-            blur_norm_kernel<false><<<grid, BLUR_THREADS, 0, bs>>>(fr->acc, H, W, k0, k1, fr->surf_dev, fr->partials, fr->tickets, fr->norms,
+            const size_t pad = build_pad_bytes();
+            blur_norm_kernel<false><<<grid, BLUR_THREADS, pad, bs>>>(fr->acc, H, W, k0, k1, fr->surf_dev, fr->partials, fr->tickets, fr->norms,
                                                                     first_slot + c0, acc0, nullptr, nullptr);
             ctx->launches++;
             EDS_CUDA(ctx, cudaGetLastError());
