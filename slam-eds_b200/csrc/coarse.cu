@@ -292,8 +292,9 @@ struct edsgpu_coarse {
     std::vector<Level> levels;
     double* partials = nullptr;  // [max grid][CT_NPART] + CT_NPART result
     int max_grid = 0;
-    void* track_io = nullptr;        // TrackIO of edsgpu_coarse_track (device)
-    unsigned* track_bar = nullptr;   // {arrivals, generation} of its grid barrier
+    unsigned* track_bar = nullptr;   // arrival counter of its grid barrier
+    unsigned track_bar_count = 0;    // host mirror of the counter; track_bar_dirty: a launch failed, reset both first
+    bool track_bar_dirty = false;
 };
 
 extern "C" {
@@ -307,7 +308,6 @@ edsgpu_status edsgpu_coarse_create(edsgpu_ctx* ctx, int num_levels, edsgpu_coars
     c->levels.resize(num_levels);
     c->max_grid = 2 * ctx->num_sms;
     cudaError_t e = cudaMalloc(&c->partials, sizeof(double) * CT_NPART * ((size_t)c->max_grid + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&c->track_io, 1024);
     if (e == cudaSuccess) e = cudaMalloc(&c->track_bar, 2 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemsetAsync(c->track_bar, 0, 2 * sizeof(unsigned), ctx->stream);
     if (e != cudaSuccess) { edsgpu_coarse_destroy(c); return edsgpu_fail(ctx, EDSGPU_CUDA_ERROR, cudaGetErrorString(e)); }
@@ -327,7 +327,6 @@ void edsgpu_coarse_destroy(edsgpu_coarse* c) {
         if (l.rows) cudaFree(l.rows);
     }
     if (c->partials) cudaFree(c->partials);
-    if (c->track_io) cudaFree(c->track_io);
     if (c->track_bar) cudaFree(c->track_bar);
     delete c;
 }
@@ -542,46 +541,56 @@ edsgpu_status edsgpu_coarse_calc_res_gs(edsgpu_coarse* c, int lvl, const double 
 // ---- trackNewestCoarse ---------------------------------------------------------------------------------------
 namespace {
 
-// Sophus SO3::exp (quaternion form) -> rotation matrix, row-major
-__device__ void so3_exp(const double* w, double* R) {
-    const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
-    double imag, real;
-    if (th < 1e-10) {
-        const double th4 = th2 * th2;
-        imag = 0.5 - th2 / 48.0 + th4 / 3840.0;
-        real = 1.0 - th2 / 8.0 + th4 / 384.0;
-    } else {
-        imag = sin(0.5 * th) / th;
-        real = cos(0.5 * th);
-    }
-    const double x = imag * w[0], y = imag * w[1], z = imag * w[2], q = real;
-    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * q); R[2] = 2 * (x * z + y * q);
-    R[3] = 2 * (x * y + z * q); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * q);
-    R[6] = 2 * (x * z - y * q); R[7] = 2 * (y * z + x * q); R[8] = 1 - 2 * (x * x + y * y);
-}
-
-// (R, t) <- SE3::exp(inc) * (R, t), inc = [translation part, rotation part]
+// (R, t) <- SE3::exp(inc) * (R, t), inc = [translation part, rotation part].  Sophus SO3::exp (quaternion form) for the
+// rotation; sin / cos of the full angle in the translation's V matrix come from the half-angle pair by the double-angle
+// identities (one sincos instead of four libm calls on the single thread that runs this).
 __device__ void se3_left_update(const double* inc6, double* R, double* t) {
     const double* u = inc6;
     const double* w = inc6 + 3;
     double Re[9], V[9];
-    so3_exp(w, Re);
     const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+    const bool small = th < 1e-10;
+    double imag, real, A = 0.0, B = 0.0;
+    if (small) {
+        const double th4 = th2 * th2;
+        imag = 0.5 - th2 / 48.0 + th4 / 3840.0;
+        real = 1.0 - th2 / 8.0 + th4 / 384.0;
+    } else {
+        double sh, ch;
+        sincos(0.5 * th, &sh, &ch);
+        const double ith = 1.0 / th;
+        imag = sh * ith;
+        real = ch;
+        const double ith2 = ith * ith;
+        A = 2.0 * sh * sh * ith2;                  // (1 - cos th) / th^2
+        B = (th - 2.0 * sh * ch) * (ith2 * ith);  // (th - sin th) / th^3
+    }
+    {
+        const double x = imag * w[0], y = imag * w[1], z = imag * w[2], q = real;
+        Re[0] = 1 - 2 * (y * y + z * z); Re[1] = 2 * (x * y - z * q); Re[2] = 2 * (x * z + y * q);
+        Re[3] = 2 * (x * y + z * q); Re[4] = 1 - 2 * (x * x + z * z); Re[5] = 2 * (y * z - x * q);
+        Re[6] = 2 * (x * z - y * q); Re[7] = 2 * (y * z + x * q); Re[8] = 1 - 2 * (x * x + y * y);
+    }
     const double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
-    if (th < 1e-10) {
+    if (small) {
         for (int i = 0; i < 9; ++i) V[i] = Re[i];
     } else {
-        const double A = (1.0 - cos(th)) / th2, B = (th - sin(th)) / (th2 * th);
+#pragma unroll
         for (int r = 0; r < 3; ++r)
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
                 double w2 = 0;
+#pragma unroll
                 for (int k = 0; k < 3; ++k) w2 += W[3 * r + k] * W[3 * k + c];
                 V[3 * r + c] = (r == c ? 1.0 : 0.0) + A * W[3 * r + c] + B * w2;
             }
     }
     double te[3], Rn[9], tn[3];
+#pragma unroll
     for (int r = 0; r < 3; ++r) te[r] = V[3 * r] * u[0] + V[3 * r + 1] * u[1] + V[3 * r + 2] * u[2];
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
+#pragma unroll
         for (int c = 0; c < 3; ++c) Rn[3 * r + c] = Re[3 * r] * R[c] + Re[3 * r + 1] * R[3 + c] + Re[3 * r + 2] * R[6 + c];
         tn[r] = Re[3 * r] * t[0] + Re[3 * r + 1] * t[1] + Re[3 * r + 2] * t[2] + te[r];
     }
@@ -589,50 +598,13 @@ __device__ void se3_left_update(const double* inc6, double* R, double* t) {
     for (int i = 0; i < 3; ++i) t[i] = tn[i];
 }
 
-// x = A^-1 rhs, A symmetric positive definite 8x8 (LDL^T; the reference calls Eigen's ldlt().solve)
-__device__ void solve8(const double* A, const double* rhs, double* x) {
-    // fully unrolled: on the device every index is a compile-time constant and L, D, y live in registers
-    double L[64] = {0}, D[8], y[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        double d = A[8 * j + j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) d -= L[8 * j + k] * L[8 * j + k] * D[k];
-        D[j] = d;
-        L[8 * j + j] = 1.0;
-#pragma unroll
-        for (int i = j + 1; i < 8; ++i) {
-            double v = A[8 * i + j];
-#pragma unroll
-            for (int k = 0; k < j; ++k) v -= L[8 * i + k] * L[8 * j + k] * D[k];
-            L[8 * i + j] = v / d;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        double v = rhs[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) v -= L[8 * i + k] * y[k];
-        y[i] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] /= D[i];
-#pragma unroll
-    for (int i = 7; i >= 0; --i) {
-        double v = y[i];
-#pragma unroll
-        for (int k = i + 1; k < 8; ++k) v -= L[8 * k + i] * x[k];
-        x[i] = v;
-    }
-}
-
-
 // ------------------------------------------------------------------------------------------
 // trackNewestCoarse on the device: ONE cooperative launch runs the whole coarse-to-fine loop.  Every evaluation is a
 // sweep of the level's points by all CTAs, one grid barrier, then every CTA adds the per-CTA partials in order and its
 // thread 0 advances the (identical) state machine: Levenberg damping, 8x8 LDL^T, SE3::exp update, accept / reject,
 // cutoff repeat, level change.  No host round trip inside the loop (it cost ~40 us per evaluation).
 // ------------------------------------------------------------------------------------------
+constexpr int CT_MAX_PER = 19;  // ceil(148 / 8): CTAs per eighth in the ordered sum of the partials
 constexpr int CT_MAX_LEVELS = 5, CT_TRACK_THREADS = 512;  // wide CTAs: fewer of them at the grid barrier and in the ordered sum  // PYR_LEVELS the loop can visit (coarsest_lvl < 5, CoarseTracker.cpp:540)
 
 struct LevelDev {
@@ -654,40 +626,36 @@ struct TrackIO {  // global memory, in-out
 
 struct TrackArgs {
     LevelDev lv[CT_MAX_LEVELS];
-    TrackIO* io;
+    TrackIO in;        // the request travels as a kernel parameter: no upload
+    TrackIO* io;       // the result: pinned host memory the device writes directly, no copy back
     double* partials;  // [2][gridDim.x][CT_NPART], double-buffered by evaluation
-    unsigned* bar;     // {arrivals, generation} of the grid barrier
+    unsigned* bar;     // arrival counter of the grid barrier
+    unsigned bar_base; // its value when this launch starts (the host keeps count: one barrier per evaluation)
 };
 
 struct TrackCtl {  // shared memory; written by thread 0 only
     double Rc[9], tc[3], affc[2];   // accepted pose
     double Rn[9], tn[3], affn[2];   // proposal under evaluation
     double H[64], b[8], resOld[6], inc[8];
+    double Hn[64], bn[8];           // the system of the evaluation just reduced
     float lambda, repeat;
-    int lvl, iteration, state, haveRepeated, ok, evaluations, done;
+    int lvl, iteration, state, haveRepeated, ok, evaluations, done, take, action;
     CoarseArgs a;                   // the evaluation every thread sweeps next
     double out[8];                  // lastResiduals (5), lastFlowIndicators (3): every CTA keeps its own copy, CTA 0 writes them out
 };
 enum { TS_FIRST = 0, TS_ITER = 1 };
 
-// sense-reversing grid barrier (cooperative launch: every CTA is resident)
-__device__ __forceinline__ void track_grid_barrier(unsigned* bar) {
+// grid barrier (cooperative launch: every CTA is resident): one arrival counter that only grows, the k-th barrier of a
+// launch is passed when it reaches base + (k + 1) * gridDim.x.  One release-add and one polled word per CTA; the writes
+// of the CTA's other threads are ordered before the add by the __syncthreads (causality order), no separate fences.
+__device__ __forceinline__ void track_grid_barrier(unsigned* bar, unsigned target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned gen;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
-        __threadfence();
-        if (atomicAdd(bar, 1u) == gridDim.x - 1u) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            unsigned g2;
-            do {  // spin: a handful of CTAs poll one word, the wait is a few microseconds at most
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(bar + 1) : "memory");
-            } while (g2 == gen);
-        }
-        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        unsigned cur;
+        do {  // spin: a handful of CTAs poll one word, the wait is a few microseconds at most
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
+        } while ((int)(cur - target) < 0);
     }
     __syncthreads();
 }
@@ -745,90 +713,167 @@ __host__ __device__ void coarse_outputs(const double* v, double* rs, double* H, 
     }
 }
 
-// thread 0: consume the evaluation that has just been reduced into `sums`, decide what happens next (CoarseTracker.cpp:540-701)
-__device__ void track_advance(TrackCtl& c, const TrackArgs& A, const TrackIO& io, double* out, const double* sums) {
+// x = A^-1 rhs, A symmetric positive definite 8x8, by LDL^T (the reference calls Eigen's ldlt().solve): one matrix row per
+// lane (lanes 0..7 of a warp; all 32 lanes must call).  A column costs one dependent chain instead of one per row, and one reciprocal instead of a division per entry.
+__device__ __forceinline__ double solve8_warp(const double* row, double rhs, int lane) {
+    double l[8], ut[8];  // l: this lane's row of L; ut: this lane's row of L^T (its column of L), collected for the back substitution
+    double dinv_mine = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { l[i] = 0.0; ut[i] = 0.0; }
+    double D[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double v = row[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+            const double ljk = __shfl_sync(0xffffffffu, l[k], j);
+            v -= l[k] * ljk * D[k];
+        }
+        const double d = __shfl_sync(0xffffffffu, v, j);
+        D[j] = d;
+        const double dinv = 1.0 / d;
+        if (lane == j) dinv_mine = dinv;
+        const double lij = lane > j ? v * dinv : (lane == j ? 1.0 : 0.0);
+        l[j] = lij;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) {
+            const double t = __shfl_sync(0xffffffffu, lij, i);
+            if (lane == j) ut[i] = t;
+        }
+    }
+    double y = rhs;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const double yk = __shfl_sync(0xffffffffu, y, k);
+        if (lane > k) y -= l[k] * yk;
+    }
+    double x = y * dinv_mine;
+#pragma unroll
+    for (int k = 7; k > 0; --k) {
+        const double xk = __shfl_sync(0xffffffffu, x, k);
+        if (lane < k) x -= ut[k] * xk;
+    }
+    return x;
+}
+
+// Warp 0 of every CTA: consume the evaluation that has just been reduced into `sums`, decide what happens next
+// (CoarseTracker.cpp:540-701).  The scalar decisions are lane 0's; forming the 8x8 system from the sums, keeping it on an
+// accepted step and the damped solve are spread over the lanes.
+__device__ void track_advance(TrackCtl& c, const TrackArgs& A, const TrackIO& io, double* out, const double* sums, int lane) {
     const int maxIterations[5] = {10, 20, 100, 100, 100};
     const float lambdaExtrapolationLimit = 0.001f;
-    double rs[6], Hn[64], bn[8];
-    coarse_outputs(sums, rs, Hn, bn);
-    bool level_end = false;
-    if (c.state == TS_FIRST) {
-        for (int i = 0; i < 6; ++i) c.resOld[i] = rs[i];
-        for (int i = 0; i < 64; ++i) c.H[i] = Hn[i];
-        for (int i = 0; i < 8; ++i) c.b[i] = bn[i];
-        if (c.resOld[5] > 0.6 && c.repeat < 50) {
-            c.repeat *= 2;
-            track_request(c, A, io, c.lvl, c.Rc, c.tc, c.affc);
-            return;
+    enum { ACT_REPEAT = 0, ACT_PROPOSE = 1, ACT_LEVEL_END = 2 };
+    // H_out = acc.H.topLeftCorner<8,8>().cast<double>() * (1.0f / n), n padded to a multiple of 4 (:466-478, :332-344): coarse_outputs, entry by entry
+    {
+        const long long npad = ((long long)sums[CT_NACC + 2] + 3) / 4 * 4;
+        const float inv_n = 1.0f / (float)npad;
+        for (int idx = lane; idx < 72; idx += 32) {
+            const int r = idx < 64 ? idx >> 3 : idx - 64, q = idx < 64 ? idx & 7 : 8;
+            const int lo = min(r, q), hi = max(r, q);
+            const int e = lo * 9 - lo * (lo - 1) / 2 + (hi - lo);  // index of (lo, hi) in the row-major upper triangle of the 9x9
+            const double sr = r == 6 ? 10.0f : (r == 7 ? 1000.0f : 1.0), sq = q == 6 ? 10.0f : (q == 7 ? 1000.0f : 1.0);
+            const double v = (double)(float)sums[e] * inv_n;
+            if (idx < 64) c.Hn[idx] = v * (sr * sq);
+            else c.bn[r] = v * sr;
         }
-        c.lambda = 0.01f;
-        c.iteration = 0;
-    } else {
-        const bool accept = (rs[0] / rs[1]) < (c.resOld[0] / c.resOld[1]);
-        if (accept) {
-            for (int i = 0; i < 64; ++i) c.H[i] = Hn[i];
-            for (int i = 0; i < 8; ++i) c.b[i] = bn[i];
-            for (int i = 0; i < 6; ++i) c.resOld[i] = rs[i];
-            c.affc[0] = c.affn[0]; c.affc[1] = c.affn[1];
-            for (int i = 0; i < 9; ++i) c.Rc[i] = c.Rn[i];
-            for (int i = 0; i < 3; ++i) c.tc[i] = c.tn[i];
-            c.lambda *= 0.5f;
-        } else {
-            c.lambda *= 4;
-            if (c.lambda < lambdaExtrapolationLimit) c.lambda = lambdaExtrapolationLimit;
-        }
-        double norm2 = 0;
-        for (int i = 0; i < 8; ++i) norm2 += c.inc[i] * c.inc[i];
-        if (!(sqrt(norm2) > 1e-3)) level_end = true;
-        c.iteration++;
     }
-    for (;;) {
-        if (!level_end && c.iteration < maxIterations[c.lvl]) {
-            // propose a step
-            double Hl[64], nb[8];
-            for (int i = 0; i < 64; ++i) Hl[i] = c.H[i];
-            for (int i = 0; i < 8; ++i) { Hl[9 * i] *= (1 + c.lambda); nb[i] = -c.b[i]; }
-            solve8(Hl, nb, c.inc);  // both affine parameters are optimised (setting_affineOptModeA/B >= 0, settings.cpp:119-120)
-            float extrapFac = 1;
-            if (c.lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / c.lambda));
-            for (int i = 0; i < 8; ++i) c.inc[i] *= extrapFac;
-            double incScaled[8];
-            for (int i = 0; i < 8; ++i) incScaled[i] = c.inc[i];
-            incScaled[6] *= 10.0f;    // SCALE_A (SCALE_XI_ROT = SCALE_XI_TRANS = 1)
-            incScaled[7] *= 1000.0f;  // SCALE_B
-            double sum = 0;
-            for (int i = 0; i < 8; ++i) sum += incScaled[i];
-            if (!isfinite(sum))
-                for (int i = 0; i < 8; ++i) incScaled[i] = 0;
-            c.affn[0] = c.affc[0] + incScaled[6];
-            c.affn[1] = c.affc[1] + incScaled[7];
-            for (int i = 0; i < 9; ++i) c.Rn[i] = c.Rc[i];
-            for (int i = 0; i < 3; ++i) c.tn[i] = c.tc[i];
-            se3_left_update(incScaled, c.Rn, c.tn);
-            c.state = TS_ITER;
-            track_request(c, A, io, c.lvl, c.Rn, c.tn, c.affn);  // the fused evaluation already has the system the reference recomputes on accept
-            return;
+    if (lane == 0) {
+        double rs[6];
+        coarse_outputs(sums, rs, nullptr, nullptr);
+        bool level_end = false;
+        c.take = 0;
+        if (c.state == TS_FIRST) {
+            for (int i = 0; i < 6; ++i) c.resOld[i] = rs[i];
+            c.take = 1;
+            if (c.resOld[5] > 0.6 && c.repeat < 50) {
+                c.repeat *= 2;
+                c.action = ACT_REPEAT;
+            } else {
+                c.lambda = 0.01f;
+                c.iteration = 0;
+                c.action = ACT_PROPOSE;  // maxIterations >= 10
+            }
+        } else {
+            const bool accept = (rs[0] / rs[1]) < (c.resOld[0] / c.resOld[1]);
+            if (accept) {
+                c.take = 1;
+                for (int i = 0; i < 6; ++i) c.resOld[i] = rs[i];
+                c.affc[0] = c.affn[0]; c.affc[1] = c.affn[1];
+                for (int i = 0; i < 9; ++i) c.Rc[i] = c.Rn[i];
+                for (int i = 0; i < 3; ++i) c.tc[i] = c.tn[i];
+                c.lambda *= 0.5f;
+            } else {
+                c.lambda *= 4;
+                if (c.lambda < lambdaExtrapolationLimit) c.lambda = lambdaExtrapolationLimit;
+            }
+            double norm2 = 0;
+            for (int i = 0; i < 8; ++i) norm2 += c.inc[i] * c.inc[i];
+            if (!(sqrt(norm2) > 1e-3)) level_end = true;
+            c.iteration++;
+            c.action = (!level_end && c.iteration < maxIterations[c.lvl]) ? ACT_PROPOSE : ACT_LEVEL_END;
         }
-        // the level is finished
-        out[c.lvl] = sqrtf((float)(c.resOld[0] / c.resOld[1]));
-        for (int i = 0; i < 3; ++i) out[5 + i] = c.resOld[2 + i];
-        if (io.has_min_res && out[c.lvl] > 1.5 * io.min_res[c.lvl]) c.ok = 0;
-        if (c.ok && c.repeat > 1 && !c.haveRepeated) { c.lvl++; c.haveRepeated = 1; }
-        c.lvl--;
-        if (c.lvl < 0 || !c.ok) { c.done = 1; return; }
-        c.repeat = 1;
-        c.state = TS_FIRST;
+    }
+    __syncwarp();
+    if (c.take) {
+        for (int idx = lane; idx < 72; idx += 32) {
+            if (idx < 64) c.H[idx] = c.Hn[idx];
+            else c.b[idx - 64] = c.bn[idx - 64];
+        }
+        __syncwarp();
+    }
+    const int action = c.action;
+    if (action == ACT_PROPOSE) {
+        // propose a step: both affine parameters are optimised (setting_affineOptModeA/B >= 0, settings.cpp:119-120)
+        double row[8];
+        const int r = lane & 7;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) row[q] = c.H[8 * r + q] * (q == r ? (double)(1 + c.lambda) : 1.0);
+        const double x = solve8_warp(row, -c.b[r], lane);
+        float extrapFac = 1;
+        if (c.lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / c.lambda));
+        if (lane < 8) c.inc[lane] = x * extrapFac;
+        __syncwarp();
+    }
+    if (lane != 0) return;
+    if (action == ACT_REPEAT) {
         track_request(c, A, io, c.lvl, c.Rc, c.tc, c.affc);
         return;
     }
+    if (action == ACT_PROPOSE) {
+        double incScaled[8];
+        for (int i = 0; i < 8; ++i) incScaled[i] = c.inc[i];
+        incScaled[6] *= 10.0f;    // SCALE_A (SCALE_XI_ROT = SCALE_XI_TRANS = 1)
+        incScaled[7] *= 1000.0f;  // SCALE_B
+        double sum = 0;
+        for (int i = 0; i < 8; ++i) sum += incScaled[i];
+        if (!isfinite(sum))
+            for (int i = 0; i < 8; ++i) incScaled[i] = 0;
+        c.affn[0] = c.affc[0] + incScaled[6];
+        c.affn[1] = c.affc[1] + incScaled[7];
+        for (int i = 0; i < 9; ++i) c.Rn[i] = c.Rc[i];
+        for (int i = 0; i < 3; ++i) c.tn[i] = c.tc[i];
+        se3_left_update(incScaled, c.Rn, c.tn);
+        c.state = TS_ITER;
+        track_request(c, A, io, c.lvl, c.Rn, c.tn, c.affn);  // the fused evaluation already has the system the reference recomputes on accept
+        return;
+    }
+    // the level is finished
+    out[c.lvl] = sqrtf((float)(c.resOld[0] / c.resOld[1]));
+    for (int i = 0; i < 3; ++i) out[5 + i] = c.resOld[2 + i];
+    if (io.has_min_res && out[c.lvl] > 1.5 * io.min_res[c.lvl]) c.ok = 0;
+    if (c.ok && c.repeat > 1 && !c.haveRepeated) { c.lvl++; c.haveRepeated = 1; }
+    c.lvl--;
+    if (c.lvl < 0 || !c.ok) { c.done = 1; return; }
+    c.repeat = 1;
+    c.state = TS_FIRST;
+    track_request(c, A, io, c.lvl, c.Rc, c.tc, c.affc);
 }
 
 __global__ void __launch_bounds__(CT_TRACK_THREADS) coarse_track_kernel(TrackArgs A) {
     __shared__ double red[CT_TRACK_THREADS / 32][CT_NPART];
-    __shared__ double quarter[4][CT_NPART];
     __shared__ double sums[CT_NPART];
     __shared__ TrackCtl c;
-    TrackIO& io = *A.io;  // inputs are only read inside the loop; CTA 0 writes the outputs once, at the end
+    const TrackIO& io = A.in;  // inputs are only read inside the loop; CTA 0 writes the outputs once, at the end
     if (threadIdx.x == 0) {
         // every CTA runs the same state machine on the same numbers
         for (int i = 0; i < 9; ++i) c.Rc[i] = io.R[i];
@@ -844,36 +889,45 @@ __global__ void __launch_bounds__(CT_TRACK_THREADS) coarse_track_kernel(TrackArg
     for (unsigned k = 0;; ++k) {
         double* buf = A.partials + (size_t)(k & 1u) * gridDim.x * CT_NPART;
         coarse_sweep<CT_TRACK_THREADS>(c.a, red, buf + (size_t)blockIdx.x * CT_NPART);
-        track_grid_barrier(A.bar);
-        // ordered sum over the CTAs: four threads per entry take a quarter of them each (fixed partition), then the quarters in order
-        if (threadIdx.x < 4 * CT_NPART) {
-            const int e = threadIdx.x % CT_NPART, q = threadIdx.x / CT_NPART;
-            const unsigned per = (gridDim.x + 3u) / 4u, b0 = q * per, b1 = min(gridDim.x, b0 + per);
+        track_grid_barrier(A.bar, A.bar_base + (k + 1u) * gridDim.x);
+        // ordered sum over the CTAs: eight threads per entry take an eighth of them each (fixed partition, loads issued
+        // together), then the eighths are added in order within the eight lanes
+        if (threadIdx.x < 8 * CT_NPART) {
+            const int e = threadIdx.x >> 3, q = threadIdx.x & 7;
+            const unsigned per = (gridDim.x + 7u) / 8u, b0 = q * per;
+            double v[CT_MAX_PER];
+#pragma unroll
+            for (unsigned i = 0; i < CT_MAX_PER; ++i) v[i] = (i < per && b0 + i < gridDim.x) ? __ldcg(buf + (size_t)(b0 + i) * CT_NPART + e) : 0.0;
             double s = 0.0;
-            for (unsigned b = b0; b < b1; ++b) s += __ldcg(buf + (size_t)b * CT_NPART + e);
-            quarter[q][e] = s;
+#pragma unroll
+            for (unsigned i = 0; i < CT_MAX_PER; ++i)
+                if (i < per) s += v[i];
+            // lanes 8g .. 8g+7 hold the eighths of one entry: ((((((e0 + e1) + e2) + e3) + e4) + e5) + e6) + e7
+            const unsigned base = threadIdx.x & 24u;
+            double t = __shfl_sync(0xffffffffu, s, base);
+#pragma unroll
+            for (unsigned i = 1; i < 8; ++i) t += __shfl_sync(0xffffffffu, s, base + i);
+            if (q == 0) sums[e] = t;
         }
         __syncthreads();
-        if (threadIdx.x < CT_NPART) sums[threadIdx.x] = ((quarter[0][threadIdx.x] + quarter[1][threadIdx.x]) + quarter[2][threadIdx.x]) + quarter[3][threadIdx.x];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            track_advance(c, A, io, c.out, sums);
-        }
+        if (threadIdx.x < 32) track_advance(c, A, io, c.out, sums, threadIdx.x);
         __syncthreads();
         if (c.done) break;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        io.evaluations = c.evaluations;
-        for (int i = 0; i < 5; ++i) io.last_residuals[i] = c.out[i];
-        for (int i = 0; i < 3; ++i) io.last_flow[i] = c.out[5 + i];
-        io.status = 0;
-        if (!c.ok) io.status = 1;
+        TrackIO& o = *A.io;
+        o.evaluations = c.evaluations;
+        for (int i = 0; i < 5; ++i) o.last_residuals[i] = c.out[i];
+        for (int i = 0; i < 3; ++i) o.last_flow[i] = c.out[5 + i];
+        int status = 0;
+        if (!c.ok) status = 1;
         else {
-            for (int i = 0; i < 9; ++i) io.R[i] = c.Rc[i];
-            for (int i = 0; i < 3; ++i) io.t[i] = c.tc[i];
-            io.aff[0] = c.affc[0]; io.aff[1] = c.affc[1];
-            if (fabsf((float)c.affc[0]) > 1.2f || fabsf((float)c.affc[1]) > 200.f) io.status = 2;  // :683-685
+            for (int i = 0; i < 9; ++i) o.R[i] = c.Rc[i];
+            for (int i = 0; i < 3; ++i) o.t[i] = c.tc[i];
+            o.aff[0] = c.affc[0]; o.aff[1] = c.affc[1];
+            if (fabsf((float)c.affc[0]) > 1.2f || fabsf((float)c.affc[1]) > 200.f) status = 2;  // :683-685
         }
+        o.status = status;
     }
 }
 
@@ -905,27 +959,35 @@ edsgpu_status edsgpu_coarse_track(edsgpu_coarse* c, int coarsest_lvl, double R[9
     edsgpu_status st = edsgpu_ensure_pinned(ctx, sizeof(TrackIO));
     if (st != EDSGPU_OK) return st;
     TrackIO* h = (TrackIO*)ctx->pinned;
-    memset(h, 0, sizeof(TrackIO));
-    memcpy(h->R, R, sizeof(h->R)); memcpy(h->t, t, sizeof(h->t));
-    h->aff[0] = aff_g2l[0]; h->aff[1] = aff_g2l[1];
-    h->ref_aff[0] = ref_aff_g2l[0]; h->ref_aff[1] = ref_aff_g2l[1];
-    h->ref_exposure = ref_exposure; h->new_exposure = new_exposure;
-    h->has_min_res = min_res_for_abort ? 1 : 0;
-    if (min_res_for_abort) memcpy(h->min_res, min_res_for_abort, sizeof(h->min_res));
-    h->coarsest = coarsest_lvl;
-    for (int i = 0; i < 5; ++i) h->last_residuals[i] = NAN;
-    for (int i = 0; i < 3; ++i) h->last_flow[i] = 1000;
-    EDS_CUDA(ctx, cudaMemcpyAsync(c->track_io, h, sizeof(TrackIO), cudaMemcpyHostToDevice, ctx->stream));
-    A.io = (TrackIO*)c->track_io;
+    TrackIO& in = A.in;
+    memcpy(in.R, R, sizeof(in.R)); memcpy(in.t, t, sizeof(in.t));
+    in.aff[0] = aff_g2l[0]; in.aff[1] = aff_g2l[1];
+    in.ref_aff[0] = ref_aff_g2l[0]; in.ref_aff[1] = ref_aff_g2l[1];
+    in.ref_exposure = ref_exposure; in.new_exposure = new_exposure;
+    in.has_min_res = min_res_for_abort ? 1 : 0;
+    if (min_res_for_abort) memcpy(in.min_res, min_res_for_abort, sizeof(in.min_res));
+    in.coarsest = coarsest_lvl;
+    for (int i = 0; i < 5; ++i) in.last_residuals[i] = NAN;
+    for (int i = 0; i < 3; ++i) in.last_flow[i] = 1000;
+    *h = in;  // a failed track leaves R, t, aff as they came
+    EDS_CUDA(ctx, cudaHostGetDevicePointer((void**)&A.io, h, 0));
     A.partials = c->partials;
     A.bar = c->track_bar;
     // one CTA per 512 points of the largest level, at most one per SM (cooperative launch: all resident)
     const int grid = std::max(1, std::min((nmax + CT_TRACK_THREADS - 1) / CT_TRACK_THREADS, std::min(ctx->num_sms, c->max_grid / 2)));
+    if (c->track_bar_dirty) {
+        EDS_CUDA(ctx, cudaMemsetAsync(c->track_bar, 0, 2 * sizeof(unsigned), ctx->stream));
+        c->track_bar_count = 0;
+        c->track_bar_dirty = false;
+    }
+    A.bar_base = c->track_bar_count;
     void* argv[] = {(void*)&A};
+    c->track_bar_dirty = true;  // until the launch is known to have run to its end
     EDS_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)coarse_track_kernel, dim3(grid), dim3(CT_TRACK_THREADS), argv, 0, ctx->stream));
     ctx->launches++;
-    EDS_CUDA(ctx, cudaMemcpyAsync(h, c->track_io, sizeof(TrackIO), cudaMemcpyDeviceToHost, ctx->stream));
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    c->track_bar_count += (unsigned)h->evaluations * (unsigned)grid;  // one barrier per evaluation
+    c->track_bar_dirty = false;
     for (int i = 0; i < 5; ++i) last_residuals[i] = h->last_residuals[i];
     for (int i = 0; i < 3; ++i) last_flow[i] = h->last_flow[i];
     if (evaluations_out) *evaluations_out = h->evaluations;
