@@ -137,7 +137,9 @@ __device__ __forceinline__ void coarse_sweep(const CoarseArgs& a, double (*red)[
     {
         float a48[48];
 #pragma unroll
-        for (int i = 0; i < 48; ++i) a48[i] = i < CT_NACC ? acc[i] : 0.f;
+        for (int i = 0; i < CT_NACC; ++i) a48[i] = acc[i];
+        // the three free slots carry the counts (small integers: exact in fp32 in any order)
+        a48[45] = (float)nE; a48[46] = (float)nW; a48[47] = (float)nSat;
         halving_step<24, 16>(a48, lane);
         halving_step<12, 8>(a48, lane);
         halving_step<6, 4>(a48, lane);
@@ -147,16 +149,15 @@ __device__ __forceinline__ void coarse_sweep(const CoarseArgs& a, double (*red)[
         if ((lane & 1) == 0) {
             const int b0 = 24 * ((lane >> 4) & 1) + 12 * ((lane >> 3) & 1) + 6 * ((lane >> 2) & 1) + 3 * ((lane >> 1) & 1);
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if (b0 + i < CT_NACC) red[warp][b0 + i] = (double)a48[i];
+            for (int i = 0; i < 3; ++i) red[warp][b0 + i < CT_NACC ? b0 + i : b0 + i + 1] = (double)a48[i];  // slots 45..47 -> nE, nW, nSat behind E
         }
-        double st[7] = {E, (double)nE, (double)nW, (double)nSat, (double)shT, (double)shRT, (double)nShift};
+        double st[4] = {E, (double)shT, (double)shRT, (double)nShift};
 #pragma unroll
-        for (int i = 0; i < 7; ++i) {
+        for (int i = 0; i < 4; ++i) {
             double s = st[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) red[warp][CT_NACC + i] = s;
+            if (lane == 0) red[warp][i == 0 ? CT_NACC : CT_NACC + 3 + i] = s;
         }
     }
     __syncthreads();
