@@ -848,55 +848,65 @@ __global__ void ba_sc_hcc_kernel(int F, const double* __restrict__ hcc_host, dou
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double adj(const double* A, int r, int c) { return A[c * 8 + r]; }  // Mat88 column-major
 
-// out(i,j) += sum_m L(i,m) T(m,j), T(m,j) = sum_n C(m,n) Rt(j,n), C given by functor c(m,n); thread (i,j) of a 64-thread CTA.
-// The CTA forms T once (thread (i,j) computes T(i,j)) and shares it through `sh` (two 8x8 buffers used alternately, `turn`
-// counts the calls: one barrier per sandwich) instead of every thread recomputing the column of T it needs from global
-// memory -- same products in the same order, an eighth of the loads and a quarter of the multiplications.  Must be called by
-// all 64 threads.
-struct SandwichShared { double T[2][64]; };
-template <typename CF>
-__device__ __forceinline__ double sandwich(SandwichShared& sh, int& turn, const double* L, CF c, const double* Rm, int i, int j) {
-    double t = 0.0;
-#pragma unroll
-    for (int n = 0; n < 8; ++n) t += c(i, n) * adj(Rm, j, n);
-    double* T = sh.T[turn & 1];
-    ++turn;
-    T[8 * i + j] = t;
-    __syncthreads();  // the buffer of two calls ago is free again: every thread has passed the barrier of the call in between
+// A frame block of a stitched matrix is a sum of sandwiches  L C R^T  (adjoint, accumulator block, adjoint):
+//   out(i,j) = sum_k ( sum_m L_k(i,m) T_k(m,j) ),  T_k(m,j) = sum_n C_k(m,n) R_k(j,n),  thread (i,j) of a 64-thread CTA.
+// The CTA first forms the T_k of a chunk of terms (thread (i,j) computes T_k(i,j); the loads of different terms are
+// independent, so they overlap), shares them through shared memory, then adds the terms in their fixed order: two barriers
+// per chunk instead of one dependent global-memory round trip per term.  Same products in the same order as a term-by-term
+// evaluation.
+struct StitchTerm { const double *L, *C, *R; int ldc; };  // C(m,n) = C[ldc * m + n]; L, R: Mat88 column-major
+constexpr int STITCH_CHUNK = 24;
+struct StitchShared { double T[STITCH_CHUNK][64]; };
+
+template <typename TermFn>
+__device__ __forceinline__ double stitch_terms(StitchShared& sh, int nterms, TermFn term, int i, int j) {
     double s = 0.0;
+    for (int k0 = 0; k0 < nterms; k0 += STITCH_CHUNK) {
+        const int kn = min(STITCH_CHUNK, nterms - k0);
+        if (k0) __syncthreads();  // the previous chunk has been consumed
+#pragma unroll 4
+        for (int k = 0; k < kn; ++k) {
+            const StitchTerm q = term(k0 + k);
+            double t = 0.0;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) s += adj(L, i, m) * T[8 * m + j];
+            for (int n = 0; n < 8; ++n) t += q.C[q.ldc * i + n] * adj(q.R, j, n);
+            sh.T[k][8 * i + j] = t;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < kn; ++k) {
+            const StitchTerm q = term(k0 + k);
+            double x = 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) x += adj(q.L, i, m) * sh.T[k][8 * m + j];
+            s += x;
+        }
+    }
     return s;
 }
 
-// AccumulatedTopHessianSSE::stitchDoubleInternal (AccumulatedTopHessian.cpp:241-303), by output block.
-__global__ void ba_top_stitch_kernel(int F, const double* __restrict__ acc, const double* __restrict__ adHost,
-                                     const double* __restrict__ adTarget, int use_prior, const double* __restrict__ cPrior,
-                                     const float* __restrict__ cDeltaF, const double* __restrict__ frame_prior,
-                                     const double* __restrict__ frame_delta_prior, double* __restrict__ H, double* __restrict__ bvec) {
-    __shared__ SandwichShared ssh;
-    int turn = 0;
-    const int a = blockIdx.x % F, b = blockIdx.x / F, n = CPARS + 8 * F;
+// AccumulatedTopHessianSSE::stitchDoubleInternal (AccumulatedTopHessian.cpp:241-303), by output block (a, b) = blk.
+__device__ __forceinline__ void top_stitch_block(StitchShared& ssh, int blk, int F, const double* __restrict__ acc, const double* __restrict__ adHost,
+                                                 const double* __restrict__ adTarget, int use_prior, const double* __restrict__ cPrior,
+                                                 const float* __restrict__ cDeltaF, const double* __restrict__ frame_prior,
+                                                 const double* __restrict__ frame_delta_prior, double* __restrict__ H, double* __restrict__ bvec) {
+    const int a = blk % F, b = blk / F, n = CPARS + 8 * F;
     const int i = threadIdx.x / 8, j = threadIdx.x % 8;
     auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
-    double s = 0.0;
-    if (a == b) {
-        for (int t = 0; t < F; ++t) {  // k = (h=a, t): adHost A88 adHost^T
-            const int k = a + F * t;
-            const double* A = acc + (size_t)169 * k;
-            s += sandwich(ssh, turn, adHost + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adHost + 64 * k, i, j);
+    const int ndiag = a == b ? 2 * F : 0;
+    const double s = stitch_terms(ssh, ndiag + 1, [&](int k) {
+        StitchTerm q;
+        q.ldc = 13;
+        int kk;
+        if (k < ndiag) {
+            if (k < F) { kk = a + F * k; q.L = q.R = adHost + 64 * kk; }          // k = (h=a, t): adHost A88 adHost^T
+            else { kk = (k - F) + F * a; q.L = q.R = adTarget + 64 * kk; }          // k = (h, t=a): adTarget A88 adTarget^T
+        } else {
+            kk = a + F * b; q.L = adHost + 64 * kk; q.R = adTarget + 64 * kk;       // H(hIdx,tIdx) += adHost A88 adTarget^T for (h=a, t=b)
         }
-        for (int h = 0; h < F; ++h) {  // k = (h, t=a): adTarget A88 adTarget^T
-            const int k = h + F * a;
-            const double* A = acc + (size_t)169 * k;
-            s += sandwich(ssh, turn, adTarget + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adTarget + 64 * k, i, j);
-        }
-    }
-    {  // H(hIdx,tIdx) += adHost A88 adTarget^T for k = (h=a, t=b)
-        const int k = a + F * b;
-        const double* A = acc + (size_t)169 * k;
-        s += sandwich(ssh, turn, adHost + 64 * k, [&](int m, int nn) { return A[13 * (CPARS + m) + CPARS + nn]; }, adTarget + 64 * k, i, j);
-    }
+        q.C = acc + (size_t)169 * kk + 13 * CPARS + CPARS;
+        return q;
+    }, i, j);
     Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
     if (a == b) {
         // calibration columns, b segment, priors for frame a; done by the diagonal CTA
@@ -906,11 +916,13 @@ __global__ void ba_top_stitch_kernel(int F, const double* __restrict__ acc, cons
             for (int t = 0; t < F; ++t) {
                 const int k = a + F * t;
                 const double* A = acc + (size_t)169 * k;
+#pragma unroll
                 for (int m = 0; m < 8; ++m) v += adj(adHost + 64 * k, i, m) * A[13 * (CPARS + m) + col];
             }
             for (int h = 0; h < F; ++h) {
                 const int k = h + F * a;
                 const double* A = acc + (size_t)169 * k;
+#pragma unroll
                 for (int m = 0; m < 8; ++m) v += adj(adTarget + 64 * k, i, m) * A[13 * (CPARS + m) + col];
             }
             if (j < CPARS) { Hat(CPARS + 8 * a + i, j) = v; Hat(j, CPARS + 8 * a + i) = v; }
@@ -919,11 +931,20 @@ __global__ void ba_top_stitch_kernel(int F, const double* __restrict__ acc, cons
         if (a == 0 && i < CPARS && j < CPARS + 1) {  // Hcc, bc
             double v = 0.0;
             const int col = (j < CPARS) ? j : CPARS + 8;
+#pragma unroll 7
             for (int k = 0; k < F * F; ++k) v += acc[(size_t)169 * k + 13 * i + col];
             if (j < CPARS) Hat(i, j) = v + ((use_prior && i == j) ? cPrior[i] : 0.0);
             else bvec[i] = v + (use_prior ? cPrior[i] * (double)cDeltaF[i] : 0.0);
         }
     }
+}
+
+__global__ void __launch_bounds__(64) ba_top_stitch_kernel(int F, const double* __restrict__ acc, const double* __restrict__ adHost,
+                                     const double* __restrict__ adTarget, int use_prior, const double* __restrict__ cPrior,
+                                     const float* __restrict__ cDeltaF, const double* __restrict__ frame_prior,
+                                     const double* __restrict__ frame_delta_prior, double* __restrict__ H, double* __restrict__ bvec) {
+    __shared__ StitchShared ssh;
+    top_stitch_block(ssh, blockIdx.x, F, acc, adHost, adTarget, use_prior, cPrior, cDeltaF, frame_prior, frame_delta_prior, H, bvec);
 }
 // "make diagonal by copying over parts" (AccumulatedTopHessian.h:125-137) + frame priors on the diagonal
 __global__ void ba_top_symmetrise_kernel(int F, int use_prior, const double* __restrict__ frame_prior, double* __restrict__ H) {
@@ -939,36 +960,36 @@ __global__ void ba_top_symmetrise_kernel(int F, int use_prior, const double* __r
     }
 }
 
-// AccumulatedSCHessianSSE::stitchDoubleInternal (AccumulatedSCHessian.cpp:78-157), by output block (a,b).
-__global__ void ba_sc_stitch_kernel(int F, const double* __restrict__ accD, const double* __restrict__ accE, const double* __restrict__ accEB,
-                                    const double* __restrict__ accHcc, const double* __restrict__ accbc, const double* __restrict__ adHost,
-                                    const double* __restrict__ adTarget, double* __restrict__ H, double* __restrict__ bvec) {
-    __shared__ SandwichShared ssh;
-    int turn = 0;
-    const int a = blockIdx.x % F, b = blockIdx.x / F, n = CPARS + 8 * F, F2 = F * F;
+// AccumulatedSCHessianSSE::stitchDoubleInternal (AccumulatedSCHessian.cpp:78-157), by output block (a, b) = blk.
+__device__ __forceinline__ void sc_stitch_block(StitchShared& ssh, int blk, int F, const double* __restrict__ accD, const double* __restrict__ accE,
+                                                const double* __restrict__ accEB, const double* __restrict__ accHcc, const double* __restrict__ accbc,
+                                                const double* __restrict__ adHost, const double* __restrict__ adTarget, double* __restrict__ H,
+                                                double* __restrict__ bvec) {
+    const int a = blk % F, b = blk / F, n = CPARS + 8 * F, F2 = F * F;
     const int i = threadIdx.x / 8, j = threadIdx.x % 8;
     auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
-    double s = 0.0;
     auto D = [&](int ii, int jj, int kk) { return accD + (size_t)64 * (ii + F * jj + F2 * kk); };
-    if (a == b) {  // H(iIdx,iIdx) += adHost[ij] D[ijk] adHost[ik]^T over all j,k, i = a
-        for (int jj = 0; jj < F; ++jj)
-            for (int kk = 0; kk < F; ++kk) {
-                const double* d = D(a, jj, kk);
-                s += sandwich(ssh, turn, adHost + 64 * (a + F * jj), [&](int m, int nn) { return d[8 * m + nn]; }, adHost + 64 * (a + F * kk), i, j);
-            }
-    }
-    for (int ii = 0; ii < F; ++ii) {  // H(jIdx,kIdx) += adTarget[ij] D[ijk] adTarget[ik]^T, j = a, k = b
-        const double* d = D(ii, a, b);
-        s += sandwich(ssh, turn, adTarget + 64 * (ii + F * a), [&](int m, int nn) { return d[8 * m + nn]; }, adTarget + 64 * (ii + F * b), i, j);
-    }
-    for (int kk = 0; kk < F; ++kk) {  // H(jIdx,iIdx) += adTarget[ij] D[ijk] adHost[ik]^T, j = a, i = b
-        const double* d = D(b, a, kk);
-        s += sandwich(ssh, turn, adTarget + 64 * (b + F * a), [&](int m, int nn) { return d[8 * m + nn]; }, adHost + 64 * (b + F * kk), i, j);
-    }
-    for (int jj = 0; jj < F; ++jj) {  // H(iIdx,kIdx) += adHost[ij] D[ijk] adTarget[ik]^T, i = a, k = b
-        const double* d = D(a, jj, b);
-        s += sandwich(ssh, turn, adHost + 64 * (a + F * jj), [&](int m, int nn) { return d[8 * m + nn]; }, adTarget + 64 * (a + F * b), i, j);
-    }
+    const int ndiag = a == b ? F2 : 0;
+    const double s = stitch_terms(ssh, ndiag + 3 * F, [&](int k) {
+        StitchTerm q;
+        q.ldc = 8;
+        if (k < ndiag) {  // H(iIdx,iIdx) += adHost[ij] D[ijk] adHost[ik]^T over all j,k, i = a
+            const int jj = k / F, kk = k % F;
+            q.C = D(a, jj, kk); q.L = adHost + 64 * (a + F * jj); q.R = adHost + 64 * (a + F * kk);
+            return q;
+        }
+        k -= ndiag;
+        if (k < F) {  // H(jIdx,kIdx) += adTarget[ij] D[ijk] adTarget[ik]^T, j = a, k = b
+            q.C = D(k, a, b); q.L = adTarget + 64 * (k + F * a); q.R = adTarget + 64 * (k + F * b);
+        } else if (k < 2 * F) {  // H(jIdx,iIdx) += adTarget[ij] D[ijk] adHost[ik]^T, j = a, i = b
+            const int kk = k - F;
+            q.C = D(b, a, kk); q.L = adTarget + 64 * (b + F * a); q.R = adHost + 64 * (b + F * kk);
+        } else {  // H(iIdx,kIdx) += adHost[ij] D[ijk] adTarget[ik]^T, i = a, k = b
+            const int jj = k - 2 * F;
+            q.C = D(a, jj, b); q.L = adHost + 64 * (a + F * jj); q.R = adTarget + 64 * (a + F * b);
+        }
+        return q;
+    }, i, j);
     Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
     if (a == b) {
         if (j < CPARS + 1) {
@@ -990,6 +1011,46 @@ __global__ void ba_sc_stitch_kernel(int F, const double* __restrict__ accD, cons
             if (j < CPARS) Hat(i, j) = accHcc[4 * i + j];
             else bvec[i] = accbc[i];
         }
+    }
+}
+
+__global__ void __launch_bounds__(64) ba_sc_stitch_kernel(int F, const double* __restrict__ accD, const double* __restrict__ accE, const double* __restrict__ accEB,
+                                    const double* __restrict__ accHcc, const double* __restrict__ accbc, const double* __restrict__ adHost,
+                                    const double* __restrict__ adTarget, double* __restrict__ H, double* __restrict__ bvec) {
+    __shared__ StitchShared ssh;
+    sc_stitch_block(ssh, blockIdx.x, F, accD, accE, accEB, accHcc, accbc, adHost, adTarget, H, bvec);
+}
+
+// solveSystemF's three stitches (active, linearized, Schur) in one launch: blockIdx.y picks the system
+struct Stitch3Args {
+    int F, use_prior;
+    const double *acc0, *acc1, *adHost, *adTarget, *cPrior, *frame_prior, *frame_delta_prior;
+    const float* cDeltaF;
+    const double *accD, *accE, *accEB, *accHcc, *accbc;
+    double *HA, *bA, *HL, *bL, *Hs, *bs;
+};
+__global__ void __launch_bounds__(64) ba_stitch3_kernel(Stitch3Args q) {
+    __shared__ StitchShared ssh;
+    if (blockIdx.y == 0)
+        top_stitch_block(ssh, blockIdx.x, q.F, q.acc0, q.adHost, q.adTarget, 0, q.cPrior, q.cDeltaF, q.frame_prior, q.frame_delta_prior, q.HA, q.bA);
+    else if (blockIdx.y == 1)
+        top_stitch_block(ssh, blockIdx.x, q.F, q.acc1, q.adHost, q.adTarget, q.use_prior, q.cPrior, q.cDeltaF, q.frame_prior, q.frame_delta_prior, q.HL, q.bL);
+    else
+        sc_stitch_block(ssh, blockIdx.x, q.F, q.accD, q.accE, q.accEB, q.accHcc, q.accbc, q.adHost, q.adTarget, q.Hs, q.bs);
+}
+// the symmetrisation of the two top systems in one launch
+__global__ void ba_top_symmetrise2_kernel(int F, int use_prior, const double* __restrict__ frame_prior, double* __restrict__ HA, double* __restrict__ HL) {
+    const int h = blockIdx.x % F, t = blockIdx.x / F, n = CPARS + 8 * F;
+    const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+    double* H = blockIdx.y == 0 ? HA : HL;
+    const int prior = blockIdx.y == 0 ? 0 : use_prior;
+    auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
+    if (t > h) {
+        const double v = Hat(CPARS + 8 * h + i, CPARS + 8 * t + j) + Hat(CPARS + 8 * t + j, CPARS + 8 * h + i);
+        Hat(CPARS + 8 * h + i, CPARS + 8 * t + j) = v;
+        Hat(CPARS + 8 * t + j, CPARS + 8 * h + i) = v;
+    } else if (t == h && prior && i == j) {
+        Hat(CPARS + 8 * h + i, CPARS + 8 * h + i) += frame_prior[8 * h + i];
     }
 }
 
@@ -1213,7 +1274,7 @@ edsgpu_status edsgpu_ba_create(edsgpu_ctx* ctx, int F, int P, int R, const int32
         std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1);
         for (int r = 0; r < R; ++r) perm[cur[host_idx[r] + F * target_idx[r]]++] = r;
     }
-    // tile size: the smallest multiple of 64 (>= 256) whose tile count fits one wave of one CTA per SM
+    // tile size: the smallest multiple of 64 (>= TOP_THREADS) whose tile count fits one wave of one CTA per SM
     int tile_sz = TOP_THREADS;
     for (;; tile_sz += 64) {
         long tiles = 0;
@@ -1717,34 +1778,53 @@ edsgpu_status edsgpu_ba_solve_system(edsgpu_ba* w, double lambda, const double* 
     DeviceGuard g(ctx->device);
     edsgpu_status st = ensure_post_block(w);
     if (st != EDSGPU_OK) return st;
-    // device block: three stitched systems (H n*n, b n) | HM | bM | delta | projector | x
-    const size_t sys = nn + (size_t)n, total = 3 * sys + nn + n + n + nn + n;
+    // device block: three stitched systems (H n*n, b n) | HM | bM | delta | projector | priors (cPrior 4, frame_prior 8F, frame_delta_prior 8F) | x
+    const size_t sys = nn + (size_t)n, n_in = 2 * nn + 2 * (size_t)n + 4 + 16 * (size_t)F, total = 3 * sys + n_in + n;
     if (!w->solve_block) {
         cudaError_t e = cudaMalloc(&w->solve_block, sizeof(double) * total);
         if (e != cudaSuccess) return edsgpu_fail(ctx, e == cudaErrorMemoryAllocation ? EDSGPU_OUT_OF_MEMORY : EDSGPU_CUDA_ERROR, cudaGetErrorString(e));
     }
     double* S = w->solve_block;
     double *HAd = S, *bAd = S + nn, *HLd = S + sys, *bLd = S + sys + nn, *Hsd = S + 2 * sys, *bsd = S + 2 * sys + nn;
-    double *HMd = S + 3 * sys, *bMd = HMd + nn, *dld = bMd + n, *prd = dld + n, *xd = prd + nn;
+    double *HMd = S + 3 * sys, *bMd = HMd + nn, *dld = bMd + n, *prd = dld + n, *pr = prd + nn, *xd = pr + 4 + 16 * F;
     cudaStream_t s = ctx->stream;
-    if (HM) {
-        EDS_CUDA(ctx, cudaMemcpyAsync(HMd, HM, 8 * nn, cudaMemcpyHostToDevice, s));
-        EDS_CUDA(ctx, cudaMemcpyAsync(bMd, bM, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
-        if (delta) EDS_CUDA(ctx, cudaMemcpyAsync(dld, delta, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
-    }
-    if (nullspace_projector) EDS_CUDA(ctx, cudaMemcpyAsync(prd, nullspace_projector, 8 * nn, cudaMemcpyHostToDevice, s));
-    double* pr = w->prior_buf;  // cPrior(4) | frame_prior(8F) | frame_delta_prior(8F)
-    if (cPrior) {
-        EDS_CUDA(ctx, cudaMemcpyAsync(pr, cPrior, 32, cudaMemcpyHostToDevice, s));
-        EDS_CUDA(ctx, cudaMemcpyAsync(pr + 4, frame_prior, 64 * (size_t)F, cudaMemcpyHostToDevice, s));
-        EDS_CUDA(ctx, cudaMemcpyAsync(pr + 4 + 8 * F, frame_delta_prior, 64 * (size_t)F, cudaMemcpyHostToDevice, s));
+    // the caller's inputs go through one pinned staging block and one copy (the caller's arrays are pageable: seven
+    // separate copies of them cost more than the three stitches)
+    if ((st = edsgpu_ensure_pinned(ctx, sizeof(double) * n_in)) != EDSGPU_OK) return st;
+    {
+        double* hst = (double*)ctx->pinned;
+        size_t lo = n_in, hi = 0;  // the range of the block that carries something
+        auto put = [&](size_t off, const double* src, size_t cnt) {
+            memcpy(hst + off, src, sizeof(double) * cnt);
+            lo = std::min(lo, off);
+            hi = std::max(hi, off + cnt);
+        };
+        if (HM) {
+            put(0, HM, nn);
+            put(nn, bM, n);
+            if (delta) put(nn + n, delta, n);
+        }
+        if (nullspace_projector) put(nn + 2 * (size_t)n, nullspace_projector, nn);
+        if (cPrior) {
+            const size_t o = 2 * nn + 2 * (size_t)n;
+            put(o, cPrior, 4);
+            put(o + 4, frame_prior, 8 * (size_t)F);
+            put(o + 4 + 8 * F, frame_delta_prior, 8 * (size_t)F);
+        }
+        // (a gap between two present parts is copied along: it is never read on the device)
+        if (hi > lo) EDS_CUDA(ctx, cudaMemcpyAsync(HMd + lo, hst + lo, sizeof(double) * (hi - lo), cudaMemcpyHostToDevice, s));
     }
     // accumulateAF_MT / accumulateLF_MT / accumulateSCF_MT's stitches (:790-800), results stay on the device
-    ba_top_stitch_kernel<<<F * F, 64, 0, s>>>(F, w->acc[0], w->adHost, w->adTarget, 0, pr, w->cDeltaF, pr + 4, pr + 4 + 8 * F, HAd, bAd);
-    ba_top_symmetrise_kernel<<<F * F, 64, 0, s>>>(F, 0, pr + 4, HAd);
-    ba_top_stitch_kernel<<<F * F, 64, 0, s>>>(F, w->acc[1], w->adHost, w->adTarget, cPrior ? 1 : 0, pr, w->cDeltaF, pr + 4, pr + 4 + 8 * F, HLd, bLd);
-    ba_top_symmetrise_kernel<<<F * F, 64, 0, s>>>(F, cPrior ? 1 : 0, pr + 4, HLd);
-    ba_sc_stitch_kernel<<<F * F, 64, 0, s>>>(F, w->accD, w->accE, w->accEB, w->accHcc, w->accbc, w->adHost, w->adTarget, Hsd, bsd);
+    {
+        Stitch3Args q{};
+        q.F = F; q.use_prior = cPrior ? 1 : 0;
+        q.acc0 = w->acc[0]; q.acc1 = w->acc[1]; q.adHost = w->adHost; q.adTarget = w->adTarget;
+        q.cPrior = pr; q.frame_prior = pr + 4; q.frame_delta_prior = pr + 4 + 8 * F; q.cDeltaF = w->cDeltaF;
+        q.accD = w->accD; q.accE = w->accE; q.accEB = w->accEB; q.accHcc = w->accHcc; q.accbc = w->accbc;
+        q.HA = HAd; q.bA = bAd; q.HL = HLd; q.bL = bLd; q.Hs = Hsd; q.bs = bsd;
+        ba_stitch3_kernel<<<dim3(F * F, 3), 64, 0, s>>>(q);
+        ba_top_symmetrise2_kernel<<<dim3(F * F, 2), 64, 0, s>>>(F, cPrior ? 1 : 0, pr + 4, HAd, HLd);
+    }
     char* pb = (char*)w->post_block;
     float* d_xAd = (float*)pb;
     float* d_cstep = (float*)(pb + align_up(32 * F2, 256));
@@ -1755,7 +1835,7 @@ edsgpu_status edsgpu_ba_solve_system(edsgpu_ba* w, double lambda, const double* 
     // resubstituteF_MT(x) (:907-909): the point steps from the device-resident x
     ba_resubstitute_kernel<<<(w->P + 127) / 128, 128, 0, s>>>(w->F, w->P, w->res_begin, w->host_idx, w->target_idx, w->flags, w->JpJdF, w->bdSum,
                                                               w->Hcd[0], w->Hcd[1], w->HdiF, d_xAd, d_cstep, d_step);
-    ctx->launches += 7;
+    ctx->launches += 4;
     EDS_CUDA(ctx, cudaGetLastError());
     EDS_CUDA(ctx, cudaMemcpyAsync(x_out, xd, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
     if (point_step_out) EDS_CUDA(ctx, cudaMemcpyAsync(point_step_out, d_step, 4 * (size_t)w->P, cudaMemcpyDeviceToHost, s));
