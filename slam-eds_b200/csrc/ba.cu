@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include <cuda_pipeline.h>
 
 namespace {
 
@@ -849,41 +850,80 @@ __global__ void ba_sc_hcc_kernel(int F, const double* __restrict__ hcc_host, dou
 __device__ __forceinline__ double adj(const double* A, int r, int c) { return A[c * 8 + r]; }  // Mat88 column-major
 
 // A frame block of a stitched matrix is a sum of sandwiches  L C R^T  (adjoint, accumulator block, adjoint):
-//   out(i,j) = sum_k ( sum_m L_k(i,m) T_k(m,j) ),  T_k(m,j) = sum_n C_k(m,n) R_k(j,n),  thread (i,j) of a 64-thread CTA.
-// The CTA first forms the T_k of a chunk of terms (thread (i,j) computes T_k(i,j); the loads of different terms are
-// independent, so they overlap), shares them through shared memory, then adds the terms in their fixed order: two barriers
-// per chunk instead of one dependent global-memory round trip per term.  Same products in the same order as a term-by-term
-// evaluation.
+//   out(i,j) = sum_k x_k(i,j),  x_k(i,j) = sum_m L_k(i,m) T_k(m,j),  T_k(m,j) = sum_n C_k(m,n) R_k(j,n).
+// A CTA of 256 threads = four groups of 64, thread e = 8 i + j of a group owns element (i, j).  Per chunk of terms:
+//  (0) the three 8x8 blocks of every term are copied into shared memory with cp.async, one element per copy, all in flight
+//      together: a chunk costs one memory round trip (a term-by-term evaluation from global memory spends a dependent round
+//      trip of 24 loads per thread on every term: 49 us for the three stitches of solveSystemF);
+//  (1) group g forms T_k, (2) then x_k, of the terms k = g, g + 4, ...;
+//  (3) group 0 adds the x_k in their fixed order.  Same products and the same order of additions as term by term.
 struct StitchTerm { const double *L, *C, *R; int ldc; };  // C(m,n) = C[ldc * m + n]; L, R: Mat88 column-major
-constexpr int STITCH_CHUNK = 24;
-struct StitchShared { double T[STITCH_CHUNK][64]; };
+constexpr int STITCH_CHUNK = 16, STITCH_THREADS = 256;
+struct StitchShared { double L[STITCH_CHUNK][64], C[STITCH_CHUNK][64], R[STITCH_CHUNK][64], T[STITCH_CHUNK][64], X[STITCH_CHUNK][64]; };  // 40 KB
 
+// returns the block's element (i, j) in the threads of group 0 (tid < 64)
 template <typename TermFn>
-__device__ __forceinline__ double stitch_terms(StitchShared& sh, int nterms, TermFn term, int i, int j) {
+__device__ __forceinline__ double stitch_terms(StitchShared& sh, int nterms, TermFn term) {
+    const int tid = threadIdx.x, e = tid & 63, g = tid >> 6, i = e >> 3, j = e & 7;
     double s = 0.0;
     for (int k0 = 0; k0 < nterms; k0 += STITCH_CHUNK) {
         const int kn = min(STITCH_CHUNK, nterms - k0);
-        if (k0) __syncthreads();  // the previous chunk has been consumed
-#pragma unroll 4
-        for (int k = 0; k < kn; ++k) {
+        __syncthreads();  // the buffers are free (previous chunk, or the caller's own use of them)
+        for (int w = tid; w < kn * 192; w += STITCH_THREADS) {
+            const int k = w / 192, r = w - 192 * k, which = r >> 6, el = r & 63;
             const StitchTerm q = term(k0 + k);
+            if (which == 0) __pipeline_memcpy_async(&sh.L[k][el], q.L + el, 8);
+            else if (which == 1) __pipeline_memcpy_async(&sh.R[k][el], q.R + el, 8);
+            else __pipeline_memcpy_async(&sh.C[k][el], q.C + q.ldc * (el >> 3) + (el & 7), 8);  // row-major 8x8
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
+        __syncthreads();
+        for (int k = g; k < kn; k += 4) {
             double t = 0.0;
 #pragma unroll
-            for (int n = 0; n < 8; ++n) t += q.C[q.ldc * i + n] * adj(q.R, j, n);
-            sh.T[k][8 * i + j] = t;
+            for (int n = 0; n < 8; ++n) t += sh.C[k][8 * i + n] * adj(sh.R[k], j, n);
+            sh.T[k][e] = t;
         }
         __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < kn; ++k) {
-            const StitchTerm q = term(k0 + k);
+        for (int k = g; k < kn; k += 4) {
             double x = 0.0;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) x += adj(q.L, i, m) * sh.T[k][8 * m + j];
-            s += x;
+            for (int m = 0; m < 8; ++m) x += adj(sh.L[k], i, m) * sh.T[k][8 * m + j];
+            sh.X[k][e] = x;
         }
+        __syncthreads();
+        if (g == 0)
+            for (int k = 0; k < kn; ++k) s += sh.X[k][e];
     }
     return s;
 }
+
+// The calibration columns and the b segment of frame `a` (rows of the diagonal CTA): v(i, col) = sum over the 2F pairs frame
+// a takes part in of  Ad_k(i, :) . E_k(:, col),  E_k an 8 x 5 block given element-wise by `e(k, m, col)`.  The adjoints
+// and the E blocks go through shared memory like the sandwiches' operands; the sum keeps its order (pair by pair, m inside).
+// Returns v(i, j) in the threads of group 0 with j < 5.
+template <typename AdFn, typename EFn>
+__device__ __forceinline__ double stitch_calibration(StitchShared& sh, int ncal, AdFn ad, EFn e) {
+    const int tid = threadIdx.x, i = (tid & 63) >> 3, j = tid & 7;
+    __syncthreads();
+    for (int w = tid; w < ncal * 104; w += STITCH_THREADS) {
+        const int k = w / 104, r = w - 104 * k;
+        if (r < 64) __pipeline_memcpy_async(&sh.L[k][r], ad(k) + r, 8);
+        else sh.C[k][r - 64] = e(k, (r - 64) / 5, (r - 64) % 5);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    double v = 0.0;
+    if (tid < 64 && j < CPARS + 1) {
+        for (int k = 0; k < ncal; ++k)
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v += adj(sh.L[k], i, m) * sh.C[k][5 * m + j];
+    }
+    return v;
+}
+static_assert(2 * MAXF <= STITCH_CHUNK, "the calibration pass keeps all 2F pairs of a frame in one chunk");
 
 // AccumulatedTopHessianSSE::stitchDoubleInternal (AccumulatedTopHessian.cpp:241-303), by output block (a, b) = blk.
 __device__ __forceinline__ void top_stitch_block(StitchShared& ssh, int blk, int F, const double* __restrict__ acc, const double* __restrict__ adHost,
@@ -891,7 +931,8 @@ __device__ __forceinline__ void top_stitch_block(StitchShared& ssh, int blk, int
                                                  const float* __restrict__ cDeltaF, const double* __restrict__ frame_prior,
                                                  const double* __restrict__ frame_delta_prior, double* __restrict__ H, double* __restrict__ bvec) {
     const int a = blk % F, b = blk / F, n = CPARS + 8 * F;
-    const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+    const int i = (threadIdx.x & 63) / 8, j = threadIdx.x % 8;
+    const bool writer = threadIdx.x < 64;  // group 0 holds the results
     auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
     const int ndiag = a == b ? 2 * F : 0;
     const double s = stitch_terms(ssh, ndiag + 1, [&](int k) {
@@ -906,29 +947,21 @@ __device__ __forceinline__ void top_stitch_block(StitchShared& ssh, int blk, int
         }
         q.C = acc + (size_t)169 * kk + 13 * CPARS + CPARS;
         return q;
-    }, i, j);
-    Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
+    });
+    if (writer) Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
     if (a == b) {
         // calibration columns, b segment, priors for frame a; done by the diagonal CTA
-        if (j < CPARS + 1) {
-            double v = 0.0;
-            const int col = (j < CPARS) ? j : CPARS + 8;
-            for (int t = 0; t < F; ++t) {
-                const int k = a + F * t;
-                const double* A = acc + (size_t)169 * k;
-#pragma unroll
-                for (int m = 0; m < 8; ++m) v += adj(adHost + 64 * k, i, m) * A[13 * (CPARS + m) + col];
-            }
-            for (int h = 0; h < F; ++h) {
-                const int k = h + F * a;
-                const double* A = acc + (size_t)169 * k;
-#pragma unroll
-                for (int m = 0; m < 8; ++m) v += adj(adTarget + 64 * k, i, m) * A[13 * (CPARS + m) + col];
-            }
+        const double v = stitch_calibration(ssh, 2 * F,
+            [&](int k) { return k < F ? adHost + 64 * (a + F * k) : adTarget + 64 * ((k - F) + F * a); },  // (h=a, t=k), then (h=k-F, t=a)
+            [&](int k, int m, int c) {
+                const int kk = k < F ? a + F * k : (k - F) + F * a;
+                return acc[(size_t)169 * kk + 13 * (CPARS + m) + (c < CPARS ? c : CPARS + 8)];
+            });
+        if (writer && j < CPARS + 1) {
             if (j < CPARS) { Hat(CPARS + 8 * a + i, j) = v; Hat(j, CPARS + 8 * a + i) = v; }
             else bvec[CPARS + 8 * a + i] = v + (use_prior ? frame_prior[8 * a + i] * frame_delta_prior[8 * a + i] : 0.0);
         }
-        if (a == 0 && i < CPARS && j < CPARS + 1) {  // Hcc, bc
+        if (writer && a == 0 && i < CPARS && j < CPARS + 1) {  // Hcc, bc
             double v = 0.0;
             const int col = (j < CPARS) ? j : CPARS + 8;
 #pragma unroll 7
@@ -939,7 +972,7 @@ __device__ __forceinline__ void top_stitch_block(StitchShared& ssh, int blk, int
     }
 }
 
-__global__ void __launch_bounds__(64) ba_top_stitch_kernel(int F, const double* __restrict__ acc, const double* __restrict__ adHost,
+__global__ void __launch_bounds__(STITCH_THREADS) ba_top_stitch_kernel(int F, const double* __restrict__ acc, const double* __restrict__ adHost,
                                      const double* __restrict__ adTarget, int use_prior, const double* __restrict__ cPrior,
                                      const float* __restrict__ cDeltaF, const double* __restrict__ frame_prior,
                                      const double* __restrict__ frame_delta_prior, double* __restrict__ H, double* __restrict__ bvec) {
@@ -966,7 +999,8 @@ __device__ __forceinline__ void sc_stitch_block(StitchShared& ssh, int blk, int 
                                                 const double* __restrict__ adHost, const double* __restrict__ adTarget, double* __restrict__ H,
                                                 double* __restrict__ bvec) {
     const int a = blk % F, b = blk / F, n = CPARS + 8 * F, F2 = F * F;
-    const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+    const int i = (threadIdx.x & 63) / 8, j = threadIdx.x % 8;
+    const bool writer = threadIdx.x < 64;  // group 0 holds the results
     auto Hat = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
     auto D = [&](int ii, int jj, int kk) { return accD + (size_t)64 * (ii + F * jj + F2 * kk); };
     const int ndiag = a == b ? F2 : 0;
@@ -989,32 +1023,28 @@ __device__ __forceinline__ void sc_stitch_block(StitchShared& ssh, int blk, int 
             q.C = D(a, jj, b); q.L = adHost + 64 * (a + F * jj); q.R = adTarget + 64 * (a + F * b);
         }
         return q;
-    }, i, j);
-    Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
+    });
+    if (writer) Hat(CPARS + 8 * a + i, CPARS + 8 * b + j) = s;
     if (a == b) {
-        if (j < CPARS + 1) {
-            double v = 0.0;
-            for (int jj = 0; jj < F; ++jj) {  // rows of frame a as host i: adHost[ij] * E[ij]
-                const int ij = a + F * jj;
-                for (int m = 0; m < 8; ++m)
-                    v += adj(adHost + 64 * ij, i, m) * (j < CPARS ? accE[(size_t)32 * ij + 4 * m + j] : accEB[(size_t)8 * ij + m]);
-            }
-            for (int ii = 0; ii < F; ++ii) {  // rows of frame a as target j: adTarget[ij] * E[ij]
-                const int ij = ii + F * a;
-                for (int m = 0; m < 8; ++m)
-                    v += adj(adTarget + 64 * ij, i, m) * (j < CPARS ? accE[(size_t)32 * ij + 4 * m + j] : accEB[(size_t)8 * ij + m]);
-            }
+        // rows of frame a as host i: adHost[ij] * E[ij], then as target j: adTarget[ij] * E[ij]
+        const double v = stitch_calibration(ssh, 2 * F,
+            [&](int k) { return k < F ? adHost + 64 * (a + F * k) : adTarget + 64 * ((k - F) + F * a); },
+            [&](int k, int m, int c) {
+                const int ij = k < F ? a + F * k : (k - F) + F * a;
+                return c < CPARS ? accE[(size_t)32 * ij + 4 * m + c] : accEB[(size_t)8 * ij + m];
+            });
+        if (writer && j < CPARS + 1) {
             if (j < CPARS) { Hat(CPARS + 8 * a + i, j) = v; Hat(j, CPARS + 8 * a + i) = v; }
             else bvec[CPARS + 8 * a + i] = v;
         }
-        if (a == 0 && i < CPARS && j < CPARS + 1) {
+        if (writer && a == 0 && i < CPARS && j < CPARS + 1) {
             if (j < CPARS) Hat(i, j) = accHcc[4 * i + j];
             else bvec[i] = accbc[i];
         }
     }
 }
 
-__global__ void __launch_bounds__(64) ba_sc_stitch_kernel(int F, const double* __restrict__ accD, const double* __restrict__ accE, const double* __restrict__ accEB,
+__global__ void __launch_bounds__(STITCH_THREADS) ba_sc_stitch_kernel(int F, const double* __restrict__ accD, const double* __restrict__ accE, const double* __restrict__ accEB,
                                     const double* __restrict__ accHcc, const double* __restrict__ accbc, const double* __restrict__ adHost,
                                     const double* __restrict__ adTarget, double* __restrict__ H, double* __restrict__ bvec) {
     __shared__ StitchShared ssh;
@@ -1029,7 +1059,7 @@ struct Stitch3Args {
     const double *accD, *accE, *accEB, *accHcc, *accbc;
     double *HA, *bA, *HL, *bL, *Hs, *bs;
 };
-__global__ void __launch_bounds__(64) ba_stitch3_kernel(Stitch3Args q) {
+__global__ void __launch_bounds__(STITCH_THREADS) ba_stitch3_kernel(Stitch3Args q) {
     __shared__ StitchShared ssh;
     if (blockIdx.y == 0)
         top_stitch_block(ssh, blockIdx.x, q.F, q.acc0, q.adHost, q.adTarget, 0, q.cPrior, q.cDeltaF, q.frame_prior, q.frame_delta_prior, q.HA, q.bA);
@@ -1065,6 +1095,7 @@ __global__ void ba_top_symmetrise2_kernel(int F, int use_prior, const double* __
 // then the per-frame-pair row vectors xAd of resubstituteF_MT (:272-281, float like the reference) for the point pass.
 // ------------------------------------------------------------------------------------------
 constexpr int SOLVE_MAXN = CPARS + 8 * MAXF, SOLVE_LD = SOLVE_MAXN + 1, SOLVE_THREADS = 256;
+constexpr int SOLVE_NB = (SOLVE_MAXN + 1 + 15) / 16;  // 16-strided entries per thread and dimension, border row included
 
 __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_kernel(int F, double lambda, const double* __restrict__ HA, const double* __restrict__ bA,
                                                                   const double* __restrict__ HL, const double* __restrict__ bL,
@@ -1073,68 +1104,101 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_kernel(int F, double l
                                                                   const double* __restrict__ delta, const double* __restrict__ projector,
                                                                   const double* __restrict__ adHost, const double* __restrict__ adTarget,
                                                                   double* __restrict__ x_out, float* __restrict__ xAd, float* __restrict__ cstep) {
-    __shared__ double A[SOLVE_MAXN][SOLVE_LD];
+    __shared__ double A[SOLVE_MAXN + 1][SOLVE_LD];
     __shared__ double rhs[SOLVE_MAXN], sv[SOLVE_MAXN], xs[SOLVE_MAXN], col[SOLVE_MAXN];
+    __shared__ double colbuf[2][SOLVE_NB * 16];
     __shared__ float xF[SOLVE_MAXN];
     const int n = CPARS + 8 * F, tid = threadIdx.x;
     const double inv1l = 1.0 / (1.0 + lambda);
-    // assemble (column-major inputs; A is symmetric, both triangles are filled)
-    for (int e = tid; e < n * n; e += SOLVE_THREADS) {
-        const int r = e % n, c = e / n;
+    // entry (r, c) of the assembled system (column-major inputs)
+    auto assembled = [&](int r, int c) {
+        const int e = c * n + r;
         double v = HL[e] + (HM ? HM[e] : 0.0) + HA[e];
         if (r == c) v *= (1.0 + lambda);
-        A[r][c] = v - Hsc[e] * inv1l;
-    }
+        return v - Hsc[e] * inv1l;
+    };
     for (int r = tid; r < n; r += SOLVE_THREADS) {
         double bm = bM ? bM[r] : 0.0;
         if (HM && delta)
             for (int c = 0; c < n; ++c) bm += HM[(size_t)c * n + r] * delta[c];
-        rhs[r] = bL[r] + bm + bA[r] - bsc[r];
+        const double s = 1.0 / sqrt(assembled(r, r) + 10.0);
+        sv[r] = s;
+        rhs[r] = (bL[r] + bm + bA[r] - bsc[r]) * s;
     }
     __syncthreads();
-    for (int r = tid; r < n; r += SOLVE_THREADS) sv[r] = 1.0 / sqrt(A[r][r] + 10.0);
-    __syncthreads();
-    for (int e = tid; e < n * n; e += SOLVE_THREADS) {
-        const int r = e % n, c = e / n;
-        A[r][c] = sv[r] * A[r][c] * sv[c];
-    }
-    for (int r = tid; r < n; r += SOLVE_THREADS) rhs[r] *= sv[r];
-    __syncthreads();
-    // right-looking LDL^T on the lower triangle.  Column k is final when step k starts and is not touched by it, so the update
-    // reads it in place (A[i][j] -= A[i][k] A[j][k] / D_k): one barrier per step.  Thread (ty, tx) of a 16 x 16 arrangement
-    // walks the trailing block in 16 x 16 tiles.  The columns are scaled to L(:,k) = A(:,k) / D_k in one pass at the end.
+    // The scaled system, bordered by the right-hand side as row and column n, lives in REGISTERS: thread (ty, tx) of a
+    // 16 x 16 arrangement owns the entries (ty + 16 a, tx + 16 b).  Right-looking LDL^T: at step k the owners of column k
+    // publish it through shared memory (double buffered: one barrier per step), every thread then updates its own
+    // entries, M(i,j) -= (M(i,k) / D_k) M(j,k), lower triangle only.  Eliminating the border row along with the rest makes
+    // it the forward substitution: after the scaling it holds y = D^-1 L^-1 rhs.
     const int tx = tid & 15, ty = tid >> 4;
-    for (int k = 0; k < n - 1; ++k) {
-        const double rd = 1.0 / A[k][k];
-        for (int i = k + 1 + ty; i < n; i += 16) {
-            const double ci = A[i][k] * rd;
-            for (int j = k + 1 + tx; j <= i; j += 16) A[i][j] -= ci * A[j][k];
+    double M[SOLVE_NB][SOLVE_NB];
+#pragma unroll
+    for (int a = 0; a < SOLVE_NB; ++a)
+#pragma unroll
+        for (int b = 0; b < SOLVE_NB; ++b) {
+            const int i = ty + 16 * a, j = tx + 16 * b;
+            double v = 0.0;
+            if (j <= i && i <= n) {
+                if (i < n) v = sv[i] * assembled(i, j) * sv[j];
+                else if (j < n) v = rhs[j];
+            }
+            M[a][b] = v;
+        }
+    for (int k = 0; k < n; ++k) {
+        double* cb = colbuf[k & 1];
+        const int kb = k >> 4;
+        if (tx == (k & 15)) {
+#pragma unroll
+            for (int b = 0; b < SOLVE_NB; ++b)
+                if (b == kb) {
+#pragma unroll
+                    for (int a = 0; a < SOLVE_NB; ++a) cb[ty + 16 * a] = M[a][b];
+                }
         }
         __syncthreads();
+        const double rd = 1.0 / cb[k];
+        double ci[SOLVE_NB], cj[SOLVE_NB];
+#pragma unroll
+        for (int a = 0; a < SOLVE_NB; ++a) { ci[a] = cb[ty + 16 * a] * rd; cj[a] = cb[tx + 16 * a]; }
+#pragma unroll
+        for (int a = 0; a < SOLVE_NB; ++a)
+#pragma unroll
+            for (int b = 0; b < SOLVE_NB; ++b) {
+                const int i = ty + 16 * a, j = tx + 16 * b;
+                if (j > k && j <= i && i <= n) M[a][b] -= ci[a] * cj[b];
+            }
     }
-    for (int e = tid; e < n * n; e += SOLVE_THREADS) {
+    // L (unit lower, scaled columns) and D to shared memory for the back substitution
+#pragma unroll
+    for (int a = 0; a < SOLVE_NB; ++a)
+#pragma unroll
+        for (int b = 0; b < SOLVE_NB; ++b) {
+            const int i = ty + 16 * a, j = tx + 16 * b;
+            if (j <= i && i <= n && j < n) A[i][j] = M[a][b];
+        }
+    __syncthreads();
+    for (int e = tid; e < (n + 1) * n; e += SOLVE_THREADS) {
         const int i = e / n, k = e - i * n;
         if (k < i) A[i][k] /= A[k][k];  // reads the diagonal, writes strictly below it
     }
     __syncthreads();
-    // L z = rhs, D y = z, L^T w = y by the first warp, column oriented: once z_j is final every later row takes its term
-    // (two rows per lane, one warp barrier per column -- no reduction across lanes)
+    // L^T w = y by the first warp: y is the scaled border row; a lane keeps the rows lane, lane + 32, lane + 64 in registers
+    // and takes w_j from its owner by shuffle (the chain per step is a shuffle and a multiply-add)
     if (tid < 32) {
-        for (int i = tid; i < n; i += 32) xs[i] = rhs[i];
-        __syncwarp();
-        for (int j = 0; j < n; ++j) {
-            const double zj = xs[j];
-            for (int i = j + 1 + tid; i < n; i += 32) xs[i] -= A[i][j] * zj;
-            __syncwarp();
-        }
-        for (int i = tid; i < n; i += 32) xs[i] /= A[i][i];
-        __syncwarp();
+        double x0 = tid < n ? A[n][tid] : 0.0, x1 = tid + 32 < n ? A[n][tid + 32] : 0.0, x2 = tid + 64 < n ? A[n][tid + 64] : 0.0;
+#pragma unroll 4
         for (int j = n - 1; j > 0; --j) {
-            const double wj = xs[j];
-            for (int i = tid; i < j; i += 32) xs[i] -= A[j][i] * wj;
-            __syncwarp();
+            const int slot = j >> 5;
+            const double mine = slot == 0 ? x0 : (slot == 1 ? x1 : x2);
+            const double wj = __shfl_sync(0xffffffffu, mine, j & 31);
+            if (tid < j) x0 -= A[j][tid] * wj;
+            if (tid + 32 < j) x1 -= A[j][tid + 32] * wj;
+            if (tid + 64 < j) x2 -= A[j][tid + 64] * wj;
         }
-        for (int i = tid; i < n; i += 32) xs[i] *= sv[i];
+        if (tid < n) xs[tid] = x0 * sv[tid];
+        if (tid + 32 < n) xs[tid + 32] = x1 * sv[tid + 32];
+        if (tid + 64 < n) xs[tid + 64] = x2 * sv[tid + 64];
     }
     __syncthreads();
     if (projector) {  // orthogonalize(&x, 0)
@@ -1486,7 +1550,7 @@ edsgpu_status edsgpu_ba_top_stitch(edsgpu_ba* w, int which, int use_prior, const
         EDS_CUDA(ctx, cudaMemcpyAsync(pr + 4, frame_prior, 64 * (size_t)F, cudaMemcpyHostToDevice, ctx->stream));
         EDS_CUDA(ctx, cudaMemcpyAsync(pr + 4 + 8 * F, frame_delta_prior, 64 * (size_t)F, cudaMemcpyHostToDevice, ctx->stream));
     }
-    ba_top_stitch_kernel<<<F * F, 64, 0, ctx->stream>>>(F, w->acc[which], w->adHost, w->adTarget, use_prior, pr, w->cDeltaF, pr + 4, pr + 4 + 8 * F,
+    ba_top_stitch_kernel<<<F * F, STITCH_THREADS, 0, ctx->stream>>>(F, w->acc[which], w->adHost, w->adTarget, use_prior, pr, w->cDeltaF, pr + 4, pr + 4 + 8 * F,
                                                         w->Hmat, w->bvec);
     ba_top_symmetrise_kernel<<<F * F, 64, 0, ctx->stream>>>(F, use_prior, pr + 4, w->Hmat);
     ctx->launches += 2;
@@ -1542,7 +1606,7 @@ edsgpu_status edsgpu_ba_sc_stitch(edsgpu_ba* w, double* H, double* b) {
     edsgpu_ctx* ctx = w->ctx;
     DeviceGuard g(ctx->device);
     const int F = w->F, n = CPARS + 8 * F;
-    ba_sc_stitch_kernel<<<F * F, 64, 0, ctx->stream>>>(F, w->accD, w->accE, w->accEB, w->accHcc, w->accbc, w->adHost, w->adTarget, w->Hmat, w->bvec);
+    ba_sc_stitch_kernel<<<F * F, STITCH_THREADS, 0, ctx->stream>>>(F, w->accD, w->accE, w->accEB, w->accHcc, w->accbc, w->adHost, w->adTarget, w->Hmat, w->bvec);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
     edsgpu_status st;
@@ -1822,7 +1886,7 @@ edsgpu_status edsgpu_ba_solve_system(edsgpu_ba* w, double lambda, const double* 
         q.cPrior = pr; q.frame_prior = pr + 4; q.frame_delta_prior = pr + 4 + 8 * F; q.cDeltaF = w->cDeltaF;
         q.accD = w->accD; q.accE = w->accE; q.accEB = w->accEB; q.accHcc = w->accHcc; q.accbc = w->accbc;
         q.HA = HAd; q.bA = bAd; q.HL = HLd; q.bL = bLd; q.Hs = Hsd; q.bs = bsd;
-        ba_stitch3_kernel<<<dim3(F * F, 3), 64, 0, s>>>(q);
+        ba_stitch3_kernel<<<dim3(F * F, 3), STITCH_THREADS, 0, s>>>(q);
         ba_top_symmetrise2_kernel<<<dim3(F * F, 2), 64, 0, s>>>(F, cPrior ? 1 : 0, pr + 4, HAd, HLd);
     }
     char* pb = (char*)w->post_block;
