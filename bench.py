@@ -472,6 +472,24 @@ class TrackRun:
         self.ctx.synchronize()
         return float(np.mean([a.elapsed_time(b) for a, b in evs[2:]]))
 
+    def time_lm_alone(self, n):
+        """The batched solve (track_lm_kernel + mad_kernel) with nothing else on the device: every launch restarts window 0 from
+        its initial state, frames already built.  Returns (mean launch ms, mean evaluations per launch)."""
+        self._create_device(0)
+        ms, evals = [], []
+        for r in range(n + 1):
+            self.reset_states()
+            self.ctx.synchronize()
+            a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            a.record(self.stream)
+            self.ctx.check(self.ctx.lib.edsgpu_batch_optimize(self.banks[0].h))
+            b.record(self.stream)
+            self.ctx.synchronize()
+            if r:  # the first one warms up
+                ms.append(a.elapsed_time(b))
+                evals.append(float(sum(i["evaluations"] for i in self.banks[0].gather()[1])))
+        return float(np.mean(ms)), float(np.mean(evals))
+
     def _issue_create(self, k):
         # host-facing C ABI with HOST (pinned) buffers: asynchronous, H2D on the library's copy stream
         C = self.edsgpu.C
@@ -529,6 +547,8 @@ def measure(run, steps, warmup, barrier, max_over_ranks, peak, traffic):
     lm_ms = float(np.mean([a.elapsed_time(b) for a, b in lm_events]))
     ef_ms = run.time_event_frames(min(steps, 10))
     states, infos = run.banks[(warmup + steps - 1) & 1].gather()
+    alone_ms, alone_evals = run.time_lm_alone(min(steps, 10))
+    alone_alg = algorithmic_bytes_lm(c["N"], c["H"], c["W"], NUM_BLOCKS, alone_evals) + 4 * c["N"] * S
     evals = float(sum(i["evaluations"] for i in infos))  # last step's launch
     usable = sum(i["usable"] for i in infos)
     iters = float(np.mean([i["iterations"] for i in infos]))
@@ -550,6 +570,10 @@ def measure(run, steps, warmup, barrier, max_over_ranks, peak, traffic):
                      "traffic": (traffic or {}).get("track_lm_kernel_dram_bytes_per_launch"),
                      "l2_bytes": (traffic or {}).get("track_lm_kernel_lts_bytes_per_launch"),
                      "algorithmic_bytes_per_launch": alg, "launch_ms": lm_ms, "evaluations_per_launch": evals,
+                     "alone": {"launch_ms": alone_ms, "evaluations_per_launch": alone_evals, "achieved": alone_alg / (alone_ms * 1e-3) / 1e9,
+                               "frac": alone_alg / (alone_ms * 1e-3) / 1e9 / peak,
+                               "note": "the same launch with nothing else on the device (window 0 of every sequence from its initial state): "
+                                       "what the concurrent frame build of the next window costs the solve is the difference"},
                      "note": "launch_ms covers track_lm_kernel + mad_kernel (CUDA events on the launching stream, frame builds of the next window running "
                              "beside it); traffic / l2_bytes are from the ncu capture in profiles/ (config 2, 64 sequences): the working set is "
                              "L2-resident, the kernel is bound by per-SM latency / issue, see DESIGN.md 4.2"},
