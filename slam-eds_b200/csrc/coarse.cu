@@ -602,8 +602,8 @@ __device__ void se3_left_update(const double* inc6, double* R, double* t) {
 // ------------------------------------------------------------------------------------------
 // trackNewestCoarse on the device: ONE cooperative launch runs the whole coarse-to-fine loop.  Every evaluation is a
 // sweep of the level's points by all CTAs, one grid barrier, then every CTA adds the per-CTA partials in order and its
-// thread 0 advances the (identical) state machine: Levenberg damping, 8x8 LDL^T, SE3::exp update, accept / reject,
-// cutoff repeat, level change.  No host round trip inside the loop (it cost ~40 us per evaluation).
+// first warp advances the (identical) state machine: Levenberg damping, 8x8 LDL^T (a matrix row per lane), SE3::exp update,
+// accept / reject, cutoff repeat, level change (the scalar decisions are lane 0's).  No host round trip inside the loop (it cost ~40 us per evaluation).
 // ------------------------------------------------------------------------------------------
 constexpr int CT_MAX_PER = 19;  // ceil(148 / 8): CTAs per eighth in the ordered sum of the partials
 constexpr int CT_MAX_LEVELS = 5, CT_TRACK_THREADS = 512;  // wide CTAs: fewer of them at the grid barrier and in the ordered sum  // PYR_LEVELS the loop can visit (coarsest_lvl < 5, CoarseTracker.cpp:540)
@@ -634,7 +634,7 @@ struct TrackArgs {
     unsigned bar_base; // its value when this launch starts (the host keeps count: one barrier per evaluation)
 };
 
-struct TrackCtl {  // shared memory; written by thread 0 only
+struct TrackCtl {  // shared memory; written by the CTA's first warp only
     double Rc[9], tc[3], affc[2];   // accepted pose
     double Rn[9], tn[3], affn[2];   // proposal under evaluation
     double H[64], b[8], resOld[6], inc[8];
