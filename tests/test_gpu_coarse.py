@@ -85,10 +85,11 @@ def test_gpu_against_committed_coarse_fixture(gpu_ctx):
     ct.close()
 
 
-def test_track_newest_coarse_matches_the_oracle_loop(gpu_ctx):
-    """edsgpu_coarse_track (host loop around the device evaluation) against the oracle's loop: same number of
+@pytest.mark.parametrize("seed,pose_error", [(5, 6e-3), (11, 2e-3), (23, 1e-2)])
+def test_track_newest_coarse_matches_the_oracle_loop(gpu_ctx, seed, pose_error):
+    """edsgpu_coarse_track (the device-resident loop: one cooperative launch) against the oracle's loop: same number of
     evaluations, same accept / reject history, final pose and brightness parameters to 1e-6."""
-    pb = SC.make_coarse_problem(W=320, H=240, levels=4, points=8000, seed=5, pose_error=6e-3)
+    pb = SC.make_coarse_problem(W=320, H=240, levels=4, points=8000, seed=seed, pose_error=pose_error)
     ct = edsgpu.CoarseTracker(gpu_ctx, 4)
     for lvl, L in enumerate(pb["levels"]):
         ct.set_level(lvl, L["w"], L["h"], L["fx"], L["fy"], L["cx"], L["cy"], L["Ki"])
