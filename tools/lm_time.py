@@ -67,6 +67,8 @@ def main():
     print("lm_time %s S=%d %s max_iter=%d: %.4f ms (min %.4f) per launch, %d evaluations, usable %d/%d, shape %s, states sha1 %s" % (
         os.path.basename(edsgpu.LIB_PATH), S, config, max_iter, float(np.mean(ms)), float(np.min(ms)), evals, sum(i["usable"] for i in infos), S,
         shape, digest))
+    if "successful_steps" in infos[0]:
+        print("  steps: %d successful, %d unsuccessful" % (sum(i["successful_steps"] for i in infos), sum(i["unsuccessful_steps"] for i in infos)))
     if has_timing:
         ctx.lib.edsgpu_debug_timing(out, C.c_int(0))
         t = np.array(list(out), dtype=np.float64)
