@@ -168,15 +168,25 @@ __device__ __forceinline__ void coarse_sweep(const CoarseArgs& a, double (*red)[
     }
 }
 
-__global__ void __launch_bounds__(CT_THREADS) coarse_res_gs_kernel(CoarseArgs a) {
+// One evaluation for the host-synchronous entry point: every CTA leaves its partial, the last one to finish (ticket) adds
+// them in CTA order and writes the CT_NPART sums where `out` points -- pinned host memory: one launch, no copy back.
+__global__ void __launch_bounds__(CT_THREADS) coarse_res_gs_kernel(CoarseArgs a, unsigned* __restrict__ ticket, double* __restrict__ out) {
     __shared__ double red[CT_THREADS / 32][CT_NPART];
+    __shared__ bool last;
     coarse_sweep<CT_THREADS>(a, red, a.partials + (size_t)blockIdx.x * CT_NPART);
-}
-
-__global__ void coarse_finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
+    __threadfence();  // this CTA's partial is visible before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1u);
+        if (last) *ticket = 0u;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
     if (threadIdx.x < CT_NPART) {
         double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * CT_NPART + threadIdx.x];
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(a.partials + (size_t)b * CT_NPART + threadIdx.x);
         out[threadIdx.x] = s;
     }
 }
@@ -293,7 +303,7 @@ struct edsgpu_coarse {
     std::vector<Level> levels;
     double* partials = nullptr;  // [max grid][CT_NPART] + CT_NPART result
     int max_grid = 0;
-    unsigned* track_bar = nullptr;   // arrival counter of its grid barrier
+    unsigned* track_bar = nullptr;   // [0] arrival counter of its grid barrier, [1] ticket of the single-evaluation kernel
     unsigned track_bar_count = 0;    // host mirror of the counter; track_bar_dirty: a launch failed, reset both first
     bool track_bar_dirty = false;
 };
@@ -524,13 +534,11 @@ edsgpu_status edsgpu_coarse_calc_res_gs(edsgpu_coarse* c, int lvl, const double 
     a.pc_u = l.pc; a.pc_v = l.pc + l.cap; a.pc_idepth = l.pc + 2 * (size_t)l.cap; a.pc_color = l.pc + 3 * (size_t)l.cap;
     a.partials = c->partials;
     const int grid = std::max(1, std::min((l.n + CT_THREADS - 1) / CT_THREADS, c->max_grid));
-    double* d_out = c->partials + (size_t)c->max_grid * CT_NPART;
-    coarse_res_gs_kernel<<<grid, CT_THREADS, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    coarse_finalize_kernel<<<1, 64, 0, ctx->stream>>>(c->partials, grid, d_out);
+    double* out_dev = nullptr;  // the pinned block as the device sees it
+    EDS_CUDA(ctx, cudaHostGetDevicePointer((void**)&out_dev, ctx->pinned, 0));
+    coarse_res_gs_kernel<<<grid, CT_THREADS, 0, ctx->stream>>>(a, c->track_bar + 1, out_dev);
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
-    EDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_out, sizeof(double) * CT_NPART, cudaMemcpyDeviceToHost, ctx->stream));
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const double* v = (const double*)ctx->pinned;
     coarse_outputs(v, rs, H, b);
