@@ -377,13 +377,16 @@ __global__ void __launch_bounds__(LE_THREADS) ba_lenergy_kernel(int F, int P, in
         partial[blockIdx.x] = s;
     }
 }
-__global__ void ba_sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+// (out / cdelta_out point into pinned host memory: the sum and the calibration delta reach the host without a copy)
+__global__ void ba_sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out, const float* __restrict__ cDeltaF,
+                                       float* __restrict__ cdelta_out) {
     // one warp, fixed order: lane l sums l, l+32, ...; then a butterfly
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (threadIdx.x == 0) *out = s;
+    if (threadIdx.x < 4) cdelta_out[threadIdx.x] = cDeltaF[threadIdx.x];
 }
 
 // ---- TMA bulk-copy + mbarrier helpers -------------------------------------------------------
@@ -1920,16 +1923,15 @@ edsgpu_status edsgpu_ba_calc_l_energy(edsgpu_ba* w, const double* cPrior, const 
     const int n_part = (std::max(w->R, w->P) + LE_THREADS - 1) / LE_THREADS;
     char* pb = (char*)w->post_block;
     double* d_partial = (double*)(pb + align_up(32 * F2, 256) + 256 + align_up(4 * (size_t)w->P, 256));
-    double* d_sum = d_partial + align_up(8 * (size_t)n_part, 256) / 8;
     ba_lenergy_kernel<<<n_part, LE_THREADS, 0, ctx->stream>>>(w->F, w->P, w->R, w->recs, w->host_idx, w->target_idx, w->point_of_res, w->flags,
                                                             w->res_toZero, w->deltaF, w->priorF, w->adHTdeltaF, w->cDeltaF, d_partial);
     ctx->launches++;
-    ba_sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(d_partial, n_part, d_sum);
+    char* pin_dev = nullptr;  // the pinned block as the device sees it
+    EDS_CUDA(ctx, cudaHostGetDevicePointer((void**)&pin_dev, ctx->pinned, 0));
+    ba_sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(d_partial, n_part, (double*)pin_dev, w->cDeltaF, (float*)(pin_dev + 16));
     ctx->launches++;
     EDS_CUDA(ctx, cudaGetLastError());
     float cd[4];
-    EDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, d_sum, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    EDS_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 16, w->cDeltaF, 16, cudaMemcpyDeviceToHost, ctx->stream));
     EDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double E = *(double*)ctx->pinned;
     memcpy(cd, (char*)ctx->pinned + 16, 16);
